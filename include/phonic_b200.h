@@ -1,0 +1,281 @@
+/*
+ * phonic_b200.h -- C-ABI of the B200-native offline renderer for phonic's mixer graph.
+ *
+ * This is the drop-in boundary: plain C types only, no torch/CUDA types.
+ * Every entry point cites the reference (emuell/phonic v0.16.0) interface it stands in for;
+ * paths are relative to the reference's repository root.
+ *
+ * Threading: one render call at a time per renderer (`&mut self` semantics of
+ * `Source::write`, src/source.rs:80-110). Graph-building and scheduling calls must not
+ * overlap a render call (offline use: no real-time constraint).
+ *
+ * Time: every `sample_time` is an absolute output frame position, exactly the `u64`
+ * sample times phonic's handles take (src/player/handles/ *.rs). `PB200_TIME_NOW`
+ * stands for `None` ("apply immediately" = at the next rendered block start).
+ *
+ * Errors: functions return 0 on success or a PB200_ERR_* code which maps 1:1 onto
+ * `phonic::Error` (src/error.rs:8-22); `pb200_last_error` gives the message.
+ * Nothing unwinds across this boundary.
+ */
+#ifndef PHONIC_B200_H
+#define PHONIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PB200_API
+#else
+#define PB200_API __attribute__((visibility("default")))
+#endif
+
+typedef struct pb200_renderer pb200_renderer;
+
+/* ---- error codes: phonic::Error (src/error.rs:8-22) + device errors ---------------------- */
+enum pb200_error {
+  PB200_OK = 0,
+  PB200_ERR_SOURCE_NOT_PLAYING = 1,   /* Error::SourceNotPlaying        */
+  PB200_ERR_MEDIA_FILE_NOT_FOUND = 2, /* Error::MediaFileNotFound       */
+  PB200_ERR_MEDIA_FILE_PROBE = 3,     /* Error::MediaFileProbeError     */
+  PB200_ERR_MEDIA_FILE_SEEK = 4,      /* Error::MediaFileSeekError      */
+  PB200_ERR_AUDIO_DECODING = 5,       /* Error::AudioDecodingError      */
+  PB200_ERR_OUTPUT_DEVICE = 6,        /* Error::OutputDeviceError       */
+  PB200_ERR_RESAMPLING = 7,           /* Error::ResamplingError         */
+  PB200_ERR_GENERATOR_NOT_FOUND = 8,  /* Error::GeneratorNotFoundError  */
+  PB200_ERR_EFFECT_NOT_FOUND = 9,     /* Error::EffectNotFoundError     */
+  PB200_ERR_MIXER_NOT_FOUND = 10,     /* Error::MixerNotFoundError      */
+  PB200_ERR_PARAMETER = 11,           /* Error::ParameterError          */
+  PB200_ERR_SEND = 12,                /* Error::SendError               */
+  PB200_ERR_IO = 13,                  /* Error::IoError                 */
+  PB200_ERR_CUDA = 100,               /* CUDA runtime / no device (maps to OutputDeviceError) */
+  PB200_ERR_UNSUPPORTED = 101         /* feature of the reference not (yet) rendered on device */
+};
+
+#define PB200_TIME_NOW UINT64_MAX /* `None` sample time of the handle methods */
+#define PB200_MAIN_MIXER 0u       /* Player::MAIN_MIXER_ID (src/player.rs) */
+#define PB200_REPEAT_DEFAULT UINT64_MAX - 1 /* FilePlaybackOptions::repeat = None */
+#define PB200_REPEAT_FOREVER UINT64_MAX     /* FilePlaybackOptions::repeat_forever() */
+#define PB200_NO_LOOP (-1)
+/* All durations cross the boundary as std::time::Duration::as_nanos() so that the
+ * reference's own Duration -> f32/f64 conversions (as_secs_f32) are reproduced bit-exactly. */
+#define PB200_DURATION_NONE UINT64_MAX
+
+/* ---- renderer: Player + WavOutput (src/player.rs:289-403, src/output/wav.rs:41-120) ------- */
+typedef struct pb200_config {
+  uint32_t sample_rate;      /* WavOutput::open_with_specs sample rate (wav.rs:50-56) */
+  uint32_t channel_count;    /* must be 2 (PlayerConfig::enforce_stereo_playback, player.rs:134) */
+  uint32_t block_frames;     /* WavStream block: 1024 frames (wav.rs:25); 0 = default */
+  int32_t device_ordinal;    /* CUDA device this renderer instance owns; -1 = current */
+  float master_volume;       /* OutputDevice::set_volume (output.rs:41-47); 1.0 default */
+  uint32_t reserved[3];
+} pb200_config;
+
+/* Player::new(WavOutput::open_with_specs(..)) */
+PB200_API int pb200_create(const pb200_config *config, pb200_renderer **out);
+/* drop(Player) */
+PB200_API void pb200_destroy(pb200_renderer *r);
+/* Display for Error */
+PB200_API const char *pb200_last_error(const pb200_renderer *r);
+/* static description of the build ("cuda sm_100a ..." / oracle) */
+PB200_API const char *pb200_backend(void);
+
+/* ---- sample data: AudioFileBuffer::new (src/source/file/buffer.rs:23-59) -------------------
+ * `interleaved` is copied (to HBM). `add_pad_frame` != 0 appends the one zero frame that
+ * AudioFileBuffer::from_audio_decoder adds for the cubic resampler (buffer.rs:103-104).
+ * loop_start/loop_end in frames or PB200_NO_LOOP (RIFF smpl loops, decoder.rs:293-330). */
+PB200_API int pb200_upload_buffer(pb200_renderer *r, const float *interleaved, uint64_t frames,
+                                  uint32_t channel_count, uint32_t sample_rate,
+                                  int64_t loop_start, int64_t loop_end, int add_pad_frame,
+                                  uint32_t *buffer_id);
+
+/* ---- mixers: Player::add_mixer (src/player.rs:772-836) ------------------------------------ */
+PB200_API int pb200_add_mixer(pb200_renderer *r, uint32_t parent_mixer_id, uint32_t *mixer_id);
+
+/* ---- effects: Player::add_effect (src/player.rs:893-939), Effect (src/effect.rs:86-215) --- */
+enum pb200_effect_kind {
+  PB200_FX_FILTER = 1,     /* FilterEffect     src/effect/filter.rs     */
+  PB200_FX_EQ5 = 2,        /* Eq5Effect        src/effect/eq5.rs        */
+  PB200_FX_COMPRESSOR = 3, /* CompressorEffect src/effect/compressor.rs */
+  PB200_FX_CHORUS = 4,     /* ChorusEffect     src/effect/chorus.rs     */
+  PB200_FX_DELAY = 5,      /* DelayEffect      src/effect/delay.rs      */
+  PB200_FX_REVERB = 6      /* ReverbEffect     src/effect/reverb.rs     */
+};
+
+/* FilterEffect::with_parameters(filter_type, cutoff, q) (filter.rs:104-116) */
+typedef struct pb200_filter_params {
+  uint32_t filter_type; /* FilterEffectType: 0 Lowpass 1 Bandpass 2 Bandstop 3 Highpass */
+  float cutoff;
+  float q;
+} pb200_filter_params;
+
+/* Eq5Effect has only Eq5Effect::new() (eq5.rs:153-170): pass params = NULL and set bands with
+ * PB200_EV_SET_EFFECT_PARAMETER events ('gan1'..'gan5', 'frq1'..'frq5', 'bw_1'..'bw_5'). */
+
+/* CompressorEffect::with_compressor_parameters / new_limiter (compressor.rs:114-157) */
+typedef struct pb200_compressor_params {
+  float threshold, ratio, knee, attack_time, release_time, makeup_gain, lookahead_time;
+} pb200_compressor_params;
+
+/* ChorusEffect::with_parameters (chorus.rs:178-200) */
+typedef struct pb200_chorus_params {
+  float rate, phase, depth, feedback, delay, wet;
+  uint32_t filter_type; /* ChorusEffectFilterType: 0 Lowpass 1 Highpass 2 Bandpass */
+  float filter_freq, filter_resonance;
+} pb200_chorus_params;
+
+/* DelayEffect has only DelayEffect::new() (delay.rs:180-212): pass params = NULL and use
+ * PB200_EV_SET_EFFECT_PARAMETER events ('mode','dlay','fdbk','ftyp','cuto','driv','wet_','wdth',
+ * 'lfor','lfos','lfdt','ldfb','lfdf'). The OS-seeded Random/SmoothRandom LFO shapes are rejected
+ * with PB200_ERR_UNSUPPORTED (not reproducible in the reference itself). */
+
+/* ReverbEffect::with_parameters(room_size, wet) (reverb.rs:153-159). The reference seeds
+ * `fpd_l/fpd_r` and the 16 vibrato phases from rand::rng() (reverb.rs:95-103,137-144);
+ * parity needs them injected, so they are explicit inputs here. */
+typedef struct pb200_reverb_params {
+  float room_size, wet;
+  uint32_t fpd[2];
+  double vib_phase[16]; /* [line 0..7][L,R] start phases in [0, 2pi) */
+} pb200_reverb_params;
+
+/* `params` may be NULL => Effect::new()/default(). */
+PB200_API int pb200_add_effect(pb200_renderer *r, uint32_t mixer_id, uint32_t kind,
+                               const void *params, size_t params_size, uint32_t *effect_id);
+
+/* ---- file playback: Player::play_file_source (src/player.rs:511-600) ---------------------- */
+typedef struct pb200_file_options { /* FilePlaybackOptions (src/source/file.rs:34-84) */
+  float volume;               /* 1.0 */
+  float panning;              /* 0.0 */
+  double speed;               /* 1.0 */
+  uint64_t repeat;            /* PB200_REPEAT_DEFAULT | count | PB200_REPEAT_FOREVER */
+  int64_t loop_start;         /* loop_range override or PB200_NO_LOOP */
+  int64_t loop_end;
+  uint64_t fade_in_nanos;     /* Duration::as_nanos(); PB200_DURATION_NONE => None */
+  uint64_t fade_out_nanos;    /* default 50 ms (file.rs:106) */
+  uint32_t resampling_quality;/* 0 Default (cubic) 1 HighQuality (sinc) */
+  uint32_t target_mixer;      /* PB200_MAIN_MIXER */
+} pb200_file_options;
+
+PB200_API void pb200_file_options_default(pb200_file_options *o);
+PB200_API int pb200_play_file(pb200_renderer *r, uint32_t buffer_id, const pb200_file_options *o,
+                              uint64_t start_time, uint32_t *playback_id);
+
+/* ---- sampler: Sampler::from_file_source + with_ahdsr (src/generator/sampler.rs:487-596),
+ *      Player::play_generator / add_generator (src/player.rs:700-770) ------------------------ */
+typedef struct pb200_ahdsr { /* AhdsrParameters::new_with_scaling (src/utils/ahdsr.rs:75-98) */
+  uint64_t attack_nanos; /* std::time::Duration::as_nanos() of each stage time */
+  uint64_t hold_nanos;
+  uint64_t decay_nanos;
+  uint64_t release_nanos;
+  float attack_scaling, decay_scaling, release_scaling;
+  float sustain_level;
+} pb200_ahdsr;
+
+typedef struct pb200_sampler_options { /* GeneratorPlaybackOptions (src/generator.rs:41-72) */
+  float volume;          /* 1.0 */
+  float panning;         /* 0.0 */
+  uint32_t voices;       /* 8 */
+  uint32_t target_mixer; /* PB200_MAIN_MIXER */
+  uint32_t transient;    /* 1: play_generator, 0: add_generator */
+  uint32_t has_ahdsr;    /* with_ahdsr(..) */
+  pb200_ahdsr ahdsr;
+} pb200_sampler_options;
+
+PB200_API void pb200_sampler_options_default(pb200_sampler_options *o);
+PB200_API int pb200_add_sampler(pb200_renderer *r, uint32_t buffer_id,
+                                const pb200_sampler_options *o, uint64_t start_time,
+                                uint32_t *generator_id);
+
+/* ---- events: handle methods (src/player/handles/{file,generator,effect}.rs) ---------------- */
+enum pb200_event_kind {
+  /* FilePlaybackHandle / GeneratorPlaybackHandle: target = playback id */
+  PB200_EV_STOP_SOURCE = 1,      /* stop(stop_time)                 handles/file.rs:69-98     */
+  PB200_EV_SET_SOURCE_VOLUME = 2,/* set_volume(volume, t)           handles/file.rs:188-222   */
+  PB200_EV_SET_SOURCE_PANNING = 3,/* set_panning(panning, t)        handles/file.rs:223-257   */
+  PB200_EV_SET_SOURCE_SPEED = 4, /* set_speed(speed, glide, t)      handles/file.rs:135-187   */
+  PB200_EV_SEEK_SOURCE = 5,      /* seek(position, t)               handles/file.rs:99-134    */
+  /* GeneratorPlaybackHandle: target = generator id */
+  PB200_EV_NOTE_ON = 10,         /* note_on(note, volume, panning, t) handles/generator.rs:200-238 */
+  PB200_EV_NOTE_OFF = 11,        /* note_off(note_id, t)            */
+  PB200_EV_ALL_NOTES_OFF = 12,   /* all_notes_off(t)                */
+  PB200_EV_SET_NOTE_SPEED = 13,  /* set_note_speed(note_id, speed, glide, t) */
+  PB200_EV_SET_NOTE_VOLUME = 14, /* set_note_volume(note_id, volume, t) */
+  PB200_EV_SET_NOTE_PANNING = 15,/* set_note_panning(note_id, panning, t) */
+  /* EffectHandle: target = effect id */
+  PB200_EV_SET_EFFECT_PARAMETER = 20 /* set_parameter((id, value), t) handles/effect.rs:67-98 */
+};
+
+typedef struct pb200_event {
+  uint64_t sample_time; /* absolute output frame, or PB200_TIME_NOW */
+  uint32_t kind;        /* pb200_event_kind */
+  uint32_t target;      /* playback / generator / effect id */
+  uint64_t note_id;     /* NotePlaybackId for note events; out for NOTE_ON via pb200_schedule */
+  uint32_t note;        /* MIDI note (NOTE_ON) */
+  uint32_t param_id;    /* FourCC as big-endian u32, e.g. 'cuto' (SET_EFFECT_PARAMETER) */
+  float value;          /* volume / panning / parameter value */
+  float value2;         /* NOTE_ON: panning */
+  float glide;          /* semitones per second; <= 0 => None */
+  uint32_t flags;       /* PB200_EVF_* */
+  double speed;         /* SET_*_SPEED */
+  uint64_t position_nanos; /* SEEK position: Duration::as_nanos() */
+} pb200_event;
+
+#define PB200_EVF_NORMALIZED 1u /* ParameterValueUpdate::Normalized instead of ::Raw */
+#define PB200_EVF_HAS_VOLUME 2u /* NOTE_ON: volume is Some(value) */
+#define PB200_EVF_HAS_PANNING 4u/* NOTE_ON: panning is Some(value2) */
+
+/* Queue one event. For PB200_EV_NOTE_ON a fresh NotePlaybackId is allocated
+ * (unique_note_id, src/generator.rs:30-33) and written back to `ev->note_id`. */
+PB200_API int pb200_schedule(pb200_renderer *r, pb200_event *ev);
+
+/* ---- render: repeated WavStream::process (src/output/wav.rs:210-250) -----------------------
+ * Renders `frames` output frames (interleaved f32, channel_count channels) as the reference
+ * would in consecutive block_frames-sized `Source::write` calls on the main mixer, including
+ * the master-volume smoothing of wav.rs:237. `out` is HOST memory. */
+PB200_API int pb200_render(pb200_renderer *r, float *out_interleaved, uint64_t frames,
+                           uint64_t *frames_written);
+/* Same, but `out` is DEVICE memory of the renderer's device (no host copy). CUDA build only. */
+PB200_API int pb200_render_device(pb200_renderer *r, float *out_device, uint64_t frames,
+                                  uint64_t *frames_written);
+/* Player::output_sample_frame_position (src/player.rs) */
+PB200_API uint64_t pb200_position(const pb200_renderer *r);
+
+/* ---- status: PlaybackStatusEvent::Stopped mirror (src/source/status.rs:15-36) --------------- */
+typedef struct pb200_source_status {
+  uint32_t is_playing;    /* FilePlaybackHandle::is_playing */
+  uint32_t exhausted;     /* Stopped{exhausted} */
+  uint64_t end_frame;     /* output frame at which the source finished (chunk end), or UINT64_MAX */
+  uint64_t playback_pos;  /* PreloadedFileSource::playback_pos (sample index), files only */
+} pb200_source_status;
+PB200_API int pb200_source_status_get(pb200_renderer *r, uint32_t playback_id,
+                                      pb200_source_status *st);
+
+/* Voice-level introspection used by the parity tests: bit-exact integer state of every sampler
+ * voice after the last render call (note id or UINT64_MAX, playback_pos sample index). */
+typedef struct pb200_voice_state {
+  uint64_t note_id;
+  uint64_t playback_pos;
+  uint32_t envelope_stage; /* AhdsrStage as 0 Idle 1 Attack 2 Hold 3 Decay 4 Sustain 5 Release */
+  uint32_t active;
+} pb200_voice_state;
+PB200_API int pb200_sampler_voice_states(pb200_renderer *r, uint32_t generator_id,
+                                         pb200_voice_state *out, uint32_t capacity,
+                                         uint32_t *count);
+
+/* ---- timing of the last render call (device side, CUDA events) ------------------------------ */
+typedef struct pb200_render_stats {
+  double device_ms;        /* all kernels of the last pb200_render* call */
+  double voice_kernel_ms;  /* the voice (resample+gain/pan/envelope+sum) kernels */
+  double effect_kernel_ms; /* mixer/effect kernels */
+  uint64_t kernel_launches;
+  uint64_t voice_frames;   /* active voice-frames rendered */
+} pb200_render_stats;
+PB200_API int pb200_last_render_stats(pb200_renderer *r, pb200_render_stats *st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHONIC_B200_H */

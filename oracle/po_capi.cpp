@@ -1,0 +1,421 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see po_dsp.hpp header).
+//
+// Exposes the CPU restatement through the SAME C signatures as include/phonic_b200.h, with the
+// `pb200_` prefix replaced by `po_`, so that tests drive the oracle and the CUDA product with one
+// scene description. Mirrors Player (src/player.rs:289-1046) + WavStream (src/output/wav.rs:196-250).
+#define pb200_create po_create
+#define pb200_destroy po_destroy
+#define pb200_last_error po_last_error
+#define pb200_backend po_backend
+#define pb200_upload_buffer po_upload_buffer
+#define pb200_add_mixer po_add_mixer
+#define pb200_add_effect po_add_effect
+#define pb200_file_options_default po_file_options_default
+#define pb200_play_file po_play_file
+#define pb200_sampler_options_default po_sampler_options_default
+#define pb200_add_sampler po_add_sampler
+#define pb200_schedule po_schedule
+#define pb200_render po_render
+#define pb200_render_device po_render_device
+#define pb200_position po_position
+#define pb200_source_status_get po_source_status_get
+#define pb200_sampler_voice_states po_sampler_voice_states
+#define pb200_last_render_stats po_last_render_stats
+#include "../include/phonic_b200.h"
+
+#include <chrono>
+#include <map>
+#include <string>
+
+#include "po_effects.hpp"
+
+using namespace po;
+
+struct pb200_renderer {
+  pb200_config cfg;
+  std::string last_error;
+  std::unique_ptr<MixedSource> main;
+  std::map<uint32_t, MixedSource*> mixers;  // id -> mixer (0 = main)
+  std::vector<std::shared_ptr<AudioFileBuffer>> buffers;
+  struct SourceRef { uint32_t mixer; PlaybackQueues queues; PreloadedFileSource* file = nullptr; Sampler* sampler = nullptr; bool transient = true; };
+  std::map<uint32_t, SourceRef> sources;
+  struct EffectRef { uint32_t mixer; };
+  std::map<uint32_t, EffectRef> effects;
+  uint32_t next_source_id = 1, next_mixer_id = 1, next_effect_id = 1;
+  uint64_t next_note_id = 1;
+  // WavStream
+  ExpSmoothed smoothed_volume;
+  uint64_t playback_pos = 0;  // samples
+  bool finished = false;
+  std::vector<float> block;
+  double last_ms = 0;
+  uint64_t last_voice_frames = 0;
+};
+
+static int fail(pb200_renderer* r, int code, const std::string& msg) {
+  if (r) r->last_error = msg;
+  return code;
+}
+
+extern "C" {
+
+const char* pb200_backend(void) { return "oracle: scalar C++ restatement of emuell/phonic v0.16.0 (CPU)"; }
+
+int pb200_create(const pb200_config* config, pb200_renderer** out) {
+  if (!config || !out) return PB200_ERR_PARAMETER;
+  if (config->channel_count != 2 || config->sample_rate == 0) return PB200_ERR_PARAMETER;
+  auto* r = new pb200_renderer();
+  r->cfg = *config;
+  if (r->cfg.block_frames == 0) r->cfg.block_frames = 1024;
+  r->main = std::make_unique<MixedSource>(config->channel_count, config->sample_rate);
+  r->mixers[0] = r->main.get();
+  // WavStream: smoothed_volume = ExponentialSmoothedValue::new(1.0, sr) then set_volume (wav.rs)
+  r->smoothed_volume = ExpSmoothed(1.0f, config->sample_rate);
+  r->smoothed_volume.init(config->master_volume);
+  r->block.resize((size_t)r->cfg.block_frames * config->channel_count);
+  *out = r;
+  return PB200_OK;
+}
+
+void pb200_destroy(pb200_renderer* r) { delete r; }
+const char* pb200_last_error(const pb200_renderer* r) { return r ? r->last_error.c_str() : ""; }
+
+int pb200_upload_buffer(pb200_renderer* r, const float* data, uint64_t frames, uint32_t ch, uint32_t rate,
+                        int64_t loop_start, int64_t loop_end, int add_pad_frame, uint32_t* buffer_id) {
+  if (!r || !data || !buffer_id) return PB200_ERR_PARAMETER;
+  if (rate == 0) return fail(r, PB200_ERR_PARAMETER, "file buffer sample rate must be > 0");
+  if (ch == 0) return fail(r, PB200_ERR_PARAMETER, "file buffer channel count must be > 0");
+  if (frames == 0) return fail(r, PB200_ERR_PARAMETER, "file buffer must not be empty");
+  if (ch > 2) return fail(r, PB200_ERR_UNSUPPORTED, "only mono and stereo buffers are supported");
+  auto fb = std::make_shared<AudioFileBuffer>();
+  fb->buffer.assign(data, data + frames * ch);
+  if (add_pad_frame) fb->buffer.insert(fb->buffer.end(), ch, 0.0f);
+  fb->sample_rate = rate;
+  fb->channel_count = ch;
+  if (loop_start >= 0 && loop_end >= 0) {
+    size_t fc = fb->frame_count();
+    if (loop_start >= loop_end || (size_t)loop_end > fc) return fail(r, PB200_ERR_PARAMETER, "file buffer loop range is out of bounds");
+    fb->has_loop = true; fb->loop_start = (size_t)loop_start; fb->loop_end = (size_t)loop_end;
+  }
+  r->buffers.push_back(fb);
+  *buffer_id = (uint32_t)r->buffers.size() - 1;
+  return PB200_OK;
+}
+
+int pb200_add_mixer(pb200_renderer* r, uint32_t parent, uint32_t* mixer_id) {
+  if (!r || !mixer_id) return PB200_ERR_PARAMETER;
+  auto it = r->mixers.find(parent);
+  if (it == r->mixers.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  auto proc = std::make_shared<SubMixerProcessor>();
+  proc->mixer = std::make_unique<MixedSource>(r->cfg.channel_count, r->cfg.sample_rate);
+  uint32_t id = r->next_mixer_id++;
+  r->mixers[id] = proc->mixer.get();
+  MixedSource::Message m; m.kind = MixedSource::Message::AddMixer; m.id = id; m.mixer = proc;
+  it->second->message_queue.push_back(std::move(m));
+  *mixer_id = id;
+  return PB200_OK;
+}
+
+int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const void* params, size_t size, uint32_t* effect_id) {
+  if (!r || !effect_id) return PB200_ERR_PARAMETER;
+  auto it = r->mixers.find(mixer);
+  if (it == r->mixers.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  std::unique_ptr<Effect> fx;
+  switch (kind) {
+    case PB200_FX_FILTER:
+      if (params) {
+        if (size != sizeof(pb200_filter_params)) return fail(r, PB200_ERR_PARAMETER, "bad filter params size");
+        auto* p = (const pb200_filter_params*)params;
+        if (p->filter_type > 3 || !(p->cutoff >= 20.0f && p->cutoff <= 20000.0f) || !(p->q >= 0.001f && p->q <= 4.0f))
+          return fail(r, PB200_ERR_PARAMETER, "Value out of bounds");
+        fx = std::make_unique<FilterEffect>(p->filter_type, p->cutoff, p->q);
+      } else fx = std::make_unique<FilterEffect>();
+      break;
+    case PB200_FX_EQ5:
+      if (params) return fail(r, PB200_ERR_PARAMETER, "Eq5Effect has no parameter constructor");
+      fx = std::make_unique<Eq5Effect>();
+      break;
+    case PB200_FX_COMPRESSOR:
+      if (params) {
+        if (size != sizeof(pb200_compressor_params)) return fail(r, PB200_ERR_PARAMETER, "bad compressor params size");
+        auto* p = (const pb200_compressor_params*)params;
+        fx = std::make_unique<CompressorEffect>(p->threshold, p->ratio, p->knee, p->attack_time, p->release_time, p->makeup_gain, p->lookahead_time);
+      } else fx = std::make_unique<CompressorEffect>();
+      break;
+    case PB200_FX_CHORUS:
+      if (params) {
+        if (size != sizeof(pb200_chorus_params)) return fail(r, PB200_ERR_PARAMETER, "bad chorus params size");
+        auto* p = (const pb200_chorus_params*)params;
+        if (p->filter_type > 2) return fail(r, PB200_ERR_PARAMETER, "bad chorus filter type");
+        fx = std::make_unique<ChorusEffect>(p->rate, p->phase, p->depth, p->feedback, p->delay, p->wet, p->filter_type, p->filter_freq, p->filter_resonance);
+      } else fx = std::make_unique<ChorusEffect>();
+      break;
+    case PB200_FX_DELAY:
+      if (params) return fail(r, PB200_ERR_PARAMETER, "DelayEffect has no parameter constructor");
+      fx = std::make_unique<DelayEffect>();
+      break;
+    case PB200_FX_REVERB: {
+      if (!params || size != sizeof(pb200_reverb_params)) return fail(r, PB200_ERR_PARAMETER, "reverb needs explicit fpd/vib_phase state");
+      auto* p = (const pb200_reverb_params*)params;
+      fx = std::make_unique<ReverbEffect>(p->room_size, p->wet, p->fpd, p->vib_phase);
+      break;
+    }
+    default: return fail(r, PB200_ERR_PARAMETER, "unknown effect kind");
+  }
+  // Player::add_effect: effect.initialize(sr, ch, MAX_MIX_BUFFER_SAMPLES / ch) (player.rs:905-909)
+  if (!fx->initialize(r->cfg.sample_rate, r->cfg.channel_count, MixedSource::MAX_MIX_BUFFER_SAMPLES / r->cfg.channel_count))
+    return fail(r, PB200_ERR_PARAMETER, "effect initialize failed");
+  uint32_t id = r->next_effect_id++;
+  MixedSource::Message m; m.kind = MixedSource::Message::AddEffect; m.id = id;
+  m.effect = std::make_shared<EffectProcessor>(std::move(fx));
+  it->second->message_queue.push_back(std::move(m));
+  r->effects[id] = {mixer};
+  *effect_id = id;
+  return PB200_OK;
+}
+
+void pb200_file_options_default(pb200_file_options* o) {
+  if (!o) return;
+  o->volume = 1.0f; o->panning = 0.0f; o->speed = 1.0; o->repeat = PB200_REPEAT_DEFAULT;
+  o->loop_start = PB200_NO_LOOP; o->loop_end = PB200_NO_LOOP;
+  o->fade_in_nanos = PB200_DURATION_NONE; o->fade_out_nanos = 50000000ull;
+  o->resampling_quality = 0; o->target_mixer = PB200_MAIN_MIXER;
+}
+
+static int validate_vol_pan(pb200_renderer* r, float volume, float panning) {
+  if (volume < 0.0f || std::isnan(volume)) return fail(r, PB200_ERR_PARAMETER, "playback options 'volume' value is invalid");
+  if (!(panning >= -1.0f && panning <= 1.0f)) return fail(r, PB200_ERR_PARAMETER, "playback options 'panning' value is invalid");
+  return PB200_OK;
+}
+
+int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_options* o, uint64_t start_time, uint32_t* playback_id) {
+  if (!r || !o || !playback_id) return PB200_ERR_PARAMETER;
+  if (buffer_id >= r->buffers.size()) return fail(r, PB200_ERR_PARAMETER, "unknown buffer");
+  if (int e = validate_vol_pan(r, o->volume, o->panning)) return e;
+  if (o->speed < 0.0 || std::isnan(o->speed) || std::isinf(o->speed)) return fail(r, PB200_ERR_PARAMETER, "playback options 'speed' value is invalid");
+  if (o->resampling_quality != 0) return fail(r, PB200_ERR_UNSUPPORTED, "HighQuality (sinc) resampling is not restated yet");
+  auto mit = r->mixers.find(o->target_mixer);
+  if (mit == r->mixers.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  FilePlaybackOptions fo;
+  fo.volume = o->volume; fo.panning = o->panning; fo.speed = o->speed;
+  if (o->repeat != PB200_REPEAT_DEFAULT) { fo.has_repeat = true; fo.repeat = o->repeat == PB200_REPEAT_FOREVER ? USIZE_MAX : (size_t)o->repeat; }
+  if (o->loop_start >= 0 && o->loop_end >= 0) { fo.has_loop_range = true; fo.loop_start = (uint64_t)o->loop_start; fo.loop_end = (uint64_t)o->loop_end; }
+  fo.has_fade_in = o->fade_in_nanos != PB200_DURATION_NONE; if (fo.has_fade_in) fo.fade_in = Duration::from_nanos(o->fade_in_nanos);
+  fo.has_fade_out = o->fade_out_nanos != PB200_DURATION_NONE; if (fo.has_fade_out) fo.fade_out = Duration::from_nanos(o->fade_out_nanos);
+  auto fs = std::make_unique<PreloadedFileSource>(r->buffers[buffer_id], fo, r->cfg.sample_rate);
+  pb200_renderer::SourceRef ref;
+  ref.mixer = o->target_mixer;
+  ref.file = fs.get();
+  ref.queues.file = fs->queue;
+  // ConvertedSource (converted.rs:15-46): file already runs at the output rate -> channel mapping only
+  std::unique_ptr<Source> src = std::move(fs);
+  if (src->channel_count() != r->cfg.channel_count) src = std::make_unique<ChannelMappedSource>(std::move(src), r->cfg.channel_count);
+  auto amp = std::make_unique<AmplifiedSource>(std::move(src), o->volume);
+  ref.queues.volume = amp->queue;
+  auto pan = std::make_unique<PannedSource>(std::move(amp), o->panning);
+  ref.queues.panning = pan->queue;
+  uint32_t id = r->next_source_id++;
+  auto ps = std::make_shared<MixedSource::PlayingSource>();
+  ps->is_transient = true; ps->playback_id = id; ps->queues = ref.queues; ps->source = std::move(pan);
+  ps->start_time = start_time == PB200_TIME_NOW ? 0 : start_time;
+  MixedSource::Message m; m.kind = MixedSource::Message::AddSource; m.source = ps; m.sample_time = ps->start_time;
+  mit->second->message_queue.push_back(std::move(m));
+  r->sources[id] = ref;
+  *playback_id = id;
+  return PB200_OK;
+}
+
+void pb200_sampler_options_default(pb200_sampler_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->volume = 1.0f; o->panning = 0.0f; o->voices = 8; o->target_mixer = PB200_MAIN_MIXER; o->transient = 0; o->has_ahdsr = 0;
+  // AhdsrParameters::default() (ahdsr.rs:348-359)
+  o->ahdsr.attack_nanos = 10000000ull; o->ahdsr.hold_nanos = 1000000000ull; o->ahdsr.decay_nanos = 500000000ull;
+  o->ahdsr.release_nanos = 1000000000ull; o->ahdsr.sustain_level = 0.75f;
+}
+
+int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler_options* o, uint64_t start_time, uint32_t* generator_id) {
+  if (!r || !o || !generator_id) return PB200_ERR_PARAMETER;
+  if (buffer_id >= r->buffers.size()) return fail(r, PB200_ERR_PARAMETER, "unknown buffer");
+  if (int e = validate_vol_pan(r, o->volume, o->panning)) return e;
+  if (o->voices == 0) return fail(r, PB200_ERR_PARAMETER, "playback options voice count is '0'");
+  auto mit = r->mixers.find(o->target_mixer);
+  if (mit == r->mixers.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  auto sampler = std::make_unique<Sampler>(r->buffers[buffer_id], o->voices, r->cfg.channel_count, r->cfg.sample_rate);
+  if (o->has_ahdsr) {
+    AhdsrParameters p;
+    const auto& a = o->ahdsr;
+    if (!AhdsrParameters::create(p, Duration::from_nanos(a.attack_nanos), a.attack_scaling, Duration::from_nanos(a.hold_nanos),
+                                 Duration::from_nanos(a.decay_nanos), a.decay_scaling, a.sustain_level,
+                                 Duration::from_nanos(a.release_nanos), a.release_scaling))
+      return fail(r, PB200_ERR_PARAMETER, "Invalid AHDSR parameters");
+    if (!sampler->with_ahdsr(p)) return fail(r, PB200_ERR_PARAMETER, "Failed to initialize AHDSR parameters");
+  }
+  sampler->transient = o->transient != 0;  // set_is_transient (player.rs:1062)
+  pb200_renderer::SourceRef ref;
+  ref.mixer = o->target_mixer; ref.sampler = sampler.get(); ref.transient = o->transient != 0;
+  ref.queues.generator = sampler->queue;
+  auto amp = std::make_unique<AmplifiedSource>(std::move(sampler), o->volume);
+  ref.queues.volume = amp->queue;
+  auto pan = std::make_unique<PannedSource>(std::move(amp), o->panning);
+  ref.queues.panning = pan->queue;
+  uint32_t id = r->next_source_id++;
+  auto ps = std::make_shared<MixedSource::PlayingSource>();
+  ps->is_transient = o->transient != 0; ps->playback_id = id; ps->queues = ref.queues; ps->source = std::move(pan);
+  ps->start_time = start_time == PB200_TIME_NOW ? 0 : start_time;
+  MixedSource::Message m; m.kind = MixedSource::Message::AddSource; m.source = ps; m.sample_time = ps->start_time;
+  mit->second->message_queue.push_back(std::move(m));
+  r->sources[id] = ref;
+  *generator_id = id;
+  return PB200_OK;
+}
+
+int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
+  if (!r || !ev) return PB200_ERR_PARAMETER;
+  const bool now = ev->sample_time == PB200_TIME_NOW;
+  if (ev->kind == PB200_EV_SET_EFFECT_PARAMETER) {
+    auto it = r->effects.find(ev->target);
+    if (it == r->effects.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+    MixedSource::Message m; m.kind = MixedSource::Message::Event;
+    m.event.kind = MixerEvent::EffectParameter; m.event.target = ev->target;
+    m.event.sample_time = now ? 0 : ev->sample_time;  // handles/effect.rs:80: None => 0
+    m.event.param_id = ev->param_id;
+    m.event.param = {ev->value, (ev->flags & PB200_EVF_NORMALIZED) != 0};
+    r->mixers[it->second.mixer]->message_queue.push_back(std::move(m));
+    return PB200_OK;
+  }
+  auto sit = r->sources.find(ev->target);
+  if (sit == r->sources.end()) return fail(r, PB200_ERR_SOURCE_NOT_PLAYING, "Source is no longer playing");
+  auto& ref = sit->second;
+  MixedSource* mixer = r->mixers[ref.mixer];
+  auto push_event = [&](MixerEvent e) {
+    e.target = ev->target; e.sample_time = ev->sample_time;
+    MixedSource::Message m; m.kind = MixedSource::Message::Event; m.event = e;
+    mixer->message_queue.push_back(std::move(m));
+  };
+  const bool has_glide = ev->glide > 0.0f;
+  switch (ev->kind) {
+    case PB200_EV_STOP_SOURCE:
+      if (now) {
+        if (ref.queues.file) { FileMsg m{FileMsg::Stop}; ref.queues.file->force_push(m); }
+        else { GenMsg m; m.is_stop = true; ref.queues.generator->force_push(m); }
+      } else {
+        MixedSource::Message m; m.kind = MixedSource::Message::StopSource; m.id = ev->target; m.sample_time = ev->sample_time;
+        mixer->message_queue.push_back(std::move(m));
+      }
+      return PB200_OK;
+    case PB200_EV_SET_SOURCE_VOLUME:
+      if (now) ref.queues.volume->force_push(ev->value);
+      else { MixerEvent e; e.kind = MixerEvent::SetSourceVolume; e.value = ev->value; push_event(e); }
+      return PB200_OK;
+    case PB200_EV_SET_SOURCE_PANNING:
+      if (now) ref.queues.panning->force_push(ev->value);
+      else { MixerEvent e; e.kind = MixerEvent::SetSourcePanning; e.value = ev->value; push_event(e); }
+      return PB200_OK;
+    case PB200_EV_SET_SOURCE_SPEED:
+      if (!ref.queues.file) return fail(r, PB200_ERR_PARAMETER, "set_speed needs a file source");
+      if (now) { FileMsg m{FileMsg::SetSpeed}; m.speed = ev->speed; m.has_glide = has_glide; m.glide = ev->glide; if (!ref.queues.file->push(m)) return fail(r, PB200_ERR_SEND, "File playback queue is full"); }
+      else { MixerEvent e; e.kind = MixerEvent::SetSourceSpeed; e.speed = ev->speed; e.has_glide = has_glide; e.glide = ev->glide; push_event(e); }
+      return PB200_OK;
+    case PB200_EV_SEEK_SOURCE:
+      if (!ref.queues.file) return fail(r, PB200_ERR_PARAMETER, "seek needs a file source");
+      if (now) { FileMsg m{FileMsg::Seek}; m.position = Duration::from_nanos(ev->position_nanos); if (!ref.queues.file->push(m)) return fail(r, PB200_ERR_SEND, "File playback queue is full"); }
+      else { MixerEvent e; e.kind = MixerEvent::SeekSource; e.position = Duration::from_nanos(ev->position_nanos); push_event(e); }
+      return PB200_OK;
+    default: break;
+  }
+  if (!ref.queues.generator) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+  GenEvent g;
+  switch (ev->kind) {
+    case PB200_EV_NOTE_ON:
+      g.kind = GenEvent::NoteOn; ev->note_id = r->next_note_id++; g.note_id = ev->note_id; g.note = (uint8_t)ev->note;
+      g.has_volume = (ev->flags & PB200_EVF_HAS_VOLUME) != 0; g.volume = ev->value;
+      g.has_panning = (ev->flags & PB200_EVF_HAS_PANNING) != 0; g.panning = ev->value2;
+      break;
+    case PB200_EV_NOTE_OFF: g.kind = GenEvent::NoteOff; g.note_id = ev->note_id; break;
+    case PB200_EV_ALL_NOTES_OFF: g.kind = GenEvent::AllNotesOff; break;
+    case PB200_EV_SET_NOTE_SPEED: g.kind = GenEvent::SetSpeed; g.note_id = ev->note_id; g.speed = ev->speed; g.has_glide = has_glide; g.glide = ev->glide; break;
+    case PB200_EV_SET_NOTE_VOLUME: g.kind = GenEvent::SetVolume; g.note_id = ev->note_id; g.volume = ev->value; break;
+    case PB200_EV_SET_NOTE_PANNING: g.kind = GenEvent::SetPanning; g.note_id = ev->note_id; g.panning = ev->value; break;
+    default: return fail(r, PB200_ERR_PARAMETER, "unknown event kind");
+  }
+  if (now) {
+    GenMsg m; m.event = g;
+    if (!ref.queues.generator->push(m)) return fail(r, PB200_ERR_SEND, "Generator playback queue is full");
+  } else {
+    MixerEvent e; e.kind = MixerEvent::TriggerGenerator; e.gen = g; push_event(e);
+  }
+  return PB200_OK;
+}
+
+int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frames_written) {
+  if (!r || !out) return PB200_ERR_PARAMETER;
+  const uint32_t bf = r->cfg.block_frames, ch = r->cfg.channel_count;
+  if (frames % bf != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
+  auto t0 = std::chrono::steady_clock::now();
+  uint64_t done = 0;
+  while (done < frames && !r->finished) {  // WavStream::process, wav.rs:210-250
+    SourceTime time{r->playback_pos / ch};
+    size_t written = r->main->write(r->block.data(), r->block.size(), time);
+    if (written == 0) { r->finished = true; break; }
+    apply_smoothed_gain(r->block.data(), written, r->smoothed_volume);
+    std::memcpy(out + done * ch, r->block.data(), written * sizeof(float));
+    r->playback_pos += r->block.size();
+    done += bf;
+  }
+  if (done < frames) std::memset(out + done * ch, 0, (frames - done) * ch * sizeof(float));
+  if (frames_written) *frames_written = done;
+  r->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return PB200_OK;
+}
+
+int pb200_render_device(pb200_renderer* r, float*, uint64_t, uint64_t*) { return fail(r, PB200_ERR_UNSUPPORTED, "oracle has no device memory"); }
+
+uint64_t pb200_position(const pb200_renderer* r) { return r ? r->playback_pos / r->cfg.channel_count : 0; }
+
+int pb200_source_status_get(pb200_renderer* r, uint32_t id, pb200_source_status* st) {
+  if (!r || !st) return PB200_ERR_PARAMETER;
+  auto it = r->sources.find(id);
+  if (it == r->sources.end()) return fail(r, PB200_ERR_SOURCE_NOT_PLAYING, "Source is no longer playing");
+  std::memset(st, 0, sizeof(*st));
+  st->end_frame = UINT64_MAX;
+  // NB: the oracle keeps raw pointers into the graph; finished transient sources are dropped from
+  // the mixer, so status is tracked lazily while they are alive only.
+  MixedSource* mixer = r->mixers[it->second.mixer];
+  bool alive = mixer->find_source(id) != nullptr;
+  bool queued = false;
+  for (auto& m : mixer->message_queue) if (m.kind == MixedSource::Message::AddSource && m.source && m.source->playback_id == id) queued = true;
+  st->is_playing = (alive || queued) ? 1 : 0;
+  if ((alive || queued) && it->second.file) {
+    st->playback_pos = it->second.file->playback_pos;
+    st->exhausted = it->second.file->stopped_exhausted;
+    st->end_frame = it->second.file->end_frame;
+  }
+  return PB200_OK;
+}
+
+int pb200_sampler_voice_states(pb200_renderer* r, uint32_t id, pb200_voice_state* out, uint32_t capacity, uint32_t* count) {
+  if (!r || !out || !count) return PB200_ERR_PARAMETER;
+  auto it = r->sources.find(id);
+  if (it == r->sources.end() || !it->second.sampler) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+  Sampler* s = it->second.sampler;
+  uint32_t n = (uint32_t)std::min<size_t>(capacity, s->voices.size());
+  for (uint32_t i = 0; i < n; ++i) {
+    const auto& v = s->voices[i];
+    out[i].note_id = v.has_note ? v.note_id : UINT64_MAX;
+    out[i].playback_pos = v.file->playback_pos;
+    out[i].envelope_stage = (uint32_t)v.envelope.stage;
+    out[i].active = v.has_note ? 1 : 0;
+  }
+  *count = (uint32_t)s->voices.size();
+  return PB200_OK;
+}
+
+int pb200_last_render_stats(pb200_renderer* r, pb200_render_stats* st) {
+  if (!r || !st) return PB200_ERR_PARAMETER;
+  std::memset(st, 0, sizeof(*st));
+  st->device_ms = r->last_ms;
+  return PB200_OK;
+}
+
+}  // extern "C"

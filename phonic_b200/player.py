@@ -1,0 +1,389 @@
+"""Host-side mirror of phonic's `Player` + handle API for the offline (WAV-output) path.
+
+Same names, argument meaning and error behaviour as the reference (src/player.rs:274-1046,
+src/player/handles/*.rs); every call forwards to the C-ABI of include/phonic_b200.h. Durations
+are `float` seconds here and cross the boundary as integer nanoseconds (std::time::Duration).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi as A
+
+
+class PhonicError(RuntimeError):
+    """phonic::Error (src/error.rs:8-22) carried across the C-ABI as a code + message."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+
+def _nanos(seconds: Optional[float]) -> int:
+    """Duration::from_secs_f64-like conversion to Duration::as_nanos()."""
+    if seconds is None:
+        return A.DURATION_NONE
+    return int(round(float(seconds) * 1e9))
+
+
+@dataclass
+class FilePlaybackOptions:
+    """FilePlaybackOptions (src/source/file.rs:34-218)."""
+    volume: float = 1.0
+    panning: float = 0.0
+    speed: float = 1.0
+    repeat: Optional[int] = None          # None | count | "forever" via repeat_forever()
+    loop_range: Optional[tuple] = None
+    fade_in: Optional[float] = None
+    fade_out: Optional[float] = 0.05
+    resampling_quality: int = 0           # ResamplingQuality::Default
+    target_mixer: int = A.MAIN_MIXER
+
+    def repeat_forever(self):
+        self.repeat = A.REPEAT_FOREVER
+        return self
+
+
+@dataclass
+class AhdsrParameters:
+    """AhdsrParameters::new / new_with_scaling (src/utils/ahdsr.rs:50-98), times in seconds."""
+    attack: float = 0.01
+    hold: float = 1.0
+    decay: float = 0.5
+    sustain: float = 0.75
+    release: float = 1.0
+    attack_scaling: float = 0.0
+    decay_scaling: float = 0.0
+    release_scaling: float = 0.0
+
+
+@dataclass
+class GeneratorPlaybackOptions:
+    """GeneratorPlaybackOptions (src/generator.rs:41-141)."""
+    volume: float = 1.0
+    panning: float = 0.0
+    voices: int = 8
+    target_mixer: int = A.MAIN_MIXER
+
+
+@dataclass
+class FilterEffect:
+    """FilterEffect::with_parameters (src/effect/filter.rs:104-116); None => FilterEffect::new()."""
+    filter_type: int = 0
+    cutoff: float = 20000.0
+    q: float = 0.707
+    default: bool = False
+
+
+@dataclass
+class Eq5Effect:
+    """Eq5Effect::new() (src/effect/eq5.rs:153-170)."""
+
+
+@dataclass
+class CompressorEffect:
+    """CompressorEffect::with_compressor_parameters (src/effect/compressor.rs:122-140)."""
+    threshold: float = -12.0
+    ratio: float = 8.0
+    knee: float = 3.0
+    attack_time: float = 0.02
+    release_time: float = 2.0
+    makeup_gain: float = 6.0
+    lookahead_time: float = 0.04
+
+    @staticmethod
+    def new_limiter():  # compressor.rs:114-157
+        return CompressorEffect(-0.01, 20.0, 0.0, 0.02, 2.0, 0.0, 0.02)
+
+
+@dataclass
+class ChorusEffect:
+    """ChorusEffect::with_parameters (src/effect/chorus.rs:178-200)."""
+    rate: float = 1.0
+    phase: float = math.pi / 2.0
+    depth: float = 0.25
+    feedback: float = 0.5
+    delay: float = 12.0
+    wet: float = 0.5
+    filter_type: int = 0
+    filter_freq: float = 20000.0
+    filter_resonance: float = 0.0
+
+
+@dataclass
+class DelayEffect:
+    """DelayEffect::new() (src/effect/delay.rs:180-212)."""
+
+
+@dataclass
+class ReverbEffect:
+    """ReverbEffect::with_parameters (src/effect/reverb.rs:153-159) with the RNG-drawn start
+    state (fpd_l/r, 16 vibrato phases, reverb.rs:95-103,535-538) made explicit."""
+    room_size: float = 0.6
+    wet: float = 0.35
+    fpd: Sequence[int] = (0x1234567, 0x89ABCDE)
+    vib_phase: Sequence[float] = field(default_factory=lambda: [0.1 + 0.37 * i for i in range(16)])
+
+
+class _Handle:
+    def __init__(self, player: "Player", ident: int):
+        self._p = player
+        self.id = ident
+
+    def _ev(self, kind, sample_time, **kw):
+        ev = A.Event()
+        ev.sample_time = A.TIME_NOW if sample_time is None else int(sample_time)
+        ev.kind = kind
+        ev.target = self.id
+        for k, v in kw.items():
+            setattr(ev, k, v)
+        self._p._check(self._p.api.schedule(self._p._r, C.byref(ev)))
+        return ev
+
+
+class FilePlaybackHandle(_Handle):
+    """FilePlaybackHandle (src/player/handles/file.rs:31-268)."""
+
+    def stop(self, stop_time=None):
+        self._ev(A.EV_STOP_SOURCE, stop_time)
+
+    def seek(self, position_seconds: float, sample_time=None):
+        self._ev(A.EV_SEEK_SOURCE, sample_time, position_nanos=_nanos(position_seconds))
+
+    def set_speed(self, speed: float, glide: Optional[float] = None, sample_time=None):
+        self._ev(A.EV_SET_SOURCE_SPEED, sample_time, speed=speed, glide=glide or 0.0)
+
+    def set_volume(self, volume: float, sample_time=None):
+        self._ev(A.EV_SET_SOURCE_VOLUME, sample_time, value=volume)
+
+    def set_panning(self, panning: float, sample_time=None):
+        self._ev(A.EV_SET_SOURCE_PANNING, sample_time, value=panning)
+
+    def status(self) -> A.SourceStatus:
+        st = A.SourceStatus()
+        self._p._check(self._p.api.source_status_get(self._p._r, self.id, C.byref(st)))
+        return st
+
+    def is_playing(self) -> bool:
+        return bool(self.status().is_playing)
+
+
+class GeneratorPlaybackHandle(_Handle):
+    """GeneratorPlaybackHandle (src/player/handles/generator.rs:62-437)."""
+
+    def stop(self, stop_time=None):
+        self._ev(A.EV_STOP_SOURCE, stop_time)
+
+    def set_volume(self, volume: float, sample_time=None):
+        self._ev(A.EV_SET_SOURCE_VOLUME, sample_time, value=volume)
+
+    def set_panning(self, panning: float, sample_time=None):
+        self._ev(A.EV_SET_SOURCE_PANNING, sample_time, value=panning)
+
+    def note_on(self, note: int, volume: Optional[float] = None, panning: Optional[float] = None,
+                sample_time=None) -> int:
+        flags = (A.EVF_HAS_VOLUME if volume is not None else 0) | (A.EVF_HAS_PANNING if panning is not None else 0)
+        ev = self._ev(A.EV_NOTE_ON, sample_time, note=int(note), value=volume or 0.0,
+                      value2=panning or 0.0, flags=flags)
+        return int(ev.note_id)
+
+    def note_off(self, note_id: int, sample_time=None):
+        self._ev(A.EV_NOTE_OFF, sample_time, note_id=note_id)
+
+    def all_notes_off(self, sample_time=None):
+        self._ev(A.EV_ALL_NOTES_OFF, sample_time)
+
+    def set_note_speed(self, note_id: int, speed: float, glide: Optional[float] = None, sample_time=None):
+        self._ev(A.EV_SET_NOTE_SPEED, sample_time, note_id=note_id, speed=speed, glide=glide or 0.0)
+
+    def set_note_volume(self, note_id: int, volume: float, sample_time=None):
+        self._ev(A.EV_SET_NOTE_VOLUME, sample_time, note_id=note_id, value=volume)
+
+    def set_note_panning(self, note_id: int, panning: float, sample_time=None):
+        self._ev(A.EV_SET_NOTE_PANNING, sample_time, note_id=note_id, value=panning)
+
+    def voice_states(self, capacity: int = 1024):
+        arr = (A.VoiceState * capacity)()
+        n = A.U32(0)
+        self._p._check(self._p.api.sampler_voice_states(self._p._r, self.id, arr, capacity, C.byref(n)))
+        return [(int(v.note_id), int(v.playback_pos), int(v.envelope_stage), int(v.active))
+                for v in arr[:min(n.value, capacity)]]
+
+
+class EffectHandle(_Handle):
+    """EffectHandle (src/player/handles/effect.rs:47-126)."""
+
+    def set_parameter(self, param_id: str, value: float, sample_time=None):
+        self._ev(A.EV_SET_EFFECT_PARAMETER, sample_time, param_id=A.fourcc(param_id), value=value)
+
+    def set_parameter_normalized(self, param_id: str, value: float, sample_time=None):
+        self._ev(A.EV_SET_EFFECT_PARAMETER, sample_time, param_id=A.fourcc(param_id), value=value,
+                 flags=A.EVF_NORMALIZED)
+
+
+class MixerHandle:
+    """MixerHandle (src/player/handles/mixer.rs:37-72)."""
+
+    def __init__(self, ident: int):
+        self.id = ident
+
+
+class Player:
+    """Player::new(WavOutput::open_with_specs(path, sample_rate, 2, duration), None)."""
+
+    def __init__(self, api: A.CApi, sample_rate: int = 48000, channel_count: int = 2,
+                 device_ordinal: int = -1, master_volume: float = 1.0, block_frames: int = 1024):
+        self.api = api
+        self.sample_rate = sample_rate
+        self.channel_count = channel_count
+        self.block_frames = block_frames
+        cfg = A.Config(sample_rate, channel_count, block_frames, device_ordinal, master_volume)
+        r = C.c_void_p()
+        code = api.create(C.byref(cfg), C.byref(r))
+        if code != A.OK:
+            raise PhonicError(code, "pb200_create failed")
+        self._r = r
+
+    def close(self):
+        if self._r:
+            self.api.destroy(self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, code: int):
+        if code != A.OK:
+            msg = self.api.last_error(self._r)
+            raise PhonicError(code, msg.decode() if msg else "")
+
+    # -- sample data -------------------------------------------------------------------------
+    def upload_buffer(self, samples: np.ndarray, sample_rate: int, loop_range=None, add_pad_frame=True) -> int:
+        """AudioFileBuffer::new; `samples` is [frames] (mono) or [frames, channels] float32."""
+        a = np.ascontiguousarray(samples, dtype=np.float32)
+        ch = 1 if a.ndim == 1 else a.shape[1]
+        frames = a.shape[0]
+        ls, le = loop_range if loop_range else (A.NO_LOOP, A.NO_LOOP)
+        bid = A.U32()
+        self._check(self.api.upload_buffer(self._r, a.ctypes.data_as(C.POINTER(A.F32)), frames, ch, sample_rate,
+                                           ls, le, 1 if add_pad_frame else 0, C.byref(bid)))
+        return bid.value
+
+    # -- graph -------------------------------------------------------------------------------
+    def add_mixer(self, parent_mixer_id: Optional[int] = None) -> MixerHandle:
+        mid = A.U32()
+        self._check(self.api.add_mixer(self._r, parent_mixer_id or A.MAIN_MIXER, C.byref(mid)))
+        return MixerHandle(mid.value)
+
+    def add_effect(self, effect, mixer_id: Optional[int] = None) -> EffectHandle:
+        eid = A.U32()
+        mixer = mixer_id or A.MAIN_MIXER
+        if isinstance(effect, FilterEffect):
+            if effect.default:
+                kind, p = A.FX_FILTER, None
+            else:
+                kind, p = A.FX_FILTER, A.FilterParams(effect.filter_type, effect.cutoff, effect.q)
+        elif isinstance(effect, Eq5Effect):
+            kind, p = A.FX_EQ5, None
+        elif isinstance(effect, CompressorEffect):
+            kind, p = A.FX_COMPRESSOR, A.CompressorParams(effect.threshold, effect.ratio, effect.knee,
+                                                         effect.attack_time, effect.release_time,
+                                                         effect.makeup_gain, effect.lookahead_time)
+        elif isinstance(effect, ChorusEffect):
+            kind, p = A.FX_CHORUS, A.ChorusParams(effect.rate, effect.phase, effect.depth, effect.feedback,
+                                                 effect.delay, effect.wet, effect.filter_type,
+                                                 effect.filter_freq, effect.filter_resonance)
+        elif isinstance(effect, DelayEffect):
+            kind, p = A.FX_DELAY, None
+        elif isinstance(effect, ReverbEffect):
+            kind = A.FX_REVERB
+            p = A.ReverbParams(effect.room_size, effect.wet, (A.U32 * 2)(*effect.fpd), (A.F64 * 16)(*effect.vib_phase))
+        else:
+            raise TypeError(effect)
+        if p is None:
+            self._check(self.api.add_effect(self._r, mixer, kind, None, 0, C.byref(eid)))
+        else:
+            self._check(self.api.add_effect(self._r, mixer, kind, C.cast(C.byref(p), C.c_void_p), C.sizeof(p), C.byref(eid)))
+        return EffectHandle(self, eid.value)
+
+    # -- sources -----------------------------------------------------------------------------
+    def play_file_source(self, buffer_id: int, options: Optional[FilePlaybackOptions] = None,
+                         start_time: Optional[int] = None) -> FilePlaybackHandle:
+        o = options or FilePlaybackOptions()
+        fo = A.FileOptions()
+        self.api.file_options_default(C.byref(fo))
+        fo.volume, fo.panning, fo.speed = o.volume, o.panning, o.speed
+        fo.repeat = A.REPEAT_DEFAULT if o.repeat is None else int(o.repeat)
+        if o.loop_range:
+            fo.loop_start, fo.loop_end = o.loop_range
+        fo.fade_in_nanos = _nanos(o.fade_in)
+        fo.fade_out_nanos = _nanos(o.fade_out)
+        fo.resampling_quality = o.resampling_quality
+        fo.target_mixer = o.target_mixer
+        pid = A.U32()
+        self._check(self.api.play_file(self._r, buffer_id, C.byref(fo),
+                                       A.TIME_NOW if start_time is None else int(start_time), C.byref(pid)))
+        return FilePlaybackHandle(self, pid.value)
+
+    def _sampler(self, buffer_id, options, ahdsr, transient, start_time):
+        o = options or GeneratorPlaybackOptions()
+        so = A.SamplerOptions()
+        self.api.sampler_options_default(C.byref(so))
+        so.volume, so.panning, so.voices, so.target_mixer = o.volume, o.panning, o.voices, o.target_mixer
+        so.transient = 1 if transient else 0
+        if ahdsr is not None:
+            so.has_ahdsr = 1
+            so.ahdsr = A.Ahdsr(_nanos(ahdsr.attack), _nanos(ahdsr.hold), _nanos(ahdsr.decay), _nanos(ahdsr.release),
+                               ahdsr.attack_scaling, ahdsr.decay_scaling, ahdsr.release_scaling, ahdsr.sustain)
+        gid = A.U32()
+        self._check(self.api.add_sampler(self._r, buffer_id, C.byref(so),
+                                         A.TIME_NOW if start_time is None else int(start_time), C.byref(gid)))
+        return GeneratorPlaybackHandle(self, gid.value)
+
+    def play_generator(self, buffer_id: int, options=None, ahdsr: Optional[AhdsrParameters] = None,
+                       start_time: Optional[int] = None) -> GeneratorPlaybackHandle:
+        """Player::play_generator(Sampler::from_file_source(..).with_ahdsr(..), start_time)."""
+        return self._sampler(buffer_id, options, ahdsr, True, start_time)
+
+    def add_generator(self, buffer_id: int, options=None, ahdsr: Optional[AhdsrParameters] = None,
+                      mixer_id: Optional[int] = None) -> GeneratorPlaybackHandle:
+        """Player::add_generator(Sampler::from_file_source(..).with_ahdsr(..), mixer_id)."""
+        o = options or GeneratorPlaybackOptions()
+        if mixer_id is not None:
+            o = GeneratorPlaybackOptions(o.volume, o.panning, o.voices, mixer_id)
+        return self._sampler(buffer_id, o, ahdsr, False, None)
+
+    # -- render ------------------------------------------------------------------------------
+    def render(self, frames: int) -> np.ndarray:
+        """`frames` output frames as WavStream::process would write them (src/output/wav.rs:210-250)."""
+        out = np.zeros((frames, self.channel_count), dtype=np.float32)
+        self.render_into(out)
+        return out
+
+    def render_into(self, out: np.ndarray) -> int:
+        written = A.U64()
+        frames = out.shape[0]
+        self._check(self.api.render(self._r, out.ctypes.data_as(C.POINTER(A.F32)), frames, C.byref(written)))
+        return written.value
+
+    def render_device(self, device_ptr: int, frames: int) -> int:
+        written = A.U64()
+        self._check(self.api.render_device(self._r, C.c_void_p(device_ptr), frames, C.byref(written)))
+        return written.value
+
+    def output_sample_frame_position(self) -> int:
+        return int(self.api.position(self._r))
+
+    def last_render_stats(self) -> A.RenderStats:
+        st = A.RenderStats()
+        self._check(self.api.last_render_stats(self._r, C.byref(st)))
+        return st

@@ -1,0 +1,147 @@
+"""Synthetic workloads of BASELINE.json's configs, built through the public
+Player API so the same scene can be handed to any implementation of the C-ABI.
+
+All randomness is seeded; all sample values are f32 in [-0.5, 0.5]; gains are <= 1/sqrt(voices)
+so buses stay below 1.0.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from .player import (AhdsrParameters, ChorusEffect, CompressorEffect, DelayEffect, Eq5Effect, FilePlaybackOptions,
+                     FilterEffect, GeneratorPlaybackOptions, Player, ReverbEffect)
+
+
+def speed_from_note(note: int) -> float:
+    """src/utils.rs:67-78"""
+    return (440.0 * 2.0 ** ((note - 69.0) / 12.0)) / (440.0 * 2.0 ** ((60 - 69.0) / 12.0))
+
+
+def synth_buffer(frames: int, sample_rate: int, seed: int = 1, channels: int = 1) -> np.ndarray:
+    """Band-limited noise + sines in [-0.5, 0.5] (cfg2 'one 44.1 k mono buffer of 4 s', seed 1)."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(frames, dtype=np.float64) / sample_rate
+    out = np.zeros((frames, channels), dtype=np.float64)
+    for c in range(channels):
+        sig = np.zeros(frames)
+        for k in range(6):
+            f = 110.0 * (k + 1) * (1.0 + 0.01 * c)
+            sig += rng.uniform(0.2, 1.0) / (k + 1) * np.sin(2 * np.pi * f * t + rng.uniform(0, 2 * np.pi))
+        noise = rng.standard_normal(frames)
+        # crude band limit: moving average over 8 samples
+        kernel = np.ones(8) / 8.0
+        noise = np.convolve(noise, kernel, mode="same")
+        sig += 0.5 * noise
+        sig *= 0.5 / np.max(np.abs(sig))
+        out[:, c] = sig
+    out32 = out.astype(np.float32)
+    return out32[:, 0].copy() if channels == 1 else out32
+
+
+@dataclass
+class VoiceBankSpec:
+    """cfg2-style sampler voice bank."""
+    voices: int = 256
+    voices_per_sampler: int = 8
+    seconds: float = 10.0
+    sample_rate: int = 48000
+    buffer_rate: int = 44100
+    buffer_seconds: float = 4.0
+    seed: int = 2
+    glide: bool = True
+    note_off: bool = True
+
+
+def frames_for(seconds: float, sample_rate: int, block: int = 1024) -> int:
+    """WavStream renders whole 1024-frame blocks until whole-seconds(pos/sr) >= duration
+    (src/output/wav.rs:222): a '10 s' render at 48 kHz is 469 blocks = 480 256 frames."""
+    blocks = 0
+    while (blocks * block) // sample_rate < seconds:
+        blocks += 1
+    return blocks * block
+
+
+def add_voice_bank(player: Player, spec: VoiceBankSpec, buffer_id: int, mixer_id=None, seed_offset: int = 0,
+                   time_scale: float = 1.0):
+    """Adds `spec.voices` sampler voices (AHDSR + glide) to `mixer_id`; returns the sampler handles.
+
+    Per voice: note uniform in 36..84, note-on uniform in [0, 2 s), glide SetSpeed to note+-7 at
+    [2, 6 s) with 12..60 st/s, note-off at [6, 8 s). Times scale with `time_scale` for short tests.
+    """
+    rng = np.random.default_rng(spec.seed + seed_offset)
+    sr = spec.sample_rate
+    n_samplers = (spec.voices + spec.voices_per_sampler - 1) // spec.voices_per_sampler
+    gain = 1.0 / math.sqrt(max(spec.voices, 1))
+    ahdsr = AhdsrParameters(attack=0.01, hold=0.0, decay=0.5, sustain=0.75, release=1.0)
+    handles = []
+    remaining = spec.voices
+    for _ in range(n_samplers):
+        nv = min(spec.voices_per_sampler, remaining)
+        remaining -= nv
+        opts = GeneratorPlaybackOptions(volume=1.0, panning=0.0, voices=nv)
+        h = player.add_generator(buffer_id, opts, ahdsr, mixer_id=mixer_id)
+        handles.append(h)
+        for _v in range(nv):
+            note = int(rng.integers(36, 85))
+            t_on = int(rng.uniform(0.0, 2.0 * time_scale) * sr)
+            pan = float(rng.uniform(-0.8, 0.8))
+            nid = h.note_on(note, volume=gain, panning=pan, sample_time=t_on)
+            if spec.glide:
+                t_gl = int(rng.uniform(2.0, 6.0) * time_scale * sr)
+                tgt = note + (7 if rng.random() < 0.5 else -7)
+                rate = float(rng.uniform(12.0, 60.0))
+                h.set_note_speed(nid, speed_from_note(tgt), glide=rate, sample_time=t_gl)
+            if spec.note_off:
+                t_off = int(rng.uniform(6.0, 8.0) * time_scale * sr)
+                h.note_off(nid, sample_time=t_off)
+    return handles
+
+
+def build_cfg2(player: Player, spec: VoiceBankSpec | None = None, time_scale: float = 1.0):
+    """cfg2: 256 Sampler voices (AHDSR + glide), cubic resampling, FilterEffect LP 2 kHz on the bus."""
+    spec = spec or VoiceBankSpec()
+    buf = synth_buffer(int(spec.buffer_seconds * spec.buffer_rate), spec.buffer_rate, seed=1)
+    bid = player.upload_buffer(buf, spec.buffer_rate)
+    handles = add_voice_bank(player, spec, bid, None, 0, time_scale)
+    fx = player.add_effect(FilterEffect(0, 2000.0, 0.707))
+    return handles, fx
+
+
+def build_cfg1(player: Player, buffer: np.ndarray, buffer_rate: int):
+    """cfg1: one stereo file through FilterEffect LP 1 kHz + ReverbEffect(0.6, 0.35)."""
+    bid = player.upload_buffer(buffer, buffer_rate)
+    h = player.play_file_source(bid, FilePlaybackOptions())
+    player.add_effect(FilterEffect(0, 1000.0, 0.707))
+    player.add_effect(ReverbEffect(0.6, 0.35))
+    return h
+
+
+def build_subtrees(player: Player, n_mixers: int, voices_per_mixer: int, spec: VoiceBankSpec, effects: str = "none",
+                   time_scale: float = 1.0, seed_base: int = 0):
+    """cfg3 / cfg5 shape: `n_mixers` sub-mixers of the main mixer, each with a cfg2-style bank.
+    effects: 'none' | 'cfg3' (Eq5 + Compressor + Chorus per sub-mixer)."""
+    buf = synth_buffer(int(spec.buffer_seconds * spec.buffer_rate), spec.buffer_rate, seed=1)
+    bid = player.upload_buffer(buf, spec.buffer_rate)
+    rng = np.random.default_rng(3 + seed_base)
+    out = []
+    for m in range(n_mixers):
+        mh = player.add_mixer(None)
+        sub = VoiceBankSpec(**{**spec.__dict__, "voices": voices_per_mixer})
+        hs = add_voice_bank(player, sub, bid, mh.id, seed_offset=1000 * (m + 1) + seed_base, time_scale=time_scale)
+        if effects == "cfg3":
+            eq = player.add_effect(Eq5Effect(), mh.id)
+            for b in range(5):
+                eq.set_parameter(f"gan{b + 1}", float(rng.uniform(-6.0, 6.0)), sample_time=0)
+            player.add_effect(CompressorEffect(), mh.id)
+            player.add_effect(ChorusEffect(), mh.id)
+        out.append((mh, hs))
+    return out
+
+
+def add_main_bus_sends(player: Player):
+    """cfg5: Delay (375 ms, fb 0.5 = DelayEffect::new() defaults) + Reverb on the main bus."""
+    player.add_effect(DelayEffect())
+    player.add_effect(ReverbEffect(0.6, 0.35))
