@@ -1,0 +1,159 @@
+// Device-resident data model of the renderer (shared by host graph compiler and kernels).
+//
+// Layout in HBM:
+//   sample buffers   : one contiguous f32 array per uploaded AudioFileBuffer (interleaved)
+//   voices           : VoiceState[n_voices]   (one record per sampler voice / file playback)
+//   groups           : GroupParams[n_groups] (immutable) + GroupState[n_groups] (mutable)
+//                      a group = one phonic `Source` attached to a mixer: a Sampler (N voices)
+//                      or one file playback (1 voice)
+//   events           : DevEvent[] sorted per group by (sample_time, insertion order)
+//   chunk schedule   : per mixer, the reference's exact `MixedSource::write` chunk boundaries
+//   group bus ring   : f32 [ring][group][block_frames][2]   (per time block scratch)
+//   mixer buses      : f32 [ring][mixer][block_frames][2]
+#pragma once
+#include <stdint.h>
+
+namespace pb {
+
+constexpr uint32_t REPEAT_FOREVER = 0xFFFFFFFFu;
+constexpr int MAX_EFFECTS_PER_MIXER = 16;
+
+struct DevBuffer {
+  const float* data;    // interleaved samples (incl. the +1 zero pad frame)
+  uint32_t n_samples;   // buffer().len()
+  uint32_t channels;    // 1 or 2
+  uint32_t sample_rate;
+  int32_t loop_start;   // frames, -1 = no embedded loop
+  int32_t loop_end;
+  uint32_t _pad;
+};
+
+// ExponentialSmoothedValue (src/utils/smoothing.rs:131-228); inertia and rate comp are constants
+struct ExpSm {
+  float current, target;
+};
+
+enum FaderState : uint8_t { FADER_STOPPED = 0, FADER_RUNNING = 1, FADER_FINISHED = 2 };
+enum EnvStage : uint8_t { ENV_IDLE = 0, ENV_ATTACK = 1, ENV_HOLD = 2, ENV_DECAY = 3, ENV_SUSTAIN = 4, ENV_RELEASE = 5 };
+
+// One voice = Panned<Amplified<ChannelMapped<PreloadedFileSource>>> (+ AhdsrEnvelope for samplers).
+struct VoiceState {
+  // PreloadedFileSource (src/source/file/preloaded.rs:29-37) + FileSourceImpl (file/common.rs:31-52)
+  double current_speed, target_speed;
+  uint64_t note_id;            // SamplerVoice::note_id (valid when has_note)
+  uint64_t release_start;      // SamplerVoice::release_start_frame
+  uint64_t end_frame;          // output frame at which playback finished (status only)
+  uint32_t playback_pos;       // sample index into the buffer
+  uint32_t repeat, repeat_count;
+  int32_t loop_ovr_start, loop_ovr_end;  // loop_range_override in frames, -1 = None
+  uint32_t to_next_speed_update;         // frames until the next glide update
+  float glide_rate;
+  // CubicInterpolator x channels (src/utils/resampler/cubic.rs:10-15); sub_pos/ratio shared
+  float ratio, sub_pos;
+  float hist[2][4];            // [channel][input[0..3]]
+  // VolumeFader (src/utils/fader.rs:27-34)
+  float fader_cur, fader_tgt, fader_inertia;
+  // AmplifiedSource / PannedSource smoothers
+  ExpSm vol, pan;
+  // AhdsrEnvelope (src/utils/ahdsr.rs:367-373)
+  float env_target, env_hold, env_release_out, env_out;
+  float note_volume, note_panning;
+  uint8_t env_stage;
+  uint8_t fader_state;
+  uint8_t initialized;         // CubicInterpolator::is_initialized
+  uint8_t pos_eof, finished;   // playback_pos_eof, playback_finished
+  uint8_t has_note, has_release, note;
+  uint8_t stopped_exhausted;
+  uint8_t _pad[7];
+};
+
+enum GroupKind : uint32_t { GROUP_SAMPLER = 0, GROUP_FILE = 1 };
+
+struct GroupParams {
+  uint32_t kind;
+  uint32_t first_voice, n_voices;
+  uint32_t buffer;
+  uint32_t mixer;        // dense mixer index
+  uint32_t ev_begin, ev_end;
+  uint32_t transient;
+  uint64_t start_time;   // PlayingSource::start_time
+  // AhdsrParameters (src/utils/ahdsr.rs:26-39), sample rate applied on the host
+  uint32_t has_env;
+  float attack_rate, decay_rate, release_rate, sustain_level, hold_samples;
+  float attack_scaling, decay_scaling, release_scaling;
+  uint32_t hold_is_zero, decay_is_zero, release_is_zero;
+  // fade-out of voices (50 ms default): inertia precomputed on the host with the reference's f32 math
+  uint32_t has_fade_out;
+  float fade_out_inertia;
+  float base_volume, base_panning;  // Sampler::base_volume/base_panning
+  uint32_t _pad;
+};
+
+struct GroupState {
+  uint64_t stop_time;
+  uint32_t has_stop_time;
+  uint32_t ev_cursor;
+  uint32_t active_voices;
+  uint32_t stopping, stopped;
+  uint32_t dead;          // removed from the mixer (transient && exhausted)
+  ExpSm vol, pan;         // generator-level AmplifiedSource / PannedSource (player.rs:1075-1081)
+  uint64_t voice_frames;  // statistics: active voice-frames rendered
+};
+
+enum EventKind : uint32_t {
+  EVK_STOP = 1, EVK_SET_VOLUME = 2, EVK_SET_PANNING = 3, EVK_SET_SPEED = 4, EVK_SEEK = 5,
+  EVK_NOTE_ON = 10, EVK_NOTE_OFF = 11, EVK_ALL_NOTES_OFF = 12, EVK_NOTE_SPEED = 13, EVK_NOTE_VOLUME = 14,
+  EVK_NOTE_PANNING = 15
+};
+
+struct DevEvent {
+  uint64_t time;
+  uint64_t note_id;
+  double speed;        // effective speed (note speed * pitch factor resolved on the host)
+  uint32_t kind;
+  float value, value2; // volume / panning
+  float glide;         // <= 0: None
+  uint32_t note;
+  uint32_t seek_pos;   // SEEK: clamped sample index (preloaded.rs:140-143)
+  uint32_t flags;
+  uint32_t _pad;
+};
+
+// ---- mixers / effects -------------------------------------------------------------------------------
+enum FxKind : uint32_t { FX_FILTER = 1, FX_EQ5 = 2, FX_COMPRESSOR = 3, FX_CHORUS = 4, FX_DELAY = 5, FX_REVERB = 6 };
+
+struct LinSm { float current, target, step, current_step; uint32_t pending; };
+struct SpringSm { float current, velocity, target, omega; };
+
+struct BiquadCoef { double a1, a2, a3, m0, m1, m2; float cutoff, q, gain; uint32_t type, sample_rate; uint32_t _pad; };
+struct SvfCoef { double g, k, a1, a2, a3; float cutoff, resonance; uint32_t type, sample_rate; };
+
+struct FxParamEvent { uint64_t time; uint32_t param_id; float value; uint32_t normalized; uint32_t _pad; };
+
+// EffectProcessor (src/source/mixed/effect.rs:10-15) + per-kind state blob (see effects.cuh)
+struct FxHeader {
+  uint32_t kind;
+  uint32_t bypassed;
+  uint64_t tail_counter, silence_counter;  // usize::MAX sentinels as in the reference
+  uint32_t ev_begin, ev_end, ev_cursor;
+  uint32_t state_offset;   // byte offset of the kind-specific state in the fx state arena
+  uint32_t aux_offset;     // byte offset of delay-line storage in the fx aux arena (f64 units)
+  uint32_t _pad;
+};
+
+struct MixerParams {
+  uint32_t parent;         // dense index, 0xFFFFFFFF for main
+  uint32_t depth;
+  uint32_t child_begin, child_end;   // into child index array (reference mixer order)
+  uint32_t src_begin, src_end;       // into source (group) index array (playing_sources order)
+  uint32_t fx_begin, fx_end;         // into FxHeader array (effect chain order)
+  uint32_t _pad[2];
+};
+
+struct MixerState {
+  uint64_t silence_counter;   // SubMixerProcessor::silence_counter
+  uint32_t effects_bypassed;  // MixedSource::effects_bypassed
+  uint32_t _pad;
+};
+
+}  // namespace pb

@@ -1,0 +1,1000 @@
+// phonic_b200 renderer: host graph builder + schedule compiler + CUDA launches behind the C-ABI of
+// include/phonic_b200.h. No CPU fallback: every render path launches the kernels of this unit.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/phonic_b200.h"
+#include "voice_kernel.cuh"
+#include "mixer_kernel.cuh"
+#include "host_fx.h"
+
+using namespace pb;
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      r->last_error = std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr;      \
+      return PB200_ERR_CUDA;                                                                     \
+    }                                                                                            \
+  } while (0)
+
+template <class T>
+struct DevVec {  // grow-only device array
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = std::max(n, cap + cap / 2);
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p) cudaFree(p);
+    p = np; cap = ncap;
+    return cudaSuccess;
+  }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = reserve(std::max<size_t>(v.size(), 1));
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  cudaError_t download(std::vector<T>& v, cudaStream_t s) const {
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(v.data(), p, v.size() * sizeof(T), cudaMemcpyDeviceToHost, s);
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuffer { DevBuffer dev; };
+
+struct HostEvent { DevEvent ev; uint64_t seq; };
+
+struct HostGroup {
+  uint32_t public_id;
+  GroupParams gp;
+  std::vector<HostEvent> events;  // pending (not yet consumed) events, sorted at compile time
+};
+
+struct HostFx {
+  uint32_t public_id, kind, mixer;  // dense mixer index
+  std::vector<FxParamEvent> events;
+  std::vector<uint64_t> seqs;
+};
+
+struct HostMixer {
+  uint32_t public_id;
+  uint32_t parent;  // dense index or 0xFFFFFFFF
+  uint32_t depth;
+  std::vector<uint32_t> children, sources, effects;
+};
+
+constexpr uint32_t RING = 3;
+
+}  // namespace
+
+struct pb200_renderer {
+  pb200_config cfg;
+  std::string last_error;
+  int device = 0;
+  cudaStream_t sv = nullptr, sm = nullptr;
+  RenderConsts rc;
+
+  std::vector<HostBuffer> buffers;
+  std::vector<HostMixer> mixers;            // dense; [0] = main
+  std::map<uint32_t, uint32_t> mixer_by_id; // public -> dense
+  std::vector<HostGroup> groups;
+  std::map<uint32_t, uint32_t> group_by_id;
+  std::vector<HostFx> fxs;
+  std::map<uint32_t, uint32_t> fx_by_id;
+  uint32_t next_source_id = 1, next_mixer_id = 1, next_effect_id = 1;
+  uint64_t next_note_id = 1, next_seq = 1;
+
+  // host mirrors of device state
+  std::vector<VoiceState> h_voices;
+  std::vector<GroupState> h_gstate;
+  std::vector<MixerState> h_mstate;
+  std::vector<FxHeader> h_fx;
+  std::vector<uint8_t> h_fx_state;
+  size_t aux_doubles = 0;
+  bool host_state_valid = true;  // host mirrors are newer or equal to device
+  bool graph_dirty = true;
+  size_t dev_n_voices = 0, dev_n_groups = 0, dev_n_mixers = 0, dev_n_fx = 0, dev_fx_state_bytes = 0;
+
+  // device arrays
+  DevVec<DevBuffer> d_buffers;
+  DevVec<VoiceState> d_voices;
+  DevVec<GroupParams> d_groups;
+  DevVec<GroupState> d_gstate;
+  DevVec<DevEvent> d_events;
+  DevVec<MixerParams> d_mixers;
+  DevVec<MixerState> d_mstate;
+  DevVec<uint32_t> d_child_index, d_source_index, d_level_mixers, d_class_groups;
+  DevVec<FxHeader> d_fx;
+  DevVec<FxParamEvent> d_fx_events;
+  DevVec<uint8_t> d_fx_state;
+  DevVec<double> d_aux;
+  size_t d_aux_used = 0;
+  DevVec<uint64_t> d_bounds;
+  DevVec<uint32_t> d_chunk_begin;
+  DevVec<float> d_group_bus, d_mixer_bus, d_out;
+  DevVec<uint8_t> d_group_flags, d_mixer_flags;
+  DevVec<ExpSm> d_master;
+  ExpSm h_master;
+  bool master_uploaded = false;
+
+  uint64_t position = 0;  // frames
+  bool finished = false;
+  uint32_t time_block = 8192;
+  uint64_t voice_frames_total = 0;
+  pb200_render_stats stats{};
+};
+
+namespace {
+
+int fail(pb200_renderer* r, int code, const std::string& msg) {
+  if (r) r->last_error = msg;
+  return code;
+}
+
+// std::time::Duration::as_secs_f32 / as_secs_f64 from as_nanos()
+float nanos_as_secs_f32(uint64_t n) { return (float)(n / 1000000000ull) + (float)(uint32_t)(n % 1000000000ull) / 1.0e9f; }
+double nanos_as_secs_f64(uint64_t n) { return (double)(n / 1000000000ull) + (double)(uint32_t)(n % 1000000000ull) / 1.0e9; }
+
+uint32_t f64_as_u32_h(double v) {
+  if (!(v > 0.0)) return 0u;
+  if (v >= 4294967295.0) return 0xFFFFFFFFu;
+  return (uint32_t)v;
+}
+
+// VolumeFader::start inertia (src/utils/fader.rs:85-90), f32 math as in the reference
+float fader_inertia(uint32_t sr, uint64_t nanos) {
+  const float LN100 = 4.605f;
+  float samples_duration = (float)sr * nanos_as_secs_f32(nanos) / LN100;
+  return 1.0f - std::exp(-1.0f / samples_duration);
+}
+
+double speed_from_note_h(uint32_t note) {  // src/utils.rs:67-78
+  double p = 440.0 * std::pow(2.0, ((double)(uint8_t)note - 69.0) / 12.0);
+  double p60 = 440.0 * std::pow(2.0, (60.0 - 69.0) / 12.0);
+  return p / p60;
+}
+
+VoiceState default_voice(const DevBuffer& b, uint32_t out_rate, double speed) {
+  VoiceState v;
+  std::memset(&v, 0, sizeof(v));
+  v.current_speed = speed; v.target_speed = speed;
+  v.end_frame = UINT64_MAX;
+  v.repeat = b.loop_start >= 0 ? REPEAT_FOREVER : 0;
+  v.repeat_count = v.repeat;
+  v.loop_ovr_start = -1; v.loop_ovr_end = -1;
+  uint32_t rate = f64_as_u32_h((double)out_rate / speed);  // file/common.rs:78-82
+  v.ratio = (float)((double)b.sample_rate / (double)rate);
+  v.fader_state = FADER_STOPPED; v.fader_cur = 1.0f; v.fader_tgt = 1.0f; v.fader_inertia = 1.0f;
+  v.vol = ExpSm{1.0f, 1.0f};
+  v.pan = ExpSm{0.0f, 0.0f};
+  v.env_stage = ENV_IDLE;
+  v.note = 60; v.note_volume = 1.0f;
+  return v;
+}
+
+// AhdsrParameters::new_with_scaling + set_sample_rate (src/utils/ahdsr.rs:75-136, 160-313)
+bool resolve_ahdsr(const pb200_ahdsr& a, uint32_t sr, GroupParams& gp) {
+  const float F32_MAX = 3.402823466e+38f;
+  auto in_unit = [](float s) { return s >= -1.0f && s <= 1.0f; };
+  if (!in_unit(a.attack_scaling) || !in_unit(a.decay_scaling) || !in_unit(a.release_scaling)) return false;
+  if (!(a.sustain_level >= 0.0f && a.sustain_level <= 1.0f)) return false;
+  // after set_sample_rate(sr) -> setup(): all rates use `sr` and the final sustain level
+  float at = nanos_as_secs_f32(a.attack_nanos);
+  gp.attack_rate = at == 0.0f ? F32_MAX : 1.0f / (at * (float)sr);
+  gp.hold_is_zero = a.hold_nanos == 0;
+  gp.hold_samples = nanos_as_secs_f32(a.hold_nanos) * (float)sr;
+  gp.decay_is_zero = a.decay_nanos == 0;
+  gp.decay_rate = a.decay_nanos == 0 ? F32_MAX : (1.0f - a.sustain_level) / (nanos_as_secs_f32(a.decay_nanos) * (float)sr);
+  gp.sustain_level = a.sustain_level;
+  float rt = nanos_as_secs_f32(a.release_nanos);
+  gp.release_is_zero = a.release_nanos == 0;
+  gp.release_rate = rt == 0.0f ? F32_MAX : 1.0f / (rt * (float)sr);
+  gp.attack_scaling = a.attack_scaling; gp.decay_scaling = a.decay_scaling; gp.release_scaling = a.release_scaling;
+  gp.has_env = 1;
+  return true;
+}
+
+int sync_state_to_host(pb200_renderer* r) {
+  if (r->host_state_valid) return PB200_OK;
+  r->h_voices.resize(r->dev_n_voices);
+  r->h_gstate.resize(r->dev_n_groups);
+  r->h_mstate.resize(r->dev_n_mixers);
+  r->h_fx.resize(r->dev_n_fx);
+  r->h_fx_state.resize(r->dev_fx_state_bytes);
+  CUDA_TRY(r->d_voices.download(r->h_voices, r->sm));
+  CUDA_TRY(r->d_gstate.download(r->h_gstate, r->sm));
+  CUDA_TRY(r->d_mstate.download(r->h_mstate, r->sm));
+  CUDA_TRY(r->d_fx.download(r->h_fx, r->sm));
+  CUDA_TRY(r->d_fx_state.download(r->h_fx_state, r->sm));
+  if (r->master_uploaded) CUDA_TRY(cudaMemcpyAsync(&r->h_master, r->d_master.p, sizeof(ExpSm), cudaMemcpyDeviceToHost, r->sm));
+  CUDA_TRY(cudaStreamSynchronize(r->sm));
+  r->host_state_valid = true;
+  return PB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pb200_backend(void) { return "cuda sm_100a: hand-written voice/mixer/effect kernels (no CPU fallback)"; }
+
+int pb200_create(const pb200_config* config, pb200_renderer** out) {
+  if (!config || !out) return PB200_ERR_PARAMETER;
+  if (config->channel_count != 2 || config->sample_rate == 0) return PB200_ERR_PARAMETER;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    fprintf(stderr, "phonic_b200: no CUDA device available -- this renderer has no CPU fallback\n");
+    return PB200_ERR_CUDA;
+  }
+  auto* r = new pb200_renderer();
+  r->cfg = *config;
+  if (r->cfg.block_frames == 0) r->cfg.block_frames = 1024;
+  if (config->device_ordinal >= 0) {
+    if (config->device_ordinal >= n || cudaSetDevice(config->device_ordinal) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+    r->device = config->device_ordinal;
+  } else {
+    cudaGetDevice(&r->device);
+  }
+  if (cudaStreamCreateWithFlags(&r->sv, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&r->sm, cudaStreamNonBlocking) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+  r->rc.sample_rate = config->sample_rate;
+  r->rc.rate_comp = 44100.0f / (float)config->sample_rate;
+  HostMixer main;
+  main.public_id = 0; main.parent = 0xFFFFFFFFu; main.depth = 0;
+  r->mixers.push_back(main);
+  r->mixer_by_id[0] = 0;
+  r->h_mstate.push_back(MixerState{0, 1, 0});
+  r->h_master = ExpSm{config->master_volume, config->master_volume};
+  if (const char* tb = getenv("PB200_TIME_BLOCK")) {
+    long v = atol(tb);
+    if (v >= (long)r->cfg.block_frames) r->time_block = (uint32_t)(v / r->cfg.block_frames) * r->cfg.block_frames;
+  }
+  r->time_block = std::max(r->time_block / r->cfg.block_frames, 1u) * r->cfg.block_frames;
+  *out = r;
+  return PB200_OK;
+}
+
+void pb200_destroy(pb200_renderer* r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  cudaDeviceSynchronize();
+  for (auto& b : r->buffers) cudaFree((void*)b.dev.data);
+  r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
+  r->d_mixers.free(); r->d_mstate.free(); r->d_child_index.free(); r->d_source_index.free(); r->d_level_mixers.free();
+  r->d_class_groups.free(); r->d_fx.free(); r->d_fx_events.free(); r->d_fx_state.free(); r->d_aux.free();
+  r->d_bounds.free(); r->d_chunk_begin.free(); r->d_group_bus.free(); r->d_mixer_bus.free(); r->d_out.free();
+  r->d_group_flags.free(); r->d_mixer_flags.free(); r->d_master.free();
+  if (r->sv) cudaStreamDestroy(r->sv);
+  if (r->sm) cudaStreamDestroy(r->sm);
+  delete r;
+}
+
+const char* pb200_last_error(const pb200_renderer* r) { return r ? r->last_error.c_str() : ""; }
+
+int pb200_upload_buffer(pb200_renderer* r, const float* data, uint64_t frames, uint32_t ch, uint32_t rate,
+                        int64_t loop_start, int64_t loop_end, int add_pad_frame, uint32_t* buffer_id) {
+  if (!r || !data || !buffer_id) return PB200_ERR_PARAMETER;
+  if (rate == 0) return fail(r, PB200_ERR_PARAMETER, "file buffer sample rate must be > 0");
+  if (ch == 0) return fail(r, PB200_ERR_PARAMETER, "file buffer channel count must be > 0");
+  if (frames == 0) return fail(r, PB200_ERR_PARAMETER, "file buffer must not be empty");
+  if (ch > 2) return fail(r, PB200_ERR_UNSUPPORTED, "only mono and stereo buffers are supported");
+  uint64_t total_frames = frames + (add_pad_frame ? 1 : 0);
+  if (total_frames * ch >= 0xFFFFFFF0ull) return fail(r, PB200_ERR_UNSUPPORTED, "buffer too large");
+  HostBuffer hb;
+  std::memset(&hb, 0, sizeof(hb));
+  hb.dev.loop_start = -1; hb.dev.loop_end = -1;
+  if (loop_start >= 0 && loop_end >= 0) {
+    if (loop_start >= loop_end || (uint64_t)loop_end > total_frames) return fail(r, PB200_ERR_PARAMETER, "file buffer loop range is out of bounds");
+    hb.dev.loop_start = (int32_t)loop_start; hb.dev.loop_end = (int32_t)loop_end;
+  }
+  cudaSetDevice(r->device);
+  float* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, total_frames * ch * sizeof(float)));
+  CUDA_TRY(cudaMemsetAsync(d, 0, total_frames * ch * sizeof(float), r->sm));
+  CUDA_TRY(cudaMemcpyAsync(d, data, frames * ch * sizeof(float), cudaMemcpyHostToDevice, r->sm));
+  CUDA_TRY(cudaStreamSynchronize(r->sm));
+  hb.dev.data = d;
+  hb.dev.n_samples = (uint32_t)(total_frames * ch);
+  hb.dev.channels = ch;
+  hb.dev.sample_rate = rate;
+  r->buffers.push_back(hb);
+  r->graph_dirty = true;
+  *buffer_id = (uint32_t)r->buffers.size() - 1;
+  return PB200_OK;
+}
+
+int pb200_add_mixer(pb200_renderer* r, uint32_t parent, uint32_t* mixer_id) {
+  if (!r || !mixer_id) return PB200_ERR_PARAMETER;
+  auto it = r->mixer_by_id.find(parent);
+  if (it == r->mixer_by_id.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  if (int e = sync_state_to_host(r)) return e;
+  HostMixer m;
+  m.public_id = r->next_mixer_id++;
+  m.parent = it->second;
+  m.depth = r->mixers[it->second].depth + 1;
+  uint32_t dense = (uint32_t)r->mixers.size();
+  r->mixers.push_back(m);
+  r->mixers[it->second].children.push_back(dense);
+  r->mixer_by_id[m.public_id] = dense;
+  r->h_mstate.push_back(MixerState{0, 1, 0});
+  r->graph_dirty = true;
+  *mixer_id = m.public_id;
+  return PB200_OK;
+}
+
+int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const void* params, size_t size, uint32_t* effect_id) {
+  if (!r || !effect_id) return PB200_ERR_PARAMETER;
+  auto it = r->mixer_by_id.find(mixer);
+  if (it == r->mixer_by_id.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  const uint32_t sr = r->cfg.sample_rate;
+  pbh::FxBuild b;
+  switch (kind) {
+    case PB200_FX_FILTER:
+      if (params && size != sizeof(pb200_filter_params)) return fail(r, PB200_ERR_PARAMETER, "bad filter params size");
+      b = pbh::build_filter((const pb200_filter_params*)params, sr);
+      break;
+    case PB200_FX_EQ5:
+      if (params) return fail(r, PB200_ERR_PARAMETER, "Eq5Effect has no parameter constructor");
+      b = pbh::build_eq5(sr);
+      break;
+    case PB200_FX_COMPRESSOR:
+      if (params && size != sizeof(pb200_compressor_params)) return fail(r, PB200_ERR_PARAMETER, "bad compressor params size");
+      b = pbh::build_compressor((const pb200_compressor_params*)params, sr);
+      break;
+    case PB200_FX_CHORUS:
+      if (params && size != sizeof(pb200_chorus_params)) return fail(r, PB200_ERR_PARAMETER, "bad chorus params size");
+      b = pbh::build_chorus((const pb200_chorus_params*)params, sr);
+      break;
+    case PB200_FX_DELAY:
+      if (params) return fail(r, PB200_ERR_PARAMETER, "DelayEffect has no parameter constructor");
+      b = pbh::build_delay(sr);
+      break;
+    case PB200_FX_REVERB:
+      if (!params || size != sizeof(pb200_reverb_params)) return fail(r, PB200_ERR_PARAMETER, "reverb needs explicit fpd/vib_phase state");
+      b = pbh::build_reverb((const pb200_reverb_params*)params, sr);
+      break;
+    default: return fail(r, PB200_ERR_PARAMETER, "unknown effect kind");
+  }
+  if (b.code) return fail(r, b.code, b.error);
+  if (r->mixers[it->second].effects.size() >= (size_t)MAX_EFFECTS_PER_MIXER) return fail(r, PB200_ERR_PARAMETER, "too many effects on one mixer");
+  if (int e = sync_state_to_host(r)) return e;
+  // device aux arena is append-only: rebase this effect's delay lines behind everything allocated so far
+  size_t aux_base = (r->aux_doubles + 1) & ~size_t(1);
+  if (aux_base + b.aux_doubles >= 0xFFFFFFF0ull) return fail(r, PB200_ERR_UNSUPPORTED, "effect delay storage exceeds 32 GiB");
+  pbh::rebase_aux(kind, b.state, (uint32_t)aux_base);
+  r->aux_doubles = aux_base + b.aux_doubles;
+  FxHeader h;
+  std::memset(&h, 0, sizeof(h));
+  h.kind = kind;
+  h.bypassed = 1;                     // EffectProcessor::new (mixed/effect.rs:23-30)
+  h.tail_counter = 0;
+  h.silence_counter = UINT64_MAX;
+  size_t off = (r->h_fx_state.size() + 15) & ~size_t(15);
+  r->h_fx_state.resize(off + b.state.size());
+  std::memcpy(r->h_fx_state.data() + off, b.state.data(), b.state.size());
+  h.state_offset = (uint32_t)off;
+  h.aux_offset = (uint32_t)aux_base;
+  HostFx fx;
+  fx.public_id = r->next_effect_id++;
+  fx.kind = kind;
+  fx.mixer = it->second;
+  uint32_t dense = (uint32_t)r->fxs.size();
+  r->fxs.push_back(fx);
+  r->h_fx.push_back(h);
+  r->mixers[it->second].effects.push_back(dense);
+  r->h_mstate[it->second].effects_bypassed = 0;  // AddEffect (mixed.rs:430-431)
+  r->fx_by_id[fx.public_id] = dense;
+  r->graph_dirty = true;
+  *effect_id = fx.public_id;
+  return PB200_OK;
+}
+
+void pb200_file_options_default(pb200_file_options* o) {
+  if (!o) return;
+  o->volume = 1.0f; o->panning = 0.0f; o->speed = 1.0; o->repeat = PB200_REPEAT_DEFAULT;
+  o->loop_start = PB200_NO_LOOP; o->loop_end = PB200_NO_LOOP;
+  o->fade_in_nanos = PB200_DURATION_NONE; o->fade_out_nanos = 50000000ull;
+  o->resampling_quality = 0; o->target_mixer = PB200_MAIN_MIXER;
+}
+
+static int validate_vol_pan(pb200_renderer* r, float volume, float panning) {
+  if (volume < 0.0f || std::isnan(volume)) return fail(r, PB200_ERR_PARAMETER, "playback options 'volume' value is invalid");
+  if (!(panning >= -1.0f && panning <= 1.0f)) return fail(r, PB200_ERR_PARAMETER, "playback options 'panning' value is invalid");
+  return PB200_OK;
+}
+
+// insert a source into the mixer's playing_sources keeping the reference's order
+// (partition_point(start_time < t): new sources go *before* equal start times, mixed.rs:324-340)
+static void insert_source(pb200_renderer* r, uint32_t mixer, uint32_t group, uint64_t start) {
+  auto& v = r->mixers[mixer].sources;
+  size_t pos = 0;
+  while (pos < v.size() && r->groups[v[pos]].gp.start_time < start) ++pos;
+  v.insert(v.begin() + pos, group);
+}
+
+int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_options* o, uint64_t start_time, uint32_t* playback_id) {
+  if (!r || !o || !playback_id) return PB200_ERR_PARAMETER;
+  if (buffer_id >= r->buffers.size()) return fail(r, PB200_ERR_PARAMETER, "unknown buffer");
+  if (int e = validate_vol_pan(r, o->volume, o->panning)) return e;
+  if (o->speed < 0.0 || std::isnan(o->speed) || std::isinf(o->speed)) return fail(r, PB200_ERR_PARAMETER, "playback options 'speed' value is invalid");
+  if (o->resampling_quality != 0) return fail(r, PB200_ERR_UNSUPPORTED, "HighQuality (sinc) resampling is not rendered on device yet");
+  auto mit = r->mixer_by_id.find(o->target_mixer);
+  if (mit == r->mixer_by_id.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  if (int e = sync_state_to_host(r)) return e;
+  const DevBuffer& b = r->buffers[buffer_id].dev;
+  const uint32_t sr = r->cfg.sample_rate;
+  HostGroup g;
+  std::memset(&g.gp, 0, sizeof(g.gp));
+  g.public_id = r->next_source_id++;
+  g.gp.kind = GROUP_FILE;
+  g.gp.first_voice = (uint32_t)r->h_voices.size();
+  g.gp.n_voices = 1;
+  g.gp.buffer = buffer_id;
+  g.gp.mixer = mit->second;
+  g.gp.transient = 1;
+  g.gp.start_time = start_time == PB200_TIME_NOW ? 0 : start_time;
+  g.gp.has_fade_out = (o->fade_out_nanos != PB200_DURATION_NONE && o->fade_out_nanos != 0) ? 1 : 0;
+  if (g.gp.has_fade_out) g.gp.fade_out_inertia = fader_inertia(sr, o->fade_out_nanos);
+  g.gp.base_volume = 1.0f;
+  VoiceState v = default_voice(b, sr, o->speed);
+  // PreloadedFileSource::from_shared_buffer (preloaded.rs:72-115)
+  if (o->repeat != PB200_REPEAT_DEFAULT) v.repeat = o->repeat == PB200_REPEAT_FOREVER ? REPEAT_FOREVER : (uint32_t)std::min<uint64_t>(o->repeat, 0xFFFFFFFEull);
+  v.repeat_count = v.repeat;
+  if (o->loop_start >= 0 && o->loop_end >= 0) {
+    uint64_t fc = b.n_samples / b.channels;
+    v.loop_ovr_start = (int32_t)std::min<uint64_t>((uint64_t)o->loop_start, fc > 0 ? fc - 1 : 0);
+    v.loop_ovr_end = (int32_t)std::min<uint64_t>((uint64_t)o->loop_end, fc);
+  }
+  if (o->fade_in_nanos != PB200_DURATION_NONE && o->fade_in_nanos != 0) {  // start_fade_in (fader.rs:60-66)
+    v.fader_state = FADER_RUNNING; v.fader_cur = 0.0f; v.fader_tgt = 1.0f;
+    v.fader_inertia = fader_inertia(sr, o->fade_in_nanos);
+  }
+  v.vol = ExpSm{o->volume, o->volume};
+  v.pan = ExpSm{o->panning, o->panning};
+  v.has_note = 1;  // a file playback is one always-active voice
+  r->h_voices.push_back(v);
+  GroupState gs;
+  std::memset(&gs, 0, sizeof(gs));
+  gs.vol = ExpSm{1.0f, 1.0f};
+  r->h_gstate.push_back(gs);
+  uint32_t dense = (uint32_t)r->groups.size();
+  r->groups.push_back(g);
+  insert_source(r, mit->second, dense, g.gp.start_time);
+  r->group_by_id[g.public_id] = dense;
+  r->graph_dirty = true;
+  *playback_id = g.public_id;
+  return PB200_OK;
+}
+
+void pb200_sampler_options_default(pb200_sampler_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->volume = 1.0f; o->panning = 0.0f; o->voices = 8; o->target_mixer = PB200_MAIN_MIXER;
+  o->ahdsr.attack_nanos = 10000000ull; o->ahdsr.hold_nanos = 1000000000ull; o->ahdsr.decay_nanos = 500000000ull;
+  o->ahdsr.release_nanos = 1000000000ull; o->ahdsr.sustain_level = 0.75f;
+}
+
+int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler_options* o, uint64_t start_time, uint32_t* generator_id) {
+  if (!r || !o || !generator_id) return PB200_ERR_PARAMETER;
+  if (buffer_id >= r->buffers.size()) return fail(r, PB200_ERR_PARAMETER, "unknown buffer");
+  if (int e = validate_vol_pan(r, o->volume, o->panning)) return e;
+  if (o->voices == 0) return fail(r, PB200_ERR_PARAMETER, "playback options voice count is '0'");
+  if (o->voices > (uint32_t)VK_MAX_VOICES) return fail(r, PB200_ERR_UNSUPPORTED, "more than 1024 voices per sampler");
+  auto mit = r->mixer_by_id.find(o->target_mixer);
+  if (mit == r->mixer_by_id.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  if (int e = sync_state_to_host(r)) return e;
+  const DevBuffer& b = r->buffers[buffer_id].dev;
+  const uint32_t sr = r->cfg.sample_rate;
+  HostGroup g;
+  std::memset(&g.gp, 0, sizeof(g.gp));
+  g.public_id = r->next_source_id++;
+  g.gp.kind = GROUP_SAMPLER;
+  g.gp.first_voice = (uint32_t)r->h_voices.size();
+  g.gp.n_voices = o->voices;
+  g.gp.buffer = buffer_id;
+  g.gp.mixer = mit->second;
+  g.gp.transient = o->transient ? 1 : 0;
+  g.gp.start_time = start_time == PB200_TIME_NOW ? 0 : start_time;
+  g.gp.has_fade_out = 1;  // sampler voices: fade_out_duration = 50 ms (sampler.rs:513-514)
+  g.gp.fade_out_inertia = fader_inertia(sr, 50000000ull);
+  g.gp.base_volume = 1.0f; g.gp.base_panning = 0.0f;
+  if (o->has_ahdsr && !resolve_ahdsr(o->ahdsr, sr, g.gp)) return fail(r, PB200_ERR_PARAMETER, "Invalid AHDSR parameters");
+  for (uint32_t i = 0; i < o->voices; ++i) r->h_voices.push_back(default_voice(b, sr, 1.0));
+  GroupState gs;
+  std::memset(&gs, 0, sizeof(gs));
+  gs.vol = ExpSm{o->volume, o->volume};
+  gs.pan = ExpSm{o->panning, o->panning};
+  r->h_gstate.push_back(gs);
+  uint32_t dense = (uint32_t)r->groups.size();
+  r->groups.push_back(g);
+  insert_source(r, mit->second, dense, g.gp.start_time);
+  r->group_by_id[g.public_id] = dense;
+  r->graph_dirty = true;
+  *generator_id = g.public_id;
+  return PB200_OK;
+}
+
+int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
+  if (!r || !ev) return PB200_ERR_PARAMETER;
+  const bool now = ev->sample_time == PB200_TIME_NOW;
+  if (ev->kind == PB200_EV_SET_EFFECT_PARAMETER) {
+    auto it = r->fx_by_id.find(ev->target);
+    if (it == r->fx_by_id.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+    HostFx& fx = r->fxs[it->second];
+    const pbh::ParamDesc* desc = nullptr;
+    for (auto& d : pbh::param_table(fx.kind)) if (d.id == ev->param_id) desc = &d;
+    if (!desc) return fail(r, PB200_ERR_PARAMETER, "Unknown parameter for effect");
+    FxParamEvent pe;
+    std::memset(&pe, 0, sizeof(pe));
+    pe.time = now ? 0 : ev->sample_time;  // handles/effect.rs:80: None => 0
+    pe.param_id = ev->param_id;
+    pe.value = pbh::resolve_plain(*desc, ev->value, (ev->flags & PB200_EVF_NORMALIZED) != 0);
+    if (fx.kind == FX_DELAY && ev->param_id == pbh::cc4("lfos") && pe.value >= 5.0f)
+      return fail(r, PB200_ERR_UNSUPPORTED, "OS-seeded random LFO shapes are not reproducible");
+    fx.events.push_back(pe);
+    fx.seqs.push_back(r->next_seq++);
+    r->graph_dirty = true;
+    return PB200_OK;
+  }
+  auto git = r->group_by_id.find(ev->target);
+  if (git == r->group_by_id.end()) return fail(r, PB200_ERR_SOURCE_NOT_PLAYING, "Source is no longer playing");
+  HostGroup& g = r->groups[git->second];
+  const bool is_sampler = g.gp.kind == GROUP_SAMPLER;
+  const DevBuffer& b = r->buffers[g.gp.buffer].dev;
+  DevEvent de;
+  std::memset(&de, 0, sizeof(de));
+  de.time = now ? r->position : ev->sample_time;
+  de.glide = ev->glide;
+  switch (ev->kind) {
+    case PB200_EV_STOP_SOURCE:
+      if (!now) {  // MixerMessage::StopSource -> PlayingSource::stop_time (mixed.rs:388-399)
+        if (int e = sync_state_to_host(r)) return e;
+        r->h_gstate[git->second].has_stop_time = 1;
+        r->h_gstate[git->second].stop_time = ev->sample_time;
+        r->graph_dirty = true;
+        return PB200_OK;
+      }
+      de.kind = EVK_STOP;
+      break;
+    case PB200_EV_SET_SOURCE_VOLUME: de.kind = EVK_SET_VOLUME; de.value = ev->value; break;
+    case PB200_EV_SET_SOURCE_PANNING: de.kind = EVK_SET_PANNING; de.value = ev->value; break;
+    case PB200_EV_SET_SOURCE_SPEED:
+      if (is_sampler) return fail(r, PB200_ERR_PARAMETER, "set_speed needs a file source");
+      de.kind = EVK_SET_SPEED; de.speed = ev->speed;
+      break;
+    case PB200_EV_SEEK_SOURCE: {
+      if (is_sampler) return fail(r, PB200_ERR_PARAMETER, "seek needs a file source");
+      de.kind = EVK_SEEK;
+      double pos = nanos_as_secs_f64(ev->position_nanos) * (double)b.sample_rate * (double)b.channels;  // preloaded.rs:140-143
+      uint64_t p = !(pos > 0.0) ? 0 : (pos >= 1.8446744073709552e19 ? UINT64_MAX : (uint64_t)pos);
+      de.seek_pos = (uint32_t)std::min<uint64_t>(p, b.n_samples);
+      break;
+    }
+    case PB200_EV_NOTE_ON:
+      if (!is_sampler) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+      de.kind = EVK_NOTE_ON;
+      ev->note_id = r->next_note_id++;
+      de.note_id = ev->note_id;
+      de.note = ev->note & 0xFF;
+      de.value = (ev->flags & PB200_EVF_HAS_VOLUME) ? ev->value : 1.0f;
+      de.value2 = (ev->flags & PB200_EVF_HAS_PANNING) ? ev->value2 : 0.0f;
+      // voice.rs:144-148: note speed * 2^(transpose/12 + finetune/1200), base transpose/finetune = 0
+      de.speed = speed_from_note_h(ev->note) * std::pow(2.0, 0.0 / 12.0 + 0.0 / 1200.0);
+      break;
+    case PB200_EV_NOTE_OFF: de.kind = EVK_NOTE_OFF; de.note_id = ev->note_id; break;
+    case PB200_EV_ALL_NOTES_OFF: de.kind = EVK_ALL_NOTES_OFF; break;
+    case PB200_EV_SET_NOTE_SPEED:
+      de.kind = EVK_NOTE_SPEED; de.note_id = ev->note_id;
+      de.speed = ev->speed * std::pow(2.0, 0.0 / 12.0 + 0.0 / 1200.0);
+      break;
+    case PB200_EV_SET_NOTE_VOLUME: de.kind = EVK_NOTE_VOLUME; de.note_id = ev->note_id; de.value = ev->value; break;
+    case PB200_EV_SET_NOTE_PANNING: de.kind = EVK_NOTE_PANNING; de.note_id = ev->note_id; de.value = ev->value; break;
+    default: return fail(r, PB200_ERR_PARAMETER, "unknown event kind");
+  }
+  if (de.kind >= EVK_NOTE_ON && !is_sampler) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+  HostEvent he;
+  he.ev = de;
+  he.seq = r->next_seq++;
+  // immediate messages do not split mixer chunks; mark them so the schedule compiler skips them
+  he.ev.flags = now ? 1u : 0u;
+  g.events.push_back(he);
+  r->graph_dirty = true;
+  return PB200_OK;
+}
+
+uint64_t pb200_position(const pb200_renderer* r) { return r ? r->position : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// compile + render
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct SizeClass { uint32_t threads; uint32_t tile; std::vector<uint32_t> groups; size_t smem; };
+
+struct Compiled {
+  std::vector<std::vector<uint32_t>> levels;  // mixers per depth
+  std::vector<SizeClass> classes;
+  uint32_t max_chunks = 1;
+  std::vector<uint32_t> level_offsets, class_offsets;
+};
+
+int upload_graph(pb200_renderer* r, Compiled& c) {
+  // drop consumed events, then flatten per-group / per-effect event lists (stable by time)
+  std::vector<DevEvent> events;
+  std::vector<GroupParams> gparams(r->groups.size());
+  for (size_t gi = 0; gi < r->groups.size(); ++gi) {
+    HostGroup& g = r->groups[gi];
+    uint32_t consumed = r->h_gstate[gi].ev_cursor - g.gp.ev_begin;
+    if (consumed) { g.events.erase(g.events.begin(), g.events.begin() + std::min<size_t>(consumed, g.events.size())); r->h_gstate[gi].ev_cursor = 0; }
+    std::stable_sort(g.events.begin(), g.events.end(), [](const HostEvent& a, const HostEvent& b) { return a.ev.time < b.ev.time; });
+    g.gp.ev_begin = (uint32_t)events.size();
+    for (auto& e : g.events) events.push_back(e.ev);
+    g.gp.ev_end = (uint32_t)events.size();
+    gparams[gi] = g.gp;
+  }
+  // GroupState::ev_cursor is absolute into the flattened array
+  for (size_t gi = 0; gi < r->groups.size(); ++gi) r->h_gstate[gi].ev_cursor = r->groups[gi].gp.ev_begin;
+  std::vector<FxParamEvent> fx_events;
+  for (size_t fi = 0; fi < r->fxs.size(); ++fi) {
+    HostFx& fx = r->fxs[fi];
+    FxHeader& h = r->h_fx[fi];
+    uint32_t consumed = h.ev_cursor - h.ev_begin;
+    if (consumed) { fx.events.erase(fx.events.begin(), fx.events.begin() + std::min<size_t>(consumed, fx.events.size())); }
+    std::stable_sort(fx.events.begin(), fx.events.end(), [](const FxParamEvent& a, const FxParamEvent& b) { return a.time < b.time; });
+    h.ev_begin = (uint32_t)fx_events.size();
+    for (auto& e : fx.events) fx_events.push_back(e);
+    h.ev_end = (uint32_t)fx_events.size();
+    h.ev_cursor = h.ev_begin;
+  }
+  // mixers
+  std::vector<MixerParams> mparams(r->mixers.size());
+  std::vector<uint32_t> child_index, source_index;
+  std::vector<FxHeader> fx_sorted;  // FxHeader array must be contiguous per mixer in chain order
+  std::vector<uint32_t> fx_perm;    // new position -> old dense index
+  uint32_t max_depth = 0;
+  for (size_t mi = 0; mi < r->mixers.size(); ++mi) {
+    const HostMixer& m = r->mixers[mi];
+    MixerParams& p = mparams[mi];
+    std::memset(&p, 0, sizeof(p));
+    p.parent = m.parent; p.depth = m.depth;
+    p.child_begin = (uint32_t)child_index.size();
+    for (uint32_t ch : m.children) child_index.push_back(ch);
+    p.child_end = (uint32_t)child_index.size();
+    p.src_begin = (uint32_t)source_index.size();
+    for (uint32_t s : m.sources) source_index.push_back(s);
+    p.src_end = (uint32_t)source_index.size();
+    p.fx_begin = (uint32_t)fx_perm.size();
+    for (uint32_t f : m.effects) fx_perm.push_back(f);
+    p.fx_end = (uint32_t)fx_perm.size();
+    max_depth = std::max(max_depth, m.depth);
+  }
+  // permute fx headers into chain order (and remember the permutation for later syncs)
+  {
+    std::vector<FxHeader> nh(fx_perm.size());
+    std::vector<HostFx> nf(fx_perm.size());
+    std::vector<uint32_t> inv(fx_perm.size());
+    for (size_t i = 0; i < fx_perm.size(); ++i) { nh[i] = r->h_fx[fx_perm[i]]; nf[i] = r->fxs[fx_perm[i]]; inv[fx_perm[i]] = (uint32_t)i; }
+    r->h_fx.swap(nh); r->fxs.swap(nf);
+    for (auto& kv : r->fx_by_id) kv.second = inv[kv.second];
+    for (auto& m : r->mixers) for (auto& f : m.effects) f = inv[f];
+  }
+  c.levels.assign(max_depth + 1, {});
+  for (size_t mi = 0; mi < r->mixers.size(); ++mi) c.levels[r->mixers[mi].depth].push_back((uint32_t)mi);
+  std::vector<uint32_t> level_mixers;
+  c.level_offsets.clear();
+  for (auto& l : c.levels) { c.level_offsets.push_back((uint32_t)level_mixers.size()); for (uint32_t m : l) level_mixers.push_back(m); }
+  // voice kernel size classes
+  const uint32_t class_threads[6] = {32, 64, 128, 256, 512, 1024};
+  c.classes.clear();
+  for (int ci = 0; ci < 6; ++ci) {
+    SizeClass sc;
+    sc.threads = class_threads[ci];
+    uint32_t lo = ci == 0 ? 0 : class_threads[ci - 1];
+    for (size_t gi = 0; gi < r->groups.size(); ++gi) {
+      uint32_t nv = r->groups[gi].gp.n_voices;
+      if (nv > lo && nv <= sc.threads) sc.groups.push_back((uint32_t)gi);
+    }
+    if (sc.groups.empty()) continue;
+    // tile: as many frames as fit ~96 KB of shared memory, power of two in [2, 32]
+    uint32_t tile = 32;
+    while (tile > 2 && (size_t)sc.threads * tile * 2 * sizeof(float) > 96 * 1024) tile >>= 1;
+    sc.tile = tile;
+    sc.smem = (size_t)sc.threads * tile * 2 * sizeof(float);
+    c.classes.push_back(sc);
+  }
+  std::vector<uint32_t> class_groups;
+  c.class_offsets.clear();
+  for (auto& sc : c.classes) { c.class_offsets.push_back((uint32_t)class_groups.size()); for (uint32_t g : sc.groups) class_groups.push_back(g); }
+
+  std::vector<DevBuffer> bufs;
+  for (auto& b : r->buffers) bufs.push_back(b.dev);
+  cudaStream_t s = r->sm;
+  CUDA_TRY(r->d_buffers.upload(bufs, s));
+  CUDA_TRY(r->d_groups.upload(gparams, s));
+  CUDA_TRY(r->d_events.upload(events, s));
+  CUDA_TRY(r->d_mixers.upload(mparams, s));
+  CUDA_TRY(r->d_child_index.upload(child_index, s));
+  CUDA_TRY(r->d_source_index.upload(source_index, s));
+  CUDA_TRY(r->d_level_mixers.upload(level_mixers, s));
+  CUDA_TRY(r->d_class_groups.upload(class_groups, s));
+  CUDA_TRY(r->d_fx_events.upload(fx_events, s));
+  // state
+  CUDA_TRY(r->d_voices.upload(r->h_voices, s));
+  CUDA_TRY(r->d_gstate.upload(r->h_gstate, s));
+  CUDA_TRY(r->d_mstate.upload(r->h_mstate, s));
+  CUDA_TRY(r->d_fx.upload(r->h_fx, s));
+  CUDA_TRY(r->d_fx_state.upload(r->h_fx_state, s));
+  std::vector<ExpSm> master{r->h_master};
+  CUDA_TRY(r->d_master.upload(master, s));
+  r->master_uploaded = true;
+  // aux arena: grow preserving contents, zero the new tail
+  if (r->aux_doubles > r->d_aux.cap) {
+    double* np = nullptr;
+    size_t ncap = r->aux_doubles + 1024;
+    CUDA_TRY(cudaMalloc(&np, ncap * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(np, 0, ncap * sizeof(double), s));
+    if (r->d_aux.p) {
+      CUDA_TRY(cudaMemcpyAsync(np, r->d_aux.p, r->d_aux_used * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      cudaFree(r->d_aux.p);
+    }
+    r->d_aux.p = np; r->d_aux.cap = ncap;
+  }
+  r->d_aux_used = r->aux_doubles;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  r->dev_n_voices = r->h_voices.size(); r->dev_n_groups = r->h_gstate.size(); r->dev_n_mixers = r->h_mstate.size();
+  r->dev_n_fx = r->h_fx.size(); r->dev_fx_state_bytes = r->h_fx_state.size();
+  r->graph_dirty = false;
+  return PB200_OK;
+}
+
+// the reference's exact chunk boundaries per mixer for [p0, p1): 1024-frame WavStream blocks, split at
+// every pending event time of the mixer itself and of all its ancestors (mixed.rs:679-693)
+void compile_schedule(pb200_renderer* r, uint64_t p0, uint64_t p1, uint32_t tb, std::vector<uint64_t>& bounds,
+                      std::vector<uint32_t>& begin, uint32_t& n_blocks, uint32_t& max_chunks) {
+  const size_t nm = r->mixers.size();
+  std::vector<std::vector<uint64_t>> per_mixer(nm);
+  std::vector<std::vector<uint64_t>> own(nm);
+  for (auto& g : r->groups)
+    for (auto& e : g.events)
+      if (!(e.ev.flags & 1u) && e.ev.time > p0 && e.ev.time < p1) own[g.gp.mixer].push_back(e.ev.time);
+  for (auto& fx : r->fxs)
+    for (auto& e : fx.events)
+      if (e.time > p0 && e.time < p1) own[fx.mixer].push_back(e.time);
+  std::vector<uint32_t> order(nm);
+  for (size_t i = 0; i < nm; ++i) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return r->mixers[a].depth < r->mixers[b].depth; });
+  for (uint32_t mi : order) {
+    std::vector<uint64_t>& v = per_mixer[mi];
+    if (r->mixers[mi].parent == 0xFFFFFFFFu) {
+      for (uint64_t t = p0; t <= p1; t += r->cfg.block_frames) v.push_back(t);
+    } else {
+      v = per_mixer[r->mixers[mi].parent];
+    }
+    v.insert(v.end(), own[mi].begin(), own[mi].end());
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+  }
+  n_blocks = (uint32_t)((p1 - p0 + tb - 1) / tb);
+  bounds.clear();
+  begin.assign((size_t)n_blocks * (nm + 1), 0);
+  max_chunks = 1;
+  std::vector<size_t> cursor(nm, 0);
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    const uint64_t b0 = p0 + (uint64_t)b * tb, b1 = std::min<uint64_t>(b0 + tb, p1);
+    for (size_t mi = 0; mi < nm; ++mi) {
+      begin[(size_t)b * (nm + 1) + mi] = (uint32_t)bounds.size();
+      const auto& v = per_mixer[mi];
+      size_t& cu = cursor[mi];
+      while (cu < v.size() && v[cu] < b0) ++cu;
+      size_t first = bounds.size();
+      size_t i = cu;
+      while (i < v.size() && v[i] <= b1) bounds.push_back(v[i++]);
+      max_chunks = std::max<uint32_t>(max_chunks, (uint32_t)(bounds.size() - first));
+    }
+    begin[(size_t)b * (nm + 1) + nm] = (uint32_t)bounds.size();
+  }
+}
+
+int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t frames, uint64_t* frames_written) {
+  const uint32_t bf = r->cfg.block_frames;
+  if (frames % bf != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
+  if (frames == 0) { if (frames_written) *frames_written = 0; return PB200_OK; }
+  cudaSetDevice(r->device);
+  // WavStream finishes when the main mixer has nothing at all to do (wav.rs:231-234, mixed.rs:664-670)
+  if (r->groups.empty() && r->fxs.empty() && r->mixers.size() == 1) r->finished = true;
+  if (r->finished) {
+    if (out_host) std::memset(out_host, 0, frames * 2 * sizeof(float));
+    if (out_dev) CUDA_TRY(cudaMemsetAsync(out_dev, 0, frames * 2 * sizeof(float), r->sm));
+    if (out_dev) CUDA_TRY(cudaStreamSynchronize(r->sm));
+    if (frames_written) *frames_written = 0;
+    return PB200_OK;
+  }
+  Compiled c;
+  if (int e = sync_state_to_host(r)) return e;
+  // (events and cursors live on the host between render calls: always rebuild the flattened lists)
+  if (int e = upload_graph(r, c)) return e;
+
+  const uint64_t p0 = r->position, p1 = p0 + frames;
+  const uint32_t tb = r->time_block;
+  std::vector<uint64_t> bounds;
+  std::vector<uint32_t> begin;
+  uint32_t n_blocks = 0, max_chunks = 1;
+  compile_schedule(r, p0, p1, tb, bounds, begin, n_blocks, max_chunks);
+  CUDA_TRY(r->d_bounds.upload(bounds, r->sm));
+  CUDA_TRY(r->d_chunk_begin.upload(begin, r->sm));
+  const size_t ng = r->groups.size(), nm = r->mixers.size();
+  CUDA_TRY(r->d_group_bus.reserve(std::max<size_t>(1, (size_t)RING * ng * tb * 2)));
+  CUDA_TRY(r->d_mixer_bus.reserve((size_t)RING * nm * tb * 2));
+  CUDA_TRY(r->d_group_flags.reserve(std::max<size_t>(1, (size_t)RING * ng * max_chunks)));
+  CUDA_TRY(r->d_mixer_flags.reserve((size_t)RING * nm * max_chunks));
+  float* dout = out_dev;
+  if (!dout) { CUDA_TRY(r->d_out.reserve(frames * 2)); dout = r->d_out.p; }
+  CUDA_TRY(cudaStreamSynchronize(r->sm));
+
+  CUDA_TRY(cudaFuncSetAttribute(voice_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(voice_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+
+  std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_m1(n_blocks);
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    CUDA_TRY(cudaEventCreate(&ev_v0[b])); CUDA_TRY(cudaEventCreate(&ev_v1[b])); CUDA_TRY(cudaEventCreate(&ev_m1[b]));
+  }
+  cudaEvent_t ev_start, ev_end;
+  CUDA_TRY(cudaEventCreate(&ev_start)); CUDA_TRY(cudaEventCreate(&ev_end));
+  CUDA_TRY(cudaEventRecord(ev_start, r->sv));
+  CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
+  uint64_t launches = 0;
+
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    const uint64_t b0 = p0 + (uint64_t)b * tb;
+    const uint32_t blen = (uint32_t)std::min<uint64_t>(tb, p1 - b0);
+    const uint32_t slot = b % RING;
+    // the voice kernel may not overwrite a ring slot the mixer kernels of block b-RING still read
+    if (b >= RING) CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_m1[b - RING], 0));
+    CUDA_TRY(cudaEventRecord(ev_v0[b], r->sv));
+    VoiceKernelArgs va;
+    va.groups = r->d_groups.p; va.gstate = r->d_gstate.p; va.voices = r->d_voices.p; va.buffers = r->d_buffers.p;
+    va.events = r->d_events.p;
+    va.chunk_bounds = r->d_bounds.p;
+    va.mixer_chunk_begin = r->d_chunk_begin.p + (size_t)b * (nm + 1);
+    va.group_bus = r->d_group_bus.p + (size_t)slot * ng * tb * 2;
+    va.group_flags = r->d_group_flags.p + (size_t)slot * ng * max_chunks;
+    va.max_chunks = max_chunks; va.block_frames = tb; va.block_start = b0; va.rc = r->rc;
+    for (size_t ci = 0; ci < c.classes.size(); ++ci) {
+      const SizeClass& sc = c.classes[ci];
+      va.tile_frames = sc.tile;
+      va.group_list = r->d_class_groups.p + c.class_offsets[ci];
+      if (sc.threads <= 256) voice_kernel<256><<<(uint32_t)sc.groups.size(), sc.threads, sc.smem, r->sv>>>(va);
+      else voice_kernel<1024><<<(uint32_t)sc.groups.size(), sc.threads, sc.smem, r->sv>>>(va);
+      ++launches;
+    }
+    CUDA_TRY(cudaEventRecord(ev_v1[b], r->sv));
+    CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_v1[b], 0));
+    MixerKernelArgs ma;
+    ma.mixers = r->d_mixers.p; ma.mstate = r->d_mstate.p; ma.child_index = r->d_child_index.p; ma.source_index = r->d_source_index.p;
+    ma.fx = r->d_fx.p; ma.fx_events = r->d_fx_events.p;
+    ma.fxc.sample_rate = r->cfg.sample_rate; ma.fxc.comp = r->rc.rate_comp; ma.fxc.state_arena = r->d_fx_state.p; ma.fxc.aux_arena = r->d_aux.p;
+    ma.chunk_bounds = r->d_bounds.p; ma.mixer_chunk_begin = va.mixer_chunk_begin;
+    ma.group_bus = va.group_bus; ma.group_flags = va.group_flags;
+    ma.mixer_bus = r->d_mixer_bus.p + (size_t)slot * nm * tb * 2;
+    ma.mixer_flags = r->d_mixer_flags.p + (size_t)slot * nm * max_chunks;
+    ma.max_chunks = max_chunks; ma.block_frames = tb; ma.block_start = b0;
+    ma.out = dout + (size_t)(b0 - p0) * 2; ma.master = r->d_master.p; ma.wav_block_frames = bf;
+    (void)blen;
+    for (int lvl = (int)c.levels.size() - 1; lvl >= 0; --lvl) {
+      ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
+      mixer_kernel<<<(uint32_t)c.levels[lvl].size(), 256, 0, r->sm>>>(ma);
+      ++launches;
+    }
+    CUDA_TRY(cudaEventRecord(ev_m1[b], r->sm));
+  }
+  CUDA_TRY(cudaEventRecord(ev_end, r->sm));
+  if (out_host) CUDA_TRY(cudaMemcpyAsync(out_host, dout, frames * 2 * sizeof(float), cudaMemcpyDeviceToHost, r->sm));
+  CUDA_TRY(cudaStreamSynchronize(r->sm));
+  CUDA_TRY(cudaStreamSynchronize(r->sv));
+  CUDA_TRY(cudaGetLastError());
+
+  float ms = 0;
+  r->stats = pb200_render_stats{};
+  cudaEventElapsedTime(&ms, ev_start, ev_end);
+  r->stats.device_ms = ms;
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.voice_kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ev_v1[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
+    cudaEventDestroy(ev_v0[b]); cudaEventDestroy(ev_v1[b]); cudaEventDestroy(ev_m1[b]);
+  }
+  cudaEventDestroy(ev_start); cudaEventDestroy(ev_end);
+  r->stats.kernel_launches = launches;
+  r->host_state_valid = false;
+  r->position = p1;
+  // statistics + event cursors come back with the (small) group state
+  {
+    std::vector<GroupState> gs(r->dev_n_groups);
+    CUDA_TRY(r->d_gstate.download(gs, r->sm));
+    CUDA_TRY(cudaStreamSynchronize(r->sm));
+    uint64_t vf = 0;
+    for (auto& g : gs) vf += g.voice_frames;
+    r->stats.voice_frames = vf - r->voice_frames_total;
+    r->voice_frames_total = vf;
+  }
+  if (frames_written) *frames_written = frames;
+  return PB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frames_written) {
+  if (!r || !out) return PB200_ERR_PARAMETER;
+  return render_impl(r, nullptr, out, frames, frames_written);
+}
+
+int pb200_render_device(pb200_renderer* r, float* out_device, uint64_t frames, uint64_t* frames_written) {
+  if (!r || !out_device) return PB200_ERR_PARAMETER;
+  return render_impl(r, out_device, nullptr, frames, frames_written);
+}
+
+int pb200_source_status_get(pb200_renderer* r, uint32_t id, pb200_source_status* st) {
+  if (!r || !st) return PB200_ERR_PARAMETER;
+  auto it = r->group_by_id.find(id);
+  if (it == r->group_by_id.end()) return fail(r, PB200_ERR_SOURCE_NOT_PLAYING, "Source is no longer playing");
+  if (int e = sync_state_to_host(r)) return e;
+  std::memset(st, 0, sizeof(*st));
+  st->end_frame = UINT64_MAX;
+  const HostGroup& g = r->groups[it->second];
+  const GroupState& gs = r->h_gstate[it->second];
+  st->is_playing = gs.dead ? 0 : 1;
+  if (g.gp.kind == GROUP_FILE && !gs.dead) {
+    const VoiceState& v = r->h_voices[g.gp.first_voice];
+    st->playback_pos = v.playback_pos;
+    st->exhausted = v.stopped_exhausted;
+    st->end_frame = v.end_frame;
+  }
+  return PB200_OK;
+}
+
+int pb200_sampler_voice_states(pb200_renderer* r, uint32_t id, pb200_voice_state* out, uint32_t capacity, uint32_t* count) {
+  if (!r || !out || !count) return PB200_ERR_PARAMETER;
+  auto it = r->group_by_id.find(id);
+  if (it == r->group_by_id.end() || r->groups[it->second].gp.kind != GROUP_SAMPLER) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+  if (int e = sync_state_to_host(r)) return e;
+  const HostGroup& g = r->groups[it->second];
+  uint32_t n = std::min(capacity, g.gp.n_voices);
+  for (uint32_t i = 0; i < n; ++i) {
+    const VoiceState& v = r->h_voices[g.gp.first_voice + i];
+    out[i].note_id = v.has_note ? v.note_id : UINT64_MAX;
+    out[i].playback_pos = v.playback_pos;
+    out[i].envelope_stage = v.env_stage;
+    out[i].active = v.has_note;
+  }
+  *count = g.gp.n_voices;
+  return PB200_OK;
+}
+
+int pb200_last_render_stats(pb200_renderer* r, pb200_render_stats* st) {
+  if (!r || !st) return PB200_ERR_PARAMETER;
+  *st = r->stats;
+  return PB200_OK;
+}
+
+}  // extern "C"

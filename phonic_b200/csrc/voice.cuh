@@ -1,0 +1,437 @@
+// Voice path on device: PreloadedFileSource + CubicResampler + VolumeFader + Amplified/Panned
+// smoothing + AHDSR, one thread per voice, one CTA per group (Sampler or file playback).
+//
+// Every f32/f64 operation keeps the reference's operation order and is separately rounded
+// (the translation unit is compiled with -fmad=false): the voice path is bit-exact against the
+// reference's scalar code, which is what makes loop/seek/event indices exact and keeps the f32
+// phase recurrence of cubic.rs:73-110 in lock-step.
+#pragma once
+#include "dev_structs.h"
+
+namespace pb {
+
+#define PB_DEV __device__ __forceinline__
+
+constexpr float F32_EPS = 1.1920929e-07f;
+constexpr float SMOOTH_INERTIA = 1.0f / 256.0f;  // ExponentialSmoothedValue::DEFAULT_INERTIA
+
+struct RenderConsts {
+  uint32_t sample_rate;
+  float rate_comp;  // 44100 / sample_rate as f32 (ExponentialSmoothedValue::sample_rate_comp)
+};
+
+// ---- ExponentialSmoothedValue (src/utils/smoothing.rs:195-223) --------------------------------------
+PB_DEV bool exp_need_ramp(const ExpSm& s, float comp) {
+  float add = (s.target - s.current) * SMOOTH_INERTIA * comp;
+  return fabsf(add) > F32_EPS * 100.0f;
+}
+PB_DEV float exp_next(ExpSm& s, float comp) {
+  float add = (s.target - s.current) * SMOOTH_INERTIA * comp;
+  if (fabsf(add) > F32_EPS * 100.0f) {
+    s.current += add;
+    return s.current;
+  }
+  return s.target;
+}
+PB_DEV void exp_set_target(ExpSm& s, float t, float comp) {
+  s.target = t;
+  if (!exp_need_ramp(s, comp)) s.current = s.target;
+}
+
+// src/utils.rs:56-62
+PB_DEV void panning_factors(float pan, float& l, float& r) {
+  const float POWER = 0.70710678118654752440f;
+  float normalized = (fminf(fmaxf(pan, -1.0f), 1.0f) + 1.0f) / 2.0f;
+  l = sqrtf(1.0f - normalized) / POWER;
+  r = sqrtf(normalized) / POWER;
+}
+
+// ---- CubicInterpolator (src/utils/resampler/cubic.rs:117-142) -----------------------------------------
+PB_DEV void hist_push(float* h, float v) { h[3] = h[2]; h[2] = h[1]; h[1] = h[0]; h[0] = v; }
+PB_DEV float hermite(const float* h, float fraction) {
+  float ym1 = h[3], y0 = h[2], y1 = h[1], y2 = h[0];
+  float c0 = y0;
+  float c1 = (y1 - ym1) * 0.5f;
+  float c2 = ym1 - y0 * 2.5f + y1 * 2.0f - y2 * 0.5f;
+  float c3 = (y2 - ym1) * 0.5f + (y0 - y1) * 1.5f;
+  return ((c3 * fraction + c2) * fraction + c1) * fraction + c0;
+}
+
+PB_DEV uint32_t f64_as_u32(double v) {  // Rust `as u32`: saturating, NaN -> 0
+  if (!(v > 0.0)) return 0u;
+  if (v >= 4294967295.0) return 0xFFFFFFFFu;
+  return (uint32_t)v;
+}
+
+// FileSourceImpl::update_speed (src/source/file/common.rs:141-169) + CubicResampler::update
+PB_DEV void update_speed(VoiceState& v, uint32_t in_rate, uint32_t out_rate) {
+  double speed_diff = v.target_speed - v.current_speed;
+  if (v.glide_rate > 0.0f && fabs(speed_diff) > 0.0001) {
+    double semitone_diff = fabs(12.0 * log2(v.target_speed / v.current_speed));
+    float duration_secs = (float)semitone_diff / v.glide_rate;
+    if (duration_secs > 0.0f) {
+      float duration_frames = duration_secs * (float)out_rate;
+      double step = (v.target_speed - v.current_speed) / (double)duration_frames;
+      double change = step * 64.0;
+      if (fabs(v.target_speed - v.current_speed) < fabs(change)) v.current_speed = v.target_speed;
+      else v.current_speed += change;
+    } else {
+      v.current_speed = v.target_speed;
+    }
+  } else {
+    v.current_speed = v.target_speed;
+  }
+  uint32_t new_rate = f64_as_u32((double)out_rate / v.current_speed);
+  v.ratio = (float)((double)in_rate / (double)new_rate);
+}
+
+PB_DEV void resampler_reset(VoiceState& v) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v.hist[c][i] = 0.0f;
+  v.sub_pos = 0.0f;
+  v.initialized = 0;
+}
+
+// PreloadedFileSource::set_speed (preloaded.rs:182-193)
+PB_DEV void file_set_speed(VoiceState& v, double speed, float glide, uint32_t in_rate, uint32_t out_rate) {
+  if (!v.finished) {
+    v.to_next_speed_update = 0;
+    v.target_speed = speed;
+    v.glide_rate = glide > 0.0f ? glide : 0.0f;
+    if (v.glide_rate == 0.0f) {
+      v.current_speed = speed;
+      update_speed(v, in_rate, out_rate);
+    }
+  }
+}
+// PreloadedFileSource::stop (preloaded.rs:196-209); VolumeFader::start_fade_out (fader.rs:68-92)
+PB_DEV void file_stop(VoiceState& v, const GroupParams& gp) {
+  if (!v.finished) {
+    if (gp.has_fade_out) {
+      float from = (v.fader_state == FADER_RUNNING) ? v.fader_cur : 1.0f;
+      v.fader_state = FADER_RUNNING;
+      v.fader_cur = from;
+      v.fader_tgt = 0.0f;
+      v.fader_inertia = gp.fade_out_inertia;
+    } else {
+      v.stopped_exhausted = v.pos_eof;
+      v.finished = 1;
+    }
+  }
+}
+// PreloadedFileSource::seek (preloaded.rs:138-146); index resolved on the host
+PB_DEV void file_seek(VoiceState& v, uint32_t pos) {
+  if (!v.finished) {
+    v.playback_pos = pos;
+    resampler_reset(v);
+  }
+}
+// PreloadedFileSource::reset (preloaded.rs:212-230)
+PB_DEV void file_reset(VoiceState& v) {
+  if (!v.finished) { v.stopped_exhausted = v.pos_eof; v.finished = 1; }
+  v.playback_pos = 0;
+  v.repeat_count = v.repeat;
+  v.pos_eof = 0;
+  v.finished = 0;
+  resampler_reset(v);
+  v.fader_state = FADER_STOPPED;
+  v.fader_cur = 1.0f;
+  v.fader_tgt = 1.0f;
+}
+
+// ---- AhdsrEnvelope (src/utils/ahdsr.rs:402-552) --------------------------------------------------------
+PB_DEV void env_note_on(VoiceState& v, const GroupParams& gp, float volume) {
+  v.env_target = volume;
+  if (gp.attack_rate == 3.402823466e+38f) {
+    v.env_out = volume;
+    if (!gp.hold_is_zero) { v.env_stage = ENV_HOLD; v.env_hold = gp.hold_samples; }
+    else v.env_stage = ENV_DECAY;
+  } else {
+    v.env_out = 0.0f;
+    v.env_stage = ENV_ATTACK;
+  }
+}
+PB_DEV void env_note_off(VoiceState& v, const GroupParams& gp) {
+  if (!gp.release_is_zero) {
+    v.env_target = 0.0f;
+    v.env_release_out = v.env_out;
+    v.env_stage = (v.env_release_out > F32_EPS) ? ENV_RELEASE : ENV_IDLE;
+  } else {
+    v.env_out = 0.0f; v.env_release_out = 0.0f; v.env_stage = ENV_IDLE;
+  }
+}
+PB_DEV float env_apply_scaling(float value, float scaling) {
+  const float EULER_DIV_2 = 2.718281828459045f / 2.0f;
+  if (scaling == 0.0f || value == 0.0f) return value;
+  float s = -scaling;
+  if (s > 0.0f) return powf(value, 1.0f + powf(s, EULER_DIV_2) * 16.0f);
+  return 1.0f - powf(1.0f - value, 1.0f + powf(-s, EULER_DIV_2) * 16.0f);
+}
+PB_DEV float env_run(VoiceState& v, const GroupParams& gp) {
+  switch (v.env_stage) {
+    case ENV_ATTACK:
+      v.env_out += gp.attack_rate;
+      if (v.env_out >= v.env_target) {
+        v.env_out = v.env_target;
+        v.env_target = gp.sustain_level;
+        if (!gp.hold_is_zero) { v.env_stage = ENV_HOLD; v.env_hold = gp.hold_samples; }
+        else v.env_stage = ENV_DECAY;
+      }
+      break;
+    case ENV_HOLD:
+      v.env_hold -= 1.0f;
+      if (v.env_hold <= 0.0f) v.env_stage = gp.decay_is_zero ? ENV_SUSTAIN : ENV_DECAY;
+      break;
+    case ENV_DECAY:
+      if (v.env_out > gp.sustain_level) {
+        v.env_out -= gp.decay_rate;
+        if (v.env_out <= gp.sustain_level) { v.env_out = gp.sustain_level; v.env_stage = ENV_SUSTAIN; }
+      } else {
+        v.env_out += gp.decay_rate;
+        if (v.env_out >= gp.sustain_level) { v.env_out = gp.sustain_level; v.env_stage = ENV_SUSTAIN; }
+      }
+      break;
+    case ENV_RELEASE:
+      v.env_out -= v.env_release_out * gp.release_rate;
+      if (v.env_out <= 0.001f) { v.env_out = 0.0f; v.env_stage = ENV_IDLE; }
+      break;
+    default: break;
+  }
+  if (v.env_stage == ENV_ATTACK && gp.attack_scaling != 0.0f) {
+    float progress = v.env_out / fmaxf(v.env_target, F32_EPS);
+    return env_apply_scaling(progress, gp.attack_scaling) * v.env_target;
+  }
+  if (v.env_stage == ENV_DECAY && gp.decay_scaling != 0.0f) {
+    float range = fmaxf(fabsf(v.env_target - gp.sustain_level), F32_EPS);
+    bool down = v.env_target > gp.sustain_level;
+    float progress = down ? (v.env_target - v.env_out) / range : (v.env_out - v.env_target) / range;
+    float sp = env_apply_scaling(progress, gp.decay_scaling);
+    return down ? v.env_target - (sp * range) : v.env_target + (sp * range);
+  }
+  if (v.env_stage == ENV_RELEASE && gp.release_scaling != 0.0f) {
+    float initial = fmaxf(v.env_out, F32_EPS);
+    float progress = 1.0f - (v.env_out / initial);
+    float sp = env_apply_scaling(progress, gp.release_scaling);
+    return initial * (1.0f - sp);
+  }
+  return v.env_out;
+}
+
+// SamplerVoice::reset (voice.rs:222-236)
+PB_DEV void voice_reset(VoiceState& v) {
+  if (v.has_note) { file_reset(v); v.has_note = 0; }
+  v.has_release = 0;
+}
+
+// ---- per write-call context (decisions the reference takes once per `write` call) -----------------------
+struct CallCtx {
+  uint32_t chunk_left;       // frames still requested in this Source::write call
+  uint32_t call_left;        // frames left in the current write_buffer call (glide sub-chunk)
+  uint32_t produced_in_call; // output of the current resampler.process call
+  uint32_t ls, le;           // active loop range / buffer range in samples
+  bool new_call;             // a new resampler.process call starts at the next frame
+  bool gliding;              // write() took the pitch-slide arm (preloaded.rs:419)
+  bool ended;                // write_buffer broke out (EOF) -> no more frames in this call
+  bool fader_running, fader_scale;
+  bool vol_ramp, vol_scale;
+  bool pan_ramp, pan_apply;
+  bool env_per_frame;
+  float pan_l, pan_r, env_const;
+};
+
+PB_DEV void loop_range_samples(const VoiceState& v, const DevBuffer& b, uint32_t& ls, uint32_t& le) {
+  ls = 0; le = b.n_samples;
+  if (v.repeat > 0) {
+    if (v.loop_ovr_start >= 0) { ls = (uint32_t)v.loop_ovr_start * b.channels; le = (uint32_t)v.loop_ovr_end * b.channels; }
+    else if (b.loop_start >= 0) { ls = (uint32_t)b.loop_start * b.channels; le = (uint32_t)b.loop_end * b.channels; }
+  }
+}
+
+// Start of PreloadedFileSource::write + the wrappers' per-call decisions. Returns false when the
+// source is finished (write returns 0).
+PB_DEV bool voice_begin_call(VoiceState& v, CallCtx& c, const GroupParams& gp, const DevBuffer& b, uint32_t n_frames,
+                             float comp, bool with_env) {
+  c.chunk_left = n_frames;
+  c.call_left = 0;
+  c.produced_in_call = 0;
+  c.new_call = true;
+  c.ended = false;
+  if (v.finished) { c.chunk_left = 0; c.ended = true; return false; }
+  c.gliding = v.current_speed != v.target_speed;
+  if (!c.gliding) v.to_next_speed_update = 0;
+  loop_range_samples(v, b, c.ls, c.le);
+  // VolumeFader::process mode (fader.rs:103-108)
+  c.fader_running = v.fader_state == FADER_RUNNING;
+  c.fader_scale = !c.fader_running && v.fader_tgt != 1.0f;
+  // apply_smoothed_gain mode (smoothing.rs:60-71)
+  c.vol_ramp = exp_need_ramp(v.vol, comp);
+  c.vol_scale = !c.vol_ramp && fabsf(1.0f - v.vol.target) > 0.000001f;
+  // apply_smoothed_panning mode (smoothing.rs:74-122)
+  c.pan_ramp = exp_need_ramp(v.pan, comp);
+  c.pan_apply = !c.pan_ramp && fabsf(v.pan.target) > 0.000001f;
+  c.pan_l = 1.0f; c.pan_r = 1.0f;
+  if (c.pan_apply) panning_factors(v.pan.target, c.pan_l, c.pan_r);
+  // envelope mode (voice.rs:470-486)
+  c.env_per_frame = with_env && !(v.env_stage == ENV_SUSTAIN || v.env_stage == ENV_IDLE);
+  c.env_const = v.env_out;
+  return true;
+}
+
+// write_buffer post-call bookkeeping (preloaded.rs:311-329)
+PB_DEV void after_process_call(VoiceState& v, CallCtx& c) {
+  if (v.playback_pos >= c.le) {
+    if (v.repeat_count > 0) {
+      if (v.repeat_count != REPEAT_FOREVER) v.repeat_count -= 1;
+      v.playback_pos = c.ls;
+    } else {
+      v.pos_eof = 1;
+    }
+  }
+}
+
+// One output frame of the resampler inside write_buffer. Returns false on the EOF break.
+template <int CC>
+PB_DEV bool resample_frame(VoiceState& v, CallCtx& c, const float* __restrict__ buf, float& x0, float& x1) {
+  for (;;) {
+    if (c.new_call) {  // CubicInterpolator::process prologue (cubic.rs:47-69)
+      c.new_call = false;
+      c.produced_in_call = 0;
+      const bool bypass = fabsf(v.ratio - 1.0f) < 0.000001f;
+      uint32_t avail = c.le > v.playback_pos ? (c.le - v.playback_pos) / CC : 0u;
+      if (!bypass && !v.initialized && avail >= 3) {
+        v.initialized = 1;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          hist_push(v.hist[0], __ldg(buf + v.playback_pos));
+          if (CC == 2) hist_push(v.hist[1], __ldg(buf + v.playback_pos + 1));
+          v.playback_pos += CC;
+        }
+      }
+    }
+    const bool has_input = v.playback_pos < c.le;
+    if (fabsf(v.ratio - 1.0f) < 0.000001f) {  // bypass copy (cubic.rs:53-58)
+      if (has_input) {
+        x0 = __ldg(buf + v.playback_pos);
+        x1 = CC == 2 ? __ldg(buf + v.playback_pos + 1) : x0;
+        v.playback_pos += CC;
+        c.produced_in_call++;
+        return true;
+      }
+    } else if (v.ratio < 1.0f) {  // cubic.rs:72-90
+      bool ok = true;
+      if (v.sub_pos >= 1.0f) {
+        if (has_input) {
+          hist_push(v.hist[0], __ldg(buf + v.playback_pos));
+          if (CC == 2) hist_push(v.hist[1], __ldg(buf + v.playback_pos + 1));
+          v.playback_pos += CC;
+          v.sub_pos -= 1.0f;
+        } else {
+          ok = false;
+        }
+      }
+      if (ok) {
+        x0 = hermite(v.hist[0], v.sub_pos);
+        x1 = CC == 2 ? hermite(v.hist[1], v.sub_pos) : x0;
+        v.sub_pos += v.ratio;
+        c.produced_in_call++;
+        return true;
+      }
+    } else {  // cubic.rs:91-110
+      bool ok = true;
+      while (v.sub_pos < v.ratio) {
+        if (v.playback_pos >= c.le) { ok = false; break; }
+        hist_push(v.hist[0], __ldg(buf + v.playback_pos));
+        if (CC == 2) hist_push(v.hist[1], __ldg(buf + v.playback_pos + 1));
+        v.playback_pos += CC;
+        v.sub_pos += 1.0f;
+      }
+      if (ok) {
+        v.sub_pos -= v.ratio;
+        float fr = 1.0f - v.sub_pos;
+        x0 = hermite(v.hist[0], fr);
+        x1 = CC == 2 ? hermite(v.hist[1], fr) : x0;
+        c.produced_in_call++;
+        return true;
+      }
+    }
+    // input exhausted: process() returned early; write_buffer loops (preloaded.rs:311-329)
+    after_process_call(v, c);
+    if (v.pos_eof && c.produced_in_call == 0) return false;
+    c.new_call = true;
+  }
+}
+
+// Render up to `n` frames of the current write call into `out` (interleaved stereo, stride 2).
+// Returns the number of frames written (< n only when the source ran dry).
+template <int CC>
+PB_DEV uint32_t voice_frames(VoiceState& v, CallCtx& c, const GroupParams& gp, const DevBuffer& b, uint32_t out_rate,
+                             float comp, uint32_t n, float* __restrict__ out) {
+  const float* __restrict__ buf = b.data;
+  uint32_t f = 0;
+  for (; f < n && !c.ended; ++f) {
+    if (c.call_left == 0) {  // next write_buffer call (preloaded.rs:419-447)
+      if (c.gliding) {
+        if (v.to_next_speed_update == 0) {
+          if (v.current_speed != v.target_speed) update_speed(v, b.sample_rate, out_rate);
+          v.to_next_speed_update = 64;
+        }
+        c.call_left = min(c.chunk_left, v.to_next_speed_update);
+      } else {
+        c.call_left = c.chunk_left;
+      }
+      loop_range_samples(v, b, c.ls, c.le);
+      c.new_call = true;
+    }
+    float x0, x1;
+    if (!resample_frame<CC>(v, c, buf, x0, x1)) { c.ended = true; break; }
+    c.call_left--;
+    c.chunk_left--;
+    if (c.gliding) v.to_next_speed_update--;
+    if (c.call_left == 0) after_process_call(v, c);  // output slice full: post-call check still runs
+    // VolumeFader::process (fader.rs:103-116)
+    if (c.fader_running) {
+      v.fader_cur += (v.fader_tgt - v.fader_cur) * v.fader_inertia;
+      x0 *= v.fader_cur; x1 *= v.fader_cur;
+    } else if (c.fader_scale) {
+      x0 *= v.fader_tgt; x1 *= v.fader_tgt;
+    }
+    // ChannelMappedSource: mono -> stereo duplicates (buffer.rs:199-206); stereo passes through
+    float l = x0, r = x1;
+    // AmplifiedSource: per *sample* smoothing (smoothing.rs:61-64)
+    if (c.vol_ramp) { l *= exp_next(v.vol, comp); r *= exp_next(v.vol, comp); }
+    else if (c.vol_scale) { l *= v.vol.target; r *= v.vol.target; }
+    // PannedSource
+    if (c.pan_ramp) {
+      float pl, pr;
+      panning_factors(exp_next(v.pan, comp), pl, pr);
+      l *= pl; r *= pr;
+    } else if (c.pan_apply) {
+      l *= c.pan_l; r *= c.pan_r;
+    }
+    // AHDSR (voice.rs:470-486)
+    if (gp.has_env) {
+      float e = c.env_per_frame ? env_run(v, gp) : c.env_const;
+      l *= e; r *= e;
+    }
+    out[2 * f] = l;
+    out[2 * f + 1] = r;
+  }
+  return f;
+}
+
+// End of PreloadedFileSource::write (preloaded.rs:449-472); `call_end_frame` = absolute frame after the call
+PB_DEV void voice_end_call(VoiceState& v, CallCtx& c, uint64_t call_end_frame) {
+  if (c.fader_running) {
+    if (fabsf(v.fader_cur - v.fader_tgt) < 0.0001f) v.fader_state = FADER_FINISHED;
+  }
+  bool fade_out_completed = v.fader_state == FADER_FINISHED && v.fader_tgt == 0.0f;
+  if (v.pos_eof || fade_out_completed) {
+    v.stopped_exhausted = v.pos_eof;
+    v.finished = 1;
+    v.end_frame = call_end_frame;
+  }
+}
+
+}  // namespace pb

@@ -1,0 +1,341 @@
+// Voice kernel: one CTA per group (a phonic `Source` attached to a mixer: a Sampler with N voices or a
+// single file playback), one thread per voice. The CTA walks the mixer's exact chunk schedule for one
+// time block (MixedSource::write chunking, src/source/mixed.rs:679-693), resolves note/speed/seek/stop
+// events on device at the frame they are due, renders every active voice in tiles of F frames into
+// shared memory, sums the tile over voices in *voice order* (Sampler::write, sampler.rs:989-1006:
+// out = ((0 + v0) + v1) + ...), applies the generator-level gain/pan and stores the group bus.
+#pragma once
+#include "voice.cuh"
+
+namespace pb {
+
+struct VoiceKernelArgs {
+  const GroupParams* groups;
+  const uint32_t* group_list;         // groups of this launch (one size class)
+  GroupState* gstate;
+  VoiceState* voices;
+  const DevBuffer* buffers;
+  const DevEvent* events;
+  // chunk schedule: per mixer the absolute chunk boundaries of this time block
+  const uint64_t* chunk_bounds;       // concatenated
+  const uint32_t* mixer_chunk_begin;  // [n_mixers + 1] offsets into chunk_bounds for this block
+  float* group_bus;                   // [n_groups][block_frames][2]
+  uint8_t* group_flags;               // [n_groups][max_chunks]: source produced output in chunk k
+  uint32_t max_chunks;
+  uint32_t block_frames;
+  uint64_t block_start;
+  RenderConsts rc;
+  uint32_t tile_frames;               // F
+};
+
+constexpr int VK_MAX_VOICES = 1024;
+
+struct VoiceHeader {  // what Sampler::next_free_voice_index needs (sampler.rs:826-860)
+  uint64_t note_id;
+  uint64_t release_start;
+  uint8_t active, in_release, has_release;
+};
+
+// Sampler::next_free_voice_index; evaluated redundantly by every thread on the shared headers
+PB_DEV uint32_t next_free_voice_index(const VoiceHeader* h, uint32_t n, bool has_env) {
+  for (uint32_t i = 0; i < n; ++i)
+    if (!h[i].active) return i;
+  uint32_t candidate = 0;
+  bool has_earliest = false, has_oldest = false;
+  uint64_t earliest = 0, oldest = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (has_env && h[i].in_release) {
+      if (h[i].has_release) {
+        if (!has_earliest || h[i].release_start < earliest) {
+          has_earliest = true; earliest = h[i].release_start; has_oldest = false; candidate = i;
+        }
+      }
+    } else if (!has_earliest) {
+      if (h[i].active) {
+        if (!has_oldest || h[i].note_id < oldest) { has_oldest = true; oldest = h[i].note_id; candidate = i; }
+      }
+    }
+  }
+  return candidate;
+}
+
+PB_DEV void publish_header(VoiceHeader* h, uint32_t i, const VoiceState& v) {
+  h[i].note_id = v.note_id;
+  h[i].release_start = v.release_start;
+  h[i].active = v.has_note;
+  h[i].in_release = v.env_stage == ENV_RELEASE;
+  h[i].has_release = v.has_release;
+}
+
+// SamplerVoice::stop (voice.rs:196-219)
+PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t frame) {
+  if (v.has_note) {
+    v.has_release = 1;
+    v.release_start = frame;
+    if (gp.has_env) env_note_off(v, gp);
+    else file_stop(v, gp);
+  }
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
+  extern __shared__ float s_tile[];  // [n_voices][2F]
+  __shared__ VoiceHeader s_head[MAXT];
+  __shared__ uint16_t s_valid[MAXT];
+  __shared__ GroupState s_gs;
+  __shared__ uint32_t s_count;
+  __shared__ float s_ggain[128];  // generator-level per-sample gains of a tile (<= 2F)
+  __shared__ float s_gpl[64], s_gpr[64];
+
+  const uint32_t g = a.group_list[blockIdx.x];
+  const uint32_t tid = threadIdx.x;
+  const GroupParams gp = a.groups[g];
+  const uint32_t nv = gp.n_voices;
+  const DevBuffer buf = a.buffers[gp.buffer];
+  const bool is_sampler = gp.kind == GROUP_SAMPLER;
+  const bool mine = tid < nv;
+  const float comp = a.rc.rate_comp;
+  const uint32_t out_rate = a.rc.sample_rate;
+  const uint32_t F = a.tile_frames;
+
+  VoiceState v;
+  if (mine) {
+    v = a.voices[gp.first_voice + tid];
+    publish_header(s_head, tid, v);
+  }
+  if (tid == 0) s_gs = a.gstate[g];
+  __syncthreads();
+
+  const uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];
+  float* gbus = a.group_bus + (size_t)g * a.block_frames * 2;
+  uint8_t* gflags = a.group_flags + (size_t)g * a.max_chunks;
+  uint64_t my_frames = 0;
+
+  for (uint32_t k = cb; k + 1 < ce; ++k) {
+    const uint64_t c0 = a.chunk_bounds[k], c1 = a.chunk_bounds[k + 1];
+    const uint32_t len = (uint32_t)(c1 - c0);
+    const uint32_t boff = (uint32_t)(c0 - a.block_start);
+    bool produced = false;
+    uint32_t total = 0;
+    bool skip = s_gs.dead != 0;
+    // MixedSource::process_sources (mixed.rs:558-624) for this one source
+    if (!skip && gp.start_time > c0) {
+      uint64_t until = gp.start_time - c0;
+      if (until >= len) skip = true;
+      else total = (uint32_t)until;
+    }
+    if (skip) {
+      if (tid == 0) gflags[k - cb] = 0;
+      continue;
+    }
+    // frames before the source starts stay silent
+    for (uint32_t i = tid; i < total * 2; i += blockDim.x) gbus[(size_t)boff * 2 + i] = 0.0f;
+
+    while (total < len) {
+      const uint64_t t = c0 + total;
+      uint64_t until_stop = UINT64_MAX;
+      __syncthreads();
+      if (s_gs.has_stop_time) until_stop = s_gs.stop_time > t ? s_gs.stop_time - t : 0;
+      bool send_stop = false;
+      if (until_stop == 0) { send_stop = true; until_stop = UINT64_MAX; }
+      __syncthreads();
+      if (send_stop && tid == 0) s_gs.has_stop_time = 0;
+      const uint32_t n = (uint32_t)min((uint64_t)(len - total), until_stop);
+
+      // ---- Source::write(n frames at time t) -------------------------------------------------------
+      // 1. messages: stop first (it was force-pushed into the source queue before the events of this
+      //    chunk were... no: events were pushed at chunk start by process_events, the stop later) --
+      //    queue order = events of this chunk (only on the first call of the chunk), then Stop.
+      uint32_t ev_end_now = s_gs.ev_cursor;
+      while (ev_end_now < gp.ev_end && a.events[ev_end_now].time <= c0) ++ev_end_now;
+      for (uint32_t e = s_gs.ev_cursor; e < ev_end_now; ++e) {
+        const DevEvent ev = a.events[e];
+        if (is_sampler) {
+          const bool ignore = s_gs.stopping != 0;  // sampler.rs:664
+          if (ev.kind == EVK_STOP) {
+            // GeneratorPlaybackMessage::Stop (sampler.rs:733-738)
+            __syncthreads();
+            if (tid == 0) s_gs.stopping = gp.transient;
+            if (mine) { sampler_voice_stop(v, gp, t); publish_header(s_head, tid, v); }
+            __syncthreads();
+          } else if (ev.kind == EVK_SET_VOLUME) {  // generator-level AmplifiedSource message
+            if (tid == 0) exp_set_target(s_gs.vol, ev.value, comp);
+          } else if (ev.kind == EVK_SET_PANNING) {
+            if (tid == 0) exp_set_target(s_gs.pan, ev.value, comp);
+          } else if (!ignore) {
+            if (ev.kind == EVK_NOTE_ON) {
+              const uint32_t idx = next_free_voice_index(s_head, nv, gp.has_env != 0);
+              __syncthreads();
+              if (tid == idx) {  // SamplerVoice::start (voice.rs:122-193)
+                voice_reset(v);
+                v.note = (uint8_t)ev.note;
+                v.note_volume = ev.value;
+                v.note_panning = ev.value2;
+                float eff_vol = gp.base_volume * ev.value;
+                float eff_pan = fminf(fmaxf(gp.base_panning + ev.value2, -1.0f), 1.0f);
+                file_set_speed(v, ev.speed, 0.0f, buf.sample_rate, out_rate);
+                exp_set_target(v.vol, eff_vol, comp);
+                exp_set_target(v.pan, eff_pan, comp);
+                if (gp.has_env) env_note_on(v, gp, 1.0f);
+                v.has_note = 1;
+                v.note_id = ev.note_id;
+                publish_header(s_head, tid, v);
+              }
+              if (tid == 0) s_gs.active_voices += 1;
+              __syncthreads();
+            } else if (ev.kind == EVK_ALL_NOTES_OFF) {
+              if (mine) { sampler_voice_stop(v, gp, t); publish_header(s_head, tid, v); }
+              __syncthreads();
+            } else {
+              // note-addressed events: first voice whose note_id matches (sampler.rs:776-822)
+              uint32_t idx = 0xFFFFFFFFu;
+              for (uint32_t i = 0; i < nv; ++i)
+                if (s_head[i].active && s_head[i].note_id == ev.note_id) { idx = i; break; }
+              __syncthreads();
+              if (tid == idx) {
+                if (ev.kind == EVK_NOTE_OFF) sampler_voice_stop(v, gp, t);
+                else if (ev.kind == EVK_NOTE_SPEED) file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate);
+                else if (ev.kind == EVK_NOTE_VOLUME) { v.note_volume = ev.value; exp_set_target(v.vol, gp.base_volume * ev.value, comp); }
+                else if (ev.kind == EVK_NOTE_PANNING) { v.note_panning = ev.value; exp_set_target(v.pan, fminf(fmaxf(gp.base_panning + ev.value, -1.0f), 1.0f), comp); }
+                publish_header(s_head, tid, v);
+              }
+              __syncthreads();
+            }
+          }
+        } else if (mine) {  // file playback: FilePlaybackMessage / Amplified / Panned messages
+          if (ev.kind == EVK_STOP) file_stop(v, gp);
+          else if (ev.kind == EVK_SET_SPEED) file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate);
+          else if (ev.kind == EVK_SEEK) file_seek(v, ev.seek_pos);
+          else if (ev.kind == EVK_SET_VOLUME) exp_set_target(v.vol, ev.value, comp);
+          else if (ev.kind == EVK_SET_PANNING) exp_set_target(v.pan, ev.value, comp);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_gs.ev_cursor = ev_end_now;
+      if (send_stop) {  // PlaybackMessageQueue::send_stop (mixed.rs:591-598)
+        if (is_sampler) {
+          if (tid == 0) s_gs.stopping = gp.transient;
+          if (mine) { sampler_voice_stop(v, gp, t); publish_header(s_head, tid, v); }
+        } else if (mine) {
+          file_stop(v, gp);
+        }
+      }
+      __syncthreads();
+
+      // 2. does the source write at all? (sampler.rs:978-981 / preloaded.rs:400-403)
+      uint32_t written;
+      bool group_writes;
+      if (is_sampler) group_writes = !(s_gs.stopped || (s_gs.active_voices == 0 && !s_gs.stopping));
+      else group_writes = true;
+      const bool was_active = mine && (is_sampler ? v.has_note != 0 : true);
+      CallCtx cc;
+      cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
+      bool call_open = false;
+      if (group_writes && was_active) call_open = voice_begin_call(v, cc, gp, buf, n, comp, gp.has_env != 0);
+      if (!is_sampler) {
+        // a file source's written count = frames its single voice produces (short on EOF)
+        written = 0;
+      } else {
+        written = group_writes ? n : 0;
+      }
+
+      // generator-level gain / pan decisions for this call (player.rs:1075-1081)
+      bool g_vol_ramp = false, g_vol_scale = false, g_pan_ramp = false, g_pan_apply = false;
+      float g_pl = 1.0f, g_pr = 1.0f;
+      if (is_sampler && group_writes) {
+        g_vol_ramp = exp_need_ramp(s_gs.vol, comp);
+        g_vol_scale = !g_vol_ramp && fabsf(1.0f - s_gs.vol.target) > 0.000001f;
+        g_pan_ramp = exp_need_ramp(s_gs.pan, comp);
+        g_pan_apply = !g_pan_ramp && fabsf(s_gs.pan.target) > 0.000001f;
+        if (g_pan_apply) panning_factors(s_gs.pan.target, g_pl, g_pr);
+      }
+      const float g_vol_t = s_gs.vol.target;
+      __syncthreads();
+
+      uint32_t file_written = 0;
+      if (group_writes) {
+        for (uint32_t t0 = 0; t0 < n; t0 += F) {
+          const uint32_t tl = min(F, n - t0);
+          uint32_t valid = 0;
+          if (call_open) {
+            if (buf.channels == 2) valid = voice_frames<2>(v, cc, gp, buf, out_rate, comp, tl, s_tile + (size_t)tid * 2 * F);
+            else valid = voice_frames<1>(v, cc, gp, buf, out_rate, comp, tl, s_tile + (size_t)tid * 2 * F);
+            my_frames += valid;
+          }
+          if (mine) s_valid[tid] = (uint16_t)valid;
+          if (!is_sampler && tid == 0) file_written += valid;
+          if (tid == 0 && (g_vol_ramp || g_pan_ramp)) {  // serial generator-level ramps for this tile
+            if (g_vol_ramp) for (uint32_t i = 0; i < tl * 2; ++i) s_ggain[i] = exp_next(s_gs.vol, comp);
+            if (g_pan_ramp) for (uint32_t i = 0; i < tl; ++i) panning_factors(exp_next(s_gs.pan, comp), s_gpl[i], s_gpr[i]);
+          }
+          __syncthreads();
+          for (uint32_t col = tid; col < tl * 2; col += blockDim.x) {
+            const uint32_t fr = col >> 1;
+            float s = 0.0f;
+            if (is_sampler) {
+              for (uint32_t i = 0; i < nv; ++i)
+                if (fr < s_valid[i]) s += s_tile[(size_t)i * 2 * F + col];
+              if (g_vol_ramp) s *= s_ggain[col];
+              else if (g_vol_scale) s *= g_vol_t;
+              if (g_pan_ramp) s *= (col & 1) ? s_gpr[fr] : s_gpl[fr];
+              else if (g_pan_apply) s *= (col & 1) ? g_pr : g_pl;
+            } else {
+              s = fr < s_valid[0] ? s_tile[col] : 0.0f;
+            }
+            gbus[(size_t)(boff + total + t0) * 2 + col] = s;
+          }
+          __syncthreads();
+        }
+      }
+      // 3. end of the write call: file finish checks, voice reset, active voice count
+      if (call_open) voice_end_call(v, cc, t + n);
+      if (is_sampler) {
+        if (was_active && group_writes) {
+          // SamplerVoice::process epilogue (voice.rs:488-502)
+          if (v.finished || (gp.has_env && v.env_stage == ENV_IDLE)) voice_reset(v);
+          publish_header(s_head, tid, v);
+        }
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        if (group_writes) {
+          if (mine && v.has_note) atomicAdd(&s_count, 1u);
+          __syncthreads();
+          if (tid == 0) {
+            s_gs.active_voices = s_count;
+            if (s_gs.stopping && s_count == 0) s_gs.stopped = 1;
+          }
+        }
+        __syncthreads();
+      } else {
+        if (tid == 0) s_count = file_written;
+        __syncthreads();
+        written = s_count;
+        __syncthreads();
+      }
+      total += written;
+      produced |= written > 0;
+      // mixed.rs:612-619
+      bool exhausted;
+      if (is_sampler) exhausted = s_gs.stopped != 0;
+      else { if (tid == 0) s_count = v.finished; __syncthreads(); exhausted = s_count != 0; __syncthreads(); }
+      if (gp.transient && exhausted) {
+        if (tid == 0) s_gs.dead = 1;
+        __syncthreads();
+        break;
+      } else if (written == 0) {
+        break;
+      }
+    }
+    // frames the source did not write stay silent
+    for (uint32_t i = tid + total * 2; i < len * 2; i += blockDim.x) gbus[(size_t)boff * 2 + i] = 0.0f;
+    if (tid == 0) gflags[k - cb] = produced ? 1 : 0;
+    __syncthreads();
+  }
+
+  if (mine) a.voices[gp.first_voice + tid] = v;
+  if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
+  __syncthreads();
+  if (tid == 0) a.gstate[g] = s_gs;
+}
+
+}  // namespace pb

@@ -1,0 +1,166 @@
+"""Seeded test scenes, described once through the Player API and rendered by whatever
+implementation of the C-ABI the Player was given."""
+import math
+
+import numpy as np
+
+from phonic_b200 import workloads as W
+from phonic_b200.player import (AhdsrParameters, ChorusEffect, CompressorEffect, DelayEffect, Eq5Effect,
+                                FilePlaybackOptions, FilterEffect, GeneratorPlaybackOptions, Player, ReverbEffect)
+
+SR = 48000
+BLOCK = 1024
+
+
+def tone(frames, rate, channels=1, seed=0):
+    return W.synth_buffer(frames, rate, seed=seed + 11, channels=channels)
+
+
+def file_mono_default(p: Player):
+    """one mono 44.1 kHz file, default options, plays to EOF (ratio < 1 branch)"""
+    b = p.upload_buffer(tone(30000, 44100), 44100)
+    return {"h": p.play_file_source(b, FilePlaybackOptions()), "frames": 40 * BLOCK}
+
+
+def file_stereo_fast_loop(p: Player):
+    """stereo file at speed 1.37 (ratio >= 1 branch), loop range x2, fade-in, volume/pan options, late start"""
+    b = p.upload_buffer(tone(20000, 48000, channels=2, seed=3), 48000)
+    o = FilePlaybackOptions(volume=0.7, panning=-0.3, speed=1.37, repeat=2, loop_range=(4000, 9000), fade_in=0.02)
+    return {"h": p.play_file_source(b, o, start_time=1500), "frames": 48 * BLOCK}
+
+
+def file_events(p: Player):
+    """seek, speed glide, volume/pan ramps, scheduled stop with fade-out, embedded loop"""
+    b = p.upload_buffer(tone(60000, 44100, seed=5), 44100, loop_range=(10000, 50000))
+    h = p.play_file_source(b, FilePlaybackOptions(volume=0.9))
+    h.set_volume(0.4, 3000)
+    h.set_panning(0.6, 3000)
+    h.set_speed(1.5, 24.0, 5000)
+    h.seek(0.25, 20000)
+    h.set_speed(0.8, None, 30000)
+    h.set_panning(-1.0, 41000)
+    h.stop(60000)
+    return {"h": h, "frames": 70 * BLOCK}
+
+
+def file_bypass_and_immediate(p: Player):
+    """equal rates (bypass copy), immediate (None) events between render calls are exercised by the test"""
+    b = p.upload_buffer(tone(50000, 48000, seed=6), 48000)
+    return {"h": p.play_file_source(b, FilePlaybackOptions(fade_out=0.01)), "frames": 60 * BLOCK}
+
+
+def sampler_notes(p: Player):
+    """8-voice sampler with AHDSR: more notes than voices (stealing), note-offs, glides, per-note vol/pan"""
+    b = p.upload_buffer(tone(44100 * 2, 44100, seed=7), 44100, loop_range=(2000, 80000))
+    ah = AhdsrParameters(attack=0.01, hold=0.05, decay=0.1, sustain=0.6, release=0.2)
+    g = p.add_generator(b, GeneratorPlaybackOptions(volume=0.8, panning=0.1, voices=8), ah)
+    rng = np.random.default_rng(42)
+    ids = []
+    t = 0
+    for i in range(24):
+        t += int(rng.integers(200, 4000))
+        nid = g.note_on(int(rng.integers(40, 80)), volume=float(rng.uniform(0.1, 0.4)),
+                        panning=float(rng.uniform(-1, 1)), sample_time=t)
+        ids.append((nid, t))
+        if i % 3 == 0:
+            g.set_note_speed(nid, float(rng.uniform(0.5, 2.0)), glide=float(rng.uniform(6, 48)), sample_time=t + 3000)
+        if i % 4 == 1:
+            g.set_note_volume(nid, 0.2, sample_time=t + 2500)
+            g.set_note_panning(nid, -0.5, sample_time=t + 2600)
+        if i % 2 == 0:
+            g.note_off(nid, sample_time=t + int(rng.integers(5000, 20000)))
+    g.set_volume(0.5, 30000)
+    g.set_panning(-0.4, 32000)
+    g.all_notes_off(90000)
+    return {"g": g, "frames": 110 * BLOCK}
+
+
+def sampler_no_envelope(p: Player):
+    """sampler without AHDSR: note_off -> 50 ms fade-out (chunk-dependent finish), transient + stop"""
+    b = p.upload_buffer(tone(30000, 44100, channels=2, seed=8), 44100)
+    g = p.play_generator(b, GeneratorPlaybackOptions(voices=4), None, start_time=700)
+    n1 = g.note_on(60, 0.5, None, sample_time=1000)
+    n2 = g.note_on(67, 0.4, 0.3, sample_time=1000)
+    g.note_on(72, 0.3, -0.3, sample_time=5000)
+    g.note_off(n1, sample_time=9000)
+    g.note_off(n2, sample_time=9500)
+    g.stop(30000)
+    return {"g": g, "frames": 48 * BLOCK}
+
+
+def cfg2_small(p: Player):
+    hs, fx = W.build_cfg2(p, W.VoiceBankSpec(voices=48), time_scale=0.15)
+    return {"hs": hs, "frames": 72 * BLOCK}
+
+
+def filter_automation(p: Player):
+    b = p.upload_buffer(tone(48000 * 2, 48000, channels=2, seed=9), 48000)
+    p.play_file_source(b, FilePlaybackOptions(volume=0.8))
+    fx = p.add_effect(FilterEffect(0, 800.0, 0.9))
+    fx.set_parameter("cuto", 5000.0, 10000)
+    fx.set_parameter("fltq", 2.0, 12000)
+    fx.set_parameter_normalized("cuto", 0.3, 40000)
+    fx.set_parameter("type", 3, 50000)
+    return {"frames": 100 * BLOCK}
+
+
+def fx_scene(effect, seconds=3.0, param_events=(), seed=10):
+    def build(p: Player):
+        b = p.upload_buffer(tone(int(44100 * 1.0), 44100, channels=2, seed=seed), 44100)
+        p.play_file_source(b, FilePlaybackOptions(volume=0.8))
+        fx = p.add_effect(effect)
+        for (pid, val, t) in param_events:
+            fx.set_parameter(pid, val, t)
+        return {"frames": W.frames_for(seconds, SR)}
+    return build
+
+
+def submixers_cfg3_small(p: Player):
+    W.build_subtrees(p, 3, 12, W.VoiceBankSpec(), effects="cfg3", time_scale=0.1)
+    return {"frames": 96 * BLOCK}
+
+
+def submixers_cfg5_small(p: Player):
+    W.build_subtrees(p, 4, 16, W.VoiceBankSpec(), effects="none", time_scale=0.1)
+    W.add_main_bus_sends(p)
+    return {"frames": 96 * BLOCK}
+
+
+def nested_and_gated(p: Player):
+    """nested sub-mixers; one goes silent for > 2 s (silence gate + effect auto-bypass), then wakes up"""
+    b = p.upload_buffer(tone(12000, 44100, seed=12), 44100)
+    m1 = p.add_mixer(None)
+    m2 = p.add_mixer(m1.id)
+    p.add_effect(FilterEffect(0, 3000.0, 0.707), m2.id)
+    p.add_effect(ChorusEffect(), m1.id)
+    p.play_file_source(b, FilePlaybackOptions(volume=0.5, target_mixer=m2.id))
+    p.play_file_source(b, FilePlaybackOptions(volume=0.5, target_mixer=m2.id), start_time=int(3.2 * SR))
+    p.play_file_source(b, FilePlaybackOptions(volume=0.3, target_mixer=m1.id), start_time=5000)
+    p.add_effect(CompressorEffect())
+    return {"frames": W.frames_for(5, SR)}
+
+
+SCENES = {
+    "file_mono_default": file_mono_default,
+    "file_stereo_fast_loop": file_stereo_fast_loop,
+    "file_events": file_events,
+    "file_bypass": file_bypass_and_immediate,
+    "sampler_notes": sampler_notes,
+    "sampler_no_envelope": sampler_no_envelope,
+    "cfg2_small": cfg2_small,
+    "filter_automation": filter_automation,
+    "fx_filter": fx_scene(FilterEffect(0, 1000.0, 0.707)),
+    "fx_eq5": fx_scene(Eq5Effect(), param_events=[("gan1", 4.0, 0), ("gan3", -5.0, 0), ("frq2", 1500.0, 20000), ("bw_3", 2.0, 30000)]),
+    "fx_compressor": fx_scene(CompressorEffect()),
+    "fx_limiter": fx_scene(CompressorEffect.new_limiter()),
+    "fx_chorus": fx_scene(ChorusEffect(), param_events=[("rate", 2.0, 30000), ("dlay", 20.0, 40000)]),
+    "fx_delay": fx_scene(DelayEffect(), seconds=4.0, param_events=[("dlay", 120.0, 0), ("fdbk", 0.6, 0), ("driv", 0.3, 50000), ("mode", 1, 90000)]),
+    "fx_reverb": fx_scene(ReverbEffect(0.6, 0.35), seconds=4.0, param_events=[("room", 0.8, 60000)]),
+    "submixers_cfg3_small": submixers_cfg3_small,
+    "submixers_cfg5_small": submixers_cfg5_small,
+    "nested_and_gated": nested_and_gated,
+}
+
+# scenes whose whole path is +,-,*,/,sqrt in the reference's order: must be bit-exact on device
+BIT_EXACT = {"file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
+             "sampler_no_envelope", "cfg2_small", "fx_filter"}

@@ -1,0 +1,147 @@
+"""Parity proper: the CUDA renderer (through the C-ABI) against the oracle on the same seeded scenes.
+Voice path + plain biquad: bit-exact. Effects that call device libm (tan/pow/sin/asin/log10/exp):
+<= 1e-5 max abs error; feedback effects (delay, reverb): error floor below -90 dBFS."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from phonic_b200.player import Player
+from scenes import BIT_EXACT, SCENES, SR
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "scenes.json")
+
+
+def render(api, name, calls=1):
+    p = Player(api, SR)
+    info = SCENES[name](p)
+    frames = info["frames"]
+    if calls == 1:
+        out = p.render(frames)
+    else:
+        per = (frames // 1024 // calls) * 1024
+        parts = [p.render(per) for _ in range(calls - 1)]
+        parts.append(p.render(frames - per * (calls - 1)))
+        out = np.concatenate(parts)
+    return p, info, out
+
+
+def dbfs(x):
+    return 20 * np.log10(max(float(x), 1e-30))
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_scene_matches_oracle(cuda_api, oracle_api, name):
+    pg, ig, gpu = render(cuda_api, name)
+    po, io, ref = render(oracle_api, name)
+    assert np.isfinite(gpu).all()
+    peak = float(np.abs(ref).max())
+    assert peak > 1e-3, "scene is silent in the oracle"
+    err = float(np.abs(gpu - ref).max())
+    if name in BIT_EXACT:
+        bad = np.flatnonzero((gpu != ref).any(axis=1))
+        assert bad.size == 0, f"{name}: first differing frame {bad[0]} of {len(ref)}, max err {err:.3e}"
+    elif name in ("fx_delay", "fx_reverb", "submixers_cfg5_small"):
+        rms = float(np.sqrt(np.mean((gpu - ref) ** 2)))
+        assert dbfs(rms) < -90.0 and dbfs(err) < -80.0, f"{name}: error floor {dbfs(rms):.1f} dBFS rms, {dbfs(err):.1f} peak"
+    else:
+        assert err <= 1e-5, f"{name}: max abs err {err:.3e}"
+    # integer state: bit-exact everywhere
+    for key in ("g",):
+        if key in ig:
+            assert ig[key].voice_states() == io[key].voice_states()
+    if "hs" in ig:
+        for a, b in zip(ig["hs"], io["hs"]):
+            assert a.voice_states() == b.voice_states()
+    if "h" in ig:
+        sa, sb = ig["h"].status(), io["h"].status()
+        assert (sa.is_playing, sa.exhausted) == (sb.is_playing, sb.exhausted)
+        if sb.is_playing:
+            assert (sa.playback_pos, sa.end_frame) == (sb.playback_pos, sb.end_frame)
+
+
+@pytest.mark.parametrize("name", ["file_events", "sampler_notes", "nested_and_gated", "fx_reverb"])
+def test_split_render_calls_equal_single_call(cuda_api, name):
+    _, _, one = render(cuda_api, name, calls=1)
+    _, _, many = render(cuda_api, name, calls=5)
+    assert np.array_equal(one, many)
+
+
+def test_bit_exact_scenes_match_committed_golden(cuda_api):
+    import hashlib
+    golden = json.load(open(GOLDEN))
+    for name in sorted(BIT_EXACT):
+        _, _, gpu = render(cuda_api, name)
+        assert hashlib.sha256(gpu.tobytes()).hexdigest() == golden[name]["sha256"], name
+
+
+def test_immediate_events_between_render_calls(cuda_api, oracle_api):
+    outs = []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, SR)
+        info = SCENES["file_bypass"](p)
+        a = p.render(8 * 1024)
+        info["h"].set_volume(0.3)          # None sample time => immediately
+        info["h"].set_speed(1.2, 12.0)
+        b = p.render(8 * 1024)
+        info["h"].stop()
+        c = p.render(16 * 1024)
+        outs.append(np.concatenate([a, b, c]))
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_error_codes_mirror_reference(cuda_api):
+    from phonic_b200 import PhonicError
+    from phonic_b200 import _capi as A
+    from phonic_b200.player import FilePlaybackOptions, FilterEffect
+    p = Player(cuda_api, SR)
+    with pytest.raises(PhonicError) as e:
+        p.add_mixer(1234)
+    assert e.value.code == A.ERR_MIXER_NOT_FOUND
+    b = p.upload_buffer(np.zeros(16, np.float32), 44100)
+    with pytest.raises(PhonicError) as e:
+        p.play_file_source(b, FilePlaybackOptions(volume=-1.0))
+    assert e.value.code == A.ERR_PARAMETER
+    with pytest.raises(PhonicError) as e:
+        p.add_effect(FilterEffect(0, 10.0, 0.7))
+    assert e.value.code == A.ERR_PARAMETER
+    with pytest.raises(PhonicError):
+        p.render(1000)  # not a multiple of the 1024-frame WavStream block
+
+
+def test_empty_player_renders_nothing(cuda_api, oracle_api):
+    for api in (cuda_api, oracle_api):
+        p = Player(api, SR)
+        out = np.ones((2048, 2), np.float32)
+        assert p.render_into(out) == 0 and not out.any()
+
+
+def test_full_size_cfg2_properties(cuda_api):
+    """BASELINE cfg2 at full size (256 voices, 10 s): size-independent properties."""
+    from phonic_b200 import workloads as W
+    frames = W.frames_for(10, SR)
+    p = Player(cuda_api, SR)
+    hs, _ = W.build_cfg2(p)
+    out = p.render(frames)
+    assert np.isfinite(out).all() and float(np.abs(out).max()) < 1.5
+    assert float(np.abs(out[: 2 * SR]).max()) > 0.05            # notes are sounding
+    # all notes are released by 8 s, release is 1 s: the last second decays to silence
+    tail = float(np.abs(out[int(9.6 * SR):]).max())
+    assert tail < 1e-3
+    st = p.last_render_stats()
+    assert st.kernel_launches > 0 and st.voice_frames > 256 * 4 * SR
+    # idempotence: the same scene renders to the same bytes, whatever the time-block size
+    os.environ["PB200_TIME_BLOCK"] = "2048"
+    try:
+        p2 = Player(cuda_api, SR)
+        W.build_cfg2(p2)
+        out2 = p2.render(frames)
+    finally:
+        del os.environ["PB200_TIME_BLOCK"]
+    assert np.array_equal(out, out2)
+    # every voice is idle again
+    for h in hs:
+        assert all(v[3] == 0 for v in h.voice_states())
