@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- voice-samples/s of the offline resample+FX+mix path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg5shard] [--impl reference]
+
+A *step* is one complete offline render of the workload (cfg2: 256 Sampler voices with AHDSR + glide,
+cubic 44.1->48 kHz resampling, FilterEffect LP on the bus, "10 s" = 469 WavStream blocks = 480 256
+frames). `value` counts voices x output frames per second of DEVICE time with the scene already
+resident in HBM (CUDA events inside the renderer, on the streams the kernels are launched on);
+`e2e` is the same metric through the public Player API from HOST buffers: sample upload, event
+scheduling, graph upload, render, read-back of the WAV data into pinned host memory.
+
+N > 1 (torchrun, one rank per GPU): every rank renders its own voice bank as one sub-mixer subtree
+(weak scaling, the path shards by independent subtrees) and the stereo bus partials are summed on
+rank 0 with one NCCL reduce per render.
+
+`--impl reference`: the reference's own CPU path cannot be compiled here (no cargo); the arm times
+the oracle port (oracle/, scalar C++) on the host cores instead -- cfg2 has a single mixer, so the
+reference's SubMixerThreadPool has nothing to distribute and one audio thread is what phonic uses.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SR = 48000
+FLOP_PER_CHANNEL_SAMPLE = 25.0   # Hermite 19 + phase 2 + gain/pan/envelope 4
+METRIC = "voice-samples/sec (resample+FX+mix, 48 kHz)"
+
+
+def oracle_api(fast=True):
+    from phonic_b200._capi import CApi
+    lib = os.path.join(ROOT, "oracle", "_build", "libphonic_oracle_fast.so" if fast else "libphonic_oracle.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return CApi(lib, "po_")
+
+
+def workload_spec(name):
+    from phonic_b200 import workloads as W
+    if name == "cfg2":
+        return dict(voices=256, n_mixers=0, seconds=10, desc="cfg2: 256 Sampler voices (AHDSR + glide), cubic 44.1->48k, "
+                    "FilterEffect LP 2 kHz on the bus, 10 s (480256 frames)")
+    if name == "cfg5shard":
+        return dict(voices=8192, n_mixers=64, seconds=10, desc="cfg5 per-GPU shard: 8192 voices in 64 sub-mixer subtrees, "
+                    "10 s (480256 frames)")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def build_scene(player, name, rank=0, as_subtree=False):
+    """Builds the workload on `player`; returns number of voices."""
+    from phonic_b200 import workloads as W
+    from phonic_b200.player import FilterEffect
+    spec = workload_spec(name)
+    if name == "cfg2":
+        if not as_subtree:
+            W.build_cfg2(player, W.VoiceBankSpec(voices=spec["voices"]))
+        else:  # one GPU's shard of an N-GPU graph: the bank lives on a sub-mixer of the main mixer
+            buf = W.synth_buffer(int(4.0 * 44100), 44100, seed=1)
+            bid = player.upload_buffer(buf, 44100)
+            mh = player.add_mixer(None)
+            W.add_voice_bank(player, W.VoiceBankSpec(voices=spec["voices"]), bid, mh.id, seed_offset=7919 * rank)
+            player.add_effect(FilterEffect(0, 2000.0, 0.707), mh.id)
+    else:
+        W.build_subtrees(player, spec["n_mixers"], spec["voices"] // spec["n_mixers"], W.VoiceBankSpec(), effects="none",
+                         seed_base=100000 * rank)
+    return spec["voices"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def fp32_fma_peak_tflops(torch, device):
+    """FP32 FMA peak measured live: a dependent-chain-free torch.addcmul loop would be HBM bound, so use
+    the arithmetic peak 148 SM x 128 lanes x 2 flop x SM clock(max) and say so (derived, not measured)."""
+    props = torch.cuda.get_device_properties(device)
+    clock_hz = 1.965e9
+    try:
+        out = subprocess.check_output(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits", "-i",
+                                       str(device.index or 0)], text=True)
+        clock_hz = float(out.strip().splitlines()[0]) * 1e6
+    except Exception:
+        pass
+    return props.multi_processor_count * 128 * 2 * clock_hz / 1e12
+
+
+def cpu_baseline(name, seconds_budget=25.0):
+    """Oracle port on the host cores, rank 0 only, bounded sample of the same workload."""
+    from phonic_b200 import workloads as W
+    from phonic_b200.player import Player
+    api = oracle_api(fast=True)
+    spec = workload_spec(name)
+    frames = W.frames_for(spec["seconds"], SR)
+    voices = spec["voices"]
+    sample = f"full {name} render once" if voices <= 512 else f"{name} with 512 of {voices} voices (same per-voice events)"
+    p = Player(api, SR)
+    if name == "cfg2":
+        build_scene(p, name)
+        v = voices
+    else:
+        W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none")
+        v = 512
+    t0 = time.perf_counter()
+    out = np.zeros((frames, 2), np.float32)
+    p.render_into(out)
+    dt = time.perf_counter() - t0
+    p.close()
+    return {"value": v * frames / dt, "unit": "voice-samples/s", "cores": 1, "kind": "port", "sample": sample,
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from phonic_b200 import workloads as W
+    from phonic_b200.player import Player
+    api = oracle_api(fast=True)
+    spec = workload_spec(args.workload)
+    frames = W.frames_for(spec["seconds"], SR)
+    times = []
+    voices = spec["voices"]
+    bounded = voices > 512
+    for i in range(args.warmup + args.steps):
+        p = Player(api, SR)
+        if not bounded:
+            build_scene(p, args.workload)
+            v = voices
+        else:
+            W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none")
+            v = 512
+        out = np.zeros((frames, 2), np.float32)
+        t0 = time.perf_counter()
+        p.render_into(out)
+        dt = time.perf_counter() - t0
+        p.close()
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = v * frames * len(times) / total
+    sample = "full workload per step" if not bounded else f"512 of {voices} voices per step (4 sub-mixers x 128)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": spec["desc"], "note": "oracle port of the reference's CPU path (Rust toolchain absent); "
+                       "single audio thread: this graph has no sub-mixers for SubMixerThreadPool to distribute"},
+            "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import phonic_b200
+    from phonic_b200 import workloads as W
+    from phonic_b200.player import Player
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: phonic_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    api = phonic_b200.load_api()
+    spec = workload_spec(args.workload)
+    frames = W.frames_for(spec["seconds"], SR)
+    voices = spec["voices"]
+    n_total = args.warmup + args.steps
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
+
+    # ---- device-resident arm: scenes built and uploaded before the timed region -------------------------------
+    players = []
+    for i in range(n_total):
+        p = Player(api, SR, device_ordinal=local_rank)
+        build_scene(p, args.workload, rank=rank, as_subtree=world > 1)
+        players.append(p)
+    out_dev = torch.zeros(frames, 2, dtype=torch.float32, device=device)
+    clocks = ClockSampler(local_rank)
+    dev_ms, wall_ms, voice_ms, fx_ms, launches, vframes = [], [], [], [], 0, 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for i, p in enumerate(players):
+        if i == args.warmup:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            clocks.start()
+        flush.fill_(float(i))  # evict L2 between steps
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        p.render_device(out_dev.data_ptr(), frames)
+        red_ms = 0.0
+        if world > 1:  # one NCCL reduce of the stereo bus partial per render (rank 0 owns the main bus)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.reduce(out_dev, dst=0, op=dist.ReduceOp.SUM)
+            e1.record()
+            torch.cuda.synchronize()
+            red_ms = e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        st = p.last_render_stats()
+        if i >= args.warmup:
+            dev_ms.append(st.device_ms + red_ms)
+            wall_ms.append((t1 - t0) * 1e3)
+            voice_ms.append(st.voice_kernel_ms)
+            fx_ms.append(st.effect_kernel_ms)
+            launches += int(st.kernel_launches) + (1 if world > 1 else 0)
+            vframes += int(st.voice_frames)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    checksum = float(out_dev.abs().sum().item())
+    for p in players:
+        p.close()
+
+    # ---- end-to-end arm: host buffers in, host WAV data out, every step -------------------------------------------
+    out_host = torch.zeros(frames, 2, dtype=torch.float32).pin_memory()
+    out_np = out_host.numpy()
+    e2e_ms = []
+    h2d = d2h = 0
+    for i in range(n_total):
+        flush.fill_(float(i))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        p = Player(api, SR, device_ordinal=local_rank)
+        build_scene(p, args.workload, rank=rank, as_subtree=world > 1)   # uploads the sample buffer (H2D) + schedules events
+        if world > 1:
+            p.render_device(out_dev.data_ptr(), frames)
+            dist.reduce(out_dev, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                out_host.copy_(out_dev, non_blocking=False)
+            torch.cuda.synchronize()
+        else:
+            p.render_into(out_np)                                         # graph upload (H2D), kernels, WAV data D2H
+        t1 = time.perf_counter()
+        p.close()
+        if i >= args.warmup:
+            e2e_ms.append((t1 - t0) * 1e3)
+    buf_bytes = int(4.0 * 44100) * 4
+    h2d = buf_bytes + voices * 176 + voices * 3 * 64       # sample buffer + voice state + event records
+    d2h = frames * 2 * 4
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    total_dev_ms = allmax(sum(dev_ms))
+    total_e2e_ms = allmax(sum(e2e_ms))
+    total_voice_ms = allmax(sum(voice_ms))
+    total_vframes = allsum(float(vframes))
+    total_launches = allsum(float(launches))
+    K = args.steps
+    value = world * voices * frames * K / (total_dev_ms / 1e3)
+    e2e_value = world * voices * frames * K / (total_e2e_ms / 1e3)
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        fma_peak = fp32_fma_peak_tflops(torch, device)
+        # dominant kernel: voice_kernel. Algorithmic work = active voice-frames x 2 channels x 25 flop
+        flops = (total_vframes / world) * 2 * FLOP_PER_CHANNEL_SAMPLE
+        ach = flops / (total_voice_ms / 1e3) / 1e12
+        roofline = {"bound": "fp32_fma", "kernel": "voice_kernel", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s",
+                    "frac": ach / fma_peak, "traffic": None,
+                    "peak_source": "derived: SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json holds only HBM and bf16 "
+                                   "tensor peaks; voices share one L2-resident buffer so the kernel is not HBM bound)",
+                    "hbm_achieved_gbs": (total_vframes / world) * 8.0 / (total_voice_ms / 1e3) / 1e9,
+                    "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_kind": peak_kind,
+                    "voice_kernel_ms_per_step": total_voice_ms / K, "effect_kernel_ms_per_step": sum(fx_ms) / K}
+        line = {"metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+                "ms_per_step": total_dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": spec["desc"] + (f"; x{world} ranks, one subtree per GPU, NCCL reduce of the stereo bus" if world > 1 else ""),
+                           "l2": "flushed between steps (256 MiB fill)", "timing": "CUDA events on the renderer's own streams",
+                           "wall_ms_per_step": sum(wall_ms) / K, "checksum": checksum},
+                "e2e": {"value": e2e_value, "unit": "voice-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": total_e2e_ms / K},
+                "gpu_launches": int(total_launches), "clocks": clk, "roofline": roofline}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.workload)
+        elif world > 1:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

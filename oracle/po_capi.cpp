@@ -398,6 +398,11 @@ int pb200_sampler_voice_states(pb200_renderer* r, uint32_t id, pb200_voice_state
   if (!r || !out || !count) return PB200_ERR_PARAMETER;
   auto it = r->sources.find(id);
   if (it == r->sources.end() || !it->second.sampler) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+  // a transient generator that got exhausted was dropped (and freed) by its mixer: no voices left
+  MixedSource* mixer = r->mixers[it->second.mixer];
+  bool alive = mixer->find_source(id) != nullptr;
+  for (auto& m : mixer->message_queue) if (m.kind == MixedSource::Message::AddSource && m.source && m.source->playback_id == id) alive = true;
+  if (!alive) { *count = 0; return PB200_OK; }
   Sampler* s = it->second.sampler;
   uint32_t n = (uint32_t)std::min<size_t>(capacity, s->voices.size());
   for (uint32_t i = 0; i < n; ++i) {

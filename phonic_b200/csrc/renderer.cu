@@ -979,6 +979,7 @@ int pb200_sampler_voice_states(pb200_renderer* r, uint32_t id, pb200_voice_state
   if (it == r->group_by_id.end() || r->groups[it->second].gp.kind != GROUP_SAMPLER) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
   if (int e = sync_state_to_host(r)) return e;
   const HostGroup& g = r->groups[it->second];
+  if (r->h_gstate[it->second].dead) { *count = 0; return PB200_OK; }  // dropped by its mixer
   uint32_t n = std::min(capacity, g.gp.n_voices);
   for (uint32_t i = 0; i < n; ++i) {
     const VoiceState& v = r->h_voices[g.gp.first_voice + i];
