@@ -268,7 +268,9 @@ PB200_API int pb200_sampler_voice_states(pb200_renderer *r, uint32_t generator_i
 /* ---- timing of the last render call (device side, CUDA events) ------------------------------ */
 typedef struct pb200_render_stats {
   double device_ms;        /* all kernels of the last pb200_render* call */
-  double voice_kernel_ms;  /* the voice (resample+gain/pan/envelope+sum) kernels */
+  double voice_kernel_ms;  /* replay kernels (resample + gain/pan/envelope + ordered sum), summed over blocks;
+                              NB: event-to-event spans on their own stream, they overlap the other passes */
+  double skeleton_kernel_ms; /* control-only pass (events, phase/ramp recurrences, segment snapshots) */
   double effect_kernel_ms; /* mixer/effect kernels */
   uint64_t kernel_launches;
   uint64_t voice_frames;   /* active voice-frames rendered */

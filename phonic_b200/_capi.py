@@ -103,7 +103,7 @@ class VoiceState(C.Structure):
 
 
 class RenderStats(C.Structure):
-    _fields_ = [("device_ms", F64), ("voice_kernel_ms", F64), ("effect_kernel_ms", F64),
+    _fields_ = [("device_ms", F64), ("voice_kernel_ms", F64), ("skeleton_kernel_ms", F64), ("effect_kernel_ms", F64),
                 ("kernel_launches", U64), ("voice_frames", U64)]
 
 

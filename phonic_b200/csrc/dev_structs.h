@@ -50,7 +50,7 @@ struct VoiceState {
   float glide_rate;
   // CubicInterpolator x channels (src/utils/resampler/cubic.rs:10-15); sub_pos/ratio shared
   float ratio, sub_pos;
-  float hist[2][4];            // [channel][input[0..3]]
+  int32_t hidx[4];             // sample index (channel 0) of input[0..3]; -1 = the zero a reset leaves
   // VolumeFader (src/utils/fader.rs:27-34)
   float fader_cur, fader_tgt, fader_inertia;
   // AmplifiedSource / PannedSource smoothers
@@ -66,6 +66,7 @@ struct VoiceState {
   uint8_t stopped_exhausted;
   uint8_t _pad[7];
 };
+static_assert(sizeof(VoiceState) % 8 == 0, "VoiceState must stay 8-byte aligned");
 
 enum GroupKind : uint32_t { GROUP_SAMPLER = 0, GROUP_FILE = 1 };
 

@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/phonic_b200.h"
-#include "voice_kernel.cuh"
+#include "replay_kernel.cuh"
 #include "mixer_kernel.cuh"
 #include "host_fx.h"
 
@@ -129,6 +129,10 @@ struct pb200_renderer {
   DevVec<uint64_t> d_bounds;
   DevVec<uint32_t> d_chunk_begin;
   DevVec<float> d_group_bus, d_mixer_bus, d_out;
+  DevVec<Segment> d_segs;
+  DevVec<GroupSeg> d_gsegs;
+  DevVec<uint16_t> d_seg_first, d_seg_count, d_gseg_first, d_gseg_count;
+  cudaStream_t sr_ = nullptr;  // replay stream
   DevVec<uint8_t> d_group_flags, d_mixer_flags;
   DevVec<ExpSm> d_master;
   ExpSm h_master;
@@ -253,6 +257,7 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
     cudaGetDevice(&r->device);
   }
   if (cudaStreamCreateWithFlags(&r->sv, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&r->sr_, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&r->sm, cudaStreamNonBlocking) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
   r->rc.sample_rate = config->sample_rate;
   r->rc.rate_comp = 44100.0f / (float)config->sample_rate;
@@ -281,6 +286,8 @@ void pb200_destroy(pb200_renderer* r) {
   r->d_class_groups.free(); r->d_fx.free(); r->d_fx_events.free(); r->d_fx_state.free(); r->d_aux.free();
   r->d_bounds.free(); r->d_chunk_begin.free(); r->d_group_bus.free(); r->d_mixer_bus.free(); r->d_out.free();
   r->d_group_flags.free(); r->d_mixer_flags.free(); r->d_master.free();
+  r->d_segs.free(); r->d_gsegs.free(); r->d_seg_first.free(); r->d_seg_count.free(); r->d_gseg_first.free(); r->d_gseg_count.free();
+  if (r->sr_) cudaStreamDestroy(r->sr_);
   if (r->sv) cudaStreamDestroy(r->sv);
   if (r->sm) cudaStreamDestroy(r->sm);
   delete r;
@@ -628,7 +635,7 @@ uint64_t pb200_position(const pb200_renderer* r) { return r ? r->position : 0; }
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
-struct SizeClass { uint32_t threads; uint32_t tile; std::vector<uint32_t> groups; size_t smem; };
+struct SizeClass { uint32_t vpad; uint32_t threads; uint32_t tpc; std::vector<uint32_t> groups; size_t smem; };
 
 struct Compiled {
   std::vector<std::vector<uint32_t>> levels;  // mixers per depth
@@ -702,23 +709,20 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
   std::vector<uint32_t> level_mixers;
   c.level_offsets.clear();
   for (auto& l : c.levels) { c.level_offsets.push_back((uint32_t)level_mixers.size()); for (uint32_t m : l) level_mixers.push_back(m); }
-  // voice kernel size classes
-  const uint32_t class_threads[6] = {32, 64, 128, 256, 512, 1024};
+  // size classes: groups bucketed by voices-per-group rounded up to a power of two
   c.classes.clear();
-  for (int ci = 0; ci < 6; ++ci) {
+  for (uint32_t vpad = 1; vpad <= 1024; vpad <<= 1) {
     SizeClass sc;
-    sc.threads = class_threads[ci];
-    uint32_t lo = ci == 0 ? 0 : class_threads[ci - 1];
+    sc.vpad = vpad;
+    sc.threads = std::max(32u, vpad);                        // skeleton: one thread per voice
     for (size_t gi = 0; gi < r->groups.size(); ++gi) {
       uint32_t nv = r->groups[gi].gp.n_voices;
-      if (nv > lo && nv <= sc.threads) sc.groups.push_back((uint32_t)gi);
+      if (nv <= vpad && (vpad == 1 || nv > vpad / 2)) sc.groups.push_back((uint32_t)gi);
     }
     if (sc.groups.empty()) continue;
-    // tile: as many frames as fit ~96 KB of shared memory, power of two in [2, 32]
-    uint32_t tile = 32;
-    while (tile > 2 && (size_t)sc.threads * tile * 2 * sizeof(float) > 96 * 1024) tile >>= 1;
-    sc.tile = tile;
-    sc.smem = (size_t)sc.threads * tile * 2 * sizeof(float);
+    sc.tpc = std::min(16u, std::max(1u, 128u / vpad));        // replay: tiles per CTA
+    const uint32_t nt = vpad * sc.tpc;
+    sc.smem = ((size_t)nt * ROW + (size_t)sc.tpc * 4 * TILE) * sizeof(float);
     c.classes.push_back(sc);
   }
   std::vector<uint32_t> class_groups;
@@ -851,50 +855,86 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   if (!dout) { CUDA_TRY(r->d_out.reserve(frames * 2)); dout = r->d_out.p; }
   CUDA_TRY(cudaStreamSynchronize(r->sm));
 
-  CUDA_TRY(cudaFuncSetAttribute(voice_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  CUDA_TRY(cudaFuncSetAttribute(voice_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(replay_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(replay_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  const uint32_t n_tiles = tb / TILE;
+  const uint32_t seg_cap = n_tiles + max_chunks + 8;
+  if (seg_cap >= 65535) return fail(r, PB200_ERR_UNSUPPORTED, "too many chunk boundaries in one time block");
+  const size_t nvoices = std::max<size_t>(1, r->h_voices.size());
+  CUDA_TRY(r->d_segs.reserve((size_t)RING * nvoices * seg_cap));
+  CUDA_TRY(r->d_gsegs.reserve(std::max<size_t>(1, (size_t)RING * ng * seg_cap)));
+  CUDA_TRY(r->d_seg_first.reserve((size_t)RING * nvoices * n_tiles));
+  CUDA_TRY(r->d_seg_count.reserve((size_t)RING * nvoices * n_tiles));
+  CUDA_TRY(r->d_gseg_first.reserve(std::max<size_t>(1, (size_t)RING * ng * n_tiles)));
+  CUDA_TRY(r->d_gseg_count.reserve(std::max<size_t>(1, (size_t)RING * ng * n_tiles)));
 
-  std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_m1(n_blocks);
+  std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r1(n_blocks), ev_m1(n_blocks);
   for (uint32_t b = 0; b < n_blocks; ++b) {
-    CUDA_TRY(cudaEventCreate(&ev_v0[b])); CUDA_TRY(cudaEventCreate(&ev_v1[b])); CUDA_TRY(cudaEventCreate(&ev_m1[b]));
+    CUDA_TRY(cudaEventCreate(&ev_v0[b])); CUDA_TRY(cudaEventCreate(&ev_v1[b])); CUDA_TRY(cudaEventCreate(&ev_r1[b])); CUDA_TRY(cudaEventCreate(&ev_m1[b]));
   }
   cudaEvent_t ev_start, ev_end;
   CUDA_TRY(cudaEventCreate(&ev_start)); CUDA_TRY(cudaEventCreate(&ev_end));
   CUDA_TRY(cudaEventRecord(ev_start, r->sv));
   CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_start, 0));
   uint64_t launches = 0;
 
   for (uint32_t b = 0; b < n_blocks; ++b) {
     const uint64_t b0 = p0 + (uint64_t)b * tb;
     const uint32_t blen = (uint32_t)std::min<uint64_t>(tb, p1 - b0);
     const uint32_t slot = b % RING;
-    // the voice kernel may not overwrite a ring slot the mixer kernels of block b-RING still read
-    if (b >= RING) CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_m1[b - RING], 0));
+    // pass 1 (skeleton) may not overwrite the segment slot the replay of block b-RING still reads
+    if (b >= RING) CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_r1[b - RING], 0));
     CUDA_TRY(cudaEventRecord(ev_v0[b], r->sv));
-    VoiceKernelArgs va;
+    SkeletonArgs va;
     va.groups = r->d_groups.p; va.gstate = r->d_gstate.p; va.voices = r->d_voices.p; va.buffers = r->d_buffers.p;
     va.events = r->d_events.p;
     va.chunk_bounds = r->d_bounds.p;
     va.mixer_chunk_begin = r->d_chunk_begin.p + (size_t)b * (nm + 1);
-    va.group_bus = r->d_group_bus.p + (size_t)slot * ng * tb * 2;
     va.group_flags = r->d_group_flags.p + (size_t)slot * ng * max_chunks;
     va.max_chunks = max_chunks; va.block_frames = tb; va.block_start = b0; va.rc = r->rc;
+    va.segs = r->d_segs.p + (size_t)slot * nvoices * seg_cap;
+    va.seg_first = r->d_seg_first.p + (size_t)slot * nvoices * n_tiles;
+    va.seg_count = r->d_seg_count.p + (size_t)slot * nvoices * n_tiles;
+    va.gsegs = r->d_gsegs.p + (size_t)slot * ng * seg_cap;
+    va.gseg_first = r->d_gseg_first.p + (size_t)slot * ng * n_tiles;
+    va.gseg_count = r->d_gseg_count.p + (size_t)slot * ng * n_tiles;
+    va.seg_cap = seg_cap; va.n_tiles = n_tiles;
     for (size_t ci = 0; ci < c.classes.size(); ++ci) {
       const SizeClass& sc = c.classes[ci];
-      va.tile_frames = sc.tile;
       va.group_list = r->d_class_groups.p + c.class_offsets[ci];
-      if (sc.threads <= 256) voice_kernel<256><<<(uint32_t)sc.groups.size(), sc.threads, sc.smem, r->sv>>>(va);
-      else voice_kernel<1024><<<(uint32_t)sc.groups.size(), sc.threads, sc.smem, r->sv>>>(va);
+      if (sc.threads <= 256) skeleton_kernel<256><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va);
+      else skeleton_kernel<1024><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va);
       ++launches;
     }
     CUDA_TRY(cudaEventRecord(ev_v1[b], r->sv));
-    CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_v1[b], 0));
+    // pass 2 (replay): needs the segments of this block; may not overwrite a group-bus slot the mixer still reads
+    CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_v1[b], 0));
+    if (b >= RING) CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_m1[b - RING], 0));
+    ReplayArgs ra;
+    ra.groups = r->d_groups.p; ra.buffers = r->d_buffers.p;
+    ra.segs = va.segs; ra.seg_first = va.seg_first; ra.seg_count = va.seg_count;
+    ra.gsegs = va.gsegs; ra.gseg_first = va.gseg_first; ra.gseg_count = va.gseg_count;
+    ra.group_bus = r->d_group_bus.p + (size_t)slot * ng * tb * 2;
+    ra.seg_cap = seg_cap; ra.n_tiles = n_tiles; ra.block_frames = tb; ra.rc = r->rc;
+    const uint32_t live_tiles = (blen + TILE - 1) / TILE;
+    for (size_t ci = 0; ci < c.classes.size(); ++ci) {
+      const SizeClass& sc = c.classes[ci];
+      ra.group_list = r->d_class_groups.p + c.class_offsets[ci];
+      ra.vpad = sc.vpad; ra.tpc = sc.tpc;
+      dim3 grid((live_tiles + sc.tpc - 1) / sc.tpc, (uint32_t)sc.groups.size());
+      if (sc.vpad * sc.tpc <= 128) replay_kernel<128, 6><<<grid, sc.vpad * sc.tpc, sc.smem, r->sr_>>>(ra);
+      else replay_kernel<1024, 1><<<grid, sc.vpad * sc.tpc, sc.smem, r->sr_>>>(ra);
+      ++launches;
+    }
+    CUDA_TRY(cudaEventRecord(ev_r1[b], r->sr_));
+    CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_r1[b], 0));
     MixerKernelArgs ma;
     ma.mixers = r->d_mixers.p; ma.mstate = r->d_mstate.p; ma.child_index = r->d_child_index.p; ma.source_index = r->d_source_index.p;
     ma.fx = r->d_fx.p; ma.fx_events = r->d_fx_events.p;
     ma.fxc.sample_rate = r->cfg.sample_rate; ma.fxc.comp = r->rc.rate_comp; ma.fxc.state_arena = r->d_fx_state.p; ma.fxc.aux_arena = r->d_aux.p;
     ma.chunk_bounds = r->d_bounds.p; ma.mixer_chunk_begin = va.mixer_chunk_begin;
-    ma.group_bus = va.group_bus; ma.group_flags = va.group_flags;
+    ma.group_bus = ra.group_bus; ma.group_flags = va.group_flags;
     ma.mixer_bus = r->d_mixer_bus.p + (size_t)slot * nm * tb * 2;
     ma.mixer_flags = r->d_mixer_flags.p + (size_t)slot * nm * max_chunks;
     ma.max_chunks = max_chunks; ma.block_frames = tb; ma.block_start = b0;
@@ -910,6 +950,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaEventRecord(ev_end, r->sm));
   if (out_host) CUDA_TRY(cudaMemcpyAsync(out_host, dout, frames * 2 * sizeof(float), cudaMemcpyDeviceToHost, r->sm));
   CUDA_TRY(cudaStreamSynchronize(r->sm));
+  CUDA_TRY(cudaStreamSynchronize(r->sr_));
   CUDA_TRY(cudaStreamSynchronize(r->sv));
   CUDA_TRY(cudaGetLastError());
 
@@ -918,9 +959,10 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   cudaEventElapsedTime(&ms, ev_start, ev_end);
   r->stats.device_ms = ms;
   for (uint32_t b = 0; b < n_blocks; ++b) {
-    cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.voice_kernel_ms += ms;
-    cudaEventElapsedTime(&ms, ev_v1[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
-    cudaEventDestroy(ev_v0[b]); cudaEventDestroy(ev_v1[b]); cudaEventDestroy(ev_m1[b]);
+    cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.skeleton_kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ev_v1[b], ev_r1[b]); r->stats.voice_kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ev_r1[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
+    cudaEventDestroy(ev_v0[b]); cudaEventDestroy(ev_v1[b]); cudaEventDestroy(ev_r1[b]); cudaEventDestroy(ev_m1[b]);
   }
   cudaEventDestroy(ev_start); cudaEventDestroy(ev_end);
   r->stats.kernel_launches = launches;

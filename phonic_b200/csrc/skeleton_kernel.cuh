@@ -1,31 +1,43 @@
-// Voice kernel: one CTA per group (a phonic `Source` attached to a mixer: a Sampler with N voices or a
-// single file playback), one thread per voice. The CTA walks the mixer's exact chunk schedule for one
-// time block (MixedSource::write chunking, src/source/mixed.rs:679-693), resolves note/speed/seek/stop
-// events on device at the frame they are due, renders every active voice in tiles of F frames into
-// shared memory, sums the tile over voices in *voice order* (Sampler::write, sampler.rs:989-1006:
-// out = ((0 + v0) + v1) + ...), applies the generator-level gain/pan and stores the group bus.
+// Skeleton kernel (pass 1 of the voice path): one CTA per group (a Sampler with N voices or one file
+// playback), one thread per voice. It walks the mixer's exact chunk schedule for one time block
+// (MixedSource::write chunking, src/source/mixed.rs:679-693), resolves note/speed/seek/stop events on
+// device at the frame they are due (voice allocation and stealing included), and advances every voice's
+// *control* state -- positions, the f32 phase recurrence, ramps, the envelope stage machine -- without
+// touching a single audio sample. At every 64-frame tile boundary and every write-call boundary it
+// emits a Segment snapshot; pass 2 (replay_kernel.cuh) renders all segments of the block in parallel.
+//
+// This is the serial part the reference's f32 recurrences force; everything per-sample
+// that can be replayed from a checkpoint is left to pass 2.
 #pragma once
 #include "voice.cuh"
 
 namespace pb {
 
-struct VoiceKernelArgs {
+constexpr uint32_t TILE = 64;  // frames per replay tile (== FileSourceImpl::SPEED_UPDATE_CHUNK_SIZE)
+
+struct SkeletonArgs {
   const GroupParams* groups;
   const uint32_t* group_list;         // groups of this launch (one size class)
   GroupState* gstate;
   VoiceState* voices;
   const DevBuffer* buffers;
   const DevEvent* events;
-  // chunk schedule: per mixer the absolute chunk boundaries of this time block
-  const uint64_t* chunk_bounds;       // concatenated
-  const uint32_t* mixer_chunk_begin;  // [n_mixers + 1] offsets into chunk_bounds for this block
-  float* group_bus;                   // [n_groups][block_frames][2]
+  const uint64_t* chunk_bounds;       // concatenated chunk boundaries of this time block
+  const uint32_t* mixer_chunk_begin;  // [n_mixers + 1]
   uint8_t* group_flags;               // [n_groups][max_chunks]: source produced output in chunk k
   uint32_t max_chunks;
   uint32_t block_frames;
   uint64_t block_start;
   RenderConsts rc;
-  uint32_t tile_frames;               // F
+  // segment output
+  Segment* segs;                      // [n_voices][seg_cap]
+  uint16_t* seg_first;                // [n_voices][n_tiles]
+  uint16_t* seg_count;                // [n_voices][n_tiles]
+  GroupSeg* gsegs;                    // [n_groups][seg_cap]
+  uint16_t* gseg_first;               // [n_groups][n_tiles]
+  uint16_t* gseg_count;               // [n_groups][n_tiles]
+  uint32_t seg_cap;
+  uint32_t n_tiles;
 };
 
 constexpr int VK_MAX_VOICES = 1024;
@@ -78,14 +90,10 @@ PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t fr
 }
 
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
-  extern __shared__ float s_tile[];  // [n_voices][2F]
+__global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   __shared__ VoiceHeader s_head[MAXT];
-  __shared__ uint16_t s_valid[MAXT];
   __shared__ GroupState s_gs;
   __shared__ uint32_t s_count;
-  __shared__ float s_ggain[128];  // generator-level per-sample gains of a tile (<= 2F)
-  __shared__ float s_gpl[64], s_gpr[64];
 
   const uint32_t g = a.group_list[blockIdx.x];
   const uint32_t tid = threadIdx.x;
@@ -96,7 +104,6 @@ __global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
   const bool mine = tid < nv;
   const float comp = a.rc.rate_comp;
   const uint32_t out_rate = a.rc.sample_rate;
-  const uint32_t F = a.tile_frames;
 
   VoiceState v;
   if (mine) {
@@ -104,12 +111,25 @@ __global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
     publish_header(s_head, tid, v);
   }
   if (tid == 0) s_gs = a.gstate[g];
+
+  // per-voice / per-group segment tables of this block
+  const uint32_t vidx = gp.first_voice + tid;
+  Segment* my_segs = a.segs + (size_t)vidx * a.seg_cap;
+  uint16_t* my_first = a.seg_first + (size_t)vidx * a.n_tiles;
+  uint16_t* my_count = a.seg_count + (size_t)vidx * a.n_tiles;
+  uint32_t n_segs = 0;
+  if (mine) for (uint32_t i = 0; i < a.n_tiles; ++i) my_count[i] = 0;
+  GroupSeg* g_segs = a.gsegs + (size_t)g * a.seg_cap;
+  uint16_t* g_first = a.gseg_first + (size_t)g * a.n_tiles;
+  uint16_t* g_count = a.gseg_count + (size_t)g * a.n_tiles;
+  uint32_t n_gsegs = 0;
+  for (uint32_t i = tid; i < a.n_tiles; i += blockDim.x) g_count[i] = 0;
   __syncthreads();
 
   const uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];
-  float* gbus = a.group_bus + (size_t)g * a.block_frames * 2;
   uint8_t* gflags = a.group_flags + (size_t)g * a.max_chunks;
   uint64_t my_frames = 0;
+  HistVals hv_unused;
 
   for (uint32_t k = cb; k + 1 < ce; ++k) {
     const uint64_t c0 = a.chunk_bounds[k], c1 = a.chunk_bounds[k + 1];
@@ -128,8 +148,6 @@ __global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
       if (tid == 0) gflags[k - cb] = 0;
       continue;
     }
-    // frames before the source starts stay silent
-    for (uint32_t i = tid; i < total * 2; i += blockDim.x) gbus[(size_t)boff * 2 + i] = 0.0f;
 
     while (total < len) {
       const uint64_t t = c0 + total;
@@ -143,9 +161,8 @@ __global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
       const uint32_t n = (uint32_t)min((uint64_t)(len - total), until_stop);
 
       // ---- Source::write(n frames at time t) -------------------------------------------------------
-      // 1. messages: stop first (it was force-pushed into the source queue before the events of this
-      //    chunk were... no: events were pushed at chunk start by process_events, the stop later) --
-      //    queue order = events of this chunk (only on the first call of the chunk), then Stop.
+      // 1. messages in queue order: the events process_events pushed at this chunk's start (consumed by
+      //    the first write call of the chunk), then a Stop the mixer force-pushed at stop_time.
       uint32_t ev_end_now = s_gs.ev_cursor;
       while (ev_end_now < gp.ev_end && a.events[ev_end_now].time <= c0) ++ev_end_now;
       for (uint32_t e = s_gs.ev_cursor; e < ev_end_now; ++e) {
@@ -223,7 +240,6 @@ __global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
       __syncthreads();
 
       // 2. does the source write at all? (sampler.rs:978-981 / preloaded.rs:400-403)
-      uint32_t written;
       bool group_writes;
       if (is_sampler) group_writes = !(s_gs.stopped || (s_gs.active_voices == 0 && !s_gs.stopping));
       else group_writes = true;
@@ -232,64 +248,59 @@ __global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
       cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
       bool call_open = false;
       if (group_writes && was_active) call_open = voice_begin_call(v, cc, gp, buf, n, comp, gp.has_env != 0);
-      if (!is_sampler) {
-        // a file source's written count = frames its single voice produces (short on EOF)
-        written = 0;
-      } else {
-        written = group_writes ? n : 0;
-      }
-
-      // generator-level gain / pan decisions for this call (player.rs:1075-1081)
-      bool g_vol_ramp = false, g_vol_scale = false, g_pan_ramp = false, g_pan_apply = false;
-      float g_pl = 1.0f, g_pr = 1.0f;
-      if (is_sampler && group_writes) {
-        g_vol_ramp = exp_need_ramp(s_gs.vol, comp);
-        g_vol_scale = !g_vol_ramp && fabsf(1.0f - s_gs.vol.target) > 0.000001f;
-        g_pan_ramp = exp_need_ramp(s_gs.pan, comp);
-        g_pan_apply = !g_pan_ramp && fabsf(s_gs.pan.target) > 0.000001f;
-        if (g_pan_apply) panning_factors(s_gs.pan.target, g_pl, g_pr);
-      }
-      const float g_vol_t = s_gs.vol.target;
       __syncthreads();
 
-      uint32_t file_written = 0;
-      if (group_writes) {
-        for (uint32_t t0 = 0; t0 < n; t0 += F) {
-          const uint32_t tl = min(F, n - t0);
-          uint32_t valid = 0;
-          if (call_open) {
-            if (buf.channels == 2) valid = voice_frames<2>(v, cc, gp, buf, out_rate, comp, tl, s_tile + (size_t)tid * 2 * F);
-            else valid = voice_frames<1>(v, cc, gp, buf, out_rate, comp, tl, s_tile + (size_t)tid * 2 * F);
-            my_frames += valid;
+      // 3. advance the voice through the call, one segment per (call x 64-frame tile)
+      const uint32_t call_off = boff + total;  // first frame of the call, relative to the block
+      uint32_t written_frames = 0;
+      if (call_open) {
+        uint32_t off = call_off, remaining = n;
+        while (remaining > 0 && !cc.ended) {
+          const uint32_t tile = off / TILE;
+          const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
+          if (n_segs < a.seg_cap) {
+            Segment& s = my_segs[n_segs];
+            s.v = v; s.c = cc; s.out_off = off; s.n = seg_len;
+            if (my_count[tile] == 0) my_first[tile] = (uint16_t)n_segs;
+            my_count[tile] += 1;
+            n_segs++;
           }
-          if (mine) s_valid[tid] = (uint16_t)valid;
-          if (!is_sampler && tid == 0) file_written += valid;
-          if (tid == 0 && (g_vol_ramp || g_pan_ramp)) {  // serial generator-level ramps for this tile
-            if (g_vol_ramp) for (uint32_t i = 0; i < tl * 2; ++i) s_ggain[i] = exp_next(s_gs.vol, comp);
-            if (g_pan_ramp) for (uint32_t i = 0; i < tl; ++i) panning_factors(exp_next(s_gs.pan, comp), s_gpl[i], s_gpr[i]);
+          uint32_t w;
+          if (buf.channels == 2) w = voice_frames<2, false>(v, cc, hv_unused, gp, buf, out_rate, comp, seg_len, nullptr);
+          else w = voice_frames<1, false>(v, cc, hv_unused, gp, buf, out_rate, comp, seg_len, nullptr);
+          written_frames += w;
+          off += w; remaining -= w;
+          if (w < seg_len) break;
+        }
+        my_frames += written_frames;
+        voice_end_call(v, cc, t + n);
+      }
+      // generator-level gain / pan (player.rs:1075-1081): checkpoint per (call x tile), advance ramps
+      if (is_sampler && group_writes && tid == 0) {
+        const bool vol_ramp = exp_need_ramp(s_gs.vol, comp);
+        const bool vol_scale = !vol_ramp && fabsf(1.0f - s_gs.vol.target) > 0.000001f;
+        const bool pan_ramp = exp_need_ramp(s_gs.pan, comp);
+        const bool pan_apply = !pan_ramp && fabsf(s_gs.pan.target) > 0.000001f;
+        const uint32_t flags = (vol_ramp ? 1u : 0u) | (vol_scale ? 2u : 0u) | (pan_ramp ? 4u : 0u) | (pan_apply ? 8u : 0u);
+        uint32_t off = call_off, remaining = n;
+        while (remaining > 0) {
+          const uint32_t tile = off / TILE;
+          const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
+          if (n_gsegs < a.seg_cap) {
+            GroupSeg& s = g_segs[n_gsegs];
+            s.vol = s_gs.vol; s.pan = s_gs.pan; s.out_off = off; s.n = seg_len; s.flags = flags;
+            if (g_count[tile] == 0) g_first[tile] = (uint16_t)n_gsegs;
+            g_count[tile] += 1;
+            n_gsegs++;
           }
-          __syncthreads();
-          for (uint32_t col = tid; col < tl * 2; col += blockDim.x) {
-            const uint32_t fr = col >> 1;
-            float s = 0.0f;
-            if (is_sampler) {
-              for (uint32_t i = 0; i < nv; ++i)
-                if (fr < s_valid[i]) s += s_tile[(size_t)i * 2 * F + col];
-              if (g_vol_ramp) s *= s_ggain[col];
-              else if (g_vol_scale) s *= g_vol_t;
-              if (g_pan_ramp) s *= (col & 1) ? s_gpr[fr] : s_gpl[fr];
-              else if (g_pan_apply) s *= (col & 1) ? g_pr : g_pl;
-            } else {
-              s = fr < s_valid[0] ? s_tile[col] : 0.0f;
-            }
-            gbus[(size_t)(boff + total + t0) * 2 + col] = s;
-          }
-          __syncthreads();
+          if (vol_ramp) for (uint32_t i = 0; i < seg_len * 2; ++i) (void)exp_next(s_gs.vol, comp);
+          if (pan_ramp) for (uint32_t i = 0; i < seg_len; ++i) (void)exp_next(s_gs.pan, comp);
+          off += seg_len; remaining -= seg_len;
         }
       }
-      // 3. end of the write call: file finish checks, voice reset, active voice count
-      if (call_open) voice_end_call(v, cc, t + n);
+      uint32_t written;
       if (is_sampler) {
+        written = group_writes ? n : 0;
         if (was_active && group_writes) {
           // SamplerVoice::process epilogue (voice.rs:488-502)
           if (v.finished || (gp.has_env && v.env_stage == ENV_IDLE)) voice_reset(v);
@@ -307,7 +318,8 @@ __global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
         }
         __syncthreads();
       } else {
-        if (tid == 0) s_count = file_written;
+        // a file source's written count = frames its single voice produced (short on EOF)
+        if (tid == 0) s_count = written_frames;
         __syncthreads();
         written = s_count;
         __syncthreads();
@@ -326,8 +338,6 @@ __global__ void __launch_bounds__(MAXT) voice_kernel(VoiceKernelArgs a) {
         break;
       }
     }
-    // frames the source did not write stay silent
-    for (uint32_t i = tid + total * 2; i < len * 2; i += blockDim.x) gbus[(size_t)boff * 2 + i] = 0.0f;
     if (tid == 0) gflags[k - cb] = produced ? 1 : 0;
     __syncthreads();
   }

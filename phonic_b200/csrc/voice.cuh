@@ -87,9 +87,7 @@ PB_DEV void update_speed(VoiceState& v, uint32_t in_rate, uint32_t out_rate) {
 
 PB_DEV void resampler_reset(VoiceState& v) {
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v.hist[c][i] = 0.0f;
+  for (int i = 0; i < 4; ++i) v.hidx[i] = -1;
   v.sub_pos = 0.0f;
   v.initialized = 0;
 }
@@ -291,9 +289,33 @@ PB_DEV void after_process_call(VoiceState& v, CallCtx& c) {
   }
 }
 
-// One output frame of the resampler inside write_buffer. Returns false on the EOF break.
+// The interpolator history as values (replay) next to the indices every pass keeps in VoiceState.
+struct HistVals { float h[2][4]; };
+
 template <int CC>
-PB_DEV bool resample_frame(VoiceState& v, CallCtx& c, const float* __restrict__ buf, float& x0, float& x1) {
+PB_DEV void hist_load(HistVals& hv, const VoiceState& v, const float* __restrict__ buf) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hv.h[0][i] = v.hidx[i] >= 0 ? __ldg(buf + v.hidx[i]) : 0.0f;
+    hv.h[1][i] = (CC == 2 && v.hidx[i] >= 0) ? __ldg(buf + v.hidx[i] + 1) : 0.0f;
+  }
+}
+
+// CubicInterpolator::push_sample for the frame at v.playback_pos (cubic.rs:117-122)
+template <int CC, bool AUDIO>
+PB_DEV void push_frame(VoiceState& v, HistVals& hv, const float* __restrict__ buf) {
+  v.hidx[3] = v.hidx[2]; v.hidx[2] = v.hidx[1]; v.hidx[1] = v.hidx[0]; v.hidx[0] = (int32_t)v.playback_pos;
+  if (AUDIO) {
+    hist_push(hv.h[0], __ldg(buf + v.playback_pos));
+    if (CC == 2) hist_push(hv.h[1], __ldg(buf + v.playback_pos + 1));
+  }
+  v.playback_pos += CC;
+}
+
+// One output frame of the resampler inside write_buffer. Returns false on the EOF break.
+// AUDIO=false advances exactly the same state (positions, phase, history indices) without touching samples.
+template <int CC, bool AUDIO>
+PB_DEV bool resample_frame(VoiceState& v, CallCtx& c, HistVals& hv, const float* __restrict__ buf, float& x0, float& x1) {
   for (;;) {
     if (c.new_call) {  // CubicInterpolator::process prologue (cubic.rs:47-69)
       c.new_call = false;
@@ -303,18 +325,16 @@ PB_DEV bool resample_frame(VoiceState& v, CallCtx& c, const float* __restrict__ 
       if (!bypass && !v.initialized && avail >= 3) {
         v.initialized = 1;
 #pragma unroll
-        for (int f = 0; f < 3; ++f) {
-          hist_push(v.hist[0], __ldg(buf + v.playback_pos));
-          if (CC == 2) hist_push(v.hist[1], __ldg(buf + v.playback_pos + 1));
-          v.playback_pos += CC;
-        }
+        for (int f = 0; f < 3; ++f) push_frame<CC, AUDIO>(v, hv, buf);
       }
     }
     const bool has_input = v.playback_pos < c.le;
     if (fabsf(v.ratio - 1.0f) < 0.000001f) {  // bypass copy (cubic.rs:53-58)
       if (has_input) {
-        x0 = __ldg(buf + v.playback_pos);
-        x1 = CC == 2 ? __ldg(buf + v.playback_pos + 1) : x0;
+        if (AUDIO) {
+          x0 = __ldg(buf + v.playback_pos);
+          x1 = CC == 2 ? __ldg(buf + v.playback_pos + 1) : x0;
+        }
         v.playback_pos += CC;
         c.produced_in_call++;
         return true;
@@ -323,17 +343,17 @@ PB_DEV bool resample_frame(VoiceState& v, CallCtx& c, const float* __restrict__ 
       bool ok = true;
       if (v.sub_pos >= 1.0f) {
         if (has_input) {
-          hist_push(v.hist[0], __ldg(buf + v.playback_pos));
-          if (CC == 2) hist_push(v.hist[1], __ldg(buf + v.playback_pos + 1));
-          v.playback_pos += CC;
+          push_frame<CC, AUDIO>(v, hv, buf);
           v.sub_pos -= 1.0f;
         } else {
           ok = false;
         }
       }
       if (ok) {
-        x0 = hermite(v.hist[0], v.sub_pos);
-        x1 = CC == 2 ? hermite(v.hist[1], v.sub_pos) : x0;
+        if (AUDIO) {
+          x0 = hermite(hv.h[0], v.sub_pos);
+          x1 = CC == 2 ? hermite(hv.h[1], v.sub_pos) : x0;
+        }
         v.sub_pos += v.ratio;
         c.produced_in_call++;
         return true;
@@ -342,16 +362,16 @@ PB_DEV bool resample_frame(VoiceState& v, CallCtx& c, const float* __restrict__ 
       bool ok = true;
       while (v.sub_pos < v.ratio) {
         if (v.playback_pos >= c.le) { ok = false; break; }
-        hist_push(v.hist[0], __ldg(buf + v.playback_pos));
-        if (CC == 2) hist_push(v.hist[1], __ldg(buf + v.playback_pos + 1));
-        v.playback_pos += CC;
+        push_frame<CC, AUDIO>(v, hv, buf);
         v.sub_pos += 1.0f;
       }
       if (ok) {
         v.sub_pos -= v.ratio;
-        float fr = 1.0f - v.sub_pos;
-        x0 = hermite(v.hist[0], fr);
-        x1 = CC == 2 ? hermite(v.hist[1], fr) : x0;
+        if (AUDIO) {
+          float fr = 1.0f - v.sub_pos;
+          x0 = hermite(hv.h[0], fr);
+          x1 = CC == 2 ? hermite(hv.h[1], fr) : x0;
+        }
         c.produced_in_call++;
         return true;
       }
@@ -363,11 +383,13 @@ PB_DEV bool resample_frame(VoiceState& v, CallCtx& c, const float* __restrict__ 
   }
 }
 
-// Render up to `n` frames of the current write call into `out` (interleaved stereo, stride 2).
-// Returns the number of frames written (< n only when the source ran dry).
-template <int CC>
-PB_DEV uint32_t voice_frames(VoiceState& v, CallCtx& c, const GroupParams& gp, const DevBuffer& b, uint32_t out_rate,
-                             float comp, uint32_t n, float* __restrict__ out) {
+// Advance the current write call by up to `n` frames. AUDIO=true renders them into `out` (interleaved
+// stereo); AUDIO=false (the skeleton pass) only advances the state: positions, f32 phase and ramp
+// recurrences, envelope stage machine. Returns the number of frames written (< n only when the
+// source ran dry).
+template <int CC, bool AUDIO>
+PB_DEV uint32_t voice_frames(VoiceState& v, CallCtx& c, HistVals& hv, const GroupParams& gp, const DevBuffer& b,
+                             uint32_t out_rate, float comp, uint32_t n, float* __restrict__ out) {
   const float* __restrict__ buf = b.data;
   uint32_t f = 0;
   for (; f < n && !c.ended; ++f) {
@@ -384,8 +406,8 @@ PB_DEV uint32_t voice_frames(VoiceState& v, CallCtx& c, const GroupParams& gp, c
       loop_range_samples(v, b, c.ls, c.le);
       c.new_call = true;
     }
-    float x0, x1;
-    if (!resample_frame<CC>(v, c, buf, x0, x1)) { c.ended = true; break; }
+    float x0 = 0.0f, x1 = 0.0f;
+    if (!resample_frame<CC, AUDIO>(v, c, hv, buf, x0, x1)) { c.ended = true; break; }
     c.call_left--;
     c.chunk_left--;
     if (c.gliding) v.to_next_speed_update--;
@@ -405,8 +427,8 @@ PB_DEV uint32_t voice_frames(VoiceState& v, CallCtx& c, const GroupParams& gp, c
     // PannedSource
     if (c.pan_ramp) {
       float pl, pr;
-      panning_factors(exp_next(v.pan, comp), pl, pr);
-      l *= pl; r *= pr;
+      float p = exp_next(v.pan, comp);
+      if (AUDIO) { panning_factors(p, pl, pr); l *= pl; r *= pr; }
     } else if (c.pan_apply) {
       l *= c.pan_l; r *= c.pan_r;
     }
@@ -415,8 +437,10 @@ PB_DEV uint32_t voice_frames(VoiceState& v, CallCtx& c, const GroupParams& gp, c
       float e = c.env_per_frame ? env_run(v, gp) : c.env_const;
       l *= e; r *= e;
     }
-    out[2 * f] = l;
-    out[2 * f + 1] = r;
+    if (AUDIO) {
+      out[2 * f] = l;
+      out[2 * f + 1] = r;
+    }
   }
   return f;
 }
@@ -433,5 +457,22 @@ PB_DEV void voice_end_call(VoiceState& v, CallCtx& c, uint64_t call_end_frame) {
     v.end_frame = call_end_frame;
   }
 }
+
+// Snapshot the skeleton pass emits at the start of every replay segment: the complete voice state and
+// write-call context, from which a replay thread reproduces the next `n` frames bit for bit.
+struct Segment {
+  VoiceState v;
+  CallCtx c;
+  uint32_t out_off;  // first frame, relative to the time block
+  uint32_t n;        // frames requested (the replay may produce fewer when the source runs dry)
+};
+
+// Generator-level gain/pan checkpoint (AmplifiedSource/PannedSource around a Sampler, player.rs:1075-1081)
+struct GroupSeg {
+  ExpSm vol, pan;
+  uint32_t out_off, n;
+  uint32_t flags;  // bit0 vol_ramp, bit1 vol_scale, bit2 pan_ramp, bit3 pan_apply
+  uint32_t _pad;
+};
 
 }  // namespace pb
