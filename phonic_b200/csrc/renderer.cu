@@ -183,6 +183,7 @@ VoiceState default_voice(const DevBuffer& b, uint32_t out_rate, double speed) {
   v.repeat = b.loop_start >= 0 ? REPEAT_FOREVER : 0;
   v.repeat_count = v.repeat;
   v.loop_ovr_start = -1; v.loop_ovr_end = -1;
+  for (int i = 0; i < 4; ++i) v.hidx[i] = -1;  // CubicInterpolator::new: input = [0.0; 4]
   uint32_t rate = f64_as_u32_h((double)out_rate / speed);  // file/common.rs:78-82
   v.ratio = (float)((double)b.sample_rate / (double)rate);
   v.fader_state = FADER_STOPPED; v.fader_cur = 1.0f; v.fader_tgt = 1.0f; v.fader_inertia = 1.0f;
@@ -884,7 +885,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     const uint32_t blen = (uint32_t)std::min<uint64_t>(tb, p1 - b0);
     const uint32_t slot = b % RING;
     // pass 1 (skeleton) may not overwrite the segment slot the replay of block b-RING still reads
-    if (b >= RING) CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_r1[b - RING], 0));
+    // ... nor the group-flag slot the mixer of block b-RING still reads
+    if (b >= RING) { CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_r1[b - RING], 0)); CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_m1[b - RING], 0)); }
     CUDA_TRY(cudaEventRecord(ev_v0[b], r->sv));
     SkeletonArgs va;
     va.groups = r->d_groups.p; va.gstate = r->d_gstate.p; va.voices = r->d_voices.p; va.buffers = r->d_buffers.p;
