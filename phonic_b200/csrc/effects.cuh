@@ -175,25 +175,101 @@ struct FxCtx {
   double* aux_arena;
 };
 
-// ---- FilterEffect::process (filter.rs:166-201): lanes 0/1 = channels ------------------------------------
-PB_DEV void filter_process(FilterState& s, const FxCtx& cx, float* buf, uint32_t frames, uint32_t lane) {
+// A chunk staged in shared memory, planar and padded (one pad word per 32 samples) so that both the
+// frame-serial effects and the lane-per-sub-block scans access it without bank conflicts.
+struct ChunkBuf {
+  float* ch[2];
+  double* scratch;   // [2][pidx(1024) + 1] zero-state responses of the scan
+  double* lane_state;// [2][32][2] sub-block end states / start states
+};
+PB_DEV uint32_t pidx(uint32_t f) { return f + (f >> 5); }
+#define CB_L(f) cb.ch[0][pidx(f)]
+#define CB_R(f) cb.ch[1][pidx(f)]
+
+
+// ---- block-parallel evaluation of one time-invariant biquad over a staged chunk ---------------------------
+// The Cytomic SVF tick (biquad.rs:314-323) is linear in (ic1eq, ic2eq, x):
+//   s' = A s + B x,  y = C s + D x,   A = [[2a1-1, -2a2], [2a2, 1-2a3]]
+// One warp handles one channel: lane j runs the *reference's own tick* over sub-block j from a zero state
+// (zero-state response y0 and end state e_j, f64), lane 0 then chains the true sub-block start states
+// s_{j+1} = A^B s_j + e_j, and every lane adds the homogeneous part y[n] = y0[n] + (C A^k) s_j.
+// Exact in real arithmetic; in f64 it differs from the frame-serial evaluation by O(1e-16) relative, far
+// below the f32 output quantum. Only used while no parameter is ramping.
+struct Mat2 { double a, b, c, d; };
+PB_DEV Mat2 mat_mul(const Mat2& x, const Mat2& y) {
+  return Mat2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+}
+PB_DEV Mat2 mat_pow(Mat2 m, uint32_t k) {
+  Mat2 r{1.0, 0.0, 0.0, 1.0};
+  while (k) {
+    if (k & 1u) r = mat_mul(r, m);
+    m = mat_mul(m, m);
+    k >>= 1;
+  }
+  return r;
+}
+PB_DEV void biquad_scan_channel(const BiquadCoef& c, double& ic1_io, double& ic2_io, float* x, double* y0, double* lane_state,
+                                uint32_t len, uint32_t lane) {
+  const uint32_t B = (len + 31) / 32;             // samples per lane
+  const uint32_t lo = min(lane * B, len), hi = min(lo + B, len);
+  const Mat2 A{2.0 * c.a1 - 1.0, -2.0 * c.a2, 2.0 * c.a2, 1.0 - 2.0 * c.a3};
+  // phase 1: zero-state response of my sub-block with the reference tick
+  double ic1 = 0.0, ic2 = 0.0;
+  for (uint32_t n = lo; n < hi; ++n) y0[pidx(n)] = biquad_tick(c, ic1, ic2, (double)x[pidx(n)]);
+  lane_state[lane * 2] = ic1;
+  lane_state[lane * 2 + 1] = ic2;
+  __syncwarp();
+  // phase 2: chain the sub-block start states (lane 0), leave them in lane_state
+  if (lane == 0) {
+    const Mat2 AB = mat_pow(A, B);
+    double s1 = ic1_io, s2 = ic2_io;
+    for (uint32_t j = 0; j < 32; ++j) {
+      const uint32_t jl = min(j * B, len), jh = min(jl + B, len);
+      const double e1 = lane_state[j * 2], e2 = lane_state[j * 2 + 1];
+      lane_state[j * 2] = s1;
+      lane_state[j * 2 + 1] = s2;
+      if (jh > jl) {
+        const Mat2 P = (jh - jl == B) ? AB : mat_pow(A, jh - jl);
+        const double n1 = P.a * s1 + P.b * s2 + e1;
+        const double n2 = P.c * s1 + P.d * s2 + e2;
+        s1 = n1; s2 = n2;
+      }
+    }
+    ic1_io = s1; ic2_io = s2;
+  }
+  __syncwarp();
+  // phase 3: add the homogeneous response of my sub-block's true start state
+  const double s1 = lane_state[lane * 2], s2 = lane_state[lane * 2 + 1];
+  // y = C s + D x with C = (m1 a1 + m2 a2, -m1 a2 + m2 (1 - a3))
+  const double C1 = c.m1 * c.a1 + c.m2 * c.a2, C2 = -c.m1 * c.a2 + c.m2 * (1.0 - c.a3);
+  double h1 = s1, h2 = s2;  // A^k s
+  for (uint32_t n = lo; n < hi; ++n) {
+    x[pidx(n)] = (float)(y0[pidx(n)] + (C1 * h1 + C2 * h2));
+    const double t1 = A.a * h1 + A.b * h2, t2 = A.c * h1 + A.d * h2;
+    h1 = t1; h2 = t2;
+  }
+  __syncwarp();
+}
+
+// ---- FilterEffect::process (filter.rs:166-201): warps 0/1 = channels ---------------------------------------
+PB_DEV void filter_process(FilterState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t lane, uint32_t warp) {
   const bool ramp = exp_need_ramp(s.cutoff, cx.comp) || lin_need_ramp(s.q);
   if (ramp) {
-    // coefficients are shared by both channels and re-derived per frame: keep it on one lane
-    if (lane == 0) {
+    // coefficients are shared by both channels and re-derived per frame: frame-serial on one thread
+    if (lane == 0 && warp == 0) {
       for (uint32_t f = 0; f < frames; ++f) {
         float c = fminf(fmaxf(exp_next(s.cutoff, cx.comp), 20.0f), (float)cx.sample_rate / 2.0f);
         float q = lin_next(s.q);
         biquad_set(s.coef, s.filter_type, cx.sample_rate, c, q, 0.0f);
-        buf[2 * f] = (float)biquad_tick(s.coef, s.ic1[0], s.ic2[0], (double)buf[2 * f]);
-        buf[2 * f + 1] = (float)biquad_tick(s.coef, s.ic1[1], s.ic2[1], (double)buf[2 * f + 1]);
+        CB_L(f) = (float)biquad_tick(s.coef, s.ic1[0], s.ic2[0], (double)CB_L(f));
+        CB_R(f) = (float)biquad_tick(s.coef, s.ic1[1], s.ic2[1], (double)CB_R(f));
       }
     }
-  } else if (lane < 2) {
+  } else if (warp < 2) {
     const BiquadCoef c = s.coef;
-    double ic1 = s.ic1[lane], ic2 = s.ic2[lane];
-    for (uint32_t f = 0; f < frames; ++f) buf[2 * f + lane] = (float)biquad_tick(c, ic1, ic2, (double)buf[2 * f + lane]);
-    s.ic1[lane] = ic1; s.ic2[lane] = ic2;
+    double ic1 = s.ic1[warp], ic2 = s.ic2[warp];
+    biquad_scan_channel(c, ic1, ic2, cb.ch[warp], cb.scratch + (size_t)warp * 1060, cb.lane_state + (size_t)warp * 64, frames, lane);
+    if (lane == 0) { s.ic1[warp] = ic1; s.ic2[warp] = ic2; }
   }
 }
 
@@ -205,11 +281,11 @@ PB_DEV void eq5_update_coefficients(Eq5State& s, const FxCtx& cx) {
     biquad_set(s.coef[i], eq5_band_type(i), cx.sample_rate, c, s.bws[i].current, s.gains[i].current);
   }
 }
-PB_DEV void eq5_process(Eq5State& s, const FxCtx& cx, float* buf, uint32_t frames, uint32_t lane) {
+PB_DEV void eq5_process(Eq5State& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t lane, uint32_t warp) {
   bool ramp = false;
   for (int i = 0; i < 5; ++i) ramp |= exp_need_ramp(s.freqs[i], cx.comp) || lin_need_ramp(s.bws[i]) || exp_need_ramp(s.gains[i], cx.comp);
   if (ramp) {
-    if (lane == 0) {
+    if (lane == 0 && warp == 0) {
       for (uint32_t f = 0; f < frames; ++f) {
         for (int i = 0; i < 5; ++i) {  // ramp_filter_coefficients
           float bw = lin_next(s.bws[i]);
@@ -219,31 +295,29 @@ PB_DEV void eq5_process(Eq5State& s, const FxCtx& cx, float* buf, uint32_t frame
           biquad_set(s.coef[i], eq5_band_type(i), cx.sample_rate, c, q, g);
         }
         for (int ch = 0; ch < 2; ++ch) {
-          float x = buf[2 * f + ch];
+          float x = cb.ch[ch][pidx(f)];
           for (int i = 0; i < 5; ++i) x = (float)biquad_tick(s.coef[i], s.ic1[ch][i], s.ic2[ch][i], (double)x);
-          buf[2 * f + ch] = x;
+          cb.ch[ch][pidx(f)] = x;
         }
       }
     }
-  } else if (lane < 2) {
-    double ic1[5], ic2[5];
-    for (int i = 0; i < 5; ++i) { ic1[i] = s.ic1[lane][i]; ic2[i] = s.ic2[lane][i]; }
-    for (uint32_t f = 0; f < frames; ++f) {
-      float x = buf[2 * f + lane];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) x = (float)biquad_tick(s.coef[i], ic1[i], ic2[i], (double)x);
-      buf[2 * f + lane] = x;
+  } else if (warp < 2) {
+    // five cascaded stages, each cast back to f32 before the next one (eq5.rs:317-321)
+    for (int i = 0; i < 5; ++i) {
+      const BiquadCoef c = s.coef[i];
+      double ic1 = s.ic1[warp][i], ic2 = s.ic2[warp][i];
+      biquad_scan_channel(c, ic1, ic2, cb.ch[warp], cb.scratch + (size_t)warp * 1060, cb.lane_state + (size_t)warp * 64, frames, lane);
+      if (lane == 0) { s.ic1[warp][i] = ic1; s.ic2[warp][i] = ic2; }
     }
-    for (int i = 0; i < 5; ++i) { s.ic1[lane][i] = ic1[i]; s.ic2[lane][i] = ic2[i]; }
   }
 }
 
 // ---- CompressorEffect::process (compressor.rs:230-294) + LookupDelayLine (delay.rs:206-265) -------------
-PB_DEV void comp_process(CompState& s, const FxCtx& cx, float* buf, uint32_t frames) {
+PB_DEV void comp_process(CompState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames) {
   double* line = cx.aux_arena + s.aux;
   const bool limiter = s.ratio >= 20.0f;
   for (uint32_t f = 0; f < frames; ++f) {
-    const float in0 = buf[2 * f], in1 = buf[2 * f + 1];
+    const float in0 = CB_L(f), in1 = CB_R(f);
     float d0 = in0, d1 = in1;
     if (s.delay_frames != 0) {
       uint32_t read_index = (s.write_pos + s.buf_frames - s.delay_frames) & s.mask;
@@ -289,18 +363,18 @@ PB_DEV void comp_process(CompState& s, const FxCtx& cx, float* buf, uint32_t fra
     }
     float makeup = exp_next(s.makeup, cx.comp);
     float total_gain = db_to_linear_dev(makeup - gr_db);
-    buf[2 * f] = d0 * total_gain;
-    buf[2 * f + 1] = d1 * total_gain;
+    CB_L(f) = d0 * total_gain;
+    CB_R(f) = d1 * total_gain;
   }
 }
 
 // ---- ChorusEffect::process (chorus.rs:311-394) -----------------------------------------------------------
-PB_DEV void chorus_process(ChorusState& s, const FxCtx& cx, float* buf, uint32_t frames) {
+PB_DEV void chorus_process(ChorusState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames) {
   double* bl = cx.aux_arena + s.dl.aux;
   double* br = cx.aux_arena + s.dr.aux;
   const float srf = (float)cx.sample_rate;
   for (uint32_t f = 0; f < frames; ++f) {
-    const float li = buf[2 * f], ri = buf[2 * f + 1];
+    const float li = CB_L(f), ri = CB_R(f);
     float delay_ms = spring_next(s.delay, cx.comp);
     float depth = exp_next(s.depth, cx.comp);
     float fb = fminf(fmaxf(exp_next(s.feedback, cx.comp), -0.999f), 0.999f);
@@ -328,8 +402,8 @@ PB_DEV void chorus_process(ChorusState& s, const FxCtx& cx, float* buf, uint32_t
     float rpos = 2.0f + delay_in_samples + (1.0f + rlfo) * depth_in_samples;
     float lo = idelay_process(s.dl, bl, (float)fl, fb, lpos);
     float ro = idelay_process(s.dr, br, (float)fr, fb, rpos);
-    buf[2 * f] = li * dry + lo * wet;
-    buf[2 * f + 1] = ri * dry + ro * wet;
+    CB_L(f) = li * dry + lo * wet;
+    CB_R(f) = ri * dry + ro * wet;
   }
   const double PI = 3.14159265358979323846;
   double phase_inc = 2.0 * PI * (double)s.rate.current / (double)cx.sample_rate;
@@ -354,12 +428,12 @@ PB_DEV float delay_feedback_path(const SvfCoef& c, double& ic1, double& ic2, dou
   float clean = (float)y1;
   return fminf(fmaxf(clean, -4.0f), 4.0f);
 }
-PB_DEV void delay_process(DelayState& s, const FxCtx& cx, float* buf, uint32_t frames) {
+PB_DEV void delay_process(DelayState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames) {
   double* bl = cx.aux_arena + s.dl.aux;
   double* br = cx.aux_arena + s.dr.aux;
   const float srf = (float)cx.sample_rate;
   for (uint32_t f = 0; f < frames; ++f) {
-    const float li = buf[2 * f], ri = buf[2 * f + 1];
+    const float li = CB_L(f), ri = CB_R(f);
     float lfo_val = lfo_run(s.lfo);
     if (exp_need_ramp(s.lfo_rate, cx.comp)) { float r = exp_next(s.lfo_rate, cx.comp); lfo_set_rate(s.lfo, cx.sample_rate, (double)r); }
     float base_delay_ms = spring_next(s.delay_time, cx.comp);
@@ -404,8 +478,8 @@ PB_DEV void delay_process(DelayState& s, const FxCtx& cx, float* buf, uint32_t f
     float orr = ri * dry_gain + wet_r * wet_gain;
     float mid = (ol + orr) * 0.5f;
     float side = (ol - orr) * 0.5f;
-    buf[2 * f] = mid + side * width;
-    buf[2 * f + 1] = mid - side * width;
+    CB_L(f) = mid + side * width;
+    CB_R(f) = mid - side * width;
   }
 }
 
@@ -447,9 +521,9 @@ PB_DEV void rv_allpass(RvAllpass& a, double* __restrict__ b, double& l, double& 
   ol += b[a.write_pos * 2]; orr += b[a.write_pos * 2 + 1];
   l = ol; r = orr;
 }
-PB_DEV void reverb_frame(ReverbState& s, const FxCtx& cx, float* frame, double blend, double regen, uint32_t predelay, double w) {
+PB_DEV void reverb_frame(ReverbState& s, const FxCtx& cx, float& frame0, float& frame1, double blend, double regen, uint32_t predelay, double w) {
   const double vib_speed = 0.1, vib_depth = 7.0;
-  double il = (double)frame[0], ir = (double)frame[1];
+  double il = (double)frame0, ir = (double)frame1;
   if (fabs(il) < 1.18e-23) il = (double)s.fpd_l * 1.18e-17;
   if (fabs(ir) < 1.18e-23) ir = (double)s.fpd_r * 1.18e-17;
   const double dry_l = il, dry_r = ir;
@@ -518,9 +592,9 @@ PB_DEV void reverb_frame(ReverbState& s, const FxCtx& cx, float* frame, double b
   il = biquad_tick(s.cc, s.c_ic[0][0], s.c_ic[0][1], il);
   ir = biquad_tick(s.cc, s.c_ic[1][0], s.c_ic[1][1], ir);
   if (w != 1.0) { il += dry_l * (1.0 - w); ir += dry_r * (1.0 - w); }
-  frame[0] = (float)il; frame[1] = (float)ir;
+  frame0 = (float)il; frame1 = (float)ir;
 }
-PB_DEV void reverb_process(ReverbState& s, const FxCtx& cx, float* buf, uint32_t frames) {
+PB_DEV void reverb_process(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames) {
   if (lin_need_ramp(s.room) || exp_need_ramp(s.wet, cx.comp)) {
     for (uint32_t f = 0; f < frames; ++f) {
       double room = (double)lin_next(s.room);
@@ -528,7 +602,7 @@ PB_DEV void reverb_process(ReverbState& s, const FxCtx& cx, float* buf, uint32_t
       RvDerived d = reverb_derive(room, w);
       uint32_t predelay = reverb_update_sizes(s, d.size);
       reverb_update_filters(s, cx, d.cutoff);
-      reverb_frame(s, cx, buf + 2 * f, d.blend, d.regen, predelay, w);
+      reverb_frame(s, cx, CB_L(f), CB_R(f), d.blend, d.regen, predelay, w);
     }
   } else {
     double room = (double)s.room.target;
@@ -536,7 +610,7 @@ PB_DEV void reverb_process(ReverbState& s, const FxCtx& cx, float* buf, uint32_t
     RvDerived d = reverb_derive(room, w);
     uint32_t predelay = reverb_update_sizes(s, d.size);
     reverb_update_filters(s, cx, d.cutoff);
-    for (uint32_t f = 0; f < frames; ++f) reverb_frame(s, cx, buf + 2 * f, d.blend, d.regen, predelay, w);
+    for (uint32_t f = 0; f < frames; ++f) reverb_frame(s, cx, CB_L(f), CB_R(f), d.blend, d.regen, predelay, w);
   }
 }
 
@@ -686,16 +760,17 @@ PB_DEV void fx_apply_param(FxHeader& h, const FxCtx& cx, const FxParamEvent& e) 
 #undef CC4
 }
 
-// Effect::process dispatch; `lane` = lane id within the effect warp
-PB_DEV void fx_process(const FxHeader& h, const FxCtx& cx, float* buf, uint32_t frames, uint32_t lane) {
+// Effect::process dispatch, called by every thread of the mixer CTA
+PB_DEV void fx_process(const FxHeader& h, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t tid) {
+  const uint32_t lane = tid & 31, warp = tid >> 5;
   uint8_t* st = cx.state_arena + h.state_offset;
   switch (h.kind) {
-    case FX_FILTER: filter_process(*(FilterState*)st, cx, buf, frames, lane); break;
-    case FX_EQ5: eq5_process(*(Eq5State*)st, cx, buf, frames, lane); break;
-    case FX_COMPRESSOR: if (lane == 0) comp_process(*(CompState*)st, cx, buf, frames); break;
-    case FX_CHORUS: if (lane == 0) chorus_process(*(ChorusState*)st, cx, buf, frames); break;
-    case FX_DELAY: if (lane == 0) delay_process(*(DelayState*)st, cx, buf, frames); break;
-    case FX_REVERB: if (lane == 0) reverb_process(*(ReverbState*)st, cx, buf, frames); break;
+    case FX_FILTER: filter_process(*(FilterState*)st, cx, cb, frames, lane, warp); break;
+    case FX_EQ5: eq5_process(*(Eq5State*)st, cx, cb, frames, lane, warp); break;
+    case FX_COMPRESSOR: if (tid == 0) comp_process(*(CompState*)st, cx, cb, frames); break;
+    case FX_CHORUS: if (tid == 0) chorus_process(*(ChorusState*)st, cx, cb, frames); break;
+    case FX_DELAY: if (tid == 0) delay_process(*(DelayState*)st, cx, cb, frames); break;
+    case FX_REVERB: if (tid == 0) reverb_process(*(ReverbState*)st, cx, cb, frames); break;
   }
 }
 

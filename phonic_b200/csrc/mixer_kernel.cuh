@@ -1,10 +1,15 @@
-// Mixer kernel: one CTA per mixer of one tree level. Walks the mixer's own chunk schedule for the time
-// block; per chunk it (1) sums gated sub-mixer buses then source (group) buses in the reference's
-// order (MixedSource::process_sub_mixers / process_sources, src/source/mixed.rs:505-624), (2) runs the
-// effect chain with the auto-bypass state machine (EffectProcessor::process, mixed/effect.rs:56-145) on
-// warp 0, (3) at every *parent* chunk end evaluates the sub-mixer silence gate
-// (SubMixerProcessor::process, mixed/submixer.rs:47-77) with an exact max|x| reduction. The main mixer
-// additionally applies the WavStream master volume per output block (src/output/wav.rs:237).
+// Mixer kernels, launched per tree level (deepest first) for every time block.
+//
+// mix_sum_kernel   (M1): bus[f] = sum of gated sub-mixer buses then source (group) buses, in the
+//                  reference's order (MixedSource::process_sub_mixers / process_sources,
+//                  src/source/mixed.rs:505-624). Fully parallel over frames.
+// mix_fx_kernel    (M2): one CTA per mixer walks the mixer's own chunk schedule: effect parameter
+//                  events, the effect chain with the auto-bypass state machine
+//                  (EffectProcessor::process, mixed/effect.rs:56-145) on a chunk staged in shared
+//                  memory, the sub-mixer silence gate at every *parent* chunk end
+//                  (SubMixerProcessor::process, mixed/submixer.rs:47-77) with an exact max|x| reduction,
+//                  and for the main mixer the WavStream master volume per 1024-frame block
+//                  (src/output/wav.rs:237) plus the final output store.
 #pragma once
 #include "effects.cuh"
 
@@ -27,6 +32,7 @@ struct MixerKernelArgs {
   uint8_t* mixer_flags;           // [n_mixers][max_chunks]: audible per *parent* chunk
   uint32_t max_chunks;
   uint32_t block_frames;
+  uint32_t block_len;             // frames actually rendered in this block
   uint64_t block_start;
   // main mixer output
   float* out;                     // device output for this block (interleaved stereo) or nullptr
@@ -37,110 +43,159 @@ struct MixerKernelArgs {
 PB_DEV uint64_t sat_sub_u64(uint64_t a, uint64_t b) { return a > b ? a - b : 0; }
 PB_DEV uint64_t sat_add_u64(uint64_t a, uint64_t b) { return (a > UINT64_MAX - b) ? UINT64_MAX : a + b; }
 
-__global__ void __launch_bounds__(256) mixer_kernel(MixerKernelArgs a) {
-  __shared__ float s_red[8];
-  __shared__ uint32_t s_flag;
+// ---- M1 -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mix_sum_kernel(MixerKernelArgs a) {
+  const uint32_t m = a.level_mixers[blockIdx.y];
+  const MixerParams mp = a.mixers[m];
+  const uint32_t cb = a.mixer_chunk_begin[m], ce = a.mixer_chunk_begin[m + 1];
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;  // frame within the block
+  if (f >= a.block_len) return;
+  // chunk index of this frame: last boundary <= frame
+  const uint64_t t = a.block_start + f;
+  uint32_t lo = cb, hi = ce - 1;  // bounds[lo] <= t < bounds[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a.chunk_bounds[mid] <= t) lo = mid; else hi = mid;
+  }
+  const uint32_t k = lo - cb;
+  float2 s = make_float2(0.0f, 0.0f);
+  for (uint32_t ci = mp.child_begin; ci < mp.child_end; ++ci) {
+    const uint32_t c = a.child_index[ci];
+    if (a.mixer_flags[(size_t)c * a.max_chunks + k]) {
+      const float2 v = *reinterpret_cast<const float2*>(a.mixer_bus + ((size_t)c * a.block_frames + f) * 2);
+      s.x += v.x; s.y += v.y;
+    }
+  }
+  for (uint32_t si = mp.src_begin; si < mp.src_end; ++si) {
+    const uint32_t g = a.source_index[si];
+    if (a.group_flags[(size_t)g * a.max_chunks + k]) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(a.group_bus + ((size_t)g * a.block_frames + f) * 2));
+      s.x += v.x; s.y += v.y;
+    }
+  }
+  *reinterpret_cast<float2*>(a.mixer_bus + ((size_t)m * a.block_frames + f) * 2) = s;
+}
+
+// ---- M2 -------------------------------------------------------------------------------------------------
+constexpr uint32_t FX_THREADS = 128;
+constexpr uint32_t CHUNK_MAX = 1024;
+constexpr uint32_t PLANE = 1060;  // pidx(CHUNK_MAX - 1) + a few words
+
+__global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
+  __shared__ float s_ch[2][PLANE];
+  __shared__ double s_scratch[2][PLANE];
+  __shared__ double s_lane_state[2][64];
+  __shared__ float s_red[FX_THREADS / 32];
+  __shared__ uint32_t s_run;      // effect e runs this chunk
+  __shared__ uint32_t s_inbyp;    // input_bypassed seen by effect e
+
   const uint32_t m = a.level_mixers[blockIdx.x];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const MixerParams mp = a.mixers[m];
   const bool is_main = mp.parent == 0xFFFFFFFFu;
+  const bool has_fx = mp.fx_end > mp.fx_begin;
   float* bus = a.mixer_bus + (size_t)m * a.block_frames * 2;
   const uint32_t cb = a.mixer_chunk_begin[m], ce = a.mixer_chunk_begin[m + 1];
-  uint32_t pcb = 0, pce = 0, pk = 0;
-  if (!is_main) { pcb = a.mixer_chunk_begin[mp.parent]; pce = a.mixer_chunk_begin[mp.parent + 1]; pk = pcb; }
+  uint32_t pcb = 0, pk = 0;
+  if (!is_main) { pcb = a.mixer_chunk_begin[mp.parent]; pk = pcb; }
   const uint32_t sr = a.fxc.sample_rate;
+  ChunkBuf cbuf;
+  cbuf.ch[0] = s_ch[0]; cbuf.ch[1] = s_ch[1];
+  cbuf.scratch = &s_scratch[0][0];
+  cbuf.lane_state = &s_lane_state[0][0];
 
   for (uint32_t k = cb; k + 1 < ce; ++k) {
     const uint64_t c0 = a.chunk_bounds[k], c1 = a.chunk_bounds[k + 1];
     const uint32_t len = (uint32_t)(c1 - c0);
     const uint32_t boff = (uint32_t)(c0 - a.block_start);
-    float* cbuf = bus + (size_t)boff * 2;
+    float* gchunk = bus + (size_t)boff * 2;
 
-    // effect parameter events due at this chunk start (MixedSource::process_events, mixed.rs:683)
-    if (tid == 0) {
-      for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
-        FxHeader& h = a.fx[e];
-        while (h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= c0) {
-          fx_apply_param(h, a.fxc, a.fx_events[h.ev_cursor]);
-          h.ev_cursor++;
+    if (has_fx) {
+      // effect parameter events due at this chunk start (MixedSource::process_events, mixed.rs:683)
+      if (tid == 0) {
+        for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
+          FxHeader& h = a.fx[e];
+          while (h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= c0) {
+            fx_apply_param(h, a.fxc, a.fx_events[h.ev_cursor]);
+            h.ev_cursor++;
+          }
         }
       }
-    }
-
-    // (1) sum children then sources, in order
-    bool audible = false;
-    for (uint32_t ci = mp.child_begin; ci < mp.child_end; ++ci)
-      audible |= a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (k - cb)] != 0;
-    for (uint32_t si = mp.src_begin; si < mp.src_end; ++si)
-      audible |= a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (k - cb)] != 0;
-    for (uint32_t i = tid; i < len * 2; i += nt) {
-      float s = 0.0f;
-      for (uint32_t ci = mp.child_begin; ci < mp.child_end; ++ci) {
-        const uint32_t c = a.child_index[ci];
-        if (a.mixer_flags[(size_t)c * a.max_chunks + (k - cb)]) s += a.mixer_bus[((size_t)c * a.block_frames + boff) * 2 + i];
-      }
-      for (uint32_t si = mp.src_begin; si < mp.src_end; ++si) {
-        const uint32_t g = a.source_index[si];
-        if (a.group_flags[(size_t)g * a.max_chunks + (k - cb)]) s += a.group_bus[((size_t)g * a.block_frames + boff) * 2 + i];
-      }
-      cbuf[i] = s;
-    }
-    __syncthreads();
-
-    // (2) effects with auto-bypass (mixed.rs:627-655, mixed/effect.rs:56-145), warp 0
-    if (warp == 0 && mp.fx_end > mp.fx_begin) {
-      MixerState& ms = a.mstate[m];
+      // audible input? (mixed.rs:701-708)
+      bool audible = false;
+      for (uint32_t ci = mp.child_begin; ci < mp.child_end; ++ci)
+        audible |= a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (k - cb)] != 0;
+      for (uint32_t si = mp.src_begin; si < mp.src_end; ++si)
+        audible |= a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (k - cb)] != 0;
       bool input_bypassed = !audible;
-      if (!(ms.effects_bypassed && input_bypassed)) {
+      const bool skip_all = a.mstate[m].effects_bypassed && input_bypassed;  // mixed.rs:629
+      __syncthreads();
+      if (!skip_all) {
+        // stage the chunk: interleaved global -> planar padded shared
+        for (uint32_t i = tid; i < len * 2; i += nt) s_ch[i & 1][pidx(i >> 1)] = gchunk[i];
+        __syncthreads();
         bool all_bypassed = true;
         for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
           FxHeader& h = a.fx[e];
-          bool bypassed = h.bypassed != 0;
-          uint64_t tail = h.tail_counter, silence = h.silence_counter;
-          const bool should_bypass = input_bypassed && tail == 0 && silence == UINT64_MAX;
-          if (should_bypass && !bypassed) bypassed = true;
-          else if (!should_bypass && bypassed) { bypassed = false; tail = UINT64_MAX; silence = 0; }
-          if (!bypassed) {
-            fx_process(h, a.fxc, cbuf, len, lane);
-            __syncwarp();
+          // EffectProcessor::process bypass transitions (mixed/effect.rs:64-109), decided by thread 0
+          if (tid == 0) {
+            bool bypassed = h.bypassed != 0;
+            const bool should_bypass = input_bypassed && h.tail_counter == 0 && h.silence_counter == UINT64_MAX;
+            if (should_bypass && !bypassed) bypassed = true;
+            else if (!should_bypass && bypassed) { bypassed = false; h.tail_counter = UINT64_MAX; h.silence_counter = 0; }
+            h.bypassed = bypassed;
+            s_run = bypassed ? 0u : 1u;
+          }
+          __syncthreads();
+          const bool run = s_run != 0;
+          if (run) {
+            fx_process(h, a.fxc, cbuf, len, tid);
+            __syncthreads();
             if (input_bypassed) {
               uint64_t tail_frames;
-              if (fx_process_tail(h, a.fxc, tail_frames)) {
-                if (tail_frames == UINT64_MAX) tail = tail_frames;
-                else if (tail == UINT64_MAX) tail = tail_frames;
-                else tail = sat_sub_u64(tail, len);
-                silence = UINT64_MAX;
-              } else {
-                float mx = 0.0f;
-                for (uint32_t i = lane; i < len * 2; i += 32) mx = fmaxf(mx, fabsf(cbuf[i]));
+              const bool has_tail = fx_process_tail(h, a.fxc, tail_frames);
+              float mx = 0.0f;
+              if (!has_tail) {  // unknown tail: exact max|x| of the processed chunk
+                for (uint32_t i = tid; i < len; i += nt) mx = fmaxf(mx, fmaxf(fabsf(s_ch[0][pidx(i)]), fabsf(s_ch[1][pidx(i)])));
                 for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-                if (mx < 0.001f) {
-                  silence = sat_add_u64(silence, len);
-                  if (silence >= 2ull * sr) { tail = 0; silence = UINT64_MAX; }
+                if (lane == 0) s_red[warp] = mx;
+                __syncthreads();
+              }
+              if (tid == 0) {
+                if (has_tail) {
+                  if (tail_frames == UINT64_MAX) h.tail_counter = tail_frames;
+                  else if (h.tail_counter == UINT64_MAX) h.tail_counter = tail_frames;
+                  else h.tail_counter = sat_sub_u64(h.tail_counter, len);
+                  h.silence_counter = UINT64_MAX;
                 } else {
-                  silence = 0;
+                  for (uint32_t w = 0; w < nt / 32; ++w) mx = fmaxf(mx, s_red[w]);
+                  if (mx < 0.001f) {
+                    h.silence_counter = sat_add_u64(h.silence_counter, len);
+                    if (h.silence_counter >= 2ull * sr) { h.tail_counter = 0; h.silence_counter = UINT64_MAX; }
+                  } else {
+                    h.silence_counter = 0;
+                  }
                 }
               }
-            } else {
-              tail = UINT64_MAX; silence = 0;
+            } else if (tid == 0) {
+              h.tail_counter = UINT64_MAX; h.silence_counter = 0;
             }
             input_bypassed = false;
             all_bypassed = false;
           }
-          __syncwarp();
-          if (lane == 0) { h.bypassed = bypassed; h.tail_counter = tail; h.silence_counter = silence; }
-          __syncwarp();
+          __syncthreads();
         }
-        if (lane == 0) ms.effects_bypassed = all_bypassed;
+        if (tid == 0) a.mstate[m].effects_bypassed = all_bypassed ? 1u : 0u;
+        // write the processed chunk back
+        for (uint32_t i = tid; i < len * 2; i += nt) gchunk[i] = s_ch[i & 1][pidx(i >> 1)];
       }
+      __syncthreads();
     }
-    __syncthreads();
 
     if (is_main) {
-      // WavStream::process: apply_smoothed_gain per 1024-frame block (wav.rs:228-237)
-      if (((c1 - 0) % a.wav_block_frames) == 0 || k + 2 == ce) {
-        // chunk ends a wav block: find the block start inside this time block
+      // WavStream::process: apply_smoothed_gain once per 1024-frame block (wav.rs:228-237)
+      if ((c1 % a.wav_block_frames) == 0 || k + 2 == ce) {
         const uint64_t wb0 = ((c1 - 1) / a.wav_block_frames) * a.wav_block_frames;
         const uint32_t o0 = (uint32_t)(wb0 - a.block_start);
         const uint32_t wl = (uint32_t)(c1 - wb0);
@@ -153,14 +208,17 @@ __global__ void __launch_bounds__(256) mixer_kernel(MixerKernelArgs a) {
             for (uint32_t i = 0; i < wl * 2; ++i) wbuf[i] *= exp_next(ms, a.fxc.comp);
             *a.master = ms;
           }
-        } else if (fabsf(1.0f - ms.target) > 0.000001f) {
-          for (uint32_t i = tid; i < wl * 2; i += nt) wbuf[i] *= ms.target;
+          __syncthreads();
+          if (a.out) for (uint32_t i = tid; i < wl * 2; i += nt) a.out[(size_t)o0 * 2 + i] = wbuf[i];
+        } else {
+          const float g = ms.target;
+          const bool scale = fabsf(1.0f - g) > 0.000001f;
+          if (a.out) for (uint32_t i = tid; i < wl * 2; i += nt) a.out[(size_t)o0 * 2 + i] = scale ? wbuf[i] * g : wbuf[i];
         }
         __syncthreads();
-        if (a.out) for (uint32_t i = tid; i < wl * 2; i += nt) a.out[(size_t)o0 * 2 + i] = wbuf[i];
       }
     } else {
-      // (3) parent chunk ends here? -> SubMixerProcessor::process gate over the parent chunk span
+      // parent chunk ends here? -> SubMixerProcessor::process gate over the parent chunk span
       if (c1 == a.chunk_bounds[pk + 1]) {
         const uint64_t p0 = a.chunk_bounds[pk];
         const uint32_t o0 = (uint32_t)(p0 - a.block_start);
@@ -171,7 +229,7 @@ __global__ void __launch_bounds__(256) mixer_kernel(MixerKernelArgs a) {
         if (lane == 0) s_red[warp] = mx;
         __syncthreads();
         if (tid == 0) {
-          for (uint32_t w = 1; w < (nt + 31) / 32; ++w) mx = fmaxf(mx, s_red[w]);
+          for (uint32_t w = 1; w < nt / 32; ++w) mx = fmaxf(mx, s_red[w]);
           MixerState& ms = a.mstate[m];
           uint32_t flag;
           if (mx < 0.001f) {
@@ -188,7 +246,6 @@ __global__ void __launch_bounds__(256) mixer_kernel(MixerKernelArgs a) {
       }
     }
   }
-  (void)s_flag; (void)pce;
 }
 
 }  // namespace pb

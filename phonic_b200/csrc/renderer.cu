@@ -251,6 +251,7 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
   auto* r = new pb200_renderer();
   r->cfg = *config;
   if (r->cfg.block_frames == 0) r->cfg.block_frames = 1024;
+  if (r->cfg.block_frames > CHUNK_MAX) { delete r; return PB200_ERR_UNSUPPORTED; }  // chunks are staged in shared memory
   if (config->device_ordinal >= 0) {
     if (config->device_ordinal >= n || cudaSetDevice(config->device_ordinal) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
     r->device = config->device_ordinal;
@@ -941,11 +942,13 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ma.mixer_flags = r->d_mixer_flags.p + (size_t)slot * nm * max_chunks;
     ma.max_chunks = max_chunks; ma.block_frames = tb; ma.block_start = b0;
     ma.out = dout + (size_t)(b0 - p0) * 2; ma.master = r->d_master.p; ma.wav_block_frames = bf;
-    (void)blen;
+    ma.block_len = blen;
     for (int lvl = (int)c.levels.size() - 1; lvl >= 0; --lvl) {
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
-      mixer_kernel<<<(uint32_t)c.levels[lvl].size(), 256, 0, r->sm>>>(ma);
-      ++launches;
+      const uint32_t nlm = (uint32_t)c.levels[lvl].size();
+      mix_sum_kernel<<<dim3((blen + 255) / 256, nlm), 256, 0, r->sm>>>(ma);
+      mix_fx_kernel<<<nlm, FX_THREADS, 0, r->sm>>>(ma);
+      launches += 2;
     }
     CUDA_TRY(cudaEventRecord(ev_m1[b], r->sm));
   }

@@ -129,7 +129,6 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   const uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];
   uint8_t* gflags = a.group_flags + (size_t)g * a.max_chunks;
   uint64_t my_frames = 0;
-  HistVals hv_unused;
 
   for (uint32_t k = cb; k + 1 < ce; ++k) {
     const uint64_t c0 = a.chunk_bounds[k], c1 = a.chunk_bounds[k + 1];
@@ -266,8 +265,8 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
             n_segs++;
           }
           uint32_t w;
-          if (buf.channels == 2) w = voice_frames<2, false>(v, cc, hv_unused, gp, buf, out_rate, comp, seg_len, nullptr);
-          else w = voice_frames<1, false>(v, cc, hv_unused, gp, buf, out_rate, comp, seg_len, nullptr);
+          if (buf.channels == 2) w = voice_advance<2>(v, cc, gp, buf, out_rate, comp, seg_len);
+          else w = voice_advance<1>(v, cc, gp, buf, out_rate, comp, seg_len);
           written_frames += w;
           off += w; remaining -= w;
           if (w < seg_len) break;

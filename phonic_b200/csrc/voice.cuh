@@ -458,6 +458,143 @@ PB_DEV void voice_end_call(VoiceState& v, CallCtx& c, uint64_t call_end_frame) {
   }
 }
 
+// ---- skeleton fast path -------------------------------------------------------------------------------------
+// State-only advance of one write call by up to `n` frames, bit-identical to voice_frames<CC,false> but with
+// the independent recurrences separated into tight loops: (1) the resampler's f32 phase/position
+// recurrence (cubic.rs:72-110), then -- only while they are actually moving -- (2) the fader, (3) the
+// per-sample gain ramp, (4) the pan ramp, (5) the AHDSR stage machine. Falls back to the general per-frame
+// code near loop ends / EOF, where input exhaustion has to be handled frame by frame.
+template <int CC>
+PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, const DevBuffer& b, uint32_t out_rate,
+                              float comp, uint32_t n) {
+  HistVals hv_unused;
+  uint32_t done = 0;
+  while (done < n && !c.ended) {
+    if (c.call_left == 0) {  // next write_buffer call (preloaded.rs:419-447)
+      if (c.gliding) {
+        if (v.to_next_speed_update == 0) {
+          if (v.current_speed != v.target_speed) update_speed(v, b.sample_rate, out_rate);
+          v.to_next_speed_update = 64;
+        }
+        c.call_left = min(c.chunk_left, v.to_next_speed_update);
+      } else {
+        c.call_left = c.chunk_left;
+      }
+      loop_range_samples(v, b, c.ls, c.le);
+      c.new_call = true;
+    }
+    const uint32_t span = min(n - done, c.call_left);
+    const float ratio = v.ratio;
+    const bool bypass = fabsf(ratio - 1.0f) < 0.000001f;
+    const uint32_t avail = c.le > v.playback_pos ? (c.le - v.playback_pos) / CC : 0u;
+    // worst-case pushes of `span` frames (+3 for a pending preload); exhaustion cannot happen below that
+    const uint32_t per_frame = bypass ? 1u : (ratio < 1.0f ? 1u : (uint32_t)ratio + 2u);
+    const bool fast = !bypass && ratio > 0.0f && ratio < 64.0f && (uint64_t)span * per_frame + 4u < (uint64_t)avail;
+    uint32_t w;
+    if (fast) {
+      if (c.new_call) {  // CubicInterpolator::process prologue (cubic.rs:47-69)
+        c.new_call = false;
+        c.produced_in_call = 0;
+        if (!v.initialized) {
+          v.initialized = 1;
+          v.hidx[3] = v.hidx[0];
+          v.hidx[2] = (int32_t)v.playback_pos; v.hidx[1] = (int32_t)(v.playback_pos + CC); v.hidx[0] = (int32_t)(v.playback_pos + 2 * CC);
+          v.playback_pos += 3 * CC;
+        }
+      }
+      float s = v.sub_pos;
+      uint32_t np = 0;
+      if (ratio < 1.0f) {
+#pragma unroll 4
+        for (uint32_t f = 0; f < span; ++f) {
+          const bool p = s >= 1.0f;
+          s = p ? s - 1.0f : s;
+          np += p ? 1u : 0u;
+          s += ratio;
+        }
+      } else {
+        const uint32_t kmax = (uint32_t)ratio + 2u;  // bound on the `while sub_pos < ratio` trip count
+        for (uint32_t f = 0; f < span; ++f) {
+          for (uint32_t j = 0; j < kmax; ++j) {      // branch-free form of the push loop (cubic.rs:94-103)
+            const bool p = s < ratio;
+            s = p ? s + 1.0f : s;
+            np += p ? 1u : 0u;
+          }
+          s -= ratio;
+        }
+      }
+      v.sub_pos = s;
+      if (np >= 4) {
+        v.playback_pos += np * CC;
+        v.hidx[0] = (int32_t)(v.playback_pos - CC); v.hidx[1] = (int32_t)(v.playback_pos - 2 * CC);
+        v.hidx[2] = (int32_t)(v.playback_pos - 3 * CC); v.hidx[3] = (int32_t)(v.playback_pos - 4 * CC);
+      } else {
+        for (uint32_t i = 0; i < np; ++i) {
+          v.hidx[3] = v.hidx[2]; v.hidx[2] = v.hidx[1]; v.hidx[1] = v.hidx[0]; v.hidx[0] = (int32_t)v.playback_pos;
+          v.playback_pos += CC;
+        }
+      }
+      c.produced_in_call += span;
+      c.call_left -= span;
+      c.chunk_left -= span;
+      if (c.gliding) v.to_next_speed_update -= span;
+      if (c.call_left == 0) after_process_call(v, c);
+      w = span;
+    } else {
+      // general path for the resampler only: switch the other recurrences off, they are advanced below
+      CallCtx t = c;
+      t.fader_running = false; t.fader_scale = false; t.vol_ramp = false; t.vol_scale = false;
+      t.pan_ramp = false; t.pan_apply = false; t.env_per_frame = false;
+      GroupParams gq = gp;
+      gq.has_env = 0;
+      w = voice_frames<CC, false>(v, t, hv_unused, gq, b, out_rate, comp, span, nullptr);
+      c.chunk_left = t.chunk_left; c.call_left = t.call_left; c.produced_in_call = t.produced_in_call;
+      c.ls = t.ls; c.le = t.le; c.new_call = t.new_call; c.ended = t.ended;
+    }
+    // (2) VolumeFader ramp (fader.rs:109-116)
+    if (c.fader_running) {
+      float cur = v.fader_cur;
+      const float tgt = v.fader_tgt, inertia = v.fader_inertia;
+      for (uint32_t i = 0; i < w; ++i) cur += (tgt - cur) * inertia;
+      v.fader_cur = cur;
+    }
+    // (3) gain ramp, two steps per frame (smoothing.rs:61-64); once it stops needing a ramp it stays put
+    if (c.vol_ramp) {
+      float cur = v.vol.current;
+      const float tgt = v.vol.target;
+      for (uint32_t i = 0; i < 2 * w; ++i) {
+        const float add = (tgt - cur) * SMOOTH_INERTIA * comp;
+        if (!(fabsf(add) > F32_EPS * 100.0f)) break;
+        cur += add;
+      }
+      v.vol.current = cur;
+    }
+    // (4) pan ramp, one step per frame
+    if (c.pan_ramp) {
+      float cur = v.pan.current;
+      const float tgt = v.pan.target;
+      for (uint32_t i = 0; i < w; ++i) {
+        const float add = (tgt - cur) * SMOOTH_INERTIA * comp;
+        if (!(fabsf(add) > F32_EPS * 100.0f)) break;
+        cur += add;
+      }
+      v.pan.current = cur;
+    }
+    // (5) AHDSR (ahdsr.rs:448-516); Sustain and Idle do not move
+    if (gp.has_env && c.env_per_frame) {
+      uint32_t i = 0;
+      while (i < w) {
+        if (v.env_stage == ENV_SUSTAIN || v.env_stage == ENV_IDLE) break;
+        (void)env_run(v, gp);
+        ++i;
+      }
+    }
+    done += w;
+    if (w < span) break;
+  }
+  return done;
+}
+
 // Snapshot the skeleton pass emits at the start of every replay segment: the complete voice state and
 // write-call context, from which a replay thread reproduces the next `n` frames bit for bit.
 struct Segment {

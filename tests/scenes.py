@@ -163,4 +163,7 @@ SCENES = {
 
 # scenes whose whole path is +,-,*,/,sqrt in the reference's order: must be bit-exact on device
 BIT_EXACT = {"file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
-             "sampler_no_envelope", "cfg2_small", "fx_filter"}
+             "sampler_no_envelope"}
+# bit-exact voice path + time-invariant biquads evaluated by the f64 block scan (exact up to O(1e-16)
+# relative reassociation error before the f32 cast): at most a rare last-bit flip
+NEAR_EXACT = {"cfg2_small", "fx_filter"}

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from phonic_b200.player import Player
-from scenes import BIT_EXACT, SCENES, SR
+from scenes import BIT_EXACT, NEAR_EXACT, SCENES, SR
 
 pytestmark = pytest.mark.gpu
 
@@ -44,6 +44,9 @@ def test_scene_matches_oracle(cuda_api, oracle_api, name):
     if name in BIT_EXACT:
         bad = np.flatnonzero((gpu != ref).any(axis=1))
         assert bad.size == 0, f"{name}: first differing frame {bad[0]} of {len(ref)}, max err {err:.3e}"
+    elif name in NEAR_EXACT:
+        assert err <= 2.5e-7, f"{name}: max abs err {err:.3e}"
+        assert np.count_nonzero(gpu != ref) <= 0.01 * ref.size, f"{name}: {np.count_nonzero(gpu != ref)} samples differ"
     elif name in ("fx_delay", "fx_reverb", "submixers_cfg5_small"):
         rms = float(np.sqrt(np.mean((gpu - ref) ** 2)))
         assert dbfs(rms) < -90.0 and dbfs(err) < -80.0, f"{name}: error floor {dbfs(rms):.1f} dBFS rms, {dbfs(err):.1f} peak"
