@@ -906,8 +906,10 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     for (size_t ci = 0; ci < c.classes.size(); ++ci) {
       const SizeClass& sc = c.classes[ci];
       va.group_list = r->d_class_groups.p + c.class_offsets[ci];
-      if (sc.threads <= 256) skeleton_kernel<256><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va);
-      else skeleton_kernel<1024><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va);
+      if (sc.vpad <= 8) skeleton_kernel<256, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va);
+      else if (sc.vpad <= 32) skeleton_kernel<1024, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va);
+      else if (sc.threads <= 256) skeleton_kernel<256, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va);
+      else skeleton_kernel<1024, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va);
       ++launches;
     }
     CUDA_TRY(cudaEventRecord(ev_v1[b], r->sv));

@@ -89,14 +89,16 @@ PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t fr
   }
 }
 
-template <int MAXT>
+// WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
+// control flow (the skeleton is a latency-bound chain of dependent f32 ops per voice, not a SIMT workload).
+template <int MAXT, bool WPV>
 __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
-  __shared__ VoiceHeader s_head[MAXT];
+  __shared__ VoiceHeader s_head[WPV ? 32 : MAXT];
   __shared__ GroupState s_gs;
   __shared__ uint32_t s_count;
 
   const uint32_t g = a.group_list[blockIdx.x];
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = WPV ? ((threadIdx.x & 31u) == 0 ? (threadIdx.x >> 5) : 0xFFFFu) : threadIdx.x;
   const GroupParams gp = a.groups[g];
   const uint32_t nv = gp.n_voices;
   const DevBuffer buf = a.buffers[gp.buffer];
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   uint16_t* g_first = a.gseg_first + (size_t)g * a.n_tiles;
   uint16_t* g_count = a.gseg_count + (size_t)g * a.n_tiles;
   uint32_t n_gsegs = 0;
-  for (uint32_t i = tid; i < a.n_tiles; i += blockDim.x) g_count[i] = 0;
+  for (uint32_t i = threadIdx.x; i < a.n_tiles; i += blockDim.x) g_count[i] = 0;
   __syncthreads();
 
   const uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];

@@ -513,15 +513,46 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
           s += ratio;
         }
       } else {
-        const uint32_t kmax = (uint32_t)ratio + 2u;  // bound on the `while sub_pos < ratio` trip count
-        for (uint32_t f = 0; f < span; ++f) {
-          for (uint32_t j = 0; j < kmax; ++j) {      // branch-free form of the push loop (cubic.rs:94-103)
-            const bool p = s < ratio;
-            s = p ? s + 1.0f : s;
-            np += p ? 1u : 0u;
-          }
+        // `while sub_pos < ratio { push; sub_pos += 1.0 }; sub_pos -= ratio` (cubic.rs:94-105).
+        // With sub_pos in [0,1) at frame start the trip count is n0 = floor(ratio) or n0 + 1. Repeated
+        // f32 `+= 1.0` only rounds when the sum enters a new binade ([1,2), [2,4), [4,8), ...) and is
+        // exact inside one, so t_n = sub_pos after n pushes has the closed form
+        //   t_n = fl(fl(fl(fl(s + a1) + a2) + a3) + a4),  a = (min(n,1), min(n-1,2), min(n-3,4), min(n-7,8))
+        // (bit-identical to the sequential adds; validated exhaustively in tests/test_phase_closed_form.py).
+        // Each frame is then a short FADD chain plus the reference's own exit test; anything unusual
+        // (sub_pos >= 1 after a ratio change, integer ratios) takes the literal loop.
+        const int n0 = (int)ratio;
+        const int nm = n0 - 1;
+        const float a1 = (float)min(max(nm, 0), 1), a2 = (float)min(max(nm - 1, 0), 2);
+        const float a3 = (float)min(max(nm - 3, 0), 4), a4 = (float)min(max(nm - 7, 0), 8);
+        // integer ratios are the one case where t_{n0-1} can reach `ratio`: leave them to the literal loop
+        const bool closed_ok = ratio < 14.0f && ratio != (float)n0;
+        uint32_t f = 0;
+        // first frame (sub_pos may be >= 1 right after a ratio change) and unsupported ratios: literal loop
+        const uint32_t literal = closed_ok ? (s < 1.0f ? 0u : 1u) : span;
+        for (; f < literal && f < span; ++f) {
+          while (s < ratio) { s += 1.0f; ++np; }
           s -= ratio;
         }
+        // from here on sub_pos = t - ratio with t in [ratio, ratio + 1): always in [0, 1)
+        uint32_t extra = 0;  // frames that needed n0 + 1 pushes
+#define PB_PHASE_LOOP(TM_EXPR)                                   \
+        for (; f < span; ++f) {                                  \
+          const float tm = (TM_EXPR);                            \
+          const float t0 = tm + 1.0f;                            \
+          const bool k0 = t0 >= ratio;                           \
+          const float t = k0 ? t0 : t0 + 1.0f;                   \
+          extra += k0 ? 0u : 1u;                                 \
+          s = t - ratio;                                         \
+        }
+        if (nm <= 0) { PB_PHASE_LOOP(s) }
+        else if (nm == 1) { PB_PHASE_LOOP(s + 1.0f) }
+        else if (nm <= 3) { PB_PHASE_LOOP((s + 1.0f) + a2) }
+        else if (nm <= 7) { PB_PHASE_LOOP(((s + 1.0f) + 2.0f) + a3) }
+        else { PB_PHASE_LOOP((((s + 1.0f) + 2.0f) + 4.0f) + a4) }
+#undef PB_PHASE_LOOP
+        np += (span - min(literal, span)) * (uint32_t)n0 + extra;
+        (void)a1;
       }
       v.sub_pos = s;
       if (np >= 4) {
@@ -584,9 +615,30 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
     if (gp.has_env && c.env_per_frame) {
       uint32_t i = 0;
       while (i < w) {
-        if (v.env_stage == ENV_SUSTAIN || v.env_stage == ENV_IDLE) break;
-        (void)env_run(v, gp);
-        ++i;
+        const uint32_t stage = v.env_stage;
+        if (stage == ENV_SUSTAIN || stage == ENV_IDLE) break;
+        // run the stage's accumulate as a bare chain of the reference's own f32 op while a threshold
+        // crossing is provably out of reach (10 % + 2 steps of slack), then fall back to env_run
+        float room = 0.0f, step = 1.0f;
+        if (stage == ENV_ATTACK) { room = v.env_target - v.env_out; step = gp.attack_rate; }
+        else if (stage == ENV_HOLD) { room = v.env_hold; step = 1.0f; }
+        else if (stage == ENV_DECAY && v.env_out > gp.sustain_level) { room = v.env_out - gp.sustain_level; step = gp.decay_rate; }
+        else if (stage == ENV_RELEASE) { room = v.env_out - 0.001f; step = v.env_release_out * gp.release_rate; }
+        uint32_t m = 0;
+        if (room > 0.0f && step > 0.0f) {
+          const float q = fminf(room / step * 0.9f, 1.0e6f);
+          m = q > 3.0f ? (uint32_t)q - 2u : 0u;
+          m = min(m, w - i);
+        }
+        if (m) {
+          if (stage == ENV_ATTACK) { float o = v.env_out; for (uint32_t j = 0; j < m; ++j) o += step; v.env_out = o; }
+          else if (stage == ENV_HOLD) { float o = v.env_hold; for (uint32_t j = 0; j < m; ++j) o -= 1.0f; v.env_hold = o; }
+          else { float o = v.env_out; for (uint32_t j = 0; j < m; ++j) o -= step; v.env_out = o; }
+          i += m;
+        } else {
+          (void)env_run(v, gp);
+          ++i;
+        }
       }
     }
     done += w;
