@@ -57,23 +57,35 @@ def workload_spec(name):
     raise SystemExit(f"unknown workload {name}")
 
 
+_BUFFER = None
+
+
+def sample_buffer():
+    """The synthetic sample data (host memory), synthesised once: it is the *input* of the path."""
+    global _BUFFER
+    if _BUFFER is None:
+        from phonic_b200 import workloads as W
+        _BUFFER = W.synth_buffer(int(4.0 * 44100), 44100, seed=1)
+    return _BUFFER
+
+
 def build_scene(player, name, rank=0, as_subtree=False):
-    """Builds the workload on `player`; returns number of voices."""
+    """Builds the workload on `player` from the host sample buffer (upload + graph + events)."""
     from phonic_b200 import workloads as W
     from phonic_b200.player import FilterEffect
     spec = workload_spec(name)
+    buf = sample_buffer()
     if name == "cfg2":
         if not as_subtree:
-            W.build_cfg2(player, W.VoiceBankSpec(voices=spec["voices"]))
+            W.build_cfg2(player, W.VoiceBankSpec(voices=spec["voices"]), buffer=buf)
         else:  # one GPU's shard of an N-GPU graph: the bank lives on a sub-mixer of the main mixer
-            buf = W.synth_buffer(int(4.0 * 44100), 44100, seed=1)
             bid = player.upload_buffer(buf, 44100)
             mh = player.add_mixer(None)
             W.add_voice_bank(player, W.VoiceBankSpec(voices=spec["voices"]), bid, mh.id, seed_offset=7919 * rank)
             player.add_effect(FilterEffect(0, 2000.0, 0.707), mh.id)
     else:
         W.build_subtrees(player, spec["n_mixers"], spec["voices"] // spec["n_mixers"], W.VoiceBankSpec(), effects="none",
-                         seed_base=100000 * rank)
+                         seed_base=100000 * rank, buffer=buf)
     return spec["voices"]
 
 
@@ -241,6 +253,8 @@ def main():
     voices = spec["voices"]
     n_total = args.warmup + args.steps
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
+
+    sample_buffer()  # synthesise the input data before anything is timed
 
     # ---- device-resident arm: scenes built and uploaded before the timed region -------------------------------
     players = []

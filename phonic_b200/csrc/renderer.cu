@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,18 +31,59 @@ namespace {
     }                                                                                            \
   } while (0)
 
+// Process-wide device memory pool (per device, power-of-two size classes): offline batch rendering
+// creates and drops many short-lived renderers, and cudaMalloc/cudaFree (which synchronise the device)
+// would otherwise dominate the end-to-end time of a render. Blocks are only handed back to the pool when
+// the owning renderer is idle (every render call ends with a stream synchronise).
+struct DevicePool {
+  std::mutex mu;
+  std::map<std::pair<int, size_t>, std::vector<void*>> free_blocks;
+  std::vector<cudaEvent_t> free_events;
+  static DevicePool& get() { static DevicePool p; return p; }
+  static size_t size_class(size_t bytes) { size_t c = 256; while (c < bytes) c <<= 1; return c; }
+  cudaError_t alloc(void** out, size_t bytes, size_t* granted) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t c = size_class(bytes);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto& v = free_blocks[{dev, c}];
+      if (!v.empty()) { *out = v.back(); v.pop_back(); *granted = c; return cudaSuccess; }
+    }
+    cudaError_t e = cudaMalloc(out, c);
+    *granted = c;
+    return e;
+  }
+  void release(void* p, size_t cls) {
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    free_blocks[{dev, cls}].push_back(p);
+  }
+  cudaError_t event(cudaEvent_t* ev) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (!free_events.empty()) { *ev = free_events.back(); free_events.pop_back(); return cudaSuccess; }
+    }
+    return cudaEventCreate(ev);
+  }
+  void release_event(cudaEvent_t ev) { std::lock_guard<std::mutex> g(mu); free_events.push_back(ev); }
+};
+
 template <class T>
-struct DevVec {  // grow-only device array
+struct DevVec {  // grow-only device array backed by the pool
   T* p = nullptr;
-  size_t cap = 0;
+  size_t cap = 0;       // elements
+  size_t cls = 0;       // pool size class in bytes
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    size_t ncap = std::max(n, cap + cap / 2);
-    T* np = nullptr;
-    cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+    void* np = nullptr;
+    size_t granted = 0;
+    cudaError_t e = DevicePool::get().alloc(&np, n * sizeof(T), &granted);
     if (e != cudaSuccess) return e;
-    if (p) cudaFree(p);
-    p = np; cap = ncap;
+    if (p) DevicePool::get().release(p, cls);
+    p = (T*)np; cls = granted; cap = granted / sizeof(T);
     return cudaSuccess;
   }
   cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
@@ -54,10 +96,10 @@ struct DevVec {  // grow-only device array
     if (v.empty()) return cudaSuccess;
     return cudaMemcpyAsync(v.data(), p, v.size() * sizeof(T), cudaMemcpyDeviceToHost, s);
   }
-  void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void free() { if (p) DevicePool::get().release(p, cls); p = nullptr; cap = 0; cls = 0; }
 };
 
-struct HostBuffer { DevBuffer dev; };
+struct HostBuffer { DevBuffer dev; size_t cls; };
 
 struct HostEvent { DevEvent ev; uint64_t seq; };
 
@@ -281,8 +323,10 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
 void pb200_destroy(pb200_renderer* r) {
   if (!r) return;
   cudaSetDevice(r->device);
-  cudaDeviceSynchronize();
-  for (auto& b : r->buffers) cudaFree((void*)b.dev.data);
+  if (r->sv) cudaStreamSynchronize(r->sv);
+  if (r->sr_) cudaStreamSynchronize(r->sr_);
+  if (r->sm) cudaStreamSynchronize(r->sm);
+  for (auto& b : r->buffers) DevicePool::get().release((void*)b.dev.data, b.cls);
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
   r->d_mixers.free(); r->d_mstate.free(); r->d_child_index.free(); r->d_source_index.free(); r->d_level_mixers.free();
   r->d_class_groups.free(); r->d_fx.free(); r->d_fx_events.free(); r->d_fx_state.free(); r->d_aux.free();
@@ -315,7 +359,7 @@ int pb200_upload_buffer(pb200_renderer* r, const float* data, uint64_t frames, u
   }
   cudaSetDevice(r->device);
   float* d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, total_frames * ch * sizeof(float)));
+  CUDA_TRY(DevicePool::get().alloc((void**)&d, total_frames * ch * sizeof(float), &hb.cls));
   CUDA_TRY(cudaMemsetAsync(d, 0, total_frames * ch * sizeof(float), r->sm));
   CUDA_TRY(cudaMemcpyAsync(d, data, frames * ch * sizeof(float), cudaMemcpyHostToDevice, r->sm));
   CUDA_TRY(cudaStreamSynchronize(r->sm));
@@ -755,15 +799,15 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
   // aux arena: grow preserving contents, zero the new tail
   if (r->aux_doubles > r->d_aux.cap) {
     double* np = nullptr;
-    size_t ncap = r->aux_doubles + 1024;
-    CUDA_TRY(cudaMalloc(&np, ncap * sizeof(double)));
-    CUDA_TRY(cudaMemsetAsync(np, 0, ncap * sizeof(double), s));
+    size_t granted = 0;
+    CUDA_TRY(DevicePool::get().alloc((void**)&np, (r->aux_doubles + 1024) * sizeof(double), &granted));
+    CUDA_TRY(cudaMemsetAsync(np, 0, granted, s));
     if (r->d_aux.p) {
       CUDA_TRY(cudaMemcpyAsync(np, r->d_aux.p, r->d_aux_used * sizeof(double), cudaMemcpyDeviceToDevice, s));
       CUDA_TRY(cudaStreamSynchronize(s));
-      cudaFree(r->d_aux.p);
+      DevicePool::get().release(r->d_aux.p, r->d_aux.cls);
     }
-    r->d_aux.p = np; r->d_aux.cap = ncap;
+    r->d_aux.p = np; r->d_aux.cap = granted / sizeof(double); r->d_aux.cls = granted;
   }
   r->d_aux_used = r->aux_doubles;
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -872,10 +916,11 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
 
   std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r1(n_blocks), ev_m1(n_blocks);
   for (uint32_t b = 0; b < n_blocks; ++b) {
-    CUDA_TRY(cudaEventCreate(&ev_v0[b])); CUDA_TRY(cudaEventCreate(&ev_v1[b])); CUDA_TRY(cudaEventCreate(&ev_r1[b])); CUDA_TRY(cudaEventCreate(&ev_m1[b]));
+    CUDA_TRY(DevicePool::get().event(&ev_v0[b])); CUDA_TRY(DevicePool::get().event(&ev_v1[b]));
+    CUDA_TRY(DevicePool::get().event(&ev_r1[b])); CUDA_TRY(DevicePool::get().event(&ev_m1[b]));
   }
   cudaEvent_t ev_start, ev_end;
-  CUDA_TRY(cudaEventCreate(&ev_start)); CUDA_TRY(cudaEventCreate(&ev_end));
+  CUDA_TRY(DevicePool::get().event(&ev_start)); CUDA_TRY(DevicePool::get().event(&ev_end));
   CUDA_TRY(cudaEventRecord(ev_start, r->sv));
   CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_start, 0));
@@ -969,9 +1014,10 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.skeleton_kernel_ms += ms;
     cudaEventElapsedTime(&ms, ev_v1[b], ev_r1[b]); r->stats.voice_kernel_ms += ms;
     cudaEventElapsedTime(&ms, ev_r1[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
-    cudaEventDestroy(ev_v0[b]); cudaEventDestroy(ev_v1[b]); cudaEventDestroy(ev_r1[b]); cudaEventDestroy(ev_m1[b]);
+    DevicePool::get().release_event(ev_v0[b]); DevicePool::get().release_event(ev_v1[b]);
+    DevicePool::get().release_event(ev_r1[b]); DevicePool::get().release_event(ev_m1[b]);
   }
-  cudaEventDestroy(ev_start); cudaEventDestroy(ev_end);
+  DevicePool::get().release_event(ev_start); DevicePool::get().release_event(ev_end);
   r->stats.kernel_launches = launches;
   r->host_state_valid = false;
   r->position = p1;

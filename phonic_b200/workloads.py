@@ -100,10 +100,11 @@ def add_voice_bank(player: Player, spec: VoiceBankSpec, buffer_id: int, mixer_id
     return handles
 
 
-def build_cfg2(player: Player, spec: VoiceBankSpec | None = None, time_scale: float = 1.0):
-    """cfg2: 256 Sampler voices (AHDSR + glide), cubic resampling, FilterEffect LP 2 kHz on the bus."""
+def build_cfg2(player: Player, spec: VoiceBankSpec | None = None, time_scale: float = 1.0, buffer=None):
+    """cfg2: 256 Sampler voices (AHDSR + glide), cubic resampling, FilterEffect LP 2 kHz on the bus.
+    `buffer`: the (already synthesised) host sample data; generated here when None."""
     spec = spec or VoiceBankSpec()
-    buf = synth_buffer(int(spec.buffer_seconds * spec.buffer_rate), spec.buffer_rate, seed=1)
+    buf = buffer if buffer is not None else synth_buffer(int(spec.buffer_seconds * spec.buffer_rate), spec.buffer_rate, seed=1)
     bid = player.upload_buffer(buf, spec.buffer_rate)
     handles = add_voice_bank(player, spec, bid, None, 0, time_scale)
     fx = player.add_effect(FilterEffect(0, 2000.0, 0.707))
@@ -120,10 +121,10 @@ def build_cfg1(player: Player, buffer: np.ndarray, buffer_rate: int):
 
 
 def build_subtrees(player: Player, n_mixers: int, voices_per_mixer: int, spec: VoiceBankSpec, effects: str = "none",
-                   time_scale: float = 1.0, seed_base: int = 0):
+                   time_scale: float = 1.0, seed_base: int = 0, buffer=None):
     """cfg3 / cfg5 shape: `n_mixers` sub-mixers of the main mixer, each with a cfg2-style bank.
     effects: 'none' | 'cfg3' (Eq5 + Compressor + Chorus per sub-mixer)."""
-    buf = synth_buffer(int(spec.buffer_seconds * spec.buffer_rate), spec.buffer_rate, seed=1)
+    buf = buffer if buffer is not None else synth_buffer(int(spec.buffer_seconds * spec.buffer_rate), spec.buffer_rate, seed=1)
     bid = player.upload_buffer(buf, spec.buffer_rate)
     rng = np.random.default_rng(3 + seed_base)
     out = []
