@@ -236,6 +236,7 @@ def main():
 
     import phonic_b200
     from phonic_b200 import workloads as W
+    from phonic_b200.distributed import reduce_partial_bus
     from phonic_b200.player import Player
 
     rank = int(os.environ.get("RANK", "0"))
@@ -282,7 +283,7 @@ def main():
         if world > 1:  # one NCCL reduce of the stereo bus partial per render (rank 0 owns the main bus)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            dist.reduce(out_dev, dst=0, op=dist.ReduceOp.SUM)
+            reduce_partial_bus(out_dev, dst=0)
             e1.record()
             torch.cuda.synchronize()
             red_ms = e0.elapsed_time(e1)
@@ -320,7 +321,7 @@ def main():
         build_scene(p, args.workload, rank=rank, as_subtree=world > 1)   # uploads the sample buffer (H2D) + schedules events
         if world > 1:
             p.render_device(out_dev.data_ptr(), frames)
-            dist.reduce(out_dev, dst=0, op=dist.ReduceOp.SUM)
+            reduce_partial_bus(out_dev, dst=0)
             if rank == 0:
                 out_host.copy_(out_dev, non_blocking=False)
             torch.cuda.synchronize()

@@ -1,0 +1,77 @@
+"""N>1 path on CPU: world_size-2 `gloo` processes render disjoint sub-mixer subtrees (the oracle stands in
+for the GPU renderer behind the same C-ABI), reduce the stereo partial buses onto rank 0 and compare with
+the single-process render of the whole graph."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ORACLE_LIB, ROOT
+
+N_SUBTREES = 5
+VOICES = 6
+FRAMES = 24 * 1024
+
+
+def build(player, subtree_ids):
+    from phonic_b200 import workloads as W
+    from phonic_b200.player import FilterEffect
+    buf = W.synth_buffer(20000, 44100, seed=1)
+    bid = player.upload_buffer(buf, 44100)
+    for s in subtree_ids:
+        mh = player.add_mixer(None)
+        W.add_voice_bank(player, W.VoiceBankSpec(voices=VOICES, voices_per_sampler=3), bid, mh.id,
+                         seed_offset=1000 * (s + 1), time_scale=0.05)
+        player.add_effect(FilterEffect(0, 2500.0, 0.707), mh.id)
+
+
+def worker(rank, world, port, result_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from phonic_b200._capi import CApi
+    from phonic_b200.distributed import assign_subtrees, reduce_partial_bus, subtree_weight
+    from phonic_b200.player import Player
+    api = CApi(ORACLE_LIB, "po_")
+    weights = [subtree_weight(VOICES, [2])] * N_SUBTREES
+    mine = assign_subtrees(weights, world)[rank]
+    p = Player(api, 48000)
+    build(p, mine)
+    part = torch.from_numpy(p.render(FRAMES))
+    reduce_partial_bus(part, dst=0)
+    if rank == 0:
+        np.save(result_path, part.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_assign_subtrees_is_the_reference_heuristic():
+    from phonic_b200.distributed import assign_subtrees
+    # heaviest first, each to the lightest bin, first minimum wins
+    assert assign_subtrees([5, 3, 3, 2, 2, 1], 2) == [[0, 3, 5], [1, 2, 4]]
+    assert assign_subtrees([1, 1, 1, 1], 4) == [[0], [1], [2], [3]]
+    bins = assign_subtrees(list(range(1, 65)), 8)
+    assert sorted(i for b in bins for i in b) == list(range(64))
+    loads = [sum(i + 1 for i in b) for b in bins]
+    assert max(loads) - min(loads) <= 8
+
+
+def test_two_rank_reduce_matches_single_process_render(tmp_path, oracle_api):
+    from phonic_b200.player import Player
+    port = 29500 + (os.getpid() % 2000)
+    result = str(tmp_path / "reduced.npy")
+    mp.spawn(worker, args=(2, port, result), nprocs=2, join=True)
+    reduced = np.load(result)
+    p = Player(oracle_api, 48000)
+    # single process: all subtrees in the order the two ranks hold them
+    build(p, list(range(N_SUBTREES)))
+    full = p.render(FRAMES)
+    assert float(np.abs(full).max()) > 0.05
+    # the reduce changes the f32 summation order across subtrees: <= 1e-6, not bit-exact
+    assert float(np.abs(reduced - full).max()) <= 1e-6
