@@ -119,12 +119,12 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   Segment* my_segs = a.segs + (size_t)vidx * a.seg_cap;
   uint16_t* my_first = a.seg_first + (size_t)vidx * a.n_tiles;
   uint16_t* my_count = a.seg_count + (size_t)vidx * a.n_tiles;
-  uint32_t n_segs = 0;
+  uint32_t n_segs = 0, cur_tile = 0xFFFFFFFFu, cur_first = 0, cur_cnt = 0;
   if (mine) for (uint32_t i = 0; i < a.n_tiles; ++i) my_count[i] = 0;
   GroupSeg* g_segs = a.gsegs + (size_t)g * a.seg_cap;
   uint16_t* g_first = a.gseg_first + (size_t)g * a.n_tiles;
   uint16_t* g_count = a.gseg_count + (size_t)g * a.n_tiles;
-  uint32_t n_gsegs = 0;
+  uint32_t n_gsegs = 0, gcur_tile = 0xFFFFFFFFu, gcur_first = 0, gcur_cnt = 0;
   for (uint32_t i = threadIdx.x; i < a.n_tiles; i += blockDim.x) g_count[i] = 0;
   __syncthreads();
 
@@ -262,8 +262,13 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
           if (n_segs < a.seg_cap) {
             Segment& s = my_segs[n_segs];
             s.v = v; s.c = cc; s.out_off = off; s.n = seg_len;
-            if (my_count[tile] == 0) my_first[tile] = (uint16_t)n_segs;
-            my_count[tile] += 1;
+            // per-tile (first, count) live in registers and are stored when the tile changes: no global
+            // load sits on this latency-critical path
+            if (tile != cur_tile) {
+              if (cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
+              cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
+            }
+            cur_cnt++;
             n_segs++;
           }
           uint32_t w;
@@ -290,8 +295,11 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
           if (n_gsegs < a.seg_cap) {
             GroupSeg& s = g_segs[n_gsegs];
             s.vol = s_gs.vol; s.pan = s_gs.pan; s.out_off = off; s.n = seg_len; s.flags = flags;
-            if (g_count[tile] == 0) g_first[tile] = (uint16_t)n_gsegs;
-            g_count[tile] += 1;
+            if (tile != gcur_tile) {
+              if (gcur_tile != 0xFFFFFFFFu) { g_first[gcur_tile] = (uint16_t)gcur_first; g_count[gcur_tile] = (uint16_t)gcur_cnt; }
+              gcur_tile = tile; gcur_first = n_gsegs; gcur_cnt = 0;
+            }
+            gcur_cnt++;
             n_gsegs++;
           }
           if (vol_ramp) for (uint32_t i = 0; i < seg_len * 2; ++i) (void)exp_next(s_gs.vol, comp);
@@ -343,6 +351,8 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
     __syncthreads();
   }
 
+  if (mine && cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
+  if (tid == 0 && gcur_tile != 0xFFFFFFFFu) { g_first[gcur_tile] = (uint16_t)gcur_first; g_count[gcur_tile] = (uint16_t)gcur_cnt; }
   if (mine) a.voices[gp.first_voice + tid] = v;
   if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
   __syncthreads();
