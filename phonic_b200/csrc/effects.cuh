@@ -183,6 +183,8 @@ struct ChunkBuf {
   double* lane_state;// [2][32][2] sub-block end states / start states
 };
 PB_DEV uint32_t pidx(uint32_t f) { return f + (f >> 5); }
+constexpr uint32_t CHUNK_MAX = 1024;  // frames per chunk (<= WavStream block)
+constexpr uint32_t PLANE = 1060;      // pidx(CHUNK_MAX - 1) + a few words
 #define CB_L(f) cb.ch[0][pidx(f)]
 #define CB_R(f) cb.ch[1][pidx(f)]
 
@@ -208,14 +210,16 @@ PB_DEV Mat2 mat_pow(Mat2 m, uint32_t k) {
   }
   return r;
 }
+// x: f32 input (planar padded); result written back to x as f32, or -- when out64 != nullptr -- left as f64
+// in out64 (planar padded) for callers whose next stage works in f64.
 PB_DEV void biquad_scan_channel(const BiquadCoef& c, double& ic1_io, double& ic2_io, float* x, double* y0, double* lane_state,
-                                uint32_t len, uint32_t lane) {
+                                uint32_t len, uint32_t lane, double* out64 = nullptr, const double* in64 = nullptr) {
   const uint32_t B = (len + 31) / 32;             // samples per lane
   const uint32_t lo = min(lane * B, len), hi = min(lo + B, len);
   const Mat2 A{2.0 * c.a1 - 1.0, -2.0 * c.a2, 2.0 * c.a2, 1.0 - 2.0 * c.a3};
   // phase 1: zero-state response of my sub-block with the reference tick
   double ic1 = 0.0, ic2 = 0.0;
-  for (uint32_t n = lo; n < hi; ++n) y0[pidx(n)] = biquad_tick(c, ic1, ic2, (double)x[pidx(n)]);
+  for (uint32_t n = lo; n < hi; ++n) y0[pidx(n)] = biquad_tick(c, ic1, ic2, in64 ? in64[pidx(n)] : (double)x[pidx(n)]);
   lane_state[lane * 2] = ic1;
   lane_state[lane * 2 + 1] = ic2;
   __syncwarp();
@@ -244,7 +248,8 @@ PB_DEV void biquad_scan_channel(const BiquadCoef& c, double& ic1_io, double& ic2
   const double C1 = c.m1 * c.a1 + c.m2 * c.a2, C2 = -c.m1 * c.a2 + c.m2 * (1.0 - c.a3);
   double h1 = s1, h2 = s2;  // A^k s
   for (uint32_t n = lo; n < hi; ++n) {
-    x[pidx(n)] = (float)(y0[pidx(n)] + (C1 * h1 + C2 * h2));
+    const double y = y0[pidx(n)] + (C1 * h1 + C2 * h2);
+    if (out64) out64[pidx(n)] = y; else x[pidx(n)] = (float)y;
     const double t1 = A.a * h1 + A.b * h2, t2 = A.c * h1 + A.d * h2;
     h1 = t1; h2 = t2;
   }
@@ -316,6 +321,15 @@ PB_DEV void eq5_process(Eq5State& s, const FxCtx& cx, const ChunkBuf& cb, uint32
 PB_DEV void comp_process(CompState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames) {
   double* line = cx.aux_arena + s.aux;
   const bool limiter = s.ratio >= 20.0f;
+  if (s.peak_dirty && s.delay_frames != 0) {  // window peak = max over the last delay_frames frames (delay.rs:245-260)
+    s.peak_value = 0.0;
+    for (uint32_t i = 1; i <= s.delay_frames; ++i) {
+      uint32_t fi = (s.write_pos + s.buf_frames - i) & s.mask;
+      double fp = fmax(fmax(0.0, fabs(line[fi * 2])), fabs(line[fi * 2 + 1]));
+      if (fp >= s.peak_value) { s.peak_value = fp; s.peak_pos = fi; }
+    }
+  }
+  s.peak_dirty = 0;
   for (uint32_t f = 0; f < frames; ++f) {
     const float in0 = CB_L(f), in1 = CB_R(f);
     float d0 = in0, d1 = in1;

@@ -33,6 +33,8 @@ struct CompState {  // src/effect/compressor.rs:24-38
   double peak_value;
   uint32_t aux;  // [buf_frames][2] doubles
   uint32_t aux_capacity_frames;
+  uint32_t peak_dirty;  // the chunk-parallel path does not track the window peak; rescan before limiter use
+  uint32_t _pad;
 };
 
 struct ChorusState {  // src/effect/chorus.rs:48-74

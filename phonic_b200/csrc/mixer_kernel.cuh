@@ -11,7 +11,7 @@
 //                  and for the main mixer the WavStream master volume per 1024-frame block
 //                  (src/output/wav.rs:237) plus the final output store.
 #pragma once
-#include "effects.cuh"
+#include "effects_par.cuh"
 
 namespace pb {
 
@@ -77,9 +77,8 @@ __global__ void __launch_bounds__(256) mix_sum_kernel(MixerKernelArgs a) {
 }
 
 // ---- M2 -------------------------------------------------------------------------------------------------
-constexpr uint32_t FX_THREADS = 128;
-constexpr uint32_t CHUNK_MAX = 1024;
-constexpr uint32_t PLANE = 1060;  // pidx(CHUNK_MAX - 1) + a few words
+constexpr uint32_t FX_THREADS = FX_THREADS_C;
+constexpr uint32_t FX_WORK_BYTES = 48 * 1024;  // shared-memory work area of the chunk-parallel effects
 
 __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
   __shared__ float s_ch[2][PLANE];
@@ -87,7 +86,8 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
   __shared__ double s_lane_state[2][64];
   __shared__ float s_red[FX_THREADS / 32];
   __shared__ uint32_t s_run;      // effect e runs this chunk
-  __shared__ uint32_t s_inbyp;    // input_bypassed seen by effect e
+  extern __shared__ __align__(16) uint8_t s_work[];
+  const ParWork pw{s_work, FX_WORK_BYTES};
 
   const uint32_t m = a.level_mixers[blockIdx.x];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
           __syncthreads();
           const bool run = s_run != 0;
           if (run) {
-            fx_process(h, a.fxc, cbuf, len, tid);
+            fx_process_chunk(h, a.fxc, cbuf, len, tid, nt, pw);
             __syncthreads();
             if (input_bypassed) {
               uint64_t tail_frames;

@@ -901,6 +901,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   if (!dout) { CUDA_TRY(r->d_out.reserve(frames * 2)); dout = r->d_out.p; }
   CUDA_TRY(cudaStreamSynchronize(r->sm));
 
+  CUDA_TRY(cudaFuncSetAttribute(mix_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_WORK_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(replay_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(replay_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   const uint32_t n_tiles = tb / TILE;
@@ -994,7 +995,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
       const uint32_t nlm = (uint32_t)c.levels[lvl].size();
       mix_sum_kernel<<<dim3((blen + 255) / 256, nlm), 256, 0, r->sm>>>(ma);
-      mix_fx_kernel<<<nlm, FX_THREADS, 0, r->sm>>>(ma);
+      mix_fx_kernel<<<nlm, FX_THREADS, FX_WORK_BYTES, r->sm>>>(ma);
       launches += 2;
     }
     CUDA_TRY(cudaEventRecord(ev_m1[b], r->sm));
