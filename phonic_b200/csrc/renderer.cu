@@ -182,7 +182,7 @@ struct pb200_renderer {
 
   uint64_t position = 0;  // frames
   bool finished = false;
-  uint32_t time_block = 8192;
+  uint32_t time_block = 32768;
   uint64_t voice_frames_total = 0;
   pb200_render_stats stats{};
 };
@@ -949,6 +949,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     va.gseg_first = r->d_gseg_first.p + (size_t)slot * ng * n_tiles;
     va.gseg_count = r->d_gseg_count.p + (size_t)slot * ng * n_tiles;
     va.seg_cap = seg_cap; va.n_tiles = n_tiles;
+    va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
     for (size_t ci = 0; ci < c.classes.size(); ++ci) {
       const SizeClass& sc = c.classes[ci];
       va.group_list = r->d_class_groups.p + c.class_offsets[ci];

@@ -38,6 +38,7 @@ struct SkeletonArgs {
   uint16_t* gseg_count;               // [n_groups][n_tiles]
   uint32_t seg_cap;
   uint32_t n_tiles;
+  uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores
 };
 
 constexpr int VK_MAX_VOICES = 1024;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
         while (remaining > 0 && !cc.ended) {
           const uint32_t tile = off / TILE;
           const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
-          if (n_segs < a.seg_cap) {
+          if (n_segs < a.seg_cap && !(a.debug_flags & 1u)) {
             Segment& s = my_segs[n_segs];
             s.v = v; s.c = cc; s.out_off = off; s.n = seg_len;
             // per-tile (first, count) live in registers and are stored when the tile changes: no global

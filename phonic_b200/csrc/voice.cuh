@@ -458,6 +458,11 @@ PB_DEV void voice_end_call(VoiceState& v, CallCtx& c, uint64_t call_end_frame) {
   }
 }
 
+// 1.0f / 0.0f comparison results in a register (SASS FSET.BF): keeps the phase recurrences free of the
+// long predicate-to-consumer latency, which is what bounds the single-warp skeleton chains
+PB_DEV float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+PB_DEV float fset_lt(float a, float b) { float d; asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+
 // ---- skeleton fast path -------------------------------------------------------------------------------------
 // State-only advance of one write call by up to `n` frames, bit-identical to voice_frames<CC,false> but with
 // the independent recurrences separated into tight loops: (1) the resampler's f32 phase/position
@@ -505,13 +510,17 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
       float s = v.sub_pos;
       uint32_t np = 0;
       if (ratio < 1.0f) {
+        // if sub_pos >= 1 { push; sub_pos -= 1 }; sub_pos += ratio  (cubic.rs:73-89): `- 1.0` and `- 0.0` are both
+        // exact, so the branch becomes a subtract of the comparison result; pushes are counted off the chain
+        float pushes = 0.0f;
 #pragma unroll 4
         for (uint32_t f = 0; f < span; ++f) {
-          const bool p = s >= 1.0f;
-          s = p ? s - 1.0f : s;
-          np += p ? 1u : 0u;
+          const float p = fset_ge(s, 1.0f);
+          s = s - p;
+          pushes += p;
           s += ratio;
         }
+        np = (uint32_t)pushes;
       } else {
         // `while sub_pos < ratio { push; sub_pos += 1.0 }; sub_pos -= ratio` (cubic.rs:94-105).
         // With sub_pos in [0,1) at frame start the trip count is n0 = floor(ratio) or n0 + 1. Repeated
@@ -535,14 +544,14 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
           s -= ratio;
         }
         // from here on sub_pos = t - ratio with t in [ratio, ratio + 1): always in [0, 1)
-        uint32_t extra = 0;  // frames that needed n0 + 1 pushes
+        float extra_f = 0.0f;  // frames that needed n0 + 1 pushes
 #define PB_PHASE_LOOP(TM_EXPR)                                   \
         for (; f < span; ++f) {                                  \
           const float tm = (TM_EXPR);                            \
           const float t0 = tm + 1.0f;                            \
-          const bool k0 = t0 >= ratio;                           \
-          const float t = k0 ? t0 : t0 + 1.0f;                   \
-          extra += k0 ? 0u : 1u;                                 \
+          const float more = fset_lt(t0, ratio);                 \
+          const float t = t0 + more; /* + 0.0 is exact */        \
+          extra_f += more;                                       \
           s = t - ratio;                                         \
         }
         if (nm <= 0) { PB_PHASE_LOOP(s) }
@@ -551,7 +560,7 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
         else if (nm <= 7) { PB_PHASE_LOOP(((s + 1.0f) + 2.0f) + a3) }
         else { PB_PHASE_LOOP((((s + 1.0f) + 2.0f) + 4.0f) + a4) }
 #undef PB_PHASE_LOOP
-        np += (span - min(literal, span)) * (uint32_t)n0 + extra;
+        np += (span - min(literal, span)) * (uint32_t)n0 + (uint32_t)extra_f;
         (void)a1;
       }
       v.sub_pos = s;
