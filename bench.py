@@ -180,41 +180,60 @@ def cpu_baseline(name, seconds_budget=25.0):
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU path (oracle port, Rust toolchain absent) on the host cores.
+    N=1: cfg2 has one mixer -> phonic renders it on one audio thread. N>1: the arm's config is N voice banks
+    on N direct sub-mixers of the main mixer, which phonic's SubMixerThreadPool renders on N worker threads
+    (one sub-mixer per worker, main thread sums: src/source/mixed.rs:505-537) -- emulated with N host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import threading
     from phonic_b200 import workloads as W
     from phonic_b200.player import Player
     api = oracle_api(fast=True)
     spec = workload_spec(args.workload)
     frames = W.frames_for(spec["seconds"], SR)
-    times = []
     voices = spec["voices"]
+    world = max(1, args.gpus)
     bounded = voices > 512
+    v_per = 512 if bounded else voices
+    sample_buffer()
+    times = []
     for i in range(args.warmup + args.steps):
-        p = Player(api, SR)
-        if not bounded:
-            build_scene(p, args.workload)
-            v = voices
-        else:
-            W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none")
-            v = 512
-        out = np.zeros((frames, 2), np.float32)
+        players, outs = [], []
+        for r in range(world):
+            p = Player(api, SR)
+            if not bounded:
+                build_scene(p, args.workload, rank=r, as_subtree=world > 1)
+            else:
+                W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none", seed_base=100000 * r, buffer=sample_buffer())
+            players.append(p)
+            outs.append(np.zeros((frames, 2), np.float32))
         t0 = time.perf_counter()
-        p.render_into(out)
+        if world == 1:
+            players[0].render_into(outs[0])
+        else:
+            ths = [threading.Thread(target=players[r].render_into, args=(outs[r],)) for r in range(world)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            total = outs[0]
+            for r in range(1, world):
+                total += outs[r]
         dt = time.perf_counter() - t0
-        p.close()
+        for p in players:
+            p.close()
         if i >= args.warmup:
             times.append(dt)
-    total = sum(times)
-    value = v * frames * len(times) / total
-    sample = "full workload per step" if not bounded else f"512 of {voices} voices per step (4 sub-mixers x 128)"
+    total_t = sum(times)
+    value = world * v_per * frames * len(times) / total_t
+    sample = "full workload per step" if not bounded else f"512 of {voices} voices per rank-equivalent per step (4 sub-mixers x 128)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total_t / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": spec["desc"], "note": "oracle port of the reference's CPU path (Rust toolchain absent); "
-                       "single audio thread: this graph has no sub-mixers for SubMixerThreadPool to distribute"},
-            "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": 1, "kind": "port", "sample": sample},
+            "config": {"workload": spec["desc"] + (f"; x{world} banks on {world} sub-mixers" if world > 1 else ""),
+                       "note": "oracle port of the reference's CPU path (Rust toolchain absent); one host thread per direct "
+                               "sub-mixer like SubMixerThreadPool, a single audio thread when the graph has no sub-mixers"},
+            "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": world, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
