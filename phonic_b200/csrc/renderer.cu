@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <atomic>
 #include <vector>
 
 #include "../../include/phonic_b200.h"
@@ -99,6 +100,14 @@ struct DevVec {  // grow-only device array backed by the pool
   void free() { if (p) DevicePool::get().release(p, cls); p = nullptr; cap = 0; cls = 0; }
 };
 
+// generation tags of TileRec records: unique per skeleton launch in this process, never 0
+uint32_t next_generation() {
+  static std::atomic<uint32_t> g{0};
+  uint32_t v = g.fetch_add(1) + 1;
+  if (v == 0) v = g.fetch_add(1) + 1;
+  return v;
+}
+
 struct HostBuffer { DevBuffer dev; size_t cls; };
 
 struct HostEvent { DevEvent ev; uint64_t seq; };
@@ -174,6 +183,7 @@ struct pb200_renderer {
   DevVec<Segment> d_segs;
   DevVec<GroupSeg> d_gsegs;
   DevVec<uint16_t> d_seg_first, d_seg_count, d_gseg_first, d_gseg_count;
+  DevVec<TileRec> d_recs;
   cudaStream_t sr_ = nullptr;  // replay stream
   DevVec<uint8_t> d_group_flags, d_mixer_flags;
   DevVec<ExpSm> d_master;
@@ -332,7 +342,7 @@ void pb200_destroy(pb200_renderer* r) {
   r->d_class_groups.free(); r->d_fx.free(); r->d_fx_events.free(); r->d_fx_state.free(); r->d_aux.free();
   r->d_bounds.free(); r->d_chunk_begin.free(); r->d_group_bus.free(); r->d_mixer_bus.free(); r->d_out.free();
   r->d_group_flags.free(); r->d_mixer_flags.free(); r->d_master.free();
-  r->d_segs.free(); r->d_gsegs.free(); r->d_seg_first.free(); r->d_seg_count.free(); r->d_gseg_first.free(); r->d_gseg_count.free();
+  r->d_segs.free(); r->d_gsegs.free(); r->d_seg_first.free(); r->d_seg_count.free(); r->d_gseg_first.free(); r->d_gseg_count.free(); r->d_recs.free();
   if (r->sr_) cudaStreamDestroy(r->sr_);
   if (r->sv) cudaStreamDestroy(r->sv);
   if (r->sm) cudaStreamDestroy(r->sm);
@@ -912,6 +922,11 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(r->d_gsegs.reserve(std::max<size_t>(1, (size_t)RING * ng * seg_cap)));
   CUDA_TRY(r->d_seg_first.reserve((size_t)RING * nvoices * n_tiles));
   CUDA_TRY(r->d_seg_count.reserve((size_t)RING * nvoices * n_tiles));
+  {  // tile records carry a process-wide unique generation tag; a freshly acquired buffer is cleared once
+    const TileRec* before = r->d_recs.p;
+    CUDA_TRY(r->d_recs.reserve((size_t)RING * nvoices * n_tiles));
+    if (r->d_recs.p != before) CUDA_TRY(cudaMemsetAsync(r->d_recs.p, 0, r->d_recs.cap * sizeof(TileRec), r->sv));
+  }
   CUDA_TRY(r->d_gseg_first.reserve(std::max<size_t>(1, (size_t)RING * ng * n_tiles)));
   CUDA_TRY(r->d_gseg_count.reserve(std::max<size_t>(1, (size_t)RING * ng * n_tiles)));
 
@@ -945,6 +960,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     va.segs = r->d_segs.p + (size_t)slot * nvoices * seg_cap;
     va.seg_first = r->d_seg_first.p + (size_t)slot * nvoices * n_tiles;
     va.seg_count = r->d_seg_count.p + (size_t)slot * nvoices * n_tiles;
+    va.recs = r->d_recs.p + (size_t)slot * nvoices * n_tiles;
+    va.gen = next_generation();
     va.gsegs = r->d_gsegs.p + (size_t)slot * ng * seg_cap;
     va.gseg_first = r->d_gseg_first.p + (size_t)slot * ng * n_tiles;
     va.gseg_count = r->d_gseg_count.p + (size_t)slot * ng * n_tiles;
@@ -966,6 +983,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ReplayArgs ra;
     ra.groups = r->d_groups.p; ra.buffers = r->d_buffers.p;
     ra.segs = va.segs; ra.seg_first = va.seg_first; ra.seg_count = va.seg_count;
+    ra.recs = va.recs; ra.gen = va.gen;
     ra.gsegs = va.gsegs; ra.gseg_first = va.gseg_first; ra.gseg_count = va.gseg_count;
     ra.group_bus = r->d_group_bus.p + (size_t)slot * ng * tb * 2;
     ra.seg_cap = seg_cap; ra.n_tiles = n_tiles; ra.block_frames = tb; ra.rc = r->rc;

@@ -20,6 +20,8 @@ struct ReplayArgs {
   const Segment* segs;
   const uint16_t* seg_first;
   const uint16_t* seg_count;
+  const TileRec* recs;    // [n_voices][n_tiles]
+  uint32_t gen;
   const GroupSeg* gsegs;
   const uint16_t* gseg_first;
   const uint16_t* gseg_count;
@@ -109,9 +111,21 @@ __global__ void __launch_bounds__(MAXT, MINB) replay_kernel(ReplayArgs a) {
   if (active_thread) {
     const size_t vidx = gp.first_voice + vi;
     const uint32_t cnt = a.seg_count[vidx * a.n_tiles + tile];
-    if (cnt) {
-      segs = a.segs + vidx * a.seg_cap;
-      seg_i = a.seg_first[vidx * a.n_tiles + tile];
+    const uint32_t first = cnt ? a.seg_first[vidx * a.n_tiles + tile] : 0u;
+    segs = a.segs + vidx * a.seg_cap;
+    const TileRec rec = a.recs[vidx * a.n_tiles + tile];
+    if (rec.gen == a.gen && (rec.stage_n & 0xFFFFu)) {
+      // the tile opens inside a simple call: state = the call's Segment advanced by the record
+      const Segment& s = segs[rec.base];
+      v = s.v; cc = s.c;
+      seg_pos = tile * TILE; seg_stop = seg_pos + (rec.stage_n & 0xFFFFu);
+      if (buf.channels == 2) { apply_tile_rec<2>(v, cc, buf, rec, seg_pos - s.out_off); hist_load<2>(hv, v, buf.data); }
+      else { apply_tile_rec<1>(v, cc, buf, rec, seg_pos - s.out_off); hist_load<1>(hv, v, buf.data); }
+      seg_i = first - 1u;  // the tile's own segments (if any) follow
+      seg_end_i = first + cnt;
+      have = true;
+    } else if (cnt) {
+      seg_i = first;
       seg_end_i = seg_i + cnt;
       const Segment& s = segs[seg_i];
       v = s.v; cc = s.c; seg_pos = s.out_off; seg_stop = s.out_off + s.n;

@@ -36,12 +36,16 @@ struct SkeletonArgs {
   GroupSeg* gsegs;                    // [n_groups][seg_cap]
   uint16_t* gseg_first;               // [n_groups][n_tiles]
   uint16_t* gseg_count;               // [n_groups][n_tiles]
+  TileRec* recs;                      // [n_voices][n_tiles]: continuation records of simple calls
+  uint32_t gen;                       // generation tag of this launch's records
   uint32_t seg_cap;
   uint32_t n_tiles;
-  uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores
+  uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores, 2 = no simple calls
 };
 
 constexpr int VK_MAX_VOICES = 1024;
+constexpr uint32_t SB_MAX = 256;   // chunk boundaries cached in shared memory
+constexpr uint32_t MAX_RUN = 64;   // chunks per free run
 
 struct VoiceHeader {  // what Sampler::next_free_voice_index needs (sampler.rs:826-860)
   uint64_t note_id;
@@ -90,6 +94,68 @@ PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t fr
   }
 }
 
+
+// One simple call (voice.cuh "simple calls"): the whole call's phase / envelope recurrences in one go, with a
+// 32-byte TileRec stored at every tile boundary crossed instead of a full Segment.
+template <int CC>
+PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const DevBuffer& buf, uint32_t n,
+                        uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen) {
+  cc.call_left = cc.chunk_left;
+  loop_range_samples(v, buf, cc.ls, cc.le);
+  cc.new_call = false;
+  if (!v.initialized) {  // CubicInterpolator::process prologue (cubic.rs:60-69)
+    v.initialized = 1;
+    v.hidx[3] = v.hidx[0];
+    v.hidx[2] = (int32_t)v.playback_pos; v.hidx[1] = (int32_t)(v.playback_pos + CC); v.hidx[0] = (int32_t)(v.playback_pos + 2 * CC);
+    v.playback_pos += 3 * CC;
+  }
+  const float ratio = v.ratio;
+  const bool env = gp.has_env && cc.env_per_frame;
+  float s = v.sub_pos;
+  uint32_t np = 0, off = call_off, remaining = n;
+  uint32_t piece = min(remaining, TILE - (off % TILE));
+  for (;;) {
+    bool fused = false;
+    if (env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE) {
+      float d;
+      bool on_hold;
+      if (env_bare_steps(v, gp, d, on_hold) >= piece) {  // the stage cannot end inside this piece: ride along
+        float o = on_hold ? v.env_hold : v.env_out;
+        np += phase_run<true>(s, ratio, piece, o, d);
+        if (on_hold) v.env_hold = o; else v.env_out = o;
+        fused = true;
+      }
+    }
+    if (!fused) {
+      np += phase_run(s, ratio, piece);
+      if (env) env_chain(v, gp, piece);
+    }
+    off += piece; remaining -= piece;
+    if (remaining == 0) break;
+    piece = min(remaining, TILE);
+    uint4 lo, hi;
+    lo.x = v.playback_pos + np * CC; lo.y = __float_as_uint(s); lo.z = __float_as_uint(v.env_out); lo.w = __float_as_uint(v.env_hold);
+    hi.x = __float_as_uint(v.env_target); hi.y = ((uint32_t)v.env_stage << 16) | piece; hi.z = base; hi.w = gen;
+    uint4* dst = reinterpret_cast<uint4*>(my_recs + off / TILE);
+    dst[0] = lo; dst[1] = hi;
+  }
+  v.sub_pos = s;
+  if (np >= 4) {
+    v.playback_pos += np * CC;
+    v.hidx[0] = (int32_t)(v.playback_pos - CC); v.hidx[1] = (int32_t)(v.playback_pos - 2 * CC);
+    v.hidx[2] = (int32_t)(v.playback_pos - 3 * CC); v.hidx[3] = (int32_t)(v.playback_pos - 4 * CC);
+  } else {
+    for (uint32_t i = 0; i < np; ++i) {
+      v.hidx[3] = v.hidx[2]; v.hidx[2] = v.hidx[1]; v.hidx[1] = v.hidx[0]; v.hidx[0] = (int32_t)v.playback_pos;
+      v.playback_pos += CC;
+    }
+  }
+  cc.produced_in_call = n;
+  cc.call_left = 0;
+  cc.chunk_left = 0;
+  after_process_call(v, cc);
+}
+
 // WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
 // control flow (the skeleton is a latency-bound chain of dependent f32 ops per voice, not a SIMT workload).
 template <int MAXT, bool WPV>
@@ -97,6 +163,8 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   __shared__ VoiceHeader s_head[WPV ? 32 : MAXT];
   __shared__ GroupState s_gs;
   __shared__ uint32_t s_count;
+  __shared__ uint64_t s_bounds[SB_MAX];   // this mixer's chunk boundaries of the block
+  __shared__ uint32_t s_cnt[MAX_RUN];      // voices still holding a note after each chunk of a free run
 
   const uint32_t g = a.group_list[blockIdx.x];
   const uint32_t tid = WPV ? ((threadIdx.x & 31u) == 0 ? (threadIdx.x >> 5) : 0xFFFFu) : threadIdx.x;
@@ -120,8 +188,17 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   Segment* my_segs = a.segs + (size_t)vidx * a.seg_cap;
   uint16_t* my_first = a.seg_first + (size_t)vidx * a.n_tiles;
   uint16_t* my_count = a.seg_count + (size_t)vidx * a.n_tiles;
+  TileRec* my_recs = a.recs + (size_t)vidx * a.n_tiles;
   uint32_t n_segs = 0, cur_tile = 0xFFFFFFFFu, cur_first = 0, cur_cnt = 0;
-  if (mine) for (uint32_t i = 0; i < a.n_tiles; ++i) my_count[i] = 0;
+  if (WPV) {  // the whole warp clears its voice's per-tile segment counts
+    const uint32_t wv = threadIdx.x >> 5;
+    if (wv < nv) {
+      uint16_t* cnt = a.seg_count + (size_t)(gp.first_voice + wv) * a.n_tiles;
+      for (uint32_t i = threadIdx.x & 31u; i < a.n_tiles; i += 32) cnt[i] = 0;
+    }
+  } else if (mine) {
+    for (uint32_t i = 0; i < a.n_tiles; ++i) my_count[i] = 0;
+  }
   GroupSeg* g_segs = a.gsegs + (size_t)g * a.seg_cap;
   uint16_t* g_first = a.gseg_first + (size_t)g * a.n_tiles;
   uint16_t* g_count = a.gseg_count + (size_t)g * a.n_tiles;
@@ -130,11 +207,156 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   __syncthreads();
 
   const uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];
+  for (uint32_t i = threadIdx.x; i < min(ce - cb, SB_MAX); i += blockDim.x) s_bounds[i] = a.chunk_bounds[cb + i];
+  __syncthreads();
+  auto bound = [&](const uint32_t i) -> uint64_t { return i - cb < SB_MAX ? s_bounds[i - cb] : a.chunk_bounds[i]; };
+  // time of the next pending event (re-read only when the cursor moved)
+  uint32_t ev_cached = 0xFFFFFFFFu;
+  uint64_t ev_next_time = UINT64_MAX;
   uint8_t* gflags = a.group_flags + (size_t)g * a.max_chunks;
   uint64_t my_frames = 0;
 
+  // One Source::write call of this thread's voice (already opened by voice_begin_call): emits the call's
+  // Segment / TileRec checkpoints and advances the control state. Returns the frames written.
+  auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) -> uint32_t {
+    uint32_t written_frames = 0;
+    bool simple = false;
+    if (n_segs < a.seg_cap && !(a.debug_flags & 2u))
+      simple = buf.channels == 2 ? simple_call_ok<2>(v, cc, buf, n) : simple_call_ok<1>(v, cc, buf, n);
+    if (simple) {
+      const uint32_t tile = call_off / TILE;
+      if (!(a.debug_flags & 1u)) {
+        Segment& s = my_segs[n_segs];
+        s.v = v; s.c = cc; s.out_off = call_off; s.n = min(n, (tile + 1) * TILE - call_off);
+      }
+      if (tile != cur_tile) {
+        if (cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
+        cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
+      }
+      cur_cnt++;
+      if (buf.channels == 2) simple_call<2>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
+      else simple_call<1>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
+      n_segs++;
+      written_frames = n;
+    } else {
+      uint32_t off = call_off, remaining = n;
+      while (remaining > 0 && !cc.ended) {
+        const uint32_t tile = off / TILE;
+        const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
+        if (n_segs < a.seg_cap && !(a.debug_flags & 1u)) {
+          Segment& s = my_segs[n_segs];
+          s.v = v; s.c = cc; s.out_off = off; s.n = seg_len;
+          // per-tile (first, count) live in registers and are stored when the tile changes: no global
+          // load sits on this latency-critical path
+          if (tile != cur_tile) {
+            if (cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
+            cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
+          }
+          cur_cnt++;
+          n_segs++;
+        }
+        uint32_t w;
+        if (buf.channels == 2) w = voice_advance<2>(v, cc, gp, buf, out_rate, comp, seg_len);
+        else w = voice_advance<1>(v, cc, gp, buf, out_rate, comp, seg_len);
+        written_frames += w;
+        off += w; remaining -= w;
+        if (w < seg_len) break;
+      }
+    }
+    my_frames += written_frames;
+    voice_end_call(v, cc, t + n);
+    return written_frames;
+  };
+  // generator-level gain / pan (player.rs:1075-1081) of one call: checkpoint per (call x tile), advance ramps (thread 0)
+  auto group_call = [&](const uint32_t n, const uint32_t call_off) {
+    const bool vol_ramp = exp_need_ramp(s_gs.vol, comp);
+    const bool vol_scale = !vol_ramp && fabsf(1.0f - s_gs.vol.target) > 0.000001f;
+    const bool pan_ramp = exp_need_ramp(s_gs.pan, comp);
+    const bool pan_apply = !pan_ramp && fabsf(s_gs.pan.target) > 0.000001f;
+    const uint32_t flags = (vol_ramp ? 1u : 0u) | (vol_scale ? 2u : 0u) | (pan_ramp ? 4u : 0u) | (pan_apply ? 8u : 0u);
+    if (flags == 0) return;  // unity gain, centre pan: the replay's default
+    uint32_t off = call_off, remaining = n;
+    while (remaining > 0) {
+      const uint32_t tile = off / TILE;
+      const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
+      if (n_gsegs < a.seg_cap) {
+        GroupSeg& s = g_segs[n_gsegs];
+        s.vol = s_gs.vol; s.pan = s_gs.pan; s.out_off = off; s.n = seg_len; s.flags = flags;
+        if (tile != gcur_tile) {
+          if (gcur_tile != 0xFFFFFFFFu) { g_first[gcur_tile] = (uint16_t)gcur_first; g_count[gcur_tile] = (uint16_t)gcur_cnt; }
+          gcur_tile = tile; gcur_first = n_gsegs; gcur_cnt = 0;
+        }
+        gcur_cnt++;
+        n_gsegs++;
+      }
+      if (vol_ramp) for (uint32_t i = 0; i < seg_len * 2; ++i) (void)exp_next(s_gs.vol, comp);
+      if (pan_ramp) for (uint32_t i = 0; i < seg_len; ++i) (void)exp_next(s_gs.pan, comp);
+      off += seg_len; remaining -= seg_len;
+    }
+  };
+
   for (uint32_t k = cb; k + 1 < ce; ++k) {
-    const uint64_t c0 = a.chunk_bounds[k], c1 = a.chunk_bounds[k + 1];
+    const uint64_t c0 = bound(k), c1 = bound(k + 1);
+    // ---- free run -------------------------------------------------------------------------------------
+    // Between two events of a Sampler nothing couples its voices: each one runs its own write calls through
+    // consecutive chunks without a CTA barrier and only reports whether it still holds a note after each
+    // chunk; thread 0 then replays the generator-level bookkeeping (active-voice count, stopped / dead,
+    // generator gain/pan checkpoints, chunk flags) for those chunks in order. A voice holding a note implies
+    // the generator writes (sampler.rs:978-981), so the voices need no group state while they run.
+    if (is_sampler) {
+      if (ev_cached != s_gs.ev_cursor) {
+        ev_cached = s_gs.ev_cursor;
+        ev_next_time = ev_cached < gp.ev_end ? a.events[ev_cached].time : UINT64_MAX;
+      }
+      uint32_t run = 0;
+      if (!s_gs.dead && gp.start_time <= c0) {
+        while (k + run + 1 < ce && run < MAX_RUN) {
+          const uint64_t r0 = bound(k + run), r1 = bound(k + run + 1);
+          if (ev_next_time <= r0) break;                            // an event is due at this chunk
+          if (s_gs.has_stop_time && s_gs.stop_time < r1) break;     // scheduled stop inside this chunk
+          ++run;
+        }
+      }
+      if (run) {
+        for (uint32_t j = threadIdx.x; j < run; j += blockDim.x) s_cnt[j] = 0;
+        __syncthreads();
+        if (mine) {
+          for (uint32_t j = 0; j < run; ++j) {
+            if (v.has_note) {
+              const uint64_t r0 = bound(k + j);
+              const uint32_t rlen = (uint32_t)(bound(k + j + 1) - r0);
+              CallCtx cc;
+              cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
+              if (voice_begin_call(v, cc, gp, buf, rlen, comp, gp.has_env != 0)) run_call(cc, rlen, (uint32_t)(r0 - a.block_start), r0);
+              // SamplerVoice::process epilogue (voice.rs:488-502)
+              if (v.finished || (gp.has_env && v.env_stage == ENV_IDLE)) voice_reset(v);
+              if (v.has_note) atomicAdd(&s_cnt[j], 1u);
+            }
+          }
+          publish_header(s_head, tid, v);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          for (uint32_t j = 0; j < run; ++j) {
+            bool writes = false;
+            if (!s_gs.dead) {
+              writes = !(s_gs.stopped || (s_gs.active_voices == 0 && !s_gs.stopping));
+              if (writes) {
+                const uint64_t r0 = bound(k + j);
+                group_call((uint32_t)(bound(k + j + 1) - r0), (uint32_t)(r0 - a.block_start));
+                s_gs.active_voices = s_cnt[j];
+                if (s_gs.stopping && s_cnt[j] == 0) s_gs.stopped = 1;
+              }
+              if (gp.transient && s_gs.stopped) s_gs.dead = 1;
+            }
+            gflags[k + j - cb] = writes ? 1 : 0;
+          }
+        }
+        __syncthreads();
+        k += run - 1;
+        continue;
+      }
+    }
     const uint32_t len = (uint32_t)(c1 - c0);
     const uint32_t boff = (uint32_t)(c0 - a.block_start);
     bool produced = false;
@@ -255,59 +477,8 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
       // 3. advance the voice through the call, one segment per (call x 64-frame tile)
       const uint32_t call_off = boff + total;  // first frame of the call, relative to the block
       uint32_t written_frames = 0;
-      if (call_open) {
-        uint32_t off = call_off, remaining = n;
-        while (remaining > 0 && !cc.ended) {
-          const uint32_t tile = off / TILE;
-          const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
-          if (n_segs < a.seg_cap && !(a.debug_flags & 1u)) {
-            Segment& s = my_segs[n_segs];
-            s.v = v; s.c = cc; s.out_off = off; s.n = seg_len;
-            // per-tile (first, count) live in registers and are stored when the tile changes: no global
-            // load sits on this latency-critical path
-            if (tile != cur_tile) {
-              if (cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
-              cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
-            }
-            cur_cnt++;
-            n_segs++;
-          }
-          uint32_t w;
-          if (buf.channels == 2) w = voice_advance<2>(v, cc, gp, buf, out_rate, comp, seg_len);
-          else w = voice_advance<1>(v, cc, gp, buf, out_rate, comp, seg_len);
-          written_frames += w;
-          off += w; remaining -= w;
-          if (w < seg_len) break;
-        }
-        my_frames += written_frames;
-        voice_end_call(v, cc, t + n);
-      }
-      // generator-level gain / pan (player.rs:1075-1081): checkpoint per (call x tile), advance ramps
-      if (is_sampler && group_writes && tid == 0) {
-        const bool vol_ramp = exp_need_ramp(s_gs.vol, comp);
-        const bool vol_scale = !vol_ramp && fabsf(1.0f - s_gs.vol.target) > 0.000001f;
-        const bool pan_ramp = exp_need_ramp(s_gs.pan, comp);
-        const bool pan_apply = !pan_ramp && fabsf(s_gs.pan.target) > 0.000001f;
-        const uint32_t flags = (vol_ramp ? 1u : 0u) | (vol_scale ? 2u : 0u) | (pan_ramp ? 4u : 0u) | (pan_apply ? 8u : 0u);
-        uint32_t off = call_off, remaining = n;
-        while (remaining > 0) {
-          const uint32_t tile = off / TILE;
-          const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
-          if (n_gsegs < a.seg_cap) {
-            GroupSeg& s = g_segs[n_gsegs];
-            s.vol = s_gs.vol; s.pan = s_gs.pan; s.out_off = off; s.n = seg_len; s.flags = flags;
-            if (tile != gcur_tile) {
-              if (gcur_tile != 0xFFFFFFFFu) { g_first[gcur_tile] = (uint16_t)gcur_first; g_count[gcur_tile] = (uint16_t)gcur_cnt; }
-              gcur_tile = tile; gcur_first = n_gsegs; gcur_cnt = 0;
-            }
-            gcur_cnt++;
-            n_gsegs++;
-          }
-          if (vol_ramp) for (uint32_t i = 0; i < seg_len * 2; ++i) (void)exp_next(s_gs.vol, comp);
-          if (pan_ramp) for (uint32_t i = 0; i < seg_len; ++i) (void)exp_next(s_gs.pan, comp);
-          off += seg_len; remaining -= seg_len;
-        }
-      }
+      if (call_open) written_frames = run_call(cc, n, call_off, t);
+      if (is_sampler && group_writes && tid == 0) group_call(n, call_off);
       uint32_t written;
       if (is_sampler) {
         written = group_writes ? n : 0;

@@ -463,6 +463,119 @@ PB_DEV void voice_end_call(VoiceState& v, CallCtx& c, uint64_t call_end_frame) {
 PB_DEV float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 PB_DEV float fset_lt(float a, float b) { float d; asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 
+// The resampler's f32 phase recurrence for `span` output frames on the fast path (no input exhaustion
+// possible, 0 < ratio < 64, not the bypass ratio): advances sub_pos exactly as CubicInterpolator::process
+// does (cubic.rs:72-110) and returns how many input frames were pushed.
+// ACC additionally runs an independent `o += d` chain (an envelope stage's bare accumulate) in the latency
+// shadow of the phase chain.
+template <bool ACC>
+PB_DEV uint32_t phase_run(float& s, const float ratio, const uint32_t span, float& o, const float d) {
+  uint32_t np = 0;
+  if (ratio < 1.0f) {
+    // if sub_pos >= 1 { push; sub_pos -= 1 }; sub_pos += ratio  (cubic.rs:73-89): `- 1.0` and `- 0.0` are both
+    // exact, so the branch becomes a subtract of the comparison result; pushes are counted off the chain
+    float pushes = 0.0f;
+#pragma unroll 4
+    for (uint32_t f = 0; f < span; ++f) {
+      const float p = fset_ge(s, 1.0f);
+      s = s - p;
+      pushes += p;
+      s += ratio;
+      if (ACC) o += d;
+    }
+    np = (uint32_t)pushes;
+  } else {
+    // `while sub_pos < ratio { push; sub_pos += 1.0 }; sub_pos -= ratio` (cubic.rs:94-105).
+    // With sub_pos in [0,1) at frame start the trip count is n0 = floor(ratio) or n0 + 1. Repeated
+    // f32 `+= 1.0` only rounds when the sum enters a new binade ([1,2), [2,4), [4,8), ...) and is
+    // exact inside one, so t_n = sub_pos after n pushes has the closed form
+    //   t_n = fl(fl(fl(fl(s + a1) + a2) + a3) + a4),  a = (min(n,1), min(n-1,2), min(n-3,4), min(n-7,8))
+    // (bit-identical to the sequential adds; validated exhaustively in tests/test_phase_closed_form.py).
+    // Each frame is then a short FADD chain plus the reference's own exit test; anything unusual
+    // (sub_pos >= 1 after a ratio change, integer ratios) takes the literal loop.
+    const int n0 = (int)ratio;
+    const int nm = n0 - 1;
+    const float a1 = (float)min(max(nm, 0), 1), a2 = (float)min(max(nm - 1, 0), 2);
+    const float a3 = (float)min(max(nm - 3, 0), 4), a4 = (float)min(max(nm - 7, 0), 8);
+    // integer ratios are the one case where t_{n0-1} can reach `ratio`: leave them to the literal loop
+    const bool closed_ok = ratio < 14.0f && ratio != (float)n0;
+    uint32_t f = 0;
+    // first frame (sub_pos may be >= 1 right after a ratio change) and unsupported ratios: literal loop
+    const uint32_t literal = closed_ok ? (s < 1.0f ? 0u : 1u) : span;
+    for (; f < literal && f < span; ++f) {
+      while (s < ratio) { s += 1.0f; ++np; }
+      s -= ratio;
+      if (ACC) o += d;
+    }
+    // from here on sub_pos = t - ratio with t in [ratio, ratio + 1): always in [0, 1)
+    float extra_f = 0.0f;  // frames that needed n0 + 1 pushes
+#define PB_PHASE_LOOP(TM_EXPR)                                   \
+    for (; f < span; ++f) {                                  \
+      const float tm = (TM_EXPR);                            \
+      const float t0 = tm + 1.0f;                            \
+      const float more = fset_lt(t0, ratio);                 \
+      const float t = t0 + more; /* + 0.0 is exact */        \
+      extra_f += more;                                       \
+      s = t - ratio;                                         \
+      if (ACC) o += d;                                       \
+    }
+    if (nm <= 0) { PB_PHASE_LOOP(s) }
+    else if (nm == 1) { PB_PHASE_LOOP(s + 1.0f) }
+    else if (nm <= 3) { PB_PHASE_LOOP((s + 1.0f) + a2) }
+    else if (nm <= 7) { PB_PHASE_LOOP(((s + 1.0f) + 2.0f) + a3) }
+    else { PB_PHASE_LOOP((((s + 1.0f) + 2.0f) + 4.0f) + a4) }
+#undef PB_PHASE_LOOP
+    np += (span - min(literal, span)) * (uint32_t)n0 + (uint32_t)extra_f;
+    (void)a1;
+  }
+  return np;
+}
+PB_DEV uint32_t phase_run(float& s, const float ratio, const uint32_t span) {
+  float o = 0.0f;
+  return phase_run<false>(s, ratio, span, o, 0.0f);
+}
+
+// How many frames the current envelope stage can run as a bare chain of the reference's own f32 accumulate
+// before a threshold crossing comes within reach (10 % + 2 steps of slack), the per-frame increment `d`
+// (`x -= step` == `x += -step` exactly) and whether the chain runs on env_hold instead of env_out.
+PB_DEV uint32_t env_bare_steps(const VoiceState& v, const GroupParams& gp, float& d, bool& on_hold) {
+  const uint32_t stage = v.env_stage;
+  float room = 0.0f, step = 1.0f;
+  on_hold = false;
+  d = 0.0f;
+  if (stage == ENV_ATTACK) { room = v.env_target - v.env_out; step = gp.attack_rate; d = step; }
+  else if (stage == ENV_HOLD) { room = v.env_hold; step = 1.0f; d = -1.0f; on_hold = true; }
+  else if (stage == ENV_DECAY && v.env_out > gp.sustain_level) { room = v.env_out - gp.sustain_level; step = gp.decay_rate; d = -step; }
+  else if (stage == ENV_RELEASE) { room = v.env_out - 0.001f; step = v.env_release_out * gp.release_rate; d = -step; }
+  if (room > 0.0f && step > 0.0f) {
+    const float q = fminf(room / step * 0.9f, 1.0e6f);
+    return q > 3.0f ? (uint32_t)q - 2u : 0u;
+  }
+  return 0u;
+}
+
+// The AHDSR stage machine advanced by `w` frames, state only (ahdsr.rs:448-516)
+PB_DEV void env_chain(VoiceState& v, const GroupParams& gp, const uint32_t w) {
+  uint32_t i = 0;
+  while (i < w) {
+    const uint32_t stage = v.env_stage;
+    if (stage == ENV_SUSTAIN || stage == ENV_IDLE) break;
+    float d;
+    bool on_hold;
+    const uint32_t m = min(env_bare_steps(v, gp, d, on_hold), w - i);
+    if (m) {
+      float o = on_hold ? v.env_hold : v.env_out;
+#pragma unroll 8
+      for (uint32_t j = 0; j < m; ++j) o += d;
+      if (on_hold) v.env_hold = o; else v.env_out = o;
+      i += m;
+    } else {
+      (void)env_run(v, gp);
+      ++i;
+    }
+  }
+}
+
 // ---- skeleton fast path -------------------------------------------------------------------------------------
 // State-only advance of one write call by up to `n` frames, bit-identical to voice_frames<CC,false> but with
 // the independent recurrences separated into tight loops: (1) the resampler's f32 phase/position
@@ -508,61 +621,7 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
         }
       }
       float s = v.sub_pos;
-      uint32_t np = 0;
-      if (ratio < 1.0f) {
-        // if sub_pos >= 1 { push; sub_pos -= 1 }; sub_pos += ratio  (cubic.rs:73-89): `- 1.0` and `- 0.0` are both
-        // exact, so the branch becomes a subtract of the comparison result; pushes are counted off the chain
-        float pushes = 0.0f;
-#pragma unroll 4
-        for (uint32_t f = 0; f < span; ++f) {
-          const float p = fset_ge(s, 1.0f);
-          s = s - p;
-          pushes += p;
-          s += ratio;
-        }
-        np = (uint32_t)pushes;
-      } else {
-        // `while sub_pos < ratio { push; sub_pos += 1.0 }; sub_pos -= ratio` (cubic.rs:94-105).
-        // With sub_pos in [0,1) at frame start the trip count is n0 = floor(ratio) or n0 + 1. Repeated
-        // f32 `+= 1.0` only rounds when the sum enters a new binade ([1,2), [2,4), [4,8), ...) and is
-        // exact inside one, so t_n = sub_pos after n pushes has the closed form
-        //   t_n = fl(fl(fl(fl(s + a1) + a2) + a3) + a4),  a = (min(n,1), min(n-1,2), min(n-3,4), min(n-7,8))
-        // (bit-identical to the sequential adds; validated exhaustively in tests/test_phase_closed_form.py).
-        // Each frame is then a short FADD chain plus the reference's own exit test; anything unusual
-        // (sub_pos >= 1 after a ratio change, integer ratios) takes the literal loop.
-        const int n0 = (int)ratio;
-        const int nm = n0 - 1;
-        const float a1 = (float)min(max(nm, 0), 1), a2 = (float)min(max(nm - 1, 0), 2);
-        const float a3 = (float)min(max(nm - 3, 0), 4), a4 = (float)min(max(nm - 7, 0), 8);
-        // integer ratios are the one case where t_{n0-1} can reach `ratio`: leave them to the literal loop
-        const bool closed_ok = ratio < 14.0f && ratio != (float)n0;
-        uint32_t f = 0;
-        // first frame (sub_pos may be >= 1 right after a ratio change) and unsupported ratios: literal loop
-        const uint32_t literal = closed_ok ? (s < 1.0f ? 0u : 1u) : span;
-        for (; f < literal && f < span; ++f) {
-          while (s < ratio) { s += 1.0f; ++np; }
-          s -= ratio;
-        }
-        // from here on sub_pos = t - ratio with t in [ratio, ratio + 1): always in [0, 1)
-        float extra_f = 0.0f;  // frames that needed n0 + 1 pushes
-#define PB_PHASE_LOOP(TM_EXPR)                                   \
-        for (; f < span; ++f) {                                  \
-          const float tm = (TM_EXPR);                            \
-          const float t0 = tm + 1.0f;                            \
-          const float more = fset_lt(t0, ratio);                 \
-          const float t = t0 + more; /* + 0.0 is exact */        \
-          extra_f += more;                                       \
-          s = t - ratio;                                         \
-        }
-        if (nm <= 0) { PB_PHASE_LOOP(s) }
-        else if (nm == 1) { PB_PHASE_LOOP(s + 1.0f) }
-        else if (nm <= 3) { PB_PHASE_LOOP((s + 1.0f) + a2) }
-        else if (nm <= 7) { PB_PHASE_LOOP(((s + 1.0f) + 2.0f) + a3) }
-        else { PB_PHASE_LOOP((((s + 1.0f) + 2.0f) + 4.0f) + a4) }
-#undef PB_PHASE_LOOP
-        np += (span - min(literal, span)) * (uint32_t)n0 + (uint32_t)extra_f;
-        (void)a1;
-      }
+      const uint32_t np = phase_run(s, ratio, span);
       v.sub_pos = s;
       if (np >= 4) {
         v.playback_pos += np * CC;
@@ -621,35 +680,7 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
       v.pan.current = cur;
     }
     // (5) AHDSR (ahdsr.rs:448-516); Sustain and Idle do not move
-    if (gp.has_env && c.env_per_frame) {
-      uint32_t i = 0;
-      while (i < w) {
-        const uint32_t stage = v.env_stage;
-        if (stage == ENV_SUSTAIN || stage == ENV_IDLE) break;
-        // run the stage's accumulate as a bare chain of the reference's own f32 op while a threshold
-        // crossing is provably out of reach (10 % + 2 steps of slack), then fall back to env_run
-        float room = 0.0f, step = 1.0f;
-        if (stage == ENV_ATTACK) { room = v.env_target - v.env_out; step = gp.attack_rate; }
-        else if (stage == ENV_HOLD) { room = v.env_hold; step = 1.0f; }
-        else if (stage == ENV_DECAY && v.env_out > gp.sustain_level) { room = v.env_out - gp.sustain_level; step = gp.decay_rate; }
-        else if (stage == ENV_RELEASE) { room = v.env_out - 0.001f; step = v.env_release_out * gp.release_rate; }
-        uint32_t m = 0;
-        if (room > 0.0f && step > 0.0f) {
-          const float q = fminf(room / step * 0.9f, 1.0e6f);
-          m = q > 3.0f ? (uint32_t)q - 2u : 0u;
-          m = min(m, w - i);
-        }
-        if (m) {
-          if (stage == ENV_ATTACK) { float o = v.env_out; for (uint32_t j = 0; j < m; ++j) o += step; v.env_out = o; }
-          else if (stage == ENV_HOLD) { float o = v.env_hold; for (uint32_t j = 0; j < m; ++j) o -= 1.0f; v.env_hold = o; }
-          else { float o = v.env_out; for (uint32_t j = 0; j < m; ++j) o -= step; v.env_out = o; }
-          i += m;
-        } else {
-          (void)env_run(v, gp);
-          ++i;
-        }
-      }
-    }
+    if (gp.has_env && c.env_per_frame) env_chain(v, gp, w);
     done += w;
     if (w < span) break;
   }
@@ -672,5 +703,58 @@ struct GroupSeg {
   uint32_t flags;  // bit0 vol_ramp, bit1 vol_scale, bit2 pan_ramp, bit3 pan_apply
   uint32_t _pad;
 };
+
+
+// ---- simple calls -----------------------------------------------------------------------------------------
+// A write call is "simple" when nothing but the phase recurrence and the envelope can move during it: no
+// glide (one write_buffer call, constant ratio), no fader / gain / pan ramp, and enough input left that
+// neither a loop wrap nor EOF can be reached. The skeleton then emits one full Segment at the call's first
+// frame and, at every later 64-frame tile boundary inside the call, only this 32-byte record; the replay
+// rebuilds the complete state from the call's Segment + the record (apply_tile_rec).
+struct __align__(16) TileRec {
+  uint32_t pos;        // playback_pos at the tile boundary
+  float sub_pos;
+  float env_out, env_hold, env_target;
+  uint32_t stage_n;    // env_stage << 16 | frames of this piece
+  uint32_t base;       // index of the call's Segment
+  uint32_t gen;        // time-block generation tag (stale records of earlier blocks are ignored)
+};
+
+template <int CC>
+PB_DEV bool simple_call_ok(const VoiceState& v, const CallCtx& c, const DevBuffer& b, uint32_t n) {
+  if (c.gliding || c.fader_running || c.vol_ramp || c.pan_ramp) return false;
+  const float ratio = v.ratio;
+  if (fabsf(ratio - 1.0f) < 0.000001f || !(ratio > 0.0f) || !(ratio < 64.0f)) return false;
+  if (ratio >= 1.0f && !(ratio < 14.0f && ratio != (float)(int)ratio && v.sub_pos < 1.0f)) return false;
+  uint32_t ls, le;
+  loop_range_samples(v, b, ls, le);
+  const uint32_t avail = le > v.playback_pos ? (le - v.playback_pos) / CC : 0u;
+  const uint32_t per_frame = ratio < 1.0f ? 1u : (uint32_t)ratio + 2u;
+  return (uint64_t)n * per_frame + 4u < (uint64_t)avail;
+}
+
+// Rebuild the voice state `frames_in` frames into a simple call from the state at the call's first frame.
+template <int CC>
+PB_DEV void apply_tile_rec(VoiceState& v, CallCtx& c, const DevBuffer& b, const TileRec& r, uint32_t frames_in) {
+  // start of the (single) write_buffer call + CubicInterpolator::process prologue (preloaded.rs:419-447, cubic.rs:47-69)
+  c.call_left = c.chunk_left;
+  loop_range_samples(v, b, c.ls, c.le);
+  c.new_call = false;
+  // all pushes since the call started (3 preload frames included) took consecutive input frames
+  const uint32_t k = (r.pos - v.playback_pos) / CC;
+  int32_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = (uint32_t)i < k ? (int32_t)(r.pos - (uint32_t)(i + 1) * CC) : v.hidx[(uint32_t)i - min(k, (uint32_t)i)];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.hidx[i] = h[i];
+  v.initialized = 1;
+  v.playback_pos = r.pos;
+  v.sub_pos = r.sub_pos;
+  c.produced_in_call = frames_in;
+  c.call_left -= frames_in;
+  c.chunk_left -= frames_in;
+  v.env_out = r.env_out; v.env_hold = r.env_hold; v.env_target = r.env_target;
+  v.env_stage = r.stage_n >> 16;
+}
 
 }  // namespace pb
