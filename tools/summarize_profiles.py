@@ -30,7 +30,7 @@ for r in rows:
     agg[name][1] += v
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(ROOT, "profiles", f"{tag}_launches_summary.csv"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 1 --warmup 1 --no-cpu-baseline\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 800 python bench.py --steps 1 --warmup 1 --no-cpu-baseline\n")
     f.write("# cold-cache, serialised per-launch times: compare SHARES, not absolutes (cfg2 workload, 1 warm-up + 1 step)\n")
     f.write("kernel,launches,total_us,share_pct\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -48,7 +48,7 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
 with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.csv"), "w") as f:
-    f.write("# ncu --set full --clock-control none --import-source on, one launch each (one 8192-frame time block of cfg2)\n")
+    f.write("# ncu --set full --clock-control none --import-source on, one launch each (one time block of cfg2; block size = PB200_TIME_BLOCK default)\n")
     f.write("report,kernel,metric,value,unit\n")
     for spec in reps:
         rep, label = spec.split(":")
