@@ -193,7 +193,7 @@ int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_opti
   if (buffer_id >= r->buffers.size()) return fail(r, PB200_ERR_PARAMETER, "unknown buffer");
   if (int e = validate_vol_pan(r, o->volume, o->panning)) return e;
   if (o->speed < 0.0 || std::isnan(o->speed) || std::isinf(o->speed)) return fail(r, PB200_ERR_PARAMETER, "playback options 'speed' value is invalid");
-  if (o->resampling_quality != 0) return fail(r, PB200_ERR_UNSUPPORTED, "HighQuality (sinc) resampling is not restated yet");
+  if (o->resampling_quality > 1) return fail(r, PB200_ERR_PARAMETER, "unknown resampling quality");
   auto mit = r->mixers.find(o->target_mixer);
   if (mit == r->mixers.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
   FilePlaybackOptions fo;
@@ -202,6 +202,7 @@ int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_opti
   if (o->loop_start >= 0 && o->loop_end >= 0) { fo.has_loop_range = true; fo.loop_start = (uint64_t)o->loop_start; fo.loop_end = (uint64_t)o->loop_end; }
   fo.has_fade_in = o->fade_in_nanos != PB200_DURATION_NONE; if (fo.has_fade_in) fo.fade_in = Duration::from_nanos(o->fade_in_nanos);
   fo.has_fade_out = o->fade_out_nanos != PB200_DURATION_NONE; if (fo.has_fade_out) fo.fade_out = Duration::from_nanos(o->fade_out_nanos);
+  fo.resampling_quality = o->resampling_quality;
   auto fs = std::make_unique<PreloadedFileSource>(r->buffers[buffer_id], fo, r->cfg.sample_rate);
   pb200_renderer::SourceRef ref;
   ref.mixer = o->target_mixer;
@@ -314,6 +315,14 @@ int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
       return PB200_OK;
     case PB200_EV_SET_SOURCE_SPEED:
       if (!ref.queues.file) return fail(r, PB200_ERR_PARAMETER, "set_speed needs a file source");
+      // HighQuality: rubato is built with max_resample_ratio_relative = 1.0 (rubato.rs:37), so any other output rate
+      // makes set_resample_ratio fail and FileSourceImpl::update_speed `expect`-panics (common.rs:166-168)
+      if (ref.file && ref.file->hq) {
+        auto* rr = static_cast<RubatoResampler*>(ref.file->resampler_box.get());
+        uint32_t new_rate = f64_as_u32((double)r->cfg.sample_rate / ev->speed);
+        if (has_glide || (double)new_rate / (double)rr->input_rate != rr->resampler.resample_ratio_original)
+          return fail(r, PB200_ERR_RESAMPLING, "HighQuality file sources cannot change speed");
+      }
       if (now) { FileMsg m{FileMsg::SetSpeed}; m.speed = ev->speed; m.has_glide = has_glide; m.glide = ev->glide; if (!ref.queues.file->push(m)) return fail(r, PB200_ERR_SEND, "File playback queue is full"); }
       else { MixerEvent e; e.kind = MixerEvent::SetSourceSpeed; e.speed = ev->speed; e.has_glide = has_glide; e.glide = ev->glide; push_event(e); }
       return PB200_OK;

@@ -464,6 +464,240 @@ struct CubicResampler {
   void reset() { for (auto& i : interpolators) i.reset(); }
 };
 
+// ---- rubato ^0.16 `SincFixedIn<f32>` (THIRD-PARTY crate, not vendored under /root/reference) ---------
+// PARITY UNPINNED: restated from rubato 0.16's published algorithm (src/sinc.rs make_sincs, src/windows.rs
+// blackman_harris / make_window, src/sinc_interpolator/mod.rs ScalarInterpolator::get_sinc_interpolated,
+// src/asynchro_sinc.rs SincFixedIn::{new, process_into_buffer}, get_nearest_times_4, interp_cubic). Neither
+// the crate nor any golden vector of it is available in this environment; the reference's only test at this
+// boundary (preloaded.rs:513-532) takes the equal-rate bypass and never enters rubato. rubato picks an
+// AVX/SSE/NEON interpolator at run time whose summation order differs from the scalar one restated here, so
+// even reference-vs-reference is only ~1e-6 exact. Call sites: src/utils/resampler/rubato.rs:22-56,100-103.
+struct RubatoSincTable {
+  size_t sinc_len = 0, factor = 0;
+  std::vector<float> sincs;  // [factor][sinc_len]
+  const float* row(size_t sub) const { return sincs.data() + sub * sinc_len; }
+  // windows.rs: blackman_harris (periodic, f32) squared for BlackmanHarris2
+  static std::vector<float> blackman_harris2(size_t npoints) {
+    std::vector<float> w(npoints);
+    const float PI = 3.14159265358979323846264338327950288f;
+    const float pi2 = 2.0f * PI, pi4 = 4.0f * PI, pi6 = 6.0f * PI;
+    const float np_f = (float)npoints;
+    const float a = 0.35875f, b = 0.48829f, c = 0.14128f, d = 0.01168f;
+    for (size_t x = 0; x < npoints; ++x) {
+      const float xf = (float)x;
+      float v = a - b * std::cos(pi2 * xf / np_f) + c * std::cos(pi4 * xf / np_f) - d * std::cos(pi6 * xf / np_f);
+      w[x] = v * v;
+    }
+    return w;
+  }
+  static float sinc(float value) {
+    const float PI = 3.14159265358979323846264338327950288f;
+    if (value == 0.0f) return 1.0f;
+    return std::sin(value * PI) / (value * PI);
+  }
+  // sinc.rs make_sincs(npoints, factor, f_cutoff, window)
+  void make(size_t npoints, size_t fac, float f_cutoff) {
+    sinc_len = npoints; factor = fac;
+    const size_t totpoints = npoints * fac;
+    std::vector<float> y(totpoints);
+    std::vector<float> window = blackman_harris2(totpoints);
+    float sum = 0.0f;
+    for (size_t x = 0; x < totpoints; ++x) {
+      float val = window[x] * sinc(((float)x - (float)(totpoints / 2)) * f_cutoff / (float)fac);
+      sum += val;
+      y[x] = val;
+    }
+    sum /= (float)fac;
+    sincs.assign(fac * npoints, 0.0f);
+    for (size_t p = 0; p < npoints; ++p)
+      for (size_t n = 0; n < fac; ++n) sincs[(fac - n - 1) * npoints + p] = y[fac * p + n] / sum;
+  }
+  // one table per cutoff (make_interpolator: f_cutoff scaled by the ratio when downsampling)
+  static std::shared_ptr<RubatoSincTable> get(size_t sinc_len, double resample_ratio, float f_cutoff, size_t factor) {
+    static std::vector<std::pair<uint32_t, std::shared_ptr<RubatoSincTable>>> cache;
+    sinc_len = 8 * (size_t)std::ceil((float)sinc_len / 8.0f);
+    float fc = resample_ratio >= 1.0 ? f_cutoff : f_cutoff * (float)resample_ratio;
+    uint32_t key;
+    std::memcpy(&key, &fc, 4);
+    for (auto& e : cache) if (e.first == key && e.second->sinc_len == sinc_len && e.second->factor == factor) return e.second;
+    auto t = std::make_shared<RubatoSincTable>();
+    t->make(sinc_len, factor, fc);
+    cache.emplace_back(key, t);
+    return t;
+  }
+  // ScalarInterpolator::get_sinc_interpolated: 8 interleaved accumulators, summed acc0+...+acc7
+  float dot(const float* wave, size_t index, size_t subindex) const {
+    const float* w = wave + index;
+    const float* s = row(subindex);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i < sinc_len; i += 8)
+      for (size_t k = 0; k < 8; ++k) acc[k] += w[i + k] * s[i + k];
+    return acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7];
+  }
+};
+
+struct RubatoSincFixedIn {
+  size_t nbr_channels, chunk_size;
+  double last_index, resample_ratio, resample_ratio_original, target_ratio, max_relative_ratio;
+  std::shared_ptr<RubatoSincTable> interpolator;
+  std::vector<std::vector<float>> buffer;  // [ch][chunk_size + 2 * sinc_len]
+  RubatoSincFixedIn(double ratio, double max_rel, size_t sinc_len, float f_cutoff, size_t oversampling, size_t chunk, size_t ch)
+      : nbr_channels(ch), chunk_size(chunk), resample_ratio(ratio), resample_ratio_original(ratio), target_ratio(ratio),
+        max_relative_ratio(max_rel), interpolator(RubatoSincTable::get(sinc_len, ratio, f_cutoff, oversampling)) {
+    buffer.assign(ch, std::vector<float>(chunk + 2 * interpolator->sinc_len, 0.0f));
+    last_index = -(double)(interpolator->sinc_len / 2);
+  }
+  size_t output_frames_max() const { return (size_t)((double)chunk_size * resample_ratio_original * max_relative_ratio + 10.0); }
+  bool set_resample_ratio(double new_ratio, bool ramp) {
+    if (new_ratio / resample_ratio_original >= 1.0 / max_relative_ratio && new_ratio / resample_ratio_original <= max_relative_ratio) {
+      if (!ramp) resample_ratio = new_ratio;
+      target_ratio = new_ratio;
+      return true;
+    }
+    return false;  // ResampleError::RatioOutOfBounds
+  }
+  static void get_nearest_times_4(double t, long factor, long (*points)[2]) {
+    long index = (long)std::floor(t);
+    long frac = (long)std::floor((t - std::floor(t)) * (double)factor);
+    if (frac == 0) {
+      points[0][0] = index - 1; points[0][1] = factor - 1;
+      points[1][0] = index; points[1][1] = 0;
+      points[2][0] = index; points[2][1] = 1;
+      points[3][0] = index; points[3][1] = 2;
+    } else if (frac == factor - 2) {
+      points[0][0] = index; points[0][1] = frac - 1;
+      points[1][0] = index; points[1][1] = frac;
+      points[2][0] = index; points[2][1] = frac + 1;
+      points[3][0] = index + 1; points[3][1] = 0;
+    } else if (frac == factor - 1) {
+      points[0][0] = index; points[0][1] = frac - 1;
+      points[1][0] = index; points[1][1] = frac;
+      points[2][0] = index + 1; points[2][1] = 0;
+      points[3][0] = index + 1; points[3][1] = 1;
+    } else {
+      for (long k = 0; k < 4; ++k) { points[k][0] = index; points[k][1] = frac - 1 + k; }
+    }
+  }
+  static float interp_cubic(float x, const float* y) {
+    float a0 = y[1];
+    float a1 = -(1.0f / 3.0f) * y[0] - 0.5f * y[1] + y[2] - (1.0f / 6.0f) * y[3];
+    float a2 = 0.5f * (y[0] + y[2]) - y[1];
+    float a3 = 0.5f * (y[1] - y[2]) + (1.0f / 6.0f) * (y[3] - y[0]);
+    float x2 = x * x;
+    float x3 = x2 * x;
+    return a0 + a1 * x + a2 * x2 + a3 * x3;
+  }
+  // process_into_buffer (cubic interpolation arm); wave_in[ch][chunk_size], returns frames written per channel
+  size_t process_into_buffer(const std::vector<std::vector<float>>& wave_in, std::vector<std::vector<float>>& wave_out) {
+    const size_t sinc_len = interpolator->sinc_len;
+    const long oversampling = (long)interpolator->factor;
+    double t_ratio = 1.0 / resample_ratio;
+    const double t_ratio_end = 1.0 / target_ratio;
+    const double approximate_nbr_frames = (double)chunk_size * (0.5 * resample_ratio + 0.5 * target_ratio);
+    const double t_ratio_increment = (t_ratio_end - t_ratio) / approximate_nbr_frames;
+    const long end_idx = (long)chunk_size - ((long)sinc_len + 1) - (long)std::ceil(t_ratio_end);
+    for (auto& buf : buffer) std::memmove(buf.data(), buf.data() + chunk_size, 2 * sinc_len * sizeof(float));
+    for (size_t c = 0; c < nbr_channels; ++c) std::memcpy(buffer[c].data() + 2 * sinc_len, wave_in[c].data(), chunk_size * sizeof(float));
+    double idx = last_index;
+    size_t n = 0;
+    float points[4];
+    long nearest[4][2];
+    while (idx < (double)end_idx) {
+      t_ratio += t_ratio_increment;
+      idx += t_ratio;
+      get_nearest_times_4(idx, oversampling, nearest);
+      double frac = idx * (double)oversampling - std::floor(idx * (double)oversampling);
+      float frac_offset = (float)frac;
+      for (size_t c = 0; c < nbr_channels; ++c) {
+        for (int k = 0; k < 4; ++k)
+          points[k] = interpolator->dot(buffer[c].data(), (size_t)(nearest[k][0] + 2 * (long)sinc_len), (size_t)nearest[k][1]);
+        wave_out[c][n] = interp_cubic(frac_offset, points);
+      }
+      n += 1;
+    }
+    last_index = idx - (double)chunk_size;
+    resample_ratio = target_ratio;
+    return n;
+  }
+};
+
+// ---- trait AudioResampler (src/utils/resampler.rs:43-64) ----------------------------------------------
+struct AudioResampler {
+  virtual ~AudioResampler() {}
+  virtual size_t required_input_buffer_size() const = 0;  // 0 = None
+  virtual size_t max_input_buffer_size() const = 0;       // 0 = None
+  virtual std::pair<size_t, size_t> process(const float* in, size_t in_len, float* out, size_t out_len) = 0;
+  virtual bool update(uint32_t in_rate, uint32_t out_rate) = 0;  // false = Err (the caller `expect`s)
+  virtual void reset() = 0;
+};
+struct CubicAudioResampler : AudioResampler {
+  CubicResampler r;
+  CubicAudioResampler(uint32_t in_rate, uint32_t out_rate, size_t cc) : r(in_rate, out_rate, cc) {}
+  size_t required_input_buffer_size() const override { return 0; }
+  size_t max_input_buffer_size() const override { return 0; }
+  std::pair<size_t, size_t> process(const float* in, size_t in_len, float* out, size_t out_len) override { return r.process(in, in_len, out, out_len); }
+  bool update(uint32_t in_rate, uint32_t out_rate) override { r.update(in_rate, out_rate); return true; }
+  void reset() override { r.reset(); }
+};
+
+// ---- RubatoResampler (src/utils/resampler/rubato.rs:12-154) -----------------------------------------
+struct RubatoResampler : AudioResampler {
+  uint32_t input_rate, output_rate;
+  size_t channel_count;
+  RubatoSincFixedIn resampler;
+  std::vector<std::vector<float>> input, output;
+  std::vector<float> pending;          // TempBuffer (utils/buffer.rs:499-610)
+  size_t pending_start = 0, pending_end = 0;
+  static constexpr size_t CHUNK_SIZE = 256;
+  RubatoResampler(uint32_t in_rate, uint32_t out_rate, size_t cc)
+      : input_rate(in_rate), output_rate(out_rate), channel_count(cc),
+        resampler((double)out_rate / (double)in_rate, 1.0, 256, 0.95f, 128, CHUNK_SIZE, cc) {
+    input.assign(cc, std::vector<float>(CHUNK_SIZE, 0.0f));                   // input_buffer_allocate(true)
+    output.assign(cc, std::vector<float>(resampler.output_frames_max(), 0.0f)); // output_buffer_allocate(true)
+    pending.assign(cc * resampler.output_frames_max(), 0.0f);
+  }
+  size_t required_input_buffer_size() const override { return CHUNK_SIZE * channel_count; }  // input_frames_next()
+  size_t max_input_buffer_size() const override { return CHUNK_SIZE * channel_count; }       // input_frames_max()
+  size_t pending_copy_to(float* out, size_t out_len) {
+    size_t n = std::min(out_len, pending_end - pending_start);
+    std::memcpy(out, pending.data() + pending_start, n * sizeof(float));
+    return n;
+  }
+  std::pair<size_t, size_t> process(const float* in, size_t in_len, float* out, size_t out_len) override {
+    if (input_rate == output_rate) {  // bypass (rubato.rs:73-78)
+      size_t m = std::min(in_len, out_len);
+      std::memcpy(out, in, m * sizeof(float));
+      return {m, m};
+    }
+    if (pending_start < pending_end) {  // flush pending outs (rubato.rs:81-86)
+      size_t w = pending_copy_to(out, out_len);
+      pending_start += w;
+      return {0, w};
+    }
+    if (in_len == 0) return {0, 0};
+    for (size_t c = 0; c < channel_count; ++c)
+      for (size_t f = 0; f < CHUNK_SIZE; ++f) input[c][f] = in[f * channel_count + c];
+    size_t frames = resampler.process_into_buffer(input, output);
+    size_t total = channel_count * frames;
+    if (total > out_len) {
+      pending_start = 0; pending_end = total;
+      for (size_t f = 0; f < frames; ++f)
+        for (size_t c = 0; c < channel_count; ++c) pending[f * channel_count + c] = output[c][f];
+      size_t w = pending_copy_to(out, out_len);
+      pending_start += w;
+      return {channel_count * CHUNK_SIZE, w};
+    }
+    for (size_t f = 0; f < frames; ++f)
+      for (size_t c = 0; c < channel_count; ++c) out[f * channel_count + c] = output[c][f];
+    return {channel_count * CHUNK_SIZE, total};
+  }
+  bool update(uint32_t in_rate, uint32_t out_rate) override {
+    input_rate = in_rate; output_rate = out_rate;
+    return resampler.set_resample_ratio((double)out_rate / (double)in_rate, false);
+  }
+  void reset() override { pending_start = 0; pending_end = 0; }  // rubato.rs:150-153: only the pending buffer
+};
+
 // f64 -> u32 `as` cast (saturating, NaN -> 0)
 inline uint32_t f64_as_u32(double v) {
   if (std::isnan(v)) return 0;

@@ -68,7 +68,10 @@ struct PreloadedFileSource : Source {
   std::shared_ptr<AudioFileBuffer> file_buffer;
   // FileSourceImpl
   VolumeFader volume_fader;
-  CubicResampler resampler;
+  std::unique_ptr<AudioResampler> resampler_box;  // Box<dyn AudioResampler> (file/common.rs:84-87)
+  AudioResampler& resampler;
+  std::vector<float> resampler_input_buffer;       // TempBuffer of max_input_buffer_size or 256 (common.rs:88-92)
+  bool hq;
   bool has_fade_out; Duration fade_out_duration;
   uint32_t output_sample_rate;
   size_t output_channel_count;
@@ -89,7 +92,10 @@ struct PreloadedFileSource : Source {
   PreloadedFileSource(std::shared_ptr<AudioFileBuffer> fb, const FilePlaybackOptions& o, uint32_t out_rate)
       : file_buffer(fb),
         volume_fader(fb->channel_count, out_rate),
-        resampler(fb->sample_rate, f64_as_u32((double)out_rate / o.speed), fb->channel_count),
+        resampler_box(make_resampler(o.resampling_quality, fb->sample_rate, f64_as_u32((double)out_rate / o.speed), fb->channel_count)),
+        resampler(*resampler_box),
+        resampler_input_buffer(resampler.max_input_buffer_size() ? resampler.max_input_buffer_size() : 256, 0.0f),
+        hq(o.resampling_quality != 0),
         has_fade_out(o.has_fade_out), fade_out_duration(o.fade_out),
         output_sample_rate(out_rate), output_channel_count(fb->channel_count),
         queue(std::make_shared<ArrayQueue<FileMsg>>(128)),
@@ -103,6 +109,10 @@ struct PreloadedFileSource : Source {
       loop_override_start = std::min<uint64_t>(o.loop_start, fc > 0 ? fc - 1 : 0);
       loop_override_end = std::min<uint64_t>(o.loop_end, fc);
     }
+  }
+  static std::unique_ptr<AudioResampler> make_resampler(uint32_t quality, uint32_t in_rate, uint32_t out_rate, size_t cc) {
+    if (quality != 0) return std::make_unique<RubatoResampler>(in_rate, out_rate, cc);  // ResamplingQuality::HighQuality
+    return std::make_unique<CubicAudioResampler>(in_rate, out_rate, cc);
   }
   uint32_t sample_rate() const override { return output_sample_rate; }
   size_t channel_count() const override { return output_channel_count; }
@@ -127,7 +137,9 @@ struct PreloadedFileSource : Source {
       current_speed = target_speed;
     }
     uint32_t new_rate = f64_as_u32((double)output_sample_rate / current_speed);
-    resampler.update(input_sample_rate, new_rate);
+    bool ok = resampler.update(input_sample_rate, new_rate);
+    assert(ok && "failed to update resampler specs");  // .expect() in the reference (common.rs:166-168)
+    (void)ok;
   }
   void seek(Duration position) {  // preloaded.rs:138-146
     if (!is_exhausted()) {
@@ -189,10 +201,21 @@ struct PreloadedFileSource : Source {
       size_t s, e;
       if (loop_range(s, e)) { ls = s * cc; le = e * cc; }
     }
+    const size_t required_input_len = resampler.required_input_buffer_size();
     while (written < len) {
       size_t remaining_in = le > playback_pos ? le - playback_pos : 0;
       const float* in = file_buffer->buffer.data() + playback_pos;
-      auto res = resampler.process(in, remaining_in, out + written, len - written);
+      std::pair<size_t, size_t> res;
+      if (remaining_in < required_input_len) {
+        // pad the input with zeros for fixed-size resamplers; the input counts as consumed whatever
+        // process() did with it (preloaded.rs:296-304)
+        std::copy(in, in + remaining_in, resampler_input_buffer.begin());
+        std::fill(resampler_input_buffer.begin() + remaining_in, resampler_input_buffer.end(), 0.0f);
+        auto r2 = resampler.process(resampler_input_buffer.data(), resampler_input_buffer.size(), out + written, len - written);
+        res = {remaining_in, r2.second};
+      } else {
+        res = resampler.process(in, remaining_in, out + written, len - written);
+      }
       playback_pos += res.first;
       written += res.second;
       if (playback_pos >= le) {

@@ -20,6 +20,7 @@ DURATION_NONE = 0xFFFFFFFFFFFFFFFF
 # pb200_error
 OK = 0
 ERR_SOURCE_NOT_PLAYING = 1
+ERR_RESAMPLING = 7
 ERR_GENERATOR_NOT_FOUND = 8
 ERR_EFFECT_NOT_FOUND = 9
 ERR_MIXER_NOT_FOUND = 10

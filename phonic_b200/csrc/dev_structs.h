@@ -64,9 +64,45 @@ struct VoiceState {
   uint8_t pos_eof, finished;   // playback_pos_eof, playback_finished
   uint8_t has_note, has_release, note;
   uint8_t stopped_exhausted;
-  uint8_t _pad[7];
+  uint8_t hq;                  // ResamplingQuality::HighQuality: 0 cubic, 1 rubato sinc, 2 rubato with equal rates (bypass)
+  uint8_t _pad[6];
 };
 static_assert(sizeof(VoiceState) % 8 == 0, "VoiceState must stay 8-byte aligned");
+
+// RubatoResampler + rubato::SincFixedIn state of one HighQuality file voice (src/utils/resampler/rubato.rs:12-56).
+// The resampler's input is a stream of 256-frame chunks cut from the sample buffer (zero padded at loop ends /
+// EOF, preloaded.rs:296-304); SincFixedIn keeps the last two chunks as history, so the open chunk's output is a
+// function of three (position, valid frames) pairs -- no sample has to be copied.
+constexpr uint32_t HQ_CHUNK = 256;     // RubatoResampler CHUNK_SIZE (rubato.rs:27) == sinc_len
+constexpr uint32_t HQ_FACTOR = 128;    // oversampling_factor (rubato.rs:31)
+constexpr uint32_t HQ_NONE = 0xFFFFFFFFu;
+struct HqState {
+  double idx0;          // SincFixedIn::last_index before the open chunk was processed
+  double last_index;    // ... after it
+  double t_ratio;       // 1 / resample_ratio
+  uint32_t src[3];      // first sample index of chunks k-2, k-1, k (k = open chunk)
+  uint16_t valid[3];    // valid frames of each; the rest of the 256 is zero padding
+  uint16_t _pad0;
+  uint32_t n_out;       // output frames of the open chunk
+  uint32_t pending;     // of those, not yet consumed (RubatoResampler::pending)
+  uint32_t slot;        // row of this voice in the per-block stream scratch
+  uint32_t table;       // sinc table index (one per cutoff)
+  uint32_t rec;         // this block's HqRec of the open chunk, HQ_NONE = not emitted yet
+  int32_t end_idx;      // chunk_size - (sinc_len + 1) - ceil(t_ratio)
+};
+
+// One piece of resampler output the sinc kernel has to materialise into the stream scratch of a time block.
+struct HqRec {
+  double idx0, t_ratio;
+  uint32_t src[3];
+  uint16_t valid[3];
+  uint16_t kind;        // 0 sinc, 1 copy (equal-rate bypass, zero padded)
+  uint32_t slot;
+  uint32_t out_off;     // block-relative frame the first materialised output lands on
+  uint32_t skip;        // outputs of the chunk consumed before `out_off` (earlier block)
+  uint32_t count;       // outputs to materialise
+  uint32_t buffer, table;
+};
 
 enum GroupKind : uint32_t { GROUP_SAMPLER = 0, GROUP_FILE = 1 };
 

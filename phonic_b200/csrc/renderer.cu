@@ -16,6 +16,7 @@
 
 #include "../../include/phonic_b200.h"
 #include "replay_kernel.cuh"
+#include "sinc_kernel.cuh"
 #include "mixer_kernel.cuh"
 #include "host_fx.h"
 
@@ -154,6 +155,11 @@ struct pb200_renderer {
 
   // host mirrors of device state
   std::vector<VoiceState> h_voices;
+  std::vector<HqState> h_hq;                // parallel to h_voices; only HighQuality voices use their entry
+  uint32_t n_hq = 0;                        // HighQuality voices (= rows of the stream scratch)
+  std::vector<uint32_t> sinc_table_keys;    // f32 bits of each table's cutoff
+  std::vector<float> sinc_tables;           // [n_tables][128][256]
+  bool sinc_tables_dirty = false;
   std::vector<GroupState> h_gstate;
   std::vector<MixerState> h_mstate;
   std::vector<FxHeader> h_fx;
@@ -166,6 +172,10 @@ struct pb200_renderer {
   // device arrays
   DevVec<DevBuffer> d_buffers;
   DevVec<VoiceState> d_voices;
+  DevVec<HqState> d_hq;
+  DevVec<float> d_sinc_tables, d_hq_scratch;
+  DevVec<HqRec> d_hq_recs;
+  DevVec<uint32_t> d_hq_nrecs;
   DevVec<GroupParams> d_groups;
   DevVec<GroupState> d_gstate;
   DevVec<DevEvent> d_events;
@@ -276,6 +286,7 @@ int sync_state_to_host(pb200_renderer* r) {
   r->h_fx.resize(r->dev_n_fx);
   r->h_fx_state.resize(r->dev_fx_state_bytes);
   CUDA_TRY(r->d_voices.download(r->h_voices, r->sm));
+  if (r->n_hq) { r->h_hq.resize(r->dev_n_voices); CUDA_TRY(r->d_hq.download(r->h_hq, r->sm)); }
   CUDA_TRY(r->d_gstate.download(r->h_gstate, r->sm));
   CUDA_TRY(r->d_mstate.download(r->h_mstate, r->sm));
   CUDA_TRY(r->d_fx.download(r->h_fx, r->sm));
@@ -286,6 +297,47 @@ int sync_state_to_host(pb200_renderer* r) {
   return PB200_OK;
 }
 
+
+// rubato ^0.16 make_sincs(256, 128, f_cutoff, BlackmanHarris2) in f32 (rubato src/sinc.rs, src/windows.rs; not
+// vendored with the reference -> PARITY UNPINNED): the filter table SincFixedIn::new builds for
+// phonic's RubatoResampler parameters (src/utils/resampler/rubato.rs:28-34). Returns the table index.
+uint32_t sinc_table_for(pb200_renderer* r, double resample_ratio) {
+  const float base_cutoff = 0.95f;
+  const float fc = resample_ratio >= 1.0 ? base_cutoff : base_cutoff * (float)resample_ratio;  // make_interpolator
+  uint32_t key;
+  std::memcpy(&key, &fc, 4);
+  for (size_t i = 0; i < r->sinc_table_keys.size(); ++i) if (r->sinc_table_keys[i] == key) return (uint32_t)i;
+  const size_t npoints = HQ_CHUNK, factor = HQ_FACTOR, tot = npoints * factor;
+  const float PI = 3.14159265358979323846264338327950288f;
+  const float pi2 = 2.0f * PI, pi4 = 4.0f * PI, pi6 = 6.0f * PI, np_f = (float)tot;
+  std::vector<float> y(tot);
+  float sum = 0.0f;
+  for (size_t x = 0; x < tot; ++x) {
+    const float xf = (float)x;
+    float w = 0.35875f - 0.48829f * std::cos(pi2 * xf / np_f) + 0.14128f * std::cos(pi4 * xf / np_f) - 0.01168f * std::cos(pi6 * xf / np_f);
+    w = w * w;  // BlackmanHarris2
+    const float v = (xf - (float)(tot / 2)) * fc / (float)factor;
+    const float sc = v == 0.0f ? 1.0f : std::sin(v * PI) / (v * PI);
+    const float val = w * sc;
+    sum += val;
+    y[x] = val;
+  }
+  sum /= (float)factor;
+  const size_t off = r->sinc_tables.size();
+  r->sinc_tables.resize(off + tot);
+  for (size_t p = 0; p < npoints; ++p)
+    for (size_t n = 0; n < factor; ++n) r->sinc_tables[off + (factor - n - 1) * npoints + p] = y[factor * p + n] / sum;
+  r->sinc_table_keys.push_back(key);
+  r->sinc_tables_dirty = true;
+  return (uint32_t)(r->sinc_table_keys.size() - 1);
+}
+
+HqState default_hq() {
+  HqState h;
+  std::memset(&h, 0, sizeof(h));
+  h.rec = HQ_NONE;
+  return h;
+}
 }  // namespace
 
 extern "C" {
@@ -497,7 +549,7 @@ int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_opti
   if (buffer_id >= r->buffers.size()) return fail(r, PB200_ERR_PARAMETER, "unknown buffer");
   if (int e = validate_vol_pan(r, o->volume, o->panning)) return e;
   if (o->speed < 0.0 || std::isnan(o->speed) || std::isinf(o->speed)) return fail(r, PB200_ERR_PARAMETER, "playback options 'speed' value is invalid");
-  if (o->resampling_quality != 0) return fail(r, PB200_ERR_UNSUPPORTED, "HighQuality (sinc) resampling is not rendered on device yet");
+  if (o->resampling_quality > 1) return fail(r, PB200_ERR_PARAMETER, "unknown resampling quality");
   auto mit = r->mixer_by_id.find(o->target_mixer);
   if (mit == r->mixer_by_id.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
   if (int e = sync_state_to_host(r)) return e;
@@ -532,6 +584,23 @@ int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_opti
   v.vol = ExpSm{o->volume, o->volume};
   v.pan = ExpSm{o->panning, o->panning};
   v.has_note = 1;  // a file playback is one always-active voice
+  HqState hq = default_hq();
+  if (o->resampling_quality == 1) {
+    // RubatoResampler::new (rubato.rs:22-56) on the specs of FileSourceImpl::new (file/common.rs:78-87)
+    const uint32_t rate = f64_as_u32_h((double)sr / o->speed);
+    if (rate == 0) return fail(r, PB200_ERR_RESAMPLING, "Invalid resampling ratio");
+    const double ratio = (double)rate / (double)b.sample_rate;
+    if (!(ratio >= 1.0 / 16.0 && ratio <= 64.0)) return fail(r, PB200_ERR_UNSUPPORTED, "HighQuality resampling ratio outside [1/16, 64]");
+    v.hq = rate == b.sample_rate ? 2 : 1;
+    hq.t_ratio = 1.0 / ratio;
+    hq.last_index = -(double)(HQ_CHUNK / 2);
+    hq.idx0 = hq.last_index;
+    hq.end_idx = (int32_t)HQ_CHUNK - ((int32_t)HQ_CHUNK + 1) - (int32_t)std::ceil(hq.t_ratio);
+    hq.slot = r->n_hq++;
+    hq.table = v.hq == 1 ? sinc_table_for(r, ratio) : 0u;
+  }
+  r->h_hq.resize(r->h_voices.size(), default_hq());
+  r->h_hq.push_back(hq);
   r->h_voices.push_back(v);
   GroupState gs;
   std::memset(&gs, 0, sizeof(gs));
@@ -580,6 +649,7 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
   g.gp.base_volume = 1.0f; g.gp.base_panning = 0.0f;
   if (o->has_ahdsr && !resolve_ahdsr(o->ahdsr, sr, g.gp)) return fail(r, PB200_ERR_PARAMETER, "Invalid AHDSR parameters");
   for (uint32_t i = 0; i < o->voices; ++i) r->h_voices.push_back(default_voice(b, sr, 1.0));
+  r->h_hq.resize(r->h_voices.size(), default_hq());
   GroupState gs;
   std::memset(&gs, 0, sizeof(gs));
   gs.vol = ExpSm{o->volume, o->volume};
@@ -640,6 +710,18 @@ int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
     case PB200_EV_SET_SOURCE_PANNING: de.kind = EVK_SET_PANNING; de.value = ev->value; break;
     case PB200_EV_SET_SOURCE_SPEED:
       if (is_sampler) return fail(r, PB200_ERR_PARAMETER, "set_speed needs a file source");
+      {
+        // HighQuality: rubato runs with max_resample_ratio_relative = 1.0 (rubato.rs:37); any other output rate fails
+        // set_resample_ratio and FileSourceImpl::update_speed `expect`-panics (file/common.rs:166-168)
+        if (int e = sync_state_to_host(r)) return e;
+        const VoiceState& fv = r->h_voices[g.gp.first_voice];
+        if (fv.hq) {
+          const uint32_t new_rate = f64_as_u32_h((double)r->cfg.sample_rate / ev->speed);
+          const double t_new = 1.0 / ((double)new_rate / (double)b.sample_rate);
+          if (ev->glide > 0.0f || new_rate == 0 || t_new != r->h_hq[g.gp.first_voice].t_ratio)
+            return fail(r, PB200_ERR_RESAMPLING, "HighQuality file sources cannot change speed");
+        }
+      }
       de.kind = EVK_SET_SPEED; de.speed = ev->speed;
       break;
     case PB200_EV_SEEK_SOURCE: {
@@ -799,6 +881,11 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
   CUDA_TRY(r->d_fx_events.upload(fx_events, s));
   // state
   CUDA_TRY(r->d_voices.upload(r->h_voices, s));
+  if (r->n_hq) {
+    r->h_hq.resize(r->h_voices.size(), default_hq());
+    CUDA_TRY(r->d_hq.upload(r->h_hq, s));
+    if (r->sinc_tables_dirty) { CUDA_TRY(r->d_sinc_tables.upload(r->sinc_tables, s)); r->sinc_tables_dirty = false; }
+  }
   CUDA_TRY(r->d_gstate.upload(r->h_gstate, s));
   CUDA_TRY(r->d_mstate.upload(r->h_mstate, s));
   CUDA_TRY(r->d_fx.upload(r->h_fx, s));
@@ -930,6 +1017,29 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(r->d_gseg_first.reserve(std::max<size_t>(1, (size_t)RING * ng * n_tiles)));
   CUDA_TRY(r->d_gseg_count.reserve(std::max<size_t>(1, (size_t)RING * ng * n_tiles)));
 
+  // HighQuality voices: per-block record list + resampler output stream scratch (hq.cuh, sinc_kernel.cuh)
+  const uint32_t n_hq = r->n_hq;
+  uint32_t hq_cap = 0;
+  int sm_count = 148;
+  if (n_hq) {
+    size_t cap = 0;
+    for (size_t vi = 0; vi < r->h_voices.size(); ++vi) {
+      if (!r->h_voices[vi].hq) continue;
+      // a chunk yields ~256 * ratio frames (>= 1 per process() call on the bypass path), plus one record per
+      // write call that re-opens a chunk and per block boundary
+      const double per = r->h_voices[vi].hq == 1 ? std::max(1.0, std::floor(256.0 / r->h_hq[vi].t_ratio) - 2.0) : 1.0;
+      cap += (size_t)((double)tb / per) + 2 * (size_t)max_chunks + 8;
+    }
+    if (cap >= 0x7FFFFFFFull) return fail(r, PB200_ERR_UNSUPPORTED, "too many HighQuality chunks in one time block");
+    hq_cap = (uint32_t)cap;
+    CUDA_TRY(r->d_hq_recs.reserve((size_t)RING * hq_cap));
+    CUDA_TRY(r->d_hq_nrecs.reserve(std::max<size_t>(RING, (size_t)n_blocks)));
+    CUDA_TRY(r->d_hq_scratch.reserve((size_t)RING * n_hq * tb * 2));
+    CUDA_TRY(cudaMemsetAsync(r->d_hq_nrecs.p, 0, std::max<size_t>(RING, (size_t)n_blocks) * sizeof(uint32_t), r->sv));
+    CUDA_TRY(cudaFuncSetAttribute(sinc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SINC_SMEM));
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, r->device);
+  }
+
   std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r1(n_blocks), ev_m1(n_blocks);
   for (uint32_t b = 0; b < n_blocks; ++b) {
     CUDA_TRY(DevicePool::get().event(&ev_v0[b])); CUDA_TRY(DevicePool::get().event(&ev_v1[b]));
@@ -966,6 +1076,10 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     va.gseg_first = r->d_gseg_first.p + (size_t)slot * ng * n_tiles;
     va.gseg_count = r->d_gseg_count.p + (size_t)slot * ng * n_tiles;
     va.seg_cap = seg_cap; va.n_tiles = n_tiles;
+    va.hq_states = n_hq ? r->d_hq.p : nullptr;
+    va.hq_recs = n_hq ? r->d_hq_recs.p + (size_t)slot * hq_cap : nullptr;
+    va.hq_n_recs = n_hq ? r->d_hq_nrecs.p + b : nullptr;   // one counter per block: read back after the render
+    va.hq_cap = hq_cap;
     va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
     for (size_t ci = 0; ci < c.classes.size(); ++ci) {
       const SizeClass& sc = c.classes[ci];
@@ -987,6 +1101,19 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ra.gsegs = va.gsegs; ra.gseg_first = va.gseg_first; ra.gseg_count = va.gseg_count;
     ra.group_bus = r->d_group_bus.p + (size_t)slot * ng * tb * 2;
     ra.seg_cap = seg_cap; ra.n_tiles = n_tiles; ra.block_frames = tb; ra.rc = r->rc;
+    ra.hq_states = va.hq_states;
+    ra.hq_scratch = n_hq ? r->d_hq_scratch.p + (size_t)slot * n_hq * tb * 2 : nullptr;
+    if (n_hq) {  // materialise the resampler output this block consumes: one launch per filter table
+      SincArgs sa;
+      sa.recs = va.hq_recs; sa.n_recs = va.hq_n_recs; sa.cap = hq_cap; sa.buffers = r->d_buffers.p;
+      sa.tables = r->d_sinc_tables.p; sa.scratch = r->d_hq_scratch.p + (size_t)slot * n_hq * tb * 2; sa.block_frames = tb;
+      const uint32_t n_tables = std::max<uint32_t>(1, (uint32_t)r->sinc_table_keys.size());
+      for (uint32_t t = 0; t < n_tables; ++t) {
+        sa.table = t; sa.do_copies = t == 0;
+        sinc_kernel<<<sm_count, SINC_THREADS, SINC_SMEM, r->sr_>>>(sa);
+        ++launches;
+      }
+    }
     const uint32_t live_tiles = (blen + TILE - 1) / TILE;
     for (size_t ci = 0; ci < c.classes.size(); ++ci) {
       const SizeClass& sc = c.classes[ci];
@@ -1039,6 +1166,12 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   }
   DevicePool::get().release_event(ev_start); DevicePool::get().release_event(ev_end);
   r->stats.kernel_launches = launches;
+  if (n_hq) {
+    std::vector<uint32_t> counts(n_blocks);
+    CUDA_TRY(cudaMemcpy(counts.data(), r->d_hq_nrecs.p, n_blocks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t c2 : counts)
+      if (c2 > hq_cap) return fail(r, PB200_ERR_CUDA, "HighQuality chunk record list overflowed");
+  }
   r->host_state_valid = false;
   r->position = p1;
   // statistics + event cursors come back with the (small) group state

@@ -30,19 +30,23 @@ struct ReplayArgs {
   uint32_t vpad;          // voices per tile rounded up to a power of two
   uint32_t tpc;           // tiles per CTA
   RenderConsts rc;
+  const float* hq_scratch;      // [n_hq][block_frames][2]: resampler output stream of HighQuality voices (sinc_kernel.cuh)
+  const HqState* hq_states;     // [n_voices] (only `slot` is read here)
 };
 
 template <int CC>
 PB_DEV void replay_voice_subtile(VoiceState& v, CallCtx& cc, HistVals& hv, const Segment* __restrict__ segs, uint32_t& seg_i,
                                  uint32_t seg_end_i, uint32_t& seg_pos, uint32_t& seg_stop, bool& have, const GroupParams& gp,
-                                 const DevBuffer& buf, const RenderConsts& rc, uint32_t sub_lo, uint32_t sub_hi, float* row) {
+                                 const DevBuffer& buf, const RenderConsts& rc, uint32_t sub_lo, uint32_t sub_hi, float* row,
+                                 const float* __restrict__ hq_row) {
   // sub_lo/sub_hi: frame range of this sub-tile relative to the block
   while (have && seg_pos < sub_hi) {
     const uint32_t lo = max(seg_pos, sub_lo);
     const uint32_t hi = min(seg_stop, sub_hi);
     uint32_t wrote = 0;
     if (hi > lo) {
-      wrote = voice_frames<CC, true>(v, cc, hv, gp, buf, rc.sample_rate, rc.rate_comp, hi - lo, row + (lo - sub_lo) * 2);
+      if (v.hq) wrote = hq_replay_frames(v, cc, hq_row, rc.rate_comp, hi - lo, row + (lo - sub_lo) * 2);
+      else wrote = voice_frames<CC, true>(v, cc, hv, gp, buf, rc.sample_rate, rc.rate_comp, hi - lo, row + (lo - sub_lo) * 2);
       seg_pos = lo + wrote;
     }
     if (seg_pos >= seg_stop || wrote < hi - lo) {  // segment done (or the source ran dry): next snapshot
@@ -108,8 +112,10 @@ __global__ void __launch_bounds__(MAXT, MINB) replay_kernel(ReplayArgs a) {
   uint32_t seg_i = 0, seg_end_i = 0, seg_pos = 0, seg_stop = 0;
   bool have = false;
   const Segment* segs = nullptr;
+  const float* hq_row = nullptr;
   if (active_thread) {
     const size_t vidx = gp.first_voice + vi;
+    if (a.hq_states) hq_row = a.hq_scratch + (size_t)a.hq_states[vidx].slot * a.block_frames * 2;
     const uint32_t cnt = a.seg_count[vidx * a.n_tiles + tile];
     const uint32_t first = cnt ? a.seg_first[vidx * a.n_tiles + tile] : 0u;
     segs = a.segs + vidx * a.seg_cap;
@@ -141,9 +147,9 @@ __global__ void __launch_bounds__(MAXT, MINB) replay_kernel(ReplayArgs a) {
     if (have) {
       const uint32_t sub_lo = tile * TILE + st * SUB, sub_hi = sub_lo + SUB;
       if (buf.channels == 2)
-        replay_voice_subtile<2>(v, cc, hv, segs, seg_i, seg_end_i, seg_pos, seg_stop, have, gp, buf, a.rc, sub_lo, sub_hi, my_row);
+        replay_voice_subtile<2>(v, cc, hv, segs, seg_i, seg_end_i, seg_pos, seg_stop, have, gp, buf, a.rc, sub_lo, sub_hi, my_row, hq_row);
       else
-        replay_voice_subtile<1>(v, cc, hv, segs, seg_i, seg_end_i, seg_pos, seg_stop, have, gp, buf, a.rc, sub_lo, sub_hi, my_row);
+        replay_voice_subtile<1>(v, cc, hv, segs, seg_i, seg_end_i, seg_pos, seg_stop, have, gp, buf, a.rc, sub_lo, sub_hi, my_row, hq_row);
     }
     __syncthreads();
     // ordered reduction over the voices of each tile, generator-level gain/pan, coalesced store

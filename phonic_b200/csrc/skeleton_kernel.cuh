@@ -9,7 +9,7 @@
 // This is the serial part the reference's f32 recurrences force; everything per-sample
 // that can be replayed from a checkpoint is left to pass 2.
 #pragma once
-#include "voice.cuh"
+#include "hq.cuh"
 
 namespace pb {
 
@@ -40,6 +40,11 @@ struct SkeletonArgs {
   uint32_t gen;                       // generation tag of this launch's records
   uint32_t seg_cap;
   uint32_t n_tiles;
+  // HighQuality (rubato sinc) file voices: resampler state per voice + this block's record list (hq.cuh)
+  HqState* hq_states;                 // [n_voices] or nullptr when the graph has no HighQuality source
+  HqRec* hq_recs;
+  uint32_t* hq_n_recs;
+  uint32_t hq_cap;
   uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores, 2 = no simple calls
 };
 
@@ -185,6 +190,11 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
 
   // per-voice / per-group segment tables of this block
   const uint32_t vidx = gp.first_voice + tid;
+  const bool is_hq = mine && v.hq != 0;
+  HqState* const hqp = is_hq ? a.hq_states + vidx : nullptr;
+  HqEmit hq_em;
+  hq_em.recs = a.hq_recs; hq_em.n_recs = a.hq_n_recs; hq_em.cap = a.hq_cap; hq_em.buffer = gp.buffer;
+  if (is_hq) hqp->rec = HQ_NONE;  // records are per time block
   Segment* my_segs = a.segs + (size_t)vidx * a.seg_cap;
   uint16_t* my_first = a.seg_first + (size_t)vidx * a.n_tiles;
   uint16_t* my_count = a.seg_count + (size_t)vidx * a.n_tiles;
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) -> uint32_t {
     uint32_t written_frames = 0;
     bool simple = false;
-    if (n_segs < a.seg_cap && !(a.debug_flags & 2u))
+    if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq)
       simple = buf.channels == 2 ? simple_call_ok<2>(v, cc, buf, n) : simple_call_ok<1>(v, cc, buf, n);
     if (simple) {
       const uint32_t tile = call_off / TILE;
@@ -256,7 +266,8 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
           n_segs++;
         }
         uint32_t w;
-        if (buf.channels == 2) w = voice_advance<2>(v, cc, gp, buf, out_rate, comp, seg_len);
+        if (is_hq) w = buf.channels == 2 ? hq_advance<2>(v, cc, hqp, hq_em, buf, comp, seg_len) : hq_advance<1>(v, cc, hqp, hq_em, buf, comp, seg_len);
+        else if (buf.channels == 2) w = voice_advance<2>(v, cc, gp, buf, out_rate, comp, seg_len);
         else w = voice_advance<1>(v, cc, gp, buf, out_rate, comp, seg_len);
         written_frames += w;
         off += w; remaining -= w;
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
               const uint32_t rlen = (uint32_t)(bound(k + j + 1) - r0);
               CallCtx cc;
               cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
-              if (voice_begin_call(v, cc, gp, buf, rlen, comp, gp.has_env != 0)) run_call(cc, rlen, (uint32_t)(r0 - a.block_start), r0);
+              if (voice_begin_call(v, cc, gp, buf, rlen, comp, gp.has_env != 0, (uint32_t)(r0 - a.block_start))) run_call(cc, rlen, (uint32_t)(r0 - a.block_start), r0);
               // SamplerVoice::process epilogue (voice.rs:488-502)
               if (v.finished || (gp.has_env && v.env_stage == ENV_IDLE)) voice_reset(v);
               if (v.has_note) atomicAdd(&s_cnt[j], 1u);
@@ -446,7 +457,10 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
         } else if (mine) {  // file playback: FilePlaybackMessage / Amplified / Panned messages
           if (ev.kind == EVK_STOP) file_stop(v, gp);
           else if (ev.kind == EVK_SET_SPEED) file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate);
-          else if (ev.kind == EVK_SEEK) file_seek(v, ev.seek_pos);
+          else if (ev.kind == EVK_SEEK) {
+            if (is_hq && !v.finished) hq_reset_pending(*hqp, hq_em, boff + total);
+            file_seek(v, ev.seek_pos);
+          }
           else if (ev.kind == EVK_SET_VOLUME) exp_set_target(v.vol, ev.value, comp);
           else if (ev.kind == EVK_SET_PANNING) exp_set_target(v.pan, ev.value, comp);
         }
@@ -471,11 +485,11 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
       CallCtx cc;
       cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
       bool call_open = false;
-      if (group_writes && was_active) call_open = voice_begin_call(v, cc, gp, buf, n, comp, gp.has_env != 0);
+      const uint32_t call_off = boff + total;  // first frame of the call, relative to the block
+      if (group_writes && was_active) call_open = voice_begin_call(v, cc, gp, buf, n, comp, gp.has_env != 0, call_off);
       __syncthreads();
 
       // 3. advance the voice through the call, one segment per (call x 64-frame tile)
-      const uint32_t call_off = boff + total;  // first frame of the call, relative to the block
       uint32_t written_frames = 0;
       if (call_open) written_frames = run_call(cc, n, call_off, t);
       if (is_sampler && group_writes && tid == 0) group_call(n, call_off);

@@ -229,6 +229,7 @@ struct CallCtx {
   uint32_t call_left;        // frames left in the current write_buffer call (glide sub-chunk)
   uint32_t produced_in_call; // output of the current resampler.process call
   uint32_t ls, le;           // active loop range / buffer range in samples
+  uint32_t hq_off;           // block-relative frame of the next output (HighQuality voices read the stream scratch there)
   bool new_call;             // a new resampler.process call starts at the next frame
   bool gliding;              // write() took the pitch-slide arm (preloaded.rs:419)
   bool ended;                // write_buffer broke out (EOF) -> no more frames in this call
@@ -250,8 +251,9 @@ PB_DEV void loop_range_samples(const VoiceState& v, const DevBuffer& b, uint32_t
 // Start of PreloadedFileSource::write + the wrappers' per-call decisions. Returns false when the
 // source is finished (write returns 0).
 PB_DEV bool voice_begin_call(VoiceState& v, CallCtx& c, const GroupParams& gp, const DevBuffer& b, uint32_t n_frames,
-                             float comp, bool with_env) {
+                             float comp, bool with_env, uint32_t call_off) {
   c.chunk_left = n_frames;
+  c.hq_off = call_off;
   c.call_left = 0;
   c.produced_in_call = 0;
   c.new_call = true;
@@ -576,6 +578,39 @@ PB_DEV void env_chain(VoiceState& v, const GroupParams& gp, const uint32_t w) {
   }
 }
 
+// The fader / gain / pan recurrences of `w` frames, state only (fader.rs:109-116, smoothing.rs:61-64,74-122)
+PB_DEV void advance_ramps(VoiceState& v, const CallCtx& c, const uint32_t w, const float comp) {
+  // (2) VolumeFader ramp (fader.rs:109-116)
+  if (c.fader_running) {
+    float cur = v.fader_cur;
+    const float tgt = v.fader_tgt, inertia = v.fader_inertia;
+    for (uint32_t i = 0; i < w; ++i) cur += (tgt - cur) * inertia;
+    v.fader_cur = cur;
+  }
+  // (3) gain ramp, two steps per frame (smoothing.rs:61-64); once it stops needing a ramp it stays put
+  if (c.vol_ramp) {
+    float cur = v.vol.current;
+    const float tgt = v.vol.target;
+    for (uint32_t i = 0; i < 2 * w; ++i) {
+      const float add = (tgt - cur) * SMOOTH_INERTIA * comp;
+      if (!(fabsf(add) > F32_EPS * 100.0f)) break;
+      cur += add;
+    }
+    v.vol.current = cur;
+  }
+  // (4) pan ramp, one step per frame
+  if (c.pan_ramp) {
+    float cur = v.pan.current;
+    const float tgt = v.pan.target;
+    for (uint32_t i = 0; i < w; ++i) {
+      const float add = (tgt - cur) * SMOOTH_INERTIA * comp;
+      if (!(fabsf(add) > F32_EPS * 100.0f)) break;
+      cur += add;
+    }
+    v.pan.current = cur;
+  }
+}
+
 // ---- skeleton fast path -------------------------------------------------------------------------------------
 // State-only advance of one write call by up to `n` frames, bit-identical to voice_frames<CC,false> but with
 // the independent recurrences separated into tight loops: (1) the resampler's f32 phase/position
@@ -650,35 +685,7 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
       c.chunk_left = t.chunk_left; c.call_left = t.call_left; c.produced_in_call = t.produced_in_call;
       c.ls = t.ls; c.le = t.le; c.new_call = t.new_call; c.ended = t.ended;
     }
-    // (2) VolumeFader ramp (fader.rs:109-116)
-    if (c.fader_running) {
-      float cur = v.fader_cur;
-      const float tgt = v.fader_tgt, inertia = v.fader_inertia;
-      for (uint32_t i = 0; i < w; ++i) cur += (tgt - cur) * inertia;
-      v.fader_cur = cur;
-    }
-    // (3) gain ramp, two steps per frame (smoothing.rs:61-64); once it stops needing a ramp it stays put
-    if (c.vol_ramp) {
-      float cur = v.vol.current;
-      const float tgt = v.vol.target;
-      for (uint32_t i = 0; i < 2 * w; ++i) {
-        const float add = (tgt - cur) * SMOOTH_INERTIA * comp;
-        if (!(fabsf(add) > F32_EPS * 100.0f)) break;
-        cur += add;
-      }
-      v.vol.current = cur;
-    }
-    // (4) pan ramp, one step per frame
-    if (c.pan_ramp) {
-      float cur = v.pan.current;
-      const float tgt = v.pan.target;
-      for (uint32_t i = 0; i < w; ++i) {
-        const float add = (tgt - cur) * SMOOTH_INERTIA * comp;
-        if (!(fabsf(add) > F32_EPS * 100.0f)) break;
-        cur += add;
-      }
-      v.pan.current = cur;
-    }
+    advance_ramps(v, c, w, comp);
     // (5) AHDSR (ahdsr.rs:448-516); Sustain and Idle do not move
     if (gp.has_env && c.env_per_frame) env_chain(v, gp, w);
     done += w;

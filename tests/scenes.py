@@ -49,6 +49,51 @@ def file_bypass_and_immediate(p: Player):
     return {"h": p.play_file_source(b, FilePlaybackOptions(fade_out=0.01)), "frames": 60 * BLOCK}
 
 
+def hq_mono_to_eof(p: Player):
+    """HighQuality (rubato sinc) 44.1 -> 48 kHz, mono, plays through EOF: zero-padded tail chunks"""
+    b = p.upload_buffer(tone(30000, 44100, seed=21), 44100)
+    return {"h": p.play_file_source(b, FilePlaybackOptions(resampling_quality=1)), "frames": 40 * BLOCK}
+
+
+def hq_stereo_down_loop(p: Player):
+    """HighQuality stereo at speed 1.37 (down-sampling: cutoff scaled by the ratio), loop range x2 (zero padding
+    at every loop end), fade-in, volume/pan options, late start"""
+    b = p.upload_buffer(tone(20000, 48000, channels=2, seed=22), 48000)
+    o = FilePlaybackOptions(volume=0.7, panning=-0.3, speed=1.37, repeat=2, loop_range=(4000, 9000), fade_in=0.02,
+                            resampling_quality=1)
+    return {"h": p.play_file_source(b, o, start_time=1500), "frames": 40 * BLOCK}
+
+
+def hq_events(p: Player):
+    """HighQuality with seek (drops pending output only), volume/pan ramps, same-speed set_speed, scheduled stop"""
+    b = p.upload_buffer(tone(60000, 44100, seed=23), 44100, loop_range=(10000, 50000))
+    h = p.play_file_source(b, FilePlaybackOptions(volume=0.9, resampling_quality=1))
+    h.set_volume(0.4, 3000)
+    h.set_panning(0.6, 3000)
+    h.seek(0.25, 20000)
+    h.set_speed(1.0, None, 25000)
+    h.seek(0.9, 33333)
+    h.set_panning(-1.0, 41000)
+    h.stop(60000)
+    return {"h": h, "frames": 70 * BLOCK}
+
+
+def hq_equal_rates(p: Player):
+    """HighQuality with equal rates: rubato bypass copy, still in 256-frame padded chunks at the loop end"""
+    b = p.upload_buffer(tone(9000, 48000, channels=2, seed=24), 48000)
+    o = FilePlaybackOptions(repeat=3, loop_range=(1000, 7268), resampling_quality=1)
+    return {"h": p.play_file_source(b, o), "frames": 36 * BLOCK}
+
+
+def hq_up_2x(p: Player):
+    """HighQuality at speed 0.5 (2x up-sampling: > 512 frames per chunk) with another HighQuality voice beside it"""
+    b = p.upload_buffer(tone(12000, 48000, seed=25), 48000)
+    b2 = p.upload_buffer(tone(15000, 32000, channels=2, seed=26), 32000)
+    h = p.play_file_source(b, FilePlaybackOptions(speed=0.5, volume=0.6, resampling_quality=1))
+    p.play_file_source(b2, FilePlaybackOptions(volume=0.5, resampling_quality=1), start_time=777)
+    return {"h": h, "frames": 36 * BLOCK}
+
+
 def sampler_notes(p: Player):
     """8-voice sampler with AHDSR: more notes than voices (stealing), note-offs, glides, per-note vol/pan"""
     b = p.upload_buffer(tone(44100 * 2, 44100, seed=7), 44100, loop_range=(2000, 80000))
@@ -145,6 +190,11 @@ SCENES = {
     "file_stereo_fast_loop": file_stereo_fast_loop,
     "file_events": file_events,
     "file_bypass": file_bypass_and_immediate,
+    "hq_mono_to_eof": hq_mono_to_eof,
+    "hq_stereo_down_loop": hq_stereo_down_loop,
+    "hq_events": hq_events,
+    "hq_equal_rates": hq_equal_rates,
+    "hq_up_2x": hq_up_2x,
     "sampler_notes": sampler_notes,
     "sampler_no_envelope": sampler_no_envelope,
     "cfg2_small": cfg2_small,
@@ -163,7 +213,7 @@ SCENES = {
 
 # scenes whose whole path is +,-,*,/,sqrt in the reference's order: must be bit-exact on device
 BIT_EXACT = {"file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
-             "sampler_no_envelope"}
+             "sampler_no_envelope", "hq_equal_rates"}
 # bit-exact voice path + time-invariant biquads evaluated by the f64 block scan (exact up to O(1e-16)
 # relative reassociation error before the f32 cast): at most a rare last-bit flip
 NEAR_EXACT = {"cfg2_small", "fx_filter"}

@@ -50,6 +50,14 @@ def test_scene_matches_oracle(cuda_api, oracle_api, name):
     elif name in ("fx_delay", "fx_reverb", "submixers_cfg5_small"):
         rms = float(np.sqrt(np.mean((gpu - ref) ** 2)))
         assert dbfs(rms) < -90.0 and dbfs(err) < -80.0, f"{name}: error floor {dbfs(rms):.1f} dBFS rms, {dbfs(err):.1f} peak"
+    elif name.startswith("hq_"):
+        # rubato sinc FIR (north_star: 1e-5 max abs for resampling stages); the device sums the 256 taps in another
+        # order with FMA, and places idx in closed form (sinc_kernel.cuh)
+        assert err <= 1e-5, f"{name}: max abs err {err:.3e}"
+        # the frame where the source falls silent is an integer property: bit-exact
+        nz_g = np.flatnonzero(np.abs(gpu).max(axis=1) > 0)
+        nz_r = np.flatnonzero(np.abs(ref).max(axis=1) > 0)
+        assert (nz_g[0], nz_g[-1]) == (nz_r[0], nz_r[-1])
     else:
         assert err <= 1e-5, f"{name}: max abs err {err:.3e}"
     # integer state: bit-exact everywhere
@@ -66,7 +74,7 @@ def test_scene_matches_oracle(cuda_api, oracle_api, name):
             assert (sa.playback_pos, sa.end_frame) == (sb.playback_pos, sb.end_frame)
 
 
-@pytest.mark.parametrize("name", ["file_events", "sampler_notes", "nested_and_gated", "fx_reverb"])
+@pytest.mark.parametrize("name", ["file_events", "sampler_notes", "nested_and_gated", "fx_reverb", "hq_events", "hq_up_2x"])
 def test_split_render_calls_equal_single_call(cuda_api, name):
     _, _, one = render(cuda_api, name, calls=1)
     _, _, many = render(cuda_api, name, calls=5)
@@ -113,6 +121,32 @@ def test_error_codes_mirror_reference(cuda_api):
     assert e.value.code == A.ERR_PARAMETER
     with pytest.raises(PhonicError):
         p.render(1000)  # not a multiple of the 1024-frame WavStream block
+
+
+def test_high_quality_sources_cannot_change_speed(cuda_api, oracle_api):
+    """rubato runs with max_resample_ratio_relative = 1.0 (rubato.rs:37): Error::ResamplingError in both."""
+    from phonic_b200 import PhonicError
+    from phonic_b200 import _capi as A
+    from phonic_b200.player import FilePlaybackOptions
+    for api in (cuda_api, oracle_api):
+        p = Player(api, SR)
+        b = p.upload_buffer(np.zeros(4096, np.float32), 44100)
+        h = p.play_file_source(b, FilePlaybackOptions(resampling_quality=1))
+        with pytest.raises(PhonicError) as e:
+            h.set_speed(1.5, None, 1000)
+        assert e.value.code == A.ERR_RESAMPLING
+        h.set_speed(1.0, None, 1000)  # same output rate: accepted
+
+
+def test_small_time_blocks_split_high_quality_chunks(cuda_api):
+    """A chunk's output straddling a time-block boundary is re-materialised in the next block (skip > 0)."""
+    _, _, one = render(cuda_api, "hq_events")
+    os.environ["PB200_TIME_BLOCK"] = "1024"
+    try:
+        _, _, small = render(cuda_api, "hq_events")
+    finally:
+        del os.environ["PB200_TIME_BLOCK"]
+    assert np.array_equal(one, small)
 
 
 def test_empty_player_renders_nothing(cuda_api, oracle_api):
