@@ -174,6 +174,23 @@ typedef struct pb200_ahdsr { /* AhdsrParameters::new_with_scaling (src/utils/ahd
   float sustain_level;
 } pb200_ahdsr;
 
+/* GranularParameters (src/generator/sampler/granular.rs:239-331); Sampler::with_granular_playback
+ * (src/generator/sampler.rs:599-637). Every GrainPool seeds its SmallRng from the OS (granular.rs:413), so
+ * settings that let a random draw reach the audio -- variation, spray, pan_spread > 0, Random direction --
+ * are not reproducible in the reference itself and are rejected with PB200_ERR_UNSUPPORTED. */
+typedef struct pb200_granular_params {
+  uint32_t overlap_mode;       /* GrainOverlapMode: 0 Cloud 1 Sequential */
+  uint32_t window;             /* GrainWindowMode: 0 Hann 1 Blackman 2 Triangle 3 Tukey 4 Trapezoid 5 Exponential 6 RampUp 7 RampDown */
+  float size;                  /* ms, 1..1000 (default 100) */
+  float density;               /* Hz, 1..100 (default 10) */
+  float variation;             /* must be 0 */
+  float spray;                 /* must be 0 */
+  float pan_spread;            /* must be 0 */
+  uint32_t playback_direction; /* GrainPlaybackDirection: 0 Forward 1 Backward (2 Random: unsupported) */
+  float position;              /* 0..1 (default 0.5) */
+  float step;                  /* -4..4 (default 0) */
+} pb200_granular_params;
+
 typedef struct pb200_sampler_options { /* GeneratorPlaybackOptions (src/generator.rs:41-72) */
   float volume;          /* 1.0 */
   float panning;         /* 0.0 */
@@ -182,6 +199,9 @@ typedef struct pb200_sampler_options { /* GeneratorPlaybackOptions (src/generato
   uint32_t transient;    /* 1: play_generator, 0: add_generator */
   uint32_t has_ahdsr;    /* with_ahdsr(..) */
   pb200_ahdsr ahdsr;
+  uint32_t has_granular; /* with_granular_playback(..) */
+  pb200_granular_params granular;
+  uint32_t reserved;
 } pb200_sampler_options;
 
 PB200_API void pb200_sampler_options_default(pb200_sampler_options *o);

@@ -252,6 +252,16 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
       return fail(r, PB200_ERR_PARAMETER, "Invalid AHDSR parameters");
     if (!sampler->with_ahdsr(p)) return fail(r, PB200_ERR_PARAMETER, "Failed to initialize AHDSR parameters");
   }
+  if (o->has_granular) {
+    const auto& g = o->granular;
+    if (g.overlap_mode > 1 || g.window >= GW_COUNT || g.playback_direction > 2) return fail(r, PB200_ERR_PARAMETER, "Invalid granular parameters");
+    if (g.variation != 0.0f || g.spray != 0.0f || g.pan_spread != 0.0f || g.playback_direction == 2)
+      return fail(r, PB200_ERR_UNSUPPORTED, "OS-seeded grain randomisation is not reproducible");
+    GranularParameters gp;
+    gp.overlap_mode = (GrainOverlapMode)g.overlap_mode; gp.window = g.window; gp.size = g.size; gp.density = g.density;
+    gp.playback_direction = (GrainPlaybackDirection)g.playback_direction; gp.position = g.position; gp.step = g.step;
+    if (!sampler->with_granular_playback(gp)) return fail(r, PB200_ERR_PARAMETER, "Invalid granular parameters");
+  }
   sampler->transient = o->transient != 0;  // set_is_transient (player.rs:1062)
   pb200_renderer::SourceRef ref;
   ref.mixer = o->target_mixer; ref.sampler = sampler.get(); ref.transient = o->transient != 0;

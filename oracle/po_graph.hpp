@@ -2,6 +2,7 @@
 // source chain, sampler, mixer graph and WAV block driver. Parity pinning: see po_dsp.hpp.
 #pragma once
 #include "po_dsp.hpp"
+#include "po_granular.hpp"
 
 namespace po {
 
@@ -351,7 +352,7 @@ struct GenEvent {
 };
 struct GenMsg { bool is_stop = false; GenEvent event; };
 
-// ---- src/generator/sampler/voice.rs:37-528 (non-granular path) --------------------------------------
+// ---- src/generator/sampler/voice.rs:37-528 ------------------------------------------------------------
 struct SamplerVoice {
   bool has_note = false; uint64_t note_id = 0;
   uint8_t note = 60;
@@ -362,6 +363,16 @@ struct SamplerVoice {
   PreloadedFileSource* file = nullptr;
   AhdsrEnvelope envelope;
   bool has_release_start = false; uint64_t release_start_frame = 0;
+  std::unique_ptr<GrainPool> grain_pool;  // voice.rs:46 (enable_granular_playback :342-380)
+  static constexpr size_t MODULATION_PROCESSOR_BLOCK_SIZE = 64;  // src/modulation/processor.rs
+
+  void enable_granular_playback(uint32_t sample_rate, std::shared_ptr<std::vector<float>> sample_buffer) {
+    const AudioFileBuffer& fb = *file->file_buffer;
+    bool has_loop = fb.has_loop;
+    float ls = 0, le = 0;
+    if (has_loop) { float total = (float)fb.frame_count(); ls = (float)fb.loop_start / total; le = (float)fb.loop_end / total; }
+    grain_pool = std::make_unique<GrainPool>(sample_rate, sample_buffer, has_loop, ls, le);
+  }
 
   SamplerVoice(std::unique_ptr<PreloadedFileSource> fs, size_t channel_count) {
     file = fs.get();
@@ -373,11 +384,12 @@ struct SamplerVoice {
   bool is_active() const { return has_note; }
   bool in_release_stage() const { return envelope.stage == AhdsrEnvelope::Release; }
   void reset() {  // voice.rs:222-236
-    if (is_active()) { file->reset(); has_note = false; }
+    if (is_active()) { file->reset(); has_note = false; if (grain_pool) grain_pool->reset(); }
     has_release_start = false;
   }
   void start(uint64_t id, uint8_t n, float volume, float panning, int32_t base_transpose, int32_t base_finetune,
-             float base_volume, float base_panning, const std::optional<AhdsrParameters>& env) {  // voice.rs:122-193
+             float base_volume, float base_panning, const std::optional<AhdsrParameters>& env,
+             const std::optional<GranularParameters>& gran) {  // voice.rs:122-193
     reset();
     note = n; note_volume = volume; note_panning = panning;
     double note_speed = speed_from_note(n);
@@ -388,6 +400,7 @@ struct SamplerVoice {
     file->set_speed(effective_speed, false, 0.0f);
     amplified->set_volume(effective_volume);
     source->set_panning(effective_panning);
+    if (grain_pool && gran) grain_pool->start(*gran, effective_speed, effective_volume, effective_panning);
     if (env) envelope.note_on(*env, 1.0f);
     has_note = true; note_id = id;
   }
@@ -395,21 +408,34 @@ struct SamplerVoice {
     if (is_active()) {
       has_release_start = true; release_start_frame = current_frame;
       if (env) envelope.note_off(*env);
-      else file->stop();
+      else { file->stop(); if (grain_pool) grain_pool->stop(); }
     }
   }
   void set_speed(double speed, bool has_glide, float glide, int32_t base_transpose, int32_t base_finetune) {
     double pitch_factor = std::pow(2.0, (double)base_transpose / 12.0 + (double)base_finetune / 1200.0);
     file->set_speed(speed * pitch_factor, has_glide, glide);
+    if (grain_pool) grain_pool->speed = speed * pitch_factor;
   }
-  void set_volume(float v, float base_volume) { note_volume = v; amplified->set_volume(base_volume * v); }
+  void set_volume(float v, float base_volume) {
+    note_volume = v; amplified->set_volume(base_volume * v);
+    if (grain_pool) grain_pool->volume = base_volume * v;
+  }
   void set_panning(float p, float base_panning) {
     note_panning = p;
-    source->set_panning(std::min(std::max(base_panning + p, -1.0f), 1.0f));
+    float eff = std::min(std::max(base_panning + p, -1.0f), 1.0f);
+    source->set_panning(eff);
+    if (grain_pool) grain_pool->panning = eff;
   }
   size_t process(float* out, size_t len, size_t channel_count, const std::optional<AhdsrParameters>& env,
-                 const SourceTime& time) {  // voice.rs:390-505
-    size_t written = source->write(out, len, time);
+                 const std::optional<GranularParameters>& gran, const SourceTime& time) {  // voice.rs:390-505
+    size_t written;
+    if (grain_pool && gran) {  // grain playback: chunks of MODULATION_PROCESSOR_BLOCK_SIZE frames (voice.rs:412-427)
+      const size_t step = MODULATION_PROCESSOR_BLOCK_SIZE * channel_count;
+      for (size_t o = 0; o < len; o += step) grain_pool->process(out + o, std::min(step, len - o), channel_count, *gran);
+      written = len;
+    } else {
+      written = source->write(out, len, time);
+    }
     if (env) {
       if (envelope.stage == AhdsrEnvelope::Sustain || envelope.stage == AhdsrEnvelope::Idle) {
         scale_buffer(out, written, envelope.output);
@@ -420,12 +446,12 @@ struct SamplerVoice {
         }
       }
     }
-    if (source->is_exhausted() || (env && envelope.stage == AhdsrEnvelope::Idle)) reset();
+    if (source->is_exhausted() || (grain_pool && grain_pool->is_exhausted()) || (env && envelope.stage == AhdsrEnvelope::Idle)) reset();
     return written;
   }
 };
 
-// ---- src/generator/sampler.rs:72-1028 (non-granular) --------------------------------------------------
+// ---- src/generator/sampler.rs:72-1028 -----------------------------------------------------------------
 struct Sampler : Source {
   std::shared_ptr<ArrayQueue<GenMsg>> queue;
   size_t active_voices = 0;
@@ -433,6 +459,8 @@ struct Sampler : Source {
   int32_t base_transpose = 0, base_finetune = 0;
   float base_volume = 1, base_panning = 0;
   std::optional<AhdsrParameters> envelope_parameters;
+  std::optional<GranularParameters> granular_parameters;
+  std::shared_ptr<AudioFileBuffer> file_buffer;
   bool transient = false, stopping = false, stopped = false;
   uint32_t output_sample_rate;
   size_t output_channel_count;
@@ -440,7 +468,7 @@ struct Sampler : Source {
 
   Sampler(std::shared_ptr<AudioFileBuffer> fb, size_t voice_count, size_t out_ch, uint32_t out_rate)
       : queue(std::make_shared<ArrayQueue<GenMsg>>((4 + 5 + 10) * 2 + 16)),
-        output_sample_rate(out_rate), output_channel_count(out_ch), temp_buffer(8 * 1024) {
+        file_buffer(fb), output_sample_rate(out_rate), output_channel_count(out_ch), temp_buffer(8 * 1024) {
     FilePlaybackOptions vo;  // sampler.rs:509-514
     vo.has_fade_out = true; vo.fade_out = Duration::from_millis(50);
     voices.reserve(voice_count);
@@ -450,6 +478,36 @@ struct Sampler : Source {
   bool with_ahdsr(AhdsrParameters p) {
     if (!p.set_sample_rate(output_sample_rate)) return false;
     envelope_parameters = p;
+    return true;
+  }
+  // Sampler::create_granular_sample_buffer (sampler.rs:908-952): the file as a mono buffer at the output rate
+  static std::shared_ptr<std::vector<float>> create_granular_sample_buffer(std::shared_ptr<AudioFileBuffer> fb, uint32_t out_rate) {
+    auto dest = std::make_shared<std::vector<float>>();
+    if (fb->channel_count == 1 && fb->sample_rate == out_rate) { *dest = fb->buffer; return dest; }
+    FilePlaybackOptions o;  // default().resampling_quality(Default).repeat(0)
+    o.has_repeat = true; o.repeat = 0;
+    PreloadedFileSource source(fb, o, out_rate);
+    size_t cc = source.channel_count();
+    std::vector<float> temp(1024 * cc, 0.0f);
+    SourceTime time;
+    for (;;) {
+      size_t read = source.write(temp.data(), temp.size(), time);
+      if (read == 0) break;
+      for (size_t f = 0; f + cc <= read; f += cc) {
+        float sum = 0.0f;
+        for (size_t c = 0; c < cc; ++c) sum += temp[f + c];
+        dest->push_back(sum / (float)cc);
+      }
+      time.pos_in_frames += read / cc;
+    }
+    if (dest->empty()) dest->push_back(0.0f);
+    return dest;
+  }
+  bool with_granular_playback(const GranularParameters& p) {  // sampler.rs:599-637
+    if (!p.validate()) return false;
+    auto buf = create_granular_sample_buffer(file_buffer, output_sample_rate);
+    for (auto& v : voices) v.enable_granular_playback(output_sample_rate, buf);
+    granular_parameters = p;
     return true;
   }
   uint32_t sample_rate() const override { return output_sample_rate; }
@@ -499,7 +557,7 @@ struct Sampler : Source {
             float vol = e.has_volume ? e.volume : 1.0f;
             float pan = e.has_panning ? e.panning : 0.0f;
             size_t idx = next_free_voice_index();
-            voices[idx].start(e.note_id, e.note, vol, pan, base_transpose, base_finetune, base_volume, base_panning, envelope_parameters);
+            voices[idx].start(e.note_id, e.note, vol, pan, base_transpose, base_finetune, base_volume, base_panning, envelope_parameters, granular_parameters);
             active_voices += 1;
             break;
           }
@@ -520,7 +578,7 @@ struct Sampler : Source {
       if (v.is_active()) {
         float* mix = temp_buffer.data();
         clear_buffer(mix, len);
-        size_t written = v.process(mix, len, output_channel_count, envelope_parameters, time);
+        size_t written = v.process(mix, len, output_channel_count, envelope_parameters, granular_parameters, time);
         add_buffers(out, mix, written);
         if (v.is_active()) active += 1;
       }

@@ -84,9 +84,15 @@ class Ahdsr(C.Structure):
                 ("release_scaling", F32), ("sustain_level", F32)]
 
 
+class Granular(C.Structure):
+    _fields_ = [("overlap_mode", U32), ("window", U32), ("size", F32), ("density", F32), ("variation", F32),
+                ("spray", F32), ("pan_spread", F32), ("playback_direction", U32), ("position", F32), ("step", F32)]
+
+
 class SamplerOptions(C.Structure):
     _fields_ = [("volume", F32), ("panning", F32), ("voices", U32), ("target_mixer", U32),
-                ("transient", U32), ("has_ahdsr", U32), ("ahdsr", Ahdsr)]
+                ("transient", U32), ("has_ahdsr", U32), ("ahdsr", Ahdsr),
+                ("has_granular", U32), ("granular", Granular), ("reserved", U32)]
 
 
 class Event(C.Structure):

@@ -104,6 +104,70 @@ struct HqRec {
   uint32_t buffer, table;
 };
 
+// ---- granular playback (src/generator/sampler/granular.rs) ---------------------------------------------------
+constexpr uint32_t GRAIN_POOL = 100;   // GRAIN_POOL_SIZE (src/generator/sampler/voice.rs:33)
+constexpr uint32_t GRAIN_LUT_N = 2048; // GRAIN_WINDOW_LUT (granular.rs:221)
+
+// GranularParameters of a Sampler, resolved on the host (static: no parameter automation yet)
+struct GranGroup {
+  uint32_t enabled;
+  uint32_t overlap_mode;      // 0 Cloud 1 Sequential
+  uint32_t window;            // GrainWindowMode
+  uint32_t backward;          // GrainPlaybackDirection::Backward
+  float position, step;
+  float trigger_inc;          // clamp(density, 1, 100) / sample_rate (granular.rs:798-801)
+  float crossfade;            // GrainWindowMode::sequential_crossfade_point
+  uint32_t grain_size;        // max((size_ms * 1.0 * sr / 1000) as usize, 2) (granular.rs:843-845)
+  uint32_t buffer;            // DevBuffer of the mono sample data at the output rate (sampler.rs:908-952)
+  uint32_t buf_len;           // its length in frames
+  uint32_t has_loop;          // sample_loop_range (voice.rs:355-361), normalised
+  float loop_start, loop_end;
+  uint32_t first_row;         // stream-scratch row of the sampler's first voice
+  uint32_t _pad;
+};
+
+// GrainPool state of one voice that the control pass needs (the grains' own f64 recurrences live in the grain kernel)
+struct GranState {
+  double speed;                       // GrainPool::speed
+  double primary_phase, primary_inc;  // Sequential: window phase of the primary grain (exact f64 accumulate)
+  uint64_t primary_end;
+  uint64_t max_end;                   // latest end frame of any grain: active_grain_indices.is_empty() <=> max_end <= now
+  uint64_t slot_end[GRAIN_POOL];      // absolute frame after a slot's grain played its last sample; 0 = free
+  uint32_t slot_rec[GRAIN_POOL];      // this block's GrainRec of the slot's grain
+  uint32_t slot_total[GRAIN_POOL];    // grain_size_samples of the slot's grain
+  float trigger_phase, playhead, volume, panning;
+  uint32_t gen;                       // time-block generation the slot_rec entries belong to
+  uint32_t n_order;
+  uint8_t order[GRAIN_POOL];          // active_grain_indices: slots in activation order (stale entries allowed)
+  uint8_t playing_loop, trigger_new, overlap_mode, has_primary;
+  uint32_t primary_slot;
+  uint32_t first_active;              // index into this block's per-voice record list of the oldest live record
+  uint32_t n_recs;                    // records of this voice in this block
+};
+
+// One grain's contribution inside one time block (grain kernel work item)
+struct GrainRec {
+  double position, increment, win_inc, loop_start, loop_end;  // Grain::activate (granular.rs:1025-1067)
+  float volume, panning;
+  uint32_t row;        // voice row
+  uint32_t start_off;  // block-relative frame of its first sample in this block
+  uint32_t len;        // samples it plays in this block (shortened when the voice resets)
+  uint32_t done;       // samples played before this block (> 0: state comes from the carry buffer)
+  uint32_t total;      // grain_size_samples
+  uint32_t slot;
+  uint32_t storage;    // first frame of its contribution in the block's grain storage
+  uint32_t buffer, buf_len;
+  uint16_t window_mode;
+  uint8_t has_loop, _pad;
+};
+
+// A grain that plays on into the next time block: its complete state after the block's last sample
+struct GrainCarry {
+  double position, window_phase, increment, win_inc, loop_start, loop_end;
+  float volume, panning;
+  uint32_t window_mode, has_loop;
+};
+
 enum GroupKind : uint32_t { GROUP_SAMPLER = 0, GROUP_FILE = 1 };
 
 struct GroupParams {

@@ -160,6 +160,12 @@ struct pb200_renderer {
   std::vector<uint32_t> sinc_table_keys;    // f32 bits of each table's cutoff
   std::vector<float> sinc_tables;           // [n_tables][128][256]
   bool sinc_tables_dirty = false;
+  std::vector<GranGroup> gran_groups;       // parallel to groups (enabled = 0 for everything but granular samplers)
+  std::vector<GranState> h_gran;            // one per voice of a granular sampler ("row")
+  uint32_t n_gran_rows = 0;
+  std::vector<float> grain_luts;            // [8][2048] GRAIN_WINDOW_LUT, built once
+  bool grain_luts_dirty = false;
+  uint32_t gran_parity = 0;                 // carry double buffer: flips every time block
   std::vector<GroupState> h_gstate;
   std::vector<MixerState> h_mstate;
   std::vector<FxHeader> h_fx;
@@ -167,6 +173,7 @@ struct pb200_renderer {
   size_t aux_doubles = 0;
   bool host_state_valid = true;  // host mirrors are newer or equal to device
   bool graph_dirty = true;
+  size_t dev_n_gran_rows = 0;
   size_t dev_n_voices = 0, dev_n_groups = 0, dev_n_mixers = 0, dev_n_fx = 0, dev_fx_state_bytes = 0;
 
   // device arrays
@@ -176,6 +183,13 @@ struct pb200_renderer {
   DevVec<float> d_sinc_tables, d_hq_scratch;
   DevVec<HqRec> d_hq_recs;
   DevVec<uint32_t> d_hq_nrecs;
+  DevVec<GranGroup> d_gran_groups;
+  DevVec<GranState> d_gran_states;
+  DevVec<GrainRec> d_grain_recs;
+  DevVec<uint32_t> d_gran_counters, d_gran_vrec, d_gran_tiles;
+  DevVec<float2> d_grain_storage;
+  DevVec<GrainCarry> d_grain_carry;
+  DevVec<float> d_grain_luts;
   DevVec<GroupParams> d_groups;
   DevVec<GroupState> d_gstate;
   DevVec<DevEvent> d_events;
@@ -287,6 +301,7 @@ int sync_state_to_host(pb200_renderer* r) {
   r->h_fx_state.resize(r->dev_fx_state_bytes);
   CUDA_TRY(r->d_voices.download(r->h_voices, r->sm));
   if (r->n_hq) { r->h_hq.resize(r->dev_n_voices); CUDA_TRY(r->d_hq.download(r->h_hq, r->sm)); }
+  if (r->dev_n_gran_rows) { r->h_gran.resize(r->dev_n_gran_rows); CUDA_TRY(r->d_gran_states.download(r->h_gran, r->sm)); }
   CUDA_TRY(r->d_gstate.download(r->h_gstate, r->sm));
   CUDA_TRY(r->d_mstate.download(r->h_mstate, r->sm));
   CUDA_TRY(r->d_fx.download(r->h_fx, r->sm));
@@ -330,6 +345,94 @@ uint32_t sinc_table_for(pb200_renderer* r, double resample_ratio) {
   r->sinc_table_keys.push_back(key);
   r->sinc_tables_dirty = true;
   return (uint32_t)(r->sinc_table_keys.size() - 1);
+}
+
+// GrainWindow::new (src/generator/sampler/granular.rs:110-196): the eight 2048-point window LUTs, f32 as the reference
+void build_grain_luts(std::vector<float>& luts) {
+  const size_t N = GRAIN_LUT_N;
+  luts.assign(8 * N, 0.0f);
+  const float PI = 3.14159265358979323846264338327950288f;
+  for (size_t i = 0; i < N; ++i) {
+    const float phase = (float)i / (float)N;
+    luts[0 * N + i] = 0.5f * (1.0f - std::cos(2.0f * PI * phase));
+    const float pi_phase = PI * phase;
+    luts[1 * N + i] = 0.42f - 0.5f * std::cos(2.0f * pi_phase) + 0.08f * std::cos(4.0f * pi_phase);
+    luts[2 * N + i] = phase < 0.5f ? 2.0f * phase : 2.0f * (1.0f - phase);
+    const float alpha = 0.5f, width = alpha / 2.0f;
+    if (phase < width) { const float u = phase / width; luts[3 * N + i] = 0.5f * (1.0f - std::cos(PI * u)); }
+    else if (phase > 1.0f - width) { const float u = (1.0f - phase) / width; luts[3 * N + i] = 0.5f * (1.0f - std::cos(PI * u)); }
+    else luts[3 * N + i] = 1.0f;
+    const float ramp_width = 0.1f;
+    if (phase < ramp_width) luts[4 * N + i] = phase / ramp_width;
+    else if (phase > 1.0f - ramp_width) luts[4 * N + i] = (1.0f - phase) / ramp_width;
+    else luts[4 * N + i] = 1.0f;
+    const float decay_rate = 6.0f;
+    luts[5 * N + i] = std::exp(-decay_rate * std::fabs(phase - 0.5f));
+    if (phase < 0.9f) luts[6 * N + i] = phase / 0.9f;
+    else { const float u = (phase - 0.9f) / 0.1f; luts[6 * N + i] = 0.5f * (1.0f + std::cos(PI * u)); }
+    if (phase < 0.1f) { const float u = phase / 0.1f; luts[7 * N + i] = 0.5f * (1.0f - std::cos(PI * u)); }
+    else luts[7 * N + i] = 1.0f - ((phase - 0.1f) / 0.9f);
+  }
+}
+
+__global__ void downmix_kernel(const float* __restrict__ stereo, float* __restrict__ mono, uint32_t frames, uint32_t src_channels) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= frames) return;
+  // `frame.iter().sum::<f32>() / channel_count` (sampler.rs:939-941); a mono source was duplicated by the mapping
+  const float l = stereo[2 * i], rr = stereo[2 * i + 1];
+  mono[i] = src_channels == 1 ? (0.0f + l) / 1.0f : ((0.0f + l) + rr) / 2.0f;
+}
+
+// Sampler::create_granular_sample_buffer (src/generator/sampler.rs:908-952): the file as a mono buffer at the output
+// rate. Like the reference this plays the file through a temporary PreloadedFileSource (Default quality, repeat 0)
+// in 1024-frame calls -- here a temporary renderer on the same device that borrows the sample data -- and mixes
+// the result down. Returns the index of the (internal) buffer holding it.
+int make_granular_buffer(pb200_renderer* r, uint32_t buffer_id, uint32_t* out_index) {
+  const DevBuffer src = r->buffers[buffer_id].dev;
+  const uint32_t sr = r->cfg.sample_rate;
+  if (src.channels == 1 && src.sample_rate == sr) { *out_index = buffer_id; return PB200_OK; }  // "just copy": shared read-only
+  pb200_config cfg = r->cfg;
+  cfg.master_volume = 1.0f;
+  pb200_renderer* t = nullptr;
+  if (int e = pb200_create(&cfg, &t)) return fail(r, e, "granular sample buffer: could not create the resampling renderer");
+  HostBuffer borrowed;
+  borrowed.dev = src; borrowed.dev.loop_start = -1; borrowed.dev.loop_end = -1; borrowed.cls = 0;
+  t->buffers.push_back(borrowed);
+  pb200_file_options fo;
+  pb200_file_options_default(&fo);
+  fo.repeat = 0;
+  uint32_t pid = 0;
+  int e = pb200_play_file(t, 0, &fo, PB200_TIME_NOW, &pid);
+  const uint64_t in_frames = src.n_samples / src.channels;
+  const uint64_t want = in_frames * sr / src.sample_rate + 100 + 2 * 1024;
+  const uint64_t frames = (want + 1023) / 1024 * 1024;
+  float* tmp = nullptr;
+  size_t tmp_cls = 0;
+  if (!e && DevicePool::get().alloc((void**)&tmp, frames * 2 * sizeof(float), &tmp_cls) != cudaSuccess) e = PB200_ERR_CUDA;
+  uint64_t written = 0;
+  if (!e) e = pb200_render_device(t, tmp, frames, &written);
+  uint64_t produced = 0;
+  if (!e) produced = t->stats.voice_frames;  // sum of what the source's write calls returned
+  std::string msg = e ? t->last_error : std::string();
+  pb200_destroy(t);
+  if (e) { if (tmp) DevicePool::get().release(tmp, tmp_cls); return fail(r, e, "granular sample buffer: " + msg); }
+  const uint64_t n = std::max<uint64_t>(produced, 1);
+  HostBuffer hb;
+  std::memset(&hb, 0, sizeof(hb));
+  float* mono = nullptr;
+  if (DevicePool::get().alloc((void**)&mono, n * sizeof(float), &hb.cls) != cudaSuccess) {
+    DevicePool::get().release(tmp, tmp_cls);
+    return fail(r, PB200_ERR_CUDA, "granular sample buffer: out of device memory");
+  }
+  if (produced == 0) cudaMemsetAsync(mono, 0, sizeof(float), r->sm);  // "ensure sample buffer is not empty"
+  else downmix_kernel<<<(uint32_t)((produced + 255) / 256), 256, 0, r->sm>>>(tmp, mono, (uint32_t)produced, src.channels);
+  cudaStreamSynchronize(r->sm);
+  DevicePool::get().release(tmp, tmp_cls);
+  hb.dev.data = mono; hb.dev.n_samples = (uint32_t)n; hb.dev.channels = 1; hb.dev.sample_rate = sr;
+  hb.dev.loop_start = -1; hb.dev.loop_end = -1;
+  r->buffers.push_back(hb);
+  *out_index = (uint32_t)r->buffers.size() - 1;
+  return PB200_OK;
 }
 
 HqState default_hq() {
@@ -388,7 +491,10 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sv) cudaStreamSynchronize(r->sv);
   if (r->sr_) cudaStreamSynchronize(r->sr_);
   if (r->sm) cudaStreamSynchronize(r->sm);
-  for (auto& b : r->buffers) DevicePool::get().release((void*)b.dev.data, b.cls);
+  for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
+  r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
+  r->d_gran_groups.free(); r->d_gran_states.free(); r->d_grain_recs.free(); r->d_gran_counters.free(); r->d_gran_vrec.free();
+  r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry.free(); r->d_grain_luts.free();
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
   r->d_mixers.free(); r->d_mstate.free(); r->d_child_index.free(); r->d_source_index.free(); r->d_level_mixers.free();
   r->d_class_groups.free(); r->d_fx.free(); r->d_fx_events.free(); r->d_fx_state.free(); r->d_aux.free();
@@ -608,6 +714,7 @@ int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_opti
   r->h_gstate.push_back(gs);
   uint32_t dense = (uint32_t)r->groups.size();
   r->groups.push_back(g);
+  { GranGroup gg; std::memset(&gg, 0, sizeof(gg)); r->gran_groups.push_back(gg); }
   insert_source(r, mit->second, dense, g.gp.start_time);
   r->group_by_id[g.public_id] = dense;
   r->graph_dirty = true;
@@ -648,7 +755,44 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
   g.gp.fade_out_inertia = fader_inertia(sr, 50000000ull);
   g.gp.base_volume = 1.0f; g.gp.base_panning = 0.0f;
   if (o->has_ahdsr && !resolve_ahdsr(o->ahdsr, sr, g.gp)) return fail(r, PB200_ERR_PARAMETER, "Invalid AHDSR parameters");
-  for (uint32_t i = 0; i < o->voices; ++i) r->h_voices.push_back(default_voice(b, sr, 1.0));
+  GranGroup gg;
+  std::memset(&gg, 0, sizeof(gg));
+  if (o->has_granular) {  // Sampler::with_granular_playback (sampler.rs:599-637)
+    const pb200_granular_params& p = o->granular;
+    if (p.overlap_mode > 1 || p.window > 7 || p.playback_direction > 2) return fail(r, PB200_ERR_PARAMETER, "Invalid granular parameters");
+    // GranularParameters::validate (granular.rs:287-331)
+    if (!(p.size >= 1.0f && p.size <= 1000.0f) || !(p.density >= 1.0f && p.density <= 100.0f) || !(p.spray >= 0.0f && p.spray <= 1.0f) ||
+        !(p.variation >= 0.0f && p.variation <= 1.0f) || !(p.pan_spread >= 0.0f && p.pan_spread <= 1.0f) ||
+        !(p.position >= 0.0f && p.position <= 1.0f) || !(p.step >= -4.0f && p.step <= 4.0f))
+      return fail(r, PB200_ERR_PARAMETER, "Invalid granular parameters");
+    if (p.variation != 0.0f || p.spray != 0.0f || p.pan_spread != 0.0f || p.playback_direction == 2)
+      return fail(r, PB200_ERR_UNSUPPORTED, "OS-seeded grain randomisation is not reproducible");
+    uint32_t gbuf = 0;
+    if (int e = make_granular_buffer(r, buffer_id, &gbuf)) return e;
+    const DevBuffer& fb = r->buffers[buffer_id].dev;  // (re-read: the buffer vector may have grown)
+    gg.enabled = 1;
+    gg.overlap_mode = p.overlap_mode; gg.window = p.window; gg.backward = p.playback_direction == 1;
+    gg.position = p.position; gg.step = p.step;
+    gg.trigger_inc = std::min(std::max(p.density * (1.0f + 0.0f), 1.0f), 100.0f) / (float)sr;  // granular.rs:798-801
+    gg.crossfade = p.window <= 3 ? 0.5f : (p.window == 4 ? 0.9f : 0.8f);                       // granular.rs:76-93
+    const float grain_size_ms = std::min(std::max(p.size * (1.0f + 0.0f), 1.0f), 1000.0f);
+    const float size_f = grain_size_ms * 1.0f * (float)sr / 1000.0f;                            // granular.rs:843-845
+    gg.grain_size = std::max<uint32_t>(size_f >= 4294967295.0f ? 0xFFFFFFFFu : (size_f > 0.0f ? (uint32_t)size_f : 0u), 2u);
+    gg.buffer = gbuf; gg.buf_len = r->buffers[gbuf].dev.n_samples;
+    if (fb.loop_start >= 0) {  // voice.rs:355-361
+      const float total = (float)(fb.n_samples / fb.channels);
+      gg.has_loop = 1; gg.loop_start = (float)fb.loop_start / total; gg.loop_end = (float)fb.loop_end / total;
+    }
+    gg.first_row = r->n_gran_rows;
+    r->n_gran_rows += o->voices;
+    GranState gs0;
+    std::memset(&gs0, 0, sizeof(gs0));
+    gs0.trigger_new = 1; gs0.speed = 1.0; gs0.volume = 1.0f;
+    r->h_gran.resize(r->n_gran_rows, gs0);
+    if (r->grain_luts.empty()) { build_grain_luts(r->grain_luts); r->grain_luts_dirty = true; }
+  }
+  const DevBuffer& b2 = r->buffers[buffer_id].dev;
+  for (uint32_t i = 0; i < o->voices; ++i) r->h_voices.push_back(default_voice(b2, sr, 1.0));
   r->h_hq.resize(r->h_voices.size(), default_hq());
   GroupState gs;
   std::memset(&gs, 0, sizeof(gs));
@@ -657,6 +801,7 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
   r->h_gstate.push_back(gs);
   uint32_t dense = (uint32_t)r->groups.size();
   r->groups.push_back(g);
+  r->gran_groups.push_back(gg);
   insert_source(r, mit->second, dense, g.gp.start_time);
   r->group_by_id[g.public_id] = dense;
   r->graph_dirty = true;
@@ -886,6 +1031,11 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
     CUDA_TRY(r->d_hq.upload(r->h_hq, s));
     if (r->sinc_tables_dirty) { CUDA_TRY(r->d_sinc_tables.upload(r->sinc_tables, s)); r->sinc_tables_dirty = false; }
   }
+  if (r->n_gran_rows) {
+    CUDA_TRY(r->d_gran_groups.upload(r->gran_groups, s));
+    CUDA_TRY(r->d_gran_states.upload(r->h_gran, s));
+    if (r->grain_luts_dirty) { CUDA_TRY(r->d_grain_luts.upload(r->grain_luts, s)); r->grain_luts_dirty = false; }
+  }
   CUDA_TRY(r->d_gstate.upload(r->h_gstate, s));
   CUDA_TRY(r->d_mstate.upload(r->h_mstate, s));
   CUDA_TRY(r->d_fx.upload(r->h_fx, s));
@@ -908,6 +1058,7 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
   }
   r->d_aux_used = r->aux_doubles;
   CUDA_TRY(cudaStreamSynchronize(s));
+  r->dev_n_gran_rows = r->n_gran_rows;
   r->dev_n_voices = r->h_voices.size(); r->dev_n_groups = r->h_gstate.size(); r->dev_n_mixers = r->h_mstate.size();
   r->dev_n_fx = r->h_fx.size(); r->dev_fx_state_bytes = r->h_fx_state.size();
   r->graph_dirty = false;
@@ -1040,6 +1191,38 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, r->device);
   }
 
+  // granular samplers: per-block grain records, per-voice record lists, tile ranges, contribution storage, carry
+  const uint32_t n_rows = r->n_gran_rows;
+  uint32_t gran_rec_cap = 0, gran_vrec_cap = 0;
+  size_t gran_storage_cap = 0;
+  if (n_rows) {
+    size_t recs = 0;
+    for (size_t gi = 0; gi < r->groups.size(); ++gi) {
+      const GranGroup& gg = r->gran_groups[gi];
+      if (!gg.enabled) continue;
+      const double per_frame = gg.overlap_mode == 1 ? 1.0 / std::max(1.0, std::floor(gg.grain_size * 0.5)) : (double)gg.trigger_inc;
+      const size_t per_voice = (size_t)GRAIN_POOL + (size_t)std::ceil((double)tb * per_frame) + 8;
+      const size_t overlap = gg.overlap_mode == 1 ? 3 : std::min<size_t>(GRAIN_POOL, (size_t)std::ceil((double)gg.grain_size * gg.trigger_inc) + 2);
+      recs += per_voice * r->groups[gi].gp.n_voices;
+      gran_vrec_cap = std::max<uint32_t>(gran_vrec_cap, (uint32_t)per_voice);
+      gran_storage_cap += (size_t)tb * overlap * r->groups[gi].gp.n_voices;
+    }
+    if (recs >= 0x7FFFFFFFull || gran_storage_cap >= 0xFFFFFFFFull)
+      return fail(r, PB200_ERR_UNSUPPORTED, "granular workload exceeds one time block's grain storage (lower PB200_TIME_BLOCK)");
+    gran_rec_cap = (uint32_t)recs;
+    CUDA_TRY(r->d_grain_recs.reserve((size_t)RING * gran_rec_cap));
+    CUDA_TRY(r->d_gran_counters.reserve(2 * (size_t)std::max<uint32_t>(RING, n_blocks)));
+    CUDA_TRY(r->d_gran_vrec.reserve((size_t)RING * n_rows * gran_vrec_cap));
+    CUDA_TRY(r->d_gran_tiles.reserve((size_t)RING * n_rows * n_tiles * 2));
+    CUDA_TRY(r->d_grain_storage.reserve((size_t)RING * gran_storage_cap));
+    {
+      const GrainCarry* before = r->d_grain_carry.p;
+      CUDA_TRY(r->d_grain_carry.reserve((size_t)2 * n_rows * GRAIN_POOL));
+      if (r->d_grain_carry.p != before) CUDA_TRY(cudaMemsetAsync(r->d_grain_carry.p, 0, r->d_grain_carry.cap * sizeof(GrainCarry), r->sv));
+    }
+    CUDA_TRY(cudaMemsetAsync(r->d_gran_counters.p, 0, 2 * (size_t)std::max<uint32_t>(RING, n_blocks) * sizeof(uint32_t), r->sv));
+  }
+
   std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r1(n_blocks), ev_m1(n_blocks);
   for (uint32_t b = 0; b < n_blocks; ++b) {
     CUDA_TRY(DevicePool::get().event(&ev_v0[b])); CUDA_TRY(DevicePool::get().event(&ev_v1[b]));
@@ -1080,6 +1263,21 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     va.hq_recs = n_hq ? r->d_hq_recs.p + (size_t)slot * hq_cap : nullptr;
     va.hq_n_recs = n_hq ? r->d_hq_nrecs.p + b : nullptr;   // one counter per block: read back after the render
     va.hq_cap = hq_cap;
+    va.gran_groups = n_rows ? r->d_gran_groups.p : nullptr;
+    va.gran_states = n_rows ? r->d_gran_states.p : nullptr;
+    std::memset(&va.gran, 0, sizeof(va.gran));
+    if (n_rows) {
+      va.gran.recs = r->d_grain_recs.p + (size_t)slot * gran_rec_cap;
+      va.gran.counters = r->d_gran_counters.p + 2 * (size_t)b;
+      va.gran.rec_cap = gran_rec_cap;
+      va.gran.vrec = r->d_gran_vrec.p + (size_t)slot * n_rows * gran_vrec_cap;
+      va.gran.vrec_cap = gran_vrec_cap;
+      va.gran.tile_range = r->d_gran_tiles.p + (size_t)slot * n_rows * n_tiles * 2;
+      va.gran.n_tiles = n_tiles;
+      va.gran.gen = va.gen;
+      va.gran.block_frames = tb;
+      CUDA_TRY(cudaMemsetAsync(va.gran.tile_range, 0xFF, (size_t)n_rows * n_tiles * 2 * sizeof(uint32_t), r->sv));
+    }
     va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
     for (size_t ci = 0; ci < c.classes.size(); ++ci) {
       const SizeClass& sc = c.classes[ci];
@@ -1103,6 +1301,22 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ra.seg_cap = seg_cap; ra.n_tiles = n_tiles; ra.block_frames = tb; ra.rc = r->rc;
     ra.hq_states = va.hq_states;
     ra.hq_scratch = n_hq ? r->d_hq_scratch.p + (size_t)slot * n_hq * tb * 2 : nullptr;
+    ra.gran_groups = va.gran_groups;
+    std::memset(&ra.gran, 0, sizeof(ra.gran));
+    if (n_rows) {  // every grain's contribution to this block
+      GrainArgs ga;
+      ga.recs = va.gran.recs; ga.counters = va.gran.counters; ga.rec_cap = gran_rec_cap; ga.buffers = r->d_buffers.p;
+      ga.window_luts = r->d_grain_luts.p;
+      ga.storage = r->d_grain_storage.p + (size_t)slot * gran_storage_cap;
+      ga.storage_cap = (uint32_t)gran_storage_cap;
+      ga.carry_in = r->d_grain_carry.p + (size_t)(r->gran_parity ^ 1u) * n_rows * GRAIN_POOL;
+      ga.carry_out = r->d_grain_carry.p + (size_t)r->gran_parity * n_rows * GRAIN_POOL;
+      r->gran_parity ^= 1u;
+      grain_kernel<<<(gran_rec_cap + 127) / 128, 128, 0, r->sr_>>>(ga);
+      ++launches;
+      ra.gran.recs = ga.recs; ra.gran.vrec = va.gran.vrec; ra.gran.tile_range = va.gran.tile_range; ra.gran.storage = ga.storage;
+      ra.gran.rec_cap = gran_rec_cap; ra.gran.vrec_cap = gran_vrec_cap; ra.gran.n_tiles = n_tiles; ra.gran.storage_cap = ga.storage_cap;
+    }
     if (n_hq) {  // materialise the resampler output this block consumes: one launch per filter table
       SincArgs sa;
       sa.recs = va.hq_recs; sa.n_recs = va.hq_n_recs; sa.cap = hq_cap; sa.buffers = r->d_buffers.p;
@@ -1171,6 +1385,13 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(cudaMemcpy(counts.data(), r->d_hq_nrecs.p, n_blocks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (uint32_t c2 : counts)
       if (c2 > hq_cap) return fail(r, PB200_ERR_CUDA, "HighQuality chunk record list overflowed");
+  }
+  if (n_rows) {
+    std::vector<uint32_t> counts(2 * (size_t)n_blocks);
+    CUDA_TRY(cudaMemcpy(counts.data(), r->d_gran_counters.p, counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t b = 0; b < n_blocks; ++b)
+      if (counts[2 * b] > gran_rec_cap || counts[2 * b + 1] > gran_storage_cap)
+        return fail(r, PB200_ERR_CUDA, "granular record list / grain storage overflowed");
   }
   r->host_state_valid = false;
   r->position = p1;

@@ -32,20 +32,23 @@ struct ReplayArgs {
   RenderConsts rc;
   const float* hq_scratch;      // [n_hq][block_frames][2]: resampler output stream of HighQuality voices (sinc_kernel.cuh)
   const HqState* hq_states;     // [n_voices] (only `slot` is read here)
+  const GranGroup* gran_groups; // [n_groups] or nullptr
+  GranReplay gran;              // this block's grain records + contribution storage (gran.cuh)
 };
 
 template <int CC>
 PB_DEV void replay_voice_subtile(VoiceState& v, CallCtx& cc, HistVals& hv, const Segment* __restrict__ segs, uint32_t& seg_i,
                                  uint32_t seg_end_i, uint32_t& seg_pos, uint32_t& seg_stop, bool& have, const GroupParams& gp,
                                  const DevBuffer& buf, const RenderConsts& rc, uint32_t sub_lo, uint32_t sub_hi, float* row,
-                                 const float* __restrict__ hq_row) {
+                                 const float* __restrict__ hq_row, const GranReplay* __restrict__ gran, uint32_t gran_row) {
   // sub_lo/sub_hi: frame range of this sub-tile relative to the block
   while (have && seg_pos < sub_hi) {
     const uint32_t lo = max(seg_pos, sub_lo);
     const uint32_t hi = min(seg_stop, sub_hi);
     uint32_t wrote = 0;
     if (hi > lo) {
-      if (v.hq) wrote = hq_replay_frames(v, cc, hq_row, rc.rate_comp, hi - lo, row + (lo - sub_lo) * 2);
+      if (gran) wrote = gran_replay_frames(v, cc, gp, *gran, gran_row, hi - lo, row + (lo - sub_lo) * 2);
+      else if (v.hq) wrote = hq_replay_frames(v, cc, hq_row, rc.rate_comp, hi - lo, row + (lo - sub_lo) * 2);
       else wrote = voice_frames<CC, true>(v, cc, hv, gp, buf, rc.sample_rate, rc.rate_comp, hi - lo, row + (lo - sub_lo) * 2);
       seg_pos = lo + wrote;
     }
@@ -113,6 +116,9 @@ __global__ void __launch_bounds__(MAXT, MINB) replay_kernel(ReplayArgs a) {
   bool have = false;
   const Segment* segs = nullptr;
   const float* hq_row = nullptr;
+  const bool is_gran = a.gran_groups != nullptr && a.gran_groups[g].enabled != 0;
+  const GranReplay* gran = is_gran ? &a.gran : nullptr;
+  const uint32_t gran_row = is_gran ? a.gran_groups[g].first_row + vi : 0u;
   if (active_thread) {
     const size_t vidx = gp.first_voice + vi;
     if (a.hq_states) hq_row = a.hq_scratch + (size_t)a.hq_states[vidx].slot * a.block_frames * 2;
@@ -147,9 +153,9 @@ __global__ void __launch_bounds__(MAXT, MINB) replay_kernel(ReplayArgs a) {
     if (have) {
       const uint32_t sub_lo = tile * TILE + st * SUB, sub_hi = sub_lo + SUB;
       if (buf.channels == 2)
-        replay_voice_subtile<2>(v, cc, hv, segs, seg_i, seg_end_i, seg_pos, seg_stop, have, gp, buf, a.rc, sub_lo, sub_hi, my_row, hq_row);
+        replay_voice_subtile<2>(v, cc, hv, segs, seg_i, seg_end_i, seg_pos, seg_stop, have, gp, buf, a.rc, sub_lo, sub_hi, my_row, hq_row, gran, gran_row);
       else
-        replay_voice_subtile<1>(v, cc, hv, segs, seg_i, seg_end_i, seg_pos, seg_stop, have, gp, buf, a.rc, sub_lo, sub_hi, my_row, hq_row);
+        replay_voice_subtile<1>(v, cc, hv, segs, seg_i, seg_end_i, seg_pos, seg_stop, have, gp, buf, a.rc, sub_lo, sub_hi, my_row, hq_row, gran, gran_row);
     }
     __syncthreads();
     // ordered reduction over the voices of each tile, generator-level gain/pan, coalesced store

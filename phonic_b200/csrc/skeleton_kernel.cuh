@@ -10,6 +10,7 @@
 // that can be replayed from a checkpoint is left to pass 2.
 #pragma once
 #include "hq.cuh"
+#include "gran.cuh"
 
 namespace pb {
 
@@ -45,6 +46,10 @@ struct SkeletonArgs {
   HqRec* hq_recs;
   uint32_t* hq_n_recs;
   uint32_t hq_cap;
+  // granular samplers (gran.cuh): per-group parameters, per-voice GrainPool control state, this block's emit context
+  const GranGroup* gran_groups;       // [n_groups] or nullptr when the graph has no granular sampler
+  GranState* gran_states;             // [n_gran_rows]
+  GranEmit gran;
   uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores, 2 = no simple calls
 };
 
@@ -195,6 +200,23 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   HqEmit hq_em;
   hq_em.recs = a.hq_recs; hq_em.n_recs = a.hq_n_recs; hq_em.cap = a.hq_cap; hq_em.buffer = gp.buffer;
   if (is_hq) hqp->rec = HQ_NONE;  // records are per time block
+  const bool is_gran = a.gran_groups != nullptr && a.gran_groups[g].enabled != 0;
+  const uint32_t gran_row = is_gran ? a.gran_groups[g].first_row + tid : 0u;
+  GranState* const gsp = (is_gran && mine) ? a.gran_states + gran_row : nullptr;
+  // SamplerVoice::stop (voice.rs:196-219) incl. the grain pool of a voice without envelope
+  auto stop_voice = [&](const uint64_t frame) {
+    if (gsp && v.has_note && !gp.has_env) gsp->trigger_new = 0;
+    sampler_voice_stop(v, gp, frame);
+  };
+  // SamplerVoice::process epilogue (voice.rs:488-502): `frame` / `off` = absolute / block-relative frame after the call
+  auto voice_epilogue = [&](const uint64_t frame, const uint32_t off) {
+    bool reset = v.finished || (gp.has_env && v.env_stage == ENV_IDLE);
+    if (gsp && !reset) reset = !gsp->trigger_new && gsp->max_end <= frame;  // GrainPool::is_exhausted
+    if (reset) {
+      if (gsp && v.has_note) gran_reset(*gsp, a.gran, frame, off);
+      voice_reset(v);
+    }
+  };
   Segment* my_segs = a.segs + (size_t)vidx * a.seg_cap;
   uint16_t* my_first = a.seg_first + (size_t)vidx * a.n_tiles;
   uint16_t* my_count = a.seg_count + (size_t)vidx * a.n_tiles;
@@ -231,7 +253,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) -> uint32_t {
     uint32_t written_frames = 0;
     bool simple = false;
-    if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq)
+    if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq && !is_gran)
       simple = buf.channels == 2 ? simple_call_ok<2>(v, cc, buf, n) : simple_call_ok<1>(v, cc, buf, n);
     if (simple) {
       const uint32_t tile = call_off / TILE;
@@ -266,7 +288,12 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
           n_segs++;
         }
         uint32_t w;
-        if (is_hq) w = buf.channels == 2 ? hq_advance<2>(v, cc, hqp, hq_em, buf, comp, seg_len) : hq_advance<1>(v, cc, hqp, hq_em, buf, comp, seg_len);
+        if (is_gran) {  // granular arm of SamplerVoice::process (voice.rs:412-427): the grain pool always fills the call
+          gran_advance(gsp, a.gran_groups + g, a.gran, gran_row, t + (off - call_off), off, seg_len);
+          w = seg_len;
+          cc.chunk_left -= w; cc.hq_off += w;
+          if (gp.has_env && cc.env_per_frame) env_chain(v, gp, w);
+        } else if (is_hq) w = buf.channels == 2 ? hq_advance<2>(v, cc, hqp, hq_em, buf, comp, seg_len) : hq_advance<1>(v, cc, hqp, hq_em, buf, comp, seg_len);
         else if (buf.channels == 2) w = voice_advance<2>(v, cc, gp, buf, out_rate, comp, seg_len);
         else w = voice_advance<1>(v, cc, gp, buf, out_rate, comp, seg_len);
         written_frames += w;
@@ -339,8 +366,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
               CallCtx cc;
               cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
               if (voice_begin_call(v, cc, gp, buf, rlen, comp, gp.has_env != 0, (uint32_t)(r0 - a.block_start))) run_call(cc, rlen, (uint32_t)(r0 - a.block_start), r0);
-              // SamplerVoice::process epilogue (voice.rs:488-502)
-              if (v.finished || (gp.has_env && v.env_stage == ENV_IDLE)) voice_reset(v);
+              voice_epilogue(r0 + rlen, (uint32_t)(r0 - a.block_start) + rlen);
               if (v.has_note) atomicAdd(&s_cnt[j], 1u);
             }
           }
@@ -408,7 +434,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
             // GeneratorPlaybackMessage::Stop (sampler.rs:733-738)
             __syncthreads();
             if (tid == 0) s_gs.stopping = gp.transient;
-            if (mine) { sampler_voice_stop(v, gp, t); publish_header(s_head, tid, v); }
+            if (mine) { stop_voice(t); publish_header(s_head, tid, v); }
             __syncthreads();
           } else if (ev.kind == EVK_SET_VOLUME) {  // generator-level AmplifiedSource message
             if (tid == 0) exp_set_target(s_gs.vol, ev.value, comp);
@@ -419,6 +445,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
               const uint32_t idx = next_free_voice_index(s_head, nv, gp.has_env != 0);
               __syncthreads();
               if (tid == idx) {  // SamplerVoice::start (voice.rs:122-193)
+                if (gsp && v.has_note) gran_reset(*gsp, a.gran, t, boff + total);
                 voice_reset(v);
                 v.note = (uint8_t)ev.note;
                 v.note_volume = ev.value;
@@ -428,6 +455,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
                 file_set_speed(v, ev.speed, 0.0f, buf.sample_rate, out_rate);
                 exp_set_target(v.vol, eff_vol, comp);
                 exp_set_target(v.pan, eff_pan, comp);
+                if (gsp) gran_start(*gsp, a.gran_groups[g], ev.speed, eff_vol, eff_pan);
                 if (gp.has_env) env_note_on(v, gp, 1.0f);
                 v.has_note = 1;
                 v.note_id = ev.note_id;
@@ -436,7 +464,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
               if (tid == 0) s_gs.active_voices += 1;
               __syncthreads();
             } else if (ev.kind == EVK_ALL_NOTES_OFF) {
-              if (mine) { sampler_voice_stop(v, gp, t); publish_header(s_head, tid, v); }
+              if (mine) { stop_voice(t); publish_header(s_head, tid, v); }
               __syncthreads();
             } else {
               // note-addressed events: first voice whose note_id matches (sampler.rs:776-822)
@@ -445,10 +473,15 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
                 if (s_head[i].active && s_head[i].note_id == ev.note_id) { idx = i; break; }
               __syncthreads();
               if (tid == idx) {
-                if (ev.kind == EVK_NOTE_OFF) sampler_voice_stop(v, gp, t);
-                else if (ev.kind == EVK_NOTE_SPEED) file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate);
-                else if (ev.kind == EVK_NOTE_VOLUME) { v.note_volume = ev.value; exp_set_target(v.vol, gp.base_volume * ev.value, comp); }
-                else if (ev.kind == EVK_NOTE_PANNING) { v.note_panning = ev.value; exp_set_target(v.pan, fminf(fmaxf(gp.base_panning + ev.value, -1.0f), 1.0f), comp); }
+                if (ev.kind == EVK_NOTE_OFF) stop_voice(t);
+                else if (ev.kind == EVK_NOTE_SPEED) { file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate); if (gsp) gsp->speed = ev.speed; }
+                else if (ev.kind == EVK_NOTE_VOLUME) { v.note_volume = ev.value; exp_set_target(v.vol, gp.base_volume * ev.value, comp); if (gsp) gsp->volume = gp.base_volume * ev.value; }
+                else if (ev.kind == EVK_NOTE_PANNING) {
+                  v.note_panning = ev.value;
+                  const float eff = fminf(fmaxf(gp.base_panning + ev.value, -1.0f), 1.0f);
+                  exp_set_target(v.pan, eff, comp);
+                  if (gsp) gsp->panning = eff;
+                }
                 publish_header(s_head, tid, v);
               }
               __syncthreads();
@@ -470,7 +503,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
       if (send_stop) {  // PlaybackMessageQueue::send_stop (mixed.rs:591-598)
         if (is_sampler) {
           if (tid == 0) s_gs.stopping = gp.transient;
-          if (mine) { sampler_voice_stop(v, gp, t); publish_header(s_head, tid, v); }
+          if (mine) { stop_voice(t); publish_header(s_head, tid, v); }
         } else if (mine) {
           file_stop(v, gp);
         }
@@ -497,8 +530,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
       if (is_sampler) {
         written = group_writes ? n : 0;
         if (was_active && group_writes) {
-          // SamplerVoice::process epilogue (voice.rs:488-502)
-          if (v.finished || (gp.has_env && v.env_stage == ENV_IDLE)) voice_reset(v);
+          voice_epilogue(t + n, call_off + n);
           publish_header(s_head, tid, v);
         }
         if (tid == 0) s_count = 0;

@@ -64,6 +64,21 @@ class AhdsrParameters:
 
 
 @dataclass
+class GranularParameters:
+    """GranularParameters (src/generator/sampler/granular.rs:239-284); Sampler::with_granular_playback."""
+    overlap_mode: int = 0         # GrainOverlapMode::Cloud
+    window: int = 2               # GrainWindowMode::Triangle
+    size: float = 100.0
+    density: float = 10.0
+    variation: float = 0.0
+    spray: float = 0.0
+    pan_spread: float = 0.0
+    playback_direction: int = 0   # GrainPlaybackDirection::Forward
+    position: float = 0.5
+    step: float = 0.0
+
+
+@dataclass
 class GeneratorPlaybackOptions:
     """GeneratorPlaybackOptions (src/generator.rs:41-141)."""
     volume: float = 1.0
@@ -334,7 +349,7 @@ class Player:
                                        A.TIME_NOW if start_time is None else int(start_time), C.byref(pid)))
         return FilePlaybackHandle(self, pid.value)
 
-    def _sampler(self, buffer_id, options, ahdsr, transient, start_time):
+    def _sampler(self, buffer_id, options, ahdsr, transient, start_time, granular=None):
         o = options or GeneratorPlaybackOptions()
         so = A.SamplerOptions()
         self.api.sampler_options_default(C.byref(so))
@@ -344,23 +359,28 @@ class Player:
             so.has_ahdsr = 1
             so.ahdsr = A.Ahdsr(_nanos(ahdsr.attack), _nanos(ahdsr.hold), _nanos(ahdsr.decay), _nanos(ahdsr.release),
                                ahdsr.attack_scaling, ahdsr.decay_scaling, ahdsr.release_scaling, ahdsr.sustain)
+        if granular is not None:
+            g = granular
+            so.has_granular = 1
+            so.granular = A.Granular(g.overlap_mode, g.window, g.size, g.density, g.variation, g.spray, g.pan_spread,
+                                     g.playback_direction, g.position, g.step)
         gid = A.U32()
         self._check(self.api.add_sampler(self._r, buffer_id, C.byref(so),
                                          A.TIME_NOW if start_time is None else int(start_time), C.byref(gid)))
         return GeneratorPlaybackHandle(self, gid.value)
 
     def play_generator(self, buffer_id: int, options=None, ahdsr: Optional[AhdsrParameters] = None,
-                       start_time: Optional[int] = None) -> GeneratorPlaybackHandle:
-        """Player::play_generator(Sampler::from_file_source(..).with_ahdsr(..), start_time)."""
-        return self._sampler(buffer_id, options, ahdsr, True, start_time)
+                       start_time: Optional[int] = None, granular: Optional[GranularParameters] = None) -> GeneratorPlaybackHandle:
+        """Player::play_generator(Sampler::from_file_source(..).with_ahdsr(..)[.with_granular_playback(..)], start_time)."""
+        return self._sampler(buffer_id, options, ahdsr, True, start_time, granular)
 
     def add_generator(self, buffer_id: int, options=None, ahdsr: Optional[AhdsrParameters] = None,
-                      mixer_id: Optional[int] = None) -> GeneratorPlaybackHandle:
+                      mixer_id: Optional[int] = None, granular: Optional[GranularParameters] = None) -> GeneratorPlaybackHandle:
         """Player::add_generator(Sampler::from_file_source(..).with_ahdsr(..), mixer_id)."""
         o = options or GeneratorPlaybackOptions()
         if mixer_id is not None:
             o = GeneratorPlaybackOptions(o.volume, o.panning, o.voices, mixer_id)
-        return self._sampler(buffer_id, o, ahdsr, False, None)
+        return self._sampler(buffer_id, o, ahdsr, False, None, granular)
 
     # -- render ------------------------------------------------------------------------------
     def render(self, frames: int) -> np.ndarray:

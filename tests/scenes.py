@@ -6,7 +6,7 @@ import numpy as np
 
 from phonic_b200 import workloads as W
 from phonic_b200.player import (AhdsrParameters, ChorusEffect, CompressorEffect, DelayEffect, Eq5Effect,
-                                FilePlaybackOptions, FilterEffect, GeneratorPlaybackOptions, Player, ReverbEffect)
+                                FilePlaybackOptions, FilterEffect, GeneratorPlaybackOptions, GranularParameters, Player, ReverbEffect)
 
 SR = 48000
 BLOCK = 1024
@@ -92,6 +92,64 @@ def hq_up_2x(p: Player):
     h = p.play_file_source(b, FilePlaybackOptions(speed=0.5, volume=0.6, resampling_quality=1))
     p.play_file_source(b2, FilePlaybackOptions(volume=0.5, resampling_quality=1), start_time=777)
     return {"h": h, "frames": 36 * BLOCK}
+
+
+def gran_cloud(p: Player):
+    """granular Cloud mode: Hann 100 ms grains at 50 Hz from a moving playhead, AHDSR, note-offs, note volume / pan /
+    speed changes, more notes than voices (stealing resets the grain pool)"""
+    b = p.upload_buffer(tone(48000, 48000, seed=31), 48000)
+    g = p.add_generator(b, GeneratorPlaybackOptions(volume=0.9, voices=3), AhdsrParameters(0.01, 0.0, 0.1, 0.7, 0.3),
+                        granular=GranularParameters(window=0, size=100.0, density=50.0, position=0.2, step=1.0))
+    n1 = g.note_on(60, 0.8, -0.3, sample_time=100)
+    n2 = g.note_on(67, 0.5, 0.4, sample_time=5000)
+    g.set_note_volume(n1, 0.3, sample_time=9000)
+    g.set_note_panning(n2, -0.8, sample_time=12000)
+    g.set_note_speed(n1, 1.5, glide=None, sample_time=15000)
+    n3 = g.note_on(55, 0.6, 0.0, sample_time=20000)
+    g.note_on(72, 0.4, 0.2, sample_time=26000)      # steals
+    g.note_off(n2, sample_time=30000)
+    g.note_off(n3, sample_time=40000)
+    g.all_notes_off(50000)
+    return {"g": g, "frames": 72 * BLOCK}
+
+
+def gran_resampled_fixed(p: Player):
+    """granular from a stereo 44.1 kHz file (mono buffer resampled on the device through the cubic path), fixed
+    position, backward Triangle grains, no envelope: note_off stops triggering and the pool drains"""
+    b = p.upload_buffer(tone(30000, 44100, channels=2, seed=32), 44100)
+    g = p.play_generator(b, GeneratorPlaybackOptions(voices=2), None, start_time=300,
+                         granular=GranularParameters(window=2, size=60.0, density=25.0, position=0.4, step=0.0,
+                                                     playback_direction=1))
+    n1 = g.note_on(62, 0.7, 0.5, sample_time=1000)
+    n2 = g.note_on(50, 0.6, -0.5, sample_time=4000)
+    g.note_off(n1, sample_time=20000)
+    g.note_off(n2, sample_time=28000)
+    g.stop(40000)
+    return {"g": g, "frames": 48 * BLOCK}
+
+
+def gran_sequential_loop(p: Player):
+    """granular Sequential mode (crossfade-gated triggering) with an embedded loop the playhead runs into"""
+    b = p.upload_buffer(tone(40000, 48000, seed=33), 48000, loop_range=(8000, 30000))
+    g = p.add_generator(b, GeneratorPlaybackOptions(voices=2), AhdsrParameters(0.005, 0.0, 0.05, 0.8, 0.2),
+                        granular=GranularParameters(overlap_mode=1, window=4, size=35.0, density=10.0, position=0.05, step=3.0))
+    n1 = g.note_on(60, 0.8, 0.0, sample_time=0)
+    n2 = g.note_on(64, 0.5, 0.6, sample_time=7777)
+    g.note_off(n1, sample_time=45000)
+    g.note_off(n2, sample_time=52000)
+    return {"g": g, "frames": 72 * BLOCK}
+
+
+def gran_dense(p: Player):
+    """100 Hz x 400 ms grains: ~40 overlapping grains per voice, Blackman window"""
+    b = p.upload_buffer(tone(36000, 48000, seed=34), 48000)
+    g = p.add_generator(b, GeneratorPlaybackOptions(voices=2), AhdsrParameters(0.01, 0.0, 0.2, 0.6, 0.5),
+                        granular=GranularParameters(window=1, size=400.0, density=100.0, position=0.3, step=0.5))
+    n1 = g.note_on(57, 0.2, -0.2, sample_time=500)
+    g.note_on(69, 0.15, 0.3, sample_time=9000)
+    g.note_off(n1, sample_time=40000)
+    g.all_notes_off(60000)
+    return {"g": g, "frames": 96 * BLOCK}
 
 
 def sampler_notes(p: Player):
@@ -195,6 +253,10 @@ SCENES = {
     "hq_events": hq_events,
     "hq_equal_rates": hq_equal_rates,
     "hq_up_2x": hq_up_2x,
+    "gran_cloud": gran_cloud,
+    "gran_resampled_fixed": gran_resampled_fixed,
+    "gran_sequential_loop": gran_sequential_loop,
+    "gran_dense": gran_dense,
     "sampler_notes": sampler_notes,
     "sampler_no_envelope": sampler_no_envelope,
     "cfg2_small": cfg2_small,
@@ -213,7 +275,7 @@ SCENES = {
 
 # scenes whose whole path is +,-,*,/,sqrt in the reference's order: must be bit-exact on device
 BIT_EXACT = {"file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
-             "sampler_no_envelope", "hq_equal_rates"}
+             "sampler_no_envelope", "hq_equal_rates", "gran_cloud", "gran_resampled_fixed", "gran_sequential_loop", "gran_dense"}
 # bit-exact voice path + time-invariant biquads evaluated by the f64 block scan (exact up to O(1e-16)
 # relative reassociation error before the f32 cast): at most a rare last-bit flip
 NEAR_EXACT = {"cfg2_small", "fx_filter"}

@@ -74,7 +74,8 @@ def test_scene_matches_oracle(cuda_api, oracle_api, name):
             assert (sa.playback_pos, sa.end_frame) == (sb.playback_pos, sb.end_frame)
 
 
-@pytest.mark.parametrize("name", ["file_events", "sampler_notes", "nested_and_gated", "fx_reverb", "hq_events", "hq_up_2x"])
+@pytest.mark.parametrize("name", ["file_events", "sampler_notes", "nested_and_gated", "fx_reverb", "hq_events", "hq_up_2x",
+                                  "gran_cloud", "gran_sequential_loop"])
 def test_split_render_calls_equal_single_call(cuda_api, name):
     _, _, one = render(cuda_api, name, calls=1)
     _, _, many = render(cuda_api, name, calls=5)
@@ -147,6 +148,36 @@ def test_small_time_blocks_split_high_quality_chunks(cuda_api):
     finally:
         del os.environ["PB200_TIME_BLOCK"]
     assert np.array_equal(one, small)
+
+
+def test_small_time_blocks_carry_grains(cuda_api):
+    """Grains that play across time-block boundaries continue from the carry the grain kernel leaves behind."""
+    for name in ("gran_cloud", "gran_dense"):
+        _, _, one = render(cuda_api, name)
+        os.environ["PB200_TIME_BLOCK"] = "2048"
+        try:
+            _, _, small = render(cuda_api, name)
+        finally:
+            del os.environ["PB200_TIME_BLOCK"]
+        assert np.array_equal(one, small), name
+
+
+def test_granular_randomisation_is_rejected(cuda_api, oracle_api):
+    """OS-seeded SmallRng (granular.rs:413): settings that let a draw reach the audio are PB200_ERR_UNSUPPORTED."""
+    from phonic_b200 import PhonicError
+    from phonic_b200 import _capi as A
+    from phonic_b200.player import GeneratorPlaybackOptions, GranularParameters
+    for api in (cuda_api, oracle_api):
+        p = Player(api, SR)
+        b = p.upload_buffer(np.zeros(4096, np.float32), 48000)
+        for bad in (GranularParameters(variation=0.5), GranularParameters(spray=0.1), GranularParameters(pan_spread=1.0),
+                    GranularParameters(playback_direction=2)):
+            with pytest.raises(PhonicError) as e:
+                p.add_generator(b, GeneratorPlaybackOptions(voices=2), None, granular=bad)
+            assert e.value.code == A.ERR_UNSUPPORTED
+        with pytest.raises(PhonicError) as e:
+            p.add_generator(b, GeneratorPlaybackOptions(voices=2), None, granular=GranularParameters(size=0.5))
+        assert e.value.code == A.ERR_PARAMETER
 
 
 def test_empty_player_renders_nothing(cuda_api, oracle_api):

@@ -147,3 +147,127 @@ def test_note_to_ratio(oracle_lib, note, speed, rate, ratio):
         assert s.value == pytest.approx(speed, rel=1e-15)
     assert r.value == rate
     assert q.value == pytest.approx(ratio, abs=1e-7)
+
+
+# ---- HighQuality (rubato sinc) path: PARITY UNPINNED against rubato itself (crate not available); these pin the
+# ---- restatement against the reference's own unit test at this boundary and against signal-level properties.
+def _player(oracle_api, sr=48000):
+    from phonic_b200.player import Player
+    return Player(oracle_api, sr)
+
+
+def test_reference_unit_test_resampling_high_quality_half(oracle_api):
+    # src/source/file/preloaded.rs:513-532: [0.2, 1.0, 0.5] @48000 -> 48000, ResamplingQuality::HighQuality
+    from phonic_b200.player import FilePlaybackOptions
+    p = _player(oracle_api)
+    buf = f32([0.2, 1.0, 0.5])
+    b = p.upload_buffer(buf, 48000, add_pad_frame=False)
+    p.play_file_source(b, FilePlaybackOptions(resampling_quality=1))
+    out = p.render(1024)[:, 0]
+    assert np.count_nonzero(out) >= 3 * 44100 // 48000
+    assert abs(float(out.sum()) - float(buf.sum())) < 0.2
+    assert float(out[3:].sum()) < 0.1
+
+
+def test_high_quality_resampler_reconstructs_a_sine(oracle_api):
+    """44.1 -> 48 kHz: a 1 kHz sine comes out as a 1 kHz sine of the same amplitude; its sub-sample delay is the one
+    the restated index arithmetic implies (first output at idx = -sinc_len/2 + t_ratio, filter centre 1/128 late)."""
+    from phonic_b200.player import FilePlaybackOptions
+    sr_in, sr_out, f = 44100, 48000, 1000.0
+    x = (0.5 * np.sin(2 * np.pi * f * np.arange(20000) / sr_in)).astype(np.float32)
+    p = _player(oracle_api, sr_out)
+    b = p.upload_buffer(x, sr_in)
+    p.play_file_source(b, FilePlaybackOptions(resampling_quality=1, fade_out=None))
+    y = p.render(24 * 1024)[:, 0]
+    seg = slice(2000, 16000)
+    n = np.arange(len(y))[seg]
+    w = 2 * np.pi * f / sr_out
+    A = np.stack([np.sin(w * n), np.cos(w * n)], 1)
+    c, *_ = np.linalg.lstsq(A, y[seg].astype(np.float64), rcond=None)
+    assert abs(np.hypot(*c) - 0.5) < 2e-5
+    assert np.abs(y[seg] - A @ c).max() < 2e-6
+    delay_in_samples = -np.arctan2(c[1], c[0]) / (2 * np.pi * f) * sr_in
+    t_ratio = sr_in / sr_out
+    assert delay_in_samples == pytest.approx(1.0 - t_ratio - 1.0 / 128.0, abs=2e-3)
+
+
+def test_high_quality_chunking(oracle_api):
+    """256-frame input chunks. 1000 input frames = 3 chunks + a 232-frame tail; the tail comes up while output of the
+    3rd chunk is still pending, and the zero-pad path counts it as consumed without processing it
+    (preloaded.rs:296-304): only 768 input frames ever reach the resampler."""
+    from phonic_b200.player import FilePlaybackOptions
+    p = _player(oracle_api)
+    b = p.upload_buffer(np.full(1000, 0.25, np.float32), 24000, add_pad_frame=False)
+    h = p.play_file_source(b, FilePlaybackOptions(resampling_quality=1, fade_out=None))
+    out = p.render(4 * 1024)[:, 0]
+    # 2x up-sampling of a DC signal: DC gain 1 in the steady state (table normalised to F / sum)
+    assert np.abs(out[400:1200] - 0.25).max() < 2e-6
+    # 768 input frames -> 1536 output frames + half the filter length (256 output frames) of ring-down
+    last = int(np.flatnonzero(np.abs(out) > 1e-7)[-1])
+    assert 1536 < last < 1536 + 256
+    # EOF is reached inside the 2nd 1024-frame call; the source is gone after it
+    assert not h.is_playing() and not out[2048:].any()
+
+
+# ---- granular playback (src/generator/sampler/granular.rs), derived from the cited formulas -------------------------
+def _grain_window_lut(mode, N=2048):
+    ph = (np.arange(N, dtype=np.float32) / np.float32(N)).astype(np.float32)
+    pi = np.float32(np.pi)
+    if mode == 2:   # Triangle (granular.rs:131-135)
+        return np.where(ph < np.float32(0.5), np.float32(2) * ph, np.float32(2) * (np.float32(1) - ph)).astype(np.float32)
+    if mode == 4:   # Trapezoid (granular.rs:152-160)
+        rw = np.float32(0.1)
+        return np.where(ph < rw, ph / rw, np.where(ph > np.float32(1) - rw, (np.float32(1) - ph) / rw, np.float32(1))).astype(np.float32)
+    raise ValueError(mode)
+
+
+def test_single_grain_is_the_window_times_the_sample(oracle_api):
+    """One Triangle grain over a constant buffer: out = ((0.25 * (window(k / size) * volume)) * gain), f32, with the
+    2048-point LUT lerp of GrainWindow::sample (granular.rs:201-215) and the 0.001 envelope threshold."""
+    from phonic_b200.player import GeneratorPlaybackOptions, GranularParameters
+    sr, size_ms, vol, pan = 48000, 100.0, np.float32(0.8), np.float32(-0.5)
+    p = _player(oracle_api, sr)
+    b = p.upload_buffer(np.full(4800, 0.25, np.float32), sr, add_pad_frame=False)
+    g = p.add_generator(b, GeneratorPlaybackOptions(voices=1), None,
+                        granular=GranularParameters(window=2, size=size_ms, density=1.0, position=0.5, step=0.0))
+    g.note_on(60, float(vol), float(pan), sample_time=0)
+    out = p.render(8 * 1024)
+    S = int(np.float32(size_ms) * np.float32(1.0) * np.float32(sr) / np.float32(1000.0))
+    assert S == 4800
+    lut = _grain_window_lut(2)
+    k = np.arange(S)
+    phase = np.cumsum(np.concatenate([[0.0], np.full(S - 1, 1.0 / S)]))   # window_phase += 1/size (f64)
+    idxf = phase * 2047.0
+    idx = idxf.astype(np.int64) & 2047
+    frac = (idxf - np.trunc(idxf)).astype(np.float32)
+    env = (lut[idx] * (np.float32(1) - frac) + lut[(idx + 1) & 2047] * frac).astype(np.float32) * vol
+    windowed = (np.float32(0.25) * env).astype(np.float32)
+    lg = (np.float32(1) - pan) * np.float32(0.5)
+    rg = (np.float32(1) + pan) * np.float32(0.5)
+    exp_l = np.where(env > np.float32(0.001), windowed * lg, np.float32(0)).astype(np.float32)
+    exp_r = np.where(env > np.float32(0.001), windowed * rg, np.float32(0)).astype(np.float32)
+    assert np.array_equal(out[:S, 0], exp_l) and np.array_equal(out[:S, 1], exp_r)
+    assert not out[S:].any()   # density 1 Hz: the next grain is 48000 frames away
+
+
+def test_grain_trigger_cadence(oracle_api):
+    """Cloud mode: trigger_phase starts at 1.0 and accumulates density / sr in f32 (granular.rs:788-809)."""
+    from phonic_b200.player import GeneratorPlaybackOptions, GranularParameters
+    sr, density = 48000, 37.0
+    p = _player(oracle_api, sr)
+    b = p.upload_buffer(np.full(4800, 0.25, np.float32), sr, add_pad_frame=False)
+    g = p.add_generator(b, GeneratorPlaybackOptions(voices=1), None,
+                        granular=GranularParameters(window=4, size=1.0, density=density, position=0.5, step=0.0))
+    g.note_on(60, 1.0, 0.0, sample_time=0)
+    frames = 16 * 1024
+    out = p.render(frames)[:, 0]
+    inc = np.float32(density) / np.float32(sr)
+    ph, trig = np.float32(1.0), []
+    for t in range(frames):
+        ph = np.float32(ph + inc)
+        if ph >= np.float32(1.0):
+            ph = np.float32(ph - np.float32(1.0))
+            trig.append(t)
+    onsets = np.flatnonzero((out != 0) & (np.concatenate([[0], out[:-1]]) == 0))
+    # 1 ms Trapezoid grain = 48 samples; sample 0 has envelope 0 (skipped), the blip starts one frame after the trigger
+    assert onsets.tolist() == [t + 1 for t in trig if t + 1 < frames]

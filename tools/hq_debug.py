@@ -1,4 +1,4 @@
-"""Renders one HighQuality scene on the device and the oracle and prints where they differ (debug aid)."""
+"""Renders scenes on the device and the oracle and prints where they differ (debug aid)."""
 import os
 import sys
 
@@ -20,12 +20,15 @@ for name in names:
         p = Player(api, SR)
         info = SCENES[name](p)
         outs.append(p.render(info["frames"]))
-        st = info["h"].status()
-        print(name, "status", st.is_playing, st.exhausted, st.playback_pos, st.end_frame)
+        if "h" in info:
+            st = info["h"].status()
+            print(name, "status", st.is_playing, st.exhausted, st.playback_pos, st.end_frame)
+        if "g" in info:
+            print(name, "voices", info["g"].voice_states())
     g, r = outs
     d = np.abs(g - r).max(axis=1)
-    bad = np.flatnonzero(d > 1e-5)
-    print(name, "max err %.3e" % d.max(), "bad frames", bad.size, bad[:10], "peak", np.abs(r).max())
+    bad = np.flatnonzero(d > 0)
+    print(name, "max err %.3e" % d.max(), "differing frames", bad.size, bad[:10], "peak", np.abs(r).max())
     if bad.size:
         i = bad[0]
         print(" gpu", g[i:i + 4].ravel(), "\n ref", r[i:i + 4].ravel())
