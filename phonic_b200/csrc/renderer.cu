@@ -1275,7 +1275,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       va.gran.tile_range = r->d_gran_tiles.p + (size_t)slot * n_rows * n_tiles * 2;
       va.gran.n_tiles = n_tiles;
       va.gran.gen = va.gen;
-      va.gran.block_frames = tb;
+      va.gran.block_frames = blen;  // grains stop at the end of what this block really renders: their carry is taken there
       CUDA_TRY(cudaMemsetAsync(va.gran.tile_range, 0xFF, (size_t)n_rows * n_tiles * 2 * sizeof(uint32_t), r->sv));
     }
     va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
