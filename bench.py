@@ -54,6 +54,12 @@ def workload_spec(name):
     if name == "cfg5shard":
         return dict(voices=8192, n_mixers=64, seconds=10, desc="cfg5 per-GPU shard: 8192 voices in 64 sub-mixer subtrees, "
                     "10 s (480256 frames)")
+    if name == "cfg4":
+        return dict(voices=160, n_mixers=0, seconds=10, desc="cfg4: granular, 160 voices x 100 grains/s x 100 ms Hann grains "
+                    "(16k grains/s) from a 362835-frame mono buffer, AHDSR, 10 s (480256 frames)")
+    if name == "sinc":
+        return dict(voices=1024, n_mixers=0, seconds=10, desc="sinc micro-benchmark: 1024 HighQuality (rubato sinc, 256 taps x 4 "
+                    "sub-phases) mono file sources 44.1->48k, 10 s (480256 frames)")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -83,6 +89,10 @@ def build_scene(player, name, rank=0, as_subtree=False):
             mh = player.add_mixer(None)
             W.add_voice_bank(player, W.VoiceBankSpec(voices=spec["voices"]), bid, mh.id, seed_offset=7919 * rank)
             player.add_effect(FilterEffect(0, 2000.0, 0.707), mh.id)
+    elif name == "cfg4":
+        W.build_cfg4(player, spec["voices"])
+    elif name == "sinc":
+        W.build_sinc_bank(player, spec["voices"], buffer=buf)
     else:
         W.build_subtrees(player, spec["n_mixers"], spec["voices"] // spec["n_mixers"], W.VoiceBankSpec(), effects="none",
                          seed_base=100000 * rank, buffer=buf)
@@ -154,6 +164,24 @@ def fp32_fma_peak_tflops(torch, device):
     return props.multi_processor_count * 128 * 2 * clock_hz / 1e12
 
 
+def build_cpu_sample(p, name, rank=0, as_subtree=False):
+    """The bounded sample of `name` the host-side arms render (same per-voice events, fewer voices where the full
+    workload would take minutes on one core). Returns (voices in the sample, description)."""
+    from phonic_b200 import workloads as W
+    spec = workload_spec(name)
+    if name == "cfg2":
+        build_scene(p, name, rank=rank, as_subtree=as_subtree)
+        return spec["voices"], f"full {name} render"
+    if name == "cfg4":
+        W.build_cfg4(p, 32)
+        return 32, "cfg4 with 32 of 160 voices (same per-voice events)"
+    if name == "sinc":
+        W.build_sinc_bank(p, 16, buffer=sample_buffer())
+        return 16, "sinc bank with 16 of 1024 voices"
+    W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none", seed_base=100000 * rank, buffer=sample_buffer())
+    return 512, f"{name} with 512 of {spec['voices']} voices (4 sub-mixers x 128, same per-voice events)"
+
+
 def cpu_baseline(name, seconds_budget=25.0):
     """Oracle port on the host cores, rank 0 only, bounded sample of the same workload."""
     from phonic_b200 import workloads as W
@@ -161,21 +189,14 @@ def cpu_baseline(name, seconds_budget=25.0):
     api = oracle_api(fast=True)
     spec = workload_spec(name)
     frames = W.frames_for(spec["seconds"], SR)
-    voices = spec["voices"]
-    sample = f"full {name} render once" if voices <= 512 else f"{name} with 512 of {voices} voices (same per-voice events)"
     p = Player(api, SR)
-    if name == "cfg2":
-        build_scene(p, name)
-        v = voices
-    else:
-        W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none")
-        v = 512
+    v, sample = build_cpu_sample(p, name)
     t0 = time.perf_counter()
     out = np.zeros((frames, 2), np.float32)
     p.render_into(out)
     dt = time.perf_counter() - t0
     p.close()
-    return {"value": v * frames / dt, "unit": "voice-samples/s", "cores": 1, "kind": "port", "sample": sample,
+    return {"value": v * frames / dt, "unit": "voice-samples/s", "cores": 1, "kind": "port", "sample": sample + ", once",
             "seconds": dt}
 
 
@@ -195,18 +216,14 @@ def run_reference(args):
     frames = W.frames_for(spec["seconds"], SR)
     voices = spec["voices"]
     world = max(1, args.gpus)
-    bounded = voices > 512
-    v_per = 512 if bounded else voices
     sample_buffer()
     times = []
+    v_per, sample = voices, ""
     for i in range(args.warmup + args.steps):
         players, outs = [], []
         for r in range(world):
             p = Player(api, SR)
-            if not bounded:
-                build_scene(p, args.workload, rank=r, as_subtree=world > 1)
-            else:
-                W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none", seed_base=100000 * r, buffer=sample_buffer())
+            v_per, sample = build_cpu_sample(p, args.workload, rank=r, as_subtree=world > 1)
             players.append(p)
             outs.append(np.zeros((frames, 2), np.float32))
         t0 = time.perf_counter()
@@ -226,7 +243,7 @@ def run_reference(args):
             times.append(dt)
     total_t = sum(times)
     value = world * v_per * frames * len(times) / total_t
-    sample = "full workload per step" if not bounded else f"512 of {voices} voices per rank-equivalent per step (4 sub-mixers x 128)"
+    sample = sample + " per step"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total_t / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -285,6 +302,7 @@ def main():
     out_dev = torch.zeros(frames, 2, dtype=torch.float32, device=device)
     clocks = ClockSampler(local_rank)
     dev_ms, wall_ms, voice_ms, skel_ms, fx_ms, launches, vframes = [], [], [], [], [], 0, 0
+    sinc_ms, grain_ms, sinc_frames, grain_samples = [], [], 0, 0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -317,6 +335,8 @@ def main():
             fx_ms.append(st.effect_kernel_ms)
             launches += int(st.kernel_launches) + (1 if world > 1 else 0)
             vframes += int(st.voice_frames)
+            sinc_ms.append(st.sinc_kernel_ms); grain_ms.append(st.grain_kernel_ms)
+            sinc_frames += int(st.sinc_frames); grain_samples += int(st.grain_samples)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -350,7 +370,7 @@ def main():
         p.close()
         if i >= args.warmup:
             e2e_ms.append((t1 - t0) * 1e3)
-    buf_bytes = int(4.0 * 44100) * 4
+    buf_bytes = (362835 if args.workload == "cfg4" else int(4.0 * 44100)) * 4
     h2d = buf_bytes + voices * 176 + voices * 3 * 64       # sample buffer + voice state + event records
     d2h = frames * 2 * 4
 
@@ -380,18 +400,42 @@ def main():
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         fma_peak = fp32_fma_peak_tflops(torch, device)
-        # dominant kernel: voice_kernel. Algorithmic work = active voice-frames x 2 channels x 25 flop
-        flops = (total_vframes / world) * 2 * FLOP_PER_CHANNEL_SAMPLE
-        ach = flops / (total_voice_ms / 1e3) / 1e12
-        roofline = {"bound": "fp32_fma", "kernel": "replay_kernel", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s",
-                    "frac": ach / fma_peak, "traffic": None,
-                    "peak_source": "derived: SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json holds only HBM and bf16 "
-                                   "tensor peaks; voices share one L2-resident buffer so the kernel is not HBM bound)",
-                    "hbm_achieved_gbs": (total_vframes / world) * 8.0 / (total_voice_ms / 1e3) / 1e9,
-                    "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_kind": peak_kind,
-                    "voice_kernel_ms_per_step": total_voice_ms / K, "skeleton_kernel_ms_per_step": sum(skel_ms) / K,
-                    "effect_kernel_ms_per_step": sum(fx_ms) / K,
-                    "note": "per-pass spans are event-to-event on their own stream; the three passes overlap across time blocks"}
+        passes = {"voice_kernel_ms_per_step": total_voice_ms / K, "skeleton_kernel_ms_per_step": sum(skel_ms) / K,
+                  "effect_kernel_ms_per_step": sum(fx_ms) / K,
+                  "note": "per-pass spans are event-to-event on their own stream; the three passes overlap across time blocks"}
+        fma_src = ("derived: SMs x 128 lanes x 2 x clocks.max.sm (MEASURED_PEAKS.json holds only HBM and bf16 tensor peaks)")
+        if args.workload == "sinc":
+            # dominant kernel: sinc_kernel. Algorithmic work = output frames x source channels x 4 x 256 FMA (2048 flop)
+            flops = sinc_frames * 1 * 2048.0
+            t = sum(sinc_ms) / 1e3
+            ach = flops / t / 1e12
+            smem_bytes = sinc_frames * 258 * (4 + 1) * 4.0   # what any one-coefficient-read-per-output mapping must move
+            roofline = {"bound": "fp32_fma", "kernel": "sinc_kernel", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s",
+                        "frac": ach / fma_peak, "traffic": None, "peak_source": fma_src,
+                        "sinc_kernel_ms_per_step": sum(sinc_ms) / K, "output_frames_per_step": sinc_frames / K,
+                        "shared_memory_gbs": smem_bytes / t / 1e9,
+                        "shared_memory_peak_gbs": torch.cuda.get_device_properties(device).multi_processor_count * 128 * 1.965,
+                        "shared_memory_note": "the kernel is bound by the shared-memory pipe (128 B/clk/SM): 258 x (4 + channels) "
+                                              "words per output against 258 x 4 x channels FFMA caps a mono source at 20 % of the FP32 pipe",
+                        **passes}
+        elif args.workload == "cfg4":
+            # dominant kernel: grain_kernel. Algorithmic traffic = 8 B contribution written + 8 B read back per grain sample
+            byts = grain_samples * 16.0
+            t = sum(grain_ms) / 1e3
+            ach = byts / t / 1e9
+            roofline = {"bound": "hbm", "kernel": "grain_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                        "grain_kernel_ms_per_step": sum(grain_ms) / K, "grain_samples_per_step": grain_samples / K,
+                        "note2": "one thread per grain runs the grain's serial f64 recurrences: latency-bound today", **passes}
+        else:
+            # dominant kernel: replay_kernel. Algorithmic work = active voice-frames x 2 channels x 25 flop
+            flops = (total_vframes / world) * 2 * FLOP_PER_CHANNEL_SAMPLE
+            ach = flops / (total_voice_ms / 1e3) / 1e12
+            roofline = {"bound": "fp32_fma", "kernel": "replay_kernel", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s",
+                        "frac": ach / fma_peak, "traffic": None,
+                        "peak_source": fma_src + "; voices share one L2-resident buffer so the kernel is not HBM bound",
+                        "hbm_achieved_gbs": (total_vframes / world) * 8.0 / (total_voice_ms / 1e3) / 1e9,
+                        "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_kind": peak_kind, **passes}
         line = {"metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": total_dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

@@ -294,6 +294,10 @@ typedef struct pb200_render_stats {
   double effect_kernel_ms; /* mixer/effect kernels */
   uint64_t kernel_launches;
   uint64_t voice_frames;   /* active voice-frames rendered */
+  double sinc_kernel_ms;   /* HighQuality resampler kernel (part of the voice_kernel_ms span) */
+  double grain_kernel_ms;  /* granular grain kernel (part of the voice_kernel_ms span) */
+  uint64_t sinc_frames;    /* resampler output frames the sinc kernel materialised */
+  uint64_t grain_samples;  /* grain samples the grain kernel rendered */
 } pb200_render_stats;
 PB200_API int pb200_last_render_stats(pb200_renderer *r, pb200_render_stats *st);
 

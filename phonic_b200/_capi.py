@@ -111,7 +111,8 @@ class VoiceState(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("device_ms", F64), ("voice_kernel_ms", F64), ("skeleton_kernel_ms", F64), ("effect_kernel_ms", F64),
-                ("kernel_launches", U64), ("voice_frames", U64)]
+                ("kernel_launches", U64), ("voice_frames", U64), ("sinc_kernel_ms", F64), ("grain_kernel_ms", F64),
+                ("sinc_frames", U64), ("grain_samples", U64)]
 
 
 # every symbol include/phonic_b200.h declares: name -> (restype, argtypes)

@@ -183,6 +183,7 @@ struct pb200_renderer {
   DevVec<float> d_sinc_tables, d_hq_scratch;
   DevVec<HqRec> d_hq_recs;
   DevVec<uint32_t> d_hq_nrecs;
+  DevVec<unsigned long long> d_hq_frames;
   DevVec<GranGroup> d_gran_groups;
   DevVec<GranState> d_gran_states;
   DevVec<GrainRec> d_grain_recs;
@@ -492,7 +493,7 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sr_) cudaStreamSynchronize(r->sr_);
   if (r->sm) cudaStreamSynchronize(r->sm);
   for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
-  r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
+  r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
   r->d_gran_groups.free(); r->d_gran_states.free(); r->d_grain_recs.free(); r->d_gran_counters.free(); r->d_gran_vrec.free();
   r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry.free(); r->d_grain_luts.free();
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
@@ -1186,6 +1187,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(r->d_hq_recs.reserve((size_t)RING * hq_cap));
     CUDA_TRY(r->d_hq_nrecs.reserve(std::max<size_t>(RING, (size_t)n_blocks)));
     CUDA_TRY(r->d_hq_scratch.reserve((size_t)RING * n_hq * tb * 2));
+    CUDA_TRY(r->d_hq_frames.reserve(1));
+    CUDA_TRY(cudaMemsetAsync(r->d_hq_frames.p, 0, sizeof(unsigned long long), r->sv));
     CUDA_TRY(cudaMemsetAsync(r->d_hq_nrecs.p, 0, std::max<size_t>(RING, (size_t)n_blocks) * sizeof(uint32_t), r->sv));
     CUDA_TRY(cudaFuncSetAttribute(sinc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SINC_SMEM));
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, r->device);
@@ -1224,6 +1227,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   }
 
   std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r1(n_blocks), ev_m1(n_blocks);
+  std::vector<cudaEvent_t> ev_x((n_hq || n_rows) ? 3 * (size_t)n_blocks : 0);  // grain begin / grain end = sinc begin / sinc end
+  for (auto& e : ev_x) CUDA_TRY(DevicePool::get().event(&e));
   for (uint32_t b = 0; b < n_blocks; ++b) {
     CUDA_TRY(DevicePool::get().event(&ev_v0[b])); CUDA_TRY(DevicePool::get().event(&ev_v1[b]));
     CUDA_TRY(DevicePool::get().event(&ev_r1[b])); CUDA_TRY(DevicePool::get().event(&ev_m1[b]));
@@ -1234,6 +1239,12 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_start, 0));
   uint64_t launches = 0;
+  // PB200_SKEL_PROF=<file>: per-voice cycle counters of the skeleton pass (debug aid)
+  unsigned long long* prof_buf = nullptr;
+  if (getenv("PB200_SKEL_PROF")) {
+    CUDA_TRY(cudaMalloc((void**)&prof_buf, nvoices * 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(prof_buf, 0, nvoices * 4 * sizeof(unsigned long long)));
+  }
 
   for (uint32_t b = 0; b < n_blocks; ++b) {
     const uint64_t b0 = p0 + (uint64_t)b * tb;
@@ -1278,6 +1289,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       va.gran.block_frames = blen;  // grains stop at the end of what this block really renders: their carry is taken there
       CUDA_TRY(cudaMemsetAsync(va.gran.tile_range, 0xFF, (size_t)n_rows * n_tiles * 2 * sizeof(uint32_t), r->sv));
     }
+    va.prof = prof_buf;
     va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
     for (size_t ci = 0; ci < c.classes.size(); ++ci) {
       const SizeClass& sc = c.classes[ci];
@@ -1303,6 +1315,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ra.hq_scratch = n_hq ? r->d_hq_scratch.p + (size_t)slot * n_hq * tb * 2 : nullptr;
     ra.gran_groups = va.gran_groups;
     std::memset(&ra.gran, 0, sizeof(ra.gran));
+    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b], r->sr_));
     if (n_rows) {  // every grain's contribution to this block
       GrainArgs ga;
       ga.recs = va.gran.recs; ga.counters = va.gran.counters; ga.rec_cap = gran_rec_cap; ga.buffers = r->d_buffers.p;
@@ -1317,9 +1330,11 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       ra.gran.recs = ga.recs; ra.gran.vrec = va.gran.vrec; ra.gran.tile_range = va.gran.tile_range; ra.gran.storage = ga.storage;
       ra.gran.rec_cap = gran_rec_cap; ra.gran.vrec_cap = gran_vrec_cap; ra.gran.n_tiles = n_tiles; ra.gran.storage_cap = ga.storage_cap;
     }
+    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b + 1], r->sr_));
     if (n_hq) {  // materialise the resampler output this block consumes: one launch per filter table
       SincArgs sa;
       sa.recs = va.hq_recs; sa.n_recs = va.hq_n_recs; sa.cap = hq_cap; sa.buffers = r->d_buffers.p;
+      sa.frames_out = r->d_hq_frames.p;
       sa.tables = r->d_sinc_tables.p; sa.scratch = r->d_hq_scratch.p + (size_t)slot * n_hq * tb * 2; sa.block_frames = tb;
       const uint32_t n_tables = std::max<uint32_t>(1, (uint32_t)r->sinc_table_keys.size());
       for (uint32_t t = 0; t < n_tables; ++t) {
@@ -1328,6 +1343,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
         ++launches;
       }
     }
+    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b + 2], r->sr_));
     const uint32_t live_tiles = (blen + TILE - 1) / TILE;
     for (size_t ci = 0; ci < c.classes.size(); ++ci) {
       const SizeClass& sc = c.classes[ci];
@@ -1367,6 +1383,16 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaStreamSynchronize(r->sv));
   CUDA_TRY(cudaGetLastError());
 
+  if (prof_buf) {
+    std::vector<unsigned long long> h(nvoices * 4);
+    cudaMemcpy(h.data(), prof_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(prof_buf);
+    if (FILE* f = fopen(getenv("PB200_SKEL_PROF"), "w")) {
+      fprintf(f, "voice,total_cycles,simple_cycles,general_cycles,frames\n");
+      for (size_t i = 0; i < nvoices; ++i) fprintf(f, "%zu,%llu,%llu,%llu,%llu\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      fclose(f);
+    }
+  }
   float ms = 0;
   r->stats = pb200_render_stats{};
   cudaEventElapsedTime(&ms, ev_start, ev_end);
@@ -1378,6 +1404,11 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     DevicePool::get().release_event(ev_v0[b]); DevicePool::get().release_event(ev_v1[b]);
     DevicePool::get().release_event(ev_r1[b]); DevicePool::get().release_event(ev_m1[b]);
   }
+  for (uint32_t b = 0; b < n_blocks && !ev_x.empty(); ++b) {
+    cudaEventElapsedTime(&ms, ev_x[3 * (size_t)b], ev_x[3 * (size_t)b + 1]); r->stats.grain_kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ev_x[3 * (size_t)b + 1], ev_x[3 * (size_t)b + 2]); r->stats.sinc_kernel_ms += ms;
+  }
+  for (auto& e : ev_x) DevicePool::get().release_event(e);
   DevicePool::get().release_event(ev_start); DevicePool::get().release_event(ev_end);
   r->stats.kernel_launches = launches;
   if (n_hq) {
@@ -1385,6 +1416,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(cudaMemcpy(counts.data(), r->d_hq_nrecs.p, n_blocks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (uint32_t c2 : counts)
       if (c2 > hq_cap) return fail(r, PB200_ERR_CUDA, "HighQuality chunk record list overflowed");
+    unsigned long long fo = 0;
+    CUDA_TRY(cudaMemcpy(&fo, r->d_hq_frames.p, sizeof(fo), cudaMemcpyDeviceToHost));
+    r->stats.sinc_frames = fo;
   }
   if (n_rows) {
     std::vector<uint32_t> counts(2 * (size_t)n_blocks);
@@ -1392,6 +1426,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     for (uint32_t b = 0; b < n_blocks; ++b)
       if (counts[2 * b] > gran_rec_cap || counts[2 * b + 1] > gran_storage_cap)
         return fail(r, PB200_ERR_CUDA, "granular record list / grain storage overflowed");
+    for (uint32_t b = 0; b < n_blocks; ++b) r->stats.grain_samples += counts[2 * b + 1];
   }
   r->host_state_valid = false;
   r->position = p1;

@@ -40,6 +40,7 @@ struct SincArgs {
   uint32_t block_frames;
   uint32_t table;          // the table this launch serves
   uint32_t do_copies;      // also serve the bypass (copy) records
+  unsigned long long* frames_out;  // statistics: output frames materialised
 };
 
 PB_DEV float sinc_interp_cubic(float x, float y0, float y1, float y2, float y3) {
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(SINC_THREADS, 1) sinc_kernel(SincArgs a) {
       uint32_t acc = 0;
       for (int i = 0; i < SINC_NB; ++i) { s_pref[i] = acc; acc += s_rec[i].count; }
       s_pref[SINC_NB] = acc;
+      if (acc) atomicAdd(a.frames_out, (unsigned long long)acc);
     }
     // stage SincFixedIn's buffer of every sinc record: [chunk k-2 | chunk k-1 | chunk k], planar, zero filled
     for (uint32_t i = tid; i < SINC_NB * SINC_WIN; i += SINC_THREADS) {

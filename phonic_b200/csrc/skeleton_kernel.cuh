@@ -50,6 +50,7 @@ struct SkeletonArgs {
   const GranGroup* gran_groups;       // [n_groups] or nullptr when the graph has no granular sampler
   GranState* gran_states;             // [n_gran_rows]
   GranEmit gran;
+  unsigned long long* prof;           // PB200_SKEL_PROF: [n_voices][4] cycles (total, simple calls, general calls, frames)
   uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores, 2 = no simple calls
 };
 
@@ -109,7 +110,8 @@ PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t fr
 // 32-byte TileRec stored at every tile boundary crossed instead of a full Segment.
 template <int CC>
 PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const DevBuffer& buf, uint32_t n,
-                        uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen) {
+                        uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen,
+                        unsigned long long* prof_phase = nullptr, uint32_t debug_flags = 0) {
   cc.call_left = cc.chunk_left;
   loop_range_samples(v, buf, cc.ls, cc.le);
   cc.new_call = false;
@@ -121,7 +123,9 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
   }
   const float ratio = v.ratio;
   const bool env = gp.has_env && cc.env_per_frame;
-  float s = v.sub_pos;
+  float s = v.sub_pos, p = 0.0f;
+  const PhaseK pk = phase_consts(ratio);  // the ratio is constant for the whole call
+  bool first = true;
   uint32_t np = 0, off = call_off, remaining = n;
   uint32_t piece = min(remaining, TILE - (off % TILE));
   for (;;) {
@@ -131,15 +135,19 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
       bool on_hold;
       if (env_bare_steps(v, gp, d, on_hold) >= piece) {  // the stage cannot end inside this piece: ride along
         float o = on_hold ? v.env_hold : v.env_out;
-        np += phase_run<true>(s, ratio, piece, o, d);
+        np += phase_piece<true>(s, p, pk, piece, first, o, d);
         if (on_hold) v.env_hold = o; else v.env_out = o;
         fused = true;
       }
     }
     if (!fused) {
-      np += phase_run(s, ratio, piece);
+      const long long c0 = prof_phase ? clock64() : 0;
+      float o_unused = 0.0f;
+      if (!(debug_flags & 4u)) np += phase_piece<false>(s, p, pk, piece, first, o_unused, 0.0f);
+      if (prof_phase) *prof_phase += clock64() - c0;
       if (env) env_chain(v, gp, piece);
     }
+    first = false;
     off += piece; remaining -= piece;
     if (remaining == 0) break;
     piece = min(remaining, TILE);
@@ -250,9 +258,12 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
 
   // One Source::write call of this thread's voice (already opened by voice_begin_call): emits the call's
   // Segment / TileRec checkpoints and advances the control state. Returns the frames written.
+  unsigned long long prof_simple = 0, prof_general = 0, prof_phase = 0;
+  const long long prof_t0 = a.prof ? clock64() : 0;
   auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) -> uint32_t {
     uint32_t written_frames = 0;
     bool simple = false;
+    const long long prof_c0 = a.prof ? clock64() : 0;
     if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq && !is_gran)
       simple = buf.channels == 2 ? simple_call_ok<2>(v, cc, buf, n) : simple_call_ok<1>(v, cc, buf, n);
     if (simple) {
@@ -266,8 +277,8 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
         cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
       }
       cur_cnt++;
-      if (buf.channels == 2) simple_call<2>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
-      else simple_call<1>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
+      if (buf.channels == 2) simple_call<2>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen, a.prof ? &prof_phase : nullptr, a.debug_flags);
+      else simple_call<1>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen, a.prof ? &prof_phase : nullptr, a.debug_flags);
       n_segs++;
       written_frames = n;
     } else {
@@ -293,7 +304,14 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
           w = seg_len;
           cc.chunk_left -= w; cc.hq_off += w;
           if (gp.has_env && cc.env_per_frame) env_chain(v, gp, w);
-        } else if (is_hq) w = buf.channels == 2 ? hq_advance<2>(v, cc, hqp, hq_em, buf, comp, seg_len) : hq_advance<1>(v, cc, hqp, hq_em, buf, comp, seg_len);
+        } else if (is_hq) {
+          // the out-of-line HighQuality state machine works on copies: taking the address of `v` / `cc` themselves
+          // would move the hot cubic path's voice state from registers to local memory
+          VoiceState vt = v;
+          CallCtx ct = cc;
+          w = buf.channels == 2 ? hq_advance<2>(vt, ct, hqp, hq_em, buf, comp, seg_len) : hq_advance<1>(vt, ct, hqp, hq_em, buf, comp, seg_len);
+          v = vt; cc = ct;
+        }
         else if (buf.channels == 2) w = voice_advance<2>(v, cc, gp, buf, out_rate, comp, seg_len);
         else w = voice_advance<1>(v, cc, gp, buf, out_rate, comp, seg_len);
         written_frames += w;
@@ -303,6 +321,7 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
     }
     my_frames += written_frames;
     voice_end_call(v, cc, t + n);
+    if (a.prof) { if (simple) prof_simple += clock64() - prof_c0; else prof_general += clock64() - prof_c0; }
     return written_frames;
   };
   // generator-level gain / pan (player.rs:1075-1081) of one call: checkpoint per (call x tile), advance ramps (thread 0)
@@ -572,6 +591,10 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   if (mine && cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
   if (tid == 0 && gcur_tile != 0xFFFFFFFFu) { g_first[gcur_tile] = (uint16_t)gcur_first; g_count[gcur_tile] = (uint16_t)gcur_cnt; }
   if (mine) a.voices[gp.first_voice + tid] = v;
+  if (a.prof && mine) {
+    unsigned long long* pr = a.prof + (size_t)(gp.first_voice + tid) * 4;
+    pr[0] += prof_phase; pr[1] += prof_simple; pr[2] += prof_general; pr[3] += my_frames;
+  }
   if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
   __syncthreads();
   if (tid == 0) a.gstate[g] = s_gs;

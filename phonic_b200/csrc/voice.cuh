@@ -460,81 +460,156 @@ PB_DEV void voice_end_call(VoiceState& v, CallCtx& c, uint64_t call_end_frame) {
   }
 }
 
-// 1.0f / 0.0f comparison results in a register (SASS FSET.BF): keeps the phase recurrences free of the
-// long predicate-to-consumer latency, which is what bounds the single-warp skeleton chains
-PB_DEV float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
-PB_DEV float fset_lt(float a, float b) { float d; asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+// Comparison results as 1.0f / 0.0f computed on the FMA pipe: [s >= x] = sat((s - pred(x)) * 2^60) as ONE
+// FFMA.SAT (the product and the difference are exact before the single rounding, so the sign is that of
+// s - pred(x); a positive difference is at least one ulp >= 2^-60 for |x| >= 2^-36). The skeleton's phase chains
+// are single-warp dependent chains: FSET / predicates sit on another pipe and cost ~2x the forwarding latency.
+constexpr float STEP_K = 1152921504606846976.0f;  // 2^60
+PB_DEV float fma_sat(float a, float b, float c) { float d; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+PB_DEV float f32_pred(float x) { return __int_as_float(__float_as_int(x) - 1); }  // x > 0
+PB_DEV float f32_succ(float x) { return __int_as_float(__float_as_int(x) + 1); }  // x > 0
+// w such that step(s, w) = [s >= x] for x > 0
+PB_DEV float step_weight(float x) { return -(f32_pred(x) * STEP_K); }
+PB_DEV float step(float s, float w) { return fma_sat(s, STEP_K, w); }
+PB_DEV float fset_ge(float a, float b) { return step(a, step_weight(b)); }                               // b > 0
+PB_DEV float fset_lt(float a, float b) { return fma_sat(a, -STEP_K, b * STEP_K); }                       // a, b >= 1
 
-// The resampler's f32 phase recurrence for `span` output frames on the fast path (no input exhaustion
-// possible, 0 < ratio < 64, not the bypass ratio): advances sub_pos exactly as CubicInterpolator::process
-// does (cubic.rs:72-110) and returns how many input frames were pushed.
-// ACC additionally runs an independent `o += d` chain (an envelope stage's bare accumulate) in the latency
-// shadow of the phase chain.
-template <bool ACC>
-PB_DEV uint32_t phase_run(float& s, const float ratio, const uint32_t span, float& o, const float d) {
-  uint32_t np = 0;
+// ---- the resampler's f32 phase recurrence on the fast path -----------------------------------------------------------
+// (no input exhaustion possible, 0 < ratio < 64, not the bypass ratio): sub_pos advances exactly as
+// CubicInterpolator::process does (cubic.rs:72-110). Everything that only depends on the ratio is resolved once
+// (PhaseK); a run of pieces with the same ratio (one simple call) carries (s, p) from piece to piece.
+//
+// ratio < 1 (cubic.rs:73-89): per frame p = [s >= 1]; s = (s - p) + ratio (`- 1.0` and `- 0.0` are exact). The push
+// flag of the NEXT frame is a function of this frame's s alone, because fl() is monotone:
+//   p' = [fl(s + ratio) >= 1] = [s >= thrA]            if s < 1   (p = 0)
+//   p' = [fl((s - 1) + ratio) >= 1] = [s >= thrB]      if s >= 1  (p = 1)
+// with thrA < 1 < thrB the smallest such floats, i.e. p' = [thrA <= s < 1] + [s >= thrB]; for ratio < 0.499 the second
+// term never fires (s < 1 + ratio < thrB). The flag is computed one frame ahead, off the s -> (s - p) -> (+ ratio)
+// chain (tests/test_phase_lookahead.py). The first frame of a run is taken literally: right after a ratio change s
+// may still exceed 1 + ratio.
+//
+// ratio >= 1 (cubic.rs:94-105): `while sub_pos < ratio { push; sub_pos += 1.0 }; sub_pos -= ratio`. With sub_pos in
+// [0,1) at frame start the trip count is n0 = floor(ratio) or n0 + 1. Repeated f32 `+= 1.0` only rounds when the sum
+// enters a new binade ([1,2), [2,4), [4,8), ...) and is exact inside one, so t_n = sub_pos after n pushes has the
+// closed form t_n = fl(fl(fl(fl(s + a1) + a2) + a3) + a4), a = (min(n,1), min(n-1,2), min(n-3,4), min(n-7,8))
+// (bit-identical to the sequential adds; tests/test_phase_closed_form.py). Integer ratios (the one case where
+// t_{n0-1} can reach `ratio`) and ratio >= 14 take the literal loop.
+//
+// Pushes are not counted per frame: s_out = s_in -/+ (pushes - span * ratio) up to the recurrence's own rounding
+// errors (< 1e-3 per piece), so the count is the nearest integer of that difference in f64.
+struct PhaseK {
+  float ratio, w1, wA, wB, wR;
+  float a2, a3, a4;
+  int mode;  // 0: ratio < 0.499   1: ratio < 1   2: ratio >= 1, closed form   3: literal loop
+  int nm;    // floor(ratio) - 1
+};
+
+PB_DEV PhaseK phase_consts(const float ratio) {
+  PhaseK k;
+  k.ratio = ratio;
+  k.w1 = step_weight(1.0f);
+  k.wA = k.wB = k.wR = 0.0f; k.a2 = k.a3 = k.a4 = 0.0f; k.nm = 0;
   if (ratio < 1.0f) {
-    // if sub_pos >= 1 { push; sub_pos -= 1 }; sub_pos += ratio  (cubic.rs:73-89): `- 1.0` and `- 0.0` are both
-    // exact, so the branch becomes a subtract of the comparison result; pushes are counted off the chain
-    float pushes = 0.0f;
-#pragma unroll 4
-    for (uint32_t f = 0; f < span; ++f) {
-      const float p = fset_ge(s, 1.0f);
-      s = s - p;
-      pushes += p;
-      s += ratio;
-      if (ACC) o += d;
+    float thrA = 1.0f - ratio;
+    while (f32_pred(thrA) + ratio >= 1.0f) thrA = f32_pred(thrA);
+    while (thrA + ratio < 1.0f) thrA = f32_succ(thrA);
+    k.wA = step_weight(thrA);
+    k.mode = 0;
+    if (!(ratio < 0.499f)) {
+      float thrB = 2.0f - ratio;
+      while ((f32_pred(thrB) - 1.0f) + ratio >= 1.0f) thrB = f32_pred(thrB);
+      while ((thrB - 1.0f) + ratio < 1.0f) thrB = f32_succ(thrB);
+      k.wB = step_weight(thrB);
+      k.mode = 1;
     }
-    np = (uint32_t)pushes;
   } else {
-    // `while sub_pos < ratio { push; sub_pos += 1.0 }; sub_pos -= ratio` (cubic.rs:94-105).
-    // With sub_pos in [0,1) at frame start the trip count is n0 = floor(ratio) or n0 + 1. Repeated
-    // f32 `+= 1.0` only rounds when the sum enters a new binade ([1,2), [2,4), [4,8), ...) and is
-    // exact inside one, so t_n = sub_pos after n pushes has the closed form
-    //   t_n = fl(fl(fl(fl(s + a1) + a2) + a3) + a4),  a = (min(n,1), min(n-1,2), min(n-3,4), min(n-7,8))
-    // (bit-identical to the sequential adds; validated exhaustively in tests/test_phase_closed_form.py).
-    // Each frame is then a short FADD chain plus the reference's own exit test; anything unusual
-    // (sub_pos >= 1 after a ratio change, integer ratios) takes the literal loop.
     const int n0 = (int)ratio;
-    const int nm = n0 - 1;
-    const float a1 = (float)min(max(nm, 0), 1), a2 = (float)min(max(nm - 1, 0), 2);
-    const float a3 = (float)min(max(nm - 3, 0), 4), a4 = (float)min(max(nm - 7, 0), 8);
-    // integer ratios are the one case where t_{n0-1} can reach `ratio`: leave them to the literal loop
-    const bool closed_ok = ratio < 14.0f && ratio != (float)n0;
-    uint32_t f = 0;
-    // first frame (sub_pos may be >= 1 right after a ratio change) and unsupported ratios: literal loop
-    const uint32_t literal = closed_ok ? (s < 1.0f ? 0u : 1u) : span;
-    for (; f < literal && f < span; ++f) {
-      while (s < ratio) { s += 1.0f; ++np; }
+    k.nm = n0 - 1;
+    k.a2 = (float)min(max(k.nm - 1, 0), 2); k.a3 = (float)min(max(k.nm - 3, 0), 4); k.a4 = (float)min(max(k.nm - 7, 0), 8);
+    k.wR = ratio * STEP_K;
+    k.mode = (ratio < 14.0f && ratio != (float)n0) ? 2 : 3;
+  }
+  return k;
+}
+
+// `span` frames. `first`: this is the first piece of a run with this ratio (p is not valid yet).
+// ACC additionally runs an independent `o += d` chain (an envelope stage's bare accumulate) in the latency shadow.
+template <bool ACC>
+PB_DEV uint32_t phase_piece(float& s, float& p, const PhaseK& k, const uint32_t span, const bool first, float& o, const float d) {
+  if (span == 0) return 0u;
+  const float ratio = k.ratio;
+  const float s_in = s;
+  uint32_t f = 0;
+  if (k.mode <= 1) {
+    if (first) {  // frame 0 and the flag of frame 1, literally
+      p = step(s, k.w1);
+      s = (s - p) + ratio;
+      if (ACC) o += d;
+      p = step(s, k.w1);
+      f = 1;
+    }
+    const float w1 = k.w1, wA = k.wA;
+    if (k.mode == 0) {
+#pragma unroll 4
+      for (; f < span; ++f) {
+        const float pn = step(s, wA) - step(s, w1);
+        s = (s - p) + ratio;
+        p = pn;
+        if (ACC) o += d;
+      }
+    } else {
+      const float wB = k.wB;
+#pragma unroll 4
+      for (; f < span; ++f) {
+        const float pn = (step(s, wA) - step(s, w1)) + step(s, wB);
+        s = (s - p) + ratio;
+        p = pn;
+        if (ACC) o += d;
+      }
+    }
+    return (uint32_t)__double2int_rn(((double)s_in - (double)s) + (double)span * (double)ratio);
+  }
+  if (k.mode == 2) {
+    if (first && !(s < 1.0f)) {  // sub_pos may be >= 1 right after a ratio change: one literal frame
+      while (s < ratio) s += 1.0f;
       s -= ratio;
       if (ACC) o += d;
+      f = 1;
     }
     // from here on sub_pos = t - ratio with t in [ratio, ratio + 1): always in [0, 1)
-    float extra_f = 0.0f;  // frames that needed n0 + 1 pushes
-#define PB_PHASE_LOOP(TM_EXPR)                                   \
-    for (; f < span; ++f) {                                  \
-      const float tm = (TM_EXPR);                            \
-      const float t0 = tm + 1.0f;                            \
-      const float more = fset_lt(t0, ratio);                 \
-      const float t = t0 + more; /* + 0.0 is exact */        \
-      extra_f += more;                                       \
-      s = t - ratio;                                         \
-      if (ACC) o += d;                                       \
+    const float wR = k.wR;
+#define PB_PHASE_LOOP(TM_EXPR)                                       \
+    for (; f < span; ++f) {                                      \
+      const float tm = (TM_EXPR);                                \
+      const float t0 = tm + 1.0f;                                \
+      const float more = fma_sat(t0, -STEP_K, wR); /* [t0 < ratio] */ \
+      const float t = t0 + more; /* + 0.0 is exact */            \
+      s = t - ratio;                                             \
+      if (ACC) o += d;                                           \
     }
+    const int nm = k.nm;
     if (nm <= 0) { PB_PHASE_LOOP(s) }
     else if (nm == 1) { PB_PHASE_LOOP(s + 1.0f) }
-    else if (nm <= 3) { PB_PHASE_LOOP((s + 1.0f) + a2) }
-    else if (nm <= 7) { PB_PHASE_LOOP(((s + 1.0f) + 2.0f) + a3) }
-    else { PB_PHASE_LOOP((((s + 1.0f) + 2.0f) + 4.0f) + a4) }
+    else if (nm <= 3) { PB_PHASE_LOOP((s + 1.0f) + k.a2) }
+    else if (nm <= 7) { PB_PHASE_LOOP(((s + 1.0f) + 2.0f) + k.a3) }
+    else { PB_PHASE_LOOP((((s + 1.0f) + 2.0f) + 4.0f) + k.a4) }
 #undef PB_PHASE_LOOP
-    np += (span - min(literal, span)) * (uint32_t)n0 + (uint32_t)extra_f;
-    (void)a1;
+    return (uint32_t)__double2int_rn(((double)s - (double)s_in) + (double)span * (double)ratio);
+  }
+  uint32_t np = 0;
+  for (; f < span; ++f) {
+    while (s < ratio) { s += 1.0f; ++np; }
+    s -= ratio;
+    if (ACC) o += d;
   }
   return np;
 }
+
+// One piece on its own (the ratio may change from piece to piece: pitch glides)
 PB_DEV uint32_t phase_run(float& s, const float ratio, const uint32_t span) {
-  float o = 0.0f;
-  return phase_run<false>(s, ratio, span, o, 0.0f);
+  float o = 0.0f, p = 0.0f;
+  const PhaseK k = phase_consts(ratio);
+  return phase_piece<false>(s, p, k, span, true, o, 0.0f);
 }
 
 // How many frames the current envelope stage can run as a bare chain of the reference's own f32 accumulate

@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from .player import (AhdsrParameters, ChorusEffect, CompressorEffect, DelayEffect, Eq5Effect, FilePlaybackOptions,
-                     FilterEffect, GeneratorPlaybackOptions, Player, ReverbEffect)
+                     FilterEffect, GeneratorPlaybackOptions, GranularParameters, Player, ReverbEffect)
 
 
 def speed_from_note(note: int) -> float:
@@ -146,3 +146,45 @@ def add_main_bus_sends(player: Player):
     """cfg5: Delay (375 ms, fb 0.5 = DelayEffect::new() defaults) + Reverb on the main bus."""
     player.add_effect(DelayEffect())
     player.add_effect(ReverbEffect(0.6, 0.35))
+
+
+def build_cfg4(player: Player, voices: int = 160, voices_per_sampler: int = 8, time_scale: float = 1.0, seed: int = 4):
+    """cfg4: granular synthesis, 16k grains/s: a pad-ambient.wav-shaped mono buffer (362 835 frames
+    @ 48 kHz, loop 286 619..362 834), `voices` voices x density 100 Hz x size 100 ms, Hann, Forward, step 1.0, no
+    randomisation. Notes as in cfg2 (on in [0, 2 s), off in [6, 8 s)), AHDSR (10 ms, 0, 500 ms, 0.75, 1 s)."""
+    frames = 362835
+    buf = synth_buffer(frames, 48000, seed=seed)
+    bid = player.upload_buffer(buf, 48000, loop_range=(286619, 362834))
+    rng = np.random.default_rng(seed + 1)
+    ahdsr = AhdsrParameters(attack=0.01, hold=0.0, decay=0.5, sustain=0.75, release=1.0)
+    gran = GranularParameters(window=0, size=100.0, density=100.0, position=0.1, step=1.0)
+    gain = 1.0 / math.sqrt(max(voices, 1)) / 3.0
+    handles = []
+    remaining = voices
+    while remaining > 0:
+        nv = min(voices_per_sampler, remaining)
+        remaining -= nv
+        h = player.add_generator(bid, GeneratorPlaybackOptions(voices=nv), ahdsr, granular=gran)
+        handles.append(h)
+        for _ in range(nv):
+            note = int(rng.integers(48, 73))
+            t_on = int(rng.uniform(0.0, 2.0 * time_scale) * 48000)
+            nid = h.note_on(note, volume=gain, panning=float(rng.uniform(-0.8, 0.8)), sample_time=t_on)
+            h.note_off(nid, sample_time=int(rng.uniform(6.0, 8.0) * time_scale * 48000))
+    return handles
+
+
+def build_sinc_bank(player: Player, voices: int = 1024, buffer=None, seed: int = 5):
+    """cfg4's sinc micro-benchmark: `voices` HighQuality file sources, 44.1 -> 48 kHz, looping over
+    the whole 4 s buffer so that every voice resamples for the full render; start times spread over 100 ms."""
+    buf = buffer if buffer is not None else synth_buffer(int(4.0 * 44100), 44100, seed=1)
+    frames = buf.shape[0]
+    bid = player.upload_buffer(buf, 44100)
+    rng = np.random.default_rng(seed)
+    gain = 1.0 / math.sqrt(max(voices, 1))
+    hs = []
+    for _ in range(voices):
+        o = FilePlaybackOptions(volume=gain, panning=float(rng.uniform(-0.8, 0.8)), loop_range=(0, frames), resampling_quality=1)
+        o.repeat_forever()
+        hs.append(player.play_file_source(bid, o, start_time=int(rng.integers(0, 4800))))
+    return hs
