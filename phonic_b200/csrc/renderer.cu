@@ -2,6 +2,7 @@
 // include/phonic_b200.h. No CPU fallback: every render path launches the kernels of this unit.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -102,11 +103,33 @@ struct DevVec {  // grow-only device array backed by the pool
 };
 
 // generation tags of TileRec records: unique per skeleton launch in this process, never 0
+uint32_t next_generation();
+// `n` consecutive generation tags (none of them 0)
+uint32_t reserve_generations(uint32_t n) {
+  for (;;) {
+    uint32_t first = next_generation();
+    bool ok = true;
+    for (uint32_t i = 1; i < n; ++i) { uint32_t g = next_generation(); if (g != first + i) { ok = false; break; } }
+    if (ok && first + n > first) return first;
+  }
+}
 uint32_t next_generation() {
   static std::atomic<uint32_t> g{0};
   uint32_t v = g.fetch_add(1) + 1;
   if (v == 0) v = g.fetch_add(1) + 1;
   return v;
+}
+
+// cuStreamWaitValue32 through the runtime's driver entry point query (no link-time dependency on libcuda)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+  static StreamWaitValue32Fn fn = []() -> StreamWaitValue32Fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (StreamWaitValue32Fn)p;
+  }();
+  return fn;
 }
 
 struct HostBuffer { DevBuffer dev; size_t cls; };
@@ -209,6 +232,7 @@ struct pb200_renderer {
   DevVec<GroupSeg> d_gsegs;
   DevVec<uint16_t> d_seg_first, d_seg_count, d_gseg_first, d_gseg_count;
   DevVec<TileRec> d_recs;
+  DevVec<uint32_t> d_block_done;
   cudaStream_t sr_ = nullptr;  // replay stream
   DevVec<uint8_t> d_group_flags, d_mixer_flags;
   DevVec<ExpSm> d_master;
@@ -493,7 +517,7 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sr_) cudaStreamSynchronize(r->sr_);
   if (r->sm) cudaStreamSynchronize(r->sm);
   for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
-  r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
+  r->d_block_done.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
   r->d_gran_groups.free(); r->d_gran_states.free(); r->d_grain_recs.free(); r->d_gran_counters.free(); r->d_gran_vrec.free();
   r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry.free(); r->d_grain_luts.free();
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
@@ -1157,17 +1181,37 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   const uint32_t seg_cap = n_tiles + max_chunks + 8;
   if (seg_cap >= 65535) return fail(r, PB200_ERR_UNSUPPORTED, "too many chunk boundaries in one time block");
   const size_t nvoices = std::max<size_t>(1, r->h_voices.size());
-  CUDA_TRY(r->d_segs.reserve((size_t)RING * nvoices * seg_cap));
-  CUDA_TRY(r->d_gsegs.reserve(std::max<size_t>(1, (size_t)RING * ng * seg_cap)));
-  CUDA_TRY(r->d_seg_first.reserve((size_t)RING * nvoices * n_tiles));
-  CUDA_TRY(r->d_seg_count.reserve((size_t)RING * nvoices * n_tiles));
+  // Persistent skeleton (small graphs): ONE launch walks all time blocks, every group at its own pace, and hands
+  // block b to the replay pass through a counter the replay stream waits on (cuStreamWaitValue32). Needs every
+  // skeleton CTA resident at once, one size class, a snapshot slot per block (no ring re-use, so the kernel never
+  // has to wait for a consumer) and no HighQuality / granular voices (their per-block lists are host-managed).
+  int sm_count_all = 0;
+  cudaDeviceGetAttribute(&sm_count_all, cudaDevAttrMultiProcessorCount, r->device);
+  bool persistent = n_blocks > 1 && r->n_hq == 0 && r->n_gran_rows == 0 && c.classes.size() == 1 &&
+                    c.classes[0].groups.size() <= (size_t)sm_count_all && !getenv("PB200_NO_PERSISTENT") &&
+                    !getenv("PB200_SKEL_PROF") && stream_wait_value32() != nullptr;
+  if (persistent) {
+    const size_t bytes = (size_t)n_blocks * (nvoices * ((size_t)seg_cap * sizeof(Segment) + (size_t)n_tiles * (sizeof(TileRec) + 4)) +
+                                             ng * ((size_t)seg_cap * sizeof(GroupSeg) + (size_t)n_tiles * 4 + max_chunks));
+    if (bytes > (size_t)4 << 30) persistent = false;
+  }
+  const uint32_t nslots = persistent ? n_blocks : RING;
+  CUDA_TRY(r->d_group_flags.reserve(std::max<size_t>(1, (size_t)nslots * ng * max_chunks)));
+  CUDA_TRY(r->d_segs.reserve((size_t)nslots * nvoices * seg_cap));
+  CUDA_TRY(r->d_gsegs.reserve(std::max<size_t>(1, (size_t)nslots * ng * seg_cap)));
+  CUDA_TRY(r->d_seg_first.reserve((size_t)nslots * nvoices * n_tiles));
+  CUDA_TRY(r->d_seg_count.reserve((size_t)nslots * nvoices * n_tiles));
   {  // tile records carry a process-wide unique generation tag; a freshly acquired buffer is cleared once
     const TileRec* before = r->d_recs.p;
-    CUDA_TRY(r->d_recs.reserve((size_t)RING * nvoices * n_tiles));
+    CUDA_TRY(r->d_recs.reserve((size_t)nslots * nvoices * n_tiles));
     if (r->d_recs.p != before) CUDA_TRY(cudaMemsetAsync(r->d_recs.p, 0, r->d_recs.cap * sizeof(TileRec), r->sv));
   }
-  CUDA_TRY(r->d_gseg_first.reserve(std::max<size_t>(1, (size_t)RING * ng * n_tiles)));
-  CUDA_TRY(r->d_gseg_count.reserve(std::max<size_t>(1, (size_t)RING * ng * n_tiles)));
+  CUDA_TRY(r->d_gseg_first.reserve(std::max<size_t>(1, (size_t)nslots * ng * n_tiles)));
+  CUDA_TRY(r->d_gseg_count.reserve(std::max<size_t>(1, (size_t)nslots * ng * n_tiles)));
+  if (persistent) {
+    CUDA_TRY(r->d_block_done.reserve(n_blocks));
+    CUDA_TRY(cudaMemsetAsync(r->d_block_done.p, 0, n_blocks * sizeof(uint32_t), r->sv));
+  }
 
   // HighQuality voices: per-block record list + resampler output stream scratch (hq.cuh, sinc_kernel.cuh)
   const uint32_t n_hq = r->n_hq;
@@ -1239,6 +1283,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_start, 0));
   uint64_t launches = 0;
+  uint32_t gen0 = 0;
+  cudaEvent_t ev_skel_end;
+  CUDA_TRY(DevicePool::get().event(&ev_skel_end));
   // PB200_SKEL_PROF=<file>: per-voice cycle counters of the skeleton pass (debug aid)
   unsigned long long* prof_buf = nullptr;
   if (getenv("PB200_SKEL_PROF")) {
@@ -1250,25 +1297,27 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     const uint64_t b0 = p0 + (uint64_t)b * tb;
     const uint32_t blen = (uint32_t)std::min<uint64_t>(tb, p1 - b0);
     const uint32_t slot = b % RING;
+    const uint32_t sslot = persistent ? b : slot;  // slot of the tables the skeleton pass owns
     // pass 1 (skeleton) may not overwrite the segment slot the replay of block b-RING still reads
     // ... nor the group-flag slot the mixer of block b-RING still reads
-    if (b >= RING) { CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_r1[b - RING], 0)); CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_m1[b - RING], 0)); }
-    CUDA_TRY(cudaEventRecord(ev_v0[b], r->sv));
+    if (!persistent && b >= RING) { CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_r1[b - RING], 0)); CUDA_TRY(cudaStreamWaitEvent(r->sv, ev_m1[b - RING], 0)); }
+    if (!persistent || b == 0) CUDA_TRY(cudaEventRecord(ev_v0[b], r->sv));
     SkeletonArgs va;
     va.groups = r->d_groups.p; va.gstate = r->d_gstate.p; va.voices = r->d_voices.p; va.buffers = r->d_buffers.p;
     va.events = r->d_events.p;
     va.chunk_bounds = r->d_bounds.p;
     va.mixer_chunk_begin = r->d_chunk_begin.p + (size_t)b * (nm + 1);
-    va.group_flags = r->d_group_flags.p + (size_t)slot * ng * max_chunks;
+    va.group_flags = r->d_group_flags.p + (size_t)sslot * ng * max_chunks;
     va.max_chunks = max_chunks; va.block_frames = tb; va.block_start = b0; va.rc = r->rc;
-    va.segs = r->d_segs.p + (size_t)slot * nvoices * seg_cap;
-    va.seg_first = r->d_seg_first.p + (size_t)slot * nvoices * n_tiles;
-    va.seg_count = r->d_seg_count.p + (size_t)slot * nvoices * n_tiles;
-    va.recs = r->d_recs.p + (size_t)slot * nvoices * n_tiles;
-    va.gen = next_generation();
-    va.gsegs = r->d_gsegs.p + (size_t)slot * ng * seg_cap;
-    va.gseg_first = r->d_gseg_first.p + (size_t)slot * ng * n_tiles;
-    va.gseg_count = r->d_gseg_count.p + (size_t)slot * ng * n_tiles;
+    va.segs = r->d_segs.p + (size_t)sslot * nvoices * seg_cap;
+    va.seg_first = r->d_seg_first.p + (size_t)sslot * nvoices * n_tiles;
+    va.seg_count = r->d_seg_count.p + (size_t)sslot * nvoices * n_tiles;
+    va.recs = r->d_recs.p + (size_t)sslot * nvoices * n_tiles;
+    if (!persistent) va.gen = next_generation();
+    else { if (b == 0) gen0 = reserve_generations(n_blocks); va.gen = gen0 + b; }
+    va.gsegs = r->d_gsegs.p + (size_t)sslot * ng * seg_cap;
+    va.gseg_first = r->d_gseg_first.p + (size_t)sslot * ng * n_tiles;
+    va.gseg_count = r->d_gseg_count.p + (size_t)sslot * ng * n_tiles;
     va.seg_cap = seg_cap; va.n_tiles = n_tiles;
     va.hq_states = n_hq ? r->d_hq.p : nullptr;
     va.hq_recs = n_hq ? r->d_hq_recs.p + (size_t)slot * hq_cap : nullptr;
@@ -1291,18 +1340,38 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     }
     va.prof = prof_buf;
     va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
-    for (size_t ci = 0; ci < c.classes.size(); ++ci) {
+    SkeletonLoop sl;
+    std::memset(&sl, 0, sizeof(sl));
+    sl.n_blocks = 1;
+    if (persistent) {
+      sl.n_blocks = n_blocks;
+      sl.chunk_begin_stride = (uint32_t)(nm + 1);
+      sl.group_flags_stride = ng * max_chunks;
+      sl.segs_stride = nvoices * seg_cap; sl.seg_tab_stride = nvoices * n_tiles;
+      sl.gsegs_stride = ng * seg_cap; sl.gseg_tab_stride = ng * n_tiles; sl.recs_stride = nvoices * n_tiles;
+      sl.block_done = r->d_block_done.p;
+    }
+    for (size_t ci = 0; ci < c.classes.size() && (!persistent || b == 0); ++ci) {
       const SizeClass& sc = c.classes[ci];
       va.group_list = r->d_class_groups.p + c.class_offsets[ci];
-      if (sc.vpad <= 8) skeleton_kernel<256, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va);
-      else if (sc.vpad <= 32) skeleton_kernel<1024, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va);
-      else if (sc.threads <= 256) skeleton_kernel<256, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va);
-      else skeleton_kernel<1024, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va);
+      if (sc.vpad <= 8) skeleton_kernel<256, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
+      else if (sc.vpad <= 32) skeleton_kernel<1024, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
+      else if (sc.threads <= 256) skeleton_kernel<256, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
+      else skeleton_kernel<1024, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
       ++launches;
     }
-    CUDA_TRY(cudaEventRecord(ev_v1[b], r->sv));
     // pass 2 (replay): needs the segments of this block; may not overwrite a group-bus slot the mixer still reads
-    CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_v1[b], 0));
+    if (!persistent) {
+      CUDA_TRY(cudaEventRecord(ev_v1[b], r->sv));
+      CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_v1[b], 0));
+    } else {
+      if (b == 0) CUDA_TRY(cudaEventRecord(ev_skel_end, r->sv));
+      if (stream_wait_value32()((CUstream)r->sr_, (CUdeviceptr)(r->d_block_done.p + b), (cuuint32_t)c.classes[0].groups.size(),
+                                CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return fail(r, PB200_ERR_CUDA, "cuStreamWaitValue32 failed");
+      if (b > 0) CUDA_TRY(cudaEventRecord(ev_v0[b], r->sr_));
+      CUDA_TRY(cudaEventRecord(ev_v1[b], r->sr_));
+    }
     if (b >= RING) CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_m1[b - RING], 0));
     ReplayArgs ra;
     ra.groups = r->d_groups.p; ra.buffers = r->d_buffers.p;
@@ -1398,7 +1467,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   cudaEventElapsedTime(&ms, ev_start, ev_end);
   r->stats.device_ms = ms;
   for (uint32_t b = 0; b < n_blocks; ++b) {
-    cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.skeleton_kernel_ms += ms;
+    if (!persistent) { cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.skeleton_kernel_ms += ms; }
+    else if (b == 0) { cudaEventElapsedTime(&ms, ev_v0[0], ev_skel_end); r->stats.skeleton_kernel_ms += ms; }
     cudaEventElapsedTime(&ms, ev_v1[b], ev_r1[b]); r->stats.voice_kernel_ms += ms;
     cudaEventElapsedTime(&ms, ev_r1[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
     DevicePool::get().release_event(ev_v0[b]); DevicePool::get().release_event(ev_v1[b]);
@@ -1410,6 +1480,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   }
   for (auto& e : ev_x) DevicePool::get().release_event(e);
   DevicePool::get().release_event(ev_start); DevicePool::get().release_event(ev_end);
+  DevicePool::get().release_event(ev_skel_end);
   r->stats.kernel_launches = launches;
   if (n_hq) {
     std::vector<uint32_t> counts(n_blocks);

@@ -177,7 +177,7 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
 // WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
 // control flow (the skeleton is a latency-bound chain of dependent f32 ops per voice, not a SIMT workload).
 template <int MAXT, bool WPV>
-__global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
+PB_DEV void skeleton_block(const SkeletonArgs& a) {
   __shared__ VoiceHeader s_head[WPV ? 32 : MAXT];
   __shared__ GroupState s_gs;
   __shared__ uint32_t s_count;
@@ -598,6 +598,37 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a) {
   if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
   __syncthreads();
   if (tid == 0) a.gstate[g] = s_gs;
+}
+
+// How one launch walks several consecutive time blocks (the persistent mode of small graphs: every group keeps
+// its own pace through the whole render, a block is handed to the replay pass as soon as ALL groups have finished
+// it; renderer.cu waits for `block_done[b]` with a stream memory operation). n_blocks = 1 and block_done = nullptr:
+// the plain one-launch-per-block mode.
+struct SkeletonLoop {
+  uint32_t n_blocks;
+  uint32_t chunk_begin_stride;   // uint32 per block in mixer_chunk_begin
+  size_t group_flags_stride;     // per-block strides of the snapshot tables (elements)
+  size_t segs_stride, seg_tab_stride, gsegs_stride, gseg_tab_stride, recs_stride;
+  uint32_t* block_done;          // [n_blocks] CTAs that finished the block
+};
+
+template <int MAXT, bool WPV>
+__global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a, SkeletonLoop L) {
+  for (uint32_t b = 0; b < L.n_blocks; ++b) {
+    skeleton_block<MAXT, WPV>(a);
+    if (L.block_done) {
+      __syncthreads();
+      if (threadIdx.x == 0) { __threadfence(); atomicAdd(L.block_done + b, 1u); }
+    }
+    a.mixer_chunk_begin += L.chunk_begin_stride;
+    a.group_flags += L.group_flags_stride;
+    a.block_start += a.block_frames;
+    a.segs += L.segs_stride; a.seg_first += L.seg_tab_stride; a.seg_count += L.seg_tab_stride;
+    a.gsegs += L.gsegs_stride; a.gseg_first += L.gseg_tab_stride; a.gseg_count += L.gseg_tab_stride;
+    a.recs += L.recs_stride;
+    a.gen += 1;
+    __syncthreads();
+  }
 }
 
 }  // namespace pb
