@@ -27,8 +27,17 @@ struct GranEmit {
   uint32_t block_frames;
 };
 
-PB_DEV double gran_rem_euclid(double a, double b) { double r = fmod(a, b); return r < 0.0 ? r + fabs(b) : r; }
-PB_DEV float gran_rem_euclidf(float a, float b) { float r = fmodf(a, b); return r < 0.0f ? r + fabsf(b) : r; }
+// f64::rem_euclid. fmod(a, b) == a exactly for 0 <= a < b: the common case skips the (slow) fmod
+PB_DEV double gran_rem_euclid(double a, double b) {
+  if (a >= 0.0 && a < b) return a;
+  double r = fmod(a, b);
+  return r < 0.0 ? r + fabs(b) : r;
+}
+PB_DEV float gran_rem_euclidf(float a, float b) {
+  if (a >= 0.0f && a < b) return a;
+  float r = fmodf(a, b);
+  return r < 0.0f ? r + fabsf(b) : r;
+}
 PB_DEV double gran_fold(double position, double ls, double le) {  // GrainPool::fold_into_loop_range
   const double loop_len = le - ls;
   return loop_len > 0.0 ? ls + gran_rem_euclid(position - ls, loop_len) : ls;
@@ -170,7 +179,31 @@ __device__ __noinline__ void gran_advance(GranState* __restrict__ sp, const Gran
   bool playing_loop = s.playing_loop != 0, has_primary = s.has_primary != 0;
   uint64_t primary_end = s.primary_end;
   double primary_phase = s.primary_phase, primary_inc = s.primary_inc;
-  for (uint32_t i = 0; i < n; ++i) {
+  uint32_t i = 0;
+  while (i < n) {
+    if (!sequential) {
+      // Cloud mode fast span: frames in which no grain triggers and the playhead update is a plain `+= increment`
+      // (no wrap, no loop entry, and inside the loop range the fold is the identity: (double)x - ls and ls + that
+      // are exact for f32 operands) are one FADD each; anything else falls through to the reference's own code.
+      float lo = 0.0f, hi = 1.0f;
+      if (move_playhead && gg.has_loop) {
+        if (playing_loop) { lo = gg.loop_start; hi = gg.loop_end; }
+        else if (playhead < gg.loop_start) { hi = fminf(gg.loop_start, 1.0f); }
+        else if (playhead >= gg.loop_end) { lo = fmaxf(gg.loop_end, 0.0f); }
+        else { lo = 1.0f; hi = 0.0f; }  // about to enter the loop: slow path
+      }
+      const float tinc = trigger_new ? gg.trigger_inc : 0.0f;
+      const float pinc = move_playhead ? position_increment : 0.0f;
+      if (!move_playhead) { lo = -3.0e38f; hi = 3.0e38f; }
+      for (; i < n; ++i) {
+        const float tpn = trigger_phase + tinc;
+        const float phn = playhead + pinc;
+        if ((tpn >= 1.0f) | !(phn >= lo) | !(phn < hi)) break;
+        trigger_phase = tpn;
+        playhead = phn;
+      }
+      if (i >= n) break;
+    }
     const uint64_t t = t0 + i;
     // try_trigger_grain (granular.rs:524-560)
     bool trig = false;
@@ -198,6 +231,7 @@ __device__ __noinline__ void gran_advance(GranState* __restrict__ sp, const Gran
     }
     // the primary grain's Grain::process of this frame (granular.rs:1094)
     if (has_primary && t < primary_end) primary_phase += primary_inc;
+    ++i;
   }
   s.trigger_phase = trigger_phase; s.playhead = playhead; s.playing_loop = playing_loop ? 1 : 0;
   s.primary_phase = primary_phase;

@@ -32,12 +32,23 @@ PB_DEV void hq_reset_pending(HqState& h, const HqEmit& em, uint32_t cur_off) {
   h.rec = HQ_NONE;
 }
 
-// One output frame of write_buffer's loop for a HighQuality voice, state only. Returns false on the EOF break.
+// State-only advance of one write call of a HighQuality voice by up to `n` frames (the skeleton pass): walks
+// write_buffer's loop iterations (preloaded.rs:283-329); frames that only drain pending output are taken in one step.
 template <int CC>
-PB_DEV bool hq_frame(VoiceState& v, CallCtx& c, HqState& h, const HqEmit& em) {
-  for (;;) {
-    if (c.new_call) {  // first iteration of this write_buffer call
-      c.new_call = false;
+__device__ __noinline__ uint32_t hq_advance(VoiceState& v, CallCtx& c, HqState* __restrict__ hp, const HqEmit em,
+                                            const DevBuffer& b, float comp, uint32_t n) {
+  HqState h = *hp;  // the resampler state lives in HBM between segments: the skeleton's hot cubic path keeps its registers
+  uint32_t done = 0;
+  uint32_t call_left = c.call_left, chunk_left = c.chunk_left, hq_off = c.hq_off;
+  bool new_call = c.new_call;
+  while (done < n && !c.ended) {
+    if (call_left == 0) {  // write() without pitch slide: one write_buffer call (preloaded.rs:441-447)
+      call_left = chunk_left;
+      loop_range_samples(v, b, c.ls, c.le);
+      new_call = true;
+    }
+    if (new_call) {  // first iteration of this write_buffer call
+      new_call = false;
       if (h.pending > 0) {
         // process() only flushes pending output (rubato.rs:81-86): nothing is consumed -- except on the zero-pad
         // path, which counts the whole remaining input as consumed whatever process() did (preloaded.rs:296-304)
@@ -56,13 +67,15 @@ PB_DEV bool hq_frame(VoiceState& v, CallCtx& c, HqState& h, const HqEmit& em) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) { r.src[k] = h.src[k]; r.valid[k] = h.valid[k]; }
           r.kind = v.hq == 2 ? 1 : 0;
-          r.slot = h.slot; r.out_off = c.hq_off; r.skip = h.n_out - h.pending; r.count = h.pending;
+          r.slot = h.slot; r.out_off = hq_off; r.skip = h.n_out - h.pending; r.count = h.pending;
           r.buffer = em.buffer; r.table = h.table;
           em.recs[i] = r;
         }
       }
-      h.pending--;
-      return true;
+      const uint32_t take = min(h.pending, n - done);  // (call_left >= n - done: a segment never outlives its call)
+      h.pending -= take;
+      call_left -= take; chunk_left -= take; hq_off += take; done += take;
+      continue;
     }
     // pending is empty: the next iteration feeds the resampler (rubato.rs:93-133)
     const uint32_t remaining = c.le > v.playback_pos ? c.le - v.playback_pos : 0u;
@@ -73,48 +86,34 @@ PB_DEV bool hq_frame(VoiceState& v, CallCtx& c, HqState& h, const HqEmit& em) {
     h.rec = HQ_NONE;
     if (v.hq == 2) {
       // equal rates: process() copies min(input, output) samples (rubato.rs:73-78); the padded input is 256 frames
-      const uint32_t room = c.call_left;
+      const uint32_t room = call_left;
       if (pad) { produced = min(HQ_CHUNK, room); consumed = remaining; h.valid[2] = (uint16_t)min(remaining / CC, produced); }
       else { produced = min(remaining / CC, room); consumed = produced * CC; h.valid[2] = (uint16_t)produced; }
       h.idx0 = 0.0;
     } else {
       h.valid[2] = (uint16_t)min(remaining / CC, HQ_CHUNK);
       consumed = pad ? remaining : HQ_CHUNK * CC;
-      // SincFixedIn::process_into_buffer: `while idx < end_idx { idx += t_ratio; n += 1 }` (fixed ratio)
+      // SincFixedIn::process_into_buffer: `while idx < end_idx { idx += t_ratio; n += 1 }` (fixed ratio), exactly
       double idx = h.last_index;
       const double t = h.t_ratio, end = (double)h.end_idx;
-      uint32_t n = 0;
-      while (idx < end) { idx += t; ++n; }
+      uint32_t cnt = 0;
+      for (;;) {  // eight adds per exit test: the chain of DADDs is the work, the compare-and-branch was most of the time
+        const double a1 = idx + t, a2 = a1 + t, a3 = a2 + t, a4 = a3 + t, a5 = a4 + t, a6 = a5 + t, a7 = a6 + t;
+        if (!(a7 < end)) break;
+        idx = a7 + t; cnt += 8;
+      }
+      while (idx < end) { idx += t; ++cnt; }
       h.idx0 = h.last_index;
       h.last_index = idx - (double)HQ_CHUNK;
-      produced = n;
+      produced = cnt;
     }
     h.n_out = produced;
     h.pending = produced;
     v.playback_pos += consumed;
     after_process_call(v, c);
-    if (produced == 0 && v.pos_eof) return false;  // `playback_pos_eof && output_written == 0` (preloaded.rs:326-329)
+    if (produced == 0 && v.pos_eof) { c.ended = true; break; }  // `playback_pos_eof && output_written == 0` (preloaded.rs:326-329)
   }
-}
-
-// State-only advance of one write call of a HighQuality voice by up to `n` frames (the skeleton pass).
-template <int CC>
-__device__ __noinline__ uint32_t hq_advance(VoiceState& v, CallCtx& c, HqState* __restrict__ hp, const HqEmit em,
-                                            const DevBuffer& b, float comp, uint32_t n) {
-  HqState h = *hp;  // the resampler state lives in HBM between segments: the skeleton's hot cubic path keeps its registers
-  uint32_t done = 0;
-  while (done < n && !c.ended) {
-    if (c.call_left == 0) {  // write() without pitch slide: one write_buffer call (preloaded.rs:441-447)
-      c.call_left = c.chunk_left;
-      loop_range_samples(v, b, c.ls, c.le);
-      c.new_call = true;
-    }
-    if (!hq_frame<CC>(v, c, h, em)) { c.ended = true; break; }
-    c.call_left--;
-    c.chunk_left--;
-    c.hq_off++;
-    ++done;
-  }
+  c.call_left = call_left; c.chunk_left = chunk_left; c.hq_off = hq_off; c.new_call = new_call;
   *hp = h;
   advance_ramps(v, c, done, comp);
   return done;

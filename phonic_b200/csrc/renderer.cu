@@ -1189,7 +1189,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   cudaDeviceGetAttribute(&sm_count_all, cudaDevAttrMultiProcessorCount, r->device);
   bool persistent = n_blocks > 1 && r->n_hq == 0 && r->n_gran_rows == 0 && c.classes.size() == 1 &&
                     c.classes[0].groups.size() <= (size_t)sm_count_all && !getenv("PB200_NO_PERSISTENT") &&
-                    !getenv("PB200_SKEL_PROF") && stream_wait_value32() != nullptr;
+                    stream_wait_value32() != nullptr;
   if (persistent) {
     const size_t bytes = (size_t)n_blocks * (nvoices * ((size_t)seg_cap * sizeof(Segment) + (size_t)n_tiles * (sizeof(TileRec) + 4)) +
                                              ng * ((size_t)seg_cap * sizeof(GroupSeg) + (size_t)n_tiles * 4 + max_chunks));
@@ -1457,7 +1457,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     cudaMemcpy(h.data(), prof_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(prof_buf);
     if (FILE* f = fopen(getenv("PB200_SKEL_PROF"), "w")) {
-      fprintf(f, "voice,total_cycles,simple_cycles,general_cycles,frames\n");
+      fprintf(f, "voice,sync_wait_cycles,simple_cycles,general_cycles,resident_cycles\n");
       for (size_t i = 0; i < nvoices; ++i) fprintf(f, "%zu,%llu,%llu,%llu,%llu\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
       fclose(f);
     }

@@ -24,7 +24,7 @@
 namespace pb {
 
 constexpr int SINC_NB = 4;            // records per batch
-constexpr int SINC_THREADS = 1024;
+constexpr int SINC_THREADS = 768;
 constexpr uint32_t SINC_ROW = 288;    // padded table row (words)
 constexpr uint32_t SINC_TAPS = 258;   // unified tap range p' = -1 .. 256
 constexpr uint32_t SINC_WIN = 3 * HQ_CHUNK;  // SincFixedIn buffer: chunk_size + 2 * sinc_len frames

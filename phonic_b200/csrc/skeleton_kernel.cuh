@@ -176,6 +176,7 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
 
 // WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
 // control flow (the skeleton is a latency-bound chain of dependent f32 ops per voice, not a SIMT workload).
+#define PB_SYNC() do { if (a.prof) { const long long _c = clock64(); __syncthreads(); prof_sync += clock64() - _c; } else __syncthreads(); } while (0)
 template <int MAXT, bool WPV>
 PB_DEV void skeleton_block(const SkeletonArgs& a) {
   __shared__ VoiceHeader s_head[WPV ? 32 : MAXT];
@@ -183,6 +184,9 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   __shared__ uint32_t s_count;
   __shared__ uint64_t s_bounds[SB_MAX];   // this mixer's chunk boundaries of the block
   __shared__ uint32_t s_cnt[MAX_RUN];      // voices still holding a note after each chunk of a free run
+  unsigned long long prof_sync = 0, prof_free = 0, prof_genpath = 0;
+  unsigned long long prof_q[4] = {0, 0, 0, 0};
+  const long long prof_blk0 = a.prof ? clock64() : 0;
 
   const uint32_t g = a.group_list[blockIdx.x];
   const uint32_t tid = WPV ? ((threadIdx.x & 31u) == 0 ? (threadIdx.x >> 5) : 0xFFFFu) : threadIdx.x;
@@ -244,11 +248,11 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   uint16_t* g_count = a.gseg_count + (size_t)g * a.n_tiles;
   uint32_t n_gsegs = 0, gcur_tile = 0xFFFFFFFFu, gcur_first = 0, gcur_cnt = 0;
   for (uint32_t i = threadIdx.x; i < a.n_tiles; i += blockDim.x) g_count[i] = 0;
-  __syncthreads();
+  PB_SYNC();
 
   const uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];
   for (uint32_t i = threadIdx.x; i < min(ce - cb, SB_MAX); i += blockDim.x) s_bounds[i] = a.chunk_bounds[cb + i];
-  __syncthreads();
+  PB_SYNC();
   auto bound = [&](const uint32_t i) -> uint64_t { return i - cb < SB_MAX ? s_bounds[i - cb] : a.chunk_bounds[i]; };
   // time of the next pending event (re-read only when the cursor moved)
   uint32_t ev_cached = 0xFFFFFFFFu;
@@ -375,8 +379,11 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         }
       }
       if (run) {
+        const long long pq0 = a.prof ? clock64() : 0;
         for (uint32_t j = threadIdx.x; j < run; j += blockDim.x) s_cnt[j] = 0;
         __syncthreads();
+        const long long prof_fr0 = a.prof ? clock64() : 0;
+        if (a.prof) prof_q[0] += prof_fr0 - pq0;
         if (mine) {
           for (uint32_t j = 0; j < run; ++j) {
             if (v.has_note) {
@@ -391,7 +398,11 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           }
           publish_header(s_head, tid, v);
         }
+        const long long pq1 = a.prof ? clock64() : 0;
+        if (a.prof) prof_free += pq1 - prof_fr0;
         __syncthreads();
+        const long long pq2 = a.prof ? clock64() : 0;
+        if (a.prof) prof_q[1] += pq2 - pq1;
         if (tid == 0) {
           for (uint32_t j = 0; j < run; ++j) {
             bool writes = false;
@@ -408,11 +419,15 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
             gflags[k + j - cb] = writes ? 1 : 0;
           }
         }
+        const long long pq3 = a.prof ? clock64() : 0;
+        if (a.prof) prof_q[2] += pq3 - pq2;
         __syncthreads();
+        if (a.prof) prof_q[3] += clock64() - pq3;
         k += run - 1;
         continue;
       }
     }
+    const long long prof_gen0 = a.prof ? clock64() : 0;
     const uint32_t len = (uint32_t)(c1 - c0);
     const uint32_t boff = (uint32_t)(c0 - a.block_start);
     bool produced = false;
@@ -432,11 +447,11 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
     while (total < len) {
       const uint64_t t = c0 + total;
       uint64_t until_stop = UINT64_MAX;
-      __syncthreads();
+      PB_SYNC();
       if (s_gs.has_stop_time) until_stop = s_gs.stop_time > t ? s_gs.stop_time - t : 0;
       bool send_stop = false;
       if (until_stop == 0) { send_stop = true; until_stop = UINT64_MAX; }
-      __syncthreads();
+      PB_SYNC();
       if (send_stop && tid == 0) s_gs.has_stop_time = 0;
       const uint32_t n = (uint32_t)min((uint64_t)(len - total), until_stop);
 
@@ -451,10 +466,10 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           const bool ignore = s_gs.stopping != 0;  // sampler.rs:664
           if (ev.kind == EVK_STOP) {
             // GeneratorPlaybackMessage::Stop (sampler.rs:733-738)
-            __syncthreads();
+            PB_SYNC();
             if (tid == 0) s_gs.stopping = gp.transient;
             if (mine) { stop_voice(t); publish_header(s_head, tid, v); }
-            __syncthreads();
+            PB_SYNC();
           } else if (ev.kind == EVK_SET_VOLUME) {  // generator-level AmplifiedSource message
             if (tid == 0) exp_set_target(s_gs.vol, ev.value, comp);
           } else if (ev.kind == EVK_SET_PANNING) {
@@ -462,7 +477,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           } else if (!ignore) {
             if (ev.kind == EVK_NOTE_ON) {
               const uint32_t idx = next_free_voice_index(s_head, nv, gp.has_env != 0);
-              __syncthreads();
+              PB_SYNC();
               if (tid == idx) {  // SamplerVoice::start (voice.rs:122-193)
                 if (gsp && v.has_note) gran_reset(*gsp, a.gran, t, boff + total);
                 voice_reset(v);
@@ -481,16 +496,16 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
                 publish_header(s_head, tid, v);
               }
               if (tid == 0) s_gs.active_voices += 1;
-              __syncthreads();
+              PB_SYNC();
             } else if (ev.kind == EVK_ALL_NOTES_OFF) {
               if (mine) { stop_voice(t); publish_header(s_head, tid, v); }
-              __syncthreads();
+              PB_SYNC();
             } else {
               // note-addressed events: first voice whose note_id matches (sampler.rs:776-822)
               uint32_t idx = 0xFFFFFFFFu;
               for (uint32_t i = 0; i < nv; ++i)
                 if (s_head[i].active && s_head[i].note_id == ev.note_id) { idx = i; break; }
-              __syncthreads();
+              PB_SYNC();
               if (tid == idx) {
                 if (ev.kind == EVK_NOTE_OFF) stop_voice(t);
                 else if (ev.kind == EVK_NOTE_SPEED) { file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate); if (gsp) gsp->speed = ev.speed; }
@@ -503,7 +518,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
                 }
                 publish_header(s_head, tid, v);
               }
-              __syncthreads();
+              PB_SYNC();
             }
           }
         } else if (mine) {  // file playback: FilePlaybackMessage / Amplified / Panned messages
@@ -517,7 +532,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           else if (ev.kind == EVK_SET_PANNING) exp_set_target(v.pan, ev.value, comp);
         }
       }
-      __syncthreads();
+      PB_SYNC();
       if (tid == 0) s_gs.ev_cursor = ev_end_now;
       if (send_stop) {  // PlaybackMessageQueue::send_stop (mixed.rs:591-598)
         if (is_sampler) {
@@ -527,7 +542,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           file_stop(v, gp);
         }
       }
-      __syncthreads();
+      PB_SYNC();
 
       // 2. does the source write at all? (sampler.rs:978-981 / preloaded.rs:400-403)
       bool group_writes;
@@ -539,7 +554,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
       bool call_open = false;
       const uint32_t call_off = boff + total;  // first frame of the call, relative to the block
       if (group_writes && was_active) call_open = voice_begin_call(v, cc, gp, buf, n, comp, gp.has_env != 0, call_off);
-      __syncthreads();
+      PB_SYNC();
 
       // 3. advance the voice through the call, one segment per (call x 64-frame tile)
       uint32_t written_frames = 0;
@@ -553,39 +568,40 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           publish_header(s_head, tid, v);
         }
         if (tid == 0) s_count = 0;
-        __syncthreads();
+        PB_SYNC();
         if (group_writes) {
           if (mine && v.has_note) atomicAdd(&s_count, 1u);
-          __syncthreads();
+          PB_SYNC();
           if (tid == 0) {
             s_gs.active_voices = s_count;
             if (s_gs.stopping && s_count == 0) s_gs.stopped = 1;
           }
         }
-        __syncthreads();
+        PB_SYNC();
       } else {
         // a file source's written count = frames its single voice produced (short on EOF)
         if (tid == 0) s_count = written_frames;
-        __syncthreads();
+        PB_SYNC();
         written = s_count;
-        __syncthreads();
+        PB_SYNC();
       }
       total += written;
       produced |= written > 0;
       // mixed.rs:612-619
       bool exhausted;
       if (is_sampler) exhausted = s_gs.stopped != 0;
-      else { if (tid == 0) s_count = v.finished; __syncthreads(); exhausted = s_count != 0; __syncthreads(); }
+      else { if (tid == 0) s_count = v.finished; PB_SYNC(); exhausted = s_count != 0; PB_SYNC(); }
       if (gp.transient && exhausted) {
         if (tid == 0) s_gs.dead = 1;
-        __syncthreads();
+        PB_SYNC();
         break;
       } else if (written == 0) {
         break;
       }
     }
     if (tid == 0) gflags[k - cb] = produced ? 1 : 0;
-    __syncthreads();
+    PB_SYNC();
+    if (a.prof) prof_genpath += clock64() - prof_gen0;
   }
 
   if (mine && cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
@@ -593,13 +609,14 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   if (mine) a.voices[gp.first_voice + tid] = v;
   if (a.prof && mine) {
     unsigned long long* pr = a.prof + (size_t)(gp.first_voice + tid) * 4;
-    pr[0] += prof_phase; pr[1] += prof_simple; pr[2] += prof_general; pr[3] += my_frames;
+    pr[0] += prof_q[0] + prof_q[1] + prof_q[3]; pr[1] += prof_free; pr[2] += prof_genpath + prof_q[2]; pr[3] += (unsigned long long)(clock64() - prof_blk0);
   }
   if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
-  __syncthreads();
+  PB_SYNC();
   if (tid == 0) a.gstate[g] = s_gs;
 }
 
+#undef PB_SYNC
 // How one launch walks several consecutive time blocks (the persistent mode of small graphs: every group keeps
 // its own pace through the whole render, a block is handed to the replay pass as soon as ALL groups have finished
 // it; renderer.cu waits for `block_done[b]` with a stream memory operation). n_blocks = 1 and block_done = nullptr:
