@@ -256,6 +256,72 @@ PB_DEV void biquad_scan_channel(const BiquadCoef& c, double& ic1_io, double& ic2
   __syncwarp();
 }
 
+// Both channels of one time-invariant biquad with ALL threads of the mixer CTA (FX_THREADS = 256): threads
+// [0,128) / [128,256) = channel 0 / 1, one sub-block of ceil(len/128) samples per thread. Same three phases as
+// biquad_scan_channel, but the sub-block start states come from a parallel prefix over affine maps instead of one
+// lane's serial chain: every sub-block before the last non-empty one has the same transition P = A^B, so
+//   S_j = P^j W + sum_{i<j} P^(j-1-i) e_i   (W = state at the warp's first sub-block)
+// is a Hillis-Steele scan over the end states e_i with the powers P^(2^k) (5 shuffle steps per warp), the four
+// warps of a channel are chained through shared memory, and P^j W is built from the same powers.
+// The chunk-parallel f64 dependent-op latency on this part is ~40 cycles, so depth is what matters:
+// 8 + 8 ticks and ~25 scan levels instead of 32 + 32 ticks and ~110 serial levels.
+// Ends with a CTA barrier. `ic1`, `ic2`: per-channel state at [ch * stride] (read at entry, written by the owner of the
+// last sample).
+PB_DEV void biquad_scan_stereo(const BiquadCoef& c, double* ic1, double* ic2, uint32_t stride, const ChunkBuf& cb, uint32_t len, uint32_t tid) {
+  const uint32_t ch = tid >> 7, j = tid & 127u, lane = tid & 31u, w = j >> 5;
+  const double in1 = ic1[ch * stride], in2 = ic2[ch * stride];
+  __syncthreads();  // every thread has read the incoming state before the owner of the last sample replaces it
+  if (len == 0) return;
+  const uint32_t B = (len + 127u) / 128u;
+  const uint32_t lo = min(j * B, len), hi = min(lo + B, len);
+  float* x = cb.ch[ch];
+  double* y0 = cb.scratch + (size_t)ch * 1060;
+  double* ls = cb.lane_state + (size_t)ch * 64;
+  const Mat2 A{2.0 * c.a1 - 1.0, -2.0 * c.a2, 2.0 * c.a2, 1.0 - 2.0 * c.a3};
+  // phase 1: zero-state response of my sub-block with the reference tick
+  double e1 = 0.0, e2 = 0.0;
+  for (uint32_t n = lo; n < hi; ++n) y0[pidx(n)] = biquad_tick(c, e1, e2, (double)x[pidx(n)]);
+  // phase 2a: inclusive scan E_j = sum_{i<=j} P^(j-i) e_i inside the warp
+  const Mat2 P = mat_pow(A, B);
+  Mat2 Pd = P;
+  double E1 = e1, E2 = e2;
+#pragma unroll
+  for (uint32_t d = 1; d < 32; d <<= 1) {
+    const double u1 = __shfl_up_sync(0xFFFFFFFFu, E1, d), u2 = __shfl_up_sync(0xFFFFFFFFu, E2, d);
+    if (lane >= d) { E1 += Pd.a * u1 + Pd.b * u2; E2 += Pd.c * u1 + Pd.d * u2; }
+    Pd = mat_mul(Pd, Pd);
+  }
+  // Pd = P^32: the transition of a whole warp
+  if (lane == 31) { ls[w * 2] = E1; ls[w * 2 + 1] = E2; }
+  __syncthreads();
+  // phase 2b: state at my warp's first sub-block
+  double W1 = in1, W2 = in2;
+  for (uint32_t q = 0; q < w; ++q) {
+    const double t1 = Pd.a * W1 + Pd.b * W2 + ls[q * 2], t2 = Pd.c * W1 + Pd.d * W2 + ls[q * 2 + 1];
+    W1 = t1; W2 = t2;
+  }
+  // phase 2c: S_j = P^lane W + E_(lane-1)
+  double p1 = __shfl_up_sync(0xFFFFFFFFu, E1, 1), p2 = __shfl_up_sync(0xFFFFFFFFu, E2, 1);
+  if (lane == 0) { p1 = 0.0; p2 = 0.0; }
+  Mat2 Q = P;
+#pragma unroll
+  for (uint32_t k = 0; k < 5; ++k) {
+    if ((lane >> k) & 1u) { const double t1 = Q.a * W1 + Q.b * W2, t2 = Q.c * W1 + Q.d * W2; W1 = t1; W2 = t2; }
+    Q = mat_mul(Q, Q);
+  }
+  // phase 3: add the homogeneous response of my sub-block's true start state
+  const double C1 = c.m1 * c.a1 + c.m2 * c.a2, C2 = -c.m1 * c.a2 + c.m2 * (1.0 - c.a3);
+  double h1 = W1 + p1, h2 = W2 + p2;
+  for (uint32_t n = lo; n < hi; ++n) {
+    x[pidx(n)] = (float)(y0[pidx(n)] + (C1 * h1 + C2 * h2));
+    const double t1 = A.a * h1 + A.b * h2, t2 = A.c * h1 + A.d * h2;
+    h1 = t1; h2 = t2;
+  }
+  // the owner of the last sample holds the chunk's end state: A^(its length) S_j + e_j
+  if (hi == len && lo < hi) { ic1[ch * stride] = h1 + e1; ic2[ch * stride] = h2 + e2; }
+  __syncthreads();
+}
+
 // ---- FilterEffect::process (filter.rs:166-201): warps 0/1 = channels ---------------------------------------
 PB_DEV void filter_process(FilterState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t lane, uint32_t warp) {
   const bool ramp = exp_need_ramp(s.cutoff, cx.comp) || lin_need_ramp(s.q);
@@ -270,11 +336,9 @@ PB_DEV void filter_process(FilterState& s, const FxCtx& cx, const ChunkBuf& cb, 
         CB_R(f) = (float)biquad_tick(s.coef, s.ic1[1], s.ic2[1], (double)CB_R(f));
       }
     }
-  } else if (warp < 2) {
+  } else {
     const BiquadCoef c = s.coef;
-    double ic1 = s.ic1[warp], ic2 = s.ic2[warp];
-    biquad_scan_channel(c, ic1, ic2, cb.ch[warp], cb.scratch + (size_t)warp * 1060, cb.lane_state + (size_t)warp * 64, frames, lane);
-    if (lane == 0) { s.ic1[warp] = ic1; s.ic2[warp] = ic2; }
+    biquad_scan_stereo(c, s.ic1, s.ic2, 1, cb, frames, warp * 32 + lane);
   }
 }
 
@@ -306,13 +370,11 @@ PB_DEV void eq5_process(Eq5State& s, const FxCtx& cx, const ChunkBuf& cb, uint32
         }
       }
     }
-  } else if (warp < 2) {
+  } else {
     // five cascaded stages, each cast back to f32 before the next one (eq5.rs:317-321)
     for (int i = 0; i < 5; ++i) {
       const BiquadCoef c = s.coef[i];
-      double ic1 = s.ic1[warp][i], ic2 = s.ic2[warp][i];
-      biquad_scan_channel(c, ic1, ic2, cb.ch[warp], cb.scratch + (size_t)warp * 1060, cb.lane_state + (size_t)warp * 64, frames, lane);
-      if (lane == 0) { s.ic1[warp][i] = ic1; s.ic2[warp][i] = ic2; }
+      biquad_scan_stereo(c, &s.ic1[0][i], &s.ic2[0][i], 5, cb, frames, warp * 32 + lane);
     }
   }
 }

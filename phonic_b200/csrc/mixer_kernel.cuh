@@ -38,6 +38,7 @@ struct MixerKernelArgs {
   float* out;                     // device output for this block (interleaved stereo) or nullptr
   ExpSm* master;                  // WavStream::smoothed_volume
   uint32_t wav_block_frames;      // 1024
+  unsigned long long* prof;       // PB200_FX_PROF: [8] cycle counters of the main mixer's CTA (debug aid)
 };
 
 PB_DEV uint64_t sat_sub_u64(uint64_t a, uint64_t b) { return a > b ? a - b : 0; }
@@ -105,7 +106,10 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
   cbuf.scratch = &s_scratch[0][0];
   cbuf.lane_state = &s_lane_state[0][0];
 
+  long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto tick = [&](int i, long long& t0) { if (a.prof) { const long long t1 = clock64(); pt[i] += t1 - t0; t0 = t1; } };
   for (uint32_t k = cb; k + 1 < ce; ++k) {
+    long long t0 = a.prof ? clock64() : 0;
     const uint64_t c0 = a.chunk_bounds[k], c1 = a.chunk_bounds[k + 1];
     const uint32_t len = (uint32_t)(c1 - c0);
     const uint32_t boff = (uint32_t)(c0 - a.block_start);
@@ -131,10 +135,12 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
       bool input_bypassed = !audible;
       const bool skip_all = a.mstate[m].effects_bypassed && input_bypassed;  // mixed.rs:629
       __syncthreads();
+      tick(0, t0);
       if (!skip_all) {
         // stage the chunk: interleaved global -> planar padded shared
         for (uint32_t i = tid; i < len * 2; i += nt) s_ch[i & 1][pidx(i >> 1)] = gchunk[i];
         __syncthreads();
+        tick(1, t0);
         bool all_bypassed = true;
         for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
           FxHeader& h = a.fx[e];
@@ -148,10 +154,12 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
             s_run = bypassed ? 0u : 1u;
           }
           __syncthreads();
+          tick(2, t0);
           const bool run = s_run != 0;
           if (run) {
             fx_process_chunk(h, a.fxc, cbuf, len, tid, nt, pw);
             __syncthreads();
+            tick(3, t0);
             if (input_bypassed) {
               uint64_t tail_frames;
               const bool has_tail = fx_process_tail(h, a.fxc, tail_frames);
@@ -186,11 +194,13 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
           }
           __syncthreads();
         }
+        tick(4, t0);
         if (tid == 0) a.mstate[m].effects_bypassed = all_bypassed ? 1u : 0u;
         // write the processed chunk back
         for (uint32_t i = tid; i < len * 2; i += nt) gchunk[i] = s_ch[i & 1][pidx(i >> 1)];
       }
       __syncthreads();
+      tick(5, t0);
     }
 
     if (is_main) {
@@ -245,7 +255,9 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
         pk++;
       }
     }
+    tick(6, t0);
   }
+  if (a.prof && tid == 0 && is_main) for (int i = 0; i < 8; ++i) atomicAdd(a.prof + i, (unsigned long long)pt[i]);
 }
 
 }  // namespace pb

@@ -1293,6 +1293,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(cudaMemset(prof_buf, 0, nvoices * 4 * sizeof(unsigned long long)));
   }
 
+  unsigned long long* fx_prof = nullptr;
+  if (getenv("PB200_FX_PROF")) { CUDA_TRY(cudaMalloc((void**)&fx_prof, 64)); CUDA_TRY(cudaMemset(fx_prof, 0, 64)); }
   for (uint32_t b = 0; b < n_blocks; ++b) {
     const uint64_t b0 = p0 + (uint64_t)b * tb;
     const uint32_t blen = (uint32_t)std::min<uint64_t>(tb, p1 - b0);
@@ -1436,6 +1438,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ma.max_chunks = max_chunks; ma.block_frames = tb; ma.block_start = b0;
     ma.out = dout + (size_t)(b0 - p0) * 2; ma.master = r->d_master.p; ma.wav_block_frames = bf;
     ma.block_len = blen;
+    ma.prof = fx_prof;
     for (int lvl = (int)c.levels.size() - 1; lvl >= 0; --lvl) {
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
       const uint32_t nlm = (uint32_t)c.levels[lvl].size();
@@ -1452,12 +1455,19 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaStreamSynchronize(r->sv));
   CUDA_TRY(cudaGetLastError());
 
+  if (fx_prof) {
+    unsigned long long h[8];
+    cudaMemcpy(h, fx_prof, 64, cudaMemcpyDeviceToHost);
+    cudaFree(fx_prof);
+    fprintf(stderr, "fx prof (Mcycles): events+audible %.2f stage %.2f bypass-decision %.2f process %.2f tail %.2f writeback %.2f master/gate %.2f\n",
+            h[0] / 1e6, h[1] / 1e6, h[2] / 1e6, h[3] / 1e6, h[4] / 1e6, h[5] / 1e6, h[6] / 1e6);
+  }
   if (prof_buf) {
     std::vector<unsigned long long> h(nvoices * 4);
     cudaMemcpy(h.data(), prof_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(prof_buf);
     if (FILE* f = fopen(getenv("PB200_SKEL_PROF"), "w")) {
-      fprintf(f, "voice,sync_wait_cycles,simple_cycles,general_cycles,resident_cycles\n");
+      fprintf(f, "voice,wait_before_run,wait_after_voices,wait_after_bookkeeping,free_run_work\n");
       for (size_t i = 0; i < nvoices; ++i) fprintf(f, "%zu,%llu,%llu,%llu,%llu\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
       fclose(f);
     }

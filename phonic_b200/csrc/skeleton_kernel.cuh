@@ -50,7 +50,7 @@ struct SkeletonArgs {
   const GranGroup* gran_groups;       // [n_groups] or nullptr when the graph has no granular sampler
   GranState* gran_states;             // [n_gran_rows]
   GranEmit gran;
-  unsigned long long* prof;           // PB200_SKEL_PROF: [n_voices][4] cycles (total, simple calls, general calls, frames)
+  unsigned long long* prof;           // PB200_SKEL_PROF: [n_voices][4] cycles waiting at the free run's three barriers + its own work
   uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores, 2 = no simple calls
 };
 
@@ -110,8 +110,7 @@ PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t fr
 // 32-byte TileRec stored at every tile boundary crossed instead of a full Segment.
 template <int CC>
 PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const DevBuffer& buf, uint32_t n,
-                        uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen,
-                        unsigned long long* prof_phase = nullptr, uint32_t debug_flags = 0) {
+                        uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen) {
   cc.call_left = cc.chunk_left;
   loop_range_samples(v, buf, cc.ls, cc.le);
   cc.new_call = false;
@@ -141,10 +140,8 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
       }
     }
     if (!fused) {
-      const long long c0 = prof_phase ? clock64() : 0;
       float o_unused = 0.0f;
-      if (!(debug_flags & 4u)) np += phase_piece<false>(s, p, pk, piece, first, o_unused, 0.0f);
-      if (prof_phase) *prof_phase += clock64() - c0;
+      np += phase_piece<false>(s, p, pk, piece, first, o_unused, 0.0f);
       if (env) env_chain(v, gp, piece);
     }
     first = false;
@@ -176,7 +173,6 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
 
 // WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
 // control flow (the skeleton is a latency-bound chain of dependent f32 ops per voice, not a SIMT workload).
-#define PB_SYNC() do { if (a.prof) { const long long _c = clock64(); __syncthreads(); prof_sync += clock64() - _c; } else __syncthreads(); } while (0)
 template <int MAXT, bool WPV>
 PB_DEV void skeleton_block(const SkeletonArgs& a) {
   __shared__ VoiceHeader s_head[WPV ? 32 : MAXT];
@@ -184,9 +180,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   __shared__ uint32_t s_count;
   __shared__ uint64_t s_bounds[SB_MAX];   // this mixer's chunk boundaries of the block
   __shared__ uint32_t s_cnt[MAX_RUN];      // voices still holding a note after each chunk of a free run
-  unsigned long long prof_sync = 0, prof_free = 0, prof_genpath = 0;
+  unsigned long long prof_free = 0;
   unsigned long long prof_q[4] = {0, 0, 0, 0};
-  const long long prof_blk0 = a.prof ? clock64() : 0;
 
   const uint32_t g = a.group_list[blockIdx.x];
   const uint32_t tid = WPV ? ((threadIdx.x & 31u) == 0 ? (threadIdx.x >> 5) : 0xFFFFu) : threadIdx.x;
@@ -248,26 +243,24 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   uint16_t* g_count = a.gseg_count + (size_t)g * a.n_tiles;
   uint32_t n_gsegs = 0, gcur_tile = 0xFFFFFFFFu, gcur_first = 0, gcur_cnt = 0;
   for (uint32_t i = threadIdx.x; i < a.n_tiles; i += blockDim.x) g_count[i] = 0;
-  PB_SYNC();
+  __syncthreads();
 
   const uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];
   for (uint32_t i = threadIdx.x; i < min(ce - cb, SB_MAX); i += blockDim.x) s_bounds[i] = a.chunk_bounds[cb + i];
-  PB_SYNC();
+  __syncthreads();
   auto bound = [&](const uint32_t i) -> uint64_t { return i - cb < SB_MAX ? s_bounds[i - cb] : a.chunk_bounds[i]; };
   // time of the next pending event (re-read only when the cursor moved)
-  uint32_t ev_cached = 0xFFFFFFFFu;
-  uint64_t ev_next_time = UINT64_MAX;
+  // next event that needs all voices at the same frame (see the free run below): its index and time
+  uint32_t hard_idx = 0xFFFFFFFFu;
+  uint64_t hard_time = UINT64_MAX;
   uint8_t* gflags = a.group_flags + (size_t)g * a.max_chunks;
   uint64_t my_frames = 0;
 
   // One Source::write call of this thread's voice (already opened by voice_begin_call): emits the call's
   // Segment / TileRec checkpoints and advances the control state. Returns the frames written.
-  unsigned long long prof_simple = 0, prof_general = 0, prof_phase = 0;
-  const long long prof_t0 = a.prof ? clock64() : 0;
   auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) -> uint32_t {
     uint32_t written_frames = 0;
     bool simple = false;
-    const long long prof_c0 = a.prof ? clock64() : 0;
     if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq && !is_gran)
       simple = buf.channels == 2 ? simple_call_ok<2>(v, cc, buf, n) : simple_call_ok<1>(v, cc, buf, n);
     if (simple) {
@@ -281,8 +274,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
       }
       cur_cnt++;
-      if (buf.channels == 2) simple_call<2>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen, a.prof ? &prof_phase : nullptr, a.debug_flags);
-      else simple_call<1>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen, a.prof ? &prof_phase : nullptr, a.debug_flags);
+      if (buf.channels == 2) simple_call<2>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
+      else simple_call<1>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
       n_segs++;
       written_frames = n;
     } else {
@@ -325,7 +318,6 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
     }
     my_frames += written_frames;
     voice_end_call(v, cc, t + n);
-    if (a.prof) { if (simple) prof_simple += clock64() - prof_c0; else prof_general += clock64() - prof_c0; }
     return written_frames;
   };
   // generator-level gain / pan (player.rs:1075-1081) of one call: checkpoint per (call x tile), advance ramps (thread 0)
@@ -359,21 +351,26 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   for (uint32_t k = cb; k + 1 < ce; ++k) {
     const uint64_t c0 = bound(k), c1 = bound(k + 1);
     // ---- free run -------------------------------------------------------------------------------------
-    // Between two events of a Sampler nothing couples its voices: each one runs its own write calls through
+    // Between two note-ons of a Sampler nothing couples its voices: each one runs its own write calls through
     // consecutive chunks without a CTA barrier and only reports whether it still holds a note after each
     // chunk; thread 0 then replays the generator-level bookkeeping (active-voice count, stopped / dead,
     // generator gain/pan checkpoints, chunk flags) for those chunks in order. A voice holding a note implies
     // the generator writes (sampler.rs:978-981), so the voices need no group state while they run.
+    // Only NOTE_ON (voice allocation looks at every voice, sampler.rs:826-860) and STOP (sets `stopping`, which
+    // makes later events ignored, sampler.rs:664) need all voices at the same frame. Every other event is applied
+    // inside the run: note-addressed events by the voice that holds the note (ids are unique), all-notes-off by
+    // every voice, generator volume / panning by thread 0 during the bookkeeping.
     if (is_sampler) {
-      if (ev_cached != s_gs.ev_cursor) {
-        ev_cached = s_gs.ev_cursor;
-        ev_next_time = ev_cached < gp.ev_end ? a.events[ev_cached].time : UINT64_MAX;
+      if (hard_idx == 0xFFFFFFFFu || hard_idx < s_gs.ev_cursor) {
+        hard_idx = s_gs.ev_cursor;
+        while (hard_idx < gp.ev_end && a.events[hard_idx].kind != EVK_NOTE_ON && a.events[hard_idx].kind != EVK_STOP) ++hard_idx;
+        hard_time = hard_idx < gp.ev_end ? a.events[hard_idx].time : UINT64_MAX;
       }
       uint32_t run = 0;
       if (!s_gs.dead && gp.start_time <= c0) {
         while (k + run + 1 < ce && run < MAX_RUN) {
           const uint64_t r0 = bound(k + run), r1 = bound(k + run + 1);
-          if (ev_next_time <= r0) break;                            // an event is due at this chunk
+          if (hard_time <= r0) break;                               // a note-on / stop is due at this chunk
           if (s_gs.has_stop_time && s_gs.stop_time < r1) break;     // scheduled stop inside this chunk
           ++run;
         }
@@ -385,7 +382,28 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         const long long prof_fr0 = a.prof ? clock64() : 0;
         if (a.prof) prof_q[0] += prof_fr0 - pq0;
         if (mine) {
+          uint32_t ec = s_gs.ev_cursor;
+          const bool ignore = s_gs.stopping != 0;
           for (uint32_t j = 0; j < run; ++j) {
+            {  // events due at this chunk's start (MixedSource::process_events -> the first write call of the chunk)
+              const uint64_t e0 = bound(k + j);
+              while (ec < gp.ev_end && a.events[ec].time <= e0) {
+                const DevEvent ev = a.events[ec];
+                ++ec;
+                if (ignore || ev.kind == EVK_SET_VOLUME || ev.kind == EVK_SET_PANNING) continue;
+                if (ev.kind == EVK_ALL_NOTES_OFF) { stop_voice(e0); continue; }
+                if (!(v.has_note && v.note_id == ev.note_id)) continue;
+                if (ev.kind == EVK_NOTE_OFF) stop_voice(e0);
+                else if (ev.kind == EVK_NOTE_SPEED) { file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate); if (gsp) gsp->speed = ev.speed; }
+                else if (ev.kind == EVK_NOTE_VOLUME) { v.note_volume = ev.value; exp_set_target(v.vol, gp.base_volume * ev.value, comp); if (gsp) gsp->volume = gp.base_volume * ev.value; }
+                else if (ev.kind == EVK_NOTE_PANNING) {
+                  v.note_panning = ev.value;
+                  const float eff = fminf(fmaxf(gp.base_panning + ev.value, -1.0f), 1.0f);
+                  exp_set_target(v.pan, eff, comp);
+                  if (gsp) gsp->panning = eff;
+                }
+              }
+            }
             if (v.has_note) {
               const uint64_t r0 = bound(k + j);
               const uint32_t rlen = (uint32_t)(bound(k + j + 1) - r0);
@@ -404,7 +422,17 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         const long long pq2 = a.prof ? clock64() : 0;
         if (a.prof) prof_q[1] += pq2 - pq1;
         if (tid == 0) {
+          uint32_t ec = s_gs.ev_cursor;
           for (uint32_t j = 0; j < run; ++j) {
+            {  // generator-level AmplifiedSource / PannedSource messages due at this chunk's start
+              const uint64_t e0 = bound(k + j);
+              while (ec < gp.ev_end && a.events[ec].time <= e0) {
+                const DevEvent ev = a.events[ec];
+                ++ec;
+                if (ev.kind == EVK_SET_VOLUME) exp_set_target(s_gs.vol, ev.value, comp);
+                else if (ev.kind == EVK_SET_PANNING) exp_set_target(s_gs.pan, ev.value, comp);
+              }
+            }
             bool writes = false;
             if (!s_gs.dead) {
               writes = !(s_gs.stopped || (s_gs.active_voices == 0 && !s_gs.stopping));
@@ -418,6 +446,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
             }
             gflags[k + j - cb] = writes ? 1 : 0;
           }
+          s_gs.ev_cursor = ec;
         }
         const long long pq3 = a.prof ? clock64() : 0;
         if (a.prof) prof_q[2] += pq3 - pq2;
@@ -427,7 +456,6 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         continue;
       }
     }
-    const long long prof_gen0 = a.prof ? clock64() : 0;
     const uint32_t len = (uint32_t)(c1 - c0);
     const uint32_t boff = (uint32_t)(c0 - a.block_start);
     bool produced = false;
@@ -447,11 +475,11 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
     while (total < len) {
       const uint64_t t = c0 + total;
       uint64_t until_stop = UINT64_MAX;
-      PB_SYNC();
+      __syncthreads();
       if (s_gs.has_stop_time) until_stop = s_gs.stop_time > t ? s_gs.stop_time - t : 0;
       bool send_stop = false;
       if (until_stop == 0) { send_stop = true; until_stop = UINT64_MAX; }
-      PB_SYNC();
+      __syncthreads();
       if (send_stop && tid == 0) s_gs.has_stop_time = 0;
       const uint32_t n = (uint32_t)min((uint64_t)(len - total), until_stop);
 
@@ -466,10 +494,10 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           const bool ignore = s_gs.stopping != 0;  // sampler.rs:664
           if (ev.kind == EVK_STOP) {
             // GeneratorPlaybackMessage::Stop (sampler.rs:733-738)
-            PB_SYNC();
+            __syncthreads();
             if (tid == 0) s_gs.stopping = gp.transient;
             if (mine) { stop_voice(t); publish_header(s_head, tid, v); }
-            PB_SYNC();
+            __syncthreads();
           } else if (ev.kind == EVK_SET_VOLUME) {  // generator-level AmplifiedSource message
             if (tid == 0) exp_set_target(s_gs.vol, ev.value, comp);
           } else if (ev.kind == EVK_SET_PANNING) {
@@ -477,7 +505,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           } else if (!ignore) {
             if (ev.kind == EVK_NOTE_ON) {
               const uint32_t idx = next_free_voice_index(s_head, nv, gp.has_env != 0);
-              PB_SYNC();
+              __syncthreads();
               if (tid == idx) {  // SamplerVoice::start (voice.rs:122-193)
                 if (gsp && v.has_note) gran_reset(*gsp, a.gran, t, boff + total);
                 voice_reset(v);
@@ -496,16 +524,16 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
                 publish_header(s_head, tid, v);
               }
               if (tid == 0) s_gs.active_voices += 1;
-              PB_SYNC();
+              __syncthreads();
             } else if (ev.kind == EVK_ALL_NOTES_OFF) {
               if (mine) { stop_voice(t); publish_header(s_head, tid, v); }
-              PB_SYNC();
+              __syncthreads();
             } else {
               // note-addressed events: first voice whose note_id matches (sampler.rs:776-822)
               uint32_t idx = 0xFFFFFFFFu;
               for (uint32_t i = 0; i < nv; ++i)
                 if (s_head[i].active && s_head[i].note_id == ev.note_id) { idx = i; break; }
-              PB_SYNC();
+              __syncthreads();
               if (tid == idx) {
                 if (ev.kind == EVK_NOTE_OFF) stop_voice(t);
                 else if (ev.kind == EVK_NOTE_SPEED) { file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate); if (gsp) gsp->speed = ev.speed; }
@@ -518,7 +546,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
                 }
                 publish_header(s_head, tid, v);
               }
-              PB_SYNC();
+              __syncthreads();
             }
           }
         } else if (mine) {  // file playback: FilePlaybackMessage / Amplified / Panned messages
@@ -532,7 +560,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           else if (ev.kind == EVK_SET_PANNING) exp_set_target(v.pan, ev.value, comp);
         }
       }
-      PB_SYNC();
+      __syncthreads();
       if (tid == 0) s_gs.ev_cursor = ev_end_now;
       if (send_stop) {  // PlaybackMessageQueue::send_stop (mixed.rs:591-598)
         if (is_sampler) {
@@ -542,7 +570,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           file_stop(v, gp);
         }
       }
-      PB_SYNC();
+      __syncthreads();
 
       // 2. does the source write at all? (sampler.rs:978-981 / preloaded.rs:400-403)
       bool group_writes;
@@ -554,7 +582,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
       bool call_open = false;
       const uint32_t call_off = boff + total;  // first frame of the call, relative to the block
       if (group_writes && was_active) call_open = voice_begin_call(v, cc, gp, buf, n, comp, gp.has_env != 0, call_off);
-      PB_SYNC();
+      __syncthreads();
 
       // 3. advance the voice through the call, one segment per (call x 64-frame tile)
       uint32_t written_frames = 0;
@@ -568,40 +596,39 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           publish_header(s_head, tid, v);
         }
         if (tid == 0) s_count = 0;
-        PB_SYNC();
+        __syncthreads();
         if (group_writes) {
           if (mine && v.has_note) atomicAdd(&s_count, 1u);
-          PB_SYNC();
+          __syncthreads();
           if (tid == 0) {
             s_gs.active_voices = s_count;
             if (s_gs.stopping && s_count == 0) s_gs.stopped = 1;
           }
         }
-        PB_SYNC();
+        __syncthreads();
       } else {
         // a file source's written count = frames its single voice produced (short on EOF)
         if (tid == 0) s_count = written_frames;
-        PB_SYNC();
+        __syncthreads();
         written = s_count;
-        PB_SYNC();
+        __syncthreads();
       }
       total += written;
       produced |= written > 0;
       // mixed.rs:612-619
       bool exhausted;
       if (is_sampler) exhausted = s_gs.stopped != 0;
-      else { if (tid == 0) s_count = v.finished; PB_SYNC(); exhausted = s_count != 0; PB_SYNC(); }
+      else { if (tid == 0) s_count = v.finished; __syncthreads(); exhausted = s_count != 0; __syncthreads(); }
       if (gp.transient && exhausted) {
         if (tid == 0) s_gs.dead = 1;
-        PB_SYNC();
+        __syncthreads();
         break;
       } else if (written == 0) {
         break;
       }
     }
     if (tid == 0) gflags[k - cb] = produced ? 1 : 0;
-    PB_SYNC();
-    if (a.prof) prof_genpath += clock64() - prof_gen0;
+    __syncthreads();
   }
 
   if (mine && cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
@@ -609,14 +636,13 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   if (mine) a.voices[gp.first_voice + tid] = v;
   if (a.prof && mine) {
     unsigned long long* pr = a.prof + (size_t)(gp.first_voice + tid) * 4;
-    pr[0] += prof_q[0] + prof_q[1] + prof_q[3]; pr[1] += prof_free; pr[2] += prof_genpath + prof_q[2]; pr[3] += (unsigned long long)(clock64() - prof_blk0);
+    pr[0] += prof_q[0]; pr[1] += prof_q[1]; pr[2] += prof_q[3]; pr[3] += prof_free;
   }
   if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
-  PB_SYNC();
+  __syncthreads();
   if (tid == 0) a.gstate[g] = s_gs;
 }
 
-#undef PB_SYNC
 // How one launch walks several consecutive time blocks (the persistent mode of small graphs: every group keeps
 // its own pace through the whole render, a block is handed to the replay pass as soon as ALL groups have finished
 // it; renderer.cu waits for `block_done[b]` with a stream memory operation). n_blocks = 1 and block_done = nullptr:
