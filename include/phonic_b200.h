@@ -102,7 +102,9 @@ enum pb200_effect_kind {
   PB200_FX_COMPRESSOR = 3, /* CompressorEffect src/effect/compressor.rs */
   PB200_FX_CHORUS = 4,     /* ChorusEffect     src/effect/chorus.rs     */
   PB200_FX_DELAY = 5,      /* DelayEffect      src/effect/delay.rs      */
-  PB200_FX_REVERB = 6      /* ReverbEffect     src/effect/reverb.rs     */
+  PB200_FX_REVERB = 6,     /* ReverbEffect     src/effect/reverb.rs     */
+  PB200_FX_GAIN = 7,       /* GainEffect       src/effect/gain.rs       */
+  PB200_FX_PANNING = 8     /* PanningEffect    src/effect/pan.rs        */
 };
 
 /* FilterEffect::with_parameters(filter_type, cutoff, q) (filter.rs:104-116) */
@@ -140,6 +142,16 @@ typedef struct pb200_reverb_params {
   uint32_t fpd[2];
   double vib_phase[16]; /* [line 0..7][L,R] start phases in [0, 2pi) */
 } pb200_reverb_params;
+
+/* GainEffect::with_parameters(gain_db, dc_mode) (gain.rs:97-104). Parameters: 'gain' (linear gain; normalized
+ * updates use ParameterScaling::Decibel(-60, 24)), 'dcfm'. */
+typedef struct pb200_gain_params {
+  float gain_db;           /* clamped to [-60, 24] */
+  uint32_t dc_filter_mode; /* GainEffectDcFilterMode: 0 Off 1 Slow (1 Hz) 2 Default (5 Hz) 3 Fast (20 Hz) */
+} pb200_gain_params;
+
+/* PanningEffect has only PanningEffect::new() (pan.rs:52-60): pass params = NULL and use
+ * PB200_EV_SET_EFFECT_PARAMETER events ('pan ', 'wdth', 'invl', 'invr'; booleans: value != 0). */
 
 /* `params` may be NULL => Effect::new()/default(). */
 PB200_API int pb200_add_effect(pb200_renderer *r, uint32_t mixer_id, uint32_t kind,

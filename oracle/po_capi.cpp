@@ -160,6 +160,18 @@ int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const voi
       fx = std::make_unique<ReverbEffect>(p->room_size, p->wet, p->fpd, p->vib_phase);
       break;
     }
+    case PB200_FX_GAIN:
+      if (params) {
+        if (size != sizeof(pb200_gain_params)) return fail(r, PB200_ERR_PARAMETER, "bad gain params size");
+        auto* p = (const pb200_gain_params*)params;
+        if (p->dc_filter_mode > 3) return fail(r, PB200_ERR_PARAMETER, "bad DC filter mode");
+        fx = std::make_unique<GainEffect>(p->gain_db, p->dc_filter_mode);
+      } else fx = std::make_unique<GainEffect>();
+      break;
+    case PB200_FX_PANNING:
+      if (params) return fail(r, PB200_ERR_PARAMETER, "PanningEffect has no parameter constructor");
+      fx = std::make_unique<PanningEffect>();
+      break;
     default: return fail(r, PB200_ERR_PARAMETER, "unknown effect kind");
   }
   // Player::add_effect: effect.initialize(sr, ch, MAX_MIX_BUFFER_SAMPLES / ch) (player.rs:905-909)

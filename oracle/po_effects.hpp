@@ -294,6 +294,107 @@ struct FilterEffect : Effect {
   }
 };
 
+// ---- src/effect/gain.rs:51-206 ---------------------------------------------------------------------------------
+struct GainEffect : Effect {
+  SmoothedParam<ExpSmoothed> gain;
+  uint32_t dc_filter_mode = 0;  // GainEffectDcFilterMode: Off, Slow, Default, Fast
+  std::vector<DcFilter> dc_filters;
+  uint32_t sample_rate = 0; size_t channel_count = 0;
+  static double mode_hz(uint32_t m) { return m == 1 ? 1.0 : (m == 3 ? 20.0 : 5.0); }  // DcFilterMode::hz; Off -> Default
+  GainEffect() { gain.from_description({fourcc("gain"), 0.000001f, 15.848932f, 1.0f, ParamScaling{ParamScaling::Decibel, -60.0f, 24.0f}}); }
+  GainEffect(float gain_db, uint32_t dc_mode) : GainEffect() {  // with_parameters (gain.rs:97-104)
+    gain.init_value(db_to_linear(std::min(std::max(gain_db, -60.0f), 24.0f)));
+    dc_filter_mode = dc_mode;
+  }
+  const char* name() const override { return "Gain"; }
+  size_t weight() const override { return 1; }
+  bool initialize(uint32_t sr, size_t ch, size_t) override {
+    sample_rate = sr; channel_count = ch;
+    gain.set_sample_rate(sr);
+    dc_filters.assign(ch, DcFilter(sr, mode_hz(dc_filter_mode)));
+    return true;
+  }
+  void process(float* buf, size_t len, uint64_t) override {
+    if (dc_filter_mode != 0)
+      for (size_t ch = 0; ch < channel_count; ++ch)
+        for (size_t i = ch; i < len; i += channel_count) buf[i] = (float)dc_filters[ch].process_sample((double)buf[i]);
+    if (gain.need_ramp()) {
+      for (size_t i = 0; i + channel_count <= len; i += channel_count) {
+        float g = gain.next_value();
+        for (size_t ch = 0; ch < channel_count; ++ch) buf[i + ch] *= g;
+      }
+    } else {
+      scale_buffer(buf, len, gain.target_value());
+    }
+  }
+  bool process_tail(size_t& f) const override {
+    f = dc_filter_mode != 0 ? (size_t)sample_rate / (size_t)mode_hz(dc_filter_mode) : 0;
+    return true;
+  }
+  bool process_parameter_update(uint32_t id, const ParamUpdate& u) override {
+    if (id == fourcc("gain")) gain.apply_update(u);
+    else if (id == fourcc("dcfm")) {
+      dc_filter_mode = enum_from_update(u, 4);
+      if (dc_filter_mode != 0) for (auto& f : dc_filters) f.r = 1.0 - (6.28318530717958647692 * mode_hz(dc_filter_mode) / (double)sample_rate);
+      else for (auto& f : dc_filters) f.reset();
+    } else return false;
+    return true;
+  }
+};
+
+// ---- src/effect/pan.rs:17-192 ----------------------------------------------------------------------------------
+struct PanningEffect : Effect {
+  size_t channel_count = 0;
+  SmoothedParam<ExpSmoothed> pan, width;
+  bool invert_l = false, invert_r = false;
+  PanningEffect() {
+    pan.from_description({fourcc("pan "), -1.0f, 1.0f, 0.0f, SC_LIN});
+    width.from_description({fourcc("wdth"), 0.0f, 2.0f, 1.0f, SC_LIN});
+  }
+  const char* name() const override { return "Panning"; }
+  size_t weight() const override { return 1; }
+  bool initialize(uint32_t sr, size_t ch, size_t) override {
+    if (ch != 2) return false;
+    channel_count = ch;
+    pan.set_sample_rate(sr); width.set_sample_rate(sr);
+    return true;
+  }
+  void process(float* buf, size_t len, uint64_t) override {
+    const float il = invert_l ? -1.0f : 1.0f, ir = invert_r ? -1.0f : 1.0f;
+    const bool has_invert = il < 0.0f || ir < 0.0f;
+    const bool pan_ramping = pan.need_ramp(), width_ramping = width.need_ramp();
+    if (!has_invert && !pan_ramping && !width_ramping && std::fabs(pan.target_value()) < 1e-6f &&
+        std::fabs(width.target_value() - 1.0f) < 1e-6f)
+      return;
+    for (size_t i = 0; i + 2 <= len; i += 2) {
+      float l = buf[i] * il, r = buf[i + 1] * ir;
+      float w = width_ramping ? width.next_value() : width.target_value();
+      if (std::fabs(w - 1.0f) > 1e-6f) {
+        float mid = (l + r) * 0.5f, side = (l - r) * 0.5f;
+        l = mid + side * w;
+        r = mid - side * w;
+      }
+      float p = pan_ramping ? pan.next_value() : pan.target_value();
+      if (std::fabs(p) > 1e-6f) {
+        float pl, pr;
+        panning_factors(p, pl, pr);
+        l *= pl; r *= pr;
+      }
+      buf[i] = l; buf[i + 1] = r;
+    }
+  }
+  bool process_tail(size_t& f) const override { f = 0; return true; }
+  bool process_parameter_update(uint32_t id, const ParamUpdate& u) override {
+    auto as_bool = [](const ParamUpdate& x) { return x.normalized ? std::min(std::max(x.value, 0.0f), 1.0f) >= 0.5f : x.value != 0.0f; };
+    if (id == fourcc("pan ")) pan.apply_update(u);
+    else if (id == fourcc("wdth")) width.apply_update(u);
+    else if (id == fourcc("invl")) invert_l = as_bool(u);
+    else if (id == fourcc("invr")) invert_r = as_bool(u);
+    else return false;
+    return true;
+  }
+};
+
 // ---- src/effect/eq5.rs:19-364 ------------------------------------------------------------------------------------
 struct Eq5Effect : Effect {
   uint32_t sample_rate = 0; size_t channel_count = 0;

@@ -30,7 +30,7 @@ ERR_CUDA = 100
 ERR_UNSUPPORTED = 101
 
 # pb200_effect_kind
-FX_FILTER, FX_EQ5, FX_COMPRESSOR, FX_CHORUS, FX_DELAY, FX_REVERB = 1, 2, 3, 4, 5, 6
+FX_FILTER, FX_EQ5, FX_COMPRESSOR, FX_CHORUS, FX_DELAY, FX_REVERB, FX_GAIN, FX_PANNING = 1, 2, 3, 4, 5, 6, 7, 8
 
 # pb200_event_kind
 EV_STOP_SOURCE = 1
@@ -66,6 +66,10 @@ class CompressorParams(C.Structure):
 class ChorusParams(C.Structure):
     _fields_ = [("rate", F32), ("phase", F32), ("depth", F32), ("feedback", F32), ("delay", F32),
                 ("wet", F32), ("filter_type", U32), ("filter_freq", F32), ("filter_resonance", F32)]
+
+
+class GainParams(C.Structure):
+    _fields_ = [("gain_db", F32), ("dc_filter_mode", U32)]
 
 
 class ReverbParams(C.Structure):

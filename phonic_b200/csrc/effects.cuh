@@ -690,6 +690,69 @@ PB_DEV void reverb_process(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb, 
   }
 }
 
+// ---- GainEffect::process (gain.rs:148-170): DC filter per channel (serial one-pole, warps 0/1), then the gain -----
+PB_DEV void gain_process(GainState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t tid, uint32_t nt) {
+  if (s.dc_mode != 0) {
+    if (tid == 0 || tid == 32) {  // DcFilter::process_sample (dc.rs:84-88), f64 state, one thread per channel
+      const uint32_t ch = tid >> 5;
+      double x1 = s.dc_x1[ch], y1 = s.dc_y1[ch];
+      const double r = s.dc_r;
+      for (uint32_t f = 0; f < frames; ++f) {
+        const double x = (double)cb.ch[ch][pidx(f)];
+        y1 = x - x1 + r * y1;
+        x1 = x;
+        cb.ch[ch][pidx(f)] = (float)y1;
+      }
+      s.dc_x1[ch] = x1; s.dc_y1[ch] = y1;
+    }
+    __syncthreads();
+  }
+  if (exp_need_ramp(s.gain, cx.comp)) {
+    if (tid == 0) {
+      for (uint32_t f = 0; f < frames; ++f) {
+        const float g = exp_next(s.gain, cx.comp);
+        CB_L(f) *= g; CB_R(f) *= g;
+      }
+    }
+  } else {
+    const float g = s.gain.target;  // scale_buffer
+    for (uint32_t f = tid; f < frames; f += nt) { CB_L(f) *= g; CB_R(f) *= g; }
+  }
+}
+
+// ---- PanningEffect::process (pan.rs:105-160) ----------------------------------------------------------------------
+PB_DEV void pan_process(PanState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t tid, uint32_t nt) {
+  const float il = s.invert_l ? -1.0f : 1.0f, ir = s.invert_r ? -1.0f : 1.0f;
+  const bool has_invert = il < 0.0f || ir < 0.0f;
+  const bool pan_ramping = exp_need_ramp(s.pan, cx.comp), width_ramping = exp_need_ramp(s.width, cx.comp);
+  if (!has_invert && !pan_ramping && !width_ramping && fabsf(s.pan.target) < 1e-6f && fabsf(s.width.target - 1.0f) < 1e-6f) return;
+  auto frame = [&](uint32_t f, float w, float p) {
+    float l = CB_L(f) * il, r = CB_R(f) * ir;
+    if (fabsf(w - 1.0f) > 1e-6f) {
+      const float mid = (l + r) * 0.5f, side = (l - r) * 0.5f;
+      l = mid + side * w;
+      r = mid - side * w;
+    }
+    if (fabsf(p) > 1e-6f) {
+      float pl, pr;
+      panning_factors(p, pl, pr);
+      l *= pl; r *= pr;
+    }
+    CB_L(f) = l; CB_R(f) = r;
+  };
+  if (pan_ramping || width_ramping) {
+    if (tid == 0)
+      for (uint32_t f = 0; f < frames; ++f) {
+        const float w = width_ramping ? exp_next(s.width, cx.comp) : s.width.target;
+        const float p = pan_ramping ? exp_next(s.pan, cx.comp) : s.pan.target;
+        frame(f, w, p);
+      }
+  } else {
+    const float w = s.width.target, p = s.pan.target;
+    for (uint32_t f = tid; f < frames; f += nt) frame(f, w, p);
+  }
+}
+
 // ---- Effect::process_tail (Option<usize>): returns false for None -------------------------------------------
 PB_DEV uint64_t f32_ceil_u64(float v) { float c = ceilf(v); return c > 0.0f ? (uint64_t)c : 0ull; }
 PB_DEV bool fx_process_tail(const FxHeader& h, const FxCtx& cx, uint64_t& frames) {
@@ -698,6 +761,12 @@ PB_DEV bool fx_process_tail(const FxHeader& h, const FxCtx& cx, uint64_t& frames
   switch (h.kind) {
     case FX_FILTER: frames = cx.sample_rate / 10; return true;
     case FX_EQ5: frames = cx.sample_rate / 5; return true;
+    case FX_GAIN: {
+      const GainState& s = *(const GainState*)st;
+      frames = s.dc_mode != 0 ? (uint64_t)cx.sample_rate / (s.dc_mode == 1 ? 1u : (s.dc_mode == 3 ? 20u : 5u)) : 0ull;
+      return true;
+    }
+    case FX_PANNING: frames = 0; return true;
     case FX_COMPRESSOR: {
       const CompState& s = *(const CompState*)st;
       frames = f32_ceil_u64(s.lookahead_time * srf) + f32_ceil_u64(s.release_time * srf);
@@ -752,6 +821,24 @@ PB_DEV void fx_apply_param(FxHeader& h, const FxCtx& cx, const FxParamEvent& e) 
   const float v = e.value;
 #define CC4(a, b, c, d) (((uint32_t)(a) << 24) | ((uint32_t)(b) << 16) | ((uint32_t)(c) << 8) | (uint32_t)(d))
   switch (h.kind) {
+    case FX_GAIN: {
+      GainState& s = *(GainState*)st;
+      if (id == CC4('g', 'a', 'i', 'n')) exp_set_target(s.gain, v, cx.comp);
+      else if (id == CC4('d', 'c', 'f', 'm')) {
+        s.dc_mode = (uint32_t)v & 3u;
+        if (s.dc_mode != 0) s.dc_r = 1.0 - (6.28318530717958647692 * (s.dc_mode == 1 ? 1.0 : (s.dc_mode == 3 ? 20.0 : 5.0)) / (double)cx.sample_rate);
+        else { s.dc_x1[0] = s.dc_x1[1] = 0.0; s.dc_y1[0] = s.dc_y1[1] = 0.0; }
+      }
+      break;
+    }
+    case FX_PANNING: {
+      PanState& s = *(PanState*)st;
+      if (id == CC4('p', 'a', 'n', ' ')) exp_set_target(s.pan, v, cx.comp);
+      else if (id == CC4('w', 'd', 't', 'h')) exp_set_target(s.width, v, cx.comp);
+      else if (id == CC4('i', 'n', 'v', 'l')) s.invert_l = v != 0.0f;
+      else if (id == CC4('i', 'n', 'v', 'r')) s.invert_r = v != 0.0f;
+      break;
+    }
     case FX_FILTER: {
       FilterState& s = *(FilterState*)st;
       if (id == CC4('t', 'y', 'p', 'e')) {
@@ -836,6 +923,7 @@ PB_DEV void fx_apply_param(FxHeader& h, const FxCtx& cx, const FxParamEvent& e) 
 #undef CC4
 }
 
+constexpr uint32_t FX_THREADS_FULL = 256;  // threads of the mixer CTA (== FX_THREADS in mixer_kernel.cuh)
 // Effect::process dispatch, called by every thread of the mixer CTA
 PB_DEV void fx_process(const FxHeader& h, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t tid) {
   const uint32_t lane = tid & 31, warp = tid >> 5;
@@ -843,6 +931,8 @@ PB_DEV void fx_process(const FxHeader& h, const FxCtx& cx, const ChunkBuf& cb, u
   switch (h.kind) {
     case FX_FILTER: filter_process(*(FilterState*)st, cx, cb, frames, lane, warp); break;
     case FX_EQ5: eq5_process(*(Eq5State*)st, cx, cb, frames, lane, warp); break;
+    case FX_GAIN: gain_process(*(GainState*)st, cx, cb, frames, tid, FX_THREADS_FULL); break;
+    case FX_PANNING: pan_process(*(PanState*)st, cx, cb, frames, tid, FX_THREADS_FULL); break;
     case FX_COMPRESSOR: if (tid == 0) comp_process(*(CompState*)st, cx, cb, frames); break;
     case FX_CHORUS: if (tid == 0) chorus_process(*(ChorusState*)st, cx, cb, frames); break;
     case FX_DELAY: if (tid == 0) delay_process(*(DelayState*)st, cx, cb, frames); break;

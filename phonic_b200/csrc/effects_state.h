@@ -62,6 +62,19 @@ struct DelayState {  // src/effect/delay.rs:83-109
   float fb_l, fb_r;
 };
 
+struct GainState {  // src/effect/gain.rs:51-60
+  ExpSm gain;
+  uint32_t dc_mode;          // GainEffectDcFilterMode: 0 Off 1 Slow 2 Default 3 Fast
+  uint32_t _pad;
+  double dc_r;               // DcFilter::r (shared by the channels)
+  double dc_x1[2], dc_y1[2];
+};
+
+struct PanState {  // src/effect/pan.rs:17-25
+  ExpSm pan, width;
+  uint32_t invert_l, invert_r;
+};
+
 struct RvLine { uint32_t aux, size, count, delay; double depth; double feedback[2]; double vib_phase[2]; };
 struct RvAllpass { uint32_t aux, size, delay, write_pos; };
 struct ReverbState {  // src/effect/reverb.rs:38-72

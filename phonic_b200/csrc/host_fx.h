@@ -33,18 +33,27 @@ inline float db_to_linear(float v) {
 struct ParamDesc {
   uint32_t id;
   float min, max;
-  int scaling;  // 0 linear, 1 exponential(a), 2 enum(count = max + 1)
+  int scaling;  // 0 linear, 1 exponential(a), 2 enum(count = max + 1), 3 decibel(a = min dB, b = max dB), 4 boolean
   float a;
+  float b = 0.0f;
 };
 inline float denormalize(const ParamDesc& d, float n) {
   n = std::min(std::max(n, 0.0f), 1.0f);
   if (d.scaling == 2) return std::round(n * d.max);
-  float s = d.scaling == 1 ? std::pow(n, d.a) : n;
+  if (d.scaling == 4) return n >= 0.5f ? 1.0f : 0.0f;  // BooleanParameter::denormalize_value (boolean.rs:83-86)
+  float s = n;
+  if (d.scaling == 1) s = std::pow(n, d.a);
+  else if (d.scaling == 3) {  // ParameterScaling::Decibel (scaling.rs:64-72)
+    const float db = d.a + n * (d.b - d.a);
+    const float lo = db_to_linear(d.a), hi = db_to_linear(d.b);
+    s = (db_to_linear(db) - lo) / (hi - lo);
+  }
   return d.min + s * (d.max - d.min);
 }
 inline float resolve_plain(const ParamDesc& d, float v, bool normalized) {
   if (normalized) return denormalize(d, v);
   if (d.scaling == 2) return std::min(std::max(std::round(v), 0.0f), d.max);
+  if (d.scaling == 4) return v != 0.0f ? 1.0f : 0.0f;
   return std::min(std::max(v, d.min), d.max);
 }
 
@@ -78,8 +87,13 @@ inline const std::vector<ParamDesc>& param_table(uint32_t kind) {
       {cc4("lfos"), 0, 6, 2, 0}, {cc4("lfdt"), -1.0f, 1.0f, 0, 0}, {cc4("ldfb"), -1.0f, 1.0f, 0, 0},
       {cc4("lfdf"), -1.0f, 1.0f, 0, 0}};
   static const std::vector<ParamDesc> reverb = {{cc4("room"), 0.0f, 1.0f, 0, 0}, {cc4("wet "), 0.0f, 1.0f, 0, 0}};
+  static const std::vector<ParamDesc> gain = {{cc4("gain"), 0.000001f, 15.848932f, 3, -60.0f, 24.0f}, {cc4("dcfm"), 0, 3, 2, 0}};
+  static const std::vector<ParamDesc> panning = {{cc4("pan "), -1.0f, 1.0f, 0, 0}, {cc4("wdth"), 0.0f, 2.0f, 0, 0},
+                                                 {cc4("invl"), 0, 1, 4, 0}, {cc4("invr"), 0, 1, 4, 0}};
   static const std::vector<ParamDesc> none;
   switch (kind) {
+    case FX_GAIN: return gain;
+    case FX_PANNING: return panning;
     case FX_FILTER: return filter;
     case FX_EQ5: return eq5;
     case FX_COMPRESSOR: return comp;
@@ -214,6 +228,28 @@ inline FxBuild build_compressor(const pb200_compressor_params* p, uint32_t sr) {
   s.aux_capacity_frames = next_pow2(ceil_u32(0.2f * (float)sr) + 1);
   s.aux = 0;
   b.aux_doubles = (size_t)s.aux_capacity_frames * 2;
+  return b;
+}
+
+inline double dc_mode_hz(uint32_t m) { return m == 1 ? 1.0 : (m == 3 ? 20.0 : 5.0); }  // DcFilterMode::hz; Off -> Default
+
+inline FxBuild build_gain(const pb200_gain_params* p, uint32_t sr) {  // gain.rs:85-146
+  FxBuild b;
+  GainState& s = blob<GainState>(b);
+  if (p && p->dc_filter_mode > 3) { b.code = PB200_ERR_PARAMETER; b.error = "bad DC filter mode"; return b; }
+  s.gain = exp_init(p ? db_to_linear(std::min(std::max(p->gain_db, -60.0f), 24.0f)) : 1.0f);
+  s.dc_mode = p ? p->dc_filter_mode : 0;
+  s.dc_r = 1.0 - (6.28318530717958647692 * dc_mode_hz(s.dc_mode) / (double)sr);
+  s.dc_x1[0] = s.dc_x1[1] = s.dc_y1[0] = s.dc_y1[1] = 0.0;
+  return b;
+}
+
+inline FxBuild build_panning() {  // pan.rs:52-60
+  FxBuild b;
+  PanState& s = blob<PanState>(b);
+  s.pan = exp_init(0.0f);
+  s.width = exp_init(1.0f);
+  s.invert_l = s.invert_r = 0;
   return b;
 }
 

@@ -616,6 +616,14 @@ int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const voi
       if (!params || size != sizeof(pb200_reverb_params)) return fail(r, PB200_ERR_PARAMETER, "reverb needs explicit fpd/vib_phase state");
       b = pbh::build_reverb((const pb200_reverb_params*)params, sr);
       break;
+    case PB200_FX_GAIN:
+      if (params && size != sizeof(pb200_gain_params)) return fail(r, PB200_ERR_PARAMETER, "bad gain params size");
+      b = pbh::build_gain((const pb200_gain_params*)params, sr);
+      break;
+    case PB200_FX_PANNING:
+      if (params) return fail(r, PB200_ERR_PARAMETER, "PanningEffect has no parameter constructor");
+      b = pbh::build_panning();
+      break;
     default: return fail(r, PB200_ERR_PARAMETER, "unknown effect kind");
   }
   if (b.code) return fail(r, b.code, b.error);

@@ -146,6 +146,19 @@ class ReverbEffect:
     vib_phase: Sequence[float] = field(default_factory=lambda: [0.1 + 0.37 * i for i in range(16)])
 
 
+@dataclass
+class GainEffect:
+    """GainEffect::with_parameters(gain_db, dc_mode) (src/effect/gain.rs:97-104); default => GainEffect::new()."""
+    gain_db: float = 0.0
+    dc_filter_mode: int = 0       # GainEffectDcFilterMode: 0 Off 1 Slow 2 Default 3 Fast
+    default: bool = False
+
+
+@dataclass
+class PanningEffect:
+    """PanningEffect::new() (src/effect/pan.rs:52-60); parameters 'pan ', 'wdth', 'invl', 'invr' via set_parameter."""
+
+
 class _Handle:
     def __init__(self, player: "Player", ident: int):
         self._p = player
@@ -322,6 +335,10 @@ class Player:
         elif isinstance(effect, ReverbEffect):
             kind = A.FX_REVERB
             p = A.ReverbParams(effect.room_size, effect.wet, (A.U32 * 2)(*effect.fpd), (A.F64 * 16)(*effect.vib_phase))
+        elif isinstance(effect, GainEffect):
+            kind, p = A.FX_GAIN, (None if effect.default else A.GainParams(effect.gain_db, effect.dc_filter_mode))
+        elif isinstance(effect, PanningEffect):
+            kind, p = A.FX_PANNING, None
         else:
             raise TypeError(effect)
         if p is None:

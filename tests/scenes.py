@@ -6,7 +6,8 @@ import numpy as np
 
 from phonic_b200 import workloads as W
 from phonic_b200.player import (AhdsrParameters, ChorusEffect, CompressorEffect, DelayEffect, Eq5Effect,
-                                FilePlaybackOptions, FilterEffect, GeneratorPlaybackOptions, GranularParameters, Player, ReverbEffect)
+                                FilePlaybackOptions, FilterEffect, GainEffect, GeneratorPlaybackOptions, GranularParameters, PanningEffect,
+                                Player, ReverbEffect)
 
 SR = 48000
 BLOCK = 1024
@@ -207,9 +208,9 @@ def filter_automation(p: Player):
     return {"frames": 100 * BLOCK}
 
 
-def fx_scene(effect, seconds=3.0, param_events=(), seed=10):
+def fx_scene(effect, seconds=3.0, param_events=(), seed=10, buffer_seconds=1.0):
     def build(p: Player):
-        b = p.upload_buffer(tone(int(44100 * 1.0), 44100, channels=2, seed=seed), 44100)
+        b = p.upload_buffer(tone(int(44100 * buffer_seconds), 44100, channels=2, seed=seed), 44100)
         p.play_file_source(b, FilePlaybackOptions(volume=0.8))
         fx = p.add_effect(effect)
         for (pid, val, t) in param_events:
@@ -267,6 +268,9 @@ SCENES = {
     "fx_limiter": fx_scene(CompressorEffect.new_limiter()),
     "fx_chorus": fx_scene(ChorusEffect(), param_events=[("rate", 2.0, 30000), ("dlay", 20.0, 40000)]),
     "fx_delay": fx_scene(DelayEffect(), seconds=4.0, param_events=[("dlay", 120.0, 0), ("fdbk", 0.6, 0), ("driv", 0.3, 50000), ("mode", 1, 90000)]),
+    "fx_gain_dc": fx_scene(GainEffect(-4.5, 2), param_events=[("gain", 0.3, 20000), ("dcfm", 3, 40000), ("dcfm", 0, 70000), ("gain", 2.0, 90000)], buffer_seconds=2.8),
+    "fx_panning": fx_scene(PanningEffect(), param_events=[("wdth", 0.4, 0), ("pan ", -0.6, 15000), ("invr", 1, 50000), ("wdth", 1.7, 80000),
+                                                           ("pan ", 0.0, 100000), ("invr", 0, 110000), ("wdth", 1.0, 120000)], buffer_seconds=2.8),
     "fx_reverb": fx_scene(ReverbEffect(0.6, 0.35), seconds=4.0, param_events=[("room", 0.8, 60000)]),
     "submixers_cfg3_small": submixers_cfg3_small,
     "submixers_cfg5_small": submixers_cfg5_small,
@@ -274,7 +278,7 @@ SCENES = {
 }
 
 # scenes whose whole path is +,-,*,/,sqrt in the reference's order: must be bit-exact on device
-BIT_EXACT = {"file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
+BIT_EXACT = {"fx_gain_dc", "fx_panning", "file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
              "sampler_no_envelope", "hq_equal_rates", "gran_cloud", "gran_resampled_fixed", "gran_sequential_loop", "gran_dense"}
 # bit-exact voice path + time-invariant biquads evaluated by the f64 block scan (exact up to O(1e-16)
 # relative reassociation error before the f32 cast): at most a rare last-bit flip
