@@ -104,7 +104,8 @@ enum pb200_effect_kind {
   PB200_FX_DELAY = 5,      /* DelayEffect      src/effect/delay.rs      */
   PB200_FX_REVERB = 6,     /* ReverbEffect     src/effect/reverb.rs     */
   PB200_FX_GAIN = 7,       /* GainEffect       src/effect/gain.rs       */
-  PB200_FX_PANNING = 8     /* PanningEffect    src/effect/pan.rs        */
+  PB200_FX_PANNING = 8,    /* PanningEffect    src/effect/pan.rs        */
+  PB200_FX_GATE = 9        /* GateEffect       src/effect/gate.rs       */
 };
 
 /* FilterEffect::with_parameters(filter_type, cutoff, q) (filter.rs:104-116) */
@@ -149,6 +150,13 @@ typedef struct pb200_gain_params {
   float gain_db;           /* clamped to [-60, 24] */
   uint32_t dc_filter_mode; /* GainEffectDcFilterMode: 0 Off 1 Slow (1 Hz) 2 Default (5 Hz) 3 Fast (20 Hz) */
 } pb200_gain_params;
+
+/* GateEffect::with_parameters(threshold, attack, hold, release, range) (gate.rs:67-81): dB, seconds, seconds,
+ * seconds, dB; out-of-range values are PB200_ERR_PARAMETER (the reference asserts). Parameters 'thrs', 'attk',
+ * 'hold', 'rels', 'rnge'. */
+typedef struct pb200_gate_params {
+  float threshold, attack_time, hold_time, release_time, range;
+} pb200_gate_params;
 
 /* PanningEffect has only PanningEffect::new() (pan.rs:52-60): pass params = NULL and use
  * PB200_EV_SET_EFFECT_PARAMETER events ('pan ', 'wdth', 'invl', 'invr'; booleans: value != 0). */

@@ -172,6 +172,17 @@ int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const voi
       if (params) return fail(r, PB200_ERR_PARAMETER, "PanningEffect has no parameter constructor");
       fx = std::make_unique<PanningEffect>();
       break;
+    case PB200_FX_GATE:
+      if (params) {
+        if (size != sizeof(pb200_gate_params)) return fail(r, PB200_ERR_PARAMETER, "bad gate params size");
+        auto* p = (const pb200_gate_params*)params;
+        if (!(p->threshold >= -60.0f && p->threshold <= 0.0f) || !(p->attack_time >= 0.001f && p->attack_time <= 0.5f) ||
+            !(p->hold_time >= 0.0f && p->hold_time <= 2.0f) || !(p->release_time >= 0.01f && p->release_time <= 2.0f) ||
+            !(p->range >= -60.0f && p->range <= 0.0f))
+          return fail(r, PB200_ERR_PARAMETER, "Value out of bounds");
+        fx = std::make_unique<GateEffect>(p->threshold, p->attack_time, p->hold_time, p->release_time, p->range);
+      } else fx = std::make_unique<GateEffect>();
+      break;
     default: return fail(r, PB200_ERR_PARAMETER, "unknown effect kind");
   }
   // Player::add_effect: effect.initialize(sr, ch, MAX_MIX_BUFFER_SAMPLES / ch) (player.rs:905-909)

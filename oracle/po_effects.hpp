@@ -395,6 +395,77 @@ struct PanningEffect : Effect {
   }
 };
 
+// ---- src/effect/gate.rs:12-224 ---------------------------------------------------------------------------------
+struct GateEffect : Effect {
+  PlainParam threshold, attack_time, hold_time, release_time, range;
+  EnvelopeFollower envelope_follower;
+  uint32_t hold_counter = 0;
+  float gate_gain_db = -60.0f, attack_coeff = 0.0f, release_coeff = 0.0f;
+  uint32_t sample_rate = 0; size_t channel_count = 0;
+  GateEffect() {
+    threshold.from_description({fourcc("thrs"), -60.0f, 0.0f, -30.0f, SC_LIN});
+    attack_time.from_description({fourcc("attk"), 0.001f, 0.5f, 0.005f, SC_LIN});
+    hold_time.from_description({fourcc("hold"), 0.0f, 2.0f, 0.1f, SC_LIN});
+    release_time.from_description({fourcc("rels"), 0.01f, 2.0f, 0.2f, SC_LIN});
+    range.from_description({fourcc("rnge"), -60.0f, 0.0f, -60.0f, SC_LIN});
+  }
+  GateEffect(float thr, float atk, float hold, float rel, float rng) : GateEffect() {
+    threshold.value = thr; attack_time.value = atk; hold_time.value = hold; release_time.value = rel; range.value = rng;
+  }
+  void update_coefficients() {  // gate.rs:83-95
+    if (sample_rate > 0) {
+      envelope_follower.set_attack_time(attack_time.value);
+      envelope_follower.set_release_time(release_time.value);
+      float sr = (float)sample_rate;
+      attack_coeff = std::exp(-1.0f / (attack_time.value * sr));
+      release_coeff = std::exp(-1.0f / (release_time.value * sr));
+    }
+  }
+  const char* name() const override { return "Gate"; }
+  size_t weight() const override { return 2; }
+  bool initialize(uint32_t sr, size_t ch, size_t) override {
+    if (ch != 2) return false;
+    sample_rate = sr; channel_count = ch;
+    envelope_follower = EnvelopeFollower(sr, attack_time.value, release_time.value);
+    envelope_follower.reset(-120.0f);
+    hold_counter = 0;
+    gate_gain_db = range.value;
+    update_coefficients();
+    return true;
+  }
+  void process(float* buf, size_t len, uint64_t) override {
+    const float thr = threshold.value, range_db = range.value;
+    const uint32_t hold_samples = f64_as_u32((double)(hold_time.value * (float)sample_rate));
+    for (size_t i = 0; i + 2 <= len; i += 2) {
+      float frame_peak = std::max(std::fabs(buf[i]), std::fabs(buf[i + 1]));
+      float input_db = frame_peak > 1e-6f ? 20.0f * std::log10(frame_peak) : -120.0f;
+      float envelope = envelope_follower.run(input_db);
+      float target_gain_db;
+      if (envelope >= thr) { hold_counter = hold_samples; target_gain_db = 0.0f; }
+      else if (hold_counter > 0) { hold_counter -= 1; target_gain_db = 0.0f; }
+      else target_gain_db = range_db;
+      if (target_gain_db > gate_gain_db) gate_gain_db = attack_coeff * gate_gain_db + (1.0f - attack_coeff) * target_gain_db;
+      else gate_gain_db = release_coeff * gate_gain_db + (1.0f - release_coeff) * target_gain_db;
+      float gain = gate_gain_db <= -60.0f ? 0.0f : db_to_linear(gate_gain_db);
+      buf[i] *= gain; buf[i + 1] *= gain;
+    }
+  }
+  bool process_tail(size_t& f) const override {
+    f = (size_t)std::ceil(hold_time.value * (float)sample_rate) + (size_t)std::ceil(release_time.value * (float)sample_rate);
+    return true;
+  }
+  bool process_parameter_update(uint32_t id, const ParamUpdate& u) override {
+    if (id == fourcc("thrs")) threshold.apply_update(u);
+    else if (id == fourcc("attk")) attack_time.apply_update(u);
+    else if (id == fourcc("hold")) hold_time.apply_update(u);
+    else if (id == fourcc("rels")) release_time.apply_update(u);
+    else if (id == fourcc("rnge")) range.apply_update(u);
+    else return false;
+    update_coefficients();
+    return true;
+  }
+};
+
 // ---- src/effect/eq5.rs:19-364 ------------------------------------------------------------------------------------
 struct Eq5Effect : Effect {
   uint32_t sample_rate = 0; size_t channel_count = 0;

@@ -30,7 +30,7 @@ ERR_CUDA = 100
 ERR_UNSUPPORTED = 101
 
 # pb200_effect_kind
-FX_FILTER, FX_EQ5, FX_COMPRESSOR, FX_CHORUS, FX_DELAY, FX_REVERB, FX_GAIN, FX_PANNING = 1, 2, 3, 4, 5, 6, 7, 8
+FX_FILTER, FX_EQ5, FX_COMPRESSOR, FX_CHORUS, FX_DELAY, FX_REVERB, FX_GAIN, FX_PANNING, FX_GATE = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 # pb200_event_kind
 EV_STOP_SOURCE = 1
@@ -70,6 +70,10 @@ class ChorusParams(C.Structure):
 
 class GainParams(C.Structure):
     _fields_ = [("gain_db", F32), ("dc_filter_mode", U32)]
+
+
+class GateParams(C.Structure):
+    _fields_ = [("threshold", F32), ("attack_time", F32), ("hold_time", F32), ("release_time", F32), ("range", F32)]
 
 
 class ReverbParams(C.Structure):

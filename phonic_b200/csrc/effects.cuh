@@ -720,6 +720,44 @@ PB_DEV void gain_process(GainState& s, const FxCtx& cx, const ChunkBuf& cb, uint
   }
 }
 
+// ---- GateEffect::process (gate.rs:152-198) -----------------------------------------------------------------------
+// Detector level (log10) and the final gain (exp) are per-frame parallel stages around the serial part: the
+// envelope follower, the open / hold / closed state machine and the one-pole gain smoothing, one thread.
+PB_DEV void gate_process(GateState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t tid, uint32_t nt, float* work) {
+  float* level = work;            // input_db, then gate_gain_db per frame
+  for (uint32_t f = tid; f < frames; f += nt) {
+    const float frame_peak = fmaxf(fabsf(CB_L(f)), fabsf(CB_R(f)));
+    level[f] = frame_peak > 1e-6f ? 20.0f * log10f(frame_peak) : -120.0f;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float thr = s.threshold, range_db = s.range;
+    const float hs = s.hold_time * (float)cx.sample_rate;
+    const uint32_t hold_samples = hs >= 4294967295.0f ? 0xFFFFFFFFu : (hs > 0.0f ? (uint32_t)hs : 0u);
+    float cur = s.env_cur, g = s.gate_gain_db;
+    uint32_t hold = s.hold_counter;
+    const float ea = s.env_atk, er = s.env_rel, ac = s.attack_coeff, rc = s.release_coeff;
+    for (uint32_t f = 0; f < frames; ++f) {
+      const float x = level[f];
+      cur = x + (x > cur ? ea : er) * (cur - x);   // EnvelopeFollower::run (envelope.rs:51-60)
+      float target;
+      if (cur >= thr) { hold = hold_samples; target = 0.0f; }
+      else if (hold > 0) { hold -= 1; target = 0.0f; }
+      else target = range_db;
+      if (target > g) g = ac * g + (1.0f - ac) * target;
+      else g = rc * g + (1.0f - rc) * target;
+      level[f] = g;
+    }
+    s.env_cur = cur; s.gate_gain_db = g; s.hold_counter = hold;
+  }
+  __syncthreads();
+  for (uint32_t f = tid; f < frames; f += nt) {
+    const float g = level[f];
+    const float gain = g <= -60.0f ? 0.0f : db_to_linear_dev(g);
+    CB_L(f) *= gain; CB_R(f) *= gain;
+  }
+}
+
 // ---- PanningEffect::process (pan.rs:105-160) ----------------------------------------------------------------------
 PB_DEV void pan_process(PanState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t tid, uint32_t nt) {
   const float il = s.invert_l ? -1.0f : 1.0f, ir = s.invert_r ? -1.0f : 1.0f;
@@ -767,6 +805,11 @@ PB_DEV bool fx_process_tail(const FxHeader& h, const FxCtx& cx, uint64_t& frames
       return true;
     }
     case FX_PANNING: frames = 0; return true;
+    case FX_GATE: {
+      const GateState& s = *(const GateState*)st;
+      frames = f32_ceil_u64(s.hold_time * srf) + f32_ceil_u64(s.release_time * srf);
+      return true;
+    }
     case FX_COMPRESSOR: {
       const CompState& s = *(const CompState*)st;
       frames = f32_ceil_u64(s.lookahead_time * srf) + f32_ceil_u64(s.release_time * srf);
@@ -829,6 +872,20 @@ PB_DEV void fx_apply_param(FxHeader& h, const FxCtx& cx, const FxParamEvent& e) 
         if (s.dc_mode != 0) s.dc_r = 1.0 - (6.28318530717958647692 * (s.dc_mode == 1 ? 1.0 : (s.dc_mode == 3 ? 20.0 : 5.0)) / (double)cx.sample_rate);
         else { s.dc_x1[0] = s.dc_x1[1] = 0.0; s.dc_y1[0] = s.dc_y1[1] = 0.0; }
       }
+      break;
+    }
+    case FX_GATE: {
+      GateState& s = *(GateState*)st;
+      if (id == CC4('t', 'h', 'r', 's')) s.threshold = v;
+      else if (id == CC4('a', 't', 't', 'k')) s.attack_time = v;
+      else if (id == CC4('h', 'o', 'l', 'd')) s.hold_time = v;
+      else if (id == CC4('r', 'e', 'l', 's')) s.release_time = v;
+      else if (id == CC4('r', 'n', 'g', 'e')) s.range = v;
+      const float srf = (float)cx.sample_rate;  // update_coefficients (gate.rs:83-95)
+      s.env_atk = s.attack_time > 0.0f ? expf(-1.0f / (s.attack_time * srf)) : 0.0f;
+      s.env_rel = s.release_time > 0.0f ? expf(-1.0f / (s.release_time * srf)) : 0.0f;
+      s.attack_coeff = expf(-1.0f / (s.attack_time * srf));
+      s.release_coeff = expf(-1.0f / (s.release_time * srf));
       break;
     }
     case FX_PANNING: {

@@ -531,6 +531,7 @@ PB_DEV void fx_process_chunk(const FxHeader& h, const FxCtx& cx, const ChunkBuf&
     case FX_CHORUS: done = chorus_parallel(*(ChorusState*)st, cx, cb, frames, tid, nt, w); break;
     case FX_DELAY: done = delay_parallel(*(DelayState*)st, cx, cb, frames, tid, nt, w); break;
     case FX_REVERB: done = reverb_parallel(*(ReverbState*)st, cx, cb, frames, tid, nt, w); break;
+    case FX_GATE: gate_process(*(GateState*)st, cx, cb, frames, tid, nt, reinterpret_cast<float*>(w.base)); done = true; break;
     default: break;
   }
   if (!done) fx_process(h, cx, cb, frames, tid);

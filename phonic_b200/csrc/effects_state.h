@@ -70,6 +70,13 @@ struct GainState {  // src/effect/gain.rs:51-60
   double dc_x1[2], dc_y1[2];
 };
 
+struct GateState {  // src/effect/gate.rs:12-28
+  float threshold, attack_time, hold_time, release_time, range;
+  float env_cur, env_atk, env_rel;   // EnvelopeFollower (envelope.rs:5-75)
+  float gate_gain_db, attack_coeff, release_coeff;
+  uint32_t hold_counter;
+};
+
 struct PanState {  // src/effect/pan.rs:17-25
   ExpSm pan, width;
   uint32_t invert_l, invert_r;

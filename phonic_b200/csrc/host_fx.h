@@ -90,8 +90,11 @@ inline const std::vector<ParamDesc>& param_table(uint32_t kind) {
   static const std::vector<ParamDesc> gain = {{cc4("gain"), 0.000001f, 15.848932f, 3, -60.0f, 24.0f}, {cc4("dcfm"), 0, 3, 2, 0}};
   static const std::vector<ParamDesc> panning = {{cc4("pan "), -1.0f, 1.0f, 0, 0}, {cc4("wdth"), 0.0f, 2.0f, 0, 0},
                                                  {cc4("invl"), 0, 1, 4, 0}, {cc4("invr"), 0, 1, 4, 0}};
+  static const std::vector<ParamDesc> gate = {{cc4("thrs"), -60.0f, 0.0f, 0, 0}, {cc4("attk"), 0.001f, 0.5f, 0, 0}, {cc4("hold"), 0.0f, 2.0f, 0, 0},
+                                              {cc4("rels"), 0.01f, 2.0f, 0, 0}, {cc4("rnge"), -60.0f, 0.0f, 0, 0}};
   static const std::vector<ParamDesc> none;
   switch (kind) {
+    case FX_GATE: return gate;
     case FX_GAIN: return gain;
     case FX_PANNING: return panning;
     case FX_FILTER: return filter;
@@ -241,6 +244,35 @@ inline FxBuild build_gain(const pb200_gain_params* p, uint32_t sr) {  // gain.rs
   s.dc_mode = p ? p->dc_filter_mode : 0;
   s.dc_r = 1.0 - (6.28318530717958647692 * dc_mode_hz(s.dc_mode) / (double)sr);
   s.dc_x1[0] = s.dc_x1[1] = s.dc_y1[0] = s.dc_y1[1] = 0.0;
+  return b;
+}
+
+// coefficients of GateEffect::update_coefficients (gate.rs:83-95) + EnvelopeFollower::set_*_time (envelope.rs:36-49)
+inline void gate_update_coefficients_h(GateState& s, uint32_t sr) {
+  const float srf = (float)sr;
+  s.env_atk = s.attack_time > 0.0f ? std::exp(-1.0f / (s.attack_time * srf)) : 0.0f;
+  s.env_rel = s.release_time > 0.0f ? std::exp(-1.0f / (s.release_time * srf)) : 0.0f;
+  s.attack_coeff = std::exp(-1.0f / (s.attack_time * srf));
+  s.release_coeff = std::exp(-1.0f / (s.release_time * srf));
+}
+
+inline FxBuild build_gate(const pb200_gate_params* p, uint32_t sr) {  // gate.rs:51-81, 124-150
+  FxBuild b;
+  GateState& s = blob<GateState>(b);
+  s.threshold = p ? p->threshold : -30.0f;
+  s.attack_time = p ? p->attack_time : 0.005f;
+  s.hold_time = p ? p->hold_time : 0.1f;
+  s.release_time = p ? p->release_time : 0.2f;
+  s.range = p ? p->range : -60.0f;
+  if (!(s.threshold >= -60.0f && s.threshold <= 0.0f) || !(s.attack_time >= 0.001f && s.attack_time <= 0.5f) ||
+      !(s.hold_time >= 0.0f && s.hold_time <= 2.0f) || !(s.release_time >= 0.01f && s.release_time <= 2.0f) ||
+      !(s.range >= -60.0f && s.range <= 0.0f)) {
+    b.code = PB200_ERR_PARAMETER; b.error = "Value out of bounds"; return b;
+  }
+  s.env_cur = -120.0f;
+  s.hold_counter = 0;
+  s.gate_gain_db = s.range;
+  gate_update_coefficients_h(s, sr);
   return b;
 }
 

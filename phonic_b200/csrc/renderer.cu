@@ -624,6 +624,10 @@ int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const voi
       if (params) return fail(r, PB200_ERR_PARAMETER, "PanningEffect has no parameter constructor");
       b = pbh::build_panning();
       break;
+    case PB200_FX_GATE:
+      if (params && size != sizeof(pb200_gate_params)) return fail(r, PB200_ERR_PARAMETER, "bad gate params size");
+      b = pbh::build_gate((const pb200_gate_params*)params, sr);
+      break;
     default: return fail(r, PB200_ERR_PARAMETER, "unknown effect kind");
   }
   if (b.code) return fail(r, b.code, b.error);

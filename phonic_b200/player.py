@@ -155,6 +155,17 @@ class GainEffect:
 
 
 @dataclass
+class GateEffect:
+    """GateEffect::with_parameters (src/effect/gate.rs:67-81): dB, s, s, s, dB; default => GateEffect::new()."""
+    threshold: float = -30.0
+    attack_time: float = 0.005
+    hold_time: float = 0.1
+    release_time: float = 0.2
+    range: float = -60.0
+    default: bool = False
+
+
+@dataclass
 class PanningEffect:
     """PanningEffect::new() (src/effect/pan.rs:52-60); parameters 'pan ', 'wdth', 'invl', 'invr' via set_parameter."""
 
@@ -339,6 +350,10 @@ class Player:
             kind, p = A.FX_GAIN, (None if effect.default else A.GainParams(effect.gain_db, effect.dc_filter_mode))
         elif isinstance(effect, PanningEffect):
             kind, p = A.FX_PANNING, None
+        elif isinstance(effect, GateEffect):
+            kind = A.FX_GATE
+            p = None if effect.default else A.GateParams(effect.threshold, effect.attack_time, effect.hold_time,
+                                                         effect.release_time, effect.range)
         else:
             raise TypeError(effect)
         if p is None:

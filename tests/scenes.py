@@ -6,7 +6,7 @@ import numpy as np
 
 from phonic_b200 import workloads as W
 from phonic_b200.player import (AhdsrParameters, ChorusEffect, CompressorEffect, DelayEffect, Eq5Effect,
-                                FilePlaybackOptions, FilterEffect, GainEffect, GeneratorPlaybackOptions, GranularParameters, PanningEffect,
+                                FilePlaybackOptions, FilterEffect, GainEffect, GateEffect, GeneratorPlaybackOptions, GranularParameters, PanningEffect,
                                 Player, ReverbEffect)
 
 SR = 48000
@@ -271,6 +271,8 @@ SCENES = {
     "fx_gain_dc": fx_scene(GainEffect(-4.5, 2), param_events=[("gain", 0.3, 20000), ("dcfm", 3, 40000), ("dcfm", 0, 70000), ("gain", 2.0, 90000)], buffer_seconds=2.8),
     "fx_panning": fx_scene(PanningEffect(), param_events=[("wdth", 0.4, 0), ("pan ", -0.6, 15000), ("invr", 1, 50000), ("wdth", 1.7, 80000),
                                                            ("pan ", 0.0, 100000), ("invr", 0, 110000), ("wdth", 1.0, 120000)], buffer_seconds=2.8),
+    "fx_gate": fx_scene(GateEffect(-22.0, 0.004, 0.03, 0.15, -40.0), param_events=[("thrs", -15.0, 50000), ("rnge", -60.0, 80000), ("hold", 0.2, 100000)],
+                        buffer_seconds=2.8, seed=14),
     "fx_reverb": fx_scene(ReverbEffect(0.6, 0.35), seconds=4.0, param_events=[("room", 0.8, 60000)]),
     "submixers_cfg3_small": submixers_cfg3_small,
     "submixers_cfg5_small": submixers_cfg5_small,
