@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- voice-samples/s of the offline resample+FX+mix path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg5shard] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|sinc|cfg5shard] [--impl reference]
 
 A *step* is one complete offline render of the workload (cfg2: 256 Sampler voices with AHDSR + glide,
 cubic 44.1->48 kHz resampling, FilterEffect LP on the bus, "10 s" = 469 WavStream blocks = 480 256
@@ -54,6 +54,10 @@ def workload_spec(name):
     if name == "cfg5shard":
         return dict(voices=8192, n_mixers=64, seconds=10, desc="cfg5 per-GPU shard: 8192 voices in 64 sub-mixer subtrees, "
                     "10 s (480256 frames)")
+    if name == "cfg3":
+        return dict(voices=4096, n_mixers=64, seconds=60, effects="cfg3", time_scale=6.0,
+                    desc="cfg3: 4096 voices over 64 sub-mixers (8 Samplers x 8 voices each), Eq5 + Compressor + Chorus per "
+                    "sub-mixer, 60 s (2880512 frames); cfg2 voice events stretched x6 so notes span the render")
     if name == "cfg4":
         return dict(voices=160, n_mixers=0, seconds=10, desc="cfg4: granular, 160 voices x 100 grains/s x 100 ms Hann grains "
                     "(16k grains/s) from a 362835-frame mono buffer, AHDSR, 10 s (480256 frames)")
@@ -94,7 +98,8 @@ def build_scene(player, name, rank=0, as_subtree=False):
     elif name == "sinc":
         W.build_sinc_bank(player, spec["voices"], buffer=buf)
     else:
-        W.build_subtrees(player, spec["n_mixers"], spec["voices"] // spec["n_mixers"], W.VoiceBankSpec(), effects="none",
+        W.build_subtrees(player, spec["n_mixers"], spec["voices"] // spec["n_mixers"], W.VoiceBankSpec(),
+                         effects=spec.get("effects", "none"), time_scale=spec.get("time_scale", 1.0),
                          seed_base=100000 * rank, buffer=buf)
     return spec["voices"]
 
@@ -178,6 +183,10 @@ def build_cpu_sample(p, name, rank=0, as_subtree=False):
     if name == "sinc":
         W.build_sinc_bank(p, 16, buffer=sample_buffer())
         return 16, "sinc bank with 16 of 1024 voices"
+    if name == "cfg3":
+        W.build_subtrees(p, 2, 64, W.VoiceBankSpec(), effects="cfg3", time_scale=spec["time_scale"], seed_base=100000 * rank,
+                         buffer=sample_buffer())
+        return 128, "cfg3 with 128 of 4096 voices (2 of 64 sub-mixers, same per-voice events and effect chains)"
     W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none", seed_base=100000 * rank, buffer=sample_buffer())
     return 512, f"{name} with 512 of {spec['voices']} voices (4 sub-mixers x 128, same per-voice events)"
 

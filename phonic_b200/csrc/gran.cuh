@@ -333,32 +333,61 @@ struct GranReplay {
   uint32_t rec_cap, vrec_cap, n_tiles, storage_cap;
 };
 
-// `n` frames of a granular voice starting at block-relative frame c.hq_off: the ordered sum of the live grains'
-// contributions, then the AHDSR exactly as voice_frames() applies it (voice.rs:470-486).
+// Up to GRAN_CHUNK frames of a granular voice starting at block-relative frame c.hq_off: the ordered sum of the live
+// grains' contributions (grains outer, frames inner -- per frame the adds keep the activation order), then the AHDSR
+// exactly as voice_frames() applies it (voice.rs:470-486); the result is stored to / added to `out`. The frame loops are
+// fully unrolled over registers: the contribution loads of one grain are independent and in flight together, and the
+// next grain's record is fetched while this one is summed (the storage / record reads come from L2 or HBM: their latency,
+// not the adds, bounds this function).
+constexpr uint32_t GRAN_CHUNK = 16;
+struct GranPiece { uint32_t s0, len, storage; };
+PB_DEV GranPiece gran_piece(const GranReplay& g, uint32_t row, uint32_t i, uint32_t last) {
+  GranPiece p{0u, 0u, 0u};
+  if (i < last) {
+    const uint32_t ri = g.vrec[(size_t)row * g.vrec_cap + i];
+    if (ri < g.rec_cap) {
+      const GrainRec& r = g.recs[ri];
+      p.s0 = r.start_off; p.len = r.len; p.storage = r.storage;
+      if ((size_t)p.storage + p.len > g.storage_cap) p.len = 0;
+    }
+  }
+  return p;
+}
 PB_DEV uint32_t gran_replay_frames(VoiceState& v, CallCtx& c, const GroupParams& gp, const GranReplay& g, uint32_t row,
-                                   uint32_t n, float* __restrict__ out) {
+                                   uint32_t n, float* __restrict__ out, const bool acc) {
   const uint32_t lo = c.hq_off, hi = lo + n;
-  for (uint32_t f = 0; f < 2 * n; ++f) out[f] = 0.0f;
+  float sl[GRAN_CHUNK], sr[GRAN_CHUNK];
+#pragma unroll
+  for (uint32_t j = 0; j < GRAN_CHUNK; ++j) { sl[j] = 0.0f; sr[j] = 0.0f; }
   const uint32_t tile = lo / 64u;
   const uint32_t* tr = g.tile_range + ((size_t)row * g.n_tiles + tile) * 2;
   const uint32_t first = tr[0], last = min(tr[1], g.vrec_cap);
+  GranPiece nxt = gran_piece(g, row, first, last);
   for (uint32_t i = first; i < last; ++i) {
-    const uint32_t ri = g.vrec[(size_t)row * g.vrec_cap + i];
-    if (ri >= g.rec_cap) continue;
-    const GrainRec& r = g.recs[ri];
-    const uint32_t s0 = r.start_off, s1 = r.start_off + r.len;
-    const uint32_t a0 = max(lo, s0), a1 = min(hi, s1);
-    if (a0 >= a1 || (size_t)r.storage + r.len > g.storage_cap) continue;
-    const float2* src = g.storage + r.storage;
-    for (uint32_t f = a0; f < a1; ++f) {
-      const float2 x = src[f - s0];
-      if (x.x == x.x) { out[2 * (f - lo)] += x.x; out[2 * (f - lo) + 1] += x.y; }
+    const GranPiece p = nxt;
+    nxt = gran_piece(g, row, i + 1, last);
+    const uint32_t a0 = max(lo, p.s0), a1 = min(hi, p.s0 + p.len);
+    if (a0 >= a1) continue;
+    const float2* __restrict__ src = g.storage + p.storage;
+    float2 x[GRAN_CHUNK];
+#pragma unroll
+    for (uint32_t j = 0; j < GRAN_CHUNK; ++j) {
+      const uint32_t f = lo + j;
+      x[j] = (f >= a0 && f < a1) ? __ldg(src + (f - p.s0)) : make_float2(__int_as_float(0x7fc00000), 0.0f);
     }
+#pragma unroll
+    for (uint32_t j = 0; j < GRAN_CHUNK; ++j)
+      if (x[j].x == x[j].x) { sl[j] += x[j].x; sr[j] += x[j].y; }  // NaN marks samples the reference skips (and the gaps here)
   }
-  if (gp.has_env) {
-    for (uint32_t f = 0; f < n; ++f) {
-      const float e = c.env_per_frame ? env_run(v, gp) : c.env_const;
-      out[2 * f] *= e; out[2 * f + 1] *= e;
+#pragma unroll
+  for (uint32_t j = 0; j < GRAN_CHUNK; ++j) {
+    if (j < n) {
+      if (gp.has_env) {
+        const float e = c.env_per_frame ? env_run(v, gp) : c.env_const;
+        sl[j] *= e; sr[j] *= e;
+      }
+      out[2 * j] = acc ? out[2 * j] + sl[j] : sl[j];
+      out[2 * j + 1] = acc ? out[2 * j + 1] + sr[j] : sr[j];
     }
   }
   c.hq_off += n;

@@ -124,7 +124,7 @@ __device__ __noinline__ uint32_t hq_advance(VoiceState& v, CallCtx& c, HqState* 
 // exactly as voice_frames() applies them. A HighQuality source never runs dry inside a call (EOF keeps feeding
 // zero chunks until the call is full, preloaded.rs:283-329), so all `n` frames are produced.
 PB_DEV uint32_t hq_replay_frames(VoiceState& v, CallCtx& c, const float* __restrict__ row, float comp, uint32_t n,
-                                 float* __restrict__ out) {
+                                 float* __restrict__ out, const bool acc) {
   for (uint32_t f = 0; f < n; ++f) {
     const float2 x = *reinterpret_cast<const float2*>(row + (size_t)c.hq_off * 2);
     c.hq_off++;
@@ -145,8 +145,8 @@ PB_DEV uint32_t hq_replay_frames(VoiceState& v, CallCtx& c, const float* __restr
     } else if (c.pan_apply) {
       l *= c.pan_l; r *= c.pan_r;
     }
-    out[2 * f] = l;
-    out[2 * f + 1] = r;
+    out[2 * f] = acc ? out[2 * f] + l : l;
+    out[2 * f + 1] = acc ? out[2 * f + 1] + r : r;
   }
   return n;
 }

@@ -955,7 +955,7 @@ uint64_t pb200_position(const pb200_renderer* r) { return r ? r->position : 0; }
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
-struct SizeClass { uint32_t vpad; uint32_t threads; uint32_t tpc; std::vector<uint32_t> groups; size_t smem; };
+struct SizeClass { uint32_t vpad; uint32_t threads; std::vector<uint32_t> groups; };
 
 struct Compiled {
   std::vector<std::vector<uint32_t>> levels;  // mixers per depth
@@ -1040,9 +1040,6 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
       if (nv <= vpad && (vpad == 1 || nv > vpad / 2)) sc.groups.push_back((uint32_t)gi);
     }
     if (sc.groups.empty()) continue;
-    sc.tpc = std::min(16u, std::max(1u, 128u / vpad));        // replay: tiles per CTA
-    const uint32_t nt = vpad * sc.tpc;
-    sc.smem = ((size_t)nt * ROW + (size_t)sc.tpc * 4 * TILE) * sizeof(float);
     c.classes.push_back(sc);
   }
   std::vector<uint32_t> class_groups;
@@ -1187,8 +1184,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaStreamSynchronize(r->sm));
 
   CUDA_TRY(cudaFuncSetAttribute(mix_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_WORK_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(replay_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  CUDA_TRY(cudaFuncSetAttribute(replay_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REPLAY_SMEM));
   const uint32_t n_tiles = tb / TILE;
   const uint32_t seg_cap = n_tiles + max_chunks + 8;
   if (seg_cap >= 65535) return fail(r, PB200_ERR_UNSUPPORTED, "too many chunk boundaries in one time block");
@@ -1282,12 +1278,13 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(cudaMemsetAsync(r->d_gran_counters.p, 0, 2 * (size_t)std::max<uint32_t>(RING, n_blocks) * sizeof(uint32_t), r->sv));
   }
 
-  std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r1(n_blocks), ev_m1(n_blocks);
+  std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r0(n_blocks), ev_r1(n_blocks), ev_m0(n_blocks), ev_m1(n_blocks);
   std::vector<cudaEvent_t> ev_x((n_hq || n_rows) ? 3 * (size_t)n_blocks : 0);  // grain begin / grain end = sinc begin / sinc end
   for (auto& e : ev_x) CUDA_TRY(DevicePool::get().event(&e));
   for (uint32_t b = 0; b < n_blocks; ++b) {
     CUDA_TRY(DevicePool::get().event(&ev_v0[b])); CUDA_TRY(DevicePool::get().event(&ev_v1[b]));
     CUDA_TRY(DevicePool::get().event(&ev_r1[b])); CUDA_TRY(DevicePool::get().event(&ev_m1[b]));
+    CUDA_TRY(DevicePool::get().event(&ev_r0[b])); CUDA_TRY(DevicePool::get().event(&ev_m0[b]));
   }
   cudaEvent_t ev_start, ev_end;
   CUDA_TRY(DevicePool::get().event(&ev_start)); CUDA_TRY(DevicePool::get().event(&ev_end));
@@ -1428,17 +1425,16 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     }
     if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b + 2], r->sr_));
     const uint32_t live_tiles = (blen + TILE - 1) / TILE;
-    for (size_t ci = 0; ci < c.classes.size(); ++ci) {
-      const SizeClass& sc = c.classes[ci];
-      ra.group_list = r->d_class_groups.p + c.class_offsets[ci];
-      ra.vpad = sc.vpad; ra.tpc = sc.tpc;
-      dim3 grid((live_tiles + sc.tpc - 1) / sc.tpc, (uint32_t)sc.groups.size());
-      if (sc.vpad * sc.tpc <= 128) replay_kernel<128, 6><<<grid, sc.vpad * sc.tpc, sc.smem, r->sr_>>>(ra);
-      else replay_kernel<1024, 1><<<grid, sc.vpad * sc.tpc, sc.smem, r->sr_>>>(ra);
+    CUDA_TRY(cudaEventRecord(ev_r0[b], r->sr_));  // stream order: every wait of this block's replay is behind it
+    {  // one launch over every group (the class lists are contiguous in d_class_groups)
+      ra.group_list = r->d_class_groups.p;
+      dim3 grid((live_tiles + REPLAY_THREADS - 1) / REPLAY_THREADS, ng);
+      replay_kernel<<<grid, REPLAY_THREADS, REPLAY_SMEM, r->sr_>>>(ra);
       ++launches;
     }
     CUDA_TRY(cudaEventRecord(ev_r1[b], r->sr_));
     CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_r1[b], 0));
+    CUDA_TRY(cudaEventRecord(ev_m0[b], r->sm));
     MixerKernelArgs ma;
     ma.mixers = r->d_mixers.p; ma.mstate = r->d_mstate.p; ma.child_index = r->d_child_index.p; ma.source_index = r->d_source_index.p;
     ma.fx = r->d_fx.p; ma.fx_events = r->d_fx_events.p;
@@ -1491,10 +1487,11 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   for (uint32_t b = 0; b < n_blocks; ++b) {
     if (!persistent) { cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.skeleton_kernel_ms += ms; }
     else if (b == 0) { cudaEventElapsedTime(&ms, ev_v0[0], ev_skel_end); r->stats.skeleton_kernel_ms += ms; }
-    cudaEventElapsedTime(&ms, ev_v1[b], ev_r1[b]); r->stats.voice_kernel_ms += ms;
-    cudaEventElapsedTime(&ms, ev_r1[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ev_r0[b], ev_r1[b]); r->stats.voice_kernel_ms += ms;   // the replay launches alone
+    cudaEventElapsedTime(&ms, ev_m0[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
     DevicePool::get().release_event(ev_v0[b]); DevicePool::get().release_event(ev_v1[b]);
     DevicePool::get().release_event(ev_r1[b]); DevicePool::get().release_event(ev_m1[b]);
+    DevicePool::get().release_event(ev_r0[b]); DevicePool::get().release_event(ev_m0[b]);
   }
   for (uint32_t b = 0; b < n_blocks && !ev_x.empty(); ++b) {
     cudaEventElapsedTime(&ms, ev_x[3 * (size_t)b], ev_x[3 * (size_t)b + 1]); r->stats.grain_kernel_ms += ms;

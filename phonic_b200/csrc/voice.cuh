@@ -391,7 +391,7 @@ PB_DEV bool resample_frame(VoiceState& v, CallCtx& c, HistVals& hv, const float*
 // source ran dry).
 template <int CC, bool AUDIO>
 PB_DEV uint32_t voice_frames(VoiceState& v, CallCtx& c, HistVals& hv, const GroupParams& gp, const DevBuffer& b,
-                             uint32_t out_rate, float comp, uint32_t n, float* __restrict__ out) {
+                             uint32_t out_rate, float comp, uint32_t n, float* __restrict__ out, const bool acc = false) {
   const float* __restrict__ buf = b.data;
   uint32_t f = 0;
   for (; f < n && !c.ended; ++f) {
@@ -439,9 +439,9 @@ PB_DEV uint32_t voice_frames(VoiceState& v, CallCtx& c, HistVals& hv, const Grou
       float e = c.env_per_frame ? env_run(v, gp) : c.env_const;
       l *= e; r *= e;
     }
-    if (AUDIO) {
-      out[2 * f] = l;
-      out[2 * f + 1] = r;
+    if (AUDIO) {  // acc: Sampler::write adds the voice to the output (sampler.rs:989-1006)
+      out[2 * f] = acc ? out[2 * f] + l : l;
+      out[2 * f + 1] = acc ? out[2 * f + 1] + r : r;
     }
   }
   return f;
@@ -826,7 +826,12 @@ PB_DEV void apply_tile_rec(VoiceState& v, CallCtx& c, const DevBuffer& b, const 
   const uint32_t k = (r.pos - v.playback_pos) / CC;
   int32_t h[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = (uint32_t)i < k ? (int32_t)(r.pos - (uint32_t)(i + 1) * CC) : v.hidx[(uint32_t)i - min(k, (uint32_t)i)];
+  for (int i = 0; i < 4; ++i) {
+    // v.hidx[i - k] as a select chain: a dynamic index would force the whole VoiceState into local memory
+    const uint32_t j = (uint32_t)i - min(k, (uint32_t)i);
+    const int32_t old = j == 0 ? v.hidx[0] : j == 1 ? v.hidx[1] : j == 2 ? v.hidx[2] : v.hidx[3];
+    h[i] = (uint32_t)i < k ? (int32_t)(r.pos - (uint32_t)(i + 1) * CC) : old;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) v.hidx[i] = h[i];
   v.initialized = 1;
@@ -838,5 +843,90 @@ PB_DEV void apply_tile_rec(VoiceState& v, CallCtx& c, const DevBuffer& b, const 
   v.env_out = r.env_out; v.env_hold = r.env_hold; v.env_target = r.env_target;
   v.env_stage = r.stage_n >> 16;
 }
+
+// ---- replay fast path ------------------------------------------------------------------------------------
+// Is the Segment at hand the first frame of a call the skeleton treated as simple? (Same predicate on the same
+// state, so the answer is the skeleton's; a call it had to treat as general for bookkeeping reasons only -- segment
+// capacity -- is still rendered correctly by either path.)
+template <int CC>
+PB_DEV bool simple_call_start(const VoiceState& v, const CallCtx& c, const DevBuffer& b) {
+  return c.new_call && c.call_left == 0 && c.produced_in_call == 0 && !c.ended && !v.hq && simple_call_ok<CC>(v, c, b, c.chunk_left);
+}
+
+// CubicInterpolator::process prologue of a simple call (cubic.rs:60-69), as simple_call() does it in the skeleton
+template <int CC>
+PB_DEV void simple_call_prologue(VoiceState& v, CallCtx& c, HistVals& hv, const DevBuffer& b) {
+  c.call_left = c.chunk_left;
+  loop_range_samples(v, b, c.ls, c.le);
+  c.new_call = false;
+  if (!v.initialized) {
+    v.initialized = 1;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) push_frame<CC, true>(v, hv, b.data);
+  }
+}
+
+// `n` frames inside a simple call, bit-identical to voice_frames<CC, true> under the simple-call preconditions (constant
+// ratio != 1, one write_buffer call, no fader / gain / pan ramp, the input cannot run out): only the phase recurrence,
+// the history pushes, the Hermite evaluation, the constant scale factors (`x * 1.0f` is exact, so an absent stage is a
+// multiplication by one) and the envelope remain. Call bookkeeping (call_left, produced_in_call, history indices) is
+// not maintained: the replay reloads it with the next Segment / TileRec.
+constexpr uint32_t SIMPLE_WIN = 16;  // input samples staged per refill
+
+template <int CC>
+PB_DEV void simple_frames(VoiceState& v, const CallCtx& c, HistVals& hv, const GroupParams& gp, const DevBuffer& b,
+                          const uint32_t n, float* __restrict__ out, const bool acc, float* __restrict__ win, const uint32_t wstride) {
+  const float* __restrict__ buf = b.data;
+  const float ratio = v.ratio;
+  float s = v.sub_pos;
+  uint32_t pos = v.playback_pos;
+  const float fs = c.fader_scale ? v.fader_tgt : 1.0f;
+  const float vs = c.vol_scale ? v.vol.target : 1.0f;
+  const float pl = c.pan_apply ? c.pan_l : 1.0f, pr = c.pan_apply ? c.pan_r : 1.0f;
+  const bool env_pf = gp.has_env && c.env_per_frame;
+  const float ec = gp.has_env ? c.env_const : 1.0f;
+  const bool down = ratio < 1.0f;
+  // The pushes consume consecutive input samples: they are staged SIMPLE_WIN at a time in the thread's window of shared
+  // memory (element i of thread t at win[i * stride], one bank per lane), so the L2 / HBM latency of the sample
+  // buffer is paid once per window by independent loads in flight together instead of once per push by a load the
+  // Hermite evaluation waits for. Reads past the last sample a push can reach are clamped into the buffer and never used.
+  const uint32_t last = b.n_samples - 1u;
+  uint32_t wbase = pos;
+  auto refill = [&]() {
+#pragma unroll
+    for (uint32_t i = 0; i < SIMPLE_WIN; ++i) win[i * wstride] = __ldg(buf + min(wbase + i, last));
+  };
+  refill();
+  auto push = [&]() {
+    if (pos - wbase >= SIMPLE_WIN) { wbase = pos; refill(); }
+    hist_push(hv.h[0], win[(pos - wbase) * wstride]);
+    if (CC == 2) hist_push(hv.h[1], win[(pos - wbase + 1u) * wstride]);
+    pos += CC;
+  };
+  for (uint32_t f = 0; f < n; ++f) {
+    float fr;
+    if (down) {  // cubic.rs:72-90
+      if (s >= 1.0f) { push(); s -= 1.0f; }
+      fr = s;
+      s += ratio;
+    } else {     // cubic.rs:91-110
+      while (s < ratio) { push(); s += 1.0f; }
+      s -= ratio;
+      fr = 1.0f - s;
+    }
+    float x0 = hermite(hv.h[0], fr);
+    float x1 = CC == 2 ? hermite(hv.h[1], fr) : x0;
+    x0 *= fs; x1 *= fs;                       // VolumeFader (fader.rs:103-116), not running
+    float l = x0 * vs, r = x1 * vs;           // AmplifiedSource (smoothing.rs:60-71), not ramping
+    l *= pl; r *= pr;                         // PannedSource, not ramping
+    const float e = env_pf ? env_run(v, gp) : ec;  // AHDSR (voice.rs:470-486)
+    l *= e; r *= e;
+    out[2 * f] = acc ? out[2 * f] + l : l;
+    out[2 * f + 1] = acc ? out[2 * f + 1] + r : r;
+  }
+  v.sub_pos = s;
+  v.playback_pos = pos;
+}
+
 
 }  // namespace pb
