@@ -105,7 +105,8 @@ enum pb200_effect_kind {
   PB200_FX_REVERB = 6,     /* ReverbEffect     src/effect/reverb.rs     */
   PB200_FX_GAIN = 7,       /* GainEffect       src/effect/gain.rs       */
   PB200_FX_PANNING = 8,    /* PanningEffect    src/effect/pan.rs        */
-  PB200_FX_GATE = 9        /* GateEffect       src/effect/gate.rs       */
+  PB200_FX_GATE = 9,       /* GateEffect       src/effect/gate.rs       */
+  PB200_FX_DISTORTION = 10 /* DistortionEffect src/effect/distortion.rs */
 };
 
 /* FilterEffect::with_parameters(filter_type, cutoff, q) (filter.rs:104-116) */
@@ -160,6 +161,14 @@ typedef struct pb200_gate_params {
 
 /* PanningEffect has only PanningEffect::new() (pan.rs:52-60): pass params = NULL and use
  * PB200_EV_SET_EFFECT_PARAMETER events ('pan ', 'wdth', 'invl', 'invr'; booleans: value != 0). */
+
+/* DistortionEffect::with_parameters(distortion_type, drive, mix) (distortion.rs:247-253). Parameters: 'type', 'driv'
+ * (0..4, linear ramp), 'mix ' (0..1). */
+typedef struct pb200_distortion_params {
+  uint32_t distortion_type; /* DistortionType: 0 SoftClip 1 HardClip 2 Diode (default) 3 Fuzz 4 Fold */
+  float drive;
+  float mix;
+} pb200_distortion_params;
 
 /* `params` may be NULL => Effect::new()/default(). */
 PB200_API int pb200_add_effect(pb200_renderer *r, uint32_t mixer_id, uint32_t kind,

@@ -183,6 +183,15 @@ int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const voi
         fx = std::make_unique<GateEffect>(p->threshold, p->attack_time, p->hold_time, p->release_time, p->range);
       } else fx = std::make_unique<GateEffect>();
       break;
+    case PB200_FX_DISTORTION:
+      if (params) {
+        if (size != sizeof(pb200_distortion_params)) return fail(r, PB200_ERR_PARAMETER, "bad distortion params size");
+        auto* p = (const pb200_distortion_params*)params;
+        if (p->distortion_type > 4 || !(p->drive >= 0.0f && p->drive <= 4.0f) || !(p->mix >= 0.0f && p->mix <= 1.0f))
+          return fail(r, PB200_ERR_PARAMETER, "Value out of bounds");
+        fx = std::make_unique<DistortionEffect>(p->distortion_type, p->drive, p->mix);
+      } else fx = std::make_unique<DistortionEffect>();
+      break;
     default: return fail(r, PB200_ERR_PARAMETER, "unknown effect kind");
   }
   // Player::add_effect: effect.initialize(sr, ch, MAX_MIX_BUFFER_SAMPLES / ch) (player.rs:905-909)

@@ -466,6 +466,139 @@ struct GateEffect : Effect {
   }
 };
 
+// ---- src/effect/distortion.rs:19-386 ---------------------------------------------------------------------------
+// Waveshapers (distortion.rs:124-190). `powi(2)` / `powi(3)` are multiplication chains.
+inline float dist_shape(uint32_t type, float sample, float drive) {
+  const float MAX_DRIVE = 4.0f;
+  const float t = drive / MAX_DRIVE;
+  switch (type) {
+    case 0: {  // SoftClip
+      const float gain = 1.0f + (t * t) * (15.0f - 1.0f);
+      const float x = sample * gain;
+      if (x >= 1.0f) return 1.0f;
+      if (x > -1.0f) return gain <= 1.0f ? sample : (3.0f / 2.0f) * (x - ((x * x) * x) / 3.0f);
+      return -1.0f;
+    }
+    case 1: {  // HardClip: sample.clamp(-threshold, threshold) * gain
+      const float gain = 1.0f + (t * t) * (25.0f - 1.0f);
+      const float threshold = 1.0f / gain;
+      float c = sample;
+      if (c < -threshold) c = -threshold;
+      if (c > threshold) c = threshold;
+      return c * gain;
+    }
+    case 2: {  // Diode
+      const float curve = 0.6f * (t * t) + 0.4f * t;
+      const float gain = 1.0f + curve * (20.0f - 1.0f);
+      const float diode_clipping = std::exp((0.1f * sample) / (0.0253f * 1.68f)) - 1.0f;
+      return 2.0f / 3.14159265358979323846f * std::atan(diode_clipping * gain);
+    }
+    case 3: {  // Fuzz
+      const float gain = 1.0f + (1.0f - std::exp(-3.0f * t)) * (30.0f - 1.0f);
+      const float amplified = sample * gain;
+      const float saturated = amplified < 0.0f ? -1.0f * (1.0f - std::exp(-std::fabs(amplified))) : 1.0f * (1.0f - std::exp(-std::fabs(amplified)));
+      return 1.5f * (saturated + std::fabs(saturated));
+    }
+    default: {  // Fold
+      const float gain = 1.0f + (t * t) * (4.0f - 1.0f);
+      const float x = sample * gain;
+      const float threshold = 1.0f / gain;
+      if (x > threshold || x < -threshold)
+        return std::fabs(std::fmod(std::fabs(x - threshold), threshold * 4.0f) - threshold * 2.0f) - threshold;
+      return x;
+    }
+  }
+}
+// DistortionType::rms_compensation (distortion.rs:84-122)
+inline float dist_rms_compensation(uint32_t type, float drive) {
+  const int N = 256;
+  const float PARTIALS[5][2] = {{1.0f, 0.60f}, {2.7f, 0.25f}, {5.3f, 0.10f}, {9.1f, 0.03f}, {14.6f, 0.02f}};
+  float partials_peak = 0.0f;
+  for (auto& p : PARTIALS) partials_peak += p[1];
+  float input_sum_sq = 0.0f, output_sum_sq = 0.0f;
+  for (int i = 0; i < N; ++i) {
+    const float t = 6.28318530717958647692f * ((float)i + 0.5f) / (float)N;
+    float sum = 0.0f;
+    for (auto& p : PARTIALS) sum += p[1] * std::sin(p[0] * t);
+    const float sample = sum / partials_peak;
+    input_sum_sq += sample * sample;
+    const float o = dist_shape(type, sample, drive);
+    output_sum_sq += o * o;
+  }
+  const float input_rms = std::sqrt(input_sum_sq / (float)N), output_rms = std::sqrt(output_sum_sq / (float)N);
+  return output_rms > 1e-10f ? input_rms / output_rms : 1.0f;
+}
+struct DistortionEffect : Effect {
+  uint32_t distortion_type = 2;  // DistortionType::Diode (TYPE default)
+  SmoothedParam<LinearSmoothed> drive;
+  SmoothedParam<ExpSmoothed> mix;
+  float luts[5][256];
+  size_t channel_count = 0;
+  DistortionEffect() {
+    drive.from_description({fourcc("driv"), 0.0f, 4.0f, 0.0f, SC_LIN});
+    drive.value.step = 0.01f;
+    mix.from_description({fourcc("mix "), 0.0f, 1.0f, 1.0f, SC_LIN});
+    mix.value.inertia = 0.1f;
+    for (uint32_t ty = 0; ty < 5; ++ty)
+      for (int i = 0; i < 256; ++i) luts[ty][i] = dist_rms_compensation(ty, (float)i / 255.0f * 4.0f);
+  }
+  DistortionEffect(uint32_t type, float drive_, float mix_) : DistortionEffect() {  // with_parameters (distortion.rs:247-253)
+    distortion_type = type;
+    drive.init_value(drive_);
+    mix.init_value(mix_);
+  }
+  float lookup(float d) const {  // lookup_gain_compensation (distortion.rs:271-279)
+    const float* lut = luts[distortion_type];
+    float pos = std::min(std::max(d / 4.0f, 0.0f), 1.0f) * 255.0f;
+    size_t lo = (size_t)pos;
+    size_t hi = std::min(lo + 1, (size_t)255);
+    float frac = pos - (float)lo;
+    return lut[lo] + (lut[hi] - lut[lo]) * frac;
+  }
+  const char* name() const override { return "Distortion"; }
+  size_t weight() const override { return 1; }
+  bool initialize(uint32_t sr, size_t ch, size_t) override {
+    channel_count = ch;
+    mix.set_sample_rate(sr); drive.set_sample_rate(sr);
+    return true;
+  }
+  void process(float* buf, size_t len, uint64_t) override {
+    if (!mix.need_ramp() && mix.target_value() == 0.0f) {
+    } else if (!mix.need_ramp() && mix.target_value() >= 1.0f) {
+      if (!drive.need_ramp()) {
+        const float d = drive.target_value();
+        const float comp = lookup(d);
+        for (size_t i = 0; i < len; ++i) buf[i] = dist_shape(distortion_type, buf[i], d) * comp;
+      } else {
+        for (size_t i = 0; i + channel_count <= len; i += channel_count) {
+          const float d = drive.next_value();
+          const float comp = lookup(d);
+          for (size_t ch = 0; ch < channel_count; ++ch) buf[i + ch] = dist_shape(distortion_type, buf[i + ch], d) * comp;
+        }
+      }
+    } else {
+      for (size_t i = 0; i + channel_count <= len; i += channel_count) {
+        const float d = drive.next_value();
+        const float comp = lookup(d);
+        const float m = mix.next_value();
+        for (size_t ch = 0; ch < channel_count; ++ch) {
+          const float dry = buf[i + ch];
+          const float wet = dist_shape(distortion_type, dry, d) * comp;
+          buf[i + ch] = (1.0f - m) * dry + m * wet;
+        }
+      }
+    }
+  }
+  bool process_tail(size_t& f) const override { f = 0; return true; }
+  bool process_parameter_update(uint32_t id, const ParamUpdate& u) override {
+    if (id == fourcc("type")) distortion_type = enum_from_update(u, 5);
+    else if (id == fourcc("driv")) drive.apply_update(u);
+    else if (id == fourcc("mix ")) mix.apply_update(u);
+    else return false;
+    return true;
+  }
+};
+
 // ---- src/effect/eq5.rs:19-364 ------------------------------------------------------------------------------------
 struct Eq5Effect : Effect {
   uint32_t sample_rate = 0; size_t channel_count = 0;

@@ -85,4 +85,8 @@ void po_test_note_ratio(uint32_t note, uint32_t in_rate, uint32_t out_rate, doub
   *speed = s; *rate = r; *ratio = (float)((double)in_rate / (double)r);
 }
 
-}  // extern "C"
+// DistortionType::shape_function / rms_compensation (src/effect/distortion.rs:84-190)
+float po_test_dist_shape(uint32_t type, float sample, float drive) { return dist_shape(type, sample, drive); }
+float po_test_dist_compensation(uint32_t type, float drive) { return dist_rms_compensation(type, drive); }
+
+}

@@ -30,7 +30,7 @@ ERR_CUDA = 100
 ERR_UNSUPPORTED = 101
 
 # pb200_effect_kind
-FX_FILTER, FX_EQ5, FX_COMPRESSOR, FX_CHORUS, FX_DELAY, FX_REVERB, FX_GAIN, FX_PANNING, FX_GATE = 1, 2, 3, 4, 5, 6, 7, 8, 9
+FX_FILTER, FX_EQ5, FX_COMPRESSOR, FX_CHORUS, FX_DELAY, FX_REVERB, FX_GAIN, FX_PANNING, FX_GATE, FX_DISTORTION = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 # pb200_event_kind
 EV_STOP_SOURCE = 1
@@ -70,6 +70,10 @@ class ChorusParams(C.Structure):
 
 class GainParams(C.Structure):
     _fields_ = [("gain_db", F32), ("dc_filter_mode", U32)]
+
+
+class DistortionParams(C.Structure):
+    _fields_ = [("distortion_type", U32), ("drive", F32), ("mix", F32)]
 
 
 class GateParams(C.Structure):

@@ -221,7 +221,7 @@ struct DevEvent {
 };
 
 // ---- mixers / effects -------------------------------------------------------------------------------
-enum FxKind : uint32_t { FX_FILTER = 1, FX_EQ5 = 2, FX_COMPRESSOR = 3, FX_CHORUS = 4, FX_DELAY = 5, FX_REVERB = 6, FX_GAIN = 7, FX_PANNING = 8, FX_GATE = 9 };
+enum FxKind : uint32_t { FX_FILTER = 1, FX_EQ5 = 2, FX_COMPRESSOR = 3, FX_CHORUS = 4, FX_DELAY = 5, FX_REVERB = 6, FX_GAIN = 7, FX_PANNING = 8, FX_GATE = 9, FX_DISTORTION = 10 };
 
 struct LinSm { float current, target, step, current_step; uint32_t pending; };
 struct SpringSm { float current, velocity, target, omega; };

@@ -791,6 +791,90 @@ PB_DEV void pan_process(PanState& s, const FxCtx& cx, const ChunkBuf& cb, uint32
   }
 }
 
+// ---- DistortionEffect (distortion.rs:69-190, 326-360): memoryless waveshaping, parallel over frames unless a smoother ramps
+constexpr float DIST_MIX_INERTIA = 0.1f;  // ExponentialSmoothedValue::with_inertia(0.1) (distortion.rs:238)
+PB_DEV bool dist_mix_need_ramp(const ExpSm& s, float comp) {
+  return fabsf((s.target - s.current) * DIST_MIX_INERTIA * comp) > F32_EPS * 100.0f;
+}
+PB_DEV float dist_mix_next(ExpSm& s, float comp) {
+  const float add = (s.target - s.current) * DIST_MIX_INERTIA * comp;
+  if (fabsf(add) > F32_EPS * 100.0f) { s.current += add; return s.current; }
+  return s.target;
+}
+PB_DEV float dist_shape(uint32_t type, float sample, float drive) {
+  const float t = drive / 4.0f;
+  switch (type) {
+    case 0: {  // SoftClip
+      const float gain = 1.0f + (t * t) * (15.0f - 1.0f);
+      const float x = sample * gain;
+      if (x >= 1.0f) return 1.0f;
+      if (x > -1.0f) return gain <= 1.0f ? sample : (3.0f / 2.0f) * (x - ((x * x) * x) / 3.0f);
+      return -1.0f;
+    }
+    case 1: {  // HardClip
+      const float gain = 1.0f + (t * t) * (25.0f - 1.0f);
+      const float threshold = 1.0f / gain;
+      float c = sample;
+      if (c < -threshold) c = -threshold;
+      if (c > threshold) c = threshold;
+      return c * gain;
+    }
+    case 2: {  // Diode
+      const float curve = 0.6f * (t * t) + 0.4f * t;
+      const float gain = 1.0f + curve * (20.0f - 1.0f);
+      const float diode_clipping = expf((0.1f * sample) / (0.0253f * 1.68f)) - 1.0f;
+      return 2.0f / 3.14159265358979323846f * atanf(diode_clipping * gain);
+    }
+    case 3: {  // Fuzz
+      const float gain = 1.0f + (1.0f - expf(-3.0f * t)) * (30.0f - 1.0f);
+      const float amplified = sample * gain;
+      const float sat = amplified < 0.0f ? -1.0f * (1.0f - expf(-fabsf(amplified))) : 1.0f * (1.0f - expf(-fabsf(amplified)));
+      return 1.5f * (sat + fabsf(sat));
+    }
+    default: {  // Fold
+      const float gain = 1.0f + (t * t) * (4.0f - 1.0f);
+      const float x = sample * gain;
+      const float threshold = 1.0f / gain;
+      if (x > threshold || x < -threshold) return fabsf(fmodf(fabsf(x - threshold), threshold * 4.0f) - threshold * 2.0f) - threshold;
+      return x;
+    }
+  }
+}
+PB_DEV float dist_lookup(const DistState& s, float drive) {  // lookup_gain_compensation (distortion.rs:271-279)
+  const float* lut = s.lut[s.type];
+  const float pos = fminf(fmaxf(drive / 4.0f, 0.0f), 1.0f) * 255.0f;
+  const uint32_t lo = (uint32_t)pos;
+  const uint32_t hi = min(lo + 1u, 255u);
+  const float frac = pos - (float)lo;
+  return lut[lo] + (lut[hi] - lut[lo]) * frac;
+}
+PB_DEV void dist_process(DistState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t tid, uint32_t nt) {
+  const bool mix_ramp = dist_mix_need_ramp(s.mix, cx.comp), drive_ramp = lin_need_ramp(s.drive);
+  const float mix_target = s.mix.target;
+  const uint32_t type = s.type;
+  __syncthreads();  // every thread has taken its decisions before thread 0 advances the smoothers
+  if (!mix_ramp && mix_target == 0.0f) return;
+  if (!mix_ramp && mix_target >= 1.0f) {
+    if (!drive_ramp) {
+      const float d = s.drive.target, comp = dist_lookup(s, d);
+      for (uint32_t f = tid; f < frames; f += nt) { CB_L(f) = dist_shape(type, CB_L(f), d) * comp; CB_R(f) = dist_shape(type, CB_R(f), d) * comp; }
+    } else if (tid == 0) {
+      for (uint32_t f = 0; f < frames; ++f) {
+        const float d = lin_next(s.drive), comp = dist_lookup(s, d);
+        CB_L(f) = dist_shape(type, CB_L(f), d) * comp; CB_R(f) = dist_shape(type, CB_R(f), d) * comp;
+      }
+    }
+  } else if (tid == 0) {
+    for (uint32_t f = 0; f < frames; ++f) {
+      const float d = lin_next(s.drive), comp = dist_lookup(s, d);
+      const float m = dist_mix_next(s.mix, cx.comp);
+      const float dl = CB_L(f), dr = CB_R(f);
+      CB_L(f) = (1.0f - m) * dl + m * (dist_shape(type, dl, d) * comp);
+      CB_R(f) = (1.0f - m) * dr + m * (dist_shape(type, dr, d) * comp);
+    }
+  }
+}
+
 // ---- Effect::process_tail (Option<usize>): returns false for None -------------------------------------------
 PB_DEV uint64_t f32_ceil_u64(float v) { float c = ceilf(v); return c > 0.0f ? (uint64_t)c : 0ull; }
 PB_DEV bool fx_process_tail(const FxHeader& h, const FxCtx& cx, uint64_t& frames) {
@@ -805,6 +889,7 @@ PB_DEV bool fx_process_tail(const FxHeader& h, const FxCtx& cx, uint64_t& frames
       return true;
     }
     case FX_PANNING: frames = 0; return true;
+    case FX_DISTORTION: frames = 0; return true;
     case FX_GATE: {
       const GateState& s = *(const GateState*)st;
       frames = f32_ceil_u64(s.hold_time * srf) + f32_ceil_u64(s.release_time * srf);
@@ -886,6 +971,13 @@ PB_DEV void fx_apply_param(FxHeader& h, const FxCtx& cx, const FxParamEvent& e) 
       s.env_rel = s.release_time > 0.0f ? expf(-1.0f / (s.release_time * srf)) : 0.0f;
       s.attack_coeff = expf(-1.0f / (s.attack_time * srf));
       s.release_coeff = expf(-1.0f / (s.release_time * srf));
+      break;
+    }
+    case FX_DISTORTION: {
+      DistState& s = *(DistState*)st;
+      if (id == CC4('t', 'y', 'p', 'e')) s.type = min((uint32_t)v, 4u);
+      else if (id == CC4('d', 'r', 'i', 'v')) lin_set_target(s.drive, v, cx.comp);
+      else if (id == CC4('m', 'i', 'x', ' ')) { s.mix.target = v; if (!dist_mix_need_ramp(s.mix, cx.comp)) s.mix.current = v; }
       break;
     }
     case FX_PANNING: {
@@ -990,6 +1082,7 @@ PB_DEV void fx_process(const FxHeader& h, const FxCtx& cx, const ChunkBuf& cb, u
     case FX_EQ5: eq5_process(*(Eq5State*)st, cx, cb, frames, lane, warp); break;
     case FX_GAIN: gain_process(*(GainState*)st, cx, cb, frames, tid, FX_THREADS_FULL); break;
     case FX_PANNING: pan_process(*(PanState*)st, cx, cb, frames, tid, FX_THREADS_FULL); break;
+    case FX_DISTORTION: dist_process(*(DistState*)st, cx, cb, frames, tid, FX_THREADS_FULL); break;
     case FX_COMPRESSOR: if (tid == 0) comp_process(*(CompState*)st, cx, cb, frames); break;
     case FX_CHORUS: if (tid == 0) chorus_process(*(ChorusState*)st, cx, cb, frames); break;
     case FX_DELAY: if (tid == 0) delay_process(*(DelayState*)st, cx, cb, frames); break;

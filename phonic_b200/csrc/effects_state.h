@@ -70,6 +70,13 @@ struct GainState {  // src/effect/gain.rs:51-60
   double dc_x1[2], dc_y1[2];
 };
 
+struct DistState {  // src/effect/distortion.rs:195-204
+  LinSm drive;               // LinearSmoothedValue, step 0.01
+  ExpSm mix;                 // ExponentialSmoothedValue, inertia 0.1
+  uint32_t type;             // DistortionType: 0 SoftClip 1 HardClip 2 Diode 3 Fuzz 4 Fold
+  float lut[5][256];         // compensation_luts, built on the host at construction like the reference
+};
+
 struct GateState {  // src/effect/gate.rs:12-28
   float threshold, attack_time, hold_time, release_time, range;
   float env_cur, env_atk, env_rel;   // EnvelopeFollower (envelope.rs:5-75)

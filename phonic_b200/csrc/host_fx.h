@@ -92,9 +92,11 @@ inline const std::vector<ParamDesc>& param_table(uint32_t kind) {
                                                  {cc4("invl"), 0, 1, 4, 0}, {cc4("invr"), 0, 1, 4, 0}};
   static const std::vector<ParamDesc> gate = {{cc4("thrs"), -60.0f, 0.0f, 0, 0}, {cc4("attk"), 0.001f, 0.5f, 0, 0}, {cc4("hold"), 0.0f, 2.0f, 0, 0},
                                               {cc4("rels"), 0.01f, 2.0f, 0, 0}, {cc4("rnge"), -60.0f, 0.0f, 0, 0}};
+  static const std::vector<ParamDesc> distortion = {{cc4("type"), 0, 4, 2, 0}, {cc4("driv"), 0.0f, 4.0f, 0, 0}, {cc4("mix "), 0.0f, 1.0f, 0, 0}};
   static const std::vector<ParamDesc> none;
   switch (kind) {
     case FX_GATE: return gate;
+    case FX_DISTORTION: return distortion;
     case FX_GAIN: return gain;
     case FX_PANNING: return panning;
     case FX_FILTER: return filter;
@@ -273,6 +275,71 @@ inline FxBuild build_gate(const pb200_gate_params* p, uint32_t sr) {  // gate.rs
   s.hold_counter = 0;
   s.gate_gain_db = s.range;
   gate_update_coefficients_h(s, sr);
+  return b;
+}
+
+// DistortionType::shape_function (distortion.rs:124-190) on the host: only used to build the RMS compensation tables at
+// construction time, as DistortionEffect::new() does (distortion.rs:256-268); the audio path evaluates it on device.
+inline float dist_shape_h(uint32_t type, float sample, float drive) {
+  const float t = drive / 4.0f;
+  if (type == 0) {
+    const float gain = 1.0f + (t * t) * (15.0f - 1.0f), x = sample * gain;
+    if (x >= 1.0f) return 1.0f;
+    if (x > -1.0f) return gain <= 1.0f ? sample : (3.0f / 2.0f) * (x - ((x * x) * x) / 3.0f);
+    return -1.0f;
+  }
+  if (type == 1) {
+    const float gain = 1.0f + (t * t) * (25.0f - 1.0f), threshold = 1.0f / gain;
+    return std::min(std::max(sample, -threshold), threshold) * gain;
+  }
+  if (type == 2) {
+    const float gain = 1.0f + (0.6f * (t * t) + 0.4f * t) * (20.0f - 1.0f);
+    const float dc = std::exp((0.1f * sample) / (0.0253f * 1.68f)) - 1.0f;
+    return 2.0f / 3.14159265358979323846f * std::atan(dc * gain);
+  }
+  if (type == 3) {
+    const float gain = 1.0f + (1.0f - std::exp(-3.0f * t)) * (30.0f - 1.0f), a = sample * gain;
+    const float sat = a < 0.0f ? -1.0f * (1.0f - std::exp(-std::fabs(a))) : 1.0f * (1.0f - std::exp(-std::fabs(a)));
+    return 1.5f * (sat + std::fabs(sat));
+  }
+  const float gain = 1.0f + (t * t) * (4.0f - 1.0f), x = sample * gain, threshold = 1.0f / gain;
+  if (x > threshold || x < -threshold) return std::fabs(std::fmod(std::fabs(x - threshold), threshold * 4.0f) - threshold * 2.0f) - threshold;
+  return x;
+}
+inline float dist_rms_compensation_h(uint32_t type, float drive) {  // distortion.rs:84-122
+  static const float PART[5][2] = {{1.0f, 0.60f}, {2.7f, 0.25f}, {5.3f, 0.10f}, {9.1f, 0.03f}, {14.6f, 0.02f}};
+  float peak = 0.0f;
+  for (int k = 0; k < 5; ++k) peak += PART[k][1];
+  float in_sq = 0.0f, out_sq = 0.0f;
+  for (int i = 0; i < 256; ++i) {
+    const float t = 6.28318530717958647692f * ((float)i + 0.5f) / 256.0f;
+    float sum = 0.0f;
+    for (int k = 0; k < 5; ++k) sum += PART[k][1] * std::sin(PART[k][0] * t);
+    const float x = sum / peak, y = dist_shape_h(type, x, drive);
+    in_sq += x * x;
+    out_sq += y * y;
+  }
+  const float in_rms = std::sqrt(in_sq / 256.0f), out_rms = std::sqrt(out_sq / 256.0f);
+  return out_rms > 1e-10f ? in_rms / out_rms : 1.0f;
+}
+inline FxBuild build_distortion(const pb200_distortion_params* p, uint32_t sr) {  // distortion.rs:226-253
+  FxBuild b;
+  DistState& s = blob<DistState>(b);
+  if (p && (p->distortion_type > 4 || !(p->drive >= 0.0f && p->drive <= 4.0f) || !(p->mix >= 0.0f && p->mix <= 1.0f))) {
+    b.code = PB200_ERR_PARAMETER; b.error = "Value out of bounds"; return b;
+  }
+  const float comp = 44100.0f / (float)sr;
+  s.type = p ? p->distortion_type : 2u;
+  s.drive = lin_init(p ? p->drive : 0.0f, 0.01f, comp);
+  s.mix = exp_init(p ? p->mix : 1.0f);
+  struct Luts { float v[5][256]; };
+  static const Luts luts = [] {  // the tables depend on nothing but the type: built once per process (thread-safe static)
+    Luts l;
+    for (uint32_t ty = 0; ty < 5; ++ty)
+      for (int i = 0; i < 256; ++i) l.v[ty][i] = dist_rms_compensation_h(ty, (float)i / 255.0f * 4.0f);
+    return l;
+  }();
+  std::memcpy(s.lut, luts.v, sizeof(s.lut));
   return b;
 }
 

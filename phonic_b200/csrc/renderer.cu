@@ -628,6 +628,10 @@ int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const voi
       if (params && size != sizeof(pb200_gate_params)) return fail(r, PB200_ERR_PARAMETER, "bad gate params size");
       b = pbh::build_gate((const pb200_gate_params*)params, sr);
       break;
+    case PB200_FX_DISTORTION:
+      if (params && size != sizeof(pb200_distortion_params)) return fail(r, PB200_ERR_PARAMETER, "bad distortion params size");
+      b = pbh::build_distortion((const pb200_distortion_params*)params, sr);
+      break;
     default: return fail(r, PB200_ERR_PARAMETER, "unknown effect kind");
   }
   if (b.code) return fail(r, b.code, b.error);
@@ -1365,8 +1369,14 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     for (size_t ci = 0; ci < c.classes.size() && (!persistent || b == 0); ++ci) {
       const SizeClass& sc = c.classes[ci];
       va.group_list = r->d_class_groups.p + c.class_offsets[ci];
-      if (sc.vpad <= 8) skeleton_kernel<256, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
-      else if (sc.vpad <= 32) skeleton_kernel<1024, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
+      // Warp per voice (latency-optimal: voices never serialise each other's control flow) while every group of the class
+      // can be resident at once; beyond that one lane per voice (a warp per group of up to 32 voices) fits 16x more voices
+      // per SM and the branch-free phase loops keep the lanes converged.
+      static const int force_wpv = getenv("PB200_SKEL_WPV") ? atoi(getenv("PB200_SKEL_WPV")) : -1;
+      const size_t wpv_resident = (size_t)sm_count_all * std::max<size_t>(1, 65536 / (224 * 32 * (size_t)sc.vpad));
+      const bool wpv = force_wpv >= 0 ? force_wpv != 0 : (persistent || sc.groups.size() <= wpv_resident);
+      if (sc.vpad <= 8 && wpv) skeleton_kernel<256, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
+      else if (sc.vpad <= 32 && wpv) skeleton_kernel<1024, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
       else if (sc.threads <= 256) skeleton_kernel<256, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
       else skeleton_kernel<1024, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
       ++launches;

@@ -166,6 +166,16 @@ class GateEffect:
 
 
 @dataclass
+class DistortionEffect:
+    """DistortionEffect::with_parameters(type, drive, mix) (src/effect/distortion.rs:247-253); type: 0 SoftClip 1 HardClip
+    2 Diode 3 Fuzz 4 Fold; default => DistortionEffect::new() (Diode, drive 0, mix 1)."""
+    distortion_type: int = 2
+    drive: float = 0.0
+    mix: float = 1.0
+    default: bool = False
+
+
+@dataclass
 class PanningEffect:
     """PanningEffect::new() (src/effect/pan.rs:52-60); parameters 'pan ', 'wdth', 'invl', 'invr' via set_parameter."""
 
@@ -354,6 +364,9 @@ class Player:
             kind = A.FX_GATE
             p = None if effect.default else A.GateParams(effect.threshold, effect.attack_time, effect.hold_time,
                                                          effect.release_time, effect.range)
+        elif isinstance(effect, DistortionEffect):
+            kind = A.FX_DISTORTION
+            p = None if effect.default else A.DistortionParams(effect.distortion_type, effect.drive, effect.mix)
         else:
             raise TypeError(effect)
         if p is None:

@@ -64,6 +64,41 @@ def frames_for(seconds: float, sample_rate: int, block: int = 1024) -> int:
     return blocks * block
 
 
+_SCORES: dict = {}
+
+
+def voice_bank_score(spec: VoiceBankSpec, seed_offset: int = 0, time_scale: float = 1.0):
+    """The seeded random score of a voice bank: per sampler a list of (note, t_on, pan, glide | None, t_off | None)
+    with glide = (t_gl, target_note, rate). Cached: drawing it is workload synthesis, not part of the render path."""
+    key = (tuple(sorted(spec.__dict__.items())), seed_offset, time_scale)
+    if key in _SCORES:
+        return _SCORES[key]
+    rng = np.random.default_rng(spec.seed + seed_offset)
+    sr = spec.sample_rate
+    n_samplers = (spec.voices + spec.voices_per_sampler - 1) // spec.voices_per_sampler
+    remaining = spec.voices
+    score = []
+    for _ in range(n_samplers):
+        nv = min(spec.voices_per_sampler, remaining)
+        remaining -= nv
+        voices = []
+        for _v in range(nv):
+            note = int(rng.integers(36, 85))
+            t_on = int(rng.uniform(0.0, 2.0 * time_scale) * sr)
+            pan = float(rng.uniform(-0.8, 0.8))
+            glide = None
+            if spec.glide:
+                t_gl = int(rng.uniform(2.0, 6.0) * time_scale * sr)
+                tgt = note + (7 if rng.random() < 0.5 else -7)
+                rate = float(rng.uniform(12.0, 60.0))
+                glide = (t_gl, tgt, rate)
+            t_off = int(rng.uniform(6.0, 8.0) * time_scale * sr) if spec.note_off else None
+            voices.append((note, t_on, pan, glide, t_off))
+        score.append(voices)
+    _SCORES[key] = score
+    return score
+
+
 def add_voice_bank(player: Player, spec: VoiceBankSpec, buffer_id: int, mixer_id=None, seed_offset: int = 0,
                    time_scale: float = 1.0):
     """Adds `spec.voices` sampler voices (AHDSR + glide) to `mixer_id`; returns the sampler handles.
@@ -71,31 +106,18 @@ def add_voice_bank(player: Player, spec: VoiceBankSpec, buffer_id: int, mixer_id
     Per voice: note uniform in 36..84, note-on uniform in [0, 2 s), glide SetSpeed to note+-7 at
     [2, 6 s) with 12..60 st/s, note-off at [6, 8 s). Times scale with `time_scale` for short tests.
     """
-    rng = np.random.default_rng(spec.seed + seed_offset)
-    sr = spec.sample_rate
-    n_samplers = (spec.voices + spec.voices_per_sampler - 1) // spec.voices_per_sampler
     gain = 1.0 / math.sqrt(max(spec.voices, 1))
     ahdsr = AhdsrParameters(attack=0.01, hold=0.0, decay=0.5, sustain=0.75, release=1.0)
     handles = []
-    remaining = spec.voices
-    for _ in range(n_samplers):
-        nv = min(spec.voices_per_sampler, remaining)
-        remaining -= nv
-        opts = GeneratorPlaybackOptions(volume=1.0, panning=0.0, voices=nv)
+    for voices in voice_bank_score(spec, seed_offset, time_scale):
+        opts = GeneratorPlaybackOptions(volume=1.0, panning=0.0, voices=len(voices))
         h = player.add_generator(buffer_id, opts, ahdsr, mixer_id=mixer_id)
         handles.append(h)
-        for _v in range(nv):
-            note = int(rng.integers(36, 85))
-            t_on = int(rng.uniform(0.0, 2.0 * time_scale) * sr)
-            pan = float(rng.uniform(-0.8, 0.8))
+        for note, t_on, pan, glide, t_off in voices:
             nid = h.note_on(note, volume=gain, panning=pan, sample_time=t_on)
-            if spec.glide:
-                t_gl = int(rng.uniform(2.0, 6.0) * time_scale * sr)
-                tgt = note + (7 if rng.random() < 0.5 else -7)
-                rate = float(rng.uniform(12.0, 60.0))
-                h.set_note_speed(nid, speed_from_note(tgt), glide=rate, sample_time=t_gl)
-            if spec.note_off:
-                t_off = int(rng.uniform(6.0, 8.0) * time_scale * sr)
+            if glide is not None:
+                h.set_note_speed(nid, speed_from_note(glide[1]), glide=glide[2], sample_time=glide[0])
+            if t_off is not None:
                 h.note_off(nid, sample_time=t_off)
     return handles
 

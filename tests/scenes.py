@@ -6,7 +6,7 @@ import numpy as np
 
 from phonic_b200 import workloads as W
 from phonic_b200.player import (AhdsrParameters, ChorusEffect, CompressorEffect, DelayEffect, Eq5Effect,
-                                FilePlaybackOptions, FilterEffect, GainEffect, GateEffect, GeneratorPlaybackOptions, GranularParameters, PanningEffect,
+                                FilePlaybackOptions, DistortionEffect, FilterEffect, GainEffect, GateEffect, GeneratorPlaybackOptions, GranularParameters, PanningEffect,
                                 Player, ReverbEffect)
 
 SR = 48000
@@ -273,6 +273,12 @@ SCENES = {
                                                            ("pan ", 0.0, 100000), ("invr", 0, 110000), ("wdth", 1.0, 120000)], buffer_seconds=2.8),
     "fx_gate": fx_scene(GateEffect(-22.0, 0.004, 0.03, 0.15, -40.0), param_events=[("thrs", -15.0, 50000), ("rnge", -60.0, 80000), ("hold", 0.2, 100000)],
                         buffer_seconds=2.8, seed=14),
+    "fx_dist_softclip": fx_scene(DistortionEffect(0, 2.5, 1.0), param_events=[("driv", 0.5, 30000), ("driv", 4.0, 60000)], buffer_seconds=2.8),
+    "fx_dist_hardclip": fx_scene(DistortionEffect(1, 1.5, 0.7), param_events=[("mix ", 0.2, 20000), ("driv", 3.0, 50000), ("mix ", 1.0, 90000)], buffer_seconds=2.8),
+    "fx_dist_fold": fx_scene(DistortionEffect(4, 3.0, 1.0), param_events=[("mix ", 0.0, 40000), ("mix ", 0.5, 70000), ("type", 1, 100000), ("type", 4, 110000)],
+                             buffer_seconds=2.8),
+    "fx_dist_diode": fx_scene(DistortionEffect(default=True), param_events=[("driv", 2.0, 10000), ("mix ", 0.6, 50000), ("type", 3, 80000), ("driv", 3.5, 100000)],
+                              buffer_seconds=2.8),
     "fx_reverb": fx_scene(ReverbEffect(0.6, 0.35), seconds=4.0, param_events=[("room", 0.8, 60000)]),
     "submixers_cfg3_small": submixers_cfg3_small,
     "submixers_cfg5_small": submixers_cfg5_small,
@@ -280,7 +286,7 @@ SCENES = {
 }
 
 # scenes whose whole path is +,-,*,/,sqrt in the reference's order: must be bit-exact on device
-BIT_EXACT = {"fx_gain_dc", "fx_panning", "file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
+BIT_EXACT = {"fx_gain_dc", "fx_panning", "fx_dist_softclip", "fx_dist_hardclip", "fx_dist_fold", "file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
              "sampler_no_envelope", "hq_equal_rates", "gran_cloud", "gran_resampled_fixed", "gran_sequential_loop", "gran_dense"}
 # bit-exact voice path + time-invariant biquads evaluated by the f64 block scan (exact up to O(1e-16)
 # relative reassociation error before the f32 cast): at most a rare last-bit flip

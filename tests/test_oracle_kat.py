@@ -271,3 +271,39 @@ def test_grain_trigger_cadence(oracle_api):
     onsets = np.flatnonzero((out != 0) & (np.concatenate([[0], out[:-1]]) == 0))
     # 1 ms Trapezoid grain = 48 samples; sample 0 has envelope 0 (skipped), the blip starts one frame after the trigger
     assert onsets.tolist() == [t + 1 for t in trig if t + 1 < frames]
+
+
+def test_distortion_shapers_known_answers(oracle_lib):
+    """src/effect/distortion.rs:124-190, values derived by hand from the cited formulas (f32)."""
+    lib = oracle_lib
+    lib.po_test_dist_shape.restype = C.c_float
+    lib.po_test_dist_compensation.restype = C.c_float
+    shape = lambda t, x, d: lib.po_test_dist_shape(C.c_uint32(t), C.c_float(x), C.c_float(d))
+    # drive 0: gain = 1 for the polynomial / clip / fold shapers -> identity inside [-1, 1]
+    for t in (0, 1, 4):
+        for x in (-0.75, -0.1, 0.0, 0.3, 0.9):
+            assert shape(t, x, 0.0) == np.float32(x)
+    # SoftClip, full drive: gain 15 -> saturates at +-1 beyond |x| >= 1/15, cubic below
+    assert shape(0, 0.5, 4.0) == 1.0 and shape(0, -0.5, 4.0) == -1.0
+    x = np.float32(0.02) * np.float32(15.0)
+    assert shape(0, 0.02, 4.0) == np.float32(1.5) * (x - (x * x * x) / np.float32(3.0))
+    # HardClip, full drive: gain 25, threshold 1/25 -> clamp(x) * gain
+    assert shape(1, 0.5, 4.0) == np.float32(np.float32(1.0) / np.float32(25.0)) * np.float32(25.0)
+    assert shape(1, 0.01, 4.0) == np.float32(0.01) * np.float32(25.0)
+    # Fuzz removes the negative half wave: 1.5 * (s + |s|) == 0 for s < 0
+    assert shape(3, -0.4, 2.0) == 0.0 and shape(3, 0.4, 2.0) > 0.0
+    # Diode at 0 is exp(0) - 1 = 0 -> atan(0) = 0
+    assert shape(2, 0.0, 3.0) == 0.0
+    # Fold, full drive: gain 4, threshold 0.25; x = 0.5 * 4 = 2 -> |(|2 - .25| % 1) - .5| - .25 = 0.0
+    assert shape(4, 0.5, 4.0) == 0.0
+    assert shape(4, 0.05, 4.0) == np.float32(0.05) * np.float32(4.0)
+    # identity shapers need no loudness compensation at drive 0; every table entry is finite and positive
+    for t in (0, 1, 4):
+        assert lib.po_test_dist_compensation(C.c_uint32(t), C.c_float(0.0)) == 1.0
+    for t in range(5):
+        for d in (0.0, 1.0, 2.5, 4.0):
+            c = lib.po_test_dist_compensation(C.c_uint32(t), C.c_float(d))
+            assert np.isfinite(c) and c > 0.0
+        # more drive -> louder output -> smaller compensation (the wavefolder folds the peaks back instead)
+        if t != 4:
+            assert lib.po_test_dist_compensation(C.c_uint32(t), C.c_float(4.0)) < lib.po_test_dist_compensation(C.c_uint32(t), C.c_float(0.5))
