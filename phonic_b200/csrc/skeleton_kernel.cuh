@@ -108,7 +108,8 @@ PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t fr
 
 // One simple call (voice.cuh "simple calls"): the whole call's phase / envelope recurrences in one go, with a
 // 32-byte TileRec stored at every tile boundary crossed instead of a full Segment.
-template <int CC>
+// UNI: lane-per-voice skeleton -- one instruction stream for every ratio / envelope state (phase_piece_uniform).
+template <int CC, bool UNI>
 PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const DevBuffer& buf, uint32_t n,
                         uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen) {
   cc.call_left = cc.chunk_left;
@@ -129,7 +130,20 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
   uint32_t piece = min(remaining, TILE - (off % TILE));
   for (;;) {
     bool fused = false;
-    if (env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE) {
+    if (UNI) {
+      float d = 0.0f, o = 0.0f;
+      bool on_hold = false;
+      if (env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE && env_bare_steps(v, gp, d, on_hold) >= piece) {
+        fused = true;
+        o = on_hold ? v.env_hold : v.env_out;
+      } else {
+        d = 0.0f;
+      }
+      np += phase_piece_uniform(s, p, pk, piece, first, o, d);
+      if (fused) { if (on_hold) v.env_hold = o; else v.env_out = o; }
+      else if (env) env_chain(v, gp, piece);
+      fused = true;  // this piece is done
+    } else if (env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE) {
       float d;
       bool on_hold;
       if (env_bare_steps(v, gp, d, on_hold) >= piece) {  // the stage cannot end inside this piece: ride along
@@ -258,7 +272,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
 
   // One Source::write call of this thread's voice (already opened by voice_begin_call): emits the call's
   // Segment / TileRec checkpoints and advances the control state. Returns the frames written.
-  auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) -> uint32_t {
+  auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) __attribute__((always_inline)) -> uint32_t {
     uint32_t written_frames = 0;
     bool simple = false;
     if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq && !is_gran)
@@ -274,8 +288,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
       }
       cur_cnt++;
-      if (buf.channels == 2) simple_call<2>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
-      else simple_call<1>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
+      if (buf.channels == 2) simple_call<2, !WPV>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
+      else simple_call<1, !WPV>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
       n_segs++;
       written_frames = n;
     } else {

@@ -605,6 +605,51 @@ PB_DEV uint32_t phase_piece(float& s, float& p, const PhaseK& k, const uint32_t 
   return np;
 }
 
+// The same piece with ONE instruction stream for modes 0-2, for the lane-per-voice skeleton (a warp = the voices of a
+// group, each with its own ratio): every lane evaluates both the ratio < 1 step and the closed-form ratio >= 1 step and
+// keeps its own, so the lanes of a warp stay converged whatever their ratios are. Constants of the arm a lane does not
+// use are neutral (`x + 0.0f` is exact for x >= 0; a step weight of -inf never fires). The envelope accumulate always
+// runs (d = 0 when not fused; the caller then discards o). Bit-identical to phase_piece<ACC> per lane.
+PB_DEV uint32_t phase_piece_uniform(float& s, float& p, const PhaseK& k, const uint32_t span, const bool first, float& o, const float d) {
+  if (span == 0) return 0u;
+  if (k.mode == 3) return phase_piece<true>(s, p, k, span, first, o, d);
+  const float ratio = k.ratio;
+  const float s_in = s;
+  const bool down = k.mode <= 1;
+  uint32_t f = 0;
+  if (first) {
+    if (down) {
+      p = step(s, k.w1);
+      s = (s - p) + ratio;
+      o += d;
+      p = step(s, k.w1);
+      f = 1;
+    } else if (!(s < 1.0f)) {
+      while (s < ratio) s += 1.0f;
+      s -= ratio;
+      o += d;
+      f = 1;
+    }
+  }
+  const float w1 = k.w1, wA = k.wA, wB = k.mode == 1 ? k.wB : -__int_as_float(0x7f800000), wR = k.wR;
+  const float nmf = (float)max(k.nm, 0);
+  const float a1 = down ? 0.0f : fminf(nmf, 1.0f), a2 = down ? 0.0f : k.a2, a3 = down ? 0.0f : k.a3, a4 = down ? 0.0f : k.a4;
+#pragma unroll 2
+  for (; f < span; ++f) {
+    const float pn = (step(s, wA) - step(s, w1)) + step(s, wB);
+    const float sd = (s - p) + ratio;
+    const float tm = (((s + a1) + a2) + a3) + a4;
+    const float t0 = tm + 1.0f;
+    const float more = fma_sat(t0, -STEP_K, wR);  // [t0 < ratio]
+    const float su = (t0 + more) - ratio;
+    s = down ? sd : su;
+    p = pn;
+    o += d;
+  }
+  const double bal = down ? ((double)s_in - (double)s) : ((double)s - (double)s_in);
+  return (uint32_t)__double2int_rn(bal + (double)span * (double)ratio);
+}
+
 // One piece on its own (the ratio may change from piece to piece: pitch glides)
 PB_DEV uint32_t phase_run(float& s, const float ratio, const uint32_t span) {
   float o = 0.0f, p = 0.0f;
