@@ -328,6 +328,7 @@ def main():
         red_ms = 0.0
         if world > 1:  # one NCCL reduce of the stereo bus partial per render (rank 0 owns the main bus)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()  # absorbs the host-side skew between the ranks' step loops: the span below is the collective itself
             e0.record()
             reduce_partial_bus(out_dev, dst=0)
             e1.record()

@@ -1490,6 +1490,16 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       fclose(f);
     }
   }
+#ifdef PB200_CYC
+  {
+    unsigned long long h[8];
+    cudaMemcpyFromSymbol(h, g_cyc, sizeof(h));
+    fprintf(stderr, "cyc voice %d: simple_call total %.2fM (loops %.2fM) calls %llu frames %llu | run_call total %.2fM, non-simple frames %llu in %.2fM | block fn total %.2fM\n",
+            (int)PB200_CYC, h[0] / 1e6, h[1] / 1e6, h[2], h[3], h[4] / 1e6, h[5], h[6] / 1e6, h[7] / 1e6);
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_cyc, z, sizeof(z));
+  }
+#endif
   float ms = 0;
   r->stats = pb200_render_stats{};
   cudaEventElapsedTime(&ms, ev_start, ev_end);

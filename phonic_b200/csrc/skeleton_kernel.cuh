@@ -55,6 +55,15 @@ struct SkeletonArgs {
 };
 
 constexpr int VK_MAX_VOICES = 1024;
+#ifdef PB200_CYC
+// build-time cycle counters of ONE voice (debug builds only, -DPB200_CYC=<global voice index>)
+__device__ unsigned long long g_cyc[8];
+#define CYC_ON(gv) ((gv) == PB200_CYC)
+#define CYC_T() clock64()
+#else
+#define CYC_ON(gv) false
+#define CYC_T() 0ll
+#endif
 constexpr uint32_t SB_MAX = 256;   // chunk boundaries cached in shared memory
 constexpr uint32_t MAX_RUN = 64;   // chunks per free run
 
@@ -111,7 +120,9 @@ PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t fr
 // UNI: lane-per-voice skeleton -- one instruction stream for every ratio / envelope state (phase_piece_uniform).
 template <int CC, bool UNI>
 PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const DevBuffer& buf, uint32_t n,
-                        uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen) {
+                        uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen, const bool cyc = false) {
+  const long long cy0 = cyc ? CYC_T() : 0ll;
+  long long cy_loop = 0;
   cc.call_left = cc.chunk_left;
   loop_range_samples(v, buf, cc.ls, cc.le);
   cc.new_call = false;
@@ -148,14 +159,18 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
       bool on_hold;
       if (env_bare_steps(v, gp, d, on_hold) >= piece) {  // the stage cannot end inside this piece: ride along
         float o = on_hold ? v.env_hold : v.env_out;
+        const long long c0 = cyc ? CYC_T() : 0ll;
         np += phase_piece<true>(s, p, pk, piece, first, o, d);
+        if (cyc) cy_loop += CYC_T() - c0;
         if (on_hold) v.env_hold = o; else v.env_out = o;
         fused = true;
       }
     }
     if (!fused) {
       float o_unused = 0.0f;
+      const long long c0 = cyc ? CYC_T() : 0ll;
       np += phase_piece<false>(s, p, pk, piece, first, o_unused, 0.0f);
+      if (cyc) cy_loop += CYC_T() - c0;
       if (env) env_chain(v, gp, piece);
     }
     first = false;
@@ -183,6 +198,9 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
   cc.call_left = 0;
   cc.chunk_left = 0;
   after_process_call(v, cc);
+#ifdef PB200_CYC
+  if (cyc) { g_cyc[0] += CYC_T() - cy0; g_cyc[1] += cy_loop; g_cyc[2] += 1; g_cyc[3] += n; }
+#endif
 }
 
 // WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
@@ -197,6 +215,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   unsigned long long prof_free = 0;
   unsigned long long prof_q[4] = {0, 0, 0, 0};
 
+  const long long cyc_block0 = CYC_T();
   const uint32_t g = a.group_list[blockIdx.x];
   const uint32_t tid = WPV ? ((threadIdx.x & 31u) == 0 ? (threadIdx.x >> 5) : 0xFFFFu) : threadIdx.x;
   const GroupParams gp = a.groups[g];
@@ -275,6 +294,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) __attribute__((always_inline)) -> uint32_t {
     uint32_t written_frames = 0;
     bool simple = false;
+    const bool cyc_v = CYC_ON(gp.first_voice + tid);
+    const long long cyr0 = cyc_v ? CYC_T() : 0ll;
     if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq && !is_gran)
       simple = buf.channels == 2 ? simple_call_ok<2>(v, cc, buf, n) : simple_call_ok<1>(v, cc, buf, n);
     if (simple) {
@@ -288,8 +309,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
       }
       cur_cnt++;
-      if (buf.channels == 2) simple_call<2, !WPV>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
-      else simple_call<1, !WPV>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen);
+      if (buf.channels == 2) simple_call<2, !WPV>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen, CYC_ON(gp.first_voice + tid));
+      else simple_call<1, !WPV>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen, CYC_ON(gp.first_voice + tid));
       n_segs++;
       written_frames = n;
     } else {
@@ -332,6 +353,9 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
     }
     my_frames += written_frames;
     voice_end_call(v, cc, t + n);
+#ifdef PB200_CYC
+    if (cyc_v) { g_cyc[4] += CYC_T() - cyr0; g_cyc[5] += simple ? 0 : n; g_cyc[6] += simple ? 0 : (unsigned long long)(CYC_T() - cyr0); }
+#endif
     return written_frames;
   };
   // generator-level gain / pan (player.rs:1075-1081) of one call: checkpoint per (call x tile), advance ramps (thread 0)
@@ -648,6 +672,9 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   if (mine && cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
   if (tid == 0 && gcur_tile != 0xFFFFFFFFu) { g_first[gcur_tile] = (uint16_t)gcur_first; g_count[gcur_tile] = (uint16_t)gcur_cnt; }
   if (mine) a.voices[gp.first_voice + tid] = v;
+#ifdef PB200_CYC
+  if (CYC_ON(gp.first_voice + tid) && mine) g_cyc[7] += CYC_T() - cyc_block0;
+#endif
   if (a.prof && mine) {
     unsigned long long* pr = a.prof + (size_t)(gp.first_voice + tid) * 4;
     pr[0] += prof_q[0]; pr[1] += prof_q[1]; pr[2] += prof_q[3]; pr[3] += prof_free;
