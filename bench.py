@@ -446,6 +446,15 @@ def main():
                         "peak_source": fma_src + "; voices share one L2-resident buffer so the kernel is not HBM bound",
                         "hbm_achieved_gbs": (total_vframes / world) * 8.0 / (total_voice_ms / 1e3) / 1e9,
                         "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_kind": peak_kind, **passes}
+        # measured DRAM traffic of the dominant kernel (one ncu --set full capture, committed under profiles/)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload) or {}
+            if tr.get("kernel") == roofline["kernel"] and tr.get("bytes_per_launch"):
+                roofline["traffic"] = tr["bytes_per_launch"]
+                roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one 32768-frame time block)"
+                roofline["traffic_source"] = tr["source"]
+        except (OSError, ValueError):
+            pass
         line = {"metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": total_dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
