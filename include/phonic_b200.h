@@ -292,6 +292,27 @@ PB200_API int pb200_render_device(pb200_renderer *r, float *out_device, uint64_t
 /* Player::output_sample_frame_position (src/player.rs) */
 PB200_API uint64_t pb200_position(const pb200_renderer *r);
 
+/* ---- WAV in / out: the steps either side of the path ------------------------------------------------
+ * in : AudioFileBuffer::from_file for RIFF/WAVE (src/source/file/buffer.rs:64-119; `smpl` loops decoder.rs:294-330):
+ *      PCM 8/16/24/32 and IEEE float 32/64, WAVE_FORMAT_EXTENSIBLE included; the first `smpl` loop becomes the
+ *      buffer's loop range (clamped as the reference does, kept only if end > start).
+ * out: WavOutput (src/output/wav.rs:50-120, 210-250): whole block_frames blocks while whole-seconds(pos / rate) <
+ *      duration, written as 32-bit float WAV. */
+typedef struct pb200_wav_info {
+  uint64_t frames;          /* decoded frames (the +1 zero pad frame is added on upload) */
+  uint32_t channels, sample_rate;
+  int64_t loop_start, loop_end; /* frames, PB200_NO_LOOP when the file has no usable `smpl` loop */
+  uint32_t bits_per_sample, is_float;
+} pb200_wav_info;
+/* Renderer-free decode into a malloc'd interleaved f32 buffer (release it with pb200_free). */
+PB200_API int pb200_decode_wav(const char *path, float **interleaved, pb200_wav_info *info);
+PB200_API void pb200_free(void *p);
+/* decode + pb200_upload_buffer(add_pad_frame = 1, the file's loop). `info` may be NULL. */
+PB200_API int pb200_upload_wav(pb200_renderer *r, const char *path, uint32_t *buffer_id, pb200_wav_info *info);
+/* Player + WavOutput::open_with_specs(path, sample_rate, 2, duration): render and write the file.
+ * duration_nanos = Duration::as_nanos(). */
+PB200_API int pb200_render_to_wav(pb200_renderer *r, const char *path, uint64_t duration_nanos, uint64_t *frames_written);
+
 /* ---- status: PlaybackStatusEvent::Stopped mirror (src/source/status.rs:15-36) --------------- */
 typedef struct pb200_source_status {
   uint32_t is_playing;    /* FilePlaybackHandle::is_playing */

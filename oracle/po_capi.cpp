@@ -21,6 +21,10 @@
 #define pb200_source_status_get po_source_status_get
 #define pb200_sampler_voice_states po_sampler_voice_states
 #define pb200_last_render_stats po_last_render_stats
+#define pb200_decode_wav po_decode_wav
+#define pb200_free po_free
+#define pb200_upload_wav po_upload_wav
+#define pb200_render_to_wav po_render_to_wav
 #include "../include/phonic_b200.h"
 
 #include <chrono>
@@ -417,6 +421,111 @@ int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frame
   if (done < frames) std::memset(out + done * ch, 0, (frames - done) * ch * sizeof(float));
   if (frames_written) *frames_written = done;
   r->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return PB200_OK;
+}
+
+// ---- WAV in / out, written independently of the product's wav_io.h (chunk walk over the FILE, sample conversion per
+// format branch): AudioFileBuffer::from_file for RIFF/WAVE (src/source/file/buffer.rs:64-119, decoder.rs:294-330) and
+// WavOutput's 32-bit float file (src/output/wav.rs:61-70, 210-250). symphonia / hound are third-party: integer PCM is
+// assumed to scale by 1 / 2^(bits-1).
+static bool po_read_exact(FILE* f, void* dst, size_t n) { return std::fread(dst, 1, n, f) == n; }
+static uint32_t po_le32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+int pb200_decode_wav(const char* path, float** interleaved, pb200_wav_info* info) {
+  if (!path || !interleaved || !info) return PB200_ERR_PARAMETER;
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return PB200_ERR_MEDIA_FILE_NOT_FOUND;
+  unsigned char hd[12];
+  if (!po_read_exact(f, hd, 12) || std::memcmp(hd, "RIFF", 4) || std::memcmp(hd + 8, "WAVE", 4)) { std::fclose(f); return PB200_ERR_MEDIA_FILE_PROBE; }
+  unsigned fmt_tag = 0, channels = 0, bits = 0, align = 0;
+  uint32_t rate = 0;
+  std::vector<unsigned char> pcm;
+  bool have_data = false, have_loop = false;
+  uint32_t ls = 0, le = 0;
+  unsigned char ck[8];
+  while (po_read_exact(f, ck, 8)) {
+    const uint32_t sz = po_le32(ck + 4);
+    std::vector<unsigned char> body(sz);
+    const size_t got = std::fread(body.data(), 1, sz, f);
+    body.resize(got);
+    if (sz & 1) std::fgetc(f);
+    if (!std::memcmp(ck, "fmt ", 4) && got >= 16) {
+      fmt_tag = body[0] | (body[1] << 8); channels = body[2] | (body[3] << 8); rate = po_le32(&body[4]);
+      align = body[12] | (body[13] << 8); bits = body[14] | (body[15] << 8);
+      if (fmt_tag == 0xFFFE && got >= 26) fmt_tag = body[24] | (body[25] << 8);
+    } else if (!std::memcmp(ck, "data", 4) && !have_data) {
+      pcm.swap(body); have_data = true;
+    } else if (!std::memcmp(ck, "smpl", 4) && !have_loop && got >= 60 && po_le32(&body[28]) > 0) {
+      ls = po_le32(&body[36 + 8]); le = po_le32(&body[36 + 12]); have_loop = true;
+    }
+    if (got < sz) break;
+  }
+  std::fclose(f);
+  const bool int_ok = fmt_tag == 1 && (bits == 8 || bits == 16 || bits == 24 || bits == 32);
+  const bool flt_ok = fmt_tag == 3 && (bits == 32 || bits == 64);
+  if (!have_data || !channels || !rate || !(int_ok || flt_ok) || align != channels * (bits / 8)) return PB200_ERR_MEDIA_FILE_PROBE;
+  const size_t frames = pcm.size() / align;
+  if (!frames) return PB200_ERR_AUDIO_DECODING;
+  float* out = (float*)std::malloc(frames * channels * sizeof(float));
+  if (!out) return PB200_ERR_IO;
+  const unsigned char* p = pcm.data();
+  for (size_t i = 0; i < frames * channels; ++i, p += bits / 8) {
+    switch (fmt_tag * 100 + bits) {
+      case 108: out[i] = (float)((int)p[0] - 128) / 128.0f; break;
+      case 116: out[i] = (float)(int16_t)(p[0] | (p[1] << 8)) / 32768.0f; break;
+      case 124: { int32_t x = (int32_t)((uint32_t)p[0] << 8 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 24) >> 8; out[i] = (float)x / 8388608.0f; break; }
+      case 132: out[i] = (float)((double)(int32_t)po_le32(p) / 2147483648.0); break;
+      case 332: std::memcpy(&out[i], p, 4); break;
+      default: { double d; std::memcpy(&d, p, 8); out[i] = (float)d; break; }
+    }
+  }
+  *interleaved = out;
+  info->frames = frames; info->channels = channels; info->sample_rate = rate;
+  info->bits_per_sample = bits; info->is_float = fmt_tag == 3;
+  info->loop_start = info->loop_end = PB200_NO_LOOP;
+  if (have_loop) {
+    const uint64_t fc = frames + 1;  // frame count after the pad frame was appended (buffer.rs:103-110)
+    const uint64_t a = std::min<uint64_t>(ls, fc), b = std::min<uint64_t>(le, fc);
+    if (b > a) { info->loop_start = (int64_t)a; info->loop_end = (int64_t)b; }
+  }
+  return PB200_OK;
+}
+
+void pb200_free(void* p) { std::free(p); }
+
+int pb200_upload_wav(pb200_renderer* r, const char* path, uint32_t* buffer_id, pb200_wav_info* info) {
+  if (!r || !path || !buffer_id) return PB200_ERR_PARAMETER;
+  float* data = nullptr;
+  pb200_wav_info wi;
+  if (int e = pb200_decode_wav(path, &data, &wi)) return fail(r, e, "Audio file failed to open / probe / decode");
+  if (info) *info = wi;
+  const int e = pb200_upload_buffer(r, data, wi.frames, wi.channels, wi.sample_rate, wi.loop_start, wi.loop_end, 1, buffer_id);
+  std::free(data);
+  return e;
+}
+
+int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frames_written);
+int pb200_render_to_wav(pb200_renderer* r, const char* path, uint64_t duration_nanos, uint64_t* frames_written) {
+  if (!r || !path) return PB200_ERR_PARAMETER;
+  const uint32_t bf = r->cfg.block_frames, ch = r->cfg.channel_count, sr = r->cfg.sample_rate;
+  uint64_t blocks = 0;  // wav.rs:222: stop once whole-seconds(pos / sr) >= duration
+  while ((blocks * bf / sr) * 1000000000ull < duration_nanos) ++blocks;
+  std::vector<float> audio((size_t)blocks * bf * ch);
+  uint64_t written = 0;
+  if (blocks) { if (int e = pb200_render(r, audio.data(), blocks * bf, &written)) return e; }
+  if (frames_written) *frames_written = written;
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return fail(r, PB200_ERR_IO, "cannot create the WAV file");
+  const uint32_t data_bytes = (uint32_t)(written * ch * 4);
+  auto w32 = [&](uint32_t v) { std::fwrite(&v, 4, 1, f); };
+  auto w16 = [&](uint16_t v) { std::fwrite(&v, 2, 1, f); };
+  std::fwrite("RIFF", 1, 4, f); w32(60 + data_bytes); std::fwrite("WAVEfmt ", 1, 8, f); w32(40);
+  w16(0xFFFE); w16((uint16_t)ch); w32(sr); w32(sr * ch * 4); w16((uint16_t)(ch * 4)); w16(32); w16(22); w16(32); w32(ch == 2 ? 3u : 4u);
+  const unsigned char guid[16] = {3, 0, 0, 0, 0, 0, 0x10, 0, 0x80, 0, 0, 0xAA, 0, 0x38, 0x9B, 0x71};
+  std::fwrite(guid, 1, 16, f);
+  std::fwrite("data", 1, 4, f); w32(data_bytes);
+  std::fwrite(audio.data(), 4, (size_t)written * ch, f);
+  std::fclose(f);
   return PB200_OK;
 }
 

@@ -26,6 +26,7 @@ ERR_EFFECT_NOT_FOUND = 9
 ERR_MIXER_NOT_FOUND = 10
 ERR_PARAMETER = 11
 ERR_SEND = 12
+ERR_MEDIA_FILE_NOT_FOUND, ERR_MEDIA_FILE_PROBE, ERR_AUDIO_DECODING, ERR_IO = 2, 3, 5, 13
 ERR_CUDA = 100
 ERR_UNSUPPORTED = 101
 
@@ -130,6 +131,11 @@ class RenderStats(C.Structure):
 # every symbol include/phonic_b200.h declares: name -> (restype, argtypes)
 _P = C.POINTER
 _R = C.c_void_p
+class WavInfo(C.Structure):
+    _fields_ = [("frames", U64), ("channels", U32), ("sample_rate", U32), ("loop_start", I64), ("loop_end", I64),
+                ("bits_per_sample", U32), ("is_float", U32)]
+
+
 SYMBOLS = {
     "create": (C.c_int, [_P(Config), _P(_R)]),
     "destroy": (None, [_R]),
@@ -149,6 +155,10 @@ SYMBOLS = {
     "source_status_get": (C.c_int, [_R, U32, _P(SourceStatus)]),
     "sampler_voice_states": (C.c_int, [_R, U32, _P(VoiceState), U32, _P(U32)]),
     "last_render_stats": (C.c_int, [_R, _P(RenderStats)]),
+    "decode_wav": (C.c_int, [C.c_char_p, _P(_P(F32)), _P(WavInfo)]),
+    "free": (None, [C.c_void_p]),
+    "upload_wav": (C.c_int, [_R, C.c_char_p, _P(U32), _P(WavInfo)]),
+    "render_to_wav": (C.c_int, [_R, C.c_char_p, U64, _P(U64)]),
 }
 
 

@@ -17,6 +17,7 @@
 
 #include "../../include/phonic_b200.h"
 #include "replay_kernel.cuh"
+#include "wav_io.h"
 #include "sinc_kernel.cuh"
 #include "mixer_kernel.cuh"
 #include "host_fx.h"
@@ -1566,6 +1567,39 @@ int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frame
 int pb200_render_device(pb200_renderer* r, float* out_device, uint64_t frames, uint64_t* frames_written) {
   if (!r || !out_device) return PB200_ERR_PARAMETER;
   return render_impl(r, out_device, nullptr, frames, frames_written);
+}
+
+int pb200_decode_wav(const char* path, float** interleaved, pb200_wav_info* info) {
+  if (!path || !interleaved || !info) return PB200_ERR_PARAMETER;
+  pbh::WavData w;
+  if (int e = pbh::decode_wav_file(path, w)) return e;
+  float* p = (float*)std::malloc(w.samples.size() * sizeof(float));
+  if (!p) return PB200_ERR_IO;
+  std::memcpy(p, w.samples.data(), w.samples.size() * sizeof(float));
+  *interleaved = p;
+  *info = w.info;
+  return PB200_OK;
+}
+
+void pb200_free(void* p) { std::free(p); }
+
+int pb200_upload_wav(pb200_renderer* r, const char* path, uint32_t* buffer_id, pb200_wav_info* info) {
+  if (!r || !path || !buffer_id) return PB200_ERR_PARAMETER;
+  pbh::WavData w;
+  if (int e = pbh::decode_wav_file(path, w)) return fail(r, e, e == PB200_ERR_MEDIA_FILE_NOT_FOUND ? "Audio file not found" : "Audio file failed to probe / decode");
+  if (info) *info = w.info;
+  return pb200_upload_buffer(r, w.samples.data(), w.info.frames, w.info.channels, w.info.sample_rate, w.info.loop_start, w.info.loop_end, 1, buffer_id);
+}
+
+int pb200_render_to_wav(pb200_renderer* r, const char* path, uint64_t duration_nanos, uint64_t* frames_written) {
+  if (!r || !path) return PB200_ERR_PARAMETER;
+  const uint64_t frames = pbh::wav_stream_frames(duration_nanos, r->cfg.sample_rate, r->cfg.block_frames ? r->cfg.block_frames : 1024u);
+  std::vector<float> out((size_t)frames * 2);
+  uint64_t written = 0;
+  if (frames) { if (int e = render_impl(r, nullptr, out.data(), frames, &written)) return e; }
+  if (frames_written) *frames_written = written;
+  if (int e = pbh::write_wav_f32(path, out.data(), written, 2, r->cfg.sample_rate)) return fail(r, e, "failed to write the WAV file");
+  return PB200_OK;
 }
 
 int pb200_source_status_get(pb200_renderer* r, uint32_t id, pb200_source_status* st) {

@@ -6,6 +6,8 @@ are `float` seconds here and cross the boundary as integer nanoseconds (std::tim
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from dataclasses import dataclass, field
@@ -326,6 +328,19 @@ class Player:
         self._check(self.api.upload_buffer(self._r, a.ctypes.data_as(C.POINTER(A.F32)), frames, ch, sample_rate,
                                            ls, le, 1 if add_pad_frame else 0, C.byref(bid)))
         return bid.value
+
+    def upload_wav(self, path: str):
+        """AudioFileBuffer::from_file for a RIFF/WAVE file (src/source/file/buffer.rs:64-119). Returns (buffer id, WavInfo)."""
+        bid, info = A.U32(), A.WavInfo()
+        self._check(self.api.upload_wav(self._r, os.fsencode(path), C.byref(bid), C.byref(info)))
+        return bid.value, info
+
+    def render_to_wav(self, path: str, seconds: float) -> int:
+        """Player::new(WavOutput::open_with_specs(path, sr, 2, Duration::from_secs_f64(seconds))) (src/output/wav.rs:50-120):
+        renders the whole duration and writes a 32-bit float WAV; returns the frames written."""
+        written = A.U64()
+        self._check(self.api.render_to_wav(self._r, os.fsencode(path), int(round(seconds * 1e9)), C.byref(written)))
+        return written.value
 
     # -- graph -------------------------------------------------------------------------------
     def add_mixer(self, parent_mixer_id: Optional[int] = None) -> MixerHandle:
