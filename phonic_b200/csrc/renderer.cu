@@ -1437,7 +1437,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b + 2], r->sr_));
     const uint32_t live_tiles = (blen + TILE - 1) / TILE;
     CUDA_TRY(cudaEventRecord(ev_r0[b], r->sr_));  // stream order: every wait of this block's replay is behind it
-    {  // one launch over every group (the class lists are contiguous in d_class_groups)
+    static const bool skel_only = getenv("PB200_SKEL_ONLY") != nullptr;  // timing experiments: the skeleton pass alone (output invalid)
+    if (!skel_only) {  // one launch over every group (the class lists are contiguous in d_class_groups)
       ra.group_list = r->d_class_groups.p;
       dim3 grid((live_tiles + REPLAY_THREADS - 1) / REPLAY_THREADS, ng);
       replay_kernel<<<grid, REPLAY_THREADS, REPLAY_SMEM, r->sr_>>>(ra);
@@ -1458,7 +1459,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ma.out = dout + (size_t)(b0 - p0) * 2; ma.master = r->d_master.p; ma.wav_block_frames = bf;
     ma.block_len = blen;
     ma.prof = fx_prof;
-    for (int lvl = (int)c.levels.size() - 1; lvl >= 0; --lvl) {
+    for (int lvl = (int)c.levels.size() - 1; lvl >= 0 && !skel_only; --lvl) {
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
       const uint32_t nlm = (uint32_t)c.levels[lvl].size();
       mix_sum_kernel<<<dim3((blen + 255) / 256, nlm), 256, 0, r->sm>>>(ma);

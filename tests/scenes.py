@@ -230,6 +230,13 @@ def submixers_cfg5_small(p: Player):
     return {"frames": 96 * BLOCK}
 
 
+def many_groups(p: Player):
+    """160 samplers of 8 voices (> one resident wave of warp-per-voice CTAs on 148 SMs): the skeleton takes its lane-per-voice mapping
+    with the uniform phase loop, as it does for cfg3 / cfg5; no effects, so the whole path is bit-exact"""
+    W.build_subtrees(p, 20, 64, W.VoiceBankSpec(), effects="none", time_scale=0.1)
+    return {"frames": 96 * BLOCK}
+
+
 def nested_and_gated(p: Player):
     """nested sub-mixers; one goes silent for > 2 s (silence gate + effect auto-bypass), then wakes up"""
     b = p.upload_buffer(tone(12000, 44100, seed=12), 44100)
@@ -283,10 +290,11 @@ SCENES = {
     "submixers_cfg3_small": submixers_cfg3_small,
     "submixers_cfg5_small": submixers_cfg5_small,
     "nested_and_gated": nested_and_gated,
+    "many_groups": many_groups,
 }
 
 # scenes whose whole path is +,-,*,/,sqrt in the reference's order: must be bit-exact on device
-BIT_EXACT = {"fx_gain_dc", "fx_panning", "fx_dist_softclip", "fx_dist_hardclip", "fx_dist_fold", "file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
+BIT_EXACT = {"many_groups", "fx_gain_dc", "fx_panning", "fx_dist_softclip", "fx_dist_hardclip", "fx_dist_fold", "file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
              "sampler_no_envelope", "hq_equal_rates", "gran_cloud", "gran_resampled_fixed", "gran_sequential_loop", "gran_dense"}
 # bit-exact voice path + time-invariant biquads evaluated by the f64 block scan (exact up to O(1e-16)
 # relative reassociation error before the f32 cast): at most a rare last-bit flip
