@@ -130,16 +130,19 @@ PB_DEV void lfo_set_phase_degrees(LfoSt& l, float p) {
   l.phase = r < 0.0f ? r + 1.0f : r;
 }
 PB_DEV void lfo_set_rate(LfoSt& l, uint32_t sr, double rate) { l.phase_inc = (float)(rate / (double)sr); }
-PB_DEV float lfo_run(LfoSt& l) {
+// the waveform at a given phase (lfo.rs:122-169): a pure function of the phase
+PB_DEV float lfo_wave(uint32_t waveform, float phase) {
   const float TAU = 6.28318530717958647692f;
-  float v;
-  switch (l.waveform) {
-    case 0: { float p = l.phase < 0.5f ? l.phase * TAU : (l.phase - 1.0f) * TAU; v = sine_approx(p); break; }
-    case 1: v = l.phase < 0.25f ? l.phase * 4.0f : (l.phase < 0.75f ? 2.0f - l.phase * 4.0f : l.phase * 4.0f - 4.0f); break;
-    case 2: v = l.phase * 2.0f - 1.0f; break;
-    case 3: v = 1.0f - l.phase * 2.0f; break;
-    default: v = l.phase < 0.5f ? 1.0f : -1.0f; break;
+  switch (waveform) {
+    case 0: { float p = phase < 0.5f ? phase * TAU : (phase - 1.0f) * TAU; return sine_approx(p); }
+    case 1: return phase < 0.25f ? phase * 4.0f : (phase < 0.75f ? 2.0f - phase * 4.0f : phase * 4.0f - 4.0f);
+    case 2: return phase * 2.0f - 1.0f;
+    case 3: return 1.0f - phase * 2.0f;
+    default: return phase < 0.5f ? 1.0f : -1.0f;
   }
+}
+PB_DEV float lfo_run(LfoSt& l) {
+  const float v = lfo_wave(l.waveform, l.phase);
   l.phase += l.phase_inc;
   if (l.phase >= 1.0f) l.phase -= 1.0f;
   return v;

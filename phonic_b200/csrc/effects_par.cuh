@@ -115,11 +115,59 @@ PB_DEV BiquadCoef svf_as_biquad(const SvfCoef& c) {
   return b;
 }
 
-// Lfo phase chain (lfo.rs:122-169, 234-239): serial f32 accumulate, one thread
-PB_DEV void lfo_fill(LfoSt& l, float* out, uint32_t n) {
-  LfoSt t = l;
-  for (uint32_t f = 0; f < n; ++f) out[f] = lfo_run(t);
-  l = t;
+// DcFilter::process_sample (dc.rs:84-88) over a block by one warp. y[n] = (v[n] - v[n-1]) + r y[n-1] is linear in y:
+// every lane runs its sub-block once from a zero state, the sub-block start states are chained through r^len (32
+// steps, every lane redundantly), then every lane re-runs the reference's own recurrence from its true start state.
+// Exact in real arithmetic; in f64 the start states differ from the serial chain by O(1e-16) relative -- used only where
+// the parity bar is a tolerance (the Delay's feedback path); GainEffect's bit-exact DC filter stays serial.
+PB_DEV void dc_scan_channel(const double r, double& x1, double& y1, const double* __restrict__ v, float* __restrict__ out,
+                            const uint32_t len, const uint32_t lane) {
+  const uint32_t B = (len + 31u) / 32u;
+  const uint32_t lo = min(lane * B, len), hi = min(lo + B, len);
+  const double before = lo == 0 ? x1 : v[pidx(lo - 1)];
+  double z = 0.0, rp = 1.0, prev = before;
+  for (uint32_t n = lo; n < hi; ++n) {
+    const double cur = v[pidx(n)];
+    z = cur - prev + r * z;
+    prev = cur;
+    rp *= r;
+  }
+  double start = y1, mine = y1;
+  for (uint32_t l = 0; l < 32; ++l) {
+    const double zl = __shfl_sync(0xFFFFFFFFu, z, l), rl = __shfl_sync(0xFFFFFFFFu, rp, l);
+    if (lane == l) mine = start;
+    start = rl * start + zl;
+  }
+  double y = mine;
+  prev = before;
+  for (uint32_t n = lo; n < hi; ++n) {
+    const double cur = v[pidx(n)];
+    y = cur - prev + r * y;
+    prev = cur;
+    out[pidx(n)] = fminf(fmaxf((float)y, -4.0f), 4.0f);
+  }
+  const double last = len ? v[pidx(len - 1)] : x1;
+  __syncwarp();
+  if (len) { x1 = last; y1 = start; }
+}
+
+// Lfo (lfo.rs:122-169, 234-239) for one warp: only the phase accumulate is a serial f32 chain (lane 0, three dependent
+// operations per frame); the waveform is a pure function of the phase and is evaluated by the 32 lanes in parallel.
+PB_DEV void lfo_fill_warp(LfoSt& l, float* out, uint32_t n, uint32_t lane) {
+  const uint32_t waveform = l.waveform;
+  if (lane == 0) {
+    float ph = l.phase;
+    const float inc = l.phase_inc;
+    for (uint32_t f = 0; f < n; ++f) {
+      out[f] = ph;
+      ph += inc;
+      if (ph >= 1.0f) ph -= 1.0f;
+    }
+    l.phase = ph;
+  }
+  __syncwarp();
+  for (uint32_t f = lane; f < n; f += 32) out[f] = lfo_wave(waveform, out[f]);
+  __syncwarp();
 }
 
 // ---- ChorusEffect::process (chorus.rs:311-394) while no parameter is ramping ----------------------------------
@@ -155,10 +203,10 @@ PB_DEV bool chorus_parallel(ChorusState& s, const FxCtx& cx, const ChunkBuf& cb,
     double ic1 = warp == 0 ? s.fl_ic1 : s.fr_ic1, ic2 = warp == 0 ? s.fl_ic2 : s.fr_ic2;
     biquad_scan_channel(c, ic1, ic2, warp == 0 ? fl : fr, cb.scratch + (size_t)warp * 1060, cb.lane_state + (size_t)warp * 64, n, lane);
     if (lane == 0) { if (warp == 0) { s.fl_ic1 = ic1; s.fl_ic2 = ic2; } else { s.fr_ic1 = ic1; s.fr_ic2 = ic2; } }
-  } else if (tid == 64) {
-    lfo_fill(s.left_osc, llfo, n);
-  } else if (tid == 96) {
-    lfo_fill(s.right_osc, rlfo, n);
+  } else if (warp == 2) {
+    lfo_fill_warp(s.left_osc, llfo, n, lane);
+  } else if (warp == 3) {
+    lfo_fill_warp(s.right_osc, rlfo, n, lane);
   }
   __syncthreads();
   const uint32_t wpl = s.dl.write_pos, wpr = s.dr.write_pos, mkl = s.dl.mask, mkr = s.dr.mask;
@@ -227,7 +275,7 @@ PB_DEV bool delay_parallel(DelayState& s, const FxCtx& cx, const ChunkBuf& cb, u
   double* flt[2] = {carve<double>(p, PLANE), carve<double>(p, PLANE)};   // filtered / saturated (f64)
   double* bufs[2] = {cx.aux_arena + s.dl.aux, cx.aux_arena + s.dr.aux};
   const uint32_t lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) lfo_fill(s.lfo, lfo, n);
+  if (warp == 0) lfo_fill_warp(s.lfo, lfo, n, lane);
   __syncthreads();
   const float base_fb = s.feedback.target, fb_depth = s.lfo_dfb.target, drive = s.drive.target;
   const float wet = s.wet.target, width = s.width.target;
@@ -262,17 +310,11 @@ PB_DEV bool delay_parallel(DelayState& s, const FxCtx& cx, const ChunkBuf& cb, u
     __syncthreads();
     for (uint32_t i = tid; i < len * 2; i += nt) { const uint32_t f = i >> 1, ch = i & 1; flt[ch][pidx(f)] = delay_saturate(flt[ch][pidx(f)], drive); }
     __syncthreads();
-    if (tid == 0 || tid == 32) {
-      const uint32_t ch = tid >> 5;
+    if (warp < 2) {  // DC blocker + clamp -> clean (dly), one warp per channel
+      const uint32_t ch = warp;
       double x1 = ch ? s.dcr_x1 : s.dcl_x1, y1 = ch ? s.dcr_y1 : s.dcl_y1;
-      const double r = s.dc_r;
-      for (uint32_t f = 0; f < len; ++f) {
-        const double v = flt[ch][pidx(f)];
-        y1 = v - x1 + r * y1;
-        x1 = v;
-        dly[ch][pidx(f)] = fminf(fmaxf((float)y1, -4.0f), 4.0f);  // clean
-      }
-      if (ch) { s.dcr_x1 = x1; s.dcr_y1 = y1; } else { s.dcl_x1 = x1; s.dcl_y1 = y1; }
+      dc_scan_channel(s.dc_r, x1, y1, flt[ch], dly[ch], len, lane);
+      if (lane == 0) { if (ch) { s.dcr_x1 = x1; s.dcr_y1 = y1; } else { s.dcl_x1 = x1; s.dcl_y1 = y1; } }
     }
     __syncthreads();
     // (3) line writes (input + previous frame's clean feedback) and the output mix
