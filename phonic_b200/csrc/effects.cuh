@@ -700,7 +700,19 @@ PB_DEV void gain_process(GainState& s, const FxCtx& cx, const ChunkBuf& cb, uint
       const uint32_t ch = tid >> 5;
       double x1 = s.dc_x1[ch], y1 = s.dc_y1[ch];
       const double r = s.dc_r;
-      for (uint32_t f = 0; f < frames; ++f) {
+      // the chain is two dependent f64 operations per frame: loads / conversions / stores of 8 frames are issued around it
+      uint32_t f = 0;
+      for (; f + 8 <= frames; f += 8) {
+        double x[8];
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (double)cb.ch[ch][pidx(f + j)];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { y1 = x[j] - x1 + r * y1; x1 = x[j]; y[j] = (float)y1; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cb.ch[ch][pidx(f + j)] = y[j];
+      }
+      for (; f < frames; ++f) {
         const double x = (double)cb.ch[ch][pidx(f)];
         y1 = x - x1 + r * y1;
         x1 = x;

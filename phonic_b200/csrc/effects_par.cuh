@@ -59,7 +59,17 @@ PB_DEV bool comp_parallel(CompState& s, const FxCtx& cx, const ChunkBuf& cb, uin
   if (tid == 0) {
     float cur = s.env_cur;
     const float atk = s.atk_coeff, rel = s.rel_coeff;
-    for (uint32_t f = 0; f < n; ++f) {
+    uint32_t f = 0;
+    for (; f + 8 <= n; f += 8) {  // loads and stores of 8 frames around the dependent chain
+      float x[8], e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = in_db[f + j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float c = x[j] > cur ? atk : rel; cur = x[j] + c * (cur - x[j]); e[j] = cur; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) env[f + j] = e[j];
+    }
+    for (; f < n; ++f) {
       const float x = in_db[f];
       const float c = x > cur ? atk : rel;
       cur = x + c * (cur - x);
