@@ -752,8 +752,7 @@ PB_DEV void gate_process(GateState& s, const FxCtx& cx, const ChunkBuf& cb, uint
     float cur = s.env_cur, g = s.gate_gain_db;
     uint32_t hold = s.hold_counter;
     const float ea = s.env_atk, er = s.env_rel, ac = s.attack_coeff, rc = s.release_coeff;
-    for (uint32_t f = 0; f < frames; ++f) {
-      const float x = level[f];
+    auto step = [&](const float x) {
       cur = x + (x > cur ? ea : er) * (cur - x);   // EnvelopeFollower::run (envelope.rs:51-60)
       float target;
       if (cur >= thr) { hold = hold_samples; target = 0.0f; }
@@ -761,8 +760,19 @@ PB_DEV void gate_process(GateState& s, const FxCtx& cx, const ChunkBuf& cb, uint
       else target = range_db;
       if (target > g) g = ac * g + (1.0f - ac) * target;
       else g = rc * g + (1.0f - rc) * target;
-      level[f] = g;
+      return g;
+    };
+    uint32_t f = 0;
+    for (; f + 8 <= frames; f += 8) {  // loads and stores of 8 frames around the two dependent chains
+      float x[8], y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = level[f + j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = step(x[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) level[f + j] = y[j];
     }
+    for (; f < frames; ++f) level[f] = step(level[f]);
     s.env_cur = cur; s.gate_gain_db = g; s.hold_counter = hold;
   }
   __syncthreads();
