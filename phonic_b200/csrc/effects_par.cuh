@@ -33,7 +33,8 @@ PB_DEV T* carve(uint8_t*& p, uint32_t n) {
 
 // ---- CompressorEffect (compressor.rs:230-294), compressor mode (ratio < 20) ------------------------------
 PB_DEV bool comp_parallel(CompState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t n, uint32_t tid, uint32_t nt, ParWork w) {
-  if (s.ratio >= 20.0f) return false;  // limiter: running window peak (serial form)
+  const bool limiter = s.ratio >= 20.0f;  // detector = running peak of the look-ahead window (LookupDelayLine, delay.rs:206-265)
+  if (limiter && (s.delay_frames == 0 || (size_t)5 * n * sizeof(float) + (size_t)s.buf_frames * 2 * sizeof(float) > w.bytes)) return false;
   uint8_t* p = w.base;
   float* in_db = carve<float>(p, n);
   float* env = carve<float>(p, n);
@@ -53,6 +54,50 @@ PB_DEV bool comp_parallel(CompState& s, const FxCtx& cx, const ChunkBuf& cb, uin
     dl[f] = d0; dr[f] = d1;
     const float peak = fmaxf(fabsf(in0), fabsf(in1));
     in_db[f] = peak > 1e-6f ? 20.0f * log10f(peak) : -120.0f;
+  }
+  if (limiter) {
+    // The window peak is a serial state machine over the delay line (new maximum / expiry of the old one -> rescan).
+    // The line holds f32 inputs widened to f64, so a float copy in shared memory is lossless; warp 0 walks the chunk
+    // on that copy, every lane holding the same scalar state, and the lanes share the rare O(delay) rescans.
+    float* ring = carve<float>(p, (size_t)bufn * 2);
+    for (uint32_t i = tid; i < bufn * 2; i += nt) ring[i] = (float)line[i];
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t lane = tid;
+      float peak = (float)s.peak_value;
+      uint32_t pos = s.peak_pos;
+      auto rescan = [&](const uint32_t newest, const uint32_t first_i, const uint32_t last_i) {
+        // `for i in first..last { fi = (newest - i) & mask; if fp >= peak { peak = fp; pos = fi } }`: the LAST i holding the maximum wins
+        float bv = 0.0f;
+        uint32_t bi = 0xFFFFFFFFu;
+        for (uint32_t i = first_i + lane; i < last_i; i += 32) {
+          const uint32_t fi = (newest + bufn - i) & mask;
+          const float fp = fmaxf(fmaxf(0.0f, fabsf(ring[fi * 2])), fabsf(ring[fi * 2 + 1]));
+          if (fp >= bv) { bv = fp; bi = i; }
+        }
+        for (uint32_t o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+          const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+          if (oi != 0xFFFFFFFFu && (bi == 0xFFFFFFFFu || ov > bv || (ov == bv && oi > bi))) { bv = ov; bi = oi; }
+        }
+        peak = 0.0f;
+        if (bi != 0xFFFFFFFFu) { peak = bv; pos = (newest + bufn - bi) & mask; }
+      };
+      if (s.peak_dirty) { rescan(wp, 1, D + 1); }  // compressor chunks do not track it (effects.cuh comp_process does the same rescan)
+      for (uint32_t f = 0; f < n; ++f) {
+        const float in0 = CB_L(f), in1 = CB_R(f);
+        const uint32_t wi = (wp + f) & mask, read_index = (wp + f + bufn - D) & mask;
+        if (lane == 0) { ring[wi * 2] = in0; ring[wi * 2 + 1] = in1; }
+        const bool expired = pos == read_index;
+        const float new_peak = fmaxf(fmaxf(0.0f, fabsf(in0)), fabsf(in1));
+        if (new_peak >= peak) { peak = new_peak; pos = wi; }
+        else if (expired) { __syncwarp(); rescan(wi, 0, D); }
+        if (lane == 0) in_db[f] = peak;  // the window peak; converted to dB below
+      }
+      if (lane == 0) { s.peak_value = (double)peak; s.peak_pos = pos; }
+    }
+    __syncthreads();
+    for (uint32_t f = tid; f < n; f += nt) { const float peak = in_db[f]; in_db[f] = peak > 1e-6f ? 20.0f * log10f(peak) : -120.0f; }
   }
   __syncthreads();
   // 2. serial parts: EnvelopeFollower::run (envelope.rs:51-60) and the makeup-gain smoother
@@ -92,7 +137,7 @@ PB_DEV bool comp_parallel(CompState& s, const FxCtx& cx, const ChunkBuf& cb, uin
   __syncthreads();
   // 3. gain computer + output (compressor.rs:262-291)
   const float t = s.threshold, wk = s.knee;
-  const float slope = 1.0f - 1.0f / s.ratio;
+  const float slope = limiter ? 1.0f : 1.0f - 1.0f / s.ratio;
   for (uint32_t f = tid; f < n; f += nt) {
     const float envelope = env[f];
     float gr_db;
@@ -109,7 +154,7 @@ PB_DEV bool comp_parallel(CompState& s, const FxCtx& cx, const ChunkBuf& cb, uin
     CB_L(f) = dl[f] * total_gain;
     CB_R(f) = dr[f] * total_gain;
   }
-  if (tid == 0 && D != 0) { s.write_pos = (wp + n) & mask; s.peak_dirty = 1; }
+  if (tid == 0 && D != 0) { s.write_pos = (wp + n) & mask; s.peak_dirty = limiter ? 0u : 1u; }
   __syncthreads();
   return true;
 }
