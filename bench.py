@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- voice-samples/s of the offline resample+FX+mix path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|sinc|cfg5shard] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|sinc|cfg5shard|cfg5] [--impl reference]
 
 A *step* is one complete offline render of the workload (cfg2: 256 Sampler voices with AHDSR + glide,
 cubic 44.1->48 kHz resampling, FilterEffect LP on the bus, "10 s" = 469 WavStream blocks = 480 256
@@ -58,6 +58,10 @@ def workload_spec(name):
         return dict(voices=4096, n_mixers=64, seconds=60, effects="cfg3", time_scale=6.0,
                     desc="cfg3: 4096 voices over 64 sub-mixers (8 Samplers x 8 voices each), Eq5 + Compressor + Chorus per "
                     "sub-mixer, 60 s (2880512 frames); cfg2 voice events stretched x6 so notes span the render")
+    if name == "cfg5":
+        return dict(voices=8192, n_mixers=64, seconds=10, main_bus=True,
+                    desc="cfg5, one GPU's share per rank: 8192 voices in 64 sub-mixer subtrees, NCCL reduce of the stereo bus, "
+                    "Delay + Reverb on the main bus (rank 0, after the reduce), 10 s (480256 frames)")
     if name == "cfg4":
         return dict(voices=160, n_mixers=0, seconds=10, desc="cfg4: granular, 160 voices x 100 grains/s x 100 ms Hann grains "
                     "(16k grains/s) from a 362835-frame mono buffer, AHDSR, 10 s (480256 frames)")
@@ -188,6 +192,8 @@ def build_cpu_sample(p, name, rank=0, as_subtree=False):
                          buffer=sample_buffer())
         return 128, "cfg3 with 128 of 4096 voices (2 of 64 sub-mixers, same per-voice events and effect chains)"
     W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none", seed_base=100000 * rank, buffer=sample_buffer())
+    if spec.get("main_bus") and not as_subtree:
+        W.add_main_bus_sends(p)
     return 512, f"{name} with 512 of {spec['voices']} voices (4 sub-mixers x 128, same per-voice events)"
 
 
@@ -245,6 +251,9 @@ def run_reference(args):
             total = outs[0]
             for r in range(1, world):
                 total += outs[r]
+            if spec.get("main_bus"):  # the main mixer's effects run on the sum, on the audio thread
+                from phonic_b200.distributed import finish_on_main_bus
+                total = finish_on_main_bus(api, total, SR, W.add_main_bus_sends)
         dt = time.perf_counter() - t0
         for p in players:
             p.close()
@@ -281,7 +290,7 @@ def main():
 
     import phonic_b200
     from phonic_b200 import workloads as W
-    from phonic_b200.distributed import reduce_partial_bus
+    from phonic_b200.distributed import finish_on_main_bus, reduce_partial_bus
     from phonic_b200.player import Player
 
     rank = int(os.environ.get("RANK", "0"))
@@ -334,16 +343,21 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             red_ms = e0.elapsed_time(e1)
+        main_ms, main_launches = 0.0, 0
+        if spec.get("main_bus") and rank == 0:  # cfg5: the main mixer's Delay + Reverb on the reduced sum (not shardable)
+            mst = {}
+            out_main = finish_on_main_bus(api, out_dev.cpu().numpy(), SR, W.add_main_bus_sends, device_ordinal=local_rank, stats=mst)
+            main_ms, main_launches = mst["device_ms"], mst["kernel_launches"]
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         st = p.last_render_stats()
         if i >= args.warmup:
-            dev_ms.append(st.device_ms + red_ms)
+            dev_ms.append(st.device_ms + red_ms + main_ms)
             wall_ms.append((t1 - t0) * 1e3)
             voice_ms.append(st.voice_kernel_ms)
             skel_ms.append(st.skeleton_kernel_ms)
             fx_ms.append(st.effect_kernel_ms)
-            launches += int(st.kernel_launches) + (1 if world > 1 else 0)
+            launches += int(st.kernel_launches) + (1 if world > 1 else 0) + main_launches
             vframes += int(st.voice_frames)
             sinc_ms.append(st.sinc_kernel_ms); grain_ms.append(st.grain_kernel_ms)
             sinc_frames += int(st.sinc_frames); grain_samples += int(st.grain_samples)
@@ -368,11 +382,14 @@ def main():
         t0 = time.perf_counter()
         p = Player(api, SR, device_ordinal=local_rank)
         build_scene(p, args.workload, rank=rank, as_subtree=world > 1)   # uploads the sample buffer (H2D) + schedules events
-        if world > 1:
+        if world > 1 or spec.get("main_bus"):
             p.render_device(out_dev.data_ptr(), frames)
-            reduce_partial_bus(out_dev, dst=0)
+            if world > 1:
+                reduce_partial_bus(out_dev, dst=0)
             if rank == 0:
                 out_host.copy_(out_dev, non_blocking=False)
+                if spec.get("main_bus"):
+                    out_np[:] = finish_on_main_bus(api, out_np, SR, W.add_main_bus_sends, device_ordinal=local_rank)
             torch.cuda.synchronize()
         else:
             p.render_into(out_np)                                         # graph upload (H2D), kernels, WAV data D2H

@@ -36,3 +36,30 @@ def reduce_partial_bus(bus, dst: int = 0, group=None):
     import torch.distributed as dist
     dist.reduce(bus, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return bus
+
+
+def finish_on_main_bus(api, bus, sample_rate: int, add_effects, device_ordinal: int = -1, stats=None):
+    """Rank 0's last stage: the reduced stereo bus runs through the MAIN mixer's effect chain
+    (nonlinear in the sum, so it cannot be sharded). The bus enters a fresh renderer as a file source at its own rate --
+    the resampler's equal-rate bypass, unity gain, centre pan: a bit-exact copy (scene `file_bypass`) -- and
+    `add_effects(player)` attaches the main-bus effects (cfg5: Delay + Reverb). `bus` is a host array [frames, 2] f32
+    (a multiple of the 1024-frame block); returns the final audio [frames, 2]. `stats`: optional dict that receives the
+    stage's device time."""
+    import numpy as np
+
+    from .player import FilePlaybackOptions, Player
+    bus = np.ascontiguousarray(bus, dtype=np.float32)
+    frames = bus.shape[0]
+    p = Player(api, sample_rate, device_ordinal=device_ordinal)
+    try:
+        bid = p.upload_buffer(bus, sample_rate)
+        p.play_file_source(bid, FilePlaybackOptions())
+        add_effects(p)
+        out = p.render(frames)
+        if stats is not None:
+            st = p.last_render_stats()
+            stats["device_ms"] = st.device_ms
+            stats["kernel_launches"] = int(st.kernel_launches)
+    finally:
+        p.close()
+    return out

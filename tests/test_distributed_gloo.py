@@ -47,6 +47,10 @@ def worker(rank, world, port, result_path):
     reduce_partial_bus(part, dst=0)
     if rank == 0:
         np.save(result_path, part.numpy())
+        # cfg5's last stage: the main-bus effects on the reduced sum, rank 0 only
+        from phonic_b200.distributed import finish_on_main_bus
+        from phonic_b200.player import DelayEffect
+        np.save(result_path.replace(".npy", "_main.npy"), finish_on_main_bus(api, part.numpy(), 48000, lambda q: q.add_effect(DelayEffect())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -75,3 +79,36 @@ def test_two_rank_reduce_matches_single_process_render(tmp_path, oracle_api):
     assert float(np.abs(full).max()) > 0.05
     # the reduce changes the f32 summation order across subtrees: <= 1e-6, not bit-exact
     assert float(np.abs(reduced - full).max()) <= 1e-6
+    # the same graph with a Delay on the main bus, rendered in one process, against rank 0's two-stage result
+    from phonic_b200.player import DelayEffect
+    p2 = Player(oracle_api, 48000)
+    build(p2, list(range(N_SUBTREES)))
+    p2.add_effect(DelayEffect())
+    full_main = p2.render(FRAMES)
+    two_stage = np.load(result.replace(".npy", "_main.npy"))
+    assert float(np.abs(full_main).max()) > 0.05
+    assert float(np.abs(two_stage - full_main).max()) <= 2e-6
+
+
+def test_main_bus_stage_alone_is_bit_exact(oracle_api):
+    """Without a reduce in between (one rank), rendering the sub-mixers first and the main-bus chain second gives the bytes
+    of the single-graph render: the bus re-enters as an equal-rate, unity-gain source (a copy) and the main chain sees the
+    same 1024-frame chunks."""
+    from phonic_b200.distributed import finish_on_main_bus
+    from phonic_b200.player import DelayEffect, FilterEffect, Player
+    p = Player(oracle_api, 48000)
+    build(p, [0, 1, 2])
+    bus = p.render(FRAMES)
+    p.close()
+
+    def chain(q):
+        q.add_effect(FilterEffect(0, 3000.0, 0.707))
+        q.add_effect(DelayEffect())
+    two_stage = finish_on_main_bus(oracle_api, bus, 48000, chain)
+    p = Player(oracle_api, 48000)
+    build(p, [0, 1, 2])
+    chain(p)
+    full = p.render(FRAMES)
+    p.close()
+    assert float(np.abs(full).max()) > 0.05
+    assert np.array_equal(two_stage, full)
