@@ -423,29 +423,27 @@ PB_DEV uint32_t cyc_pos(uint32_t w0, uint32_t k, uint32_t delay) {
   return v;
 }
 
-constexpr uint32_t RV_L = 256;     // frames per sub-block: below every feedback lag (predelay >= 29 * 25 = 725)
 constexpr uint32_t RV_BATCH = FX_THREADS_C / 2;  // frames per delay-line read/write batch (one thread per frame x channel)
-constexpr uint32_t RV_PL = RV_L + RV_L / 32 + 4;
+__host__ __device__ constexpr size_t rv_work_bytes(uint32_t L) { return ((size_t)10 * (L + L / 32 + 4) + (size_t)2 * 16 * RV_BATCH + 16) * sizeof(double); }
 
-PB_DEV bool reverb_parallel(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t n, uint32_t tid, uint32_t nt, ParWork w) {
-  if (lin_need_ramp(s.room) || exp_need_ramp(s.wet, cx.comp)) return false;
-  const double room = (double)s.room.target, wet = (double)s.wet.target;
-  const RvDerived d = reverb_derive(room, wet);
-  __syncthreads();
-  if (tid == 0) {  // per-call updates of ReverbEffect::process (reverb.rs:428-441)
-    (void)reverb_update_sizes(s, d.size);
-    reverb_update_filters(s, cx, d.cutoff);
-  }
-  __syncthreads();
-  const uint32_t predelay = f64_as_usize32(29.0 * d.size);
-  if (predelay < RV_L || s.ap[3].delay < RV_L || s.lines[7].delay < RV_L + 16) return false;
+// RVL = frames per sub-block: every feedback path of the reverb goes through a delay of at least RVL frames (checked by
+// the caller), so inside a sub-block each stage is a pass over all frames. 1024 (a whole chunk) when the room is large
+// enough, else 256 (predelay >= 29 * 25 = 725 always).
+template <uint32_t RVL>
+PB_DEV void reverb_parallel_impl(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t n, uint32_t tid, uint32_t nt, ParWork w,
+                                 const RvDerived& d, const uint32_t predelay) {
+  constexpr uint32_t PL = RVL + RVL / 32 + 4;
+  constexpr uint32_t E = 2 * RVL / FX_THREADS_C;  // (frame, channel) elements per thread and pass
+  const double wet = (double)s.wet.target;
   const double blend = d.blend, regen = d.regen;
   const double vib_speed = 0.1, vib_depth = 7.0;
   uint8_t* p = w.base;
-  double* A[2] = {carve<double>(p, RV_PL), carve<double>(p, RV_PL)};
+  double* A[2] = {carve<double>(p, PL), carve<double>(p, PL)};
   double* AP[4][2];
-  for (int i = 0; i < 4; ++i) { AP[i][0] = carve<double>(p, RV_PL); AP[i][1] = carve<double>(p, RV_PL); }
-  double* VP = carve<double>(p, 16 * RV_BATCH);  // vib phase after step, [line*2+ch][frame in batch]
+  for (int i = 0; i < 4; ++i) { AP[i][0] = carve<double>(p, PL); AP[i][1] = carve<double>(p, PL); }
+  double* VP = carve<double>(p, 16 * RV_BATCH);  // vibrato phase after the step, [line*2+ch][frame in batch]
+  double* FB = carve<double>(p, 16 * RV_BATCH);  // feedback of every frame of the batch, same layout
+  double* carry = carve<double>(p, 16);          // feedback of the last frame before the batch, [line*2+ch]
   const uint32_t lane = tid & 31, warp = tid >> 5;
   double* aux = cx.aux_arena;
   // counters at chunk start
@@ -457,28 +455,34 @@ PB_DEV bool reverb_parallel(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb,
   const uint32_t m_aux = s.m_aux;
   const double fpd_l = (double)s.fpd_l * 1.18e-17, fpd_r = (double)s.fpd_r * 1.18e-17;
   const int src[8] = {3, 2, 1, 0, 0, 1, 2, 3};  // a<-l, b<-k, c<-j, d<-i, e<-i, f<-j, g<-k, h<-l
+  if (tid < 16) carry[tid] = s.lines[tid >> 1].feedback[tid & 1];
 
-  for (uint32_t f0 = 0; f0 < n; f0 += RV_L) {
-    const uint32_t len = min(RV_L, n - f0);
+  for (uint32_t f0 = 0; f0 < n; f0 += RVL) {
+    const uint32_t len = min(RVL, n - f0);
     // (a) input + denormal dither, predelay DelayLine<2>::process (delay.rs:47-66): reads then writes
-    double keep[2 * RV_L / FX_THREADS_C];
     {
-      uint32_t q = 0;
-      for (uint32_t i = tid; i < len * 2; i += nt, ++q) {
-        const uint32_t f = i >> 1, ch = i & 1;
-        double x = (double)(ch ? CB_R(f0 + f) : CB_L(f0 + f));
-        if (fabs(x) < 1.18e-23) x = ch ? fpd_r : fpd_l;
-        keep[q] = x;
-        A[ch][pidx(f)] = aux[m_aux + (size_t)cyc_pos(m_w0, f0 + f + 1, predelay) * 2 + ch];
+      double keep[E];  // q is a compile-time index: the array stays in registers
+#pragma unroll
+      for (uint32_t q = 0; q < E; ++q) {
+        const uint32_t i = tid + q * FX_THREADS_C;
+        if (i < len * 2) {
+          const uint32_t f = i >> 1, ch = i & 1;
+          double x = (double)(ch ? CB_R(f0 + f) : CB_L(f0 + f));
+          if (fabs(x) < 1.18e-23) x = ch ? fpd_r : fpd_l;
+          keep[q] = x;
+          A[ch][pidx(f)] = aux[m_aux + (size_t)cyc_pos(m_w0, f0 + f + 1, predelay) * 2 + ch];
+        }
       }
       __syncthreads();
-      q = 0;
-      for (uint32_t i = tid; i < len * 2; i += nt, ++q) {
-        const uint32_t f = i >> 1, ch = i & 1;
-        aux[m_aux + (size_t)cyc_pos(m_w0, f0 + f, predelay) * 2 + ch] = keep[q];
+#pragma unroll
+      for (uint32_t q = 0; q < E; ++q) {
+        const uint32_t i = tid + q * FX_THREADS_C;
+        if (i < len * 2) {
+          const uint32_t f = i >> 1, ch = i & 1;
+          aux[m_aux + (size_t)cyc_pos(m_w0, f0 + f, predelay) * 2 + ch] = keep[q];
+        }
       }
     }
-    __syncthreads();
     // (b) biquad A (block scan, in place), * wet, sin
     if (warp < 2) {
       double ic1 = s.a_ic[warp][0], ic2 = s.a_ic[warp][1];
@@ -487,29 +491,42 @@ PB_DEV bool reverb_parallel(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb,
       if (lane == 0) { s.a_ic[warp][0] = ic1; s.a_ic[warp][1] = ic2; }
     }
     __syncthreads();
-    for (uint32_t i = tid; i < len * 2; i += nt) { const uint32_t f = i >> 1, ch = i & 1; A[ch][pidx(f)] = sin(A[ch][pidx(f)] * wet); }
-    __syncthreads();
-    // (c) four Schroeder allpasses in series (delay.rs:314-350): per stage reads, then writes
-    for (int st = 0; st < 4; ++st) {
-      double* apb = aux + ap_aux[st];
-      uint32_t q = 0;
-      for (uint32_t i = tid; i < len * 2; i += nt, ++q) {
-        const uint32_t f = i >> 1, ch = i & 1;
-        const double in = st == 0 ? A[ch][pidx(f)] : AP[st - 1][ch][pidx(f)];
-        const double delayed = apb[(size_t)cyc_pos(ap_w0[st], f0 + f + 1, ap_delay[st]) * 2 + ch];
-        const double buf = in - (delayed * 0.5);
-        keep[q] = buf;
-        AP[st][ch][pidx(f)] = buf * 0.5 + delayed;
+    // (c) sin(x * wet), then the four Schroeder allpasses in series (delay.rs:314-350). An allpass reads the slot the NEXT
+    // frame overwrites, but never a slot written inside this sub-block (delay >= RVL): the chain is pointwise per
+    // (frame, channel) -- all reads of the four stages first, then, behind one barrier, all writes.
+    {
+      double keep[4][E];
+#pragma unroll
+      for (uint32_t q = 0; q < E; ++q) {
+        const uint32_t i = tid + q * FX_THREADS_C;
+        if (i < len * 2) {
+          const uint32_t f = i >> 1, ch = i & 1;
+          double delayed[4];
+#pragma unroll
+          for (int st = 0; st < 4; ++st) delayed[st] = aux[ap_aux[st] + (size_t)cyc_pos(ap_w0[st], f0 + f + 1, ap_delay[st]) * 2 + ch];
+          double in = sin(A[ch][pidx(f)] * wet);
+#pragma unroll
+          for (int st = 0; st < 4; ++st) {
+            const double buf = in - (delayed[st] * 0.5);
+            keep[st][q] = buf;
+            in = buf * 0.5 + delayed[st];
+            AP[st][ch][pidx(f)] = in;
+          }
+        }
       }
       __syncthreads();
-      q = 0;
-      for (uint32_t i = tid; i < len * 2; i += nt, ++q) {
-        const uint32_t f = i >> 1, ch = i & 1;
-        apb[(size_t)cyc_pos(ap_w0[st], f0 + f, ap_delay[st]) * 2 + ch] = keep[q];
+#pragma unroll
+      for (uint32_t q = 0; q < E; ++q) {
+        const uint32_t i = tid + q * FX_THREADS_C;
+        if (i < len * 2) {
+          const uint32_t f = i >> 1, ch = i & 1;
+#pragma unroll
+          for (int st = 0; st < 4; ++st) aux[ap_aux[st] + (size_t)cyc_pos(ap_w0[st], f0 + f, ap_delay[st]) * 2 + ch] = keep[st][q];
+        }
       }
-      __syncthreads();
     }
-    // (d) eight modulated delay lines + Householder feedback, in batches of RV_BATCH frames
+    // (d) eight modulated delay lines + Householder feedback, in batches of RV_BATCH frames (the vibrato reads reach up
+    // to 15 frames ahead of the write position, never into frames of the same batch that are not written yet)
     for (uint32_t b0 = 0; b0 < len; b0 += RV_BATCH) {
       const uint32_t bl = min(RV_BATCH, len - b0);
       if (tid < 16) {  // vibrato phase chains (reverb.rs:596-604): serial f64 accumulate per (line, channel)
@@ -522,7 +539,6 @@ PB_DEV bool reverb_parallel(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb,
       __syncthreads();
       // gets (reverb.rs:554-586) for frame (b0 + fb) of the sub-block, channel ch
       double o[8];
-      double fbv[8];
       const uint32_t fb_i = tid >> 1, ch = tid & 1;
       const bool act = fb_i < bl;
       const uint32_t fabs_ = f0 + b0 + fb_i;  // frame index within the chunk
@@ -544,32 +560,23 @@ PB_DEV bool reverb_parallel(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb,
           ip = (1.0 - blend) * ip + (v1 * blend);
           o[i] = ip;
         }
-        fbv[0] = (o[0] - (o[1] + o[2] + o[3])) * regen;
-        fbv[1] = (o[1] - (o[0] + o[2] + o[3])) * regen;
-        fbv[2] = (o[2] - (o[0] + o[1] + o[3])) * regen;
-        fbv[3] = (o[3] - (o[0] + o[1] + o[2])) * regen;
-        fbv[4] = (o[4] - (o[5] + o[6] + o[7])) * regen;
-        fbv[5] = (o[5] - (o[4] + o[6] + o[7])) * regen;
-        fbv[6] = (o[6] - (o[4] + o[5] + o[7])) * regen;
-        fbv[7] = (o[7] - (o[4] + o[5] + o[6])) * regen;
+        FB[(0 * 2 + ch) * RV_BATCH + fb_i] = (o[0] - (o[1] + o[2] + o[3])) * regen;
+        FB[(1 * 2 + ch) * RV_BATCH + fb_i] = (o[1] - (o[0] + o[2] + o[3])) * regen;
+        FB[(2 * 2 + ch) * RV_BATCH + fb_i] = (o[2] - (o[0] + o[1] + o[3])) * regen;
+        FB[(3 * 2 + ch) * RV_BATCH + fb_i] = (o[3] - (o[0] + o[1] + o[2])) * regen;
+        FB[(4 * 2 + ch) * RV_BATCH + fb_i] = (o[4] - (o[5] + o[6] + o[7])) * regen;
+        FB[(5 * 2 + ch) * RV_BATCH + fb_i] = (o[5] - (o[4] + o[6] + o[7])) * regen;
+        FB[(6 * 2 + ch) * RV_BATCH + fb_i] = (o[6] - (o[4] + o[5] + o[7])) * regen;
+        FB[(7 * 2 + ch) * RV_BATCH + fb_i] = (o[7] - (o[4] + o[5] + o[6])) * regen;
       }
       __syncthreads();
-      if (act) {
-        // the set of THIS frame used the previous frame's feedback; this frame's feedback feeds the next set.
-        // Writes: set(frame) = ap_src[frame] + feedback[frame - 1]. Do the sets of frames b0..b0+bl-1 here:
-        // frame's own set needs feedback of frame-1, which lives in the neighbouring thread -> exchange via VP.
-      }
-      // exchange feedback through shared memory (reuse VP: [line*2+ch][frame in batch])
-      if (act) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) VP[(i * 2 + ch) * RV_BATCH + fb_i] = fbv[i];
-      }
-      __syncthreads();
+      // sets: set(frame) = allpass output of the frame + the feedback of frame - 1 (the neighbouring thread's, or the
+      // carry of the previous batch for the first frame)
       if (act) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           double* lb = aux + ln_aux[i];
-          const double prev_fb = fb_i == 0 ? s.lines[i].feedback[ch] : VP[(i * 2 + ch) * RV_BATCH + fb_i - 1];
+          const double prev_fb = fb_i == 0 ? carry[i * 2 + ch] : FB[(i * 2 + ch) * RV_BATCH + fb_i - 1];
           const uint32_t cnt = cyc_pos(ln_c0[i], fabs_, ln_delay[i]);
           lb[(size_t)cnt * 2 + ch] = AP[src[i]][ch][pidx(b0 + fb_i)] + prev_fb;
         }
@@ -577,8 +584,7 @@ PB_DEV bool reverb_parallel(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb,
         A[ch][pidx(b0 + fb_i)] = (o[0] + o[1] + o[2] + o[3] + o[4] + o[5] + o[6] + o[7]) / 8.0;
       }
       __syncthreads();
-      if (tid < 16) s.lines[tid >> 1].feedback[tid & 1] = VP[tid * RV_BATCH + bl - 1];
-      __syncthreads();
+      if (tid < 16) carry[tid] = FB[tid * RV_BATCH + bl - 1];  // read again only behind the next batch's two barriers
     }
     // (e) biquad B, clamp, asin, biquad C, dry mix
     if (warp < 2) {
@@ -610,12 +616,31 @@ PB_DEV bool reverb_parallel(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb,
     }
     __syncthreads();
   }
+  if (tid < 16) s.lines[tid >> 1].feedback[tid & 1] = carry[tid];
   if (tid == 0) {
     s.m_write_pos = cyc_pos(m_w0, n, predelay);
     for (int i = 0; i < 4; ++i) s.ap[i].write_pos = cyc_pos(ap_w0[i], n, ap_delay[i]);
     for (int i = 0; i < 8; ++i) s.lines[i].count = cyc_pos(ln_c0[i], n, ln_delay[i]);
   }
   __syncthreads();
+}
+
+PB_DEV bool reverb_parallel(ReverbState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t n, uint32_t tid, uint32_t nt, ParWork w) {
+  if (lin_need_ramp(s.room) || exp_need_ramp(s.wet, cx.comp)) return false;
+  const double room = (double)s.room.target, wet = (double)s.wet.target;
+  const RvDerived d = reverb_derive(room, wet);
+  __syncthreads();
+  if (tid == 0) {  // per-call updates of ReverbEffect::process (reverb.rs:428-441)
+    (void)reverb_update_sizes(s, d.size);
+    reverb_update_filters(s, cx, d.cutoff);
+  }
+  __syncthreads();
+  const uint32_t predelay = f64_as_usize32(29.0 * d.size);
+  // shortest feedback lag: the predelay, the shortest allpass (ap[3]) and the shortest line (lines[7]) less its look-ahead
+  const uint32_t lag = min(min(predelay, s.ap[3].delay), s.lines[7].delay >= 16 ? s.lines[7].delay - 16 : 0u);
+  if (lag >= 1024 && w.bytes >= rv_work_bytes(1024)) reverb_parallel_impl<1024>(s, cx, cb, n, tid, nt, w, d, predelay);
+  else if (lag >= 256 && w.bytes >= rv_work_bytes(256)) reverb_parallel_impl<256>(s, cx, cb, n, tid, nt, w, d, predelay);
+  else return false;
   return true;
 }
 

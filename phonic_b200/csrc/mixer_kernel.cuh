@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) mix_sum_kernel(MixerKernelArgs a) {
 
 // ---- M2 -------------------------------------------------------------------------------------------------
 constexpr uint32_t FX_THREADS = FX_THREADS_C;
-constexpr uint32_t FX_WORK_BYTES = 48 * 1024;  // shared-memory work area of the chunk-parallel effects
+constexpr uint32_t FX_WORK_BYTES = 120 * 1024;  // shared-memory work area of the chunk-parallel effects (the reverb's ten f64 planes of a whole chunk)
 
 __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
   __shared__ float s_ch[2][PLANE];
