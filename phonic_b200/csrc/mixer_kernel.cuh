@@ -38,6 +38,7 @@ struct MixerKernelArgs {
   float* out;                     // device output for this block (interleaved stereo) or nullptr
   ExpSm* master;                  // WavStream::smoothed_volume
   uint32_t wav_block_frames;      // 1024
+  uint32_t work_bytes;            // dynamic shared memory of this launch (FX_WORK_SMALL unless a mixer of the level holds a reverb)
   unsigned long long* prof;       // PB200_FX_PROF: [8] cycle counters of the main mixer's CTA (debug aid)
 };
 
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) mix_sum_kernel(MixerKernelArgs a) {
 
 // ---- M2 -------------------------------------------------------------------------------------------------
 constexpr uint32_t FX_THREADS = FX_THREADS_C;
+constexpr uint32_t FX_WORK_SMALL = 48 * 1024;   // every effect but the whole-chunk reverb fits: keeps the L1 carve-out and 3 CTAs per SM
 constexpr uint32_t FX_WORK_BYTES = 120 * 1024;  // shared-memory work area of the chunk-parallel effects (the reverb's ten f64 planes of a whole chunk)
 
 __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
   __shared__ float s_red[FX_THREADS / 32];
   __shared__ uint32_t s_run;      // effect e runs this chunk
   extern __shared__ __align__(16) uint8_t s_work[];
-  const ParWork pw{s_work, FX_WORK_BYTES};
+  const ParWork pw{s_work, a.work_bytes};
 
   const uint32_t m = a.level_mixers[blockIdx.x];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;

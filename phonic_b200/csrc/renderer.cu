@@ -1463,7 +1463,10 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
       const uint32_t nlm = (uint32_t)c.levels[lvl].size();
       mix_sum_kernel<<<dim3((blen + 255) / 256, nlm), 256, 0, r->sm>>>(ma);
-      mix_fx_kernel<<<nlm, FX_THREADS, FX_WORK_BYTES, r->sm>>>(ma);
+      bool has_reverb = false;
+      for (uint32_t mi : c.levels[lvl]) for (uint32_t fi : r->mixers[mi].effects) has_reverb |= r->fxs[fi].kind == FX_REVERB;
+      ma.work_bytes = has_reverb ? FX_WORK_BYTES : FX_WORK_SMALL;
+      mix_fx_kernel<<<nlm, FX_THREADS, ma.work_bytes, r->sm>>>(ma);
       launches += 2;
     }
     CUDA_TRY(cudaEventRecord(ev_m1[b], r->sm));
