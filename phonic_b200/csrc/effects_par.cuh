@@ -424,7 +424,7 @@ PB_DEV uint32_t cyc_pos(uint32_t w0, uint32_t k, uint32_t delay) {
 }
 
 constexpr uint32_t RV_BATCH = FX_THREADS_C / 2;  // frames per delay-line read/write batch (one thread per frame x channel)
-__host__ __device__ constexpr size_t rv_work_bytes(uint32_t L) { return ((size_t)10 * (L + L / 32 + 4) + (size_t)2 * 16 * RV_BATCH + 16) * sizeof(double); }
+__host__ __device__ constexpr size_t rv_work_bytes(uint32_t L) { return ((size_t)10 * (L + L / 32 + 4) + (size_t)2 * 16 * RV_BATCH + 32 + 16) * sizeof(double); }
 
 // RVL = frames per sub-block: every feedback path of the reverb goes through a delay of at least RVL frames (checked by
 // the caller), so inside a sub-block each stage is a pass over all frames. 1024 (a whole chunk) when the room is large
@@ -441,7 +441,8 @@ PB_DEV void reverb_parallel_impl(ReverbState& s, const FxCtx& cx, const ChunkBuf
   double* A[2] = {carve<double>(p, PL), carve<double>(p, PL)};
   double* AP[4][2];
   for (int i = 0; i < 4; ++i) { AP[i][0] = carve<double>(p, PL); AP[i][1] = carve<double>(p, PL); }
-  double* VP = carve<double>(p, 16 * RV_BATCH);  // vibrato phase after the step, [line*2+ch][frame in batch]
+  double* VT = carve<double>(p, 16 * RV_BATCH);  // (cos, sin)(k * inc_line), k = 1..RV_BATCH: [line][k - 1][2]
+  double* VB = carve<double>(p, 32);             // (sin, cos) of every (line, channel)'s phase at the batch start
   double* FB = carve<double>(p, 16 * RV_BATCH);  // feedback of every frame of the batch, same layout
   double* carry = carve<double>(p, 16);          // feedback of the last frame before the batch, [line*2+ch]
   const uint32_t lane = tid & 31, warp = tid >> 5;
@@ -456,6 +457,16 @@ PB_DEV void reverb_parallel_impl(ReverbState& s, const FxCtx& cx, const ChunkBuf
   const double fpd_l = (double)s.fpd_l * 1.18e-17, fpd_r = (double)s.fpd_r * 1.18e-17;
   const int src[8] = {3, 2, 1, 0, 0, 1, 2, 3};  // a<-l, b<-k, c<-j, d<-i, e<-i, f<-j, g<-k, h<-l
   if (tid < 16) carry[tid] = s.lines[tid >> 1].feedback[tid & 1];
+  // The vibrato phase of a line advances by a constant per frame (reverb.rs:596-604), so sin(phase) of frame k of a batch
+  // is a rotation of the batch's start phase by k * inc: the 2048 f64 sines of a batch become 16 sincos + a table
+  // lookup and two multiplies per read. The phase itself is still accumulated serially (the state must stay the
+  // reference's); the rotated argument differs from the accumulated one by rounding noise (~1e-11 rad).
+  for (uint32_t i = tid; i < 8 * RV_BATCH; i += nt) {
+    const uint32_t line = i / RV_BATCH, k = i % RV_BATCH + 1;
+    double sk, ck;
+    sincos((double)k * (s.lines[line].depth * vib_speed), &sk, &ck);
+    VT[i * 2] = ck; VT[i * 2 + 1] = sk;
+  }
 
   for (uint32_t f0 = 0; f0 < n; f0 += RVL) {
     const uint32_t len = min(RVL, n - f0);
@@ -532,8 +543,11 @@ PB_DEV void reverb_parallel_impl(ReverbState& s, const FxCtx& cx, const ChunkBuf
       if (tid < 16) {  // vibrato phase chains (reverb.rs:596-604): serial f64 accumulate per (line, channel)
         RvLine& L = s.lines[tid >> 1];
         double ph = L.vib_phase[tid & 1];
+        double sb, cb_;
+        sincos(ph, &sb, &cb_);
+        VB[tid * 2] = sb; VB[tid * 2 + 1] = cb_;
         const double inc = L.depth * vib_speed;
-        for (uint32_t f = 0; f < bl; ++f) { ph += inc; VP[tid * RV_BATCH + f] = ph; }
+        for (uint32_t f = 0; f < bl; ++f) ph += inc;
         L.vib_phase[tid & 1] = ph;
       }
       __syncthreads();
@@ -548,7 +562,8 @@ PB_DEV void reverb_parallel_impl(ReverbState& s, const FxCtx& cx, const ChunkBuf
           const double* lb = aux + ln_aux[i];
           const uint32_t dl = ln_delay[i];
           const uint32_t cnt = cyc_pos(ln_c0[i], fabs_ + 1, dl);
-          const double offset = (sin(VP[(i * 2 + ch) * RV_BATCH + fb_i]) + 1.0) * vib_depth;
+          const double vsin = VB[(i * 2 + ch) * 2] * VT[(i * RV_BATCH + fb_i) * 2] + VB[(i * 2 + ch) * 2 + 1] * VT[(i * RV_BATCH + fb_i) * 2 + 1];
+          const double offset = (vsin + 1.0) * vib_depth;
           const double working = (double)cnt + offset;
           const double wf = floor(working);
           const double frac = working - wf;
