@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU pass that produces every number / profile of a round (run through gpurun; outputs under gpurun_out/).
 # usage: tools/final_gpu_pass.sh <round tag>
-TAG=${1:-r01d}
+TAG=${1:-r01f}
 O=gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > $O/${TAG}_pytest_gpu.txt
 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.txt 2>&1
