@@ -280,6 +280,14 @@ typedef struct pb200_event {
  * (unique_note_id, src/generator.rs:30-33) and written back to `ev->note_id`. */
 PB200_API int pb200_schedule(pb200_renderer *r, pb200_event *ev);
 
+/* A whole score in one call: the events are queued in array order exactly as `count` pb200_schedule calls would (ids of
+ * NOTE_ON events are written back). An event flagged PB200_EVF_NOTE_FROM_BATCH carries in `note_id` the INDEX (in this
+ * array, lower than its own) of the NOTE_ON event whose freshly allocated id it refers to. Stops at the first error;
+ * `*scheduled` = events queued. (The reference's handles push one message per call into lock-free queues,
+ * src/player/handles/generator.rs:62-437; an offline score has no reason to cross the FFI once per event.) */
+#define PB200_EVF_NOTE_FROM_BATCH 8u
+PB200_API int pb200_schedule_many(pb200_renderer *r, pb200_event *events, uint32_t count, uint32_t *scheduled);
+
 /* ---- render: repeated WavStream::process (src/output/wav.rs:210-250) -----------------------
  * Renders `frames` output frames (interleaved f32, channel_count channels) as the reference
  * would in consecutive block_frames-sized `Source::write` calls on the main mixer, including

@@ -25,6 +25,7 @@
 #define pb200_free po_free
 #define pb200_upload_wav po_upload_wav
 #define pb200_render_to_wav po_render_to_wav
+#define pb200_schedule_many po_schedule_many
 #include "../include/phonic_b200.h"
 
 #include <chrono>
@@ -422,6 +423,24 @@ int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frame
   if (frames_written) *frames_written = done;
   r->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return PB200_OK;
+}
+
+int pb200_schedule_many(pb200_renderer* r, pb200_event* events, uint32_t count, uint32_t* scheduled) {
+  if (!r || (!events && count)) return PB200_ERR_PARAMETER;
+  uint32_t i = 0;
+  int rc = PB200_OK;
+  for (; i < count; ++i) {
+    pb200_event& ev = events[i];
+    if (ev.flags & PB200_EVF_NOTE_FROM_BATCH) {
+      const uint64_t idx = ev.note_id;
+      if (idx >= i || events[idx].kind != PB200_EV_NOTE_ON) { rc = fail(r, PB200_ERR_PARAMETER, "batch note reference must point at an earlier NOTE_ON"); break; }
+      ev.note_id = events[idx].note_id;
+      ev.flags &= ~PB200_EVF_NOTE_FROM_BATCH;
+    }
+    if ((rc = pb200_schedule(r, &ev)) != PB200_OK) break;
+  }
+  if (scheduled) *scheduled = i;
+  return rc;
 }
 
 // ---- WAV in / out, written independently of the product's wav_io.h (chunk walk over the FILE, sample conversion per

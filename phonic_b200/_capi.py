@@ -47,7 +47,7 @@ EV_SET_NOTE_VOLUME = 14
 EV_SET_NOTE_PANNING = 15
 EV_SET_EFFECT_PARAMETER = 20
 
-EVF_NORMALIZED, EVF_HAS_VOLUME, EVF_HAS_PANNING = 1, 2, 4
+EVF_NORMALIZED, EVF_HAS_VOLUME, EVF_HAS_PANNING, EVF_NOTE_FROM_BATCH = 1, 2, 4, 8
 
 
 class Config(C.Structure):
@@ -155,6 +155,7 @@ SYMBOLS = {
     "source_status_get": (C.c_int, [_R, U32, _P(SourceStatus)]),
     "sampler_voice_states": (C.c_int, [_R, U32, _P(VoiceState), U32, _P(U32)]),
     "last_render_stats": (C.c_int, [_R, _P(RenderStats)]),
+    "schedule_many": (C.c_int, [_R, _P(Event), U32, _P(U32)]),
     "decode_wav": (C.c_int, [C.c_char_p, _P(_P(F32)), _P(WavInfo)]),
     "free": (None, [C.c_void_p]),
     "upload_wav": (C.c_int, [_R, C.c_char_p, _P(U32), _P(WavInfo)]),

@@ -1573,6 +1573,24 @@ int pb200_render_device(pb200_renderer* r, float* out_device, uint64_t frames, u
   return render_impl(r, out_device, nullptr, frames, frames_written);
 }
 
+int pb200_schedule_many(pb200_renderer* r, pb200_event* events, uint32_t count, uint32_t* scheduled) {
+  if (!r || (!events && count)) return PB200_ERR_PARAMETER;
+  uint32_t i = 0;
+  int rc = PB200_OK;
+  for (; i < count; ++i) {
+    pb200_event& ev = events[i];
+    if (ev.flags & PB200_EVF_NOTE_FROM_BATCH) {
+      const uint64_t idx = ev.note_id;
+      if (idx >= i || events[idx].kind != PB200_EV_NOTE_ON) { rc = fail(r, PB200_ERR_PARAMETER, "batch note reference must point at an earlier NOTE_ON"); break; }
+      ev.note_id = events[idx].note_id;
+      ev.flags &= ~PB200_EVF_NOTE_FROM_BATCH;
+    }
+    if ((rc = pb200_schedule(r, &ev)) != PB200_OK) break;
+  }
+  if (scheduled) *scheduled = i;
+  return rc;
+}
+
 int pb200_decode_wav(const char* path, float** interleaved, pb200_wav_info* info) {
   if (!path || !interleaved || !info) return PB200_ERR_PARAMETER;
   pbh::WavData w;

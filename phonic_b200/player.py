@@ -182,6 +182,21 @@ class PanningEffect:
     """PanningEffect::new() (src/effect/pan.rs:52-60); parameters 'pan ', 'wdth', 'invl', 'invr' via set_parameter."""
 
 
+class BatchNote:
+    """Placeholder for the NotePlaybackId of a note_on queued inside `Player.batch()`: `index` = position of the NOTE_ON in
+    the batch; `id` is the real id once the batch has been flushed."""
+    __slots__ = ("index", "id")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.id = None
+
+    def __int__(self):
+        if self.id is None:
+            raise RuntimeError("note id is only known after the batch has been flushed")
+        return self.id
+
+
 class _Handle:
     def __init__(self, player: "Player", ident: int):
         self._p = player
@@ -193,7 +208,18 @@ class _Handle:
         ev.kind = kind
         ev.target = self.id
         for k, v in kw.items():
-            setattr(ev, k, v)
+            if k == "note_id" and isinstance(v, BatchNote):
+                if v.id is None:  # refers to a NOTE_ON of the open batch
+                    ev.note_id = v.index
+                    ev.flags |= A.EVF_NOTE_FROM_BATCH
+                else:
+                    ev.note_id = v.id
+            else:
+                setattr(ev, k, v)
+        batch = self._p._batch
+        if batch is not None:
+            batch.append(ev)
+            return ev
         self._p._check(self._p.api.schedule(self._p._r, C.byref(ev)))
         return ev
 
@@ -242,6 +268,10 @@ class GeneratorPlaybackHandle(_Handle):
         flags = (A.EVF_HAS_VOLUME if volume is not None else 0) | (A.EVF_HAS_PANNING if panning is not None else 0)
         ev = self._ev(A.EV_NOTE_ON, sample_time, note=int(note), value=volume or 0.0,
                       value2=panning or 0.0, flags=flags)
+        if self._p._batch is not None:
+            note = BatchNote(len(self._p._batch) - 1)
+            self._p._batch_notes.append(note)
+            return note
         return int(ev.note_id)
 
     def note_off(self, note_id: int, sample_time=None):
@@ -300,6 +330,8 @@ class Player:
         if code != A.OK:
             raise PhonicError(code, "pb200_create failed")
         self._r = r
+        self._batch = None       # events collected by batch()
+        self._batch_notes = []
 
     def close(self):
         if self._r:
@@ -328,6 +360,30 @@ class Player:
         self._check(self.api.upload_buffer(self._r, a.ctypes.data_as(C.POINTER(A.F32)), frames, ch, sample_rate,
                                            ls, le, 1 if add_pad_frame else 0, C.byref(bid)))
         return bid.value
+
+    def batch(self):
+        """Context manager: handle calls made inside are collected and queued with ONE pb200_schedule_many call on exit
+        (same order, same result as the individual calls). note_on returns a BatchNote placeholder usable for the note's
+        later events inside or after the batch."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            if self._batch is not None:
+                raise RuntimeError("batches do not nest")
+            self._batch, self._batch_notes = [], []
+            try:
+                yield self
+            finally:
+                evs, notes = self._batch, self._batch_notes
+                self._batch, self._batch_notes = None, []
+                if evs:
+                    arr = (A.Event * len(evs))(*evs)
+                    done = A.U32()
+                    self._check(self.api.schedule_many(self._r, arr, len(evs), C.byref(done)))
+                    for n in notes:
+                        n.id = int(arr[n.index].note_id)
+        return cm()
 
     def upload_wav(self, path: str):
         """AudioFileBuffer::from_file for a RIFF/WAVE file (src/source/file/buffer.rs:64-119). Returns (buffer id, WavInfo)."""

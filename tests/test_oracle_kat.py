@@ -307,3 +307,47 @@ def test_distortion_shapers_known_answers(oracle_lib):
         # more drive -> louder output -> smaller compensation (the wavefolder folds the peaks back instead)
         if t != 4:
             assert lib.po_test_dist_compensation(C.c_uint32(t), C.c_float(4.0)) < lib.po_test_dist_compensation(C.c_uint32(t), C.c_float(0.5))
+
+
+def test_schedule_many_equals_individual_calls(oracle_api):
+    """pb200_schedule_many: one call for a whole score, same audio and same note ids as the individual handle calls
+    (note-addressed events refer to NOTE_ONs of the same batch by index)."""
+    from phonic_b200 import workloads as W
+    from phonic_b200.player import BatchNote, Player
+    outs, ids = [], []
+    for batched in (False, True):
+        p = Player(oracle_api, 48000)
+        buf = W.synth_buffer(20000, 44100, seed=1)
+        bid = p.upload_buffer(buf, 44100)
+        if batched:
+            with p.batch():
+                hs = W.add_voice_bank(p, W.VoiceBankSpec(voices=12, voices_per_sampler=4), bid, None, 0, 0.05)
+                late = hs[0].note_on(50, volume=0.2, sample_time=1000)
+                assert isinstance(late, BatchNote)
+            hs[0].note_off(late, sample_time=9000)   # a placeholder keeps working after the flush
+            ids.append(int(late))
+        else:
+            hs = W.add_voice_bank(p, W.VoiceBankSpec(voices=12, voices_per_sampler=4), bid, None, 0, 0.05)
+            late = hs[0].note_on(50, volume=0.2, sample_time=1000)
+            hs[0].note_off(late, sample_time=9000)
+            ids.append(int(late))
+        outs.append(p.render(24 * 1024))
+        p.close()
+    assert ids[0] == ids[1]
+    assert float(np.abs(outs[0]).max()) > 0.01
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_schedule_many_rejects_forward_references(oracle_api):
+    import ctypes as CT
+    from phonic_b200 import _capi as A
+    from phonic_b200.player import Player
+    p = Player(oracle_api, 48000)
+    evs = (A.Event * 1)()
+    evs[0].kind = A.EV_NOTE_OFF
+    evs[0].target = 1
+    evs[0].note_id = 0
+    evs[0].flags = A.EVF_NOTE_FROM_BATCH
+    done = A.U32(7)
+    assert oracle_api.schedule_many(p._r, evs, 1, CT.byref(done)) == A.ERR_PARAMETER and done.value == 0
+    p.close()
