@@ -91,11 +91,11 @@ def build_scene(player, name, rank=0, as_subtree=False):
     buf = sample_buffer()
     if name == "cfg2":
         if not as_subtree:
-            W.build_cfg2(player, W.VoiceBankSpec(voices=spec["voices"]), buffer=buf)
+            W.build_cfg2(player, W.VoiceBankSpec(voices=spec["voices"]), buffer=buf, fast=True)
         else:  # one GPU's shard of an N-GPU graph: the bank lives on a sub-mixer of the main mixer
             bid = player.upload_buffer(buf, 44100)
             mh = player.add_mixer(None)
-            W.add_voice_bank(player, W.VoiceBankSpec(voices=spec["voices"]), bid, mh.id, seed_offset=7919 * rank)
+            W.add_voice_bank_fast(player, W.VoiceBankSpec(voices=spec["voices"]), bid, mh.id, seed_offset=7919 * rank)
             player.add_effect(FilterEffect(0, 2000.0, 0.707), mh.id)
     elif name == "cfg4":
         W.build_cfg4(player, spec["voices"])
@@ -104,7 +104,7 @@ def build_scene(player, name, rank=0, as_subtree=False):
     else:
         W.build_subtrees(player, spec["n_mixers"], spec["voices"] // spec["n_mixers"], W.VoiceBankSpec(),
                          effects=spec.get("effects", "none"), time_scale=spec.get("time_scale", 1.0),
-                         seed_base=100000 * rank, buffer=buf)
+                         seed_base=100000 * rank, buffer=buf, fast=True)
     return spec["voices"]
 
 
@@ -189,9 +189,9 @@ def build_cpu_sample(p, name, rank=0, as_subtree=False):
         return 16, "sinc bank with 16 of 1024 voices"
     if name == "cfg3":
         W.build_subtrees(p, 2, 64, W.VoiceBankSpec(), effects="cfg3", time_scale=spec["time_scale"], seed_base=100000 * rank,
-                         buffer=sample_buffer())
+                         buffer=sample_buffer(), fast=True)
         return 128, "cfg3 with 128 of 4096 voices (2 of 64 sub-mixers, same per-voice events and effect chains)"
-    W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none", seed_base=100000 * rank, buffer=sample_buffer())
+    W.build_subtrees(p, 4, 128, W.VoiceBankSpec(), effects="none", seed_base=100000 * rank, buffer=sample_buffer(), fast=True)
     if spec.get("main_bus") and not as_subtree:
         W.add_main_bus_sends(p)
     return 512, f"{name} with 512 of {spec['voices']} voices (4 sub-mixers x 128, same per-voice events)"

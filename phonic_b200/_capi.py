@@ -114,6 +114,16 @@ class Event(C.Structure):
                 ("flags", U32), ("speed", F64), ("position_nanos", U64)]
 
 
+def event_dtype():
+    """numpy structured dtype with the memory layout of pb200_event (for pb200_schedule_many from an array)."""
+    import numpy as np
+    dt = np.dtype([("sample_time", "<u8"), ("kind", "<u4"), ("target", "<u4"), ("note_id", "<u8"), ("note", "<u4"),
+                   ("param_id", "<u4"), ("value", "<f4"), ("value2", "<f4"), ("glide", "<f4"), ("flags", "<u4"),
+                   ("speed", "<f8"), ("position_nanos", "<u8")], align=True)
+    assert dt.itemsize == C.sizeof(Event)
+    return dt
+
+
 class SourceStatus(C.Structure):
     _fields_ = [("is_playing", U32), ("exhausted", U32), ("end_frame", U64), ("playback_pos", U64)]
 

@@ -385,6 +385,14 @@ class Player:
                         n.id = int(arr[n.index].note_id)
         return cm()
 
+    def schedule_array(self, events: np.ndarray) -> int:
+        """Queue a whole score held in a numpy array of `_capi.event_dtype()` records with ONE pb200_schedule_many call
+        (the array is updated in place: NOTE_ON ids are written back, batch references resolved). Returns the count."""
+        assert events.dtype == A.event_dtype() and events.flags.c_contiguous
+        done = A.U32()
+        self._check(self.api.schedule_many(self._r, events.ctypes.data_as(C.POINTER(A.Event)), len(events), C.byref(done)))
+        return done.value
+
     def upload_wav(self, path: str):
         """AudioFileBuffer::from_file for a RIFF/WAVE file (src/source/file/buffer.rs:64-119). Returns (buffer id, WavInfo)."""
         bid, info = A.U32(), A.WavInfo()

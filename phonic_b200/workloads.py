@@ -122,13 +122,54 @@ def add_voice_bank(player: Player, spec: VoiceBankSpec, buffer_id: int, mixer_id
     return handles
 
 
-def build_cfg2(player: Player, spec: VoiceBankSpec | None = None, time_scale: float = 1.0, buffer=None):
+_SCORE_ARRAYS: dict = {}
+
+
+def voice_bank_events(spec: VoiceBankSpec, seed_offset: int = 0, time_scale: float = 1.0):
+    """The same score as `voice_bank_score`, as one array of pb200_event records in the order add_voice_bank queues
+    them (note-on, glide, note-off per voice; note-addressed events refer to their NOTE_ON by batch index). `target`
+    holds the sampler's index in the bank; `add_voice_bank_fast` replaces it with the generator id. Cached."""
+    from . import _capi as A
+    key = (tuple(sorted(spec.__dict__.items())), seed_offset, time_scale)
+    if key in _SCORE_ARRAYS:
+        return _SCORE_ARRAYS[key]
+    gain = 1.0 / math.sqrt(max(spec.voices, 1))
+    rows = []
+    for si, voices in enumerate(voice_bank_score(spec, seed_offset, time_scale)):
+        for note, t_on, pan, glide, t_off in voices:
+            on = len(rows)
+            rows.append((t_on, A.EV_NOTE_ON, si, 0, note, 0, gain, pan, 0.0, A.EVF_HAS_VOLUME | A.EVF_HAS_PANNING, 0.0, 0))
+            if glide is not None:
+                rows.append((glide[0], A.EV_SET_NOTE_SPEED, si, on, 0, 0, 0.0, 0.0, glide[2], A.EVF_NOTE_FROM_BATCH, speed_from_note(glide[1]), 0))
+            if t_off is not None:
+                rows.append((t_off, A.EV_NOTE_OFF, si, on, 0, 0, 0.0, 0.0, 0.0, A.EVF_NOTE_FROM_BATCH, 0.0, 0))
+    arr = np.array(rows, dtype=A.event_dtype())
+    counts = [len(v) for v in voice_bank_score(spec, seed_offset, time_scale)]
+    _SCORE_ARRAYS[key] = (arr, counts)
+    return _SCORE_ARRAYS[key]
+
+
+def add_voice_bank_fast(player: Player, spec: VoiceBankSpec, buffer_id: int, mixer_id=None, seed_offset: int = 0,
+                        time_scale: float = 1.0):
+    """add_voice_bank with the events queued by one pb200_schedule_many call from the cached event array (what a host
+    program does with a score it has loaded): same graph, same events in the same order, same audio."""
+    template, counts = voice_bank_events(spec, seed_offset, time_scale)
+    ahdsr = AhdsrParameters(attack=0.01, hold=0.0, decay=0.5, sustain=0.75, release=1.0)
+    handles = [player.add_generator(buffer_id, GeneratorPlaybackOptions(volume=1.0, panning=0.0, voices=nv), ahdsr, mixer_id=mixer_id)
+               for nv in counts]
+    events = template.copy()
+    events["target"] = np.asarray([h.id for h in handles], dtype=np.uint32)[template["target"]]
+    player.schedule_array(events)
+    return handles
+
+
+def build_cfg2(player: Player, spec: VoiceBankSpec | None = None, time_scale: float = 1.0, buffer=None, fast: bool = False):
     """cfg2: 256 Sampler voices (AHDSR + glide), cubic resampling, FilterEffect LP 2 kHz on the bus.
     `buffer`: the (already synthesised) host sample data; generated here when None."""
     spec = spec or VoiceBankSpec()
     buf = buffer if buffer is not None else synth_buffer(int(spec.buffer_seconds * spec.buffer_rate), spec.buffer_rate, seed=1)
     bid = player.upload_buffer(buf, spec.buffer_rate)
-    handles = add_voice_bank(player, spec, bid, None, 0, time_scale)
+    handles = (add_voice_bank_fast if fast else add_voice_bank)(player, spec, bid, None, 0, time_scale)
     fx = player.add_effect(FilterEffect(0, 2000.0, 0.707))
     return handles, fx
 
@@ -143,7 +184,7 @@ def build_cfg1(player: Player, buffer: np.ndarray, buffer_rate: int):
 
 
 def build_subtrees(player: Player, n_mixers: int, voices_per_mixer: int, spec: VoiceBankSpec, effects: str = "none",
-                   time_scale: float = 1.0, seed_base: int = 0, buffer=None):
+                   time_scale: float = 1.0, seed_base: int = 0, buffer=None, fast: bool = False):
     """cfg3 / cfg5 shape: `n_mixers` sub-mixers of the main mixer, each with a cfg2-style bank.
     effects: 'none' | 'cfg3' (Eq5 + Compressor + Chorus per sub-mixer)."""
     buf = buffer if buffer is not None else synth_buffer(int(spec.buffer_seconds * spec.buffer_rate), spec.buffer_rate, seed=1)
@@ -153,7 +194,7 @@ def build_subtrees(player: Player, n_mixers: int, voices_per_mixer: int, spec: V
     for m in range(n_mixers):
         mh = player.add_mixer(None)
         sub = VoiceBankSpec(**{**spec.__dict__, "voices": voices_per_mixer})
-        hs = add_voice_bank(player, sub, bid, mh.id, seed_offset=1000 * (m + 1) + seed_base, time_scale=time_scale)
+        hs = (add_voice_bank_fast if fast else add_voice_bank)(player, sub, bid, mh.id, seed_offset=1000 * (m + 1) + seed_base, time_scale=time_scale)
         if effects == "cfg3":
             eq = player.add_effect(Eq5Effect(), mh.id)
             for b in range(5):

@@ -351,3 +351,19 @@ def test_schedule_many_rejects_forward_references(oracle_api):
     done = A.U32(7)
     assert oracle_api.schedule_many(p._r, evs, 1, CT.byref(done)) == A.ERR_PARAMETER and done.value == 0
     p.close()
+
+
+def test_score_array_equals_handle_calls(oracle_api):
+    """workloads.add_voice_bank_fast (one pb200_schedule_many call from a numpy score) == add_voice_bank (handle calls)."""
+    from phonic_b200 import workloads as W
+    from phonic_b200.player import Player
+    outs = []
+    for fast in (False, True):
+        p = Player(oracle_api, 48000)
+        bid = p.upload_buffer(W.synth_buffer(20000, 44100, seed=1), 44100)
+        spec = W.VoiceBankSpec(voices=20, voices_per_sampler=8)
+        (W.add_voice_bank_fast if fast else W.add_voice_bank)(p, spec, bid, None, 3, 0.05)
+        outs.append(p.render(24 * 1024))
+        p.close()
+    assert float(np.abs(outs[0]).max()) > 0.01
+    assert np.array_equal(outs[0], outs[1])
