@@ -468,7 +468,7 @@ def main():
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload) or {}
             if tr.get("kernel") == roofline["kernel"] and tr.get("bytes_per_launch"):
                 roofline["traffic"] = tr["bytes_per_launch"]
-                roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one 32768-frame time block)"
+                roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one time block)"
                 roofline["traffic_source"] = tr["source"]
         except (OSError, ValueError):
             pass
