@@ -1175,7 +1175,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   // Large graphs (every launch already fills the GPU) take longer time blocks: fewer launches and per-block joins
   // (cfg5shard 53.0 -> 50.9 ms); small graphs keep 32768 frames, where the un-overlapped tail of the last block matters.
   uint32_t tb = r->time_block;
-  if (!getenv("PB200_TIME_BLOCK") && r->h_voices.size() >= 2048) tb *= 2;
+  if (!getenv("PB200_TIME_BLOCK") && (r->h_voices.size() >= 2048 || r->n_gran_rows > 0)) tb *= 2;  // granular: cfg4 48 -> 36 ms
   std::vector<uint64_t> bounds;
   std::vector<uint32_t> begin;
   uint32_t n_blocks = 0, max_chunks = 1;
