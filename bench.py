@@ -212,7 +212,32 @@ def cpu_baseline(name, seconds_budget=25.0):
     dt = time.perf_counter() - t0
     p.close()
     return {"value": v * frames / dt, "unit": "voice-samples/s", "cores": 1, "kind": "port", "sample": sample + ", once",
-            "seconds": dt}
+            "seconds": dt}, out
+
+
+# parity bars of tests/ (DESIGN.md §2): max |gpu - oracle| per workload; feedback effects are judged on the rms floor
+PARITY_BARS = {"cfg2": 2.5e-7, "cfg3": 1e-5, "cfg4": 0.0, "sinc": 1e-5, "cfg5shard": 0.0, "cfg5": 1e-4}
+
+
+def check_parity(api, name, device_ordinal, ref):
+    """Renders the scene the oracle just rendered (the cpu_baseline sample: the FULL workload for cfg2) on the GPU through
+    the same C-ABI and asserts the parity bar. Outside every timed region; the oracle is the checker, not the product."""
+    from phonic_b200.player import Player
+    p = Player(api, SR, device_ordinal=device_ordinal)
+    build_cpu_sample(p, name)
+    gpu = np.zeros_like(ref)
+    p.render_into(gpu)
+    p.close()
+    d = gpu.astype(np.float64) - ref
+    err = float(np.abs(d).max())
+    rms = float(np.sqrt(np.mean(d ** 2)))
+    rms_db = 20.0 * np.log10(max(rms, 1e-30))
+    bar = PARITY_BARS[name]
+    ok = err <= bar and (name != "cfg5" or rms_db < -90.0) and float(np.abs(ref).max()) > 1e-3
+    if not ok:
+        raise SystemExit(f"bench.py: PARITY FAILED on {name}: max|gpu-oracle| = {err:.3e} (bar {bar:g}), rms {rms_db:.1f} dBFS")
+    return {"parity_max_abs_err": err, "parity_rms_dbfs": rms_db, "parity_bar": bar,
+            "parity_scene": "the cpu_baseline sample rendered on both sides (cfg2: the full 256-voice, 480256-frame workload)"}
 
 
 def run_reference(args):
@@ -482,7 +507,8 @@ def main():
                         "ms_per_step": total_e2e_ms / K},
                 "gpu_launches": int(total_launches), "clocks": clk, "roofline": roofline}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.workload)
+            line["cpu_baseline"], ref_out = cpu_baseline(args.workload)
+            line.update(check_parity(api, args.workload, local_rank, ref_out))
         elif world > 1:
             line["cpu_baseline"] = None
         print(json.dumps(line))

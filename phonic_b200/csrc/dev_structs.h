@@ -199,6 +199,7 @@ struct GroupState {
   uint32_t dead;          // removed from the mixer (transient && exhausted)
   ExpSm vol, pan;         // generator-level AmplifiedSource / PannedSource (player.rs:1075-1081)
   uint64_t voice_frames;  // statistics: active voice-frames rendered
+  uint64_t dead_time;     // end of the mixer chunk in which the source was dropped (valid when dead)
 };
 
 enum EventKind : uint32_t {

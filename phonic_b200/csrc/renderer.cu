@@ -100,6 +100,21 @@ struct DevVec {  // grow-only device array backed by the pool
     if (v.empty()) return cudaSuccess;
     return cudaMemcpyAsync(v.data(), p, v.size() * sizeof(T), cudaMemcpyDeviceToHost, s);
   }
+  // grow keeping the first `keep` elements (device-to-device copy) and zeroing everything behind them
+  cudaError_t grow_preserve(size_t n, size_t keep, cudaStream_t s) {
+    if (n <= cap) return cudaSuccess;
+    void* np = nullptr;
+    size_t granted = 0;
+    cudaError_t e = DevicePool::get().alloc(&np, n * sizeof(T), &granted);
+    if (e != cudaSuccess) return e;
+    keep = std::min(keep, cap);
+    if ((e = cudaMemsetAsync((char*)np + keep * sizeof(T), 0, granted - keep * sizeof(T), s)) != cudaSuccess) return e;
+    if (p && keep && (e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    if (p) DevicePool::get().release(p, cls);
+    p = (T*)np; cls = granted; cap = granted / sizeof(T);
+    return cudaSuccess;
+  }
   void free() { if (p) DevicePool::get().release(p, cls); p = nullptr; cap = 0; cls = 0; }
 };
 
@@ -213,7 +228,8 @@ struct pb200_renderer {
   DevVec<GrainRec> d_grain_recs;
   DevVec<uint32_t> d_gran_counters, d_gran_vrec, d_gran_tiles;
   DevVec<float2> d_grain_storage;
-  DevVec<GrainCarry> d_grain_carry;
+  DevVec<GrainCarry> d_grain_carry[2];      // double buffer, each [n_rows][GRAIN_POOL]: rows keep their offset when samplers are added
+  size_t carry_rows = 0;                    // rows of the carry buffers that hold live state
   DevVec<float> d_grain_luts;
   DevVec<GroupParams> d_groups;
   DevVec<GroupState> d_gstate;
@@ -520,7 +536,7 @@ void pb200_destroy(pb200_renderer* r) {
   for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
   r->d_block_done.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
   r->d_gran_groups.free(); r->d_gran_states.free(); r->d_grain_recs.free(); r->d_gran_counters.free(); r->d_gran_vrec.free();
-  r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry.free(); r->d_grain_luts.free();
+  r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry[0].free(); r->d_grain_carry[1].free(); r->d_grain_luts.free();
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
   r->d_mixers.free(); r->d_mstate.free(); r->d_child_index.free(); r->d_source_index.free(); r->d_level_mixers.free();
   r->d_class_groups.free(); r->d_fx.free(); r->d_fx_events.free(); r->d_fx_state.free(); r->d_aux.free();
@@ -1278,11 +1294,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(r->d_gran_vrec.reserve((size_t)RING * n_rows * gran_vrec_cap));
     CUDA_TRY(r->d_gran_tiles.reserve((size_t)RING * n_rows * n_tiles * 2));
     CUDA_TRY(r->d_grain_storage.reserve((size_t)RING * gran_storage_cap));
-    {
-      const GrainCarry* before = r->d_grain_carry.p;
-      CUDA_TRY(r->d_grain_carry.reserve((size_t)2 * n_rows * GRAIN_POOL));
-      if (r->d_grain_carry.p != before) CUDA_TRY(cudaMemsetAsync(r->d_grain_carry.p, 0, r->d_grain_carry.cap * sizeof(GrainCarry), r->sv));
-    }
+    // carry of grains in flight: rows of samplers that were already playing keep their state when rows are added
+    for (int h = 0; h < 2; ++h) CUDA_TRY(r->d_grain_carry[h].grow_preserve((size_t)n_rows * GRAIN_POOL, r->carry_rows * GRAIN_POOL, r->sv));
+    r->carry_rows = n_rows;
     CUDA_TRY(cudaMemsetAsync(r->d_gran_counters.p, 0, 2 * (size_t)std::max<uint32_t>(RING, n_blocks) * sizeof(uint32_t), r->sv));
   }
 
@@ -1416,8 +1430,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       ga.window_luts = r->d_grain_luts.p;
       ga.storage = r->d_grain_storage.p + (size_t)slot * gran_storage_cap;
       ga.storage_cap = (uint32_t)gran_storage_cap;
-      ga.carry_in = r->d_grain_carry.p + (size_t)(r->gran_parity ^ 1u) * n_rows * GRAIN_POOL;
-      ga.carry_out = r->d_grain_carry.p + (size_t)r->gran_parity * n_rows * GRAIN_POOL;
+      ga.carry_in = r->d_grain_carry[r->gran_parity ^ 1u].p;
+      ga.carry_out = r->d_grain_carry[r->gran_parity].p;
       r->gran_parity ^= 1u;
       grain_kernel<<<(gran_rec_cap + 127) / 128, 128, 0, r->sr_>>>(ga);
       ++launches;
@@ -1557,8 +1571,34 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     for (auto& g : gs) vf += g.voice_frames;
     r->stats.voice_frames = vf - r->voice_frames_total;
     r->voice_frames_total = vf;
+    // WavStream stops at the first block whose MixedSource::write returns 0 (wav.rs:231-234): the main mixer has no
+    // playing source, effect, sub-mixer or pending event left (mixed.rs:664-670). Sources are dropped at the end of
+    // the block they finished in; an event is popped by the chunk that starts at its time.
+    uint64_t written = frames;
+    if (r->fxs.empty() && r->mixers.size() == 1) {
+      bool all_dead = true;
+      uint64_t fin = p0;
+      for (size_t gi = 0; gi < gs.size(); ++gi) {
+        if (!gs[gi].dead) { all_dead = false; break; }
+        fin = std::max(fin, (gs[gi].dead_time + bf - 1) / bf * bf);
+      }
+      if (all_dead) {
+        for (auto& g : r->groups)
+          for (auto& e : g.events)
+            if (!(e.ev.flags & 1u)) fin = std::max(fin, (e.ev.time / bf + 1) * bf);
+        if (fin <= p1) {
+          r->finished = true;
+          written = fin - p0;
+          if (written < frames) {
+            if (out_host) std::memset(out_host + written * 2, 0, (frames - written) * 2 * sizeof(float));
+            if (out_dev) { CUDA_TRY(cudaMemsetAsync(out_dev + written * 2, 0, (frames - written) * 2 * sizeof(float), r->sm)); CUDA_TRY(cudaStreamSynchronize(r->sm)); }
+          }
+        }
+      }
+    }
+    if (r->finished) r->position = p0 + written;  // WavStream::playback_pos stops with the stream
+    if (frames_written) *frames_written = written;
   }
-  if (frames_written) *frames_written = frames;
   return PB200_OK;
 }
 

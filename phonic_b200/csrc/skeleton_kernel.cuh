@@ -480,7 +480,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
                 s_gs.active_voices = s_cnt[j];
                 if (s_gs.stopping && s_cnt[j] == 0) s_gs.stopped = 1;
               }
-              if (gp.transient && s_gs.stopped) s_gs.dead = 1;
+              if (gp.transient && s_gs.stopped && !s_gs.dead) { s_gs.dead = 1; s_gs.dead_time = bound(k + j + 1); }
             }
             gflags[k + j - cb] = writes ? 1 : 0;
           }
@@ -658,7 +658,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
       if (is_sampler) exhausted = s_gs.stopped != 0;
       else { if (tid == 0) s_count = v.finished; __syncthreads(); exhausted = s_count != 0; __syncthreads(); }
       if (gp.transient && exhausted) {
-        if (tid == 0) s_gs.dead = 1;
+        if (tid == 0) { s_gs.dead = 1; s_gs.dead_time = c1; }
         __syncthreads();
         break;
       } else if (written == 0) {

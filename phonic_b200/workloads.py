@@ -183,6 +183,20 @@ def build_cfg1(player: Player, buffer: np.ndarray, buffer_rate: int):
     return h
 
 
+def build_cfg1_asset(player: Player, wav_path: str, repeat_forever: bool = False):
+    """cfg1 on a real asset (BASELINE configs[0]): the WAV file decoded by the implementation's own reader
+    (AudioFileBuffer::from_file, src/source/file/buffer.rs:64-119), default FilePlaybackOptions (cubic resampling to the
+    player's output rate), FilterEffect LP 1 kHz / Q 0.707 + ReverbEffect(0.6, 0.35) on the main mixer."""
+    bid, info = player.upload_wav(wav_path)
+    o = FilePlaybackOptions()
+    if repeat_forever:
+        o.repeat_forever()
+    h = player.play_file_source(bid, o)
+    player.add_effect(FilterEffect(0, 1000.0, 0.707))
+    player.add_effect(ReverbEffect(0.6, 0.35))
+    return h, info
+
+
 def build_subtrees(player: Player, n_mixers: int, voices_per_mixer: int, spec: VoiceBankSpec, effects: str = "none",
                    time_scale: float = 1.0, seed_base: int = 0, buffer=None, fast: bool = False):
     """cfg3 / cfg5 shape: `n_mixers` sub-mixers of the main mixer, each with a cfg2-style bank.
@@ -211,13 +225,17 @@ def add_main_bus_sends(player: Player):
     player.add_effect(ReverbEffect(0.6, 0.35))
 
 
-def build_cfg4(player: Player, voices: int = 160, voices_per_sampler: int = 8, time_scale: float = 1.0, seed: int = 4):
+def build_cfg4(player: Player, voices: int = 160, voices_per_sampler: int = 8, time_scale: float = 1.0, seed: int = 4,
+               wav_path: str | None = None):
     """cfg4: granular synthesis, 16k grains/s: a pad-ambient.wav-shaped mono buffer (362 835 frames
     @ 48 kHz, loop 286 619..362 834), `voices` voices x density 100 Hz x size 100 ms, Hann, Forward, step 1.0, no
     randomisation. Notes as in cfg2 (on in [0, 2 s), off in [6, 8 s)), AHDSR (10 ms, 0, 500 ms, 0.75, 1 s)."""
-    frames = 362835
-    buf = synth_buffer(frames, 48000, seed=seed)
-    bid = player.upload_buffer(buf, 48000, loop_range=(286619, 362834))
+    if wav_path is not None:  # the real asset (stereo float32 + smpl loop): mixed down on device like sampler.rs:908-952
+        bid, _ = player.upload_wav(wav_path)
+    else:
+        frames = 362835
+        buf = synth_buffer(frames, 48000, seed=seed)
+        bid = player.upload_buffer(buf, 48000, loop_range=(286619, 362834))
     rng = np.random.default_rng(seed + 1)
     ahdsr = AhdsrParameters(attack=0.01, hold=0.0, decay=0.5, sustain=0.75, release=1.0)
     gran = GranularParameters(window=0, size=100.0, density=100.0, position=0.1, step=1.0)

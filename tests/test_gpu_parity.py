@@ -213,3 +213,60 @@ def test_full_size_cfg2_properties(cuda_api):
     # every voice is idle again
     for h in hs:
         assert all(v[3] == 0 for v in h.voice_states())
+
+
+def test_one_shot_scene_ends_the_stream(cuda_api, oracle_api, tmp_path):
+    """WavStream stops at the first block whose main-mixer write returns 0 (wav.rs:231-234, mixed.rs:664-670): a one-shot
+    file on an otherwise empty main mixer yields a shorter `frames_written` / WAV file, identical to the oracle's;
+    a pending event keeps the stream alive until the block after it is due."""
+    from phonic_b200.player import FilePlaybackOptions
+    for late_event in (None, 30000):
+        res = []
+        for name, api in (("gpu", cuda_api), ("ref", oracle_api)):
+            p = Player(api, SR)
+            b = p.upload_buffer(np.linspace(-0.5, 0.5, 9000, dtype=np.float32), 44100)
+            h = p.play_file_source(b, FilePlaybackOptions(repeat=0))
+            if late_event:
+                h.set_volume(0.5, late_event)
+            out = np.full((40 * 1024, 2), 3.0, np.float32)
+            w1 = p.render_into(out[:8 * 1024])
+            w2 = p.render_into(out[8 * 1024:])
+            w3 = p.render_into(out[:1024].copy())
+            path = str(tmp_path / f"{name}_{late_event}.wav")
+            p2 = Player(api, SR)
+            b2 = p2.upload_buffer(np.linspace(-0.5, 0.5, 9000, dtype=np.float32), 44100)
+            p2.play_file_source(b2, FilePlaybackOptions(repeat=0))
+            wf = p2.render_to_wav(path, 1.0)
+            res.append((w1, w2, w3, p.output_sample_frame_position(), out.copy(), wf, open(path, "rb").read()))
+        g, o = res
+        assert g[:4] == o[:4], (g[:4], o[:4])
+        assert np.array_equal(g[4], o[4])
+        assert g[5] == o[5] and g[6] == o[6]
+        assert 0 < g[5] < 47 * 1024
+
+
+def test_adding_a_granular_sampler_between_render_calls_keeps_grains_in_flight(cuda_api, oracle_api):
+    """Grains of an already playing granular sampler continue from their carry when another sampler (more carry rows)
+    is added between two render calls."""
+    from phonic_b200.player import AhdsrParameters, GeneratorPlaybackOptions, GranularParameters
+    outs = []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, SR)
+        buf = p.upload_buffer(W_synth(60000), 48000)
+        gran = GranularParameters(window=0, size=120.0, density=40.0, position=0.2, step=0.5)
+        ahdsr = AhdsrParameters(attack=0.01, hold=0.0, decay=0.2, sustain=0.8, release=0.3)
+        g1 = p.add_generator(buf, GeneratorPlaybackOptions(voices=3), ahdsr, granular=gran)
+        g1.note_on(60, volume=0.5, panning=-0.2, sample_time=100)
+        g1.note_on(67, volume=0.4, panning=0.3, sample_time=3000)
+        a = p.render(9 * 1024)
+        g2 = p.add_generator(buf, GeneratorPlaybackOptions(voices=2), ahdsr, granular=gran)
+        g2.note_on(55, volume=0.5, sample_time=10 * 1024)
+        b = p.render(20 * 1024)
+        outs.append(np.concatenate([a, b]))
+    assert np.abs(outs[1][9 * 1024:]).max() > 0.01
+    assert np.array_equal(outs[0], outs[1])
+
+
+def W_synth(frames):
+    from phonic_b200 import workloads as W
+    return W.synth_buffer(frames, 48000, seed=77)
