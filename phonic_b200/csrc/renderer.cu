@@ -250,6 +250,11 @@ struct pb200_renderer {
   DevVec<uint16_t> d_seg_first, d_seg_count, d_gseg_first, d_gseg_count;
   DevVec<TileRec> d_recs;
   DevVec<uint32_t> d_block_done;
+  // exact phase-jump tables (phase_table.cuh): one per steady resampling ratio seen so far, built on the device
+  std::map<uint32_t, uint32_t> phase_off;   // f32 bits of the ratio -> word offset of its table
+  DevVec<uint32_t> d_phase_tabs;
+  DevVec<uint2> d_phase_dir, d_phase_new;
+  size_t phase_words = 0;
   cudaStream_t sr_ = nullptr;  // replay stream
   DevVec<uint8_t> d_group_flags, d_mixer_flags;
   DevVec<ExpSm> d_master;
@@ -534,7 +539,7 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sr_) cudaStreamSynchronize(r->sr_);
   if (r->sm) cudaStreamSynchronize(r->sm);
   for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
-  r->d_block_done.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
+  r->d_block_done.free(); r->d_phase_tabs.free(); r->d_phase_dir.free(); r->d_phase_new.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
   r->d_gran_groups.free(); r->d_gran_states.free(); r->d_grain_recs.free(); r->d_gran_counters.free(); r->d_gran_vrec.free();
   r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry[0].free(); r->d_grain_carry[1].free(); r->d_grain_luts.free();
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
@@ -985,6 +990,61 @@ struct Compiled {
   std::vector<uint32_t> level_offsets, class_offsets;
 };
 
+// Jump tables for every steady ratio the graph can reach: the speeds of playing voices and of every pending note-on /
+// speed event (FileSourceImpl::update_speed's rate arithmetic, file/common.rs:165). Ratios in the middle of a glide are
+// not foreseen and take the literal loop. New tables are appended and built by one kernel launch on `s`.
+int update_phase_tables(pb200_renderer* r, cudaStream_t s) {
+  static const bool off = getenv("PB200_NO_PHASE_TABLES") != nullptr;
+  if (off) return PB200_OK;
+  const uint32_t sr = r->cfg.sample_rate;
+  std::vector<uint2> fresh;
+  size_t words = r->phase_words;
+  uint64_t last_key = ~0ull;
+  auto add = [&](double speed, uint32_t in_rate) {
+    uint64_t key;
+    std::memcpy(&key, &speed, 8);
+    key ^= (uint64_t)in_rate << 1;
+    if (key == last_key) return;  // runs of equal speeds are common
+    last_key = key;
+    if (!(speed > 0.0) || !std::isfinite(speed)) return;
+    const uint32_t rate = f64_as_u32_h((double)sr / speed);
+    if (rate == 0) return;
+    const float ratio = (float)((double)in_rate / (double)rate);
+    uint32_t bits;
+    std::memcpy(&bits, &ratio, 4);
+    if (r->phase_off.count(bits) || r->phase_off.size() >= 8192) return;
+    const PhaseGeom g = phase_geom(ratio);
+    if (g.mode == PT_LITERAL) return;
+    r->phase_off[bits] = (uint32_t)words;
+    fresh.push_back(make_uint2(bits, (uint32_t)words));
+    words += phase_table_words(g);
+  };
+  for (size_t gi = 0; gi < r->groups.size(); ++gi) {
+    const HostGroup& g = r->groups[gi];
+    if (r->h_gstate[gi].dead) continue;
+    const uint32_t in_rate = r->buffers[g.gp.buffer].dev.sample_rate;
+    for (uint32_t vi = g.gp.first_voice; vi < g.gp.first_voice + g.gp.n_voices; ++vi) {
+      if (r->h_voices[vi].hq) continue;
+      add(r->h_voices[vi].current_speed, in_rate);
+      add(r->h_voices[vi].target_speed, in_rate);
+    }
+    for (const HostEvent& e : g.events)
+      if (e.ev.kind == EVK_NOTE_ON || e.ev.kind == EVK_NOTE_SPEED || e.ev.kind == EVK_SET_SPEED) add(e.ev.speed, in_rate);
+  }
+  if (!fresh.empty()) {
+    if (words >= 0xFFFFFFF0ull) return fail(r, PB200_ERR_UNSUPPORTED, "phase tables exceed 16 GiB");
+    CUDA_TRY(r->d_phase_tabs.grow_preserve(words, r->phase_words, s));
+    r->phase_words = words;
+    CUDA_TRY(r->d_phase_new.upload(fresh, s));
+    phase_table_kernel<<<(uint32_t)fresh.size(), 256, 0, s>>>(r->d_phase_tabs.p, r->d_phase_new.p);
+    std::vector<uint2> dir;
+    dir.reserve(r->phase_off.size());
+    for (auto& kv : r->phase_off) dir.push_back(make_uint2(kv.first, kv.second));  // std::map: sorted by the ratio bits
+    CUDA_TRY(r->d_phase_dir.upload(dir, s));
+  }
+  return PB200_OK;
+}
+
 int upload_graph(pb200_renderer* r, Compiled& c) {
   // drop consumed events, then flatten per-group / per-effect event lists (stable by time)
   std::vector<DevEvent> events;
@@ -1112,6 +1172,7 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
     r->d_aux.p = np; r->d_aux.cap = granted / sizeof(double); r->d_aux.cls = granted;
   }
   r->d_aux_used = r->aux_doubles;
+  if (int e = update_phase_tables(r, s)) return e;
   CUDA_TRY(cudaStreamSynchronize(s));
   r->dev_n_gran_rows = r->n_gran_rows;
   r->dev_n_voices = r->h_voices.size(); r->dev_n_groups = r->h_gstate.size(); r->dev_n_mixers = r->h_mstate.size();
@@ -1209,6 +1270,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
 
   CUDA_TRY(cudaFuncSetAttribute(mix_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_WORK_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REPLAY_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(skeleton_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (TAB_SLOT_WORDS * 4 + 12) + 16));
   const uint32_t n_tiles = tb / TILE;
   const uint32_t seg_cap = n_tiles + max_chunks + 8;
   if (seg_cap >= 65535) return fail(r, PB200_ERR_UNSUPPORTED, "too many chunk boundaries in one time block");
@@ -1320,8 +1382,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   // PB200_SKEL_PROF=<file>: per-voice cycle counters of the skeleton pass (debug aid)
   unsigned long long* prof_buf = nullptr;
   if (getenv("PB200_SKEL_PROF")) {
-    CUDA_TRY(cudaMalloc((void**)&prof_buf, nvoices * 4 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(prof_buf, 0, nvoices * 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc((void**)&prof_buf, nvoices * 12 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(prof_buf, 0, nvoices * 12 * sizeof(unsigned long long)));
   }
 
   unsigned long long* fx_prof = nullptr;
@@ -1371,6 +1433,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       va.gran.block_frames = blen;  // grains stop at the end of what this block really renders: their carry is taken there
       CUDA_TRY(cudaMemsetAsync(va.gran.tile_range, 0xFF, (size_t)n_rows * n_tiles * 2 * sizeof(uint32_t), r->sv));
     }
+    va.phase_tabs = r->d_phase_tabs.p; va.phase_dir = r->d_phase_dir.p; va.n_phase = (uint32_t)r->phase_off.size();
     va.prof = prof_buf;
     va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
     SkeletonLoop sl;
@@ -1393,7 +1456,12 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       static const int force_wpv = getenv("PB200_SKEL_WPV") ? atoi(getenv("PB200_SKEL_WPV")) : -1;
       const size_t wpv_resident = (size_t)sm_count_all * std::max<size_t>(1, 65536 / (224 * 32 * (size_t)sc.vpad));
       const bool wpv = force_wpv >= 0 ? force_wpv != 0 : (persistent || sc.groups.size() <= wpv_resident);
-      if (sc.vpad <= 8 && wpv) skeleton_kernel<256, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
+      sl.tab_slots = 0;
+      if (sc.vpad <= 8 && wpv) {  // the voice's jump table in its warp's shared-memory slot
+        sl.tab_slots = sc.vpad;
+        const size_t smem = (size_t)sc.vpad * (TAB_SLOT_WORDS * 4 + 8 + 4) + 16;
+        skeleton_kernel<256, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, smem, r->sv>>>(va, sl);
+      }
       else if (sc.vpad <= 32 && wpv) skeleton_kernel<1024, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
       else if (sc.threads <= 256) skeleton_kernel<256, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
       else skeleton_kernel<1024, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
@@ -1503,12 +1571,16 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
             h[0] / 1e6, h[1] / 1e6, h[2] / 1e6, h[3] / 1e6, h[4] / 1e6, h[5] / 1e6, h[6] / 1e6);
   }
   if (prof_buf) {
-    std::vector<unsigned long long> h(nvoices * 4);
+    std::vector<unsigned long long> h(nvoices * 12);
     cudaMemcpy(h.data(), prof_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(prof_buf);
     if (FILE* f = fopen(getenv("PB200_SKEL_PROF"), "w")) {
-      fprintf(f, "voice,wait_before_run,wait_after_voices,wait_after_bookkeeping,free_run_work\n");
-      for (size_t i = 0; i < nvoices; ++i) fprintf(f, "%zu,%llu,%llu,%llu,%llu\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      fprintf(f, "voice,wait_before_run,wait_after_voices,wait_after_bookkeeping,free_run_work,simple_calls,simple_cycles,jumped_tiles,literal_frames,general_frames,general_cycles,unused,block_cycles\n");
+      for (size_t i = 0; i < nvoices; ++i) {
+        fprintf(f, "%zu", i);
+        for (int k = 0; k < 12; ++k) fprintf(f, ",%llu", h[12 * i + k]);
+        fprintf(f, "\n");
+      }
       fclose(f);
     }
   }

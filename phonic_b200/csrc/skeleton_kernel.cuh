@@ -11,6 +11,7 @@
 #pragma once
 #include "hq.cuh"
 #include "gran.cuh"
+#include "phase_table.cuh"
 
 namespace pb {
 
@@ -50,8 +51,12 @@ struct SkeletonArgs {
   const GranGroup* gran_groups;       // [n_groups] or nullptr when the graph has no granular sampler
   GranState* gran_states;             // [n_gran_rows]
   GranEmit gran;
+  // exact 64-frame phase jumps (phase_table.cuh): one table per steady ratio of the graph, directory sorted by ratio bits
+  const uint32_t* phase_tabs;
+  const uint2* phase_dir;             // (f32 bits of the ratio, word offset of its table)
+  uint32_t n_phase;
   unsigned long long* prof;           // PB200_SKEL_PROF: [n_voices][4] cycles waiting at the free run's three barriers + its own work
-  uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores, 2 = no simple calls
+  uint32_t debug_flags;  // timing experiments only (PB200_SKEL_DEBUG): 1 = no snapshot stores, 2 = no simple calls, 4 = no phase jumps
 };
 
 constexpr int VK_MAX_VOICES = 1024;
@@ -115,14 +120,142 @@ PB_DEV void sampler_voice_stop(VoiceState& v, const GroupParams& gp, uint64_t fr
 }
 
 
-// One simple call (voice.cuh "simple calls"): the whole call's phase / envelope recurrences in one go, with a
-// 32-byte TileRec stored at every tile boundary crossed instead of a full Segment.
-// UNI: lane-per-voice skeleton -- one instruction stream for every ratio / envelope state (phase_piece_uniform).
-template <int CC, bool UNI>
-PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const DevBuffer& buf, uint32_t n,
-                        uint32_t call_off, TileRec* __restrict__ my_recs, uint32_t base, uint32_t gen, const bool cyc = false) {
-  const long long cy0 = cyc ? CYC_T() : 0ll;
-  long long cy_loop = 0;
+// The jump table of `ratio`, or nullptr when the host did not foresee this ratio (a glide in progress): literal loop.
+PB_DEV const uint32_t* find_phase_tab(const SkeletonArgs& a, const float ratio) {
+  const uint32_t bits = (uint32_t)__float_as_int(ratio);
+  uint32_t lo = 0, hi = a.n_phase;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t k = a.phase_dir[mid].x;
+    if (k == bits) return a.phase_tabs + a.phase_dir[mid].y;
+    if (k < bits) lo = mid + 1; else hi = mid;
+  }
+  return nullptr;
+}
+
+// ---- a voice's jump table staged in shared memory (warp-per-voice skeleton) ------------------------------------------
+// The jump is a chain of three dependent table reads; from L2 that is ~1000 cycles per tile on a path where one thread
+// per voice works alone. The voice's warp therefore keeps the body of its current table in its own 16 KB slot of shared
+// memory, fetched with ONE bulk async copy (cp.async.bulk, completion on an mbarrier) whenever the ratio changes.
+constexpr uint32_t TAB_SLOT_WORDS = 4096;   // fits every table of ratio >= 1/8; larger ones are read from global memory
+struct TabSlot { uint32_t* words; uint64_t* mbar; uint32_t* parity; };
+
+PB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PB_DEV void tab_slot_init(const TabSlot& ts) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(ts.mbar)));
+  *ts.parity = 0u;
+}
+PB_DEV void tab_slot_fetch(const TabSlot& ts, const uint32_t* __restrict__ src, const uint32_t bytes) {
+  const uint32_t mbar = smem_u32(ts.mbar), dst = smem_u32(ts.words);
+  // earlier generic-proxy reads of the slot are ordered before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+  const uint32_t parity = *ts.parity;
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  }
+  *ts.parity = parity ^ 1u;
+}
+
+// Builds the tables of `dir[blockIdx.x]` (phase_table.cuh: analytic break points, every entry verified against the model).
+__global__ void __launch_bounds__(256) phase_table_kernel(uint32_t* __restrict__ tabs, const uint2* __restrict__ dir) {
+  __shared__ uint32_t scratch[PT_MAX_BP];
+  const uint2 d = dir[blockIdx.x];
+  const float ratio = __int_as_float((int)d.x);
+  uint32_t* tab = tabs + d.y;
+  const PhaseGeom g = phase_geom(ratio);
+  if (threadIdx.x == 0) phase_build_header(tab, ratio, g);
+  if (g.mode != PT_DOWN_TABLE && g.mode != PT_UP_TABLE) return;
+  phase_build_p1(g, scratch, threadIdx.x, blockDim.x);
+  __syncthreads();
+  phase_build_p2(tab, g, scratch, threadIdx.x, blockDim.x);
+  __syncthreads();
+  phase_build_p3(tab, g, threadIdx.x, blockDim.x);
+  __syncthreads();
+  phase_build_p4(tab, g, threadIdx.x, blockDim.x);
+}
+
+// ---- simple calls and super-calls --------------------------------------------------------------------------------
+// A simple call (voice.cuh "simple calls") advances only the phase recurrence and the envelope; the skeleton stores one
+// full Segment at its first frame and a 32-byte TileRec at every tile boundary it crosses. A voice that stays steady --
+// no event addressed to it, envelope in Sustain or far from its next threshold, input far from its loop end -- does not
+// notice the mixer's chunk boundaries at all (they come from OTHER sources' events, mixed.rs:686-693): the following
+// chunks are accepted into the open call ("super-call") without a new Segment, and whole tiles are advanced with one
+// exact jump of the phase recurrence (phase_table.cuh) + a closed-form envelope step, however the chunk boundaries
+// fall inside them. Frames of an unfinished tile stay pending until later chunks complete it or something ends the
+// steady span (then they are advanced literally and the call is closed).
+struct SuperCall {
+  uint32_t open;
+  uint32_t open_off;   // block-relative frame of the call's Segment
+  uint32_t adv_off;    // phase / envelope state is advanced up to here (tile aligned once past the first piece)
+  uint32_t end_off;    // chunks accepted up to here; end_off - adv_off frames are pending
+  uint32_t np;         // samples pushed since the call opened (folded into playback_pos / hidx when it closes)
+  uint32_t base;       // index of the call's Segment
+  uint32_t budget;     // frames from adv_off for which the voice provably stays steady
+  uint32_t le;         // end of the input range in samples (loop end / buffer end)
+  float s, p;          // sub_pos at adv_off, look-ahead push flag of the literal loop
+  bool first, env;
+  PhaseRef tab;
+};
+
+// per-frame increment of the current envelope stage's bare accumulate chain (see env_bare_steps)
+PB_DEV void env_increment(const VoiceState& v, const GroupParams& gp, float& d, bool& on_hold) {
+  const uint32_t stage = v.env_stage;
+  on_hold = false; d = 0.0f;
+  if (stage == ENV_ATTACK) d = gp.attack_rate;
+  else if (stage == ENV_HOLD) { d = -1.0f; on_hold = true; }
+  else if (stage == ENV_DECAY && v.env_out > gp.sustain_level) d = -gp.decay_rate;
+  else if (stage == ENV_RELEASE) d = -(v.env_release_out * gp.release_rate);
+}
+
+// The literal pieces and the envelope's stage machine are off the steady path: they live out of line (scalars in,
+// scalars out -- nothing of the voice state has its address taken) so that the tile loop stays small.
+struct PieceOut { float s, p, o; uint32_t np; };
+template <bool UNI>
+__device__ __noinline__ PieceOut phase_piece_nl(float s, float p, float o, const float d, const float ratio, const uint32_t span,
+                                                const bool first, const bool acc) {
+  const PhaseK pk = phase_consts(ratio);
+  PieceOut r;
+  if (UNI) r.np = phase_piece_uniform(s, p, pk, span, first, o, acc ? d : 0.0f);
+  else if (acc) r.np = phase_piece<true>(s, p, pk, span, first, o, d);
+  else r.np = phase_piece<false>(s, p, pk, span, first, o, 0.0f);
+  r.s = s; r.p = p; r.o = o;
+  return r;
+}
+struct EnvOut { float out, hold, target; uint32_t stage; };
+__device__ __noinline__ EnvOut env_chain_nl(const float out, const float hold, const float target, const float release_out,
+                                            const uint32_t stage, const GroupParams* __restrict__ gp, const uint32_t w) {
+  VoiceState t;
+  t.env_out = out; t.env_hold = hold; t.env_target = target; t.env_release_out = release_out; t.env_stage = (uint8_t)stage;
+  const GroupParams g = *gp;
+  env_chain(t, g, w);
+  EnvOut r;
+  r.out = t.env_out; r.hold = t.env_hold; r.target = t.env_target; r.stage = t.env_stage;
+  return r;
+}
+PB_DEV void env_chain_call(VoiceState& v, const GroupParams* gp, const uint32_t w) {
+  const EnvOut r = env_chain_nl(v.env_out, v.env_hold, v.env_target, v.env_release_out, v.env_stage, gp, w);
+  v.env_out = r.out; v.env_hold = r.hold; v.env_target = r.target; v.env_stage = (uint8_t)r.stage;
+}
+// the general per-frame path of a call (glides, ramps, loop ends): works on copies like the HighQuality state machine
+template <int CC>
+__device__ __noinline__ uint32_t voice_advance_nl(VoiceState* v, CallCtx* c, const GroupParams* __restrict__ gp, const DevBuffer* __restrict__ b,
+                                                  const uint32_t out_rate, const float comp, const uint32_t n) {
+  VoiceState vt = *v;
+  CallCtx ct = *c;
+  const GroupParams g = *gp;
+  const DevBuffer bb = *b;
+  const uint32_t w = voice_advance<CC>(vt, ct, g, bb, out_rate, comp, n);
+  *v = vt; *c = ct;
+  return w;
+}
+
+PB_DEV void sc_open(SuperCall& sc, VoiceState& v, CallCtx& cc, const GroupParams& gp, const DevBuffer& buf, const uint32_t CC,
+                    const uint32_t call_off, const uint32_t base, const PhaseRef& tab) {
   cc.call_left = cc.chunk_left;
   loop_range_samples(v, buf, cc.ls, cc.le);
   cc.new_call = false;
@@ -132,58 +265,115 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
     v.hidx[2] = (int32_t)v.playback_pos; v.hidx[1] = (int32_t)(v.playback_pos + CC); v.hidx[0] = (int32_t)(v.playback_pos + 2 * CC);
     v.playback_pos += 3 * CC;
   }
-  const float ratio = v.ratio;
-  const bool env = gp.has_env && cc.env_per_frame;
-  float s = v.sub_pos, p = 0.0f;
-  const PhaseK pk = phase_consts(ratio);  // the ratio is constant for the whole call
-  bool first = true;
-  uint32_t np = 0, off = call_off, remaining = n;
-  uint32_t piece = min(remaining, TILE - (off % TILE));
-  for (;;) {
-    bool fused = false;
-    if (UNI) {
-      float d = 0.0f, o = 0.0f;
-      bool on_hold = false;
-      if (env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE && env_bare_steps(v, gp, d, on_hold) >= piece) {
-        fused = true;
-        o = on_hold ? v.env_hold : v.env_out;
-      } else {
-        d = 0.0f;
-      }
-      np += phase_piece_uniform(s, p, pk, piece, first, o, d);
-      if (fused) { if (on_hold) v.env_hold = o; else v.env_out = o; }
-      else if (env) env_chain(v, gp, piece);
-      fused = true;  // this piece is done
-    } else if (env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE) {
+  sc.open = 1; sc.open_off = sc.adv_off = sc.end_off = call_off; sc.np = 0; sc.base = base; sc.budget = 0; sc.le = cc.le;
+  sc.s = v.sub_pos; sc.p = 0.0f; sc.first = true; sc.env = gp.has_env && cc.env_per_frame;
+  sc.tab = tab;
+}
+
+// Frames from adv_off for which nothing but the phase recurrence and a bare envelope chain can happen.
+PB_DEV uint32_t sc_steady_budget(const SuperCall& sc, const VoiceState& v, const GroupParams& gp, const uint32_t CC) {
+  uint32_t b = 0xFFFFFFFFu;
+  if (sc.env && v.env_stage != ENV_SUSTAIN) {  // Sustain: env_run returns the constant level until a note-off
+    if (v.env_stage == ENV_IDLE) return 0u;
+    float d;
+    bool on_hold;
+    b = env_bare_steps(v, gp, d, on_hold);
+  }
+  const uint32_t pos = v.playback_pos + sc.np * CC;
+  const uint32_t avail = sc.le > pos ? (sc.le - pos) / CC : 0u;
+  const uint32_t per_frame = v.ratio < 1.0f ? 1u : (uint32_t)v.ratio + 2u;
+  const uint32_t in_b = avail > 5u ? (avail - 5u) / per_frame : 0u;  // simple_call_ok: n * per_frame + 4 < avail
+  return min(b, in_b);
+}
+
+PB_DEV void sc_store_rec(const SuperCall& sc, const VoiceState& v, TileRec* __restrict__ my_recs, const uint32_t gen, const uint32_t CC,
+                         const uint32_t piece) {
+  uint4 lo, hi;
+  lo.x = v.playback_pos + sc.np * CC; lo.y = __float_as_uint(sc.s); lo.z = __float_as_uint(v.env_out); lo.w = __float_as_uint(v.env_hold);
+  hi.x = __float_as_uint(v.env_target); hi.y = ((uint32_t)v.env_stage << 16) | piece; hi.z = sc.base; hi.w = gen;
+  uint4* dst = reinterpret_cast<uint4*>(my_recs + sc.adv_off / TILE);
+  dst[0] = lo; dst[1] = hi;
+}
+
+// Advance the open call to `to_off`. !final: only whole tiles (the rest stays pending). UNI: lane-per-voice skeleton,
+// one instruction stream for every ratio class in the literal pieces (phase_piece_uniform).
+template <bool UNI>
+PB_DEV void sc_advance(SuperCall& sc, VoiceState& v, const GroupParams& gp, const GroupParams* __restrict__ gp_mem, TileRec* __restrict__ my_recs,
+                       const uint32_t gen, const uint32_t CC, const uint32_t to_off, const bool final, unsigned long long* __restrict__ stat) {
+  // steady tiles: one exact jump of the phase recurrence + a closed-form step of a bare envelope chain
+  while (sc.adv_off != sc.open_off && sc.adv_off + TILE <= to_off) {
+    const bool moving = sc.env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE;
+    if (moving && sc.budget < TILE) break;
+    float s2 = sc.s;
+    uint32_t w = 0;
+    if (!phase_jump(sc.tab, s2, w)) break;
+    sc_store_rec(sc, v, my_recs, gen, CC, TILE);
+    sc.s = s2; sc.np += w;
+    if (moving) {
       float d;
       bool on_hold;
-      if (env_bare_steps(v, gp, d, on_hold) >= piece) {  // the stage cannot end inside this piece: ride along
-        float o = on_hold ? v.env_hold : v.env_out;
-        const long long c0 = cyc ? CYC_T() : 0ll;
-        np += phase_piece<true>(s, p, pk, piece, first, o, d);
-        if (cyc) cy_loop += CYC_T() - c0;
-        if (on_hold) v.env_hold = o; else v.env_out = o;
-        fused = true;
+      env_increment(v, gp, d, on_hold);
+      float o = on_hold ? v.env_hold : v.env_out;
+      if (!accum_jump(o, d, TILE)) {
+#pragma unroll 8
+        for (uint32_t j = 0; j < TILE; ++j) o += d;
       }
+      if (on_hold) v.env_hold = o; else v.env_out = o;
     }
-    if (!fused) {
-      float o_unused = 0.0f;
-      const long long c0 = cyc ? CYC_T() : 0ll;
-      np += phase_piece<false>(s, p, pk, piece, first, o_unused, 0.0f);
-      if (cyc) cy_loop += CYC_T() - c0;
-      if (env) env_chain(v, gp, piece);
-    }
-    first = false;
-    off += piece; remaining -= piece;
-    if (remaining == 0) break;
-    piece = min(remaining, TILE);
-    uint4 lo, hi;
-    lo.x = v.playback_pos + np * CC; lo.y = __float_as_uint(s); lo.z = __float_as_uint(v.env_out); lo.w = __float_as_uint(v.env_hold);
-    hi.x = __float_as_uint(v.env_target); hi.y = ((uint32_t)v.env_stage << 16) | piece; hi.z = base; hi.w = gen;
-    uint4* dst = reinterpret_cast<uint4*>(my_recs + off / TILE);
-    dst[0] = lo; dst[1] = hi;
+    if (stat) stat[0] += 1;
+    sc.first = true;  // the literal loop's look-ahead push flag is stale after a jump
+    sc.adv_off += TILE;
+    sc.budget = sc.budget > TILE ? sc.budget - TILE : 0u;
   }
-  v.sub_pos = s;
+  while (sc.adv_off < to_off) {
+    const uint32_t tile_end = (sc.adv_off / TILE + 1u) * TILE;
+    const uint32_t piece_end = min(tile_end, to_off);
+    // the first piece belongs to the Segment (its length is stored there): it is never left pending
+    if (piece_end < tile_end && !final && sc.adv_off != sc.open_off) break;
+    const uint32_t piece = piece_end - sc.adv_off;
+    if (sc.adv_off != sc.open_off) sc_store_rec(sc, v, my_recs, gen, CC, piece);  // a tile that opens inside the call
+    const bool env_moving = sc.env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE;
+    bool bare = false, on_hold = false;
+    float d = 0.0f;
+    if (env_moving) {
+      if (sc.budget >= piece) { bare = true; env_increment(v, gp, d, on_hold); }
+      else bare = env_bare_steps(v, gp, d, on_hold) >= piece;
+    }
+    bool jumped = false;
+    if (piece == TILE) {
+      uint32_t w = 0;
+      jumped = phase_jump(sc.tab, sc.s, w);
+      sc.np += w;
+    }
+    if (jumped) {
+      if (bare) {
+        float o = on_hold ? v.env_hold : v.env_out;
+        if (!accum_jump(o, d, TILE)) {
+#pragma unroll 8
+          for (uint32_t j = 0; j < TILE; ++j) o += d;
+        }
+        if (on_hold) v.env_hold = o; else v.env_out = o;
+      } else if (env_moving) {
+        env_chain_call(v, gp_mem, piece);
+      }
+    } else {
+      const float o_in = bare ? (on_hold ? v.env_hold : v.env_out) : 0.0f;
+      const PieceOut r = phase_piece_nl<UNI>(sc.s, sc.p, o_in, d, v.ratio, piece, sc.first, bare);
+      sc.s = r.s; sc.p = r.p; sc.np += r.np;
+      if (bare) { if (on_hold) v.env_hold = r.o; else v.env_out = r.o; }
+      else if (env_moving) env_chain_call(v, gp_mem, piece);
+    }
+    if (stat) { if (jumped) stat[0] += 1; else stat[1] += piece; }
+    sc.first = jumped;  // after a jump the look-ahead push flag of the literal loop is stale
+    sc.adv_off = piece_end;
+    sc.budget = sc.budget > piece ? sc.budget - piece : 0u;
+  }
+}
+
+// Fold the call's pushes into the voice state (everything the call consumed is consecutive input).
+PB_DEV void sc_close(SuperCall& sc, VoiceState& v, const uint32_t CC) {
+  v.sub_pos = sc.s;
+  const uint32_t np = sc.np;
   if (np >= 4) {
     v.playback_pos += np * CC;
     v.hidx[0] = (int32_t)(v.playback_pos - CC); v.hidx[1] = (int32_t)(v.playback_pos - 2 * CC);
@@ -194,19 +384,13 @@ PB_DEV void simple_call(VoiceState& v, CallCtx& cc, const GroupParams& gp, const
       v.playback_pos += CC;
     }
   }
-  cc.produced_in_call = n;
-  cc.call_left = 0;
-  cc.chunk_left = 0;
-  after_process_call(v, cc);
-#ifdef PB200_CYC
-  if (cyc) { g_cyc[0] += CYC_T() - cy0; g_cyc[1] += cy_loop; g_cyc[2] += 1; g_cyc[3] += n; }
-#endif
+  sc.open = 0;
 }
 
 // WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
 // control flow (the skeleton is a latency-bound chain of dependent f32 ops per voice, not a SIMT workload).
 template <int MAXT, bool WPV>
-PB_DEV void skeleton_block(const SkeletonArgs& a) {
+PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
   __shared__ VoiceHeader s_head[WPV ? 32 : MAXT];
   __shared__ GroupState s_gs;
   __shared__ uint32_t s_count;
@@ -214,6 +398,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   __shared__ uint32_t s_cnt[MAX_RUN];      // voices still holding a note after each chunk of a free run
   unsigned long long prof_free = 0;
   unsigned long long prof_q[4] = {0, 0, 0, 0};
+  unsigned long long prof_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // simple calls, their cycles, jumped tiles, literal frames, general frames, their cycles, -, block cycles
+  const long long prof_b0 = a.prof ? clock64() : 0;
 
   const long long cyc_block0 = CYC_T();
   const uint32_t g = a.group_list[blockIdx.x];
@@ -289,15 +475,42 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   uint8_t* gflags = a.group_flags + (size_t)g * a.max_chunks;
   uint64_t my_frames = 0;
 
+  // jump table of the voice's current ratio, looked up when the ratio changes
+  uint32_t tab_bits = 0;
+  PhaseRef tab_ref = phase_ref(nullptr, nullptr);
+  auto tab_for = [&](const float ratio) -> const PhaseRef& {
+    const uint32_t bits = (uint32_t)__float_as_int(ratio);
+    if (bits != tab_bits) {
+      tab_bits = bits;
+      const uint32_t* t = (a.debug_flags & 4u) ? nullptr : find_phase_tab(a, ratio);
+      const uint32_t* body = nullptr;
+      if (WPV && t != nullptr && tslot.words != nullptr && (t[PT_H_MODE] == PT_DOWN_TABLE || t[PT_H_MODE] == PT_UP_TABLE)) {
+        const uint32_t words = t[PT_H_WORDS] - PT_HEADER;
+        if (words <= TAB_SLOT_WORDS) { tab_slot_fetch(tslot, t + PT_HEADER, words * 4u); body = tslot.words; }
+      }
+      tab_ref = phase_ref(t, body);
+    }
+    return tab_ref;
+  };
+  SuperCall sc;   // the voice's open simple call, if any (see "simple calls and super-calls")
+  sc.open = 0;
+  // advance the pending frames of the open call literally and close it: the voice state is exact at sc.end_off again
+  const uint32_t CCr = buf.channels;
+  auto sc_finish = [&]() {
+    if (!sc.open) return;
+    sc_advance<!WPV>(sc, v, gp, a.groups + g, my_recs, a.gen, CCr, sc.end_off, true, a.prof ? prof_s + 2 : nullptr);
+    sc_close(sc, v, CCr);
+  };
   // One Source::write call of this thread's voice (already opened by voice_begin_call): emits the call's
   // Segment / TileRec checkpoints and advances the control state. Returns the frames written.
-  auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t) __attribute__((always_inline)) -> uint32_t {
+  auto run_call = [&](CallCtx& cc, const uint32_t n, const uint32_t call_off, const uint64_t t, const bool allow_lazy) __attribute__((always_inline)) -> uint32_t {
     uint32_t written_frames = 0;
     bool simple = false;
     const bool cyc_v = CYC_ON(gp.first_voice + tid);
     const long long cyr0 = cyc_v ? CYC_T() : 0ll;
     if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq && !is_gran)
       simple = buf.channels == 2 ? simple_call_ok<2>(v, cc, buf, n) : simple_call_ok<1>(v, cc, buf, n);
+    const long long prc0 = a.prof ? clock64() : 0;
     if (simple) {
       const uint32_t tile = call_off / TILE;
       if (!(a.debug_flags & 1u)) {
@@ -309,8 +522,18 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         cur_tile = tile; cur_first = n_segs; cur_cnt = 0;
       }
       cur_cnt++;
-      if (buf.channels == 2) simple_call<2, !WPV>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen, CYC_ON(gp.first_voice + tid));
-      else simple_call<1, !WPV>(v, cc, gp, buf, n, call_off, my_recs, n_segs, a.gen, CYC_ON(gp.first_voice + tid));
+      // open the call; inside a free run it may stay open as a super-call (whole tiles advanced, the rest pending)
+      const PhaseRef& tr = tab_for(v.ratio);
+      unsigned long long* st = a.prof ? prof_s + 2 : nullptr;
+      const uint32_t end_off = call_off + n;
+      sc_open(sc, v, cc, gp, buf, CCr, call_off, n_segs, tr);
+      sc.end_off = end_off;
+      bool lazy = false;
+      if (allow_lazy) { sc.budget = sc_steady_budget(sc, v, gp, CCr); lazy = sc.budget >= (end_off + TILE - 1u) / TILE * TILE - call_off; }
+      sc_advance<!WPV>(sc, v, gp, a.groups + g, my_recs, a.gen, CCr, end_off, !lazy, st);
+      if (!lazy || (sc.adv_off % TILE) != 0u) sc_close(sc, v, CCr);
+      cc.produced_in_call = n; cc.call_left = 0; cc.chunk_left = 0;
+      if (!sc.open) after_process_call(v, cc);  // (an open super-call cannot have reached its loop end: sc_steady_budget)
       n_segs++;
       written_frames = n;
     } else {
@@ -335,7 +558,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           gran_advance(gsp, a.gran_groups + g, a.gran, gran_row, t + (off - call_off), off, seg_len);
           w = seg_len;
           cc.chunk_left -= w; cc.hq_off += w;
-          if (gp.has_env && cc.env_per_frame) env_chain(v, gp, w);
+          if (gp.has_env && cc.env_per_frame) env_chain_call(v, a.groups + g, w);
         } else if (is_hq) {
           // the out-of-line HighQuality state machine works on copies: taking the address of `v` / `cc` themselves
           // would move the hot cubic path's voice state from registers to local memory
@@ -344,12 +567,21 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
           w = buf.channels == 2 ? hq_advance<2>(vt, ct, hqp, hq_em, buf, comp, seg_len) : hq_advance<1>(vt, ct, hqp, hq_em, buf, comp, seg_len);
           v = vt; cc = ct;
         }
-        else if (buf.channels == 2) w = voice_advance<2>(v, cc, gp, buf, out_rate, comp, seg_len);
-        else w = voice_advance<1>(v, cc, gp, buf, out_rate, comp, seg_len);
+        else {  // out of line, on copies (taking the address of `v` / `cc` themselves would move them to local memory)
+          VoiceState vt = v;
+          CallCtx ct = cc;
+          w = buf.channels == 2 ? voice_advance_nl<2>(&vt, &ct, a.groups + g, a.buffers + gp.buffer, out_rate, comp, seg_len)
+                                : voice_advance_nl<1>(&vt, &ct, a.groups + g, a.buffers + gp.buffer, out_rate, comp, seg_len);
+          v = vt; cc = ct;
+        }
         written_frames += w;
         off += w; remaining -= w;
         if (w < seg_len) break;
       }
+    }
+    if (a.prof) {
+      const unsigned long long dt = (unsigned long long)(clock64() - prc0);
+      if (simple) { prof_s[0] += 1; prof_s[1] += dt; } else { prof_s[4] += n; prof_s[5] += dt; }
     }
     my_frames += written_frames;
     voice_end_call(v, cc, t + n);
@@ -421,37 +653,52 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
         if (a.prof) prof_q[0] += prof_fr0 - pq0;
         if (mine) {
           uint32_t ec = s_gs.ev_cursor;
+          uint64_t ev_t = ec < gp.ev_end ? a.events[ec].time : UINT64_MAX;   // time of the group's next pending event
           const bool ignore = s_gs.stopping != 0;
           for (uint32_t j = 0; j < run; ++j) {
-            {  // events due at this chunk's start (MixedSource::process_events -> the first write call of the chunk)
-              const uint64_t e0 = bound(k + j);
-              while (ec < gp.ev_end && a.events[ec].time <= e0) {
-                const DevEvent ev = a.events[ec];
-                ++ec;
-                if (ignore || ev.kind == EVK_SET_VOLUME || ev.kind == EVK_SET_PANNING) continue;
-                if (ev.kind == EVK_ALL_NOTES_OFF) { stop_voice(e0); continue; }
-                if (!(v.has_note && v.note_id == ev.note_id)) continue;
-                if (ev.kind == EVK_NOTE_OFF) stop_voice(e0);
-                else if (ev.kind == EVK_NOTE_SPEED) { file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate); if (gsp) gsp->speed = ev.speed; }
-                else if (ev.kind == EVK_NOTE_VOLUME) { v.note_volume = ev.value; exp_set_target(v.vol, gp.base_volume * ev.value, comp); if (gsp) gsp->volume = gp.base_volume * ev.value; }
-                else if (ev.kind == EVK_NOTE_PANNING) {
-                  v.note_panning = ev.value;
-                  const float eff = fminf(fmaxf(gp.base_panning + ev.value, -1.0f), 1.0f);
-                  exp_set_target(v.pan, eff, comp);
-                  if (gsp) gsp->panning = eff;
-                }
+            const uint64_t r0 = bound(k + j);
+            const uint32_t rlen = (uint32_t)(bound(k + j + 1) - r0);
+            const uint32_t r0_off = (uint32_t)(r0 - a.block_start);
+            // events due at this chunk's start (MixedSource::process_events -> the first write call of the chunk)
+            while (ev_t <= r0) {
+              const DevEvent ev = a.events[ec];
+              ++ec;
+              ev_t = ec < gp.ev_end ? a.events[ec].time : UINT64_MAX;
+              if (ignore || ev.kind == EVK_SET_VOLUME || ev.kind == EVK_SET_PANNING) continue;
+              if (ev.kind != EVK_ALL_NOTES_OFF && !(v.has_note && v.note_id == ev.note_id)) continue;
+              sc_finish();  // the event changes this voice: its state has to be exact at r0 first
+              if (ev.kind == EVK_ALL_NOTES_OFF || ev.kind == EVK_NOTE_OFF) stop_voice(r0);
+              else if (ev.kind == EVK_NOTE_SPEED) { file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate); if (gsp) gsp->speed = ev.speed; }
+              else if (ev.kind == EVK_NOTE_VOLUME) { v.note_volume = ev.value; exp_set_target(v.vol, gp.base_volume * ev.value, comp); if (gsp) gsp->volume = gp.base_volume * ev.value; }
+              else if (ev.kind == EVK_NOTE_PANNING) {
+                v.note_panning = ev.value;
+                const float eff = fminf(fmaxf(gp.base_panning + ev.value, -1.0f), 1.0f);
+                exp_set_target(v.pan, eff, comp);
+                if (gsp) gsp->panning = eff;
               }
             }
-            if (v.has_note) {
-              const uint64_t r0 = bound(k + j);
-              const uint32_t rlen = (uint32_t)(bound(k + j + 1) - r0);
-              CallCtx cc;
-              cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
-              if (voice_begin_call(v, cc, gp, buf, rlen, comp, gp.has_env != 0, (uint32_t)(r0 - a.block_start))) run_call(cc, rlen, (uint32_t)(r0 - a.block_start), r0);
-              voice_epilogue(r0 + rlen, (uint32_t)(r0 - a.block_start) + rlen);
-              if (v.has_note) atomicAdd(&s_cnt[j], 1u);
+            if (!v.has_note) continue;
+            if (sc.open) {  // steady voice: accept the chunk into the open call when it provably stays steady to the tile's end
+              const uint32_t r1_off = r0_off + rlen;
+              const uint32_t need = (r1_off + TILE - 1u) / TILE * TILE - sc.adv_off;
+              if (sc.budget < need) sc.budget = sc_steady_budget(sc, v, gp, CCr);
+              if (sc.budget >= need) {
+                sc.end_off = r1_off;
+                unsigned long long* st = a.prof ? prof_s + 2 : nullptr;
+                sc_advance<!WPV>(sc, v, gp, a.groups + g, my_recs, a.gen, CCr, r1_off, false, st);
+                my_frames += rlen;
+                atomicAdd(&s_cnt[j], 1u);
+                continue;
+              }
+              sc_finish();
             }
+            CallCtx cc;
+            cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
+            if (voice_begin_call(v, cc, gp, buf, rlen, comp, gp.has_env != 0, r0_off)) run_call(cc, rlen, r0_off, r0, true);
+            voice_epilogue(r0 + rlen, r0_off + rlen);
+            if (v.has_note) atomicAdd(&s_cnt[j], 1u);
           }
+          sc_finish();
           publish_header(s_head, tid, v);
         }
         const long long pq1 = a.prof ? clock64() : 0;
@@ -624,7 +871,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
 
       // 3. advance the voice through the call, one segment per (call x 64-frame tile)
       uint32_t written_frames = 0;
-      if (call_open) written_frames = run_call(cc, n, call_off, t);
+      if (call_open) written_frames = run_call(cc, n, call_off, t, false);
       if (is_sampler && group_writes && tid == 0) group_call(n, call_off);
       uint32_t written;
       if (is_sampler) {
@@ -676,8 +923,10 @@ PB_DEV void skeleton_block(const SkeletonArgs& a) {
   if (CYC_ON(gp.first_voice + tid) && mine) g_cyc[7] += CYC_T() - cyc_block0;
 #endif
   if (a.prof && mine) {
-    unsigned long long* pr = a.prof + (size_t)(gp.first_voice + tid) * 4;
+    unsigned long long* pr = a.prof + (size_t)(gp.first_voice + tid) * 12;
     pr[0] += prof_q[0]; pr[1] += prof_q[1]; pr[2] += prof_q[3]; pr[3] += prof_free;
+    prof_s[7] = (unsigned long long)(clock64() - prof_b0);
+    for (int i = 0; i < 8; ++i) pr[4 + i] += prof_s[i];
   }
   if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
   __syncthreads();
@@ -694,12 +943,27 @@ struct SkeletonLoop {
   size_t group_flags_stride;     // per-block strides of the snapshot tables (elements)
   size_t segs_stride, seg_tab_stride, gsegs_stride, gseg_tab_stride, recs_stride;
   uint32_t* block_done;          // [n_blocks] CTAs that finished the block
+  uint32_t tab_slots;            // warp-per-voice: shared-memory table slots (one per warp), 0 = tables are read from global memory
 };
 
 template <int MAXT, bool WPV>
 __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a, SkeletonLoop L) {
+  extern __shared__ __align__(128) uint32_t tab_smem[];   // WPV: [tab_slots][TAB_SLOT_WORDS] | mbarriers | parities
+  TabSlot tslot;
+  tslot.words = nullptr; tslot.mbar = nullptr; tslot.parity = nullptr;
+  if (WPV && L.tab_slots) {
+    const uint32_t w = threadIdx.x >> 5;
+    if (w < L.tab_slots) {
+      tslot.words = tab_smem + (size_t)w * TAB_SLOT_WORDS;
+      tslot.mbar = reinterpret_cast<uint64_t*>(tab_smem + (size_t)L.tab_slots * TAB_SLOT_WORDS) + w;
+      tslot.parity = tab_smem + (size_t)L.tab_slots * (TAB_SLOT_WORDS + 2u) + w;
+      if ((threadIdx.x & 31u) == 0) tab_slot_init(tslot);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+  }
   for (uint32_t b = 0; b < L.n_blocks; ++b) {
-    skeleton_block<MAXT, WPV>(a);
+    skeleton_block<MAXT, WPV>(a, tslot);
     if (L.block_done) {
       __syncthreads();
       if (threadIdx.x == 0) { __threadfence(); atomicAdd(L.block_done + b, 1u); }

@@ -270,3 +270,17 @@ def test_adding_a_granular_sampler_between_render_calls_keeps_grains_in_flight(c
 def W_synth(frames):
     from phonic_b200 import workloads as W
     return W.synth_buffer(frames, 48000, seed=77)
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "sampler_notes", "many_groups", "file_events", "submixers_cfg5_small"])
+def test_phase_jumps_and_super_calls_equal_the_literal_loop(cuda_api, name):
+    """PB200_SKEL_DEBUG=4 switches the exact 64-frame phase jumps off (literal f32 recurrence per frame), =2 also the
+    simple / super-call machinery: the same bytes must come out."""
+    _, _, fast = render(cuda_api, name)
+    for flag in ("4", "2"):
+        os.environ["PB200_SKEL_DEBUG"] = flag
+        try:
+            _, _, slow = render(cuda_api, name)
+        finally:
+            del os.environ["PB200_SKEL_DEBUG"]
+        assert np.array_equal(fast, slow), (name, flag)
