@@ -120,10 +120,11 @@ PB_HD PhaseGeom phase_geom(float ratio) {
   return g;
 }
 
-// words of one ratio's table: header | coarse[PT_COARSE + 1] | bp[n_bp] | lo[n_bp + 1] | hi[n_bp + 1] | entry[(n_bp + 1) * L]
+// words of one ratio's table: header | coarse[PT_COARSE + 1] | bpx[n_bp + 2] | lo[n_bp + 1] | hi[n_bp + 1] | entry[(n_bp + 1) * L]
+// bpx[0] = 0 and bpx[n_bp + 1] = ONE are sentinels around the sorted break points bpx[1 .. n_bp]
 PB_HD uint32_t phase_table_words(const PhaseGeom& g) {
   if (g.mode != PT_DOWN_TABLE && g.mode != PT_UP_TABLE) return PT_HEADER;
-  const uint32_t w = PT_HEADER + (PT_COARSE + 1u) + g.n_bp + 2u * (g.n_bp + 1u) + (g.n_bp + 1u) * g.L;
+  const uint32_t w = PT_HEADER + (PT_COARSE + 1u) + (g.n_bp + 2u) + 2u * (g.n_bp + 1u) + (g.n_bp + 1u) * g.L;
   return (w + 3u) & ~3u;  // tables start 16-byte aligned (bulk copies into shared memory)
 }
 
@@ -202,8 +203,8 @@ PB_HD void phase_build_header(uint32_t* tab, float ratio, const PhaseGeom& g) {
   tab[PT_H_WORDS] = phase_table_words(g);
 }
 PB_HD uint32_t* phase_tab_coarse(uint32_t* tab) { return tab + PT_HEADER; }
-PB_HD uint32_t* phase_tab_bp(uint32_t* tab) { return tab + PT_HEADER + PT_COARSE + 1u; }
-PB_HD uint32_t* phase_tab_lo(uint32_t* tab, uint32_t n_bp) { return phase_tab_bp(tab) + n_bp; }
+PB_HD uint32_t* phase_tab_bp(uint32_t* tab) { return tab + PT_HEADER + PT_COARSE + 2u; }  // bpx + 1: the real break points
+PB_HD uint32_t* phase_tab_lo(uint32_t* tab, uint32_t n_bp) { return phase_tab_bp(tab) + n_bp + 1u; }
 PB_HD uint32_t* phase_tab_hi(uint32_t* tab, uint32_t n_bp) { return phase_tab_lo(tab, n_bp) + n_bp + 1u; }
 PB_HD uint32_t* phase_tab_entry(uint32_t* tab, uint32_t n_bp) { return phase_tab_hi(tab, n_bp) + n_bp + 1u; }
 
@@ -228,6 +229,7 @@ PB_HD void phase_build_p3(uint32_t* tab, const PhaseGeom& g, uint32_t tid, uint3
   uint32_t* lo = phase_tab_lo(tab, g.n_bp);
   uint32_t* hi = phase_tab_hi(tab, g.n_bp);
   const uint32_t cshift = tab[PT_H_CSHIFT], ONE = 1u << g.sh;
+  if (tid == 0) { phase_tab_bp(tab)[-1] = 0u; phase_tab_bp(tab)[g.n_bp] = ONE; }
   for (uint32_t c = tid; c <= PT_COARSE; c += nthreads) {      // coarse[c] = number of break points below the bucket's first state
     const uint32_t first = c << cshift;
     uint32_t n = 0;
@@ -258,20 +260,22 @@ PB_HD void phase_build_p4(uint32_t* tab, const PhaseGeom& g, uint32_t tid, uint3
 struct PhaseRef {
   const uint32_t* body;   // coarse[] | bp[] | lo[] | hi[] | entry[]
   const uint32_t* entry;
-  uint32_t mode, sh, R, KR, lmask, n_bp, cshift, margin;
+  uint32_t mode, sh, R, KR, lmask, lshift, n_bp, cshift, margin;
   float scale, inv_scale; // 2^sh (S = sub_pos * scale) and 2^-sh
+  uint32_t smem_body;     // device: shared-memory address of a staged body, 0 = read through `body`
 };
 PB_HD PhaseRef phase_ref(const uint32_t* tab, const uint32_t* body) {
   PhaseRef r;
-  r.body = nullptr; r.entry = nullptr; r.mode = PT_LITERAL; r.sh = r.R = r.KR = r.lmask = r.n_bp = r.cshift = r.margin = 0;
-  r.scale = r.inv_scale = 1.0f;
+  r.body = nullptr; r.entry = nullptr; r.mode = PT_LITERAL; r.sh = r.R = r.KR = r.lmask = r.lshift = r.n_bp = r.cshift = r.margin = 0;
+  r.scale = r.inv_scale = 1.0f; r.smem_body = 0;
   if (tab == nullptr) return r;
   r.mode = tab[PT_H_MODE]; r.sh = tab[PT_H_SH]; r.R = tab[PT_H_R]; r.lmask = tab[PT_H_LMASK]; r.n_bp = tab[PT_H_NBP];
   r.cshift = tab[PT_H_CSHIFT]; r.margin = tab[PT_H_MARGIN];
   r.KR = PT_K * r.R;
   r.scale = pt_bits_f32((127u + r.sh) << 23); r.inv_scale = pt_bits_f32((127u - r.sh) << 23);
   r.body = body ? body : tab + PT_HEADER;
-  r.entry = r.body + PT_COARSE + 1u + 3u * r.n_bp + 2u;
+  r.entry = r.body + PT_COARSE + 1u + (r.n_bp + 2u) + 2u * (r.n_bp + 1u);
+  r.lshift = 0; while ((1u << r.lshift) <= r.lmask) ++r.lshift;
   return r;
 }
 
@@ -302,17 +306,15 @@ PB_HD bool phase_jump(const PhaseRef& t, float& s, uint32_t& np) {
     SK = (S - t.KR) & (ONE - 1u);
     W = (t.KR + SK - S) >> sh;
   } else {
-    const uint32_t n_bp = t.n_bp;
     const uint32_t* coarse = t.body;
-    const uint32_t* bp = coarse + PT_COARSE + 1u;
+    const uint32_t* bpx = coarse + PT_COARSE + 1u;
     uint32_t i = coarse[S >> t.cshift];
-    uint32_t next = i < n_bp ? bp[i] : ONE;
-    while (next <= S) { ++i; next = i < n_bp ? bp[i] : ONE; }
-    const uint32_t prev = i ? bp[i - 1u] : 0u;
-    // interval i = [prev, next) minus the margin on the side of a real break point (phase_build_p3's bounds)
-    if (i > 0u && S < prev + t.margin) return false;
-    if (i < n_bp && S + t.margin + 1u > next) return false;
-    const uint32_t e = t.entry[i * (t.lmask + 1u) + (S & t.lmask)];
+    uint32_t next = bpx[i + 1u];
+    while (next <= S) { ++i; next = bpx[i + 1u]; }
+    const uint32_t prev = bpx[i];
+    // interval i = [prev, next) minus the margin at both ends (never looser than phase_build_p3's bounds)
+    if (S - prev < t.margin || next - S <= t.margin) return false;
+    const uint32_t e = t.entry[(i << t.lshift) + (S & t.lmask)];
     if (!(e & 0x80000000u)) return false;
     W = (e >> 16) & 0xFFFu;
     const uint32_t P = (e & 0xFFFFu) - 32768u;

@@ -70,7 +70,7 @@ __device__ unsigned long long g_cyc[8];
 #define CYC_T() 0ll
 #endif
 constexpr uint32_t SB_MAX = 256;   // chunk boundaries cached in shared memory
-constexpr uint32_t MAX_RUN = 64;   // chunks per free run
+constexpr uint32_t MAX_RUN = 256;  // chunks per free run (fewer joins: the voices of a group take turns being the slowest)
 
 struct VoiceHeader {  // what Sampler::next_free_voice_index needs (sampler.rs:826-860)
   uint64_t note_id;
@@ -295,20 +295,76 @@ PB_DEV void sc_store_rec(const SuperCall& sc, const VoiceState& v, TileRec* __re
   dst[0] = lo; dst[1] = hi;
 }
 
-// Advance the open call to `to_off`. !final: only whole tiles (the rest stays pending). UNI: lane-per-voice skeleton,
-// one instruction stream for every ratio class in the literal pieces (phase_piece_uniform).
-template <bool UNI>
-PB_DEV void sc_advance(SuperCall& sc, VoiceState& v, const GroupParams& gp, const GroupParams* __restrict__ gp_mem, TileRec* __restrict__ my_recs,
-                       const uint32_t gen, const uint32_t CC, const uint32_t to_off, const bool final, unsigned long long* __restrict__ stat) {
-  // steady tiles: one exact jump of the phase recurrence + a closed-form step of a bare envelope chain
-  while (sc.adv_off != sc.open_off && sc.adv_off + TILE <= to_off) {
+// Word `idx` of a table body: from the warp's staged copy (ld.shared, 32-bit address) or through the global pointer.
+template <bool SMEM>
+PB_DEV uint32_t pt_word(const PhaseRef& t, const uint32_t idx) {
+  if (SMEM) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(t.smem_body + idx * 4u));
+    return v;
+  }
+  return t.body[idx];
+}
+
+// The steady tile loop of a super-call: whole tiles past the first piece, the phase state kept as the integer S of
+// phase_table.cuh across tiles (converted once on entry; the conversion doubles as the on-grid test). Stops at the
+// first tile the jump declines or whose envelope is not provably a bare chain; sc_advance's general loop takes over.
+template <bool SMEM>
+PB_DEV void sc_fast_tiles(SuperCall& sc, VoiceState& v, const GroupParams& gp, TileRec* __restrict__ my_recs, const uint32_t gen,
+                          const uint32_t CC, const uint32_t to_off, unsigned long long* __restrict__ stat) {
+  const PhaseRef& t = sc.tab;
+  const uint32_t mode = t.mode;
+  if (mode == PT_LITERAL) return;
+  const float x = sc.s * t.scale;
+  if (!(x >= 0.0f) || !(x < 1073741824.0f)) return;
+  uint32_t S = (uint32_t)x;
+  if ((float)S != x) return;                                   // not on the ratio's grid (yet)
+  if (mode == PT_DOWN_EXACT && (S & t.lmask)) return;
+  const bool down = mode <= PT_DOWN_TABLE;
+  // a ratio >= 1 whose states and R are all even never rounds: the exact rotation applies (see phase_jump)
+  const bool table = (mode == PT_DOWN_TABLE) || (mode == PT_UP_TABLE && ((S | t.R) & 1u));
+  const uint32_t sh = t.sh, ONE = 1u << sh, KR = t.KR, wrap = down ? ONE : 0xFFFFFFFFu;
+  const uint32_t bpx = PT_COARSE + 1u, ent = (uint32_t)(t.entry - t.body);
+  uint32_t np = sc.np, adv = sc.adv_off, budget = sc.budget, done = 0;
+  const uint32_t pos0 = v.playback_pos;
+  TileRec* __restrict__ rec = my_recs + adv / TILE;
+  const uint32_t n_max = (to_off - adv) / TILE;
+  // The loop body is branch-free up to its single exit test so that the record store and the envelope step fill the
+  // issue slots of the S -> lookup -> S' dependency chain (one thread per voice: nothing else hides its latency).
+  for (uint32_t it = 0; it < n_max; ++it) {
     const bool moving = sc.env && v.env_stage != ENV_SUSTAIN && v.env_stage != ENV_IDLE;
-    if (moving && sc.budget < TILE) break;
-    float s2 = sc.s;
-    uint32_t w = 0;
-    if (!phase_jump(sc.tab, s2, w)) break;
-    sc_store_rec(sc, v, my_recs, gen, CC, TILE);
-    sc.s = s2; sc.np += w;
+    if (moving && budget < TILE) break;
+    const uint32_t w0 = S >= wrap ? 1u : 0u;                     // ratio < 1: the first frame's wrap
+    const uint32_t Sr = S - (w0 << sh);
+    bool ok = Sr < ONE;
+    uint32_t SK, W;
+    if (table) {
+      const uint32_t c = pt_word<SMEM>(t, min(Sr, ONE - 1u) >> t.cshift);
+      const uint32_t p0 = pt_word<SMEM>(t, bpx + c), n1 = pt_word<SMEM>(t, bpx + c + 1u), n2 = pt_word<SMEM>(t, bpx + min(c + 2u, t.n_bp + 1u));
+      const bool step = n1 <= Sr;                                // at most one break point of the bucket lies below S ...
+      const uint32_t i = c + (step ? 1u : 0u), next = step ? n2 : n1, prev = step ? n1 : p0;
+      ok = ok && next > Sr;                                      // ... else the general loop takes this tile
+      const uint32_t e = pt_word<SMEM>(t, ent + (min(i, t.n_bp) << t.lshift) + (Sr & t.lmask));
+      ok = ok && (Sr - prev >= t.margin) && (next - Sr > t.margin) && (e & 0x80000000u);
+      W = (e >> 16) & 0xFFFu;
+      const uint32_t P = (e & 0xFFFFu) - 32768u;
+      SK = down ? Sr + KR - (W << sh) + P : Sr + (W << sh) - KR + P;
+    } else if (down) {
+      W = (Sr + KR - t.R) >> sh;
+      SK = Sr + KR - (W << sh);
+    } else {
+      SK = (Sr - KR) & (ONE - 1u);
+      W = (KR + SK - Sr) >> sh;
+    }
+    {  // the tile's continuation record: the state at its first frame (rewritten by the general loop if we stop here)
+      uint4 lo, hi;
+      lo.x = pos0 + np * CC; lo.y = __float_as_uint((float)S * t.inv_scale); lo.z = __float_as_uint(v.env_out); lo.w = __float_as_uint(v.env_hold);
+      hi.x = __float_as_uint(v.env_target); hi.y = ((uint32_t)v.env_stage << 16) | TILE; hi.z = sc.base; hi.w = gen;
+      uint4* dst = reinterpret_cast<uint4*>(rec);
+      dst[0] = lo; dst[1] = hi;
+    }
+    if (!ok) break;
+    np += w0 + W; S = SK;
     if (moving) {
       float d;
       bool on_hold;
@@ -320,10 +376,28 @@ PB_DEV void sc_advance(SuperCall& sc, VoiceState& v, const GroupParams& gp, cons
       }
       if (on_hold) v.env_hold = o; else v.env_out = o;
     }
-    if (stat) stat[0] += 1;
-    sc.first = true;  // the literal loop's look-ahead push flag is stale after a jump
-    sc.adv_off += TILE;
-    sc.budget = sc.budget > TILE ? sc.budget - TILE : 0u;
+    ++rec; ++done;
+    budget = budget > TILE ? budget - TILE : 0u;
+  }
+  if (done) {
+    sc.s = (float)S * t.inv_scale;  // at most 24 significant bits: exact
+    sc.np = np; sc.adv_off = adv + done * TILE; sc.budget = budget;
+    sc.first = true;                // the literal loop's look-ahead push flag is stale after a jump
+    if (stat) stat[0] += done;
+  }
+}
+
+// Advance the open call to `to_off`. !final: only whole tiles (the rest stays pending). UNI: lane-per-voice skeleton,
+// one instruction stream for every ratio class in the literal pieces (phase_piece_uniform).
+template <bool UNI>
+PB_DEV void sc_advance(SuperCall& sc, VoiceState& v, const GroupParams& gp, const GroupParams* __restrict__ gp_mem, TileRec* __restrict__ my_recs,
+                       const uint32_t gen, const uint32_t CC, const uint32_t to_off, const bool final, unsigned long long* __restrict__ stat) {
+  // steady tiles: one exact jump of the phase recurrence + a closed-form step of a bare envelope chain
+  if (sc.adv_off != sc.open_off && sc.adv_off + TILE <= to_off) {
+    const long long f0 = stat ? clock64() : 0;
+    if (sc.tab.smem_body) sc_fast_tiles<true>(sc, v, gp, my_recs, gen, CC, to_off, stat);
+    else sc_fast_tiles<false>(sc, v, gp, my_recs, gen, CC, to_off, stat);
+    if (stat) stat[4] += (unsigned long long)(clock64() - f0);
   }
   while (sc.adv_off < to_off) {
     const uint32_t tile_end = (sc.adv_off / TILE + 1u) * TILE;
@@ -489,6 +563,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
         if (words <= TAB_SLOT_WORDS) { tab_slot_fetch(tslot, t + PT_HEADER, words * 4u); body = tslot.words; }
       }
       tab_ref = phase_ref(t, body);
+      if (body) tab_ref.smem_body = smem_u32(body);
     }
     return tab_ref;
   };
@@ -685,7 +760,9 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
               if (sc.budget >= need) {
                 sc.end_off = r1_off;
                 unsigned long long* st = a.prof ? prof_s + 2 : nullptr;
+                const long long q0 = a.prof ? clock64() : 0;
                 sc_advance<!WPV>(sc, v, gp, a.groups + g, my_recs, a.gen, CCr, r1_off, false, st);
+                if (a.prof) prof_s[7] += (unsigned long long)(clock64() - q0);
                 my_frames += rlen;
                 atomicAdd(&s_cnt[j], 1u);
                 continue;
@@ -925,7 +1002,6 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
   if (a.prof && mine) {
     unsigned long long* pr = a.prof + (size_t)(gp.first_voice + tid) * 12;
     pr[0] += prof_q[0]; pr[1] += prof_q[1]; pr[2] += prof_q[3]; pr[3] += prof_free;
-    prof_s[7] = (unsigned long long)(clock64() - prof_b0);
     for (int i = 0; i < 8; ++i) pr[4 + i] += prof_s[i];
   }
   if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);

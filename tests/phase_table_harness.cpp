@@ -97,7 +97,7 @@ void pt_table_stats(const uint32_t* tab, uint64_t* out) {
   out[0] = out[1] = out[2] = out[3] = 0;
   if (mode != PT_DOWN_TABLE && mode != PT_UP_TABLE) return;
   const uint32_t n_bp = tab[PT_H_NBP], L = tab[PT_H_LMASK] + 1;
-  const uint32_t* lo = tab + PT_HEADER + PT_COARSE + 1 + n_bp;
+  const uint32_t* lo = tab + PT_HEADER + PT_COARSE + 1 + n_bp + 2;
   const uint32_t* hi = lo + n_bp + 1;
   const uint32_t* entry = hi + n_bp + 1;
   for (uint32_t i = 0; i <= n_bp; ++i) {

@@ -120,7 +120,7 @@ def test_jumps_equal_64_literal_frames(lib):
         # (c) states at and around every break point and margin edge
         if g["mode"] in (2, 4):
             n_bp = g["n_bp"]
-            bp = tab[16 + 257:16 + 257 + n_bp].astype(np.int64)
+            bp = tab[16 + 258:16 + 258 + n_bp].astype(np.int64)
             one = 1 << g["sh"]
             offs = np.array([-g["margin"] - 2, -g["margin"] - 1, -g["margin"], -g["margin"] + 1, -3, -2, -1, 0, 1, 2, 3,
                              g["margin"] - 1, g["margin"], g["margin"] + 1, g["margin"] + 2], np.int64)

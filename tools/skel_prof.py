@@ -20,7 +20,7 @@ gi = int(np.argmax(g[:, :, 3].max(axis=1)))
 print("group", gi, "columns: sync1(before run) sync2(after voices) sync3(after thread0 bookkeeping) free-run-work  [Mcycles]")
 for v in range(8): print("  voice", gi * 8 + v, np.round(g[gi, v] / 1e6, 2))
 print("mean over all voices:", np.round(d[:, 1:5].mean(axis=0) / 1e6, 2))
-print("columns: simple calls, their Mcycles, jumped tiles, literal frames, general-path frames, their Mcycles, Mcycles in phase_jump, block Mcycles")
+print("columns: simple calls, their Mcycles, jumped tiles, literal frames, general-path frames, their Mcycles, Mcycles in the fast tile loop, Mcycles in soft sc_advance")
 for v in range(8):
     r = x[gi, v]
     print("  voice", gi * 8 + v, int(r[0]), round(r[1] / 1e6, 2), int(r[2]), int(r[3]), int(r[4]), round(r[5] / 1e6, 2), round(r[6] / 1e6, 2), round(r[7] / 1e6, 2))
