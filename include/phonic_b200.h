@@ -57,7 +57,7 @@ enum pb200_error {
 
 #define PB200_TIME_NOW UINT64_MAX /* `None` sample time of the handle methods */
 #define PB200_MAIN_MIXER 0u       /* Player::MAIN_MIXER_ID (src/player.rs) */
-#define PB200_REPEAT_DEFAULT UINT64_MAX - 1 /* FilePlaybackOptions::repeat = None */
+#define PB200_REPEAT_DEFAULT (UINT64_MAX - 1) /* FilePlaybackOptions::repeat = None */
 #define PB200_REPEAT_FOREVER UINT64_MAX     /* FilePlaybackOptions::repeat_forever() */
 #define PB200_NO_LOOP (-1)
 /* All durations cross the boundary as std::time::Duration::as_nanos() so that the
@@ -253,9 +253,19 @@ enum pb200_event_kind {
   PB200_EV_SET_NOTE_SPEED = 13,  /* set_note_speed(note_id, speed, glide, t) */
   PB200_EV_SET_NOTE_VOLUME = 14, /* set_note_volume(note_id, volume, t) */
   PB200_EV_SET_NOTE_PANNING = 15,/* set_note_panning(note_id, panning, t) */
+  /* set_parameter((id, value), t) -> GeneratorPlaybackEvent::SetParameter (handles/generator.rs, src/generator.rs:172-226;
+   * Sampler::process_parameter_update, src/generator/sampler.rs:1069-1192): param_id = 'STRN' transpose, 'SFTN' finetune
+   * (integer parameters: raw values are truncated to i32), 'SVOL' volume, 'SPAN' panning, and with an AHDSR envelope
+   * 'AATK' 'AHLD' 'ADCY' 'ASTN' 'AREL'; `value` raw or, with PB200_EVF_NORMALIZED, normalized. */
+  PB200_EV_SET_GENERATOR_PARAMETER = 16,
+  /* send_message(SamplerMessage::SetLoopRange(range), t) (src/generator/sampler.rs:1246-1271): position_nanos = first
+   * frame, note_id = end frame of the loop; PB200_EVF_NO_RANGE: None (looping off). */
+  PB200_EV_SET_GENERATOR_LOOP_RANGE = 17,
   /* EffectHandle: target = effect id */
-  PB200_EV_SET_EFFECT_PARAMETER = 20 /* set_parameter((id, value), t) handles/effect.rs:67-98 */
+  PB200_EV_SET_EFFECT_PARAMETER = 20, /* set_parameter((id, value), t) handles/effect.rs:67-98 */
+  PB200_EV_EFFECT_MESSAGE = 21        /* send_message(message, t)      handles/effect.rs:127-163; param_id = PB200_MSG_* */
 };
+#define PB200_MSG_REVERB_RESET 1u /* ReverbEffectMessage::Reset (src/effect/reverb.rs:469-487) */
 
 typedef struct pb200_event {
   uint64_t sample_time; /* absolute output frame, or PB200_TIME_NOW */
@@ -275,6 +285,7 @@ typedef struct pb200_event {
 #define PB200_EVF_NORMALIZED 1u /* ParameterValueUpdate::Normalized instead of ::Raw */
 #define PB200_EVF_HAS_VOLUME 2u /* NOTE_ON: volume is Some(value) */
 #define PB200_EVF_HAS_PANNING 4u/* NOTE_ON: panning is Some(value2) */
+#define PB200_EVF_NO_RANGE 16u  /* SET_GENERATOR_LOOP_RANGE: the range is None */
 
 /* Queue one event. For PB200_EV_NOTE_ON a fresh NotePlaybackId is allocated
  * (unique_note_id, src/generator.rs:30-33) and written back to `ev->note_id`. */
@@ -287,6 +298,25 @@ PB200_API int pb200_schedule(pb200_renderer *r, pb200_event *ev);
  * src/player/handles/generator.rs:62-437; an offline score has no reason to cross the FFI once per event.) */
 #define PB200_EVF_NOTE_FROM_BATCH 8u
 PB200_API int pb200_schedule_many(pb200_renderer *r, pb200_event *events, uint32_t count, uint32_t *scheduled);
+
+/* ---- structural messages: take effect at the next block start, i.e. with the next render call ------------------------
+ * (MixedSource::process_messages runs at the top of every Source::write, src/source/mixed.rs:294-499) */
+/* Player::remove_generator (src/player.rs:747-770) -> MixerMessage::RemoveSource (mixed.rs:391-393): the source is
+ * dropped from its mixer, whatever it is playing. Also valid for file playbacks. */
+PB200_API int pb200_remove_source(pb200_renderer *r, uint32_t playback_id);
+/* Player::remove_mixer (src/player.rs:825-868) -> MixerMessage::RemoveMixer: the sub-mixer, its effects, sources and
+ * sub-mixers disappear from the parent's sum. PB200_ERR_PARAMETER for the main mixer. */
+PB200_API int pb200_remove_mixer(pb200_renderer *r, uint32_t mixer_id);
+/* Player::remove_effect (src/player.rs:977-991) -> MixerMessage::RemoveEffect (mixed.rs:432-439) */
+PB200_API int pb200_remove_effect(pb200_renderer *r, uint32_t effect_id);
+/* Player::move_effect (src/player.rs:942-974) -> MixerMessage::MoveEffect (mixed.rs:440-459); EffectMovement:
+ * Direction(offset) | Start | End. `mixer_id` must be the effect's mixer (PB200_ERR_PARAMETER otherwise). */
+enum pb200_effect_movement { PB200_MOVE_DIRECTION = 0, PB200_MOVE_START = 1, PB200_MOVE_END = 2 };
+PB200_API int pb200_move_effect(pb200_renderer *r, uint32_t effect_id, uint32_t mixer_id, uint32_t movement, int32_t offset);
+/* Player::stop_all_sources (src/player.rs:1012-1045): Stop to every transient source + MixerMessage::
+ * RemoveAllPendingEvents on every mixer (scheduled sources that have not started and all pending events are dropped,
+ * mixed.rs:297-305). */
+PB200_API int pb200_stop_all_sources(pb200_renderer *r);
 
 /* ---- render: repeated WavStream::process (src/output/wav.rs:210-250) -----------------------
  * Renders `frames` output frames (interleaved f32, channel_count channels) as the reference

@@ -26,6 +26,11 @@
 #define pb200_upload_wav po_upload_wav
 #define pb200_render_to_wav po_render_to_wav
 #define pb200_schedule_many po_schedule_many
+#define pb200_remove_source po_remove_source
+#define pb200_remove_mixer po_remove_mixer
+#define pb200_remove_effect po_remove_effect
+#define pb200_move_effect po_move_effect
+#define pb200_stop_all_sources po_stop_all_sources
 #include "../include/phonic_b200.h"
 
 #include <chrono>
@@ -41,10 +46,11 @@ struct pb200_renderer {
   std::string last_error;
   std::unique_ptr<MixedSource> main;
   std::map<uint32_t, MixedSource*> mixers;  // id -> mixer (0 = main)
+  std::map<uint32_t, uint32_t> mixer_parents; // sub-mixer id -> parent id
   std::vector<std::shared_ptr<AudioFileBuffer>> buffers;
   struct SourceRef { uint32_t mixer; PlaybackQueues queues; PreloadedFileSource* file = nullptr; Sampler* sampler = nullptr; bool transient = true; };
   std::map<uint32_t, SourceRef> sources;
-  struct EffectRef { uint32_t mixer; };
+  struct EffectRef { uint32_t mixer; uint32_t kind; };
   std::map<uint32_t, EffectRef> effects;
   uint32_t next_source_id = 1, next_mixer_id = 1, next_effect_id = 1;
   uint64_t next_note_id = 1;
@@ -115,6 +121,7 @@ int pb200_add_mixer(pb200_renderer* r, uint32_t parent, uint32_t* mixer_id) {
   proc->mixer = std::make_unique<MixedSource>(r->cfg.channel_count, r->cfg.sample_rate);
   uint32_t id = r->next_mixer_id++;
   r->mixers[id] = proc->mixer.get();
+  r->mixer_parents[id] = parent;
   MixedSource::Message m; m.kind = MixedSource::Message::AddMixer; m.id = id; m.mixer = proc;
   it->second->message_queue.push_back(std::move(m));
   *mixer_id = id;
@@ -206,7 +213,7 @@ int pb200_add_effect(pb200_renderer* r, uint32_t mixer, uint32_t kind, const voi
   MixedSource::Message m; m.kind = MixedSource::Message::AddEffect; m.id = id;
   m.effect = std::make_shared<EffectProcessor>(std::move(fx));
   it->second->message_queue.push_back(std::move(m));
-  r->effects[id] = {mixer};
+  r->effects[id] = {mixer, kind};
   *effect_id = id;
   return PB200_OK;
 }
@@ -321,12 +328,26 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
 int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
   if (!r || !ev) return PB200_ERR_PARAMETER;
   const bool now = ev->sample_time == PB200_TIME_NOW;
+  if (ev->kind == PB200_EV_EFFECT_MESSAGE) {  // EffectHandle::send_message (handles/effect.rs:127-163)
+    auto it = r->effects.find(ev->target);
+    if (it == r->effects.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+    if (ev->param_id != PB200_MSG_REVERB_RESET || it->second.kind != PB200_FX_REVERB)
+      return fail(r, PB200_ERR_PARAMETER, "Invalid message for this effect");
+    MixedSource::Message m; m.kind = MixedSource::Message::Event;
+    m.event.kind = MixerEvent::EffectMessage; m.event.target = ev->target;
+    m.event.sample_time = now ? 0 : ev->sample_time;
+    m.event.param_id = ev->param_id;
+    r->mixers[it->second.mixer]->message_queue.push_back(std::move(m));
+    return PB200_OK;
+  }
   if (ev->kind == PB200_EV_SET_EFFECT_PARAMETER) {
     auto it = r->effects.find(ev->target);
     if (it == r->effects.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
     MixedSource::Message m; m.kind = MixedSource::Message::Event;
     m.event.kind = MixerEvent::EffectParameter; m.event.target = ev->target;
     m.event.sample_time = now ? 0 : ev->sample_time;  // handles/effect.rs:80: None => 0
+    if ((ev->flags & PB200_EVF_NORMALIZED) && !(ev->value >= 0.0f && ev->value <= 1.0f))  // handles/effect.rs:72-77
+      return fail(r, PB200_ERR_PARAMETER, "Invalid parameter update: value should be a normalized value");
     m.event.param_id = ev->param_id;
     m.event.param = {ev->value, (ev->flags & PB200_EVF_NORMALIZED) != 0};
     r->mixers[it->second.mixer]->message_queue.push_back(std::move(m));
@@ -393,6 +414,22 @@ int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
     case PB200_EV_SET_NOTE_SPEED: g.kind = GenEvent::SetSpeed; g.note_id = ev->note_id; g.speed = ev->speed; g.has_glide = has_glide; g.glide = ev->glide; break;
     case PB200_EV_SET_NOTE_VOLUME: g.kind = GenEvent::SetVolume; g.note_id = ev->note_id; g.volume = ev->value; break;
     case PB200_EV_SET_NOTE_PANNING: g.kind = GenEvent::SetPanning; g.note_id = ev->note_id; g.panning = ev->value; break;
+    case PB200_EV_SET_GENERATOR_PARAMETER:  // GeneratorPlaybackHandle::set_parameter: the id must be one of the generator's parameters
+      if (!Sampler::is_parameter(ev->param_id, ref.sampler->envelope_parameters.has_value()))
+        return fail(r, PB200_ERR_PARAMETER, "Invalid or unknown sampler parameter");
+      if (std::isnan(ev->value)) return fail(r, PB200_ERR_PARAMETER, "Invalid parameter value");
+      if ((ev->flags & PB200_EVF_NORMALIZED) && !(ev->value >= 0.0f && ev->value <= 1.0f))
+        return fail(r, PB200_ERR_PARAMETER, "Invalid parameter update: value should be a normalized value");
+      g.kind = GenEvent::SetParameter; g.param_id = ev->param_id; g.param_value = ev->value; g.param_normalized = (ev->flags & PB200_EVF_NORMALIZED) != 0;
+      break;
+    case PB200_EV_SET_GENERATOR_LOOP_RANGE:
+      g.kind = GenEvent::SetLoopRange; g.has_range = !(ev->flags & PB200_EVF_NO_RANGE); g.range_start = ev->position_nanos; g.range_end = ev->note_id;
+      if (ref.sampler->granular_parameters) return fail(r, PB200_ERR_UNSUPPORTED, "loop range messages to granular samplers");
+      if (g.has_range) {
+        const uint64_t fc = ref.sampler->file_buffer->frame_count();
+        if (g.range_start >= g.range_end || g.range_start >= fc || g.range_end > fc) return fail(r, PB200_ERR_PARAMETER, "Invalid loop range");
+      }
+      break;
     default: return fail(r, PB200_ERR_PARAMETER, "unknown event kind");
   }
   if (now) {
@@ -400,6 +437,75 @@ int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
     if (!ref.queues.generator->push(m)) return fail(r, PB200_ERR_SEND, "Generator playback queue is full");
   } else {
     MixerEvent e; e.kind = MixerEvent::TriggerGenerator; e.gen = g; push_event(e);
+  }
+  return PB200_OK;
+}
+
+// ---- structural messages (processed by MixedSource::process_messages at the next block start) -------------------------
+int pb200_remove_source(pb200_renderer* r, uint32_t playback_id) {  // Player::remove_generator (player.rs:747-770)
+  if (!r) return PB200_ERR_PARAMETER;
+  auto it = r->sources.find(playback_id);
+  if (it == r->sources.end()) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+  MixedSource::Message m; m.kind = MixedSource::Message::RemoveSource; m.id = playback_id;
+  r->mixers[it->second.mixer]->message_queue.push_back(std::move(m));
+  r->sources.erase(it);
+  return PB200_OK;
+}
+
+int pb200_remove_mixer(pb200_renderer* r, uint32_t mixer_id) {  // Player::remove_mixer (player.rs:825-868)
+  if (!r) return PB200_ERR_PARAMETER;
+  if (mixer_id == PB200_MAIN_MIXER) return fail(r, PB200_ERR_PARAMETER, "Cannot remove the main mixer");
+  auto pit = r->mixer_parents.find(mixer_id);
+  if (pit == r->mixer_parents.end() || !r->mixers.count(mixer_id)) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  MixedSource::Message m; m.kind = MixedSource::Message::RemoveMixer; m.id = mixer_id;
+  r->mixers[pit->second]->message_queue.push_back(std::move(m));
+  // the removed subtree is gone for the player too (the reference drops the mixer's effects from its tracking maps;
+  // its sources and sub-mixers die with the mixer object)
+  std::vector<uint32_t> gone{mixer_id};
+  for (size_t i = 0; i < gone.size(); ++i)
+    for (auto& kv : r->mixer_parents) if (kv.second == gone[i]) gone.push_back(kv.first);
+  for (uint32_t g : gone) {
+    for (auto it = r->effects.begin(); it != r->effects.end();) { if (it->second.mixer == g) it = r->effects.erase(it); else ++it; }
+    for (auto it = r->sources.begin(); it != r->sources.end();) { if (it->second.mixer == g) it = r->sources.erase(it); else ++it; }
+    r->mixers.erase(g);
+    r->mixer_parents.erase(g);
+  }
+  return PB200_OK;
+}
+
+int pb200_remove_effect(pb200_renderer* r, uint32_t effect_id) {  // Player::remove_effect (player.rs:977-991)
+  if (!r) return PB200_ERR_PARAMETER;
+  auto it = r->effects.find(effect_id);
+  if (it == r->effects.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+  MixedSource::Message m; m.kind = MixedSource::Message::RemoveEffect; m.id = effect_id;
+  r->mixers[it->second.mixer]->message_queue.push_back(std::move(m));
+  r->effects.erase(it);
+  return PB200_OK;
+}
+
+int pb200_move_effect(pb200_renderer* r, uint32_t effect_id, uint32_t mixer_id, uint32_t movement, int32_t offset) {  // player.rs:942-974
+  if (!r) return PB200_ERR_PARAMETER;
+  auto it = r->effects.find(effect_id);
+  if (it == r->effects.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+  if (it->second.mixer != mixer_id) return fail(r, PB200_ERR_PARAMETER, "Effect does not belong to this mixer");
+  if (movement > PB200_MOVE_END) return fail(r, PB200_ERR_PARAMETER, "unknown effect movement");
+  MixedSource::Message m; m.kind = MixedSource::Message::MoveEffect; m.id = effect_id; m.movement = movement; m.offset = offset;
+  r->mixers[mixer_id]->message_queue.push_back(std::move(m));
+  return PB200_OK;
+}
+
+int pb200_stop_all_sources(pb200_renderer* r) {  // Player::stop_all_sources (player.rs:1012-1045)
+  if (!r) return PB200_ERR_PARAMETER;
+  for (auto it = r->sources.begin(); it != r->sources.end();) {
+    if (it->second.transient) {
+      if (it->second.queues.file) { FileMsg m{FileMsg::Stop}; it->second.queues.file->force_push(m); }
+      else { GenMsg m; m.is_stop = true; it->second.queues.generator->force_push(m); }
+      it = r->sources.erase(it);
+    } else ++it;
+  }
+  for (auto& kv : r->mixers) {
+    MixedSource::Message m; m.kind = MixedSource::Message::RemoveAllPendingEvents;
+    kv.second->message_queue.push_back(std::move(m));
   }
   return PB200_OK;
 }

@@ -36,6 +36,8 @@ struct Duration {
   static Duration from_nanos(uint64_t n) { return {n / 1000000000ull, (uint32_t)(n % 1000000000ull)}; }
   static Duration from_millis(uint64_t ms) { return from_nanos(ms * 1000000ull); }
   static Duration from_secs(uint64_t s) { return {s, 0}; }
+  // Duration::from_secs_f32: the exact value rounded to the nearest nanosecond (core::time, try_from_secs_f32)
+  static Duration from_secs_f32(float s) { return from_nanos((uint64_t)std::nearbyint((double)s * 1.0e9)); }
   bool is_zero() const { return secs == 0 && nanos == 0; }
   float as_secs_f32() const { return (float)secs + (float)nanos / 1.0e9f; }
   double as_secs_f64() const { return (double)secs + (double)nanos / 1.0e9; }

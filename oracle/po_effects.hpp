@@ -1090,6 +1090,12 @@ struct ReverbEffect : Effect {
   }
   const char* name() const override { return "Reverb"; }
   size_t weight() const override { return 5; }
+  bool process_message(uint32_t message) override {  // ReverbEffectMessage::Reset (reverb.rs:469-487)
+    if (message != 1u) return false;
+    for (auto& l : lines) l.flush();
+    ai.flush(); aj.flush(); ak.flush(); al.flush(); m.flush();
+    return true;
+  }
   bool initialize(uint32_t sr, size_t ch, size_t) override {
     sample_rate = sr; channel_count = ch;
     if (ch != 2) return false;

@@ -343,7 +343,9 @@ struct PannedSource : Source {
 
 // ---- GeneratorPlaybackEvent / GeneratorPlaybackMessage (src/generator.rs:172-239) -------------------
 struct GenEvent {
-  enum Kind { NoteOn, NoteOff, AllNotesOff, SetSpeed, SetVolume, SetPanning } kind;
+  enum Kind { NoteOn, NoteOff, AllNotesOff, SetSpeed, SetVolume, SetPanning, SetParameter, SetLoopRange } kind;
+  uint32_t param_id = 0; float param_value = 0; bool param_normalized = false;  // SetParameter (generator.rs:172-226)
+  bool has_range = false; uint64_t range_start = 0, range_end = 0;                 // ProcessMessage(SamplerMessage::SetLoopRange)
   uint64_t note_id = 0;
   uint8_t note = 60;
   bool has_volume = false; float volume = 1;
@@ -415,6 +417,31 @@ struct SamplerVoice {
     double pitch_factor = std::pow(2.0, (double)base_transpose / 12.0 + (double)base_finetune / 1200.0);
     file->set_speed(speed * pitch_factor, has_glide, glide);
     if (grain_pool) grain_pool->speed = speed * pitch_factor;
+  }
+  void set_base_pitch(int32_t base_transpose, int32_t base_finetune) {  // voice.rs:258-268
+    double note_speed = speed_from_note(note);
+    double pitch_factor = std::pow(2.0, (double)base_transpose / 12.0 + (double)base_finetune / 1200.0);
+    double effective_speed = note_speed * pitch_factor;
+    file->set_speed(effective_speed, false, 0.0f);
+    if (grain_pool) grain_pool->speed = effective_speed;
+  }
+  void set_base_volume(float base_volume) {  // voice.rs:283-289
+    amplified->set_volume(base_volume * note_volume);
+    if (grain_pool) grain_pool->volume = base_volume * note_volume;
+  }
+  void set_base_panning(float base_panning) {  // voice.rs:304-310
+    float eff = std::min(std::max(base_panning + note_panning, -1.0f), 1.0f);
+    source->set_panning(eff);
+    if (grain_pool) grain_pool->panning = eff;
+  }
+  void set_loop_range(bool has, uint64_t s, uint64_t e) {  // voice.rs:313-339
+    file->set_loop_range(has, s, e);
+    file->set_repeat(has ? USIZE_MAX : 0);
+    if (grain_pool) {
+      float total = (float)file->file_buffer->frame_count();
+      grain_pool->has_loop_range = has;  // GrainPool::set_loop_range (granular.rs:516-518)
+      grain_pool->loop_start = has ? (float)s / total : 0.0f; grain_pool->loop_end = has ? (float)e / total : 0.0f;
+    }
   }
   void set_volume(float v, float base_volume) {
     note_volume = v; amplified->set_volume(base_volume * v);
@@ -543,6 +570,54 @@ struct Sampler : Source {
     for (auto& v : voices) if (v.has_note && v.note_id == id) return &v;
     return nullptr;
   }
+  // FloatParameter::denormalize_value with its ParameterScaling (parameter/float.rs, scaling.rs:45-75)
+  static float denorm_linear(float n, float lo, float hi) { return lo + n * (hi - lo); }
+  static float denorm_exp2(float n, float lo, float hi) { return lo + std::pow(n, 2.0f) * (hi - lo); }
+  static float denorm_db(float n, float lo, float hi, float db_lo, float db_hi) {
+    float db = db_lo + n * (db_hi - db_lo);
+    float l = db_to_linear(db_lo), h = db_to_linear(db_hi);
+    return lo + ((db_to_linear(db) - l) / (h - l)) * (hi - lo);
+  }
+  static float clampf(float v, float lo, float hi) { return std::min(std::max(v, lo), hi); }
+  // Sampler::process_parameter_update (sampler.rs:1069-1192): base + envelope parameters. Returns false for ids the
+  // reference answers with Error::ParameterError (logged and ignored on the audio thread, sampler.rs:694-697).
+  bool process_parameter_update(uint32_t id, float value, bool normalized) {
+    const float n = clampf(value, 0.0f, 1.0f);
+    auto time_value = [&]() { return normalized ? denorm_exp2(n, 0.0f, 10.0f) : clampf(value, 0.0f, 10.0f); };
+    if (id == fourcc("STRN")) {
+      base_transpose = normalized ? (int32_t)std::round(-48.0f + n * 96.0f) : std::min(std::max((int32_t)value, -48), 48);
+      for (auto& v : voices) if (v.is_active()) v.set_base_pitch(base_transpose, base_finetune);
+      return true;
+    }
+    if (id == fourcc("SFTN")) {
+      base_finetune = normalized ? (int32_t)std::round(-100.0f + n * 200.0f) : std::min(std::max((int32_t)value, -100), 100);
+      for (auto& v : voices) if (v.is_active()) v.set_base_pitch(base_transpose, base_finetune);
+      return true;
+    }
+    if (id == fourcc("SVOL")) {
+      base_volume = normalized ? denorm_db(n, 0.000001f, 15.848932f, -60.0f, 24.0f) : clampf(value, 0.000001f, 15.848932f);
+      for (auto& v : voices) if (v.is_active()) v.set_base_volume(base_volume);
+      return true;
+    }
+    if (id == fourcc("SPAN")) {
+      base_panning = normalized ? denorm_linear(n, -1.0f, 1.0f) : clampf(value, -1.0f, 1.0f);
+      for (auto& v : voices) if (v.is_active()) v.set_base_panning(base_panning);
+      return true;
+    }
+    if (envelope_parameters) {  // Sampler::set_envelope_parameter (sampler.rs:184-218)
+      AhdsrParameters& p = *envelope_parameters;
+      if (id == fourcc("AATK")) { p.set_attack_time(Duration::from_secs_f32(std::max(time_value(), 0.0f))); return true; }
+      if (id == fourcc("AHLD")) { p.set_hold_time(Duration::from_secs_f32(std::max(time_value(), 0.0f))); return true; }
+      if (id == fourcc("ADCY")) { p.set_decay_time(Duration::from_secs_f32(std::max(time_value(), 0.0f))); return true; }
+      if (id == fourcc("ASTN")) { return p.set_sustain_level(normalized ? denorm_linear(n, 0.0f, 1.0f) : clampf(value, 0.0f, 1.0f)); }
+      if (id == fourcc("AREL")) { p.set_release_time(Duration::from_secs_f32(std::max(time_value(), 0.0f))); return true; }
+    }
+    return false;
+  }
+  static bool is_parameter(uint32_t id, bool has_env) {
+    if (id == fourcc("STRN") || id == fourcc("SFTN") || id == fourcc("SVOL") || id == fourcc("SPAN")) return true;
+    return has_env && (id == fourcc("AATK") || id == fourcc("AHLD") || id == fourcc("ADCY") || id == fourcc("ASTN") || id == fourcc("AREL"));
+  }
   void process_playback_messages(uint64_t frame) {  // sampler.rs:656-731
     GenMsg m;
     while (queue->pop(m)) {
@@ -565,6 +640,13 @@ struct Sampler : Source {
           case GenEvent::SetSpeed: if (auto* v = find_voice(e.note_id)) v->set_speed(e.speed, e.has_glide, e.glide, base_transpose, base_finetune); break;
           case GenEvent::SetVolume: if (auto* v = find_voice(e.note_id)) v->set_volume(e.volume, base_volume); break;
           case GenEvent::SetPanning: if (auto* v = find_voice(e.note_id)) v->set_panning(e.panning, base_panning); break;
+          case GenEvent::SetParameter: (void)process_parameter_update(e.param_id, e.param_value, e.param_normalized); break;
+          case GenEvent::SetLoopRange: {  // Sampler::process_message (sampler.rs:1246-1271)
+            uint64_t fc = voices.empty() ? 0 : voices[0].file->file_buffer->frame_count();
+            if (!e.has_range || (e.range_start < fc && e.range_end <= fc))
+              for (auto& v : voices) v.set_loop_range(e.has_range, e.range_start, e.range_end);
+            break;
+          }
         }
       }
     }
@@ -600,6 +682,7 @@ struct Effect {
   virtual void process(float* buf, size_t len, uint64_t time_frames) = 0;
   virtual bool process_tail(size_t& frames) const { (void)frames; return false; }  // Option<usize>
   virtual bool process_parameter_update(uint32_t id, const ParamUpdate& value) = 0;
+  virtual bool process_message(uint32_t message) { (void)message; return false; }  // Effect::process_message (effect.rs)
 };
 
 // ---- src/source/mixed/effect.rs:10-153 ------------------------------------------------------------------
@@ -645,7 +728,7 @@ struct EffectProcessor {
 
 // ---- MixerMessage / MixerEvent (src/source/mixed.rs:47-194) --------------------------------------------
 struct MixerEvent {
-  enum Kind { SeekSource, SetSourceSpeed, SetSourceVolume, SetSourcePanning, TriggerGenerator, EffectParameter } kind;
+  enum Kind { SeekSource, SetSourceSpeed, SetSourceVolume, SetSourcePanning, TriggerGenerator, EffectParameter, EffectMessage } kind;
   uint32_t target = 0;  // playback id / effect id
   uint64_t sample_time = 0;
   Duration position; double speed = 1; bool has_glide = false; float glide = 0;
@@ -681,7 +764,9 @@ struct MixedSource : Source {
     bool has_stop_time = false; uint64_t stop_time = 0;
   };
   struct Message {  // the subset of MixerMessage the offline path uses
-    enum Kind { AddSource, StopSource, AddMixer, AddEffect, Event } kind;
+    enum Kind { AddSource, StopSource, AddMixer, AddEffect, Event, RemoveSource, RemoveMixer, RemoveEffect, MoveEffect,
+                RemoveAllPendingEvents } kind;
+    uint32_t movement = 0; int32_t offset = 0;  // MoveEffect: EffectMovement (0 Direction(offset), 1 Start, 2 End)
     std::shared_ptr<PlayingSource> source;  // AddSource (moved out on processing)
     uint32_t id = 0; uint64_t sample_time = 0;
     std::shared_ptr<SubMixerProcessor> mixer;
@@ -714,7 +799,7 @@ struct MixedSource : Source {
     for (auto& s : playing_sources) if (s->playback_id == id) return s.get();
     return nullptr;
   }
-  void process_messages(const SourceTime&) {  // mixed.rs:294-499
+  void process_messages(const SourceTime& time) {  // mixed.rs:294-499
     while (!message_queue.empty()) {
       Message m = std::move(message_queue.front());
       message_queue.pop_front();
@@ -732,6 +817,42 @@ struct MixedSource : Source {
         case Message::AddMixer: mixers.emplace_back(m.id, m.mixer); break;
         case Message::AddEffect: effects.emplace_back(m.id, m.effect); effects_bypassed = false; break;
         case Message::Event: insert_event(m.event); break;
+        case Message::RemoveAllPendingEvents:  // mixed.rs:297-305
+          for (size_t i = 0; i < playing_sources.size();) {
+            if (playing_sources[i]->is_transient && playing_sources[i]->start_time > time.pos_in_frames) playing_sources.erase(playing_sources.begin() + i);
+            else ++i;
+          }
+          for (size_t i = 0; i < events.size();) {
+            if (events[i].sample_time > time.pos_in_frames) events.erase(events.begin() + i);
+            else ++i;
+          }
+          break;
+        case Message::RemoveSource:  // mixed.rs:391-393
+          for (size_t i = 0; i < playing_sources.size();) {
+            if (playing_sources[i]->playback_id == m.id) playing_sources.erase(playing_sources.begin() + i);
+            else ++i;
+          }
+          break;
+        case Message::RemoveMixer:  // mixed.rs:417-419
+          for (size_t i = 0; i < mixers.size();) { if (mixers[i].first == m.id) mixers.erase(mixers.begin() + i); else ++i; }
+          break;
+        case Message::RemoveEffect:  // mixed.rs:432-439
+          for (size_t i = 0; i < effects.size(); ++i)
+            if (effects[i].first == m.id) { effects.erase(effects.begin() + i); if (effects.empty()) effects_bypassed = true; break; }
+          break;
+        case Message::MoveEffect:  // mixed.rs:440-459
+          for (size_t i = 0; i < effects.size(); ++i)
+            if (effects[i].first == m.id) {
+              auto fx = effects[i];
+              effects.erase(effects.begin() + i);
+              size_t pos;
+              if (m.movement == 0) { int32_t t = (int32_t)i + m.offset; pos = (size_t)std::min(std::max(t, 0), (int32_t)effects.size()); }
+              else if (m.movement == 1) pos = 0;
+              else pos = effects.size();
+              effects.insert(effects.begin() + pos, fx);
+              break;
+            }
+          break;
       }
     }
   }
@@ -757,6 +878,9 @@ struct MixedSource : Source {
         break;
       case MixerEvent::EffectParameter:
         for (auto& fx : effects) if (fx.first == e.target) { fx.second->effect->process_parameter_update(e.param_id, e.param); break; }
+        break;
+      case MixerEvent::EffectMessage:  // mixed.rs: ProcessEffectMessage -> Effect::process_message
+        for (auto& fx : effects) if (fx.first == e.target) { fx.second->effect->process_message(e.param_id); break; }
         break;
     }
   }

@@ -45,9 +45,14 @@ EV_ALL_NOTES_OFF = 12
 EV_SET_NOTE_SPEED = 13
 EV_SET_NOTE_VOLUME = 14
 EV_SET_NOTE_PANNING = 15
+EV_SET_GENERATOR_PARAMETER = 16
+EV_SET_GENERATOR_LOOP_RANGE = 17
 EV_SET_EFFECT_PARAMETER = 20
+EV_EFFECT_MESSAGE = 21
+MSG_REVERB_RESET = 1
+MOVE_DIRECTION, MOVE_START, MOVE_END = 0, 1, 2
 
-EVF_NORMALIZED, EVF_HAS_VOLUME, EVF_HAS_PANNING, EVF_NOTE_FROM_BATCH = 1, 2, 4, 8
+EVF_NORMALIZED, EVF_HAS_VOLUME, EVF_HAS_PANNING, EVF_NOTE_FROM_BATCH, EVF_NO_RANGE = 1, 2, 4, 8, 16
 
 
 class Config(C.Structure):
@@ -170,6 +175,11 @@ SYMBOLS = {
     "free": (None, [C.c_void_p]),
     "upload_wav": (C.c_int, [_R, C.c_char_p, _P(U32), _P(WavInfo)]),
     "render_to_wav": (C.c_int, [_R, C.c_char_p, U64, _P(U64)]),
+    "remove_source": (C.c_int, [_R, U32]),
+    "remove_mixer": (C.c_int, [_R, U32]),
+    "remove_effect": (C.c_int, [_R, U32]),
+    "move_effect": (C.c_int, [_R, U32, U32, U32, I32]),
+    "stop_all_sources": (C.c_int, [_R]),
 }
 
 

@@ -200,13 +200,21 @@ struct GroupState {
   ExpSm vol, pan;         // generator-level AmplifiedSource / PannedSource (player.rs:1075-1081)
   uint64_t voice_frames;  // statistics: active voice-frames rendered
   uint64_t dead_time;     // end of the mixer chunk in which the source was dropped (valid when dead)
+  uint32_t gp_idx;        // index of the group's CURRENT parameter version in the GroupParams array (sampler parameter automation)
+  uint32_t _pad;
 };
 
 enum EventKind : uint32_t {
   EVK_STOP = 1, EVK_SET_VOLUME = 2, EVK_SET_PANNING = 3, EVK_SET_SPEED = 4, EVK_SEEK = 5,
   EVK_NOTE_ON = 10, EVK_NOTE_OFF = 11, EVK_ALL_NOTES_OFF = 12, EVK_NOTE_SPEED = 13, EVK_NOTE_VOLUME = 14,
-  EVK_NOTE_PANNING = 15
+  EVK_NOTE_PANNING = 15,
+  // Sampler::process_parameter_update (sampler.rs:1069-1192): seek_pos = index of the parameter version that becomes current,
+  // note = what the active voices have to re-derive (PARAM_*), speed = the new pitch factor
+  EVK_SET_PARAM = 16,
+  // SamplerMessage::SetLoopRange (sampler.rs:1246-1271): seek_pos / note = first / end frame, flags bit1: None
+  EVK_SET_LOOP = 17
 };
+enum ParamClass : uint32_t { PARAM_PITCH = 0, PARAM_VOLUME = 1, PARAM_PANNING = 2, PARAM_ENVELOPE = 3 };
 
 struct DevEvent {
   uint64_t time;
@@ -217,8 +225,8 @@ struct DevEvent {
   float glide;         // <= 0: None
   uint32_t note;
   uint32_t seek_pos;   // SEEK: clamped sample index (preloaded.rs:140-143)
-  uint32_t flags;
-  uint32_t _pad;
+  uint32_t flags;      // bit0: immediate message (does not split mixer chunks), bit1: SET_LOOP without a range
+  uint32_t flags2;     // host scratch
 };
 
 // ---- mixers / effects -------------------------------------------------------------------------------

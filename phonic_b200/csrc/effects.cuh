@@ -968,6 +968,27 @@ PB_DEV bool fx_process_tail(const FxHeader& h, const FxCtx& cx, uint64_t& frames
 
 // Effect::process_parameter_update with the value already resolved to a plain value on the host
 // (normalized -> denormalized, clamped; enums -> index).
+// Effect::process_message, cooperatively by the mixer's CTA. ReverbEffectMessage::Reset (src/effect/reverb.rs:469-487):
+// flush() of the eight ReverbDelayLines (buffer only), the four allpasses and the predelay (buffer + write position).
+PB_DEV void fx_process_message(FxHeader& h, const FxCtx& cx, const uint32_t msg, const uint32_t tid, const uint32_t nt) {
+  if (h.kind != FX_REVERB || msg != 1u) return;
+  ReverbState& s = *(ReverbState*)(cx.state_arena + h.state_offset);
+  for (int l = 0; l < 8; ++l) {
+    double* b = cx.aux_arena + s.lines[l].aux;
+    for (uint32_t i = tid; i < (s.lines[l].size + 1u) * 2u; i += nt) b[i] = 0.0;
+  }
+  for (int l = 0; l < 4; ++l) {
+    double* b = cx.aux_arena + s.ap[l].aux;
+    for (uint32_t i = tid; i < s.ap[l].size * 2u; i += nt) b[i] = 0.0;
+  }
+  {
+    double* b = cx.aux_arena + s.m_aux;
+    for (uint32_t i = tid; i < (s.m_mask + 1u) * 2u; i += nt) b[i] = 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) { for (int l = 0; l < 4; ++l) s.ap[l].write_pos = 0; s.m_write_pos = 0; }
+}
+
 PB_DEV void fx_apply_param(FxHeader& h, const FxCtx& cx, const FxParamEvent& e) {
   uint8_t* st = cx.state_arena + h.state_offset;
   const uint32_t id = e.param_id;

@@ -119,13 +119,23 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
 
     if (has_fx) {
       // effect parameter events due at this chunk start (MixedSource::process_events, mixed.rs:683)
-      if (tid == 0) {
-        for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
-          FxHeader& h = a.fx[e];
-          while (h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= c0) {
-            fx_apply_param(h, a.fxc, a.fx_events[h.ev_cursor]);
-            h.ev_cursor++;
+      for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
+        FxHeader& h = a.fx[e];
+        for (;;) {  // events in order; a message (Effect::process_message) is carried out by the whole CTA
+          if (tid == 0) {
+            s_run = 0u;
+            while (h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= c0) {
+              const FxParamEvent pe = a.fx_events[h.ev_cursor];
+              h.ev_cursor++;
+              if (pe.normalized == 2u) { s_run = pe.param_id; break; }
+              fx_apply_param(h, a.fxc, pe);
+            }
           }
+          __syncthreads();
+          const uint32_t msg = s_run;
+          if (msg == 0u) break;
+          fx_process_message(h, a.fxc, msg, tid, nt);
+          __syncthreads();
         }
       }
       // audible input? (mixed.rs:701-708)

@@ -150,12 +150,16 @@ StreamWaitValue32Fn stream_wait_value32() {
 
 struct HostBuffer { DevBuffer dev; size_t cls; };
 
-struct HostEvent { DevEvent ev; uint64_t seq; };
+struct HostEvent { DevEvent ev; uint64_t seq; double raw_speed = 0.0; uint32_t param_id = 0; };  // raw_speed: before the sampler's pitch factor
 
 struct HostGroup {
   uint32_t public_id;
   GroupParams gp;
   std::vector<HostEvent> events;  // pending (not yet consumed) events, sorted at compile time
+  // automatable Sampler state (sampler.rs:79-86): base pitch + the AHDSR times the rates in `gp` were derived from
+  int32_t base_transpose = 0, base_finetune = 0;
+  pb200_ahdsr env{};
+  bool removed = false;           // MixerMessage::RemoveSource / its mixer was removed
 };
 
 struct HostFx {
@@ -168,6 +172,7 @@ struct HostMixer {
   uint32_t public_id;
   uint32_t parent;  // dense index or 0xFFFFFFFF
   uint32_t depth;
+  bool removed = false;  // MixerMessage::RemoveMixer: detached from its parent, never rendered again
   std::vector<uint32_t> children, sources, effects;
 };
 
@@ -337,6 +342,65 @@ bool resolve_ahdsr(const pb200_ahdsr& a, uint32_t sr, GroupParams& gp) {
   gp.attack_scaling = a.attack_scaling; gp.decay_scaling = a.decay_scaling; gp.release_scaling = a.release_scaling;
   gp.has_env = 1;
   return true;
+}
+
+// Duration::from_secs_f32(seconds.max(0.0)): the exact value rounded to the nearest nanosecond
+uint64_t secs_f32_to_nanos(float s) { return (uint64_t)std::nearbyint((double)std::max(s, 0.0f) * 1.0e9); }
+
+// Sampler parameter descriptors (src/generator/sampler.rs:94-183): plain value of a raw / normalized update
+// (Sampler::parameter_update_value / parameter_update_value_integer, sampler.rs:862-906). Returns false for unknown ids.
+bool sampler_param_plain(uint32_t id, float v, bool normalized, bool has_env, float& out) {
+  const float n = std::min(std::max(v, 0.0f), 1.0f);
+  auto cl = [](float x, float lo, float hi) { return std::min(std::max(x, lo), hi); };
+  if (id == pbh::cc4("STRN")) { out = normalized ? std::round(-48.0f + n * 96.0f) : (float)std::min(std::max((int32_t)v, -48), 48); return true; }
+  if (id == pbh::cc4("SFTN")) { out = normalized ? std::round(-100.0f + n * 200.0f) : (float)std::min(std::max((int32_t)v, -100), 100); return true; }
+  if (id == pbh::cc4("SVOL")) {
+    const pbh::ParamDesc d{id, 0.000001f, 15.848932f, 3, -60.0f, 24.0f};
+    out = normalized ? pbh::denormalize(d, n) : cl(v, d.min, d.max);
+    return true;
+  }
+  if (id == pbh::cc4("SPAN")) { out = normalized ? -1.0f + n * 2.0f : cl(v, -1.0f, 1.0f); return true; }
+  if (!has_env) return false;
+  if (id == pbh::cc4("AATK") || id == pbh::cc4("AHLD") || id == pbh::cc4("ADCY") || id == pbh::cc4("AREL")) {
+    out = normalized ? 0.0f + std::pow(n, 2.0f) * 10.0f : cl(v, 0.0f, 10.0f);
+    return true;
+  }
+  if (id == pbh::cc4("ASTN")) { out = normalized ? n : cl(v, 0.0f, 1.0f); return true; }
+  return false;
+}
+
+// Sampler::process_parameter_update on the host mirror of a sampler (sampler.rs:1069-1135, AhdsrParameters setters
+// ahdsr.rs:160-249). Returns which state of the sounding voices the device has to re-derive.
+uint32_t apply_sampler_param(HostGroup& g, uint32_t sr, uint32_t id, float plain) {
+  const float F32_MAX = 3.402823466e+38f;
+  GroupParams& gp = g.gp;
+  if (id == pbh::cc4("STRN")) { g.base_transpose = (int32_t)plain; return PARAM_PITCH; }
+  if (id == pbh::cc4("SFTN")) { g.base_finetune = (int32_t)plain; return PARAM_PITCH; }
+  if (id == pbh::cc4("SVOL")) { gp.base_volume = plain; return PARAM_VOLUME; }
+  if (id == pbh::cc4("SPAN")) { gp.base_panning = plain; return PARAM_PANNING; }
+  const uint64_t nanos = secs_f32_to_nanos(plain);
+  if (id == pbh::cc4("AATK")) {
+    g.env.attack_nanos = nanos;
+    const float t = nanos_as_secs_f32(nanos);
+    gp.attack_rate = t == 0.0f ? F32_MAX : 1.0f / (t * (float)sr);
+  } else if (id == pbh::cc4("AHLD")) {
+    g.env.hold_nanos = nanos;
+    gp.hold_is_zero = nanos == 0; gp.hold_samples = nanos_as_secs_f32(nanos) * (float)sr;
+  } else if (id == pbh::cc4("ADCY")) {
+    g.env.decay_nanos = nanos;
+    gp.decay_is_zero = nanos == 0;
+    gp.decay_rate = nanos == 0 ? F32_MAX : (1.0f - gp.sustain_level) / (nanos_as_secs_f32(nanos) * (float)sr);
+  } else if (id == pbh::cc4("ASTN")) {
+    g.env.sustain_level = plain; gp.sustain_level = plain;  // (the decay rate keeps the sustain level it was set with)
+  } else if (id == pbh::cc4("AREL")) {
+    g.env.release_nanos = nanos;
+    const float t = nanos_as_secs_f32(nanos);
+    gp.release_is_zero = nanos == 0; gp.release_rate = t == 0.0f ? F32_MAX : 1.0f / (t * (float)sr);
+  }
+  return PARAM_ENVELOPE;
+}
+double sampler_pitch_factor(const HostGroup& g) {  // voice.rs:144-148
+  return std::pow(2.0, (double)g.base_transpose / 12.0 + (double)g.base_finetune / 1200.0);
 }
 
 int sync_state_to_host(pb200_renderer* r) {
@@ -515,6 +579,11 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
   if (cudaStreamCreateWithFlags(&r->sv, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&r->sr_, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&r->sm, cudaStreamNonBlocking) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+  {
+    double note_speed[128];
+    for (uint32_t n = 0; n < 128; ++n) note_speed[n] = speed_from_note_h(n);
+    if (cudaMemcpyToSymbol(c_note_speed, note_speed, sizeof(note_speed)) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+  }
   r->rc.sample_rate = config->sample_rate;
   r->rc.rate_comp = 44100.0f / (float)config->sample_rate;
   HostMixer main;
@@ -818,6 +887,7 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
   g.gp.fade_out_inertia = fader_inertia(sr, 50000000ull);
   g.gp.base_volume = 1.0f; g.gp.base_panning = 0.0f;
   if (o->has_ahdsr && !resolve_ahdsr(o->ahdsr, sr, g.gp)) return fail(r, PB200_ERR_PARAMETER, "Invalid AHDSR parameters");
+  if (o->has_ahdsr) g.env = o->ahdsr;
   GranGroup gg;
   std::memset(&gg, 0, sizeof(gg));
   if (o->has_granular) {  // Sampler::with_granular_playback (sampler.rs:599-637)
@@ -875,9 +945,27 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
 int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
   if (!r || !ev) return PB200_ERR_PARAMETER;
   const bool now = ev->sample_time == PB200_TIME_NOW;
+  if (ev->kind == PB200_EV_EFFECT_MESSAGE) {  // EffectHandle::send_message (handles/effect.rs:127-163)
+    auto it = r->fx_by_id.find(ev->target);
+    if (it == r->fx_by_id.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+    HostFx& fx = r->fxs[it->second];
+    if (ev->param_id != PB200_MSG_REVERB_RESET || fx.kind != FX_REVERB) return fail(r, PB200_ERR_PARAMETER, "Invalid message for this effect");
+    FxParamEvent pe;
+    std::memset(&pe, 0, sizeof(pe));
+    pe.time = now ? 0 : ev->sample_time;
+    pe.param_id = ev->param_id;
+    pe.normalized = 2;  // a message, not a parameter update
+    fx.events.push_back(pe);
+    fx.seqs.push_back(r->next_seq++);
+    r->graph_dirty = true;
+    return PB200_OK;
+  }
   if (ev->kind == PB200_EV_SET_EFFECT_PARAMETER) {
     auto it = r->fx_by_id.find(ev->target);
     if (it == r->fx_by_id.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+    // EffectHandle::set_parameter (handles/effect.rs:72-77): a normalized update outside [0, 1] is a ParameterError
+    if ((ev->flags & PB200_EVF_NORMALIZED) && !(ev->value >= 0.0f && ev->value <= 1.0f))
+      return fail(r, PB200_ERR_PARAMETER, "Invalid parameter update: value should be a normalized value");
     HostFx& fx = r->fxs[it->second];
     const pbh::ParamDesc* desc = nullptr;
     for (auto& d : pbh::param_table(fx.kind)) if (d.id == ev->param_id) desc = &d;
@@ -903,6 +991,8 @@ int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
   std::memset(&de, 0, sizeof(de));
   de.time = now ? r->position : ev->sample_time;
   de.glide = ev->glide;
+  double raw_speed = 0.0;
+  uint32_t param_id = 0;
   switch (ev->kind) {
     case PB200_EV_STOP_SOURCE:
       if (!now) {  // MixerMessage::StopSource -> PlayingSource::stop_time (mixed.rs:388-399)
@@ -948,31 +1038,173 @@ int pb200_schedule(pb200_renderer* r, pb200_event* ev) {
       de.note = ev->note & 0xFF;
       de.value = (ev->flags & PB200_EVF_HAS_VOLUME) ? ev->value : 1.0f;
       de.value2 = (ev->flags & PB200_EVF_HAS_PANNING) ? ev->value2 : 0.0f;
-      // voice.rs:144-148: note speed * 2^(transpose/12 + finetune/1200), base transpose/finetune = 0
-      de.speed = speed_from_note_h(ev->note) * std::pow(2.0, 0.0 / 12.0 + 0.0 / 1200.0);
+      // voice.rs:144-148: note speed * 2^(transpose/12 + finetune/1200); the factor in force at the event's time is
+      // applied when the score is compiled (upload_graph)
+      raw_speed = speed_from_note_h(ev->note);
+      de.speed = raw_speed;
       break;
     case PB200_EV_NOTE_OFF: de.kind = EVK_NOTE_OFF; de.note_id = ev->note_id; break;
     case PB200_EV_ALL_NOTES_OFF: de.kind = EVK_ALL_NOTES_OFF; break;
     case PB200_EV_SET_NOTE_SPEED:
       de.kind = EVK_NOTE_SPEED; de.note_id = ev->note_id;
-      de.speed = ev->speed * std::pow(2.0, 0.0 / 12.0 + 0.0 / 1200.0);
+      raw_speed = ev->speed;
+      de.speed = raw_speed;
       break;
     case PB200_EV_SET_NOTE_VOLUME: de.kind = EVK_NOTE_VOLUME; de.note_id = ev->note_id; de.value = ev->value; break;
     case PB200_EV_SET_NOTE_PANNING: de.kind = EVK_NOTE_PANNING; de.note_id = ev->note_id; de.value = ev->value; break;
+    case PB200_EV_SET_GENERATOR_PARAMETER: {
+      if (!is_sampler) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+      if ((ev->flags & PB200_EVF_NORMALIZED) && !(ev->value >= 0.0f && ev->value <= 1.0f))
+        return fail(r, PB200_ERR_PARAMETER, "Invalid parameter update: value should be a normalized value");
+      if (std::isnan(ev->value)) return fail(r, PB200_ERR_PARAMETER, "Invalid parameter value");
+      float plain = 0.0f;
+      if (!sampler_param_plain(ev->param_id, ev->value, (ev->flags & PB200_EVF_NORMALIZED) != 0, g.gp.has_env != 0, plain))
+        return fail(r, PB200_ERR_PARAMETER, "Invalid or unknown sampler parameter");
+      de.kind = EVK_SET_PARAM; de.value = plain; param_id = ev->param_id;
+      break;
+    }
+    case PB200_EV_SET_GENERATOR_LOOP_RANGE: {
+      if (!is_sampler) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+      if (r->gran_groups[git->second].enabled) return fail(r, PB200_ERR_UNSUPPORTED, "loop range messages to granular samplers");
+      de.kind = EVK_SET_LOOP;
+      if (ev->flags & PB200_EVF_NO_RANGE) de.flags2 = 2u;
+      else {
+        const uint64_t fc = b.n_samples / b.channels;  // frame_count() includes the pad frame
+        if (ev->position_nanos >= ev->note_id || ev->position_nanos >= fc || ev->note_id > fc) return fail(r, PB200_ERR_PARAMETER, "Invalid loop range");
+        de.seek_pos = (uint32_t)std::min<uint64_t>(ev->position_nanos, 0xFFFFFFFFull);
+        de.note = (uint32_t)std::min<uint64_t>(ev->note_id, 0xFFFFFFFFull);
+      }
+      break;
+    }
     default: return fail(r, PB200_ERR_PARAMETER, "unknown event kind");
   }
   if (de.kind >= EVK_NOTE_ON && !is_sampler) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
   HostEvent he;
   he.ev = de;
   he.seq = r->next_seq++;
+  he.raw_speed = raw_speed;
+  he.param_id = param_id;
   // immediate messages do not split mixer chunks; mark them so the schedule compiler skips them
-  he.ev.flags = now ? 1u : 0u;
+  he.ev.flags = (now ? 1u : 0u) | de.flags2;
+  he.ev.flags2 = 0;
   g.events.push_back(he);
   r->graph_dirty = true;
   return PB200_OK;
 }
 
 uint64_t pb200_position(const pb200_renderer* r) { return r ? r->position : 0; }
+
+// ---- structural messages: MixedSource::process_messages runs them at the next block start = the next render call ----
+static void drop_group(pb200_renderer* r, uint32_t dense) {
+  HostGroup& g = r->groups[dense];
+  auto& v = r->mixers[g.gp.mixer].sources;
+  v.erase(std::remove(v.begin(), v.end(), dense), v.end());
+  g.removed = true;
+  g.events.clear();
+  r->h_gstate[dense].dead = 1;
+  r->h_gstate[dense].dead_time = r->position;
+  r->h_gstate[dense].ev_cursor = g.gp.ev_begin;
+  r->group_by_id.erase(g.public_id);
+}
+
+int pb200_remove_source(pb200_renderer* r, uint32_t playback_id) {
+  if (!r) return PB200_ERR_PARAMETER;
+  auto it = r->group_by_id.find(playback_id);
+  if (it == r->group_by_id.end()) return fail(r, PB200_ERR_GENERATOR_NOT_FOUND, "Generator not found");
+  if (int e = sync_state_to_host(r)) return e;
+  drop_group(r, it->second);
+  r->graph_dirty = true;
+  return PB200_OK;
+}
+
+int pb200_remove_mixer(pb200_renderer* r, uint32_t mixer_id) {
+  if (!r) return PB200_ERR_PARAMETER;
+  if (mixer_id == PB200_MAIN_MIXER) return fail(r, PB200_ERR_PARAMETER, "Cannot remove the main mixer");
+  auto it = r->mixer_by_id.find(mixer_id);
+  if (it == r->mixer_by_id.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
+  if (int e = sync_state_to_host(r)) return e;
+  const uint32_t top = it->second;
+  auto& sib = r->mixers[r->mixers[top].parent].children;
+  sib.erase(std::remove(sib.begin(), sib.end(), top), sib.end());
+  std::vector<uint32_t> gone{top};
+  for (size_t i = 0; i < gone.size(); ++i)
+    for (uint32_t ch : r->mixers[gone[i]].children) gone.push_back(ch);
+  for (uint32_t mi : gone) {
+    HostMixer& m = r->mixers[mi];
+    m.removed = true;
+    const std::vector<uint32_t> srcs = m.sources;
+    for (uint32_t gdense : srcs) drop_group(r, gdense);
+    for (uint32_t f : m.effects) r->fx_by_id.erase(r->fxs[f].public_id);
+    m.effects.clear();
+    r->mixer_by_id.erase(m.public_id);
+  }
+  r->graph_dirty = true;
+  return PB200_OK;
+}
+
+int pb200_remove_effect(pb200_renderer* r, uint32_t effect_id) {
+  if (!r) return PB200_ERR_PARAMETER;
+  auto it = r->fx_by_id.find(effect_id);
+  if (it == r->fx_by_id.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+  if (int e = sync_state_to_host(r)) return e;
+  const uint32_t dense = it->second, mi = r->fxs[dense].mixer;
+  auto& v = r->mixers[mi].effects;
+  v.erase(std::remove(v.begin(), v.end(), dense), v.end());
+  if (v.empty()) r->h_mstate[mi].effects_bypassed = 1;  // mixed.rs:436-438
+  r->fx_by_id.erase(it);
+  r->graph_dirty = true;
+  return PB200_OK;
+}
+
+int pb200_move_effect(pb200_renderer* r, uint32_t effect_id, uint32_t mixer_id, uint32_t movement, int32_t offset) {
+  if (!r) return PB200_ERR_PARAMETER;
+  auto it = r->fx_by_id.find(effect_id);
+  if (it == r->fx_by_id.end()) return fail(r, PB200_ERR_EFFECT_NOT_FOUND, "Effect not found");
+  auto mit = r->mixer_by_id.find(mixer_id);
+  if (mit == r->mixer_by_id.end() || r->fxs[it->second].mixer != mit->second) return fail(r, PB200_ERR_PARAMETER, "Effect does not belong to this mixer");
+  if (movement > PB200_MOVE_END) return fail(r, PB200_ERR_PARAMETER, "unknown effect movement");
+  if (int e = sync_state_to_host(r)) return e;
+  auto& v = r->mixers[mit->second].effects;
+  const size_t cur = std::find(v.begin(), v.end(), it->second) - v.begin();
+  const uint32_t dense = v[cur];
+  v.erase(v.begin() + cur);
+  size_t pos;
+  if (movement == PB200_MOVE_DIRECTION) pos = (size_t)std::min<int64_t>(std::max<int64_t>((int64_t)cur + offset, 0), (int64_t)v.size());
+  else if (movement == PB200_MOVE_START) pos = 0;
+  else pos = v.size();
+  v.insert(v.begin() + pos, dense);
+  r->graph_dirty = true;
+  return PB200_OK;
+}
+
+int pb200_stop_all_sources(pb200_renderer* r) {
+  if (!r) return PB200_ERR_PARAMETER;
+  if (int e = sync_state_to_host(r)) return e;
+  const uint64_t now = r->position;
+  for (size_t gi = 0; gi < r->groups.size(); ++gi) {
+    HostGroup& g = r->groups[gi];
+    if (g.removed || r->h_gstate[gi].dead) continue;
+    // MixerMessage::RemoveAllPendingEvents (mixed.rs:297-305): pending events of every source ...
+    g.events.erase(std::remove_if(g.events.begin(), g.events.end(), [&](const HostEvent& e) { return !(e.ev.flags & 1u) && e.ev.time > now; }), g.events.end());
+    if (!g.gp.transient) continue;
+    if (g.gp.start_time > now) { drop_group(r, (uint32_t)gi); continue; }  // ... and sources that have not started
+    // PlaybackMessageQueue::send_stop to every transient source; the player forgets it
+    HostEvent he;
+    std::memset(&he.ev, 0, sizeof(he.ev));
+    he.ev.time = now; he.ev.kind = EVK_STOP; he.ev.flags = 1u;
+    he.seq = r->next_seq++;
+    g.events.push_back(he);
+    r->group_by_id.erase(g.public_id);
+  }
+  for (auto& fx : r->fxs) {
+    for (size_t i = 0; i < fx.events.size();) {
+      if (fx.events[i].time > now) { fx.events.erase(fx.events.begin() + i); fx.seqs.erase(fx.seqs.begin() + i); }
+      else ++i;
+    }
+  }
+  r->graph_dirty = true;
+  return PB200_OK;
+}
 
 }  // extern "C"
 
@@ -1048,19 +1280,44 @@ int update_phase_tables(pb200_renderer* r, cudaStream_t s) {
 int upload_graph(pb200_renderer* r, Compiled& c) {
   // drop consumed events, then flatten per-group / per-effect event lists (stable by time)
   std::vector<DevEvent> events;
-  std::vector<GroupParams> gparams(r->groups.size());
-  for (size_t gi = 0; gi < r->groups.size(); ++gi) {
+  const size_t ng = r->groups.size();
+  std::vector<GroupParams> gparams(ng);   // [0, ng): every group's current parameters; behind them the versions that
+                                          // pending sampler parameter events switch to (EVK_SET_PARAM.seek_pos)
+  const uint32_t sr_out = r->cfg.sample_rate;
+  for (size_t gi = 0; gi < ng; ++gi) {
     HostGroup& g = r->groups[gi];
     uint32_t consumed = r->h_gstate[gi].ev_cursor - g.gp.ev_begin;
-    if (consumed) { g.events.erase(g.events.begin(), g.events.begin() + std::min<size_t>(consumed, g.events.size())); r->h_gstate[gi].ev_cursor = 0; }
+    if (consumed) {
+      const size_t nc = std::min<size_t>(consumed, g.events.size());
+      // parameter events the device has applied become the sampler's state (Sampler::process_parameter_update)
+      for (size_t i = 0; i < nc; ++i)
+        if (g.events[i].ev.kind == EVK_SET_PARAM && !r->h_gstate[gi].stopping) apply_sampler_param(g, sr_out, g.events[i].param_id, g.events[i].ev.value);
+      g.events.erase(g.events.begin(), g.events.begin() + nc);
+      r->h_gstate[gi].ev_cursor = 0;
+    }
     std::stable_sort(g.events.begin(), g.events.end(), [](const HostEvent& a, const HostEvent& b) { return a.ev.time < b.ev.time; });
     g.gp.ev_begin = (uint32_t)events.size();
-    for (auto& e : g.events) events.push_back(e.ev);
-    g.gp.ev_end = (uint32_t)events.size();
+    g.gp.ev_end = (uint32_t)(events.size() + g.events.size());
     gparams[gi] = g.gp;
+    // walk the score: note speeds take the pitch factor in force at their time, parameter events get their version
+    HostGroup w;      // working copy of the automatable state
+    w.public_id = g.public_id; w.gp = g.gp; w.base_transpose = g.base_transpose; w.base_finetune = g.base_finetune; w.env = g.env;
+    double factor = g.gp.kind == GROUP_SAMPLER ? sampler_pitch_factor(w) : 1.0;
+    for (auto& e : g.events) {
+      if (e.ev.kind == EVK_NOTE_ON || e.ev.kind == EVK_NOTE_SPEED) e.ev.speed = e.raw_speed * factor;
+      else if (e.ev.kind == EVK_SET_PARAM) {
+        e.ev.note = apply_sampler_param(w, sr_out, e.param_id, e.ev.value);
+        factor = sampler_pitch_factor(w);
+        e.ev.speed = factor;
+        e.ev.seek_pos = (uint32_t)gparams.size();
+        gparams.push_back(w.gp);
+      }
+      events.push_back(e.ev);
+    }
+    r->h_gstate[gi].gp_idx = (uint32_t)gi;
   }
   // GroupState::ev_cursor is absolute into the flattened array
-  for (size_t gi = 0; gi < r->groups.size(); ++gi) r->h_gstate[gi].ev_cursor = r->groups[gi].gp.ev_begin;
+  for (size_t gi = 0; gi < ng; ++gi) r->h_gstate[gi].ev_cursor = r->groups[gi].gp.ev_begin;
   std::vector<FxParamEvent> fx_events;
   for (size_t fi = 0; fi < r->fxs.size(); ++fi) {
     HostFx& fx = r->fxs[fi];
@@ -1093,20 +1350,20 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
     p.fx_begin = (uint32_t)fx_perm.size();
     for (uint32_t f : m.effects) fx_perm.push_back(f);
     p.fx_end = (uint32_t)fx_perm.size();
-    max_depth = std::max(max_depth, m.depth);
+    if (!m.removed) max_depth = std::max(max_depth, m.depth);
   }
   // permute fx headers into chain order (and remember the permutation for later syncs)
   {
     std::vector<FxHeader> nh(fx_perm.size());
     std::vector<HostFx> nf(fx_perm.size());
-    std::vector<uint32_t> inv(fx_perm.size());
+    std::vector<uint32_t> inv(r->fxs.size(), 0xFFFFFFFFu);  // (removed effects are not listed by any mixer: they drop out here)
     for (size_t i = 0; i < fx_perm.size(); ++i) { nh[i] = r->h_fx[fx_perm[i]]; nf[i] = r->fxs[fx_perm[i]]; inv[fx_perm[i]] = (uint32_t)i; }
     r->h_fx.swap(nh); r->fxs.swap(nf);
     for (auto& kv : r->fx_by_id) kv.second = inv[kv.second];
     for (auto& m : r->mixers) for (auto& f : m.effects) f = inv[f];
   }
   c.levels.assign(max_depth + 1, {});
-  for (size_t mi = 0; mi < r->mixers.size(); ++mi) c.levels[r->mixers[mi].depth].push_back((uint32_t)mi);
+  for (size_t mi = 0; mi < r->mixers.size(); ++mi) if (!r->mixers[mi].removed) c.levels[r->mixers[mi].depth].push_back((uint32_t)mi);
   std::vector<uint32_t> level_mixers;
   c.level_offsets.clear();
   for (auto& l : c.levels) { c.level_offsets.push_back((uint32_t)level_mixers.size()); for (uint32_t m : l) level_mixers.push_back(m); }
@@ -1235,7 +1492,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   if (frames == 0) { if (frames_written) *frames_written = 0; return PB200_OK; }
   cudaSetDevice(r->device);
   // WavStream finishes when the main mixer has nothing at all to do (wav.rs:231-234, mixed.rs:664-670)
-  if (r->groups.empty() && r->fxs.empty() && r->mixers.size() == 1) r->finished = true;
+  size_t live_mixers = 0, live_fx = 0;
+  for (auto& m : r->mixers) if (!m.removed) { ++live_mixers; live_fx += m.effects.size(); }
+  if (r->groups.empty() && live_fx == 0 && live_mixers == 1) r->finished = true;
   if (r->finished) {
     if (out_host) std::memset(out_host, 0, frames * 2 * sizeof(float));
     if (out_dev) CUDA_TRY(cudaMemsetAsync(out_dev, 0, frames * 2 * sizeof(float), r->sm));
@@ -1647,7 +1906,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     // playing source, effect, sub-mixer or pending event left (mixed.rs:664-670). Sources are dropped at the end of
     // the block they finished in; an event is popped by the chunk that starts at its time.
     uint64_t written = frames;
-    if (r->fxs.empty() && r->mixers.size() == 1) {
+    if (live_fx == 0 && live_mixers == 1) {
       bool all_dead = true;
       uint64_t fin = p0;
       for (size_t gi = 0; gi < gs.size(); ++gi) {

@@ -38,7 +38,7 @@ struct ReplayArgs {
 
 // All frames of one voice inside one tile: its TileRec / Segments replayed into `row` (tile-relative, interleaved stereo).
 template <int CC>
-PB_DEV void replay_voice_tile(const ReplayArgs& a, const GroupParams& gp, const DevBuffer& buf, const size_t vidx, const uint32_t tile,
+PB_DEV void replay_voice_tile(const ReplayArgs& a, const GroupParams& gp0, const uint32_t g, const DevBuffer& buf, const size_t vidx, const uint32_t tile,
                               float* __restrict__ row, float* __restrict__ win, const bool acc, const float* __restrict__ hq_row,
                               const GranReplay* __restrict__ gran, const uint32_t gran_row) {
   const uint32_t cnt = a.seg_count[vidx * a.n_tiles + tile];
@@ -48,12 +48,18 @@ PB_DEV void replay_voice_tile(const ReplayArgs& a, const GroupParams& gp, const 
   VoiceState v;
   CallCtx cc;
   HistVals hv;
+  // the parameter version of the segment at hand (sampler parameter automation): the group's own record unless an event
+  // switched versions
+  GroupParams gp_alt;
+  const GroupParams* gpp = &gp0;
+  auto use_version = [&](const uint32_t idx) { if (idx == g) gpp = &gp0; else { gp_alt = a.groups[idx]; gpp = &gp_alt; } };
   uint32_t seg_i, seg_end_i = first + cnt, seg_pos, seg_stop;
   bool simple;
   if (rec.gen == a.gen && (rec.stage_n & 0xFFFFu)) {
     // the tile opens inside a simple call: state = the call's Segment advanced by the record
     const Segment& s = segs[rec.base];
     v = s.v; cc = s.c;
+    use_version(s.gp_idx);
     seg_pos = tile * TILE; seg_stop = seg_pos + (rec.stage_n & 0xFFFFu);
     apply_tile_rec<CC>(v, cc, buf, rec, seg_pos - s.out_off);
     hist_load<CC>(hv, v, buf.data);
@@ -63,6 +69,7 @@ PB_DEV void replay_voice_tile(const ReplayArgs& a, const GroupParams& gp, const 
     seg_i = first;
     const Segment& s = segs[seg_i];
     v = s.v; cc = s.c; seg_pos = s.out_off; seg_stop = s.out_off + s.n;
+    use_version(s.gp_idx);
     hist_load<CC>(hv, v, buf.data);
     simple = !gran && simple_call_start<CC>(v, cc, buf);
     if (simple) simple_call_prologue<CC>(v, cc, hv, buf);
@@ -74,17 +81,18 @@ PB_DEV void replay_voice_tile(const ReplayArgs& a, const GroupParams& gp, const 
     float* out = row + (seg_pos - tile_lo) * 2;
     const uint32_t n = seg_stop - seg_pos;
     if (gran) {
-      for (uint32_t o = 0; o < n; o += GRAN_CHUNK) gran_replay_frames(v, cc, gp, *gran, gran_row, min(GRAN_CHUNK, n - o), out + 2 * o, acc);
+      for (uint32_t o = 0; o < n; o += GRAN_CHUNK) gran_replay_frames(v, cc, *gpp, *gran, gran_row, min(GRAN_CHUNK, n - o), out + 2 * o, acc);
     } else if (v.hq) {
       hq_replay_frames(v, cc, hq_row, a.rc.rate_comp, n, out, acc);
     } else if (simple) {
-      simple_frames<CC>(v, cc, hv, gp, buf, n, out, acc, win, REPLAY_THREADS);
+      simple_frames<CC>(v, cc, hv, *gpp, buf, n, out, acc, win, REPLAY_THREADS);
     } else {
-      voice_frames<CC, true>(v, cc, hv, gp, buf, a.rc.sample_rate, a.rc.rate_comp, n, out, acc);  // may run dry early
+      voice_frames<CC, true>(v, cc, hv, *gpp, buf, a.rc.sample_rate, a.rc.rate_comp, n, out, acc);  // may run dry early
     }
     if (++seg_i >= seg_end_i) return;
     const Segment& s = segs[seg_i];
     v = s.v; cc = s.c; seg_pos = s.out_off; seg_stop = s.out_off + s.n;
+    use_version(s.gp_idx);
     hist_load<CC>(hv, v, buf.data);
     simple = !gran && simple_call_start<CC>(v, cc, buf);
     if (simple) simple_call_prologue<CC>(v, cc, hv, buf);
@@ -111,8 +119,8 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 6) replay_kernel(ReplayArgs a)
       const size_t vidx = gp.first_voice + vi;
       const float* hq_row = a.hq_states ? a.hq_scratch + (size_t)a.hq_states[vidx].slot * a.block_frames * 2 : nullptr;
       const uint32_t gran_row = is_gran ? a.gran_groups[g].first_row + vi : 0u;
-      if (buf.channels == 2) replay_voice_tile<2>(a, gp, buf, vidx, tile, row, win, is_sampler, hq_row, gran, gran_row);
-      else replay_voice_tile<1>(a, gp, buf, vidx, tile, row, win, is_sampler, hq_row, gran, gran_row);
+      if (buf.channels == 2) replay_voice_tile<2>(a, gp, g, buf, vidx, tile, row, win, is_sampler, hq_row, gran, gran_row);
+      else replay_voice_tile<1>(a, gp, g, buf, vidx, tile, row, win, is_sampler, hq_row, gran, gran_row);
     }
     // generator-level per-sample gain / per-frame pan (AmplifiedSource / PannedSource around a Sampler, player.rs:1075-1081)
     if (is_sampler) {

@@ -60,6 +60,9 @@ struct SkeletonArgs {
 };
 
 constexpr int VK_MAX_VOICES = 1024;
+// speed_from_note (src/utils.rs:67-78) of the 128 MIDI notes, computed once on the host with the libm the reference's
+// `powf` calls go to: a sampler pitch parameter change re-derives the speed of every sounding voice from its note
+__constant__ double c_note_speed[128];
 #ifdef PB200_CYC
 // build-time cycle counters of ONE voice (debug builds only, -DPB200_CYC=<global voice index>)
 __device__ unsigned long long g_cyc[8];
@@ -478,7 +481,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
   const long long cyc_block0 = CYC_T();
   const uint32_t g = a.group_list[blockIdx.x];
   const uint32_t tid = WPV ? ((threadIdx.x & 31u) == 0 ? (threadIdx.x >> 5) : 0xFFFFu) : threadIdx.x;
-  const GroupParams gp = a.groups[g];
+  uint32_t gp_idx = a.gstate[g].gp_idx;   // the parameter version in force (== g until a parameter event arrives)
+  GroupParams gp = a.groups[gp_idx];
   const uint32_t nv = gp.n_voices;
   const DevBuffer buf = a.buffers[gp.buffer];
   const bool is_sampler = gp.kind == GROUP_SAMPLER;
@@ -573,7 +577,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
   const uint32_t CCr = buf.channels;
   auto sc_finish = [&]() {
     if (!sc.open) return;
-    sc_advance<!WPV>(sc, v, gp, a.groups + g, my_recs, a.gen, CCr, sc.end_off, true, a.prof ? prof_s + 2 : nullptr);
+    sc_advance<!WPV>(sc, v, gp, a.groups + gp_idx, my_recs, a.gen, CCr, sc.end_off, true, a.prof ? prof_s + 2 : nullptr);
     sc_close(sc, v, CCr);
   };
   // One Source::write call of this thread's voice (already opened by voice_begin_call): emits the call's
@@ -590,7 +594,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
       const uint32_t tile = call_off / TILE;
       if (!(a.debug_flags & 1u)) {
         Segment& s = my_segs[n_segs];
-        s.v = v; s.c = cc; s.out_off = call_off; s.n = min(n, (tile + 1) * TILE - call_off);
+        s.v = v; s.c = cc; s.out_off = call_off; s.n = min(n, (tile + 1) * TILE - call_off); s.gp_idx = gp_idx;
       }
       if (tile != cur_tile) {
         if (cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
@@ -605,7 +609,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
       sc.end_off = end_off;
       bool lazy = false;
       if (allow_lazy) { sc.budget = sc_steady_budget(sc, v, gp, CCr); lazy = sc.budget >= (end_off + TILE - 1u) / TILE * TILE - call_off; }
-      sc_advance<!WPV>(sc, v, gp, a.groups + g, my_recs, a.gen, CCr, end_off, !lazy, st);
+      sc_advance<!WPV>(sc, v, gp, a.groups + gp_idx, my_recs, a.gen, CCr, end_off, !lazy, st);
       if (!lazy || (sc.adv_off % TILE) != 0u) sc_close(sc, v, CCr);
       cc.produced_in_call = n; cc.call_left = 0; cc.chunk_left = 0;
       if (!sc.open) after_process_call(v, cc);  // (an open super-call cannot have reached its loop end: sc_steady_budget)
@@ -618,7 +622,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
         const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
         if (n_segs < a.seg_cap && !(a.debug_flags & 1u)) {
           Segment& s = my_segs[n_segs];
-          s.v = v; s.c = cc; s.out_off = off; s.n = seg_len;
+          s.v = v; s.c = cc; s.out_off = off; s.n = seg_len; s.gp_idx = gp_idx;
           // per-tile (first, count) live in registers and are stored when the tile changes: no global
           // load sits on this latency-critical path
           if (tile != cur_tile) {
@@ -633,7 +637,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
           gran_advance(gsp, a.gran_groups + g, a.gran, gran_row, t + (off - call_off), off, seg_len);
           w = seg_len;
           cc.chunk_left -= w; cc.hq_off += w;
-          if (gp.has_env && cc.env_per_frame) env_chain_call(v, a.groups + g, w);
+          if (gp.has_env && cc.env_per_frame) env_chain_call(v, a.groups + gp_idx, w);
         } else if (is_hq) {
           // the out-of-line HighQuality state machine works on copies: taking the address of `v` / `cc` themselves
           // would move the hot cubic path's voice state from registers to local memory
@@ -645,8 +649,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
         else {  // out of line, on copies (taking the address of `v` / `cc` themselves would move them to local memory)
           VoiceState vt = v;
           CallCtx ct = cc;
-          w = buf.channels == 2 ? voice_advance_nl<2>(&vt, &ct, a.groups + g, a.buffers + gp.buffer, out_rate, comp, seg_len)
-                                : voice_advance_nl<1>(&vt, &ct, a.groups + g, a.buffers + gp.buffer, out_rate, comp, seg_len);
+          w = buf.channels == 2 ? voice_advance_nl<2>(&vt, &ct, a.groups + gp_idx, a.buffers + gp.buffer, out_rate, comp, seg_len)
+                                : voice_advance_nl<1>(&vt, &ct, a.groups + gp_idx, a.buffers + gp.buffer, out_rate, comp, seg_len);
           v = vt; cc = ct;
         }
         written_frames += w;
@@ -708,7 +712,8 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
     if (is_sampler) {
       if (hard_idx == 0xFFFFFFFFu || hard_idx < s_gs.ev_cursor) {
         hard_idx = s_gs.ev_cursor;
-        while (hard_idx < gp.ev_end && a.events[hard_idx].kind != EVK_NOTE_ON && a.events[hard_idx].kind != EVK_STOP) ++hard_idx;
+        while (hard_idx < gp.ev_end && a.events[hard_idx].kind != EVK_NOTE_ON && a.events[hard_idx].kind != EVK_STOP &&
+               a.events[hard_idx].kind != EVK_SET_PARAM && a.events[hard_idx].kind != EVK_SET_LOOP) ++hard_idx;
         hard_time = hard_idx < gp.ev_end ? a.events[hard_idx].time : UINT64_MAX;
       }
       uint32_t run = 0;
@@ -761,7 +766,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
                 sc.end_off = r1_off;
                 unsigned long long* st = a.prof ? prof_s + 2 : nullptr;
                 const long long q0 = a.prof ? clock64() : 0;
-                sc_advance<!WPV>(sc, v, gp, a.groups + g, my_recs, a.gen, CCr, r1_off, false, st);
+                sc_advance<!WPV>(sc, v, gp, a.groups + gp_idx, my_recs, a.gen, CCr, r1_off, false, st);
                 if (a.prof) prof_s[7] += (unsigned long long)(clock64() - q0);
                 my_frames += rlen;
                 atomicAdd(&s_cnt[j], 1u);
@@ -889,6 +894,34 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
               __syncthreads();
             } else if (ev.kind == EVK_ALL_NOTES_OFF) {
               if (mine) { stop_voice(t); publish_header(s_head, tid, v); }
+              __syncthreads();
+            } else if (ev.kind == EVK_SET_PARAM) {
+              // Sampler::process_parameter_update: the version the host resolved becomes current; active voices re-derive
+              // what depends on it (voice.rs:258-310)
+              gp_idx = ev.seek_pos;
+              gp = a.groups[gp_idx];
+              if (tid == 0) s_gs.gp_idx = gp_idx;
+              if (mine && v.has_note) {
+                if (ev.note == PARAM_PITCH) {
+                  const double eff = c_note_speed[v.note & 127u] * ev.speed;
+                  file_set_speed(v, eff, 0.0f, buf.sample_rate, out_rate);
+                  if (gsp) gsp->speed = eff;
+                } else if (ev.note == PARAM_VOLUME) {
+                  exp_set_target(v.vol, gp.base_volume * v.note_volume, comp);
+                  if (gsp) gsp->volume = gp.base_volume * v.note_volume;
+                } else if (ev.note == PARAM_PANNING) {
+                  const float eff = fminf(fmaxf(gp.base_panning + v.note_panning, -1.0f), 1.0f);
+                  exp_set_target(v.pan, eff, comp);
+                  if (gsp) gsp->panning = eff;
+                }
+              }
+              __syncthreads();
+            } else if (ev.kind == EVK_SET_LOOP) {
+              if (mine) {  // SamplerVoice::set_loop_range on every voice (voice.rs:313-339)
+                const bool has = !(ev.flags & 2u);
+                v.loop_ovr_start = has ? (int32_t)ev.seek_pos : -1; v.loop_ovr_end = has ? (int32_t)ev.note : -1;
+                v.repeat = has ? REPEAT_FOREVER : 0u; v.repeat_count = v.repeat;
+              }
               __syncthreads();
             } else {
               // note-addressed events: first voice whose note_id matches (sampler.rs:776-822)

@@ -821,6 +821,8 @@ struct Segment {
   CallCtx c;
   uint32_t out_off;  // first frame, relative to the time block
   uint32_t n;        // frames requested (the replay may produce fewer when the source runs dry)
+  uint32_t gp_idx;   // the group's parameter version in force (GroupParams array index)
+  uint32_t _pad;
 };
 
 // Generator-level gain/pan checkpoint (AmplifiedSource/PannedSource around a Sampler, player.rs:1075-1081)

@@ -289,6 +289,20 @@ class GeneratorPlaybackHandle(_Handle):
     def set_note_panning(self, note_id: int, panning: float, sample_time=None):
         self._ev(A.EV_SET_NOTE_PANNING, sample_time, note_id=note_id, value=panning)
 
+    def set_parameter(self, param_id: str, value: float, sample_time=None):
+        """GeneratorPlaybackHandle::set_parameter((id, value), t): 'STRN' 'SFTN' 'SVOL' 'SPAN' 'AATK' 'AHLD' 'ADCY' 'ASTN' 'AREL'"""
+        self._ev(A.EV_SET_GENERATOR_PARAMETER, sample_time, param_id=A.fourcc(param_id), value=value)
+
+    def set_parameter_normalized(self, param_id: str, value: float, sample_time=None):
+        self._ev(A.EV_SET_GENERATOR_PARAMETER, sample_time, param_id=A.fourcc(param_id), value=value, flags=A.EVF_NORMALIZED)
+
+    def set_loop_range(self, loop_range, sample_time=None):
+        """send_message(SamplerMessage::SetLoopRange(range), t); `loop_range` = (start frame, end frame) or None"""
+        if loop_range is None:
+            self._ev(A.EV_SET_GENERATOR_LOOP_RANGE, sample_time, flags=A.EVF_NO_RANGE)
+        else:
+            self._ev(A.EV_SET_GENERATOR_LOOP_RANGE, sample_time, position_nanos=int(loop_range[0]), note_id=int(loop_range[1]))
+
     def voice_states(self, capacity: int = 1024):
         arr = (A.VoiceState * capacity)()
         n = A.U32(0)
@@ -306,6 +320,10 @@ class EffectHandle(_Handle):
     def set_parameter_normalized(self, param_id: str, value: float, sample_time=None):
         self._ev(A.EV_SET_EFFECT_PARAMETER, sample_time, param_id=A.fourcc(param_id), value=value,
                  flags=A.EVF_NORMALIZED)
+
+    def send_message(self, message: int, sample_time=None):
+        """EffectHandle::send_message (handles/effect.rs:127-163); message = _capi.MSG_REVERB_RESET"""
+        self._ev(A.EV_EFFECT_MESSAGE, sample_time, param_id=message)
 
 
 class MixerHandle:
@@ -411,6 +429,27 @@ class Player:
         mid = A.U32()
         self._check(self.api.add_mixer(self._r, parent_mixer_id or A.MAIN_MIXER, C.byref(mid)))
         return MixerHandle(mid.value)
+
+    def remove_mixer(self, mixer_id: int):
+        """Player::remove_mixer (src/player.rs:825-868)"""
+        self._check(self.api.remove_mixer(self._r, mixer_id))
+
+    def remove_generator(self, playback_id: int):
+        """Player::remove_generator (src/player.rs:747-770)"""
+        self._check(self.api.remove_source(self._r, playback_id))
+
+    def remove_effect(self, effect_id: int):
+        """Player::remove_effect (src/player.rs:977-991)"""
+        self._check(self.api.remove_effect(self._r, effect_id))
+
+    def move_effect(self, movement, effect_id: int, mixer_id: Optional[int] = None):
+        """Player::move_effect (src/player.rs:942-974); movement = 'start' | 'end' | int offset (EffectMovement)"""
+        kind, off = (A.MOVE_START, 0) if movement == "start" else (A.MOVE_END, 0) if movement == "end" else (A.MOVE_DIRECTION, int(movement))
+        self._check(self.api.move_effect(self._r, effect_id, mixer_id or A.MAIN_MIXER, kind, off))
+
+    def stop_all_sources(self):
+        """Player::stop_all_sources (src/player.rs:1012-1045)"""
+        self._check(self.api.stop_all_sources(self._r))
 
     def add_effect(self, effect, mixer_id: Optional[int] = None) -> EffectHandle:
         eid = A.U32()
