@@ -361,6 +361,35 @@ typedef struct pb200_source_status {
 PB200_API int pb200_source_status_get(pb200_renderer *r, uint32_t playback_id,
                                       pb200_source_status *st);
 
+/* ---- observability: the PlaybackStatusEvent stream and the main mixer's level meter --------------------
+ * PlaybackStatusEvent (src/source/status.rs:15-36) of file playbacks, in emission order: Position every second of output
+ * time, reported at the end of the source's write call (FileSourceImpl::send_playback_position_status,
+ * src/source/file/common.rs:171-208; FilePlaybackOptions' default playback_pos_emit_rate of 1 s), and Stopped when the
+ * source finishes (preloaded.rs:196-209, 464-472). pb200_poll_status hands out and clears what the render calls so far
+ * produced. */
+enum pb200_status_kind { PB200_STATUS_POSITION = 0, PB200_STATUS_STOPPED = 1 };
+typedef struct pb200_status_event {
+  uint64_t frame;          /* output frame of the write call that emitted the event (its start; Stopped: its end) */
+  uint32_t kind;           /* pb200_status_kind */
+  uint32_t playback_id;
+  uint64_t position_nanos; /* Position: Duration::from_secs_f64(playback frame / file rate).as_nanos() */
+  uint32_t exhausted;      /* Stopped: played to its end (true) or was stopped (false) */
+  uint32_t reserved;
+} pb200_status_event;
+PB200_API int pb200_poll_status(pb200_renderer *r, pb200_status_event *out, uint32_t capacity, uint32_t *count);
+
+/* PlayerConfig::metering_interval + Player::audio_level (src/player.rs:166,216,464-471): MeteredSource around the main
+ * mixer (src/source/metered.rs:107-148) -- per-channel peak and RMS of the main mixer's output, published whenever a
+ * 1024-frame block starts `interval` or more after the last publication. PB200_DURATION_NONE switches metering off
+ * (the default). On the device the per-block peak / sum of squares is a reduction fused into the main mixer's last
+ * kernel. */
+typedef struct pb200_audio_level {
+  float peak[2];
+  float rms[2];
+} pb200_audio_level;
+PB200_API int pb200_set_metering_interval(pb200_renderer *r, uint64_t interval_nanos);
+PB200_API int pb200_get_audio_level(pb200_renderer *r, pb200_audio_level *out);
+
 /* Voice-level introspection used by the parity tests: bit-exact integer state of every sampler
  * voice after the last render call (note id or UINT64_MAX, playback_pos sample index). */
 typedef struct pb200_voice_state {

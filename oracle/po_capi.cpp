@@ -31,6 +31,9 @@
 #define pb200_remove_effect po_remove_effect
 #define pb200_move_effect po_move_effect
 #define pb200_stop_all_sources po_stop_all_sources
+#define pb200_poll_status po_poll_status
+#define pb200_set_metering_interval po_set_metering_interval
+#define pb200_get_audio_level po_get_audio_level
 #include "../include/phonic_b200.h"
 
 #include <chrono>
@@ -61,6 +64,14 @@ struct pb200_renderer {
   std::vector<float> block;
   double last_ms = 0;
   uint64_t last_voice_frames = 0;
+  // observability: PlaybackStatusEvent stream (file sources push into `raw_status`) + MeteredSource of the main mixer
+  std::vector<PreloadedFileSource::StatusEv> raw_status;
+  std::vector<pb200_status_event> status_events;
+  std::map<uint32_t, std::pair<uint32_t, uint32_t>> status_file_format;  // playback id -> (channels, rate) of its buffer
+  uint64_t meter_interval = UINT64_MAX, meter_clock = 0, meter_frames = 0;
+  float meter_peak_hold[2] = {0, 0};
+  double meter_sum_square[2] = {0, 0};
+  pb200_audio_level audio_level{};
 };
 
 static int fail(pb200_renderer* r, int code, const std::string& msg) {
@@ -251,6 +262,7 @@ int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_opti
   pb200_renderer::SourceRef ref;
   ref.mixer = o->target_mixer;
   ref.file = fs.get();
+  fs->status_sink = &r->raw_status; fs->pos_emit_rate = r->cfg.sample_rate;  // FilePlaybackOptions::default(): 1 s (file.rs:110)
   ref.queues.file = fs->queue;
   // ConvertedSource (converted.rs:15-46): file already runs at the output rate -> channel mapping only
   std::unique_ptr<Source> src = std::move(fs);
@@ -260,6 +272,8 @@ int pb200_play_file(pb200_renderer* r, uint32_t buffer_id, const pb200_file_opti
   auto pan = std::make_unique<PannedSource>(std::move(amp), o->panning);
   ref.queues.panning = pan->queue;
   uint32_t id = r->next_source_id++;
+  ref.file->status_id = id;
+  r->status_file_format[id] = {(uint32_t)r->buffers[buffer_id]->channel_count, r->buffers[buffer_id]->sample_rate};
   auto ps = std::make_shared<MixedSource::PlayingSource>();
   ps->is_transient = true; ps->playback_id = id; ps->queues = ref.queues; ps->source = std::move(pan);
   ps->start_time = start_time == PB200_TIME_NOW ? 0 : start_time;
@@ -520,6 +534,23 @@ int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frame
     SourceTime time{r->playback_pos / ch};
     size_t written = r->main->write(r->block.data(), r->block.size(), time);
     if (written == 0) { r->finished = true; break; }
+    if (r->meter_interval != UINT64_MAX) {  // MeteredSource::write -> AudioLevelState::record (metered.rs:107-148)
+      for (size_t i = 0; i + 1 < written; i += 2)
+        for (int c = 0; c < 2; ++c) {
+          const float x = r->block[i + c];
+          if (std::fabs(x) > r->meter_peak_hold[c]) r->meter_peak_hold[c] = std::fabs(x);
+          r->meter_sum_square[c] += (double)x * (double)x;
+        }
+      r->meter_frames += written / 2;
+      if (time.pos_in_frames - std::min(time.pos_in_frames, r->meter_clock) >= r->meter_interval) {
+        for (int c = 0; c < 2; ++c) {
+          r->audio_level.peak[c] = r->meter_peak_hold[c];
+          r->audio_level.rms[c] = r->meter_frames ? (float)std::sqrt(r->meter_sum_square[c] / (double)r->meter_frames) : 0.0f;
+          r->meter_peak_hold[c] = 0; r->meter_sum_square[c] = 0;
+        }
+        r->meter_clock = time.pos_in_frames; r->meter_frames = 0;
+      }
+    }
     apply_smoothed_gain(r->block.data(), written, r->smoothed_volume);
     std::memcpy(out + done * ch, r->block.data(), written * sizeof(float));
     r->playback_pos += r->block.size();
@@ -527,7 +558,49 @@ int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frame
   }
   if (done < frames) std::memset(out + done * ch, 0, (frames - done) * ch * sizeof(float));
   if (frames_written) *frames_written = done;
+  {  // PlaybackStatusEvent stream in a canonical order (frame, playback id, kind)
+    auto& raw = r->raw_status;
+    std::stable_sort(raw.begin(), raw.end(), [](const PreloadedFileSource::StatusEv& a, const PreloadedFileSource::StatusEv& b) {
+      if (a.frame != b.frame) return a.frame < b.frame;
+      if (a.id != b.id) return a.id < b.id;
+      return a.kind < b.kind;
+    });
+    for (auto& e : raw) {
+      pb200_status_event o;
+      std::memset(&o, 0, sizeof(o));
+      o.frame = e.frame; o.playback_id = e.id;
+      if (e.kind == 0) {
+        auto fmt = r->status_file_format[e.id];
+        o.kind = PB200_STATUS_POSITION;
+        o.position_nanos = (uint64_t)std::nearbyint(((double)(e.pos / fmt.first) / (double)fmt.second) * 1.0e9);
+      } else { o.kind = PB200_STATUS_STOPPED; o.exhausted = e.kind == 1; }
+      r->status_events.push_back(o);
+    }
+    raw.clear();
+  }
   r->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return PB200_OK;
+}
+
+int pb200_poll_status(pb200_renderer* r, pb200_status_event* out, uint32_t capacity, uint32_t* count) {
+  if (!r || !count || (!out && capacity)) return PB200_ERR_PARAMETER;
+  const uint32_t n = (uint32_t)std::min<size_t>(capacity, r->status_events.size());
+  for (uint32_t i = 0; i < n; ++i) out[i] = r->status_events[i];
+  r->status_events.erase(r->status_events.begin(), r->status_events.begin() + n);
+  *count = n;
+  return PB200_OK;
+}
+
+int pb200_set_metering_interval(pb200_renderer* r, uint64_t interval_nanos) {
+  if (!r) return PB200_ERR_PARAMETER;
+  r->meter_interval = interval_nanos == PB200_DURATION_NONE ? UINT64_MAX : (uint64_t)(Duration::from_nanos(interval_nanos).as_secs_f64() * (double)r->cfg.sample_rate);
+  return PB200_OK;
+}
+
+int pb200_get_audio_level(pb200_renderer* r, pb200_audio_level* out) {
+  if (!r || !out) return PB200_ERR_PARAMETER;
+  if (r->meter_interval == UINT64_MAX) return fail(r, PB200_ERR_PARAMETER, "metering is off (PlayerConfig::metering_interval is None)");
+  *out = r->audio_level;
   return PB200_OK;
 }
 

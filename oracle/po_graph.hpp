@@ -86,6 +86,11 @@ struct PreloadedFileSource : Source {
   bool playback_pos_eof = false;
   bool has_loop_override = false; uint64_t loop_override_start = 0, loop_override_end = 0;
   uint64_t end_frame = UINT64_MAX;  // oracle-side bookkeeping for status queries
+  // PlaybackStatusEvent sink (file/common.rs:171-221): null for sampler voices; events are (frame, kind, pos)
+  struct StatusEv { uint64_t frame; uint32_t kind; uint64_t pos; uint32_t id; };
+  std::vector<StatusEv>* status_sink = nullptr;
+  uint32_t status_id = 0; uint64_t pos_emit_rate = 0, pos_clock = 0, msg_frame = 0;
+  void send_stopped(uint64_t frame) { if (status_sink) status_sink->push_back({frame, playback_pos_eof ? 1u : 2u, playback_pos, status_id}); }
   bool stopped_exhausted = false;
 
   static constexpr size_t SPEED_UPDATE_CHUNK_SIZE = 64;
@@ -163,10 +168,10 @@ struct PreloadedFileSource : Source {
   void stop() {  // preloaded.rs:196-209
     if (!is_exhausted()) {
       if (has_fade_out && !fade_out_duration.is_zero()) volume_fader.start_fade_out(fade_out_duration);
-      else { stopped_exhausted = playback_pos_eof; playback_finished = true; }
+      else { stopped_exhausted = playback_pos_eof; playback_finished = true; send_stopped(msg_frame); }
     }
   }
-  void kill() { if (!is_exhausted()) { stopped_exhausted = playback_pos_eof; playback_finished = true; } }
+  void kill() { if (!is_exhausted()) { stopped_exhausted = playback_pos_eof; playback_finished = true; send_stopped(msg_frame); } }
   void reset() {  // preloaded.rs:212-230
     if (!is_exhausted()) kill();
     playback_pos = 0;
@@ -232,6 +237,7 @@ struct PreloadedFileSource : Source {
     return written;
   }
   size_t write(float* out, size_t len, const SourceTime& time) override {  // preloaded.rs:396-475
+    msg_frame = time.pos_in_frames;
     process_messages();
     if (playback_finished) return 0;
     size_t total = 0;
@@ -252,11 +258,17 @@ struct PreloadedFileSource : Source {
       total = write_buffer(out, len);
     }
     volume_fader.process(out, total);
+    // send_playback_position_status (file/common.rs:183-208): once per emit interval, at the end of a write call
+    if (status_sink && pos_emit_rate && time.pos_in_frames - std::min(time.pos_in_frames, pos_clock) >= pos_emit_rate) {
+      pos_clock = time.pos_in_frames;
+      status_sink->push_back({time.pos_in_frames, 0u, playback_pos, status_id});
+    }
     bool fade_out_completed = volume_fader.state == VolumeFader::Finished && volume_fader.target_volume == 0.0f;
     if (playback_pos_eof || fade_out_completed) {
       stopped_exhausted = playback_pos_eof;
       playback_finished = true;
       end_frame = time.pos_in_frames + len / output_channel_count;
+      send_stopped(end_frame);
     }
     return total;
   }

@@ -146,6 +146,14 @@ class RenderStats(C.Structure):
 # every symbol include/phonic_b200.h declares: name -> (restype, argtypes)
 _P = C.POINTER
 _R = C.c_void_p
+class StatusEvent(C.Structure):
+    _fields_ = [("frame", U64), ("kind", U32), ("playback_id", U32), ("position_nanos", U64), ("exhausted", U32), ("reserved", U32)]
+
+
+class AudioLevel(C.Structure):
+    _fields_ = [("peak", F32 * 2), ("rms", F32 * 2)]
+
+
 class WavInfo(C.Structure):
     _fields_ = [("frames", U64), ("channels", U32), ("sample_rate", U32), ("loop_start", I64), ("loop_end", I64),
                 ("bits_per_sample", U32), ("is_float", U32)]
@@ -180,6 +188,9 @@ SYMBOLS = {
     "remove_effect": (C.c_int, [_R, U32]),
     "move_effect": (C.c_int, [_R, U32, U32, U32, I32]),
     "stop_all_sources": (C.c_int, [_R]),
+    "poll_status": (C.c_int, [_R, _P(StatusEvent), U32, _P(U32)]),
+    "set_metering_interval": (C.c_int, [_R, U64]),
+    "get_audio_level": (C.c_int, [_R, _P(AudioLevel)]),
 }
 
 

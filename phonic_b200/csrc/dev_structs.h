@@ -43,6 +43,7 @@ struct VoiceState {
   uint64_t note_id;            // SamplerVoice::note_id (valid when has_note)
   uint64_t release_start;      // SamplerVoice::release_start_frame
   uint64_t end_frame;          // output frame at which playback finished (status only)
+  uint64_t pos_clock;          // FileSourceImpl::playback_pos_sample_time_clock: output frame of the last Position event
   uint32_t playback_pos;       // sample index into the buffer
   uint32_t repeat, repeat_count;
   int32_t loop_ovr_start, loop_ovr_end;  // loop_range_override in frames, -1 = None
@@ -169,6 +170,9 @@ struct GrainCarry {
 };
 
 enum GroupKind : uint32_t { GROUP_SAMPLER = 0, GROUP_FILE = 1 };
+
+// PlaybackStatusEvent of a file playback as the skeleton pass records it (src/source/status.rs:15-36)
+struct StatusRec { uint64_t frame; uint64_t pos; uint32_t group; uint32_t kind; };  // kind: 0 Position, 1 Stopped (exhausted), 2 Stopped
 
 struct GroupParams {
   uint32_t kind;

@@ -39,6 +39,8 @@ struct MixerKernelArgs {
   ExpSm* master;                  // WavStream::smoothed_volume
   uint32_t wav_block_frames;      // 1024
   uint32_t work_bytes;            // dynamic shared memory of this launch (FX_WORK_SMALL unless a mixer of the level holds a reverb)
+  double* meter;                  // main mixer: [wav block of the render][peak L, peak R, sum of squares L, R] or nullptr (MeteredSource)
+  uint64_t render_start;          // first frame of the render call (meter rows count from it)
   unsigned long long* prof;       // PB200_FX_PROF: [8] cycle counters of the main mixer's CTA (debug aid)
 };
 
@@ -222,6 +224,23 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
         const uint32_t o0 = (uint32_t)(wb0 - a.block_start);
         const uint32_t wl = (uint32_t)(c1 - wb0);
         float* wbuf = bus + (size_t)o0 * 2;
+        if (a.meter) {  // MeteredSource::record of this block (metered.rs:107-128): per-channel peak and sum of squares
+          __syncthreads();
+          float pk = 0.0f;
+          double sq = 0.0;
+          // thread parity == channel: a thread only ever sees samples of one channel
+          for (uint32_t i = tid; i < wl * 2; i += nt) { const float x = wbuf[i]; pk = fmaxf(pk, fabsf(x)); sq += (double)x * (double)x; }
+          for (int o = 16; o >= 2; o >>= 1) { pk = fmaxf(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o)); sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o); }
+          if (lane < 2) { s_scratch[0][warp * 4 + lane] = (double)pk; s_scratch[0][warp * 4 + 2 + lane] = sq; }
+          __syncthreads();
+          if (tid < 2) {
+            double p2 = 0.0, s2 = 0.0;
+            for (uint32_t w = 0; w < nt / 32; ++w) { p2 = fmax(p2, s_scratch[0][w * 4 + tid]); s2 += s_scratch[0][w * 4 + 2 + tid]; }
+            double* row = a.meter + ((wb0 - a.render_start) / a.wav_block_frames) * 4;
+            row[tid] = p2; row[2 + tid] = s2;
+          }
+          __syncthreads();
+        }
         ExpSm ms = *a.master;
         const bool ramp = exp_need_ramp(ms, a.fxc.comp);
         __syncthreads();

@@ -266,6 +266,16 @@ struct pb200_renderer {
   ExpSm h_master;
   bool master_uploaded = false;
 
+  // observability: PlaybackStatusEvent stream + MeteredSource state of the main mixer
+  DevVec<StatusRec> d_status;
+  DevVec<uint32_t> d_status_count;
+  std::vector<pb200_status_event> status_events;
+  DevVec<double> d_meter;
+  uint64_t meter_interval = UINT64_MAX;     // frames; UINT64_MAX = metering off
+  uint64_t meter_clock = 0, meter_frames = 0;
+  float meter_peak_hold[2] = {0.0f, 0.0f};
+  double meter_sum_square[2] = {0.0, 0.0};
+  pb200_audio_level audio_level{};
   uint64_t position = 0;  // frames
   bool finished = false;
   uint32_t time_block = 32768;
@@ -608,7 +618,7 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sr_) cudaStreamSynchronize(r->sr_);
   if (r->sm) cudaStreamSynchronize(r->sm);
   for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
-  r->d_block_done.free(); r->d_phase_tabs.free(); r->d_phase_dir.free(); r->d_phase_new.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
+  r->d_status.free(); r->d_status_count.free(); r->d_meter.free(); r->d_block_done.free(); r->d_phase_tabs.free(); r->d_phase_dir.free(); r->d_phase_new.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
   r->d_gran_groups.free(); r->d_gran_states.free(); r->d_grain_recs.free(); r->d_gran_counters.free(); r->d_gran_vrec.free();
   r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry[0].free(); r->d_grain_carry[1].free(); r->d_grain_luts.free();
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
@@ -1645,6 +1655,22 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(cudaMemset(prof_buf, 0, nvoices * 12 * sizeof(unsigned long long)));
   }
 
+  // PlaybackStatusEvent records of the file playbacks: a Position per second of output + a Stopped each
+  uint32_t n_file_groups = 0;
+  for (auto& g : r->groups) if (g.gp.kind == GROUP_FILE && !g.removed) ++n_file_groups;
+  const uint32_t pos_rate = r->cfg.sample_rate;  // FilePlaybackOptions::default().playback_pos_emit_rate = 1 s (file.rs:110)
+  const uint32_t status_cap = n_file_groups ? n_file_groups * (uint32_t)(frames / pos_rate + 4) : 0u;
+  if (status_cap) {
+    CUDA_TRY(r->d_status.reserve(status_cap));
+    CUDA_TRY(r->d_status_count.reserve(1));
+    CUDA_TRY(cudaMemsetAsync(r->d_status_count.p, 0, sizeof(uint32_t), r->sv));
+  }
+  const bool metering = r->meter_interval != UINT64_MAX;
+  const size_t meter_rows = (size_t)(frames / bf);
+  if (metering) {
+    CUDA_TRY(r->d_meter.reserve(meter_rows * 4));
+    CUDA_TRY(cudaMemsetAsync(r->d_meter.p, 0, meter_rows * 4 * sizeof(double), r->sm));
+  }
   unsigned long long* fx_prof = nullptr;
   if (getenv("PB200_FX_PROF")) { CUDA_TRY(cudaMalloc((void**)&fx_prof, 64)); CUDA_TRY(cudaMemset(fx_prof, 0, 64)); }
   for (uint32_t b = 0; b < n_blocks; ++b) {
@@ -1693,6 +1719,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       CUDA_TRY(cudaMemsetAsync(va.gran.tile_range, 0xFF, (size_t)n_rows * n_tiles * 2 * sizeof(uint32_t), r->sv));
     }
     va.phase_tabs = r->d_phase_tabs.p; va.phase_dir = r->d_phase_dir.p; va.n_phase = (uint32_t)r->phase_off.size();
+    va.status = status_cap ? r->d_status.p : nullptr; va.status_count = r->d_status_count.p; va.status_cap = status_cap; va.pos_emit_rate = pos_rate;
     va.prof = prof_buf;
     va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
     SkeletonLoop sl;
@@ -1802,6 +1829,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ma.max_chunks = max_chunks; ma.block_frames = tb; ma.block_start = b0;
     ma.out = dout + (size_t)(b0 - p0) * 2; ma.master = r->d_master.p; ma.wav_block_frames = bf;
     ma.block_len = blen;
+    ma.meter = metering ? r->d_meter.p : nullptr; ma.render_start = p0;
     ma.prof = fx_prof;
     for (int lvl = (int)c.levels.size() - 1; lvl >= 0 && !skel_only; --lvl) {
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
@@ -1891,6 +1919,32 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
         return fail(r, PB200_ERR_CUDA, "granular record list / grain storage overflowed");
     for (uint32_t b = 0; b < n_blocks; ++b) r->stats.grain_samples += counts[2 * b + 1];
   }
+  if (status_cap) {  // PlaybackStatusEvent stream, in emission order (frame, then the mixer's source order ~ id)
+    uint32_t n = 0;
+    CUDA_TRY(cudaMemcpy(&n, r->d_status_count.p, sizeof(n), cudaMemcpyDeviceToHost));
+    if (n > status_cap) return fail(r, PB200_ERR_CUDA, "status event list overflowed");
+    std::vector<StatusRec> recs(n);
+    if (n) CUDA_TRY(cudaMemcpy(recs.data(), r->d_status.p, n * sizeof(StatusRec), cudaMemcpyDeviceToHost));
+    std::sort(recs.begin(), recs.end(), [&](const StatusRec& a, const StatusRec& b) {
+      if (a.frame != b.frame) return a.frame < b.frame;
+      if (a.group != b.group) return r->groups[a.group].public_id < r->groups[b.group].public_id;
+      return a.kind < b.kind;
+    });
+    for (const StatusRec& sr : recs) {
+      pb200_status_event e;
+      std::memset(&e, 0, sizeof(e));
+      const DevBuffer& b = r->buffers[r->groups[sr.group].gp.buffer].dev;
+      e.frame = sr.frame; e.playback_id = r->groups[sr.group].public_id;
+      if (sr.kind == 0) {
+        e.kind = PB200_STATUS_POSITION;
+        const double second_pos = (double)(sr.pos / b.channels) / (double)b.sample_rate;   // file/common.rs:195-196
+        e.position_nanos = (uint64_t)std::nearbyint(second_pos * 1.0e9);
+      } else {
+        e.kind = PB200_STATUS_STOPPED; e.exhausted = sr.kind == 1;
+      }
+      r->status_events.push_back(e);
+    }
+  }
   r->host_state_valid = false;
   r->position = p1;
   // statistics + event cursors come back with the (small) group state
@@ -1924,6 +1978,26 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
             if (out_host) std::memset(out_host + written * 2, 0, (frames - written) * 2 * sizeof(float));
             if (out_dev) { CUDA_TRY(cudaMemsetAsync(out_dev + written * 2, 0, (frames - written) * 2 * sizeof(float), r->sm)); CUDA_TRY(cudaStreamSynchronize(r->sm)); }
           }
+        }
+      }
+    }
+    if (metering) {  // AudioLevelState::record per WavStream block (metered.rs:107-148) from the device's per-block reductions
+      std::vector<double> rows(meter_rows * 4);
+      CUDA_TRY(cudaMemcpy(rows.data(), r->d_meter.p, rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (size_t bi = 0; bi < std::min<size_t>(meter_rows, (size_t)(written / bf)); ++bi) {  // (blocks the stream really wrote)
+        const uint64_t t = p0 + bi * bf;
+        for (int c2 = 0; c2 < 2; ++c2) {
+          r->meter_peak_hold[c2] = std::max(r->meter_peak_hold[c2], (float)rows[bi * 4 + c2]);
+          r->meter_sum_square[c2] += rows[bi * 4 + 2 + c2];
+        }
+        r->meter_frames += bf;
+        if (t - std::min(t, r->meter_clock) >= r->meter_interval) {
+          for (int c2 = 0; c2 < 2; ++c2) {
+            r->audio_level.peak[c2] = r->meter_peak_hold[c2];
+            r->audio_level.rms[c2] = r->meter_frames ? (float)std::sqrt(r->meter_sum_square[c2] / (double)r->meter_frames) : 0.0f;
+            r->meter_peak_hold[c2] = 0.0f; r->meter_sum_square[c2] = 0.0;
+          }
+          r->meter_clock = t; r->meter_frames = 0;
         }
       }
     }
@@ -2033,6 +2107,29 @@ int pb200_sampler_voice_states(pb200_renderer* r, uint32_t id, pb200_voice_state
     out[i].active = v.has_note;
   }
   *count = g.gp.n_voices;
+  return PB200_OK;
+}
+
+int pb200_poll_status(pb200_renderer* r, pb200_status_event* out, uint32_t capacity, uint32_t* count) {
+  if (!r || !count || (!out && capacity)) return PB200_ERR_PARAMETER;
+  const uint32_t n = (uint32_t)std::min<size_t>(capacity, r->status_events.size());
+  for (uint32_t i = 0; i < n; ++i) out[i] = r->status_events[i];
+  r->status_events.erase(r->status_events.begin(), r->status_events.begin() + n);
+  *count = n;
+  return PB200_OK;
+}
+
+int pb200_set_metering_interval(pb200_renderer* r, uint64_t interval_nanos) {
+  if (!r) return PB200_ERR_PARAMETER;
+  // SampleTimeClock::duration_to_sample_time (utils/time.rs:28-35)
+  r->meter_interval = interval_nanos == PB200_DURATION_NONE ? UINT64_MAX : (uint64_t)(nanos_as_secs_f64(interval_nanos) * (double)r->cfg.sample_rate);
+  return PB200_OK;
+}
+
+int pb200_get_audio_level(pb200_renderer* r, pb200_audio_level* out) {
+  if (!r || !out) return PB200_ERR_PARAMETER;
+  if (r->meter_interval == UINT64_MAX) return fail(r, PB200_ERR_PARAMETER, "metering is off (PlayerConfig::metering_interval is None)");
+  *out = r->audio_level;
   return PB200_OK;
 }
 

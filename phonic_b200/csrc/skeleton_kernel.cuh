@@ -51,6 +51,11 @@ struct SkeletonArgs {
   const GranGroup* gran_groups;       // [n_groups] or nullptr when the graph has no granular sampler
   GranState* gran_states;             // [n_gran_rows]
   GranEmit gran;
+  // PlaybackStatusEvent stream of file playbacks (nullptr: nobody listens)
+  StatusRec* status;
+  uint32_t* status_count;
+  uint32_t status_cap;
+  uint32_t pos_emit_rate;            // frames between Position events (1 s)
   // exact 64-frame phase jumps (phase_table.cuh): one table per steady ratio of the graph, directory sorted by ratio bits
   const uint32_t* phase_tabs;
   const uint2* phase_dir;             // (f32 bits of the ratio, word offset of its table)
@@ -853,6 +858,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
       // ---- Source::write(n frames at time t) -------------------------------------------------------
       // 1. messages in queue order: the events process_events pushed at this chunk's start (consumed by
       //    the first write call of the chunk), then a Stop the mixer force-pushed at stop_time.
+      const bool file_was_finished = !is_sampler && mine && v.finished;   // (before this call's messages)
       uint32_t ev_end_now = s_gs.ev_cursor;
       while (ev_end_now < gp.ev_end && a.events[ev_end_now].time <= c0) ++ev_end_now;
       for (uint32_t e = s_gs.ev_cursor; e < ev_end_now; ++e) {
@@ -982,6 +988,14 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
       // 3. advance the voice through the call, one segment per (call x 64-frame tile)
       uint32_t written_frames = 0;
       if (call_open) written_frames = run_call(cc, n, call_off, t, false);
+      if (!is_sampler && mine && a.status) {  // PlaybackStatusEvent (file/common.rs:171-221, preloaded.rs:196-209,454-472)
+        auto emit = [&](const uint32_t kind, const uint64_t frame) {
+          const uint32_t i = atomicAdd(a.status_count, 1u);
+          if (i < a.status_cap) { StatusRec sr; sr.frame = frame; sr.pos = v.playback_pos; sr.group = g; sr.kind = kind; a.status[i] = sr; }
+        };
+        if (call_open && t - min(t, v.pos_clock) >= a.pos_emit_rate) { v.pos_clock = t; emit(0u, t); }
+        if (v.finished && !file_was_finished) emit(v.stopped_exhausted ? 1u : 2u, call_open ? t + n : t);
+      }
       if (is_sampler && group_writes && tid == 0) group_call(n, call_off);
       uint32_t written;
       if (is_sampler) {

@@ -447,6 +447,24 @@ class Player:
         kind, off = (A.MOVE_START, 0) if movement == "start" else (A.MOVE_END, 0) if movement == "end" else (A.MOVE_DIRECTION, int(movement))
         self._check(self.api.move_effect(self._r, effect_id, mixer_id or A.MAIN_MIXER, kind, off))
 
+    def poll_status(self, capacity: int = 4096):
+        """PlaybackStatusEvent stream (src/source/status.rs): [(frame, 'position', id, nanos) | (frame, 'stopped', id, exhausted)]"""
+        buf = (A.StatusEvent * capacity)()
+        n = A.U32()
+        self._check(self.api.poll_status(self._r, buf, capacity, C.byref(n)))
+        return [(e.frame, "position", e.playback_id, e.position_nanos) if e.kind == 0 else (e.frame, "stopped", e.playback_id, bool(e.exhausted))
+                for e in buf[:n.value]]
+
+    def set_metering_interval(self, seconds: Optional[float]):
+        """PlayerConfig::metering_interval (src/player.rs:166,216)"""
+        self._check(self.api.set_metering_interval(self._r, A.DURATION_NONE if seconds is None else int(round(seconds * 1e9))))
+
+    def audio_level(self):
+        """Player::audio_level (src/player.rs:464-471): ((peak L, peak R), (rms L, rms R)) of the main mixer's output"""
+        lv = A.AudioLevel()
+        self._check(self.api.get_audio_level(self._r, C.byref(lv)))
+        return tuple(lv.peak), tuple(lv.rms)
+
     def stop_all_sources(self):
         """Player::stop_all_sources (src/player.rs:1012-1045)"""
         self._check(self.api.stop_all_sources(self._r))

@@ -244,6 +244,24 @@ pub struct pb200_render_stats {
     pub grain_samples: u64,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct pb200_status_event {
+    pub frame: u64,
+    pub kind: u32,
+    pub playback_id: u32,
+    pub position_nanos: u64,
+    pub exhausted: u32,
+    pub reserved: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct pb200_audio_level {
+    pub peak: [f32; 2],
+    pub rms: [f32; 2],
+}
+
 extern "C" {
     pub fn pb200_backend() -> *const c_char;
     pub fn pb200_create(config: *const pb200_config, out: *mut *mut pb200_renderer) -> c_int;
@@ -273,6 +291,9 @@ extern "C" {
     pub fn pb200_render_to_wav(r: *mut pb200_renderer, path: *const c_char, duration_nanos: u64, frames_written: *mut u64) -> c_int;
     pub fn pb200_source_status_get(r: *mut pb200_renderer, playback_id: u32, st: *mut pb200_source_status) -> c_int;
     pub fn pb200_sampler_voice_states(r: *mut pb200_renderer, generator_id: u32, out: *mut pb200_voice_state, capacity: u32, count: *mut u32) -> c_int;
+    pub fn pb200_poll_status(r: *mut pb200_renderer, out: *mut pb200_status_event, capacity: u32, count: *mut u32) -> c_int;
+    pub fn pb200_set_metering_interval(r: *mut pb200_renderer, interval_nanos: u64) -> c_int;
+    pub fn pb200_get_audio_level(r: *mut pb200_renderer, out: *mut pb200_audio_level) -> c_int;
     pub fn pb200_last_render_stats(r: *mut pb200_renderer, st: *mut pb200_render_stats) -> c_int;
 }
 

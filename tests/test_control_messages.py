@@ -211,3 +211,50 @@ def test_control_scene_matches_oracle(cuda_api, oracle_api, name):
         assert 20 * np.log10(max(rms, 1e-30)) < -90.0 and err < 1e-4
     else:
         assert err <= 1e-5, f"max abs err {err:.3e}"
+
+
+# ---- observability: PlaybackStatusEvent stream + the main mixer's level meter ----------------------------
+def scene_observability(api):
+    p = Player(api, SR)
+    p.set_metering_interval(0.25)
+    b = p.upload_buffer(buf(150000, seed=21), 44100)
+    b2 = p.upload_buffer(buf(30000, rate=48000, seed=22, channels=2), 48000, loop_range=(1000, 29000))
+    h1 = p.play_file_source(b, FilePlaybackOptions(volume=0.6, speed=1.1))            # plays to its end (~3.1 s)
+    o = FilePlaybackOptions(volume=0.5, fade_out=0.02)
+    o.repeat_forever()
+    h2 = p.play_file_source(b2, o, start_time=5000)
+    h2.stop(100000)                                                                    # stopped, with fade-out
+    o3 = FilePlaybackOptions(volume=0.4, fade_out=None, resampling_quality=1)
+    h3 = p.play_file_source(b, o3, start_time=20000)
+    h3.stop(70000)                                                                     # stopped abruptly (no fade)
+    levels, events = [], []
+    parts = []
+    for _ in range(5):
+        parts.append(p.render(40 * BLOCK))
+        levels.append(p.audio_level())
+        events += p.poll_status()
+    assert p.poll_status() == []
+    return np.concatenate(parts), events, levels
+
+
+def test_oracle_status_stream_and_meter(oracle_api):
+    out, events, levels = scene_observability(oracle_api)
+    kinds = [(e[1], e[2]) for e in events]
+    assert kinds.count(("stopped", 1)) == 1 and kinds.count(("stopped", 2)) == 1 and kinds.count(("stopped", 3)) == 1
+    stopped = {e[2]: e for e in events if e[1] == "stopped"}
+    assert stopped[1][3] is True and stopped[2][3] is False and stopped[3][3] is False and stopped[3][0] == 70000
+    pos1 = [e for e in events if e[1] == "position" and e[2] == 1]
+    assert len(pos1) == 3 and all(b[0] - a[0] >= SR for a, b in zip(pos1, pos1[1:]))
+    assert all(b[3] > a[3] for a, b in zip(pos1, pos1[1:]))
+    (peak, rms) = levels[0]
+    assert 0.05 < max(peak) < 1.5 and 0.0 < max(rms) < max(peak)
+
+
+@pytest.mark.gpu
+def test_status_stream_and_meter_match_oracle(cuda_api, oracle_api):
+    g_out, g_ev, g_lv = scene_observability(cuda_api)
+    o_out, o_ev, o_lv = scene_observability(oracle_api)
+    assert g_ev == o_ev                     # frames, ids, positions (ns) and exhausted flags: integers, exact
+    assert float(np.abs(g_out - o_out).max()) <= 1e-5
+    for (gp, gr), (op, orr) in zip(g_lv, o_lv):
+        assert np.allclose(gp, op, rtol=0, atol=1e-5) and np.allclose(gr, orr, rtol=1e-5, atol=1e-7)
