@@ -118,11 +118,21 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
     const uint32_t len = (uint32_t)(c1 - c0);
     const uint32_t boff = (uint32_t)(c0 - a.block_start);
     float* gchunk = bus + (size_t)boff * 2;
+    // WavStream's master volume (wav.rs:237) is decided per 1024-frame block; while it is not ramping its state does not
+    // move, so the decision holds for every chunk of the block
+    bool master_direct = false, master_scale = false, chunk_done = false;
+    float master_gain = 1.0f;
+    if (is_main && a.out && !a.meter) {
+      const ExpSm ms0 = *a.master;
+      if (!exp_need_ramp(ms0, a.fxc.comp)) { master_direct = true; master_gain = ms0.target; master_scale = fabsf(1.0f - master_gain) > 0.000001f; }
+    }
 
     if (has_fx) {
       // effect parameter events due at this chunk start (MixedSource::process_events, mixed.rs:683)
       for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
         FxHeader& h = a.fx[e];
+        // most chunks have no event due. The vote is also a barrier: every thread has read the cursor before thread 0 moves it
+        if (!__syncthreads_or(h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= c0)) continue;
         for (;;) {  // events in order; a message (Effect::process_message) is carried out by the whole CTA
           if (tid == 0) {
             s_run = 0u;
@@ -135,20 +145,21 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
           }
           __syncthreads();
           const uint32_t msg = s_run;
+          __syncthreads();  // (everybody has read the verdict before thread 0 reuses the flag)
           if (msg == 0u) break;
           fx_process_message(h, a.fxc, msg, tid, nt);
           __syncthreads();
         }
       }
-      // audible input? (mixed.rs:701-708)
-      bool audible = false;
-      for (uint32_t ci = mp.child_begin; ci < mp.child_end; ++ci)
-        audible |= a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (k - cb)] != 0;
-      for (uint32_t si = mp.src_begin; si < mp.src_end; ++si)
-        audible |= a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (k - cb)] != 0;
+      // audible input? (mixed.rs:701-708) -- one flag per child / source, gathered by the whole CTA
+      int aud = 0;
+      for (uint32_t ci = mp.child_begin + tid; ci < mp.child_end; ci += nt)
+        aud |= a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (k - cb)] != 0;
+      for (uint32_t si = mp.src_begin + tid; si < mp.src_end; si += nt)
+        aud |= a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (k - cb)] != 0;
+      const bool audible = __syncthreads_or(aud) != 0;
       bool input_bypassed = !audible;
       const bool skip_all = a.mstate[m].effects_bypassed && input_bypassed;  // mixed.rs:629
-      __syncthreads();
       tick(0, t0);
       if (!skip_all) {
         // stage the chunk: interleaved global -> planar padded shared
@@ -210,14 +221,26 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
         }
         tick(4, t0);
         if (tid == 0) a.mstate[m].effects_bypassed = all_bypassed ? 1u : 0u;
-        // write the processed chunk back
-        for (uint32_t i = tid; i < len * 2; i += nt) gchunk[i] = s_ch[i & 1][pidx(i >> 1)];
+        if (master_direct) {
+          // main mixer, master volume not ramping, no meter: the chunk goes from shared memory straight to the output
+          // (nobody reads the main bus again), scaled as WavStream::process does per block (wav.rs:237)
+          for (uint32_t i = tid; i < len * 2; i += nt) {
+            const float x = s_ch[i & 1][pidx(i >> 1)];
+            a.out[(size_t)boff * 2 + i] = master_scale ? x * master_gain : x;
+          }
+          chunk_done = true;
+        } else {
+          // write the processed chunk back
+          for (uint32_t i = tid; i < len * 2; i += nt) gchunk[i] = s_ch[i & 1][pidx(i >> 1)];
+        }
       }
       __syncthreads();
       tick(5, t0);
     }
 
-    if (is_main) {
+    if (is_main && master_direct) {
+      if (!chunk_done) for (uint32_t i = tid; i < len * 2; i += nt) a.out[(size_t)boff * 2 + i] = master_scale ? gchunk[i] * master_gain : gchunk[i];
+    } else if (is_main) {
       // WavStream::process: apply_smoothed_gain once per 1024-frame block (wav.rs:228-237)
       if ((c1 % a.wav_block_frames) == 0 || k + 2 == ce) {
         const uint64_t wb0 = ((c1 - 1) / a.wav_block_frames) * a.wav_block_frames;

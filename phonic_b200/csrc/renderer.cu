@@ -254,7 +254,7 @@ struct pb200_renderer {
   DevVec<GroupSeg> d_gsegs;
   DevVec<uint16_t> d_seg_first, d_seg_count, d_gseg_first, d_gseg_count;
   DevVec<TileRec> d_recs;
-  DevVec<uint32_t> d_block_done;
+  DevVec<uint32_t> d_block_done, d_quiet_block, d_auton;
   // exact phase-jump tables (phase_table.cuh): one per steady resampling ratio seen so far, built on the device
   std::map<uint32_t, uint32_t> phase_off;   // f32 bits of the ratio -> word offset of its table
   DevVec<uint32_t> d_phase_tabs;
@@ -618,7 +618,7 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sr_) cudaStreamSynchronize(r->sr_);
   if (r->sm) cudaStreamSynchronize(r->sm);
   for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
-  r->d_status.free(); r->d_status_count.free(); r->d_meter.free(); r->d_block_done.free(); r->d_phase_tabs.free(); r->d_phase_dir.free(); r->d_phase_new.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
+  r->d_quiet_block.free(); r->d_auton.free(); r->d_status.free(); r->d_status_count.free(); r->d_meter.free(); r->d_block_done.free(); r->d_phase_tabs.free(); r->d_phase_dir.free(); r->d_phase_new.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
   r->d_gran_groups.free(); r->d_gran_states.free(); r->d_grain_recs.free(); r->d_gran_counters.free(); r->d_gran_vrec.free();
   r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry[0].free(); r->d_grain_carry[1].free(); r->d_grain_luts.free();
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
@@ -1571,9 +1571,36 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   }
   CUDA_TRY(r->d_gseg_first.reserve(std::max<size_t>(1, (size_t)nslots * ng * n_tiles)));
   CUDA_TRY(r->d_gseg_count.reserve(std::max<size_t>(1, (size_t)nslots * ng * n_tiles)));
+  bool autonomous = false;
   if (persistent) {
     CUDA_TRY(r->d_block_done.reserve(n_blocks));
     CUDA_TRY(cudaMemsetAsync(r->d_block_done.p, 0, n_blocks * sizeof(uint32_t), r->sv));
+    // Autonomous voices (SkeletonLoop): per group the first block from which no event couples its voices any more
+    static const bool no_auton = getenv("PB200_NO_AUTONOMOUS") != nullptr;
+    const SizeClass& sc0 = c.classes[0];
+    if (!no_auton && sc0.vpad <= 8) {
+      std::vector<uint32_t> quiet(sc0.groups.size(), n_blocks);
+      for (size_t ci = 0; ci < sc0.groups.size(); ++ci) {
+        const uint32_t gi = sc0.groups[ci];
+        const HostGroup& g = r->groups[gi];
+        const GroupState& gs = r->h_gstate[gi];
+        if (g.gp.kind != GROUP_SAMPLER || gs.dead || gs.stopping || gs.stopped || gs.has_stop_time || g.gp.start_time > p0) continue;
+        uint64_t last_hard = 0;
+        bool any = false;
+        for (auto& e : g.events)
+          if (e.ev.kind == EVK_NOTE_ON || e.ev.kind == EVK_STOP || e.ev.kind == EVK_SET_PARAM || e.ev.kind == EVK_SET_LOOP) { any = true; last_hard = std::max(last_hard, e.ev.time); }
+        // the first block that starts after the last coupling event (an event AT a block's first frame still belongs to it)
+        const uint32_t qb = !any || last_hard < p0 ? 0u : (uint32_t)std::min<uint64_t>((last_hard - p0) / tb + 1, n_blocks);
+        quiet[ci] = qb;
+        autonomous |= qb < n_blocks;
+      }
+      if (autonomous) {
+        CUDA_TRY(r->d_quiet_block.upload(quiet, r->sv));
+        const size_t words = sc0.groups.size() * (size_t)n_blocks * (1 + (size_t)max_chunks);
+        CUDA_TRY(r->d_auton.reserve(words));
+        CUDA_TRY(cudaMemsetAsync(r->d_auton.p, 0, words * sizeof(uint32_t), r->sv));
+      }
+    }
   }
 
   // HighQuality voices: per-block record list + resampler output stream scratch (hq.cuh, sinc_kernel.cuh)
@@ -1732,6 +1759,11 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       sl.segs_stride = nvoices * seg_cap; sl.seg_tab_stride = nvoices * n_tiles;
       sl.gsegs_stride = ng * seg_cap; sl.gseg_tab_stride = ng * n_tiles; sl.recs_stride = nvoices * n_tiles;
       sl.block_done = r->d_block_done.p;
+      if (autonomous) {
+        sl.quiet_block = r->d_quiet_block.p;
+        sl.auton_done = r->d_auton.p;
+        sl.auton_cnt = r->d_auton.p + c.classes[0].groups.size() * (size_t)n_blocks;
+      }
     }
     for (size_t ci = 0; ci < c.classes.size() && (!persistent || b == 0); ++ci) {
       const SizeClass& sc = c.classes[ci];

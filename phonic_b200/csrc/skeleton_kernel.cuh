@@ -469,10 +469,32 @@ PB_DEV void sc_close(SuperCall& sc, VoiceState& v, const uint32_t CC) {
   sc.open = 0;
 }
 
+// How one launch walks several consecutive time blocks (the persistent mode of small graphs: every group keeps
+// its own pace through the whole render, a block is handed to the replay pass as soon as ALL groups have finished
+// it; renderer.cu waits for `block_done[b]` with a stream memory operation). n_blocks = 1 and block_done = nullptr:
+// the plain one-launch-per-block mode.
+struct SkeletonLoop {
+  uint32_t n_blocks;
+  uint32_t chunk_begin_stride;   // uint32 per block in mixer_chunk_begin
+  size_t group_flags_stride;     // per-block strides of the snapshot tables (elements)
+  size_t segs_stride, seg_tab_stride, gsegs_stride, gseg_tab_stride, recs_stride;
+  uint32_t* block_done;          // [n_blocks] CTAs that finished the block
+  uint32_t tab_slots;            // warp-per-voice: shared-memory table slots (one per warp), 0 = tables are read from global memory
+  // Autonomous voices (persistent mode): from block quiet_block[cta] on, the group has no event left that couples its
+  // voices (note-on / stop / parameter / loop message, scheduled stop). Each voice's warp then walks the remaining blocks
+  // at its own pace; a voice that finishes block b bumps auton_done[cta][b], and the LAST voice to do so carries out the
+  // group-level bookkeeping of the block and hands it to the replay. Without this every block costs the group as much as
+  // its slowest voice (one of eight is usually in a pitch glide), i.e. the sum of all voices' slow paths.
+  const uint32_t* quiet_block;   // [ctas] first block of autonomy, >= n_blocks: never
+  uint32_t* auton_done;          // [ctas][n_blocks]
+  uint32_t* auton_cnt;           // [ctas][n_blocks][max_chunks] voices still holding a note after each chunk
+};
+
+
 // WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
 // control flow (the skeleton is a latency-bound chain of dependent f32 ops per voice, not a SIMT workload).
-template <int MAXT, bool WPV>
-PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
+template <int MAXT, bool WPV, bool AUTON>
+PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonLoop& L, const uint32_t b_first) {
   __shared__ VoiceHeader s_head[WPV ? 32 : MAXT];
   __shared__ GroupState s_gs;
   __shared__ uint32_t s_count;
@@ -547,10 +569,11 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
   for (uint32_t i = threadIdx.x; i < a.n_tiles; i += blockDim.x) g_count[i] = 0;
   __syncthreads();
 
-  const uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];
+  uint32_t cb = a.mixer_chunk_begin[gp.mixer], ce = a.mixer_chunk_begin[gp.mixer + 1];
   for (uint32_t i = threadIdx.x; i < min(ce - cb, SB_MAX); i += blockDim.x) s_bounds[i] = a.chunk_bounds[cb + i];
   __syncthreads();
-  auto bound = [&](const uint32_t i) -> uint64_t { return i - cb < SB_MAX ? s_bounds[i - cb] : a.chunk_bounds[i]; };
+  // (autonomous voices are in different blocks at the same time: they read the schedule from global memory)
+  auto bound = [&](const uint32_t i) -> uint64_t { return (!AUTON && i - cb < SB_MAX) ? s_bounds[i - cb] : a.chunk_bounds[i]; };
   // time of the next pending event (re-read only when the cursor moved)
   // next event that needs all voices at the same frame (see the free run below): its index and time
   uint32_t hard_idx = 0xFFFFFFFFu;
@@ -702,6 +725,131 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
     }
   };
 
+  // One mixer chunk [r0, r0 + rlen) of this thread's voice inside a span that needs no group-wide agreement: the events
+  // addressed to the voice, then its Source::write call (or the chunk's acceptance into the open super-call). `cnt`
+  // counts the voices that still hold a note after the chunk.
+  auto voice_chunk = [&](const uint64_t r0, const uint32_t rlen, uint32_t* cnt, uint32_t& ec, uint64_t& ev_t, const bool ignore) __attribute__((always_inline)) {
+    const uint32_t r0_off = (uint32_t)(r0 - a.block_start);
+    // events due at this chunk's start (MixedSource::process_events -> the first write call of the chunk)
+    while (ev_t <= r0) {
+      const DevEvent ev = a.events[ec];
+      ++ec;
+      ev_t = ec < gp.ev_end ? a.events[ec].time : UINT64_MAX;
+      if (ignore || ev.kind == EVK_SET_VOLUME || ev.kind == EVK_SET_PANNING) continue;
+      if (ev.kind != EVK_ALL_NOTES_OFF && !(v.has_note && v.note_id == ev.note_id)) continue;
+      sc_finish();  // the event changes this voice: its state has to be exact at r0 first
+      if (ev.kind == EVK_ALL_NOTES_OFF || ev.kind == EVK_NOTE_OFF) stop_voice(r0);
+      else if (ev.kind == EVK_NOTE_SPEED) { file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate); if (gsp) gsp->speed = ev.speed; }
+      else if (ev.kind == EVK_NOTE_VOLUME) { v.note_volume = ev.value; exp_set_target(v.vol, gp.base_volume * ev.value, comp); if (gsp) gsp->volume = gp.base_volume * ev.value; }
+      else if (ev.kind == EVK_NOTE_PANNING) {
+        v.note_panning = ev.value;
+        const float eff = fminf(fmaxf(gp.base_panning + ev.value, -1.0f), 1.0f);
+        exp_set_target(v.pan, eff, comp);
+        if (gsp) gsp->panning = eff;
+      }
+    }
+    if (!v.has_note) return;
+    if (sc.open) {  // steady voice: accept the chunk into the open call when it provably stays steady to the tile's end
+      const uint32_t r1_off = r0_off + rlen;
+      const uint32_t need = (r1_off + TILE - 1u) / TILE * TILE - sc.adv_off;
+      if (sc.budget < need) sc.budget = sc_steady_budget(sc, v, gp, CCr);
+      if (sc.budget >= need) {
+        sc.end_off = r1_off;
+        unsigned long long* st = a.prof ? prof_s + 2 : nullptr;
+        const long long q0 = a.prof ? clock64() : 0;
+        sc_advance<!WPV>(sc, v, gp, a.groups + gp_idx, my_recs, a.gen, CCr, r1_off, false, st);
+        if (a.prof) prof_s[7] += (unsigned long long)(clock64() - q0);
+        my_frames += rlen;
+        atomicAdd(cnt, 1u);
+        return;
+      }
+      sc_finish();
+    }
+    CallCtx cc;
+    cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
+    if (voice_begin_call(v, cc, gp, buf, rlen, comp, gp.has_env != 0, r0_off)) run_call(cc, rlen, r0_off, r0, true);
+    voice_epilogue(r0 + rlen, r0_off + rlen);
+    if (v.has_note) atomicAdd(cnt, 1u);
+  };
+
+  if (AUTON) {
+    // ---- autonomous voices (see SkeletonLoop): this warp's voice walks blocks b_first .. n_blocks-1 on its own --------
+    const uint32_t cta = blockIdx.x;
+    if (mine) {
+      uint32_t ec = s_gs.ev_cursor;
+      uint64_t ev_t = ec < gp.ev_end ? a.events[ec].time : UINT64_MAX;
+      const uint32_t chunk_stride = L.chunk_begin_stride;
+      for (uint32_t bb = b_first; bb < L.n_blocks; ++bb) {
+        if (bb > b_first) {  // the tables of the next block (persistent mode: one snapshot slot per block)
+          a.mixer_chunk_begin += chunk_stride;
+          a.block_start += a.block_frames;
+          a.segs += L.segs_stride; a.seg_first += L.seg_tab_stride; a.seg_count += L.seg_tab_stride;
+          a.recs += L.recs_stride;
+          a.gen += 1;
+          my_segs = a.segs + (size_t)vidx * a.seg_cap;
+          my_first = a.seg_first + (size_t)vidx * a.n_tiles;
+          my_count = a.seg_count + (size_t)vidx * a.n_tiles;
+          my_recs = a.recs + (size_t)vidx * a.n_tiles;
+          n_segs = 0; cur_tile = 0xFFFFFFFFu; cur_first = 0; cur_cnt = 0;
+          uint4* z = reinterpret_cast<uint4*>(my_count);   // n_tiles is a multiple of 16: 16-byte aligned rows
+          for (uint32_t i = 0; i < a.n_tiles / 8u; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
+          cb = a.mixer_chunk_begin[gp.mixer]; ce = a.mixer_chunk_begin[gp.mixer + 1];
+        }
+        uint32_t* cnt = L.auton_cnt + ((size_t)cta * L.n_blocks + bb) * a.max_chunks;
+        my_frames = 0;
+        for (uint32_t k = cb; k + 1 < ce; ++k) {
+          const uint64_t r0 = bound(k);
+          voice_chunk(r0, (uint32_t)(bound(k + 1) - r0), cnt + (k - cb), ec, ev_t, false);
+        }
+        sc_finish();
+        if (cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
+        if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
+        __threadfence();
+        const uint32_t arrived = atomicAdd(L.auton_done + (size_t)cta * L.n_blocks + bb, 1u) + 1u;
+        if (arrived == nv) {
+          // ---- last voice out: the generator-level bookkeeping of block bb (what thread 0 does after a free run) ----
+          __threadfence();
+          const uint32_t* bbegin = a.mixer_chunk_begin;
+          const uint32_t kb = bbegin[gp.mixer], ke = bbegin[gp.mixer + 1];
+          const size_t boff_g = (size_t)(bb - b_first);
+          g_segs = a.gsegs + boff_g * L.gsegs_stride + (size_t)g * a.seg_cap;
+          g_first = a.gseg_first + boff_g * L.gseg_tab_stride + (size_t)g * a.n_tiles;
+          g_count = a.gseg_count + boff_g * L.gseg_tab_stride + (size_t)g * a.n_tiles;
+          gflags = a.group_flags + boff_g * L.group_flags_stride + (size_t)g * a.max_chunks;
+          n_gsegs = 0; gcur_tile = 0xFFFFFFFFu; gcur_first = 0; gcur_cnt = 0;
+          if (bb > b_first) for (uint32_t i = 0; i < a.n_tiles; ++i) g_count[i] = 0;
+          uint32_t gec = s_gs.ev_cursor;
+          for (uint32_t k = kb; k + 1 < ke; ++k) {
+            const uint64_t e0 = a.chunk_bounds[k];
+            while (gec < gp.ev_end && a.events[gec].time <= e0) {  // generator-level AmplifiedSource / PannedSource messages
+              const DevEvent ev = a.events[gec];
+              ++gec;
+              if (ev.kind == EVK_SET_VOLUME) exp_set_target(s_gs.vol, ev.value, comp);
+              else if (ev.kind == EVK_SET_PANNING) exp_set_target(s_gs.pan, ev.value, comp);
+            }
+            bool writes = false;
+            if (!s_gs.dead) {
+              writes = !(s_gs.stopped || (s_gs.active_voices == 0 && !s_gs.stopping));
+              if (writes) {
+                group_call((uint32_t)(a.chunk_bounds[k + 1] - e0), (uint32_t)(e0 - a.block_start));
+                s_gs.active_voices = cnt[k - kb];
+                if (s_gs.stopping && cnt[k - kb] == 0) s_gs.stopped = 1;
+              }
+              if (gp.transient && s_gs.stopped && !s_gs.dead) { s_gs.dead = 1; s_gs.dead_time = a.chunk_bounds[k + 1]; }
+            }
+            gflags[k - kb] = writes ? 1 : 0;
+          }
+          s_gs.ev_cursor = gec;
+          if (gcur_tile != 0xFFFFFFFFu) { g_first[gcur_tile] = (uint16_t)gcur_first; g_count[gcur_tile] = (uint16_t)gcur_cnt; }
+          if (bb + 1 == L.n_blocks) a.gstate[g] = s_gs;
+          __threadfence();
+          atomicAdd(L.block_done + bb, 1u);
+        }
+      }
+      a.voices[gp.first_voice + tid] = v;
+    }
+    return;
+  }
   for (uint32_t k = cb; k + 1 < ce; ++k) {
     const uint64_t c0 = bound(k), c1 = bound(k + 1);
     // ---- free run -------------------------------------------------------------------------------------
@@ -742,48 +890,7 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
           const bool ignore = s_gs.stopping != 0;
           for (uint32_t j = 0; j < run; ++j) {
             const uint64_t r0 = bound(k + j);
-            const uint32_t rlen = (uint32_t)(bound(k + j + 1) - r0);
-            const uint32_t r0_off = (uint32_t)(r0 - a.block_start);
-            // events due at this chunk's start (MixedSource::process_events -> the first write call of the chunk)
-            while (ev_t <= r0) {
-              const DevEvent ev = a.events[ec];
-              ++ec;
-              ev_t = ec < gp.ev_end ? a.events[ec].time : UINT64_MAX;
-              if (ignore || ev.kind == EVK_SET_VOLUME || ev.kind == EVK_SET_PANNING) continue;
-              if (ev.kind != EVK_ALL_NOTES_OFF && !(v.has_note && v.note_id == ev.note_id)) continue;
-              sc_finish();  // the event changes this voice: its state has to be exact at r0 first
-              if (ev.kind == EVK_ALL_NOTES_OFF || ev.kind == EVK_NOTE_OFF) stop_voice(r0);
-              else if (ev.kind == EVK_NOTE_SPEED) { file_set_speed(v, ev.speed, ev.glide, buf.sample_rate, out_rate); if (gsp) gsp->speed = ev.speed; }
-              else if (ev.kind == EVK_NOTE_VOLUME) { v.note_volume = ev.value; exp_set_target(v.vol, gp.base_volume * ev.value, comp); if (gsp) gsp->volume = gp.base_volume * ev.value; }
-              else if (ev.kind == EVK_NOTE_PANNING) {
-                v.note_panning = ev.value;
-                const float eff = fminf(fmaxf(gp.base_panning + ev.value, -1.0f), 1.0f);
-                exp_set_target(v.pan, eff, comp);
-                if (gsp) gsp->panning = eff;
-              }
-            }
-            if (!v.has_note) continue;
-            if (sc.open) {  // steady voice: accept the chunk into the open call when it provably stays steady to the tile's end
-              const uint32_t r1_off = r0_off + rlen;
-              const uint32_t need = (r1_off + TILE - 1u) / TILE * TILE - sc.adv_off;
-              if (sc.budget < need) sc.budget = sc_steady_budget(sc, v, gp, CCr);
-              if (sc.budget >= need) {
-                sc.end_off = r1_off;
-                unsigned long long* st = a.prof ? prof_s + 2 : nullptr;
-                const long long q0 = a.prof ? clock64() : 0;
-                sc_advance<!WPV>(sc, v, gp, a.groups + gp_idx, my_recs, a.gen, CCr, r1_off, false, st);
-                if (a.prof) prof_s[7] += (unsigned long long)(clock64() - q0);
-                my_frames += rlen;
-                atomicAdd(&s_cnt[j], 1u);
-                continue;
-              }
-              sc_finish();
-            }
-            CallCtx cc;
-            cc.ended = true; cc.chunk_left = 0; cc.fader_running = false;
-            if (voice_begin_call(v, cc, gp, buf, rlen, comp, gp.has_env != 0, r0_off)) run_call(cc, rlen, r0_off, r0, true);
-            voice_epilogue(r0 + rlen, r0_off + rlen);
-            if (v.has_note) atomicAdd(&s_cnt[j], 1u);
+            voice_chunk(r0, (uint32_t)(bound(k + j + 1) - r0), &s_cnt[j], ec, ev_t, ignore);
           }
           sc_finish();
           publish_header(s_head, tid, v);
@@ -1056,19 +1163,6 @@ PB_DEV void skeleton_block(const SkeletonArgs& a, const TabSlot& tslot) {
   if (tid == 0) a.gstate[g] = s_gs;
 }
 
-// How one launch walks several consecutive time blocks (the persistent mode of small graphs: every group keeps
-// its own pace through the whole render, a block is handed to the replay pass as soon as ALL groups have finished
-// it; renderer.cu waits for `block_done[b]` with a stream memory operation). n_blocks = 1 and block_done = nullptr:
-// the plain one-launch-per-block mode.
-struct SkeletonLoop {
-  uint32_t n_blocks;
-  uint32_t chunk_begin_stride;   // uint32 per block in mixer_chunk_begin
-  size_t group_flags_stride;     // per-block strides of the snapshot tables (elements)
-  size_t segs_stride, seg_tab_stride, gsegs_stride, gseg_tab_stride, recs_stride;
-  uint32_t* block_done;          // [n_blocks] CTAs that finished the block
-  uint32_t tab_slots;            // warp-per-voice: shared-memory table slots (one per warp), 0 = tables are read from global memory
-};
-
 template <int MAXT, bool WPV>
 __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a, SkeletonLoop L) {
   extern __shared__ __align__(128) uint32_t tab_smem[];   // WPV: [tab_slots][TAB_SLOT_WORDS] | mbarriers | parities
@@ -1086,7 +1180,13 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a, Skeleton
     __syncthreads();
   }
   for (uint32_t b = 0; b < L.n_blocks; ++b) {
-    skeleton_block<MAXT, WPV>(a, tslot);
+    if constexpr (WPV) {
+      if (L.quiet_block != nullptr && b >= L.quiet_block[blockIdx.x]) {  // the group's voices go their own way from here on
+        skeleton_block<MAXT, WPV, true>(a, tslot, L, b);
+        return;
+      }
+    }
+    skeleton_block<MAXT, WPV, false>(a, tslot, L, b);
     if (L.block_done) {
       __syncthreads();
       if (threadIdx.x == 0) { __threadfence(); atomicAdd(L.block_done + b, 1u); }
