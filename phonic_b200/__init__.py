@@ -16,7 +16,7 @@ from .player import (AhdsrParameters, ChorusEffect, CompressorEffect, DelayEffec
                      GeneratorPlaybackOptions, MixerHandle, PhonicError, Player, ReverbEffect)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libphonic_b200.so")
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "csrc", "libphonic_b200.so")  # PB200_LIB: A/B builds of the same library
 
 _api = None
 

@@ -112,10 +112,25 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
 
   long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto tick = [&](int i, long long& t0) { if (a.prof) { const long long t1 = clock64(); pt[i] += t1 - t0; t0 = t1; } };
+  // audible input per chunk (mixed.rs:701-708): one flag per child / source and chunk, gathered for the whole block at once
+  // (the children's and sources' kernels of this block have finished)
+  constexpr uint32_t AUD_MAX = 1024;
+  __shared__ uint8_t s_aud[AUD_MAX];
+  auto audible_of = [&](const uint32_t kk) -> bool {
+    bool aud = false;
+    for (uint32_t ci = mp.child_begin; ci < mp.child_end && !aud; ++ci) aud = a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (kk - cb)] != 0;
+    for (uint32_t si = mp.src_begin; si < mp.src_end && !aud; ++si) aud = a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (kk - cb)] != 0;
+    return aud;
+  };
+  if (has_fx) {
+    for (uint32_t kk = cb + tid; kk + 1 < ce && kk - cb < AUD_MAX; kk += nt) s_aud[kk - cb] = audible_of(kk) ? 1 : 0;
+    __syncthreads();
+  }
   for (uint32_t k = cb; k + 1 < ce; ++k) {
     long long t0 = a.prof ? clock64() : 0;
-    const uint64_t c0 = a.chunk_bounds[k], c1 = a.chunk_bounds[k + 1];
-    const uint32_t len = (uint32_t)(c1 - c0);
+    const uint64_t c0 = a.chunk_bounds[k];
+    uint64_t c1 = a.chunk_bounds[k + 1];
+    uint32_t len = (uint32_t)(c1 - c0);
     const uint32_t boff = (uint32_t)(c0 - a.block_start);
     float* gchunk = bus + (size_t)boff * 2;
     // WavStream's master volume (wav.rs:237) is decided per 1024-frame block; while it is not ramping its state does not
@@ -151,13 +166,28 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
           __syncthreads();
         }
       }
-      // audible input? (mixed.rs:701-708) -- one flag per child / source, gathered by the whole CTA
-      int aud = 0;
-      for (uint32_t ci = mp.child_begin + tid; ci < mp.child_end; ci += nt)
-        aud |= a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (k - cb)] != 0;
-      for (uint32_t si = mp.src_begin + tid; si < mp.src_end; si += nt)
-        aud |= a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (k - cb)] != 0;
-      const bool audible = __syncthreads_or(aud) != 0;
+      const bool audible = (k - cb < AUD_MAX) ? s_aud[k - cb] != 0 : audible_of(k);
+      // While the input is audible every effect runs and its bypass counters are reset chunk after chunk
+      // (mixed/effect.rs:71-79): processing consecutive audible chunks in one go gives the same samples. Merge them up
+      // to the next 1024-frame block boundary / parent chunk boundary / effect event -- most chunk boundaries of a busy
+      // mixer come from its SOURCES' events (mixed.rs:686-693) and mean nothing to the effects.
+      if (audible) {
+        while (k + 2 < ce) {
+          const uint64_t nb = a.chunk_bounds[k + 1];   // start of the next chunk
+          if (nb % a.wav_block_frames == 0) break;
+          if (!is_main && nb == a.chunk_bounds[pk + 1]) break;
+          if (!((k + 1 - cb < AUD_MAX) ? s_aud[k + 1 - cb] != 0 : audible_of(k + 1))) break;
+          bool ev_due = false;
+          for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
+            const FxHeader& h = a.fx[e];
+            ev_due |= h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= nb;
+          }
+          if (ev_due) break;
+          ++k;
+          c1 = a.chunk_bounds[k + 1];
+        }
+        len = (uint32_t)(c1 - c0);
+      }
       bool input_bypassed = !audible;
       const bool skip_all = a.mstate[m].effects_bypassed && input_bypassed;  // mixed.rs:629
       tick(0, t0);

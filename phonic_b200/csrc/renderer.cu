@@ -1775,12 +1775,22 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       const size_t wpv_resident = (size_t)sm_count_all * std::max<size_t>(1, 65536 / (224 * 32 * (size_t)sc.vpad));
       const bool wpv = force_wpv >= 0 ? force_wpv != 0 : (persistent || sc.groups.size() <= wpv_resident);
       sl.tab_slots = 0;
-      if (sc.vpad <= 8 && wpv) {  // the voice's jump table in its warp's shared-memory slot
+      // launches whose voices are all granular / HighQuality take the variant without the simple-call machinery
+      bool plain_only = true;
+      for (uint32_t gi : sc.groups) {
+        const bool gran = r->gran_groups[gi].enabled != 0;
+        const bool hq = r->groups[gi].gp.kind == GROUP_FILE && r->h_voices[r->groups[gi].gp.first_voice].hq != 0;
+        plain_only &= gran || hq;
+      }
+      if (sc.vpad <= 8 && wpv && plain_only) {
+        skeleton_kernel<256, true, false><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
+      } else if (sc.vpad <= 8 && wpv) {  // the voice's jump table in its warp's shared-memory slot
         sl.tab_slots = sc.vpad;
-        const size_t smem = (size_t)sc.vpad * (TAB_SLOT_WORDS * 4 + 8 + 4) + 16;
+        const size_t smem = (size_t)sl.tab_slots * (TAB_SLOT_WORDS * 4 + 8 + 4) + 16;
         skeleton_kernel<256, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, smem, r->sv>>>(va, sl);
       }
       else if (sc.vpad <= 32 && wpv) skeleton_kernel<1024, true><<<(uint32_t)sc.groups.size(), sc.vpad * 32, 0, r->sv>>>(va, sl);
+      else if (sc.threads <= 256 && plain_only) skeleton_kernel<256, false, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
       else if (sc.threads <= 256) skeleton_kernel<256, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
       else skeleton_kernel<1024, false><<<(uint32_t)sc.groups.size(), sc.threads, 0, r->sv>>>(va, sl);
       ++launches;

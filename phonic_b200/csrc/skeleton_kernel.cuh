@@ -469,6 +469,42 @@ PB_DEV void sc_close(SuperCall& sc, VoiceState& v, const uint32_t CC) {
   sc.open = 0;
 }
 
+// The granular arm of one Source::write call (SamplerVoice::process, voice.rs:412-427), out of line and on copies of the
+// voice state: the per-tile loop calls gran_advance (itself out of line), and a call made from the skeleton's main body
+// would save and restore that body's ~250 live registers around every tile.
+struct SegCursor { uint32_t n_segs, cur_tile, cur_first, cur_cnt; };
+__device__ __noinline__ void gran_call_nl(VoiceState* vp, CallCtx* cp, const GroupParams* __restrict__ gpp, GranState* gsp,
+                                          const GranGroup* __restrict__ ggp, const GranEmit* __restrict__ emp, const uint32_t gran_row,
+                                          const uint64_t t, const uint32_t call_off, const uint32_t n, Segment* __restrict__ my_segs,
+                                          uint16_t* __restrict__ my_first, uint16_t* __restrict__ my_count, const uint32_t seg_cap,
+                                          const uint32_t gp_idx, const bool store, SegCursor* cur) {
+  VoiceState v = *vp;
+  CallCtx cc = *cp;
+  SegCursor c = *cur;
+  const GroupParams gp = *gpp;
+  const GranEmit em = *emp;
+  uint32_t off = call_off, remaining = n;
+  while (remaining > 0) {
+    const uint32_t tile = off / TILE;
+    const uint32_t seg_len = min(remaining, (tile + 1) * TILE - off);
+    if (c.n_segs < seg_cap && store) {
+      Segment& s = my_segs[c.n_segs];
+      s.v = v; s.c = cc; s.out_off = off; s.n = seg_len; s.gp_idx = gp_idx;
+      if (tile != c.cur_tile) {
+        if (c.cur_tile != 0xFFFFFFFFu) { my_first[c.cur_tile] = (uint16_t)c.cur_first; my_count[c.cur_tile] = (uint16_t)c.cur_cnt; }
+        c.cur_tile = tile; c.cur_first = c.n_segs; c.cur_cnt = 0;
+      }
+      c.cur_cnt++;
+      c.n_segs++;
+    }
+    gran_advance(gsp, ggp, em, gran_row, t + (off - call_off), off, seg_len);
+    cc.chunk_left -= seg_len; cc.hq_off += seg_len;
+    if (gp.has_env && cc.env_per_frame) env_chain(v, gp, seg_len);
+    off += seg_len; remaining -= seg_len;
+  }
+  *vp = v; *cp = cc; *cur = c;
+}
+
 // How one launch walks several consecutive time blocks (the persistent mode of small graphs: every group keeps
 // its own pace through the whole render, a block is handed to the replay pass as soon as ALL groups have finished
 // it; renderer.cu waits for `block_done[b]` with a stream memory operation). n_blocks = 1 and block_done = nullptr:
@@ -493,7 +529,9 @@ struct SkeletonLoop {
 
 // WPV (warp per voice): lane 0 of warp i owns voice i, so voices never serialise each other's divergent
 // control flow (the skeleton is a latency-bound chain of dependent f32 ops per voice, not a SIMT workload).
-template <int MAXT, bool WPV, bool AUTON>
+// SIMPLE = false: the launch holds only granular / HighQuality voices, which never take a simple call -- the super-call
+// machinery (and the registers it keeps live across the whole chunk loop) is compiled out.
+template <int MAXT, bool WPV, bool AUTON, bool SIMPLE>
 PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonLoop& L, const uint32_t b_first) {
   __shared__ VoiceHeader s_head[WPV ? 32 : MAXT];
   __shared__ GroupState s_gs;
@@ -604,7 +642,7 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
   // advance the pending frames of the open call literally and close it: the voice state is exact at sc.end_off again
   const uint32_t CCr = buf.channels;
   auto sc_finish = [&]() {
-    if (!sc.open) return;
+    if (!SIMPLE || !sc.open) return;
     sc_advance<!WPV>(sc, v, gp, a.groups + gp_idx, my_recs, a.gen, CCr, sc.end_off, true, a.prof ? prof_s + 2 : nullptr);
     sc_close(sc, v, CCr);
   };
@@ -615,7 +653,7 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
     bool simple = false;
     const bool cyc_v = CYC_ON(gp.first_voice + tid);
     const long long cyr0 = cyc_v ? CYC_T() : 0ll;
-    if (n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq && !is_gran)
+    if (SIMPLE && n_segs < a.seg_cap && !(a.debug_flags & 2u) && !is_hq && !is_gran)
       simple = buf.channels == 2 ? simple_call_ok<2>(v, cc, buf, n) : simple_call_ok<1>(v, cc, buf, n);
     const long long prc0 = a.prof ? clock64() : 0;
     if (simple) {
@@ -643,6 +681,15 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
       if (!sc.open) after_process_call(v, cc);  // (an open super-call cannot have reached its loop end: sc_steady_budget)
       n_segs++;
       written_frames = n;
+    } else if (is_gran) {
+      VoiceState vt = v;
+      CallCtx ct = cc;
+      SegCursor cur{n_segs, cur_tile, cur_first, cur_cnt};
+      gran_call_nl(&vt, &ct, a.groups + gp_idx, gsp, a.gran_groups + g, &a.gran, gran_row, t, call_off, n, my_segs, my_first, my_count,
+                   a.seg_cap, gp_idx, !(a.debug_flags & 1u), &cur);
+      v = vt; cc = ct;
+      n_segs = cur.n_segs; cur_tile = cur.cur_tile; cur_first = cur.cur_first; cur_cnt = cur.cur_cnt;
+      written_frames = n;
     } else {
       uint32_t off = call_off, remaining = n;
       while (remaining > 0 && !cc.ended) {
@@ -665,7 +712,7 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
           gran_advance(gsp, a.gran_groups + g, a.gran, gran_row, t + (off - call_off), off, seg_len);
           w = seg_len;
           cc.chunk_left -= w; cc.hq_off += w;
-          if (gp.has_env && cc.env_per_frame) env_chain_call(v, a.groups + gp_idx, w);
+          if (gp.has_env && cc.env_per_frame) env_chain(v, gp, w);
         } else if (is_hq) {
           // the out-of-line HighQuality state machine works on copies: taking the address of `v` / `cc` themselves
           // would move the hot cubic path's voice state from registers to local memory
@@ -749,7 +796,7 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
       }
     }
     if (!v.has_note) return;
-    if (sc.open) {  // steady voice: accept the chunk into the open call when it provably stays steady to the tile's end
+    if (SIMPLE && sc.open) {  // steady voice: accept the chunk into the open call when it provably stays steady to the tile's end
       const uint32_t r1_off = r0_off + rlen;
       const uint32_t need = (r1_off + TILE - 1u) / TILE * TILE - sc.adv_off;
       if (sc.budget < need) sc.budget = sc_steady_budget(sc, v, gp, CCr);
@@ -1163,7 +1210,7 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
   if (tid == 0) a.gstate[g] = s_gs;
 }
 
-template <int MAXT, bool WPV>
+template <int MAXT, bool WPV, bool SIMPLE = true>
 __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a, SkeletonLoop L) {
   extern __shared__ __align__(128) uint32_t tab_smem[];   // WPV: [tab_slots][TAB_SLOT_WORDS] | mbarriers | parities
   TabSlot tslot;
@@ -1180,13 +1227,13 @@ __global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a, Skeleton
     __syncthreads();
   }
   for (uint32_t b = 0; b < L.n_blocks; ++b) {
-    if constexpr (WPV) {
+    if constexpr (WPV && SIMPLE) {
       if (L.quiet_block != nullptr && b >= L.quiet_block[blockIdx.x]) {  // the group's voices go their own way from here on
-        skeleton_block<MAXT, WPV, true>(a, tslot, L, b);
+        skeleton_block<MAXT, WPV, true, SIMPLE>(a, tslot, L, b);
         return;
       }
     }
-    skeleton_block<MAXT, WPV, false>(a, tslot, L, b);
+    skeleton_block<MAXT, WPV, false, SIMPLE>(a, tslot, L, b);
     if (L.block_done) {
       __syncthreads();
       if (threadIdx.x == 0) { __threadfence(); atomicAdd(L.block_done + b, 1u); }
