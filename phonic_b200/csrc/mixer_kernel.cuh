@@ -39,9 +39,16 @@ struct MixerKernelArgs {
   ExpSm* master;                  // WavStream::smoothed_volume
   uint32_t wav_block_frames;      // 1024
   uint32_t work_bytes;            // dynamic shared memory of this launch (FX_WORK_SMALL unless a mixer of the level holds a reverb)
+  // Effect-chain pipelining (n_stages > 1): CTA (mixer, stage) runs the effects [stage_begin[stage], stage_begin[stage+1]) of
+  // its mixer; chunk q moves from stage to stage through the mixer bus in global memory, announced by fx_progress.
+  uint32_t n_stages;              // blockDim.y of the launch; 1 = one CTA per mixer runs the whole chain
+  const uint32_t* stage_begin;    // [n_mixers][n_stages + 1] effect indices relative to fx_begin (by dense mixer index)
+  uint32_t* fx_progress;          // [n_mixers][n_stages] chunks of this block finished by the stage (zeroed per block)
+  uint8_t* fx_pflags;             // [n_mixers][n_stages][max_chunks] bit0 input still bypassed, bit1 some effect ran
   double* meter;                  // main mixer: [wav block of the render][peak L, peak R, sum of squares L, R] or nullptr (MeteredSource)
   uint64_t render_start;          // first frame of the render call (meter rows count from it)
-  unsigned long long* prof;       // PB200_FX_PROF: [8] cycle counters of the main mixer's CTA (debug aid)
+  unsigned long long* prof;
+  uint32_t prof_all;       // PB200_FX_PROF: [8] cycle counters of the main mixer's CTA (debug aid)
 };
 
 PB_DEV uint64_t sat_sub_u64(uint64_t a, uint64_t b) { return a > b ? a - b : 0; }
@@ -82,10 +89,13 @@ __global__ void __launch_bounds__(256) mix_sum_kernel(MixerKernelArgs a) {
 
 // ---- M2 -------------------------------------------------------------------------------------------------
 constexpr uint32_t FX_THREADS = FX_THREADS_C;
+constexpr uint32_t MAX_FX_STAGES = 4;    // pipeline stages of a mixer's effect chain (one CTA each)
 constexpr uint32_t FX_WORK_SMALL = 48 * 1024;   // every effect but the whole-chunk reverb fits: keeps the L1 carve-out and 3 CTAs per SM
 constexpr uint32_t FX_WORK_BYTES = 120 * 1024;  // shared-memory work area of the chunk-parallel effects (the reverb's ten f64 planes of a whole chunk)
 
-__global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
+// MINB = 2: the 128-register build, two CTAs per SM, for levels whose pipeline needs more co-resident CTAs than SMs
+template <int MINB>
+__global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArgs a) {
   __shared__ float s_ch[2][PLANE];
   __shared__ double s_scratch[2][PLANE];
   __shared__ double s_lane_state[2][64];
@@ -96,10 +106,26 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
 
   const uint32_t m = a.level_mixers[blockIdx.x];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t stage = blockIdx.y, n_stages = a.n_stages;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const MixerParams mp = a.mixers[m];
   const bool is_main = mp.parent == 0xFFFFFFFFu;
   const bool has_fx = mp.fx_end > mp.fx_begin;
+  // the effects this CTA runs, and its place in the mixer's pipeline
+  uint32_t e_lo = mp.fx_begin, e_hi = mp.fx_end;
+  if (n_stages > 1) {
+    const uint32_t* sb = a.stage_begin + (size_t)m * (n_stages + 1);
+    e_lo = mp.fx_begin + sb[stage]; e_hi = mp.fx_begin + sb[stage + 1];
+    if (stage > 0 && e_lo >= e_hi) return;   // (a mixer with fewer effects than stages; stage 0 always runs: gate / master)
+  }
+  const bool first_stage = e_lo == mp.fx_begin, last_stage = e_hi == mp.fx_end;
+  uint32_t prev_stage = stage;               // the stage whose output this one consumes
+  if (!first_stage) { const uint32_t* sb = a.stage_begin + (size_t)m * (n_stages + 1); do { --prev_stage; } while (sb[prev_stage] == sb[prev_stage + 1]); }
+  volatile uint32_t* prog_in = a.fx_progress ? a.fx_progress + (size_t)m * n_stages + prev_stage : nullptr;
+  uint32_t* prog_out = a.fx_progress ? a.fx_progress + (size_t)m * n_stages + stage : nullptr;
+  const uint8_t* pf_in = a.fx_pflags ? a.fx_pflags + ((size_t)m * n_stages + prev_stage) * a.max_chunks : nullptr;
+  uint8_t* pf_out = a.fx_pflags ? a.fx_pflags + ((size_t)m * n_stages + stage) * a.max_chunks : nullptr;
+  uint32_t q = 0;                            // sequence number of the (merged) chunk: the same in every stage
   float* bus = a.mixer_bus + (size_t)m * a.block_frames * 2;
   const uint32_t cb = a.mixer_chunk_begin[m], ce = a.mixer_chunk_begin[m + 1];
   uint32_t pcb = 0, pk = 0;
@@ -125,6 +151,23 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
   if (has_fx) {
     for (uint32_t kk = cb + tid; kk + 1 < ce && kk - cb < AUD_MAX; kk += nt) s_aud[kk - cb] = audible_of(kk) ? 1 : 0;
     __syncthreads();
+  } else if (is_main && a.out && !a.meter) {
+    // a main mixer without effects (the top of a tree whose work sits in the sub-mixers): while the master volume is not
+    // ramping the whole time block is one scaled copy, whatever the chunk boundaries are
+    const ExpSm ms0 = *a.master;
+    if (!exp_need_ramp(ms0, a.fxc.comp)) {
+      const float g = ms0.target;
+      const bool scale = fabsf(1.0f - g) > 0.000001f;
+      const float4* src = reinterpret_cast<const float4*>(bus);
+      float4* dst = reinterpret_cast<float4*>(a.out);
+      const uint32_t n4 = a.block_len / 2;   // block lengths are multiples of the 1024-frame WavStream block
+      for (uint32_t i = tid; i < n4; i += nt) {
+        float4 v = src[i];
+        if (scale) { v.x *= g; v.y *= g; v.z *= g; v.w *= g; }
+        dst[i] = v;
+      }
+      return;
+    }
   }
   for (uint32_t k = cb; k + 1 < ce; ++k) {
     long long t0 = a.prof ? clock64() : 0;
@@ -144,7 +187,7 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
 
     if (has_fx) {
       // effect parameter events due at this chunk start (MixedSource::process_events, mixed.rs:683)
-      for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
+      for (uint32_t e = e_lo; e < e_hi; ++e) {
         FxHeader& h = a.fx[e];
         // most chunks have no event due. The vote is also a barrier: every thread has read the cursor before thread 0 moves it
         if (!__syncthreads_or(h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= c0)) continue;
@@ -177,10 +220,14 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
           if (nb % a.wav_block_frames == 0) break;
           if (!is_main && nb == a.chunk_bounds[pk + 1]) break;
           if (!((k + 1 - cb < AUD_MAX) ? s_aud[k + 1 - cb] != 0 : audible_of(k + 1))) break;
+          // an event of ANY effect of the mixer in (c0, nb] ends the merge. Judged on the event times alone (the
+          // cursors belong to the effects' own stages), so that every stage of a pipeline cuts the same chunks.
           bool ev_due = false;
           for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
             const FxHeader& h = a.fx[e];
-            ev_due |= h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= nb;
+            uint32_t lo2 = h.ev_begin, hi2 = h.ev_end;   // first event with time > c0
+            while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (a.fx_events[mid].time <= c0) lo2 = mid + 1; else hi2 = mid; }
+            ev_due |= lo2 < h.ev_end && a.fx_events[lo2].time <= nb;
           }
           if (ev_due) break;
           ++k;
@@ -189,15 +236,31 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
         len = (uint32_t)(c1 - c0);
       }
       bool input_bypassed = !audible;
-      const bool skip_all = a.mstate[m].effects_bypassed && input_bypassed;  // mixed.rs:629
+      bool all_bypassed = true;
+      if (!first_stage) {  // chunk q leaves the previous stage: its samples are in the bus, its flags in pf_in[q]
+        tick(0, t0);
+        if (tid == 0) { while (*prog_in < q + 1u) __nanosleep(64); }
+        __syncthreads();
+        tick(7, t0);
+        __threadfence();
+        const uint8_t f = __ldcg(pf_in + q);
+        input_bypassed = (f & 1u) != 0; all_bypassed = (f & 2u) == 0;
+      }
+      // (a pipeline stage cannot see the chain's verdict of the previous chunk; skipping is only a shortcut: with every
+      // effect bypassed and the input silent each EffectProcessor stays bypassed by itself, mixed/effect.rs:88-91)
+      bool skip_all = n_stages == 1 && a.mstate[m].effects_bypassed && input_bypassed;  // mixed.rs:629
+      if (n_stages > 1 && input_bypassed) {  // nothing to stage when every effect of this stage stays bypassed
+        bool any = false;
+        for (uint32_t e = e_lo; e < e_hi; ++e) any |= !(a.fx[e].tail_counter == 0 && a.fx[e].silence_counter == UINT64_MAX);
+        skip_all = !any;
+      }
       tick(0, t0);
       if (!skip_all) {
-        // stage the chunk: interleaved global -> planar padded shared
-        for (uint32_t i = tid; i < len * 2; i += nt) s_ch[i & 1][pidx(i >> 1)] = gchunk[i];
+        // stage the chunk: interleaved global -> planar padded shared (L2 loads: another SM may have written it)
+        for (uint32_t i = tid; i < len * 2; i += nt) s_ch[i & 1][pidx(i >> 1)] = __ldcg(gchunk + i);
         __syncthreads();
         tick(1, t0);
-        bool all_bypassed = true;
-        for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
+        for (uint32_t e = e_lo; e < e_hi; ++e) {
           FxHeader& h = a.fx[e];
           // EffectProcessor::process bypass transitions (mixed/effect.rs:64-109), decided by thread 0
           if (tid == 0) {
@@ -250,8 +313,8 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
           __syncthreads();
         }
         tick(4, t0);
-        if (tid == 0) a.mstate[m].effects_bypassed = all_bypassed ? 1u : 0u;
-        if (master_direct) {
+        if (tid == 0 && last_stage) a.mstate[m].effects_bypassed = all_bypassed ? 1u : 0u;
+        if (master_direct && last_stage) {
           // main mixer, master volume not ramping, no meter: the chunk goes from shared memory straight to the output
           // (nobody reads the main bus again), scaled as WavStream::process does per block (wav.rs:237)
           for (uint32_t i = tid; i < len * 2; i += nt) {
@@ -263,8 +326,24 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
           // write the processed chunk back
           for (uint32_t i = tid; i < len * 2; i += nt) gchunk[i] = s_ch[i & 1][pidx(i >> 1)];
         }
+      } else if (n_stages > 1 && tid == 0) {
+        for (uint32_t e = e_lo; e < e_hi; ++e) a.fx[e].bypassed = 1u;   // (the transition the skipped loop would have made)
+        if (last_stage) a.mstate[m].effects_bypassed = all_bypassed ? 1u : 0u;
+      }
+      if (!last_stage) {  // hand chunk q to the next stage: samples first, then the flags, then the count
+        if (!is_main && c1 == a.chunk_bounds[pk + 1]) pk++;   // (the gate itself is the last stage's business)
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          pf_out[q] = (uint8_t)((input_bypassed ? 1u : 0u) | (all_bypassed ? 0u : 2u));
+          __threadfence();
+          atomicExch(prog_out, q + 1u);
+        }
+        ++q;
+        continue;   // gate / master volume / output belong to the last stage
       }
       __syncthreads();
+      ++q;
       tick(5, t0);
     }
 
@@ -341,7 +420,8 @@ __global__ void __launch_bounds__(FX_THREADS) mix_fx_kernel(MixerKernelArgs a) {
     }
     tick(6, t0);
   }
-  if (a.prof && tid == 0 && is_main) for (int i = 0; i < 8; ++i) atomicAdd(a.prof + i, (unsigned long long)pt[i]);
+  if (a.prof && tid == 0 && (is_main || a.prof_all))
+    for (int i = 0; i < 8; ++i) atomicAdd(a.prof + (a.prof_all ? ((size_t)m * MAX_FX_STAGES + stage) * 8 : 0) + i, (unsigned long long)pt[i]);
 }
 
 }  // namespace pb

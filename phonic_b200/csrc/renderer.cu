@@ -254,7 +254,8 @@ struct pb200_renderer {
   DevVec<GroupSeg> d_gsegs;
   DevVec<uint16_t> d_seg_first, d_seg_count, d_gseg_first, d_gseg_count;
   DevVec<TileRec> d_recs;
-  DevVec<uint32_t> d_block_done, d_quiet_block, d_auton;
+  DevVec<uint32_t> d_block_done, d_quiet_block, d_auton, d_stage_begin, d_fx_progress;
+  DevVec<uint8_t> d_fx_pflags;
   // exact phase-jump tables (phase_table.cuh): one per steady resampling ratio seen so far, built on the device
   std::map<uint32_t, uint32_t> phase_off;   // f32 bits of the ratio -> word offset of its table
   DevVec<uint32_t> d_phase_tabs;
@@ -618,7 +619,7 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sr_) cudaStreamSynchronize(r->sr_);
   if (r->sm) cudaStreamSynchronize(r->sm);
   for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
-  r->d_quiet_block.free(); r->d_auton.free(); r->d_status.free(); r->d_status_count.free(); r->d_meter.free(); r->d_block_done.free(); r->d_phase_tabs.free(); r->d_phase_dir.free(); r->d_phase_new.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
+  r->d_quiet_block.free(); r->d_auton.free(); r->d_stage_begin.free(); r->d_fx_progress.free(); r->d_fx_pflags.free(); r->d_status.free(); r->d_status_count.free(); r->d_meter.free(); r->d_block_done.free(); r->d_phase_tabs.free(); r->d_phase_dir.free(); r->d_phase_new.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
   r->d_gran_groups.free(); r->d_gran_states.free(); r->d_grain_recs.free(); r->d_gran_counters.free(); r->d_gran_vrec.free();
   r->d_gran_tiles.free(); r->d_grain_storage.free(); r->d_grain_carry[0].free(); r->d_grain_carry[1].free(); r->d_grain_luts.free();
   r->d_buffers.free(); r->d_voices.free(); r->d_groups.free(); r->d_gstate.free(); r->d_events.free();
@@ -1537,7 +1538,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   if (!dout) { CUDA_TRY(r->d_out.reserve(frames * 2)); dout = r->d_out.p; }
   CUDA_TRY(cudaStreamSynchronize(r->sm));
 
-  CUDA_TRY(cudaFuncSetAttribute(mix_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_WORK_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(mix_fx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_WORK_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(mix_fx_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_WORK_SMALL));
   CUDA_TRY(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REPLAY_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(skeleton_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (TAB_SLOT_WORDS * 4 + 12) + 16));
   const uint32_t n_tiles = tb / TILE;
@@ -1658,6 +1660,77 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(cudaMemsetAsync(r->d_gran_counters.p, 0, 2 * (size_t)std::max<uint32_t>(RING, n_blocks) * sizeof(uint32_t), r->sv));
   }
 
+  // Effect-chain pipelining (mixer_kernel.cuh): per tree level the number of pipeline stages, per mixer the effects of
+  // each stage (contiguous ranges of the chain, balanced by the measured cost per chunk of each effect kind).
+  std::vector<uint32_t> level_stages(c.levels.size(), 1), stage_offsets(c.levels.size(), 0), level_small(c.levels.size(), 0);
+  {
+    static const bool no_pipe = getenv("PB200_NO_FX_PIPELINE") != nullptr, no_small = getenv("PB200_NO_FX_SMALL") != nullptr;
+    auto fx_cost = [](uint32_t kind) -> double {  // microseconds per 1024-frame chunk (tools/fx_cost.py)
+      switch (kind) {
+        case FX_FILTER: return 7; case FX_EQ5: return 15; case FX_COMPRESSOR: return 20; case FX_CHORUS: return 22; case FX_DELAY: return 33;
+        case FX_REVERB: return 98; case FX_GAIN: return 27; case FX_GATE: return 23; default: return 6;
+      }
+    };
+    std::vector<uint32_t> stage_begin;
+    int dev_sms = 0;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, r->device);
+    for (size_t lvl = 0; lvl < c.levels.size() && !no_pipe; ++lvl) {
+      size_t max_fx = 0;
+      bool reverb = false;
+      for (uint32_t mi : c.levels[lvl]) {
+        max_fx = std::max(max_fx, r->mixers[mi].effects.size());
+        for (uint32_t fi : r->mixers[mi].effects) reverb |= r->fxs[fi].kind == FX_REVERB;
+      }
+      if (max_fx < 2) continue;
+      int per_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mix_fx_kernel<1>, FX_THREADS, reverb ? FX_WORK_BYTES : FX_WORK_SMALL);
+      const size_t want = std::min<size_t>(max_fx, MAX_FX_STAGES), nlm = std::max<size_t>(1, c.levels[lvl].size());
+      uint32_t S = (uint32_t)std::min<size_t>(want, (size_t)std::max(per_sm, 0) * dev_sms / nlm);
+      if (S < want && !reverb && !no_small) {   // the 128-register build fits twice as many CTAs
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mix_fx_kernel<2>, FX_THREADS, FX_WORK_SMALL);
+        const uint32_t S2 = (uint32_t)std::min<size_t>(want, (size_t)std::max(per_sm, 0) * dev_sms / nlm);
+        if (S2 > S) { S = S2; level_small[lvl] = 1; }
+      }
+      if (S < 2) continue;
+      level_stages[lvl] = S;
+      stage_offsets[lvl] = 0;  // (indexed by dense mixer index: one table for the whole graph)
+    }
+    bool any = false;
+    for (uint32_t S : level_stages) any |= S > 1;
+    if (any) {
+      stage_begin.assign(nm * (size_t)(MAX_FX_STAGES + 1), 0);
+      for (size_t lvl = 0; lvl < c.levels.size(); ++lvl) {
+        const uint32_t S = level_stages[lvl];
+        if (S < 2) continue;
+        for (uint32_t mi : c.levels[lvl]) {
+          const auto& fx = r->mixers[mi].effects;
+          const size_t E = fx.size();
+          // contiguous partition of the chain into <= S parts with the smallest largest part (E <= 16: brute force DP)
+          std::vector<double> pre(E + 1, 0.0);
+          for (size_t i = 0; i < E; ++i) pre[i + 1] = pre[i] + fx_cost(r->fxs[fx[i]].kind);
+          const uint32_t P = (uint32_t)std::min<size_t>(S, E);   // non-empty parts; the stages after them stay empty
+          std::vector<std::vector<double>> best(P + 1, std::vector<double>(E + 1, 1e300));
+          std::vector<std::vector<size_t>> cut(P + 1, std::vector<size_t>(E + 1, 0));
+          best[0][0] = 0.0;
+          for (uint32_t k = 1; k <= P; ++k)
+            for (size_t j = k; j <= E; ++j)
+              for (size_t i = k - 1; i < j; ++i) {
+                const double v = std::max(best[k - 1][i], pre[j] - pre[i]);
+                if (v < best[k][j]) { best[k][j] = v; cut[k][j] = i; }
+              }
+          uint32_t* sb = stage_begin.data() + (size_t)mi * (S + 1);
+          for (uint32_t k = P; k <= S; ++k) sb[k] = (uint32_t)E;
+          size_t j = E;
+          for (uint32_t k = P; k >= 1; --k) { sb[k] = (uint32_t)j; j = cut[k][j]; }
+          sb[0] = 0;
+        }
+      }
+      CUDA_TRY(r->d_stage_begin.upload(stage_begin, r->sm));
+      CUDA_TRY(r->d_fx_progress.reserve(nm * (size_t)MAX_FX_STAGES));
+      CUDA_TRY(r->d_fx_pflags.reserve(nm * (size_t)MAX_FX_STAGES * max_chunks));
+      CUDA_TRY(cudaStreamSynchronize(r->sm));
+    }
+  }
   std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r0(n_blocks), ev_r1(n_blocks), ev_m0(n_blocks), ev_m1(n_blocks);
   std::vector<cudaEvent_t> ev_x((n_hq || n_rows) ? 3 * (size_t)n_blocks : 0);  // grain begin / grain end = sinc begin / sinc end
   for (auto& e : ev_x) CUDA_TRY(DevicePool::get().event(&e));
@@ -1699,7 +1772,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     CUDA_TRY(cudaMemsetAsync(r->d_meter.p, 0, meter_rows * 4 * sizeof(double), r->sm));
   }
   unsigned long long* fx_prof = nullptr;
-  if (getenv("PB200_FX_PROF")) { CUDA_TRY(cudaMalloc((void**)&fx_prof, 64)); CUDA_TRY(cudaMemset(fx_prof, 0, 64)); }
+  const bool fx_prof_all = getenv("PB200_FX_PROF") && atoi(getenv("PB200_FX_PROF")) >= 2;   // per mixer and stage
+  const size_t fx_prof_n = fx_prof_all ? r->mixers.size() * MAX_FX_STAGES * 8 : 8;
+  if (getenv("PB200_FX_PROF")) { CUDA_TRY(cudaMalloc((void**)&fx_prof, fx_prof_n * 8)); CUDA_TRY(cudaMemset(fx_prof, 0, fx_prof_n * 8)); }
   for (uint32_t b = 0; b < n_blocks; ++b) {
     const uint64_t b0 = p0 + (uint64_t)b * tb;
     const uint32_t blen = (uint32_t)std::min<uint64_t>(tb, p1 - b0);
@@ -1873,6 +1948,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ma.block_len = blen;
     ma.meter = metering ? r->d_meter.p : nullptr; ma.render_start = p0;
     ma.prof = fx_prof;
+    ma.prof_all = fx_prof_all ? 1u : 0u;
     for (int lvl = (int)c.levels.size() - 1; lvl >= 0 && !skel_only; --lvl) {
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
       const uint32_t nlm = (uint32_t)c.levels[lvl].size();
@@ -1880,7 +1956,20 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       bool has_reverb = false;
       for (uint32_t mi : c.levels[lvl]) for (uint32_t fi : r->mixers[mi].effects) has_reverb |= r->fxs[fi].kind == FX_REVERB;
       ma.work_bytes = has_reverb ? FX_WORK_BYTES : FX_WORK_SMALL;
-      mix_fx_kernel<<<nlm, FX_THREADS, ma.work_bytes, r->sm>>>(ma);
+      const uint32_t S = level_stages[lvl];
+      ma.n_stages = S;
+      ma.stage_begin = S > 1 ? r->d_stage_begin.p + stage_offsets[lvl] : nullptr;
+      ma.fx_progress = S > 1 ? r->d_fx_progress.p : nullptr;
+      ma.fx_pflags = S > 1 ? r->d_fx_pflags.p : nullptr;
+      if (S > 1) {
+        // all stages of a mixer must run at the same time: a cooperative launch checks that the grid is co-resident
+        CUDA_TRY(cudaMemsetAsync(r->d_fx_progress.p, 0, nm * (size_t)MAX_FX_STAGES * sizeof(uint32_t), r->sm));
+        void* kargs[] = {(void*)&ma};
+        const void* fn = level_small[lvl] ? (const void*)mix_fx_kernel<2> : (const void*)mix_fx_kernel<1>;
+        CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(nlm, S), dim3(FX_THREADS), kargs, ma.work_bytes, r->sm));
+      } else {
+        mix_fx_kernel<1><<<nlm, FX_THREADS, ma.work_bytes, r->sm>>>(ma);
+      }
       launches += 2;
     }
     CUDA_TRY(cudaEventRecord(ev_m1[b], r->sm));
@@ -1893,9 +1982,20 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaGetLastError());
 
   if (fx_prof) {
-    unsigned long long h[8];
-    cudaMemcpy(h, fx_prof, 64, cudaMemcpyDeviceToHost);
+    std::vector<unsigned long long> hp(fx_prof_n);
+    cudaMemcpy(hp.data(), fx_prof, fx_prof_n * 8, cudaMemcpyDeviceToHost);
     cudaFree(fx_prof);
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 8; ++i) h[i] = hp[i];
+    if (fx_prof_all) {
+      for (size_t mi = 0; mi < r->mixers.size(); mi += std::max<size_t>(1, r->mixers.size() / 4))
+        for (uint32_t st = 0; st < MAX_FX_STAGES; ++st) {
+          const unsigned long long* q = hp.data() + (mi * MAX_FX_STAGES + st) * 8;
+          if (q[0] + q[3] + q[6] == 0) continue;
+          fprintf(stderr, "fx prof mixer %zu stage %u (Mcycles): ev %.2f stage-in %.2f decide %.2f process %.2f tail %.2f writeback %.2f gate %.2f wait %.2f\n", mi, st,
+                  q[0] / 1e6, q[1] / 1e6, q[2] / 1e6, q[3] / 1e6, q[4] / 1e6, q[5] / 1e6, q[6] / 1e6, q[7] / 1e6);
+        }
+    }
     fprintf(stderr, "fx prof (Mcycles): events+audible %.2f stage %.2f bypass-decision %.2f process %.2f tail %.2f writeback %.2f master/gate %.2f\n",
             h[0] / 1e6, h[1] / 1e6, h[2] / 1e6, h[3] / 1e6, h[4] / 1e6, h[5] / 1e6, h[6] / 1e6);
   }

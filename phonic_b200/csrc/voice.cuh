@@ -794,6 +794,17 @@ PB_DEV uint32_t voice_advance(VoiceState& v, CallCtx& c, const GroupParams& gp, 
       if (c.gliding) v.to_next_speed_update -= span;
       if (c.call_left == 0) after_process_call(v, c);
       w = span;
+    } else if (bypass && span > 0u && span <= avail) {
+      // equal rates (cubic.rs:53-58): a plain copy, one input frame per output frame and no history; with `span` frames
+      // of input left nothing else can happen
+      if (c.new_call) { c.new_call = false; c.produced_in_call = 0; }
+      v.playback_pos += span * CC;
+      c.produced_in_call += span;
+      c.call_left -= span;
+      c.chunk_left -= span;
+      if (c.gliding) v.to_next_speed_update -= span;
+      if (c.call_left == 0) after_process_call(v, c);
+      w = span;
     } else {
       // general path for the resampler only: switch the other recurrences off, they are advanced below
       CallCtx t = c;

@@ -60,6 +60,9 @@ def finish_on_main_bus(api, bus, sample_rate: int, add_effects, device_ordinal: 
             st = p.last_render_stats()
             stats["device_ms"] = st.device_ms
             stats["kernel_launches"] = int(st.kernel_launches)
+            stats["skeleton_kernel_ms"] = st.skeleton_kernel_ms
+            stats["voice_kernel_ms"] = st.voice_kernel_ms
+            stats["effect_kernel_ms"] = st.effect_kernel_ms
     finally:
         p.close()
     return out
