@@ -83,12 +83,32 @@ def sample_buffer():
     return _BUFFER
 
 
-def build_scene(player, name, rank=0, as_subtree=False):
+# cfg5 at N > 1: rank 0 also runs the main mixer's Delay + Reverb, a serial chain nobody else can take (49 ms for a 10 s
+# render, against 37 ms for a 64-sub-mixer shard: DESIGN.md 5). The sub-mixers are spread with the reference's greedy weight
+# heuristic, rank 0 starting with the chain's cost in voice units -- at 8 ranks it ends up holding the main bus alone.
+MAIN_CHAIN_VOICE_UNITS = int(8192 * 49.0 / 37.0)
+
+
+def cfg5_submixers(world):
+    """Sub-mixers per rank of the `world`-rank cfg5 run (world x 64 sub-mixers of 128 voices in total)."""
+    from phonic_b200.distributed import assign_subtrees
+    if world == 1:
+        return [64]
+    bins = assign_subtrees([128] * (64 * world), world, preload=[MAIN_CHAIN_VOICE_UNITS] + [0] * (world - 1))
+    return [len(b) for b in bins]
+
+
+def build_scene(player, name, rank=0, as_subtree=False, world=1):
     """Builds the workload on `player` from the host sample buffer (upload + graph + events)."""
     from phonic_b200 import workloads as W
     from phonic_b200.player import FilterEffect
     spec = workload_spec(name)
     buf = sample_buffer()
+    if name == "cfg5" and world > 1:
+        n_mine = cfg5_submixers(world)[rank]
+        if n_mine:
+            W.build_subtrees(player, n_mine, spec["voices"] // spec["n_mixers"], W.VoiceBankSpec(), seed_base=100000 * rank, buffer=buf, fast=True)
+        return n_mine * (spec["voices"] // spec["n_mixers"])
     if name == "cfg2":
         if not as_subtree:
             W.build_cfg2(player, W.VoiceBankSpec(voices=spec["voices"]), buffer=buf, fast=True)
@@ -109,16 +129,57 @@ def build_scene(player, name, rank=0, as_subtree=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + clock-event (throttle) reasons during the timed region (B200_PROFILING.md's clocks line). Sampled through
+    NVML in this process every 50 ms -- a looping `nvidia-smi --query-gpu` holds driver locks for milliseconds per sample,
+    which a step made of many short launches and host synchronisations feels (cfg5: 88 -> 110 ms); nvidia-smi is the
+    fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []      # nvidia-smi fallback
+        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
+        self.nvml = None
+        self.stop_flag = threading.Event()
+        self.t = None
+        self.period = float(os.environ.get("PB200_CLOCKS_PERIOD", "0.05"))
+
+    def _nvml_loop(self):
+        n = self.nvml
+        try:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = n.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            names = {n.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     n.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", n.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag.is_set():
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.mx.append(mx)
+                bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for b, name in names.items():
+                    if bits & b:
+                        self.reasons.add(name)
+                self.stop_flag.wait(self.period)
+        except Exception as e:  # keep what was sampled
+            self.reasons.add(f"nvml sampling stopped: {e!r}"[:80])
 
     def start(self):
+        if os.environ.get("PB200_NO_CLOCKS"):   # (debug: how much the sampling itself costs)
+            return
+        try:
+            if os.environ.get("PB200_CLOCKS") == "smi":
+                raise RuntimeError("nvidia-smi requested")
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -132,8 +193,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -149,7 +215,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def measured_peaks():
@@ -306,6 +372,8 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--piece-frames", type=int, default=131072,
+                    help="cfg5: frames per piece of the pipelined sharded render (shards render piece p+1 while rank 0's main-bus stage runs p)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -315,7 +383,7 @@ def main():
 
     import phonic_b200
     from phonic_b200 import workloads as W
-    from phonic_b200.distributed import finish_on_main_bus, reduce_partial_bus
+    from phonic_b200.distributed import MainBusStage, piece_bounds, reduce_partial_bus, render_sharded
     from phonic_b200.player import Player
 
     rank = int(os.environ.get("RANK", "0"))
@@ -337,15 +405,20 @@ def main():
     sample_buffer()  # synthesise the input data before anything is timed
 
     # ---- device-resident arm: scenes built and uploaded before the timed region -------------------------------
-    players = []
+    main_bus = bool(spec.get("main_bus"))
+    players, stages = [], []
     for i in range(n_total):
         p = Player(api, SR, device_ordinal=local_rank)
-        build_scene(p, args.workload, rank=rank, as_subtree=world > 1)
+        build_scene(p, args.workload, rank=rank, as_subtree=world > 1 or main_bus, world=world)
         players.append(p)
+        # cfg5: rank 0 also owns the main mixer's Delay + Reverb (not shardable); its renderer takes the reduced bus on the device
+        stages.append(MainBusStage(api, SR, W.add_main_bus_sends, device_ordinal=local_rank) if main_bus and rank == 0 else None)
     out_dev = torch.zeros(frames, 2, dtype=torch.float32, device=device)
+    bus_dev = torch.zeros(frames, 2, dtype=torch.float32, device=device) if main_bus else out_dev
     clocks = ClockSampler(local_rank)
     dev_ms, wall_ms, voice_ms, skel_ms, fx_ms, launches, vframes = [], [], [], [], [], 0, 0
     sinc_ms, grain_ms, sinc_frames, grain_samples = [], [], 0, 0
+    red_ms_all, main_ms_all, shard_ms_all, wait_ms_all = [], [], [], []
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -358,41 +431,75 @@ def main():
         flush.fill_(float(i))  # evict L2 between steps
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        p.render_device(out_dev.data_ptr(), frames)
-        red_ms = 0.0
-        if world > 1:  # one NCCL reduce of the stereo bus partial per render (rank 0 owns the main bus)
+        red_ms = main_ms = 0.0
+        extra_launches = 0
+        if main_bus:
+            # pipelined: piece p+1 renders on every rank while piece p is reduced (NCCL) and runs through rank 0's main-bus
+            # chain. The step's device time is the span of the whole pipeline: one pair of events around it.
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            dist.barrier()  # absorbs the host-side skew between the ranks' step loops: the span below is the collective itself
+            if world > 1:
+                dist.barrier()
             e0.record()
-            reduce_partial_bus(out_dev, dst=0)
+            pst = {}
+            render_sharded(p, bus_dev, args.piece_frames, stages[i], out_dev, stats=pst)
             e1.record()
             torch.cuda.synchronize()
-            red_ms = e0.elapsed_time(e1)
-        main_ms, main_launches = 0.0, 0
-        if spec.get("main_bus") and rank == 0:  # cfg5: the main mixer's Delay + Reverb on the reduced sum (not shardable)
-            mst = {}
-            out_main = finish_on_main_bus(api, out_dev.cpu().numpy(), SR, W.add_main_bus_sends, device_ordinal=local_rank, stats=mst)
-            main_ms, main_launches = mst["device_ms"], mst["kernel_launches"]
+            step_ms = e0.elapsed_time(e1)
+            extra_launches = pst["shard_launches"] + pst.get("main_bus_launches", 0)
+            if i >= args.warmup:
+                shard_ms_all.append(pst["shard_ms"]); main_ms_all.append(pst.get("main_bus_ms", 0.0)); wait_ms_all.append(pst.get("reduce_wait_ms", 0.0))
+        else:
+            p.render_device(out_dev.data_ptr(), frames)
+            if world > 1:  # one NCCL reduce of the stereo bus partial per render (rank 0 owns the main bus)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()  # absorbs the host-side skew between the ranks' step loops: the span below is the collective itself
+                e0.record()
+                reduce_partial_bus(out_dev, dst=0)
+                e1.record()
+                torch.cuda.synchronize()
+                red_ms = e0.elapsed_time(e1)
+                extra_launches = 1
+            step_ms = None
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         st = p.last_render_stats()
         if i >= args.warmup:
-            dev_ms.append(st.device_ms + red_ms + main_ms)
+            dev_ms.append(step_ms if step_ms is not None else st.device_ms + red_ms)
+            red_ms_all.append(red_ms)
             wall_ms.append((t1 - t0) * 1e3)
-            voice_ms.append(st.voice_kernel_ms)
-            skel_ms.append(st.skeleton_kernel_ms)
-            fx_ms.append(st.effect_kernel_ms)
-            launches += int(st.kernel_launches) + (1 if world > 1 else 0) + main_launches
-            vframes += int(st.voice_frames)
+            voice_ms.append(pst["voice_kernel_ms"] if main_bus else st.voice_kernel_ms)
+            skel_ms.append(pst["skeleton_kernel_ms"] if main_bus else st.skeleton_kernel_ms)
+            fx_ms.append(pst["effect_kernel_ms"] if main_bus else st.effect_kernel_ms)
+            launches += (0 if main_bus else int(st.kernel_launches)) + extra_launches
+            vframes += int(pst["voice_frames"]) if main_bus else int(st.voice_frames)
             sinc_ms.append(st.sinc_kernel_ms); grain_ms.append(st.grain_kernel_ms)
             sinc_frames += int(st.sinc_frames); grain_samples += int(st.grain_samples)
+        if i + 1 == n_total:
+            checksum = float(out_dev.abs().sum().item())
+        # the renderer's work areas (snapshots, buses) go back to the process-wide pool for the next step's renderer: every
+        # step runs in the same, warm device memory instead of a fresh multi-GB range (steps 20: 10.4 -> 7.3 ms per step)
+        p.close()
+        if stages[i] is not None:
+            stages[i].close()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clk = clocks.stop()
-    checksum = float(out_dev.abs().sum().item())
-    for p in players:
-        p.close()
+    # the collective alone (not overlapped), for the record: every piece's reduce back to back behind a barrier
+    reduce_alone_ms = None
+    if world > 1:
+        pieces = piece_bounds(frames, args.piece_frames) if main_bus else [(0, frames)]
+        spans = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            e0.record()
+            for (off, n) in pieces:
+                reduce_partial_bus(bus_dev[off:off + n], dst=0)
+            e1.record()
+            torch.cuda.synchronize()
+            spans.append(e0.elapsed_time(e1))
+        reduce_alone_ms = min(spans)
 
     # ---- end-to-end arm: host buffers in, host WAV data out, every step -------------------------------------------
     out_host = torch.zeros(frames, 2, dtype=torch.float32).pin_memory()
@@ -406,15 +513,19 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         p = Player(api, SR, device_ordinal=local_rank)
-        build_scene(p, args.workload, rank=rank, as_subtree=world > 1)   # uploads the sample buffer (H2D) + schedules events
-        if world > 1 or spec.get("main_bus"):
+        build_scene(p, args.workload, rank=rank, as_subtree=world > 1 or main_bus, world=world)   # uploads the sample buffer (H2D) + schedules events
+        if main_bus:
+            stage = MainBusStage(api, SR, W.add_main_bus_sends, device_ordinal=local_rank) if rank == 0 else None
+            render_sharded(p, bus_dev, args.piece_frames, stage, out_dev)
+            if rank == 0:
+                out_host.copy_(out_dev, non_blocking=False)   # the WAV data, D2H
+                stage.close()
+            torch.cuda.synchronize()
+        elif world > 1:
             p.render_device(out_dev.data_ptr(), frames)
-            if world > 1:
-                reduce_partial_bus(out_dev, dst=0)
+            reduce_partial_bus(out_dev, dst=0)
             if rank == 0:
                 out_host.copy_(out_dev, non_blocking=False)
-                if spec.get("main_bus"):
-                    out_np[:] = finish_on_main_bus(api, out_np, SR, W.add_main_bus_sends, device_ordinal=local_rank)
             torch.cuda.synchronize()
         else:
             p.render_into(out_np)                                         # graph upload (H2D), kernels, WAV data D2H
@@ -480,13 +591,26 @@ def main():
                         "grain_kernel_ms_per_step": sum(grain_ms) / K, "grain_samples_per_step": grain_samples / K,
                         "note2": "one thread per grain runs the grain's serial f64 recurrences: latency-bound today", **passes}
         else:
-            # dominant kernel: replay_kernel. Algorithmic work = active voice-frames x 2 channels x 25 flop
+            # The voice path is three passes that overlap across time blocks; the step is as fast as the pass with the longest
+            # span, so THAT is the kernel the roofline names. Algorithmic work of the path = active voice-frames x 2 channels
+            # x 25 flop, FMA-pipe bound because the voices share one L2-resident sample buffer.
             flops = (total_vframes / world) * 2 * FLOP_PER_CHANNEL_SAMPLE
-            ach = flops / (total_voice_ms / 1e3) / 1e12
-            roofline = {"bound": "fp32_fma", "kernel": "replay_kernel", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s",
+            spans = {"skeleton_kernel": sum(skel_ms), "replay_kernel": total_voice_ms, "mix_fx_kernel": sum(fx_ms)}
+            if main_bus:
+                spans["mix_fx_kernel (main-bus Delay + Reverb, rank 0)"] = sum(main_ms_all)
+            dominant = max(spans, key=lambda k: spans[k])
+            ach = flops / (spans[dominant] / 1e3) / 1e12
+            step_ach = flops / (total_dev_ms / 1e3) / 1e12
+            replay_ach = flops / (total_voice_ms / 1e3) / 1e12
+            roofline = {"bound": "fp32_fma", "kernel": dominant, "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s",
                         "frac": ach / fma_peak, "traffic": None,
-                        "peak_source": fma_src + "; voices share one L2-resident buffer so the kernel is not HBM bound",
-                        "hbm_achieved_gbs": (total_vframes / world) * 8.0 / (total_voice_ms / 1e3) / 1e9,
+                        "peak_source": fma_src + "; voices share one L2-resident buffer so the path is not HBM bound",
+                        "achieved_note": "the path's algorithmic flops (active voice-frames x 2 ch x 25) over the span of its slowest "
+                                         "pass, the one named in `kernel`; step_frac is the same work over ms_per_step",
+                        "step_achieved": step_ach, "step_frac": step_ach / fma_peak,
+                        "replay_kernel_achieved": replay_ach, "replay_kernel_frac": replay_ach / fma_peak,
+                        "fp32_peak_nominal_tflops": 74.45, "fp32_peak_used_tflops": fma_peak,
+                        "hbm_achieved_gbs": (total_vframes / world) * 8.0 / (spans[dominant] / 1e3) / 1e9,
                         "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_kind": peak_kind, **passes}
         # measured DRAM traffic of the dominant kernel (one ncu --set full capture, committed under profiles/)
         try:
@@ -501,11 +625,21 @@ def main():
                 "ms_per_step": total_dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": spec["desc"] + (f"; x{world} ranks, one subtree per GPU, NCCL reduce of the stereo bus" if world > 1 else ""),
-                           "l2": "flushed between steps (256 MiB fill)", "timing": "CUDA events on the renderer's own streams",
+                           "l2": "flushed between steps (256 MiB fill)", "timing": "CUDA events around the whole pipeline" if main_bus else "CUDA events on the renderer's own streams",
                            "wall_ms_per_step": sum(wall_ms) / K, "checksum": checksum},
                 "e2e": {"value": e2e_value, "unit": "voice-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": total_e2e_ms / K},
                 "gpu_launches": int(total_launches), "clocks": clk, "roofline": roofline}
+        if world > 1 or main_bus:
+            line["multi_gpu"] = {"reduce_ms": reduce_alone_ms, "reduce_note": "every piece's NCCL reduce back to back behind a barrier, "
+                                 "measured after the timed steps (inside them the reduces overlap the next piece's render)",
+                                 "reduce_in_step_ms": sum(red_ms_all) / K if not main_bus else None,
+                                 "pieces": len(piece_bounds(frames, args.piece_frames)) if main_bus else 1}
+            if main_bus:
+                line["multi_gpu"].update({"shard_ms": sum(shard_ms_all) / K, "main_bus_ms": sum(main_ms_all) / K,
+                                          "reduce_wait_ms": sum(wait_ms_all) / K,
+                                          "note": "ms_per_step is the span of the whole pipeline (events around it): shard pieces, "
+                                                  "per-piece reduce, rank 0's main-bus chain on piece p while p+1 renders"})
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], ref_out = cpu_baseline(args.workload)
             line.update(check_parity(api, args.workload, local_rank, ref_out))

@@ -324,7 +324,20 @@ PB200_API int pb200_stop_all_sources(pb200_renderer *r);
  * the master-volume smoothing of wav.rs:237. `out` is HOST memory. */
 PB200_API int pb200_render(pb200_renderer *r, float *out_interleaved, uint64_t frames,
                            uint64_t *frames_written);
-/* Same, but `out` is DEVICE memory of the renderer's device (no host copy). CUDA build only. */
+/* Multi-GPU renders: the main mixer of this renderer additionally receives `bus_device`, an interleaved
+ * stereo f32 bus in DEVICE memory holding the summed output of the sub-mixers that were rendered elsewhere (the reduced
+ * partial buses of the other ranks). It takes the place of those SubMixerProcessor outputs in MixedSource::write
+ * (src/source/mixed.rs:701-716): added to the main mixer's input ahead of its own children, always audible. Frame 0 of
+ * the bus is the first frame of the NEXT pb200_render* call, which consumes the attachment (the pointer is borrowed for
+ * that one call); `frames` is a multiple of block_frames; nullptr detaches. */
+PB200_API int pb200_set_main_input(pb200_renderer *r, const float *bus_device, uint64_t frames);
+/* Output frames finalized so far, counted over ALL render calls of the renderer: after a call that rendered `frames` has
+ * returned it has grown by `frames`; while a pb200_render_device call is still rendering it advances time block by time
+ * block, and the frames it has passed are final in `out_device`. The one entry point that may be called from another host
+ * thread while a render runs: a sharded render starts the reduce of a finished piece (and rank 0 its main-bus stage)
+ * without waiting for the whole render. */
+PB200_API uint64_t pb200_render_progress(const pb200_renderer *r);
+/* Same as pb200_render, but `out` is DEVICE memory of the renderer's device (no host copy). CUDA build only. */
 PB200_API int pb200_render_device(pb200_renderer *r, float *out_device, uint64_t frames,
                                   uint64_t *frames_written);
 /* Player::output_sample_frame_position (src/player.rs) */

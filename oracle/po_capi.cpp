@@ -34,8 +34,11 @@
 #define pb200_poll_status po_poll_status
 #define pb200_set_metering_interval po_set_metering_interval
 #define pb200_get_audio_level po_get_audio_level
+#define pb200_set_main_input po_set_main_input
+#define pb200_render_progress po_render_progress
 #include "../include/phonic_b200.h"
 
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <string>
@@ -61,6 +64,7 @@ struct pb200_renderer {
   ExpSmoothed smoothed_volume;
   uint64_t playback_pos = 0;  // samples
   bool finished = false;
+  std::atomic<uint64_t> progress{0};   // pb200_render_progress
   std::vector<float> block;
   double last_ms = 0;
   uint64_t last_voice_frames = 0;
@@ -530,6 +534,8 @@ int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frame
   if (frames % bf != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
   auto t0 = std::chrono::steady_clock::now();
   uint64_t done = 0;
+  const uint64_t progress_base = r->progress.load(std::memory_order_acquire);
+  struct ProgressDone { pb200_renderer* r; uint64_t total; ~ProgressDone() { r->progress.store(total, std::memory_order_release); } } progress_done{r, progress_base + frames};
   while (done < frames && !r->finished) {  // WavStream::process, wav.rs:210-250
     SourceTime time{r->playback_pos / ch};
     size_t written = r->main->write(r->block.data(), r->block.size(), time);
@@ -555,7 +561,9 @@ int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frame
     std::memcpy(out + done * ch, r->block.data(), written * sizeof(float));
     r->playback_pos += r->block.size();
     done += bf;
+    r->progress.store(progress_base + done, std::memory_order_release);
   }
+  r->main->ext_bus = nullptr; r->main->ext_frames = 0;   // (an external main-mixer input serves one render call)
   if (done < frames) std::memset(out + done * ch, 0, (frames - done) * ch * sizeof(float));
   if (frames_written) *frames_written = done;
   {  // PlaybackStatusEvent stream in a canonical order (frame, playback id, kind)
@@ -724,6 +732,17 @@ int pb200_render_to_wav(pb200_renderer* r, const char* path, uint64_t duration_n
   std::fwrite("data", 1, 4, f); w32(data_bytes);
   std::fwrite(audio.data(), 4, (size_t)written * ch, f);
   std::fclose(f);
+  return PB200_OK;
+}
+
+uint64_t pb200_render_progress(const pb200_renderer* r) { return r ? r->progress.load(std::memory_order_acquire) : 0; }
+
+int pb200_set_main_input(pb200_renderer* r, const float* bus, uint64_t frames) {
+  if (!r) return PB200_ERR_PARAMETER;
+  if (bus && frames % r->cfg.block_frames != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
+  r->main->ext_bus = bus;
+  r->main->ext_start = r->playback_pos / r->cfg.channel_count;
+  r->main->ext_frames = bus ? frames : 0;
   return PB200_OK;
 }
 

@@ -938,6 +938,8 @@ struct MixedSource : Source {
     }
     return produced;
   }
+  const float* ext_bus = nullptr;   // pb200_set_main_input (the oracle's "device" memory is host memory)
+  uint64_t ext_start = 0, ext_frames = 0;
   void process_effects(float* out, size_t len, const SourceTime& time, bool input_bypassed) {  // mixed.rs:627-655
     if (effects_bypassed && input_bypassed) return;
     bool all_bypassed = true;
@@ -949,7 +951,7 @@ struct MixedSource : Source {
   }
   size_t write(float* out, size_t len, const SourceTime& time) override {  // mixed.rs:659-719
     process_messages(time);
-    if (playing_sources.empty() && effects.empty() && mixers.empty() && events.empty()) return 0;
+    if (playing_sources.empty() && effects.empty() && mixers.empty() && events.empty() && !ext_bus) return 0;
     clear_buffer(out, len);
     size_t out_frames = len / channels;
     size_t done = 0;
@@ -967,7 +969,15 @@ struct MixedSource : Source {
       if (n > 0) {
         SourceTime ct{time.pos_in_frames + done};
         float* chunk = out + done * channels;
-        bool audible = process_sub_mixers(chunk, n * channels, ct);
+        bool audible = false;
+        if (ext_bus && ct.pos_in_frames >= ext_start && ct.pos_in_frames < ext_start + ext_frames) {
+          // pb200_set_main_input: the summed output of sub-mixers rendered elsewhere, added like a SubMixerProcessor's
+          const size_t m = (size_t)std::min<uint64_t>(n, ext_start + ext_frames - ct.pos_in_frames);
+          const float* e = ext_bus + (ct.pos_in_frames - ext_start) * channels;
+          for (size_t i = 0; i < m * channels; ++i) chunk[i] += e[i];
+          audible = true;
+        }
+        audible |= process_sub_mixers(chunk, n * channels, ct);
         audible |= process_sources(chunk, n * channels, ct);
         process_effects(chunk, n * channels, ct, !audible);
         done += n;

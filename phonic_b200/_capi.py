@@ -192,6 +192,8 @@ SYMBOLS = {
     "poll_status": (C.c_int, [_R, _P(StatusEvent), U32, _P(U32)]),
     "set_metering_interval": (C.c_int, [_R, U64]),
     "get_audio_level": (C.c_int, [_R, _P(AudioLevel)]),
+    "set_main_input": (C.c_int, [_R, C.c_void_p, U64]),
+    "render_progress": (U64, [_R]),
 }
 
 

@@ -41,12 +41,17 @@ struct MixerKernelArgs {
   uint32_t work_bytes;            // dynamic shared memory of this launch (FX_WORK_SMALL unless a mixer of the level holds a reverb)
   // Effect-chain pipelining (n_stages > 1): CTA (mixer, stage) runs the effects [stage_begin[stage], stage_begin[stage+1]) of
   // its mixer; chunk q moves from stage to stage through the mixer bus in global memory, announced by fx_progress.
-  uint32_t n_stages;              // blockDim.y of the launch; 1 = one CTA per mixer runs the whole chain
+  uint32_t n_stages;              // gridDim.y of the launch; 1 = one CTA per mixer runs the whole chain
   const uint32_t* stage_begin;    // [n_mixers][n_stages + 1] effect indices relative to fx_begin (by dense mixer index)
   uint32_t* fx_progress;          // [n_mixers][n_stages] chunks of this block finished by the stage (zeroed per block)
   uint8_t* fx_pflags;             // [n_mixers][n_stages][max_chunks] bit0 input still bypassed, bit1 some effect ran
+  uint32_t* fx_ticket;            // CTA start counter of the launch (zeroed per launch)
+  const float* ext_in;            // main mixer: external stereo bus of this block added to its input (pb200_set_main_input) or nullptr
+  uint32_t ext_len;               // frames of it inside this block
   double* meter;                  // main mixer: [wav block of the render][peak L, peak R, sum of squares L, R] or nullptr (MeteredSource)
   uint64_t render_start;          // first frame of the render call (meter rows count from it)
+  unsigned long long* progress;   // mapped host word: the main mixer's CTA stores progress_value when the block's output is final
+  unsigned long long progress_value;
   unsigned long long* prof;
   uint32_t prof_all;       // PB200_FX_PROF: [8] cycle counters of the main mixer's CTA (debug aid)
 };
@@ -70,6 +75,7 @@ __global__ void __launch_bounds__(256) mix_sum_kernel(MixerKernelArgs a) {
   }
   const uint32_t k = lo - cb;
   float2 s = make_float2(0.0f, 0.0f);
+  if (a.ext_in && mp.parent == 0xFFFFFFFFu && f < a.ext_len) s = __ldg(reinterpret_cast<const float2*>(a.ext_in) + f);   // the sub-mixers rendered elsewhere
   for (uint32_t ci = mp.child_begin; ci < mp.child_end; ++ci) {
     const uint32_t c = a.child_index[ci];
     if (a.mixer_flags[(size_t)c * a.max_chunks + k]) {
@@ -104,9 +110,20 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   extern __shared__ __align__(16) uint8_t s_work[];
   const ParWork pw{s_work, a.work_bytes};
 
-  const uint32_t m = a.level_mixers[blockIdx.x];
   const uint32_t tid = threadIdx.x, nt = blockDim.x;
-  const uint32_t stage = blockIdx.y, n_stages = a.n_stages;
+  const uint32_t n_stages = a.n_stages;
+  // Pipelined launch: a CTA's place (mixer, stage) comes from a ticket taken when it starts running, stage-major, so every
+  // CTA it will wait for holds a lower ticket and is therefore already running (or done) -- no co-residency requirement,
+  // whatever order the hardware dispatches the grid in.
+  uint32_t slot_x = blockIdx.x, stage = 0;
+  if (n_stages > 1) {
+    if (tid == 0) s_run = atomicAdd(a.fx_ticket, 1u);
+    __syncthreads();
+    const uint32_t ticket = s_run;
+    __syncthreads();
+    slot_x = ticket % gridDim.x; stage = ticket / gridDim.x;
+  }
+  const uint32_t m = a.level_mixers[slot_x];
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const MixerParams mp = a.mixers[m];
   const bool is_main = mp.parent == 0xFFFFFFFFu;
@@ -138,12 +155,20 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
 
   long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto tick = [&](int i, long long& t0) { if (a.prof) { const long long t1 = clock64(); pt[i] += t1 - t0; t0 = t1; } };
+  // pb200_render_progress: the main mixer's (last-stage) CTA writes the block's output last; once every thread's stores are
+  // out, one system-scope store tells the host that the block is final
+  auto publish_progress = [&]() {
+    if (!a.progress) return;
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) { __threadfence_system(); *reinterpret_cast<volatile unsigned long long*>(a.progress) = a.progress_value; }
+  };
   // audible input per chunk (mixed.rs:701-708): one flag per child / source and chunk, gathered for the whole block at once
   // (the children's and sources' kernels of this block have finished)
   constexpr uint32_t AUD_MAX = 1024;
   __shared__ uint8_t s_aud[AUD_MAX];
   auto audible_of = [&](const uint32_t kk) -> bool {
-    bool aud = false;
+    bool aud = is_main && a.ext_in != nullptr;   // (an external bus counts as an audible sub-mixer)
     for (uint32_t ci = mp.child_begin; ci < mp.child_end && !aud; ++ci) aud = a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (kk - cb)] != 0;
     for (uint32_t si = mp.src_begin; si < mp.src_end && !aud; ++si) aud = a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (kk - cb)] != 0;
     return aud;
@@ -166,6 +191,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
         if (scale) { v.x *= g; v.y *= g; v.z *= g; v.w *= g; }
         dst[i] = v;
       }
+      publish_progress();
       return;
     }
   }
@@ -420,6 +446,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
     }
     tick(6, t0);
   }
+  if (is_main && last_stage) publish_progress();
   if (a.prof && tid == 0 && (is_main || a.prof_all))
     for (int i = 0; i < 8; ++i) atomicAdd(a.prof + (a.prof_all ? ((size_t)m * MAX_FX_STAGES + stage) * 8 : 0) + i, (unsigned long long)pt[i]);
 }

@@ -180,6 +180,29 @@ constexpr uint32_t RING = 3;
 
 }  // namespace
 
+// Pinned, device-mapped progress words (one per renderer) out of one process-wide slab: cudaHostAlloc / cudaFreeHost per
+// renderer would synchronise the device every time a short-lived renderer comes or goes.
+class ProgressWords {
+ public:
+  static ProgressWords& get() { static ProgressWords p; return p; }
+  unsigned long long* take() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (free_.empty()) {
+      unsigned long long* slab = nullptr;
+      if (cudaHostAlloc((void**)&slab, SLAB * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+      for (size_t i = 0; i < SLAB; ++i) free_.push_back(slab + (SLAB - 1 - i));
+    }
+    unsigned long long* w = free_.back();
+    free_.pop_back();
+    return w;
+  }
+  void give(unsigned long long* w) { if (w) { std::lock_guard<std::mutex> g(mu_); free_.push_back(w); } }
+ private:
+  static constexpr size_t SLAB = 256;
+  std::mutex mu_;
+  std::vector<unsigned long long*> free_;
+};
+
 struct pb200_renderer {
   pb200_config cfg;
   std::string last_error;
@@ -279,6 +302,11 @@ struct pb200_renderer {
   pb200_audio_level audio_level{};
   uint64_t position = 0;  // frames
   bool finished = false;
+  // pb200_render_progress: output frames that are final (read from other host threads while a render runs)
+  unsigned long long* progress = nullptr;   // pinned, mapped host word: the main mixer's last CTA of a time block stores into it
+  uint64_t progress_base = 0;               // frames of all earlier render calls
+  const float* ext_input = nullptr;   // pb200_set_main_input: device stereo bus the next render adds to the main mixer
+  uint64_t ext_frames = 0;
   uint32_t time_block = 32768;
   uint64_t voice_frames_total = 0;
   pb200_render_stats stats{};
@@ -587,9 +615,19 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
   } else {
     cudaGetDevice(&r->device);
   }
-  if (cudaStreamCreateWithFlags(&r->sv, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&r->sr_, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&r->sm, cudaStreamNonBlocking) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+  // The mixer pass is the end of every time block's dependency chain and its CTAs are few and long-running: they go first
+  // when SMs free up (also against the kernels of another renderer on the same device, e.g. the shard of a sharded render
+  // next to rank 0's main-bus stage). The serial skeleton pass comes next, the wide replay launches last.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // (numerically lower = higher priority)
+  static const bool flat_prio = getenv("PB200_FLAT_PRIORITIES") != nullptr;
+  const int p_mix = flat_prio ? prio_lo : prio_hi, p_skel = flat_prio ? prio_lo : std::min(prio_lo, prio_hi + 1);
+  if (cudaStreamCreateWithPriority(&r->sv, cudaStreamNonBlocking, p_skel) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&r->sr_, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&r->sm, cudaStreamNonBlocking, p_mix) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+  r->progress = ProgressWords::get().take();
+  if (!r->progress) { delete r; return PB200_ERR_CUDA; }
+  *r->progress = 0;
   {
     double note_speed[128];
     for (uint32_t n = 0; n < 128; ++n) note_speed[n] = speed_from_note_h(n);
@@ -631,6 +669,7 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sr_) cudaStreamDestroy(r->sr_);
   if (r->sv) cudaStreamDestroy(r->sv);
   if (r->sm) cudaStreamDestroy(r->sm);
+  ProgressWords::get().give(r->progress);
   delete r;
 }
 
@@ -1502,10 +1541,15 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   if (frames % bf != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
   if (frames == 0) { if (frames_written) *frames_written = 0; return PB200_OK; }
   cudaSetDevice(r->device);
+  const uint64_t progress_base = r->progress_base;
+  struct ProgressDone {   // whatever way the call ends, pollers see it end
+    pb200_renderer* r; uint64_t total;
+    ~ProgressDone() { r->progress_base = total; __atomic_store_n(r->progress, (unsigned long long)total, __ATOMIC_RELEASE); }
+  } progress_done{r, progress_base + frames};
   // WavStream finishes when the main mixer has nothing at all to do (wav.rs:231-234, mixed.rs:664-670)
   size_t live_mixers = 0, live_fx = 0;
   for (auto& m : r->mixers) if (!m.removed) { ++live_mixers; live_fx += m.effects.size(); }
-  if (r->groups.empty() && live_fx == 0 && live_mixers == 1) r->finished = true;
+  if (r->groups.empty() && live_fx == 0 && live_mixers == 1 && !r->ext_input) r->finished = true;
   if (r->finished) {
     if (out_host) std::memset(out_host, 0, frames * 2 * sizeof(float));
     if (out_dev) CUDA_TRY(cudaMemsetAsync(out_dev, 0, frames * 2 * sizeof(float), r->sm));
@@ -1726,7 +1770,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
         }
       }
       CUDA_TRY(r->d_stage_begin.upload(stage_begin, r->sm));
-      CUDA_TRY(r->d_fx_progress.reserve(nm * (size_t)MAX_FX_STAGES));
+      CUDA_TRY(r->d_fx_progress.reserve(nm * (size_t)MAX_FX_STAGES + 1));
       CUDA_TRY(r->d_fx_pflags.reserve(nm * (size_t)MAX_FX_STAGES * max_chunks));
       CUDA_TRY(cudaStreamSynchronize(r->sm));
     }
@@ -1926,7 +1970,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     const uint32_t live_tiles = (blen + TILE - 1) / TILE;
     CUDA_TRY(cudaEventRecord(ev_r0[b], r->sr_));  // stream order: every wait of this block's replay is behind it
     static const bool skel_only = getenv("PB200_SKEL_ONLY") != nullptr;  // timing experiments: the skeleton pass alone (output invalid)
-    if (!skel_only) {  // one launch over every group (the class lists are contiguous in d_class_groups)
+    if (!skel_only && ng > 0) {  // one launch over every group (the class lists are contiguous in d_class_groups)
       ra.group_list = r->d_class_groups.p;
       dim3 grid((live_tiles + REPLAY_THREADS - 1) / REPLAY_THREADS, ng);
       replay_kernel<<<grid, REPLAY_THREADS, REPLAY_SMEM, r->sr_>>>(ra);
@@ -1948,6 +1992,10 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ma.block_len = blen;
     ma.meter = metering ? r->d_meter.p : nullptr; ma.render_start = p0;
     ma.prof = fx_prof;
+    ma.progress = out_dev ? r->progress : nullptr;
+    ma.progress_value = progress_base + (b0 - p0) + blen;
+    ma.ext_in = (r->ext_input && b0 - p0 < r->ext_frames) ? r->ext_input + (b0 - p0) * 2 : nullptr;
+    ma.ext_len = ma.ext_in ? (uint32_t)std::min<uint64_t>(blen, r->ext_frames - (b0 - p0)) : 0u;
     ma.prof_all = fx_prof_all ? 1u : 0u;
     for (int lvl = (int)c.levels.size() - 1; lvl >= 0 && !skel_only; --lvl) {
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
@@ -1961,12 +2009,13 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       ma.stage_begin = S > 1 ? r->d_stage_begin.p + stage_offsets[lvl] : nullptr;
       ma.fx_progress = S > 1 ? r->d_fx_progress.p : nullptr;
       ma.fx_pflags = S > 1 ? r->d_fx_pflags.p : nullptr;
+      ma.fx_ticket = S > 1 ? r->d_fx_progress.p + nm * (size_t)MAX_FX_STAGES : nullptr;
       if (S > 1) {
-        // all stages of a mixer must run at the same time: a cooperative launch checks that the grid is co-resident
-        CUDA_TRY(cudaMemsetAsync(r->d_fx_progress.p, 0, nm * (size_t)MAX_FX_STAGES * sizeof(uint32_t), r->sm));
-        void* kargs[] = {(void*)&ma};
-        const void* fn = level_small[lvl] ? (const void*)mix_fx_kernel<2> : (const void*)mix_fx_kernel<1>;
-        CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(nlm, S), dim3(FX_THREADS), kargs, ma.work_bytes, r->sm));
+        // (an ordinary launch: the ticket order makes the hand-over deadlock-free; a cooperative launch would serialise the
+        // kernel against everything else on the device, the replay of the next block included)
+        CUDA_TRY(cudaMemsetAsync(r->d_fx_progress.p, 0, (nm * (size_t)MAX_FX_STAGES + 1) * sizeof(uint32_t), r->sm));
+        if (level_small[lvl]) mix_fx_kernel<2><<<dim3(nlm, S), FX_THREADS, ma.work_bytes, r->sm>>>(ma);
+        else mix_fx_kernel<1><<<dim3(nlm, S), FX_THREADS, ma.work_bytes, r->sm>>>(ma);
       } else {
         mix_fx_kernel<1><<<nlm, FX_THREADS, ma.work_bytes, r->sm>>>(ma);
       }
@@ -2102,7 +2151,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     // playing source, effect, sub-mixer or pending event left (mixed.rs:664-670). Sources are dropped at the end of
     // the block they finished in; an event is popped by the chunk that starts at its time.
     uint64_t written = frames;
-    if (live_fx == 0 && live_mixers == 1) {
+    if (live_fx == 0 && live_mixers == 1 && !r->ext_input) {
       bool all_dead = true;
       uint64_t fin = p0;
       for (size_t gi = 0; gi < gs.size(); ++gi) {
@@ -2146,6 +2195,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     if (r->finished) r->position = p0 + written;  // WavStream::playback_pos stops with the stream
     if (frames_written) *frames_written = written;
   }
+  r->ext_input = nullptr; r->ext_frames = 0;   // (an external main-mixer input serves one render call)
   return PB200_OK;
 }
 
@@ -2162,6 +2212,16 @@ int pb200_render_device(pb200_renderer* r, float* out_device, uint64_t frames, u
   if (!r || !out_device) return PB200_ERR_PARAMETER;
   return render_impl(r, out_device, nullptr, frames, frames_written);
 }
+
+int pb200_set_main_input(pb200_renderer* r, const float* bus_device, uint64_t frames) {
+  if (!r) return PB200_ERR_PARAMETER;
+  if (bus_device && frames % r->cfg.block_frames != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
+  r->ext_input = bus_device;
+  r->ext_frames = bus_device ? frames : 0;
+  return PB200_OK;
+}
+
+uint64_t pb200_render_progress(const pb200_renderer* r) { return r && r->progress ? __atomic_load_n(r->progress, __ATOMIC_ACQUIRE) : 0; }
 
 int pb200_schedule_many(pb200_renderer* r, pb200_event* events, uint32_t count, uint32_t* scheduled) {
   if (!r || (!events && count)) return PB200_ERR_PARAMETER;

@@ -1210,8 +1210,11 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
   if (tid == 0) a.gstate[g] = s_gs;
 }
 
+#ifndef SKEL_LPV_MINB
+#define SKEL_LPV_MINB 1
+#endif
 template <int MAXT, bool WPV, bool SIMPLE = true>
-__global__ void __launch_bounds__(MAXT) skeleton_kernel(SkeletonArgs a, SkeletonLoop L) {
+__global__ void __launch_bounds__(MAXT, (WPV || MAXT > 256) ? 1 : SKEL_LPV_MINB) skeleton_kernel(SkeletonArgs a, SkeletonLoop L) {
   extern __shared__ __align__(128) uint32_t tab_smem[];   // WPV: [tab_slots][TAB_SLOT_WORDS] | mbarriers | parities
   TabSlot tslot;
   tslot.words = nullptr; tslot.mbar = nullptr; tslot.parity = nullptr;

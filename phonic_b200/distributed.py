@@ -9,14 +9,16 @@ from __future__ import annotations
 from typing import List, Sequence
 
 
-def assign_subtrees(weights: Sequence[int], world_size: int) -> List[List[int]]:
+def assign_subtrees(weights: Sequence[int], world_size: int, preload: Sequence[int] | None = None) -> List[List[int]]:
     """Greedy weight bin-packing of sub-mixer subtrees onto ranks -- the heuristic the reference uses
     to spread sub-mixers over its worker threads (WorkerTaskBatcher::update,
     src/source/mixed/submixer/thread_pool.rs:92-121): heaviest first (stable), each to the currently
-    lightest bin (first minimum wins, like Iterator::min_by_key)."""
+    lightest bin (first minimum wins, like Iterator::min_by_key). `preload`: load a rank carries before any subtree
+    (rank 0's main-bus effect chain, which nobody else can run), in the same units as `weights`."""
     order = sorted(range(len(weights)), key=lambda i: -weights[i])  # Python's sort is stable, like sort_by
     bins: List[List[int]] = [[] for _ in range(world_size)]
-    totals = [0] * world_size
+    totals = list(preload) if preload is not None else [0] * world_size
+    assert len(totals) == world_size
     for i in order:
         b = min(range(world_size), key=lambda k: totals[k])
         totals[b] += weights[i]
@@ -66,3 +68,147 @@ def finish_on_main_bus(api, bus, sample_rate: int, add_effects, device_ordinal: 
     finally:
         p.close()
     return out
+
+
+class MainBusStage:
+    """Rank 0's main mixer in a sharded render: a renderer that holds nothing but the main mixer's own effect chain and
+    receives the reduced sub-mixer bus piece by piece through `pb200_set_main_input` (device memory stays on the device:
+    no host round trip, no second sample upload). `add_effects(player)` attaches the chain (cfg5: Delay + Reverb)."""
+
+    def __init__(self, api, sample_rate: int, add_effects, device_ordinal: int = -1):
+        from .player import Player
+        self.player = Player(api, sample_rate, device_ordinal=device_ordinal)
+        add_effects(self.player)
+        self.device_ms = 0.0
+        self.kernel_launches = 0
+
+    def process(self, bus, out):
+        """bus, out: torch tensors [n, 2] f32, contiguous, both on the renderer's device (CPU tensors for the oracle)."""
+        n = bus.shape[0]
+        self.player.set_main_input(bus.data_ptr(), n)
+        if out.is_cuda:
+            self.player.render_device(out.data_ptr(), n)
+        else:
+            self.player.render_into(out.numpy())
+        st = self.player.last_render_stats()
+        self.device_ms += st.device_ms
+        self.kernel_launches += int(st.kernel_launches)
+
+    def close(self):
+        self.player.close()
+
+
+def piece_bounds(frames: int, piece_frames: int):
+    """[(offset, length)] of the pieces a sharded render is cut into (whole multiples of the 1024-frame block)."""
+    assert frames % 1024 == 0 and piece_frames % 1024 == 0 and piece_frames > 0
+    return [(o, min(piece_frames, frames - o)) for o in range(0, frames, piece_frames)]
+
+
+def render_sharded(player, bus, piece_frames: int, main_stage: MainBusStage | None = None, out=None, group=None, stats=None):
+    """One render of a graph partitioned over the ranks of `group`, pipelined piece by piece:
+
+      every rank   renders its sub-mixer subtrees into `bus` (its partial stereo bus) in ONE render call -- the renderer's
+                   own pipelining across time blocks stays intact -- while a second host thread follows
+                   `pb200_render_progress` and starts the reduce of every finished piece onto rank 0 (asynchronously:
+                   NCCL's stream / gloo's thread);
+      rank 0 only  a third thread waits for the reduce of piece p and runs the main mixer's own effect chain on it
+                   (`main_stage`, nonlinear in the sum, so not shardable) into `out[p]`, while the shards render on.
+
+    `bus`, `out`: torch [frames, 2] f32 on the rank's device. Without a process group the reduce is skipped (one rank).
+    Returns `out` on rank 0 when there is a main stage, else `bus` (the reduced sum on rank 0)."""
+    import queue
+    import threading
+    import time
+
+    import torch
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if distributed else 0
+    frames = bus.shape[0]
+    pieces = piece_bounds(frames, piece_frames)
+    ready: "queue.Queue" = queue.Queue()
+    err = []
+    wait_s = [0.0]
+    works = []
+    base = player.render_progress()
+    render_over = threading.Event()
+    has_stage = main_stage is not None and rank == 0
+    if has_stage:
+        assert out is not None
+
+    def follow():  # every rank: the collectives, in piece order, as the pieces become final
+        try:
+            if bus.is_cuda:
+                torch.cuda.set_device(bus.device)
+            for (off, n) in pieces:
+                while player.render_progress() - base < off + n:
+                    if render_over.is_set() and player.render_progress() - base < off + n:
+                        return   # the render call failed; the caller raises
+                    time.sleep(0.00005)
+                work = dist.reduce(bus[off:off + n], dst=0, op=dist.ReduceOp.SUM, group=group, async_op=True) if distributed else True
+                works.append(work)
+                if has_stage:
+                    ready.put(work)
+        except BaseException as e:
+            err.append(e)
+        finally:
+            if has_stage:
+                ready.put(None)
+
+    def consume():  # rank 0: the main mixer's own chain on every reduced piece
+        try:
+            if bus.is_cuda:
+                torch.cuda.set_device(bus.device)
+                side = torch.cuda.Stream(device=bus.device)
+            for (off, n) in pieces:
+                work = ready.get()
+                if work is None:
+                    return
+                t0 = time.perf_counter()
+                if work is not True:
+                    if bus.is_cuda:
+                        with torch.cuda.stream(side):
+                            work.wait()          # the side stream waits for the collective; then the host for the stream
+                        side.synchronize()
+                    else:
+                        work.wait()
+                wait_s[0] += time.perf_counter() - t0
+                main_stage.process(bus[off:off + n], out[off:off + n])
+        except BaseException as e:  # surfaced by the caller
+            err.append(e)
+
+    threads = []
+    if distributed or has_stage:
+        threads.append(threading.Thread(target=follow, name="piece-reduce"))
+    if has_stage:
+        threads.append(threading.Thread(target=consume, name="main-bus-stage"))
+    for t in threads:
+        t.start()
+    try:
+        if bus.is_cuda:
+            player.render_device(bus.data_ptr(), frames)
+        else:
+            player.render_into(bus.numpy())
+    finally:
+        render_over.set()
+        for t in threads:
+            t.join()
+    for w in works:
+        if w is not True:
+            w.wait()
+    if bus.is_cuda:
+        torch.cuda.synchronize(bus.device)
+    if err:
+        raise err[0]
+    if stats is not None:
+        st = player.last_render_stats()
+        stats["shard_ms"] = st.device_ms
+        stats["shard_launches"] = int(st.kernel_launches) + (len(pieces) if distributed else 0)
+        stats["pieces"] = len(pieces)
+        for k in ("voice_kernel_ms", "skeleton_kernel_ms", "effect_kernel_ms", "voice_frames"):
+            stats[k] = getattr(st, k)
+        if has_stage:
+            stats["main_bus_ms"] = main_stage.device_ms
+            stats["main_bus_launches"] = main_stage.kernel_launches
+            stats["reduce_wait_ms"] = wait_s[0] * 1e3
+    return out if has_stage else bus

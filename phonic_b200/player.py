@@ -581,6 +581,15 @@ class Player:
         self._check(self.api.render_device(self._r, C.c_void_p(device_ptr), frames, C.byref(written)))
         return written.value
 
+    def render_progress(self) -> int:
+        """Output frames finalized so far over all render calls (callable from another thread while `render*` runs)."""
+        return int(self.api.render_progress(self._r))
+
+    def set_main_input(self, device_ptr: int | None, frames: int = 0) -> None:
+        """Multi-GPU renders: the next render adds the stereo f32 bus at `device_ptr` (device memory; host memory for the
+        oracle) to the main mixer's input -- the reduced output of the sub-mixers rendered on other ranks. None detaches."""
+        self._check(self.api.set_main_input(self._r, C.c_void_p(device_ptr) if device_ptr else None, frames))
+
     def output_sample_frame_position(self) -> int:
         return int(self.api.position(self._r))
 

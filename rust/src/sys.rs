@@ -283,6 +283,8 @@ extern "C" {
     pub fn pb200_move_effect(r: *mut pb200_renderer, effect_id: u32, mixer_id: u32, movement: u32, offset: i32) -> c_int;
     pub fn pb200_stop_all_sources(r: *mut pb200_renderer) -> c_int;
     pub fn pb200_render(r: *mut pb200_renderer, out_interleaved: *mut f32, frames: u64, frames_written: *mut u64) -> c_int;
+    pub fn pb200_render_progress(r: *const pb200_renderer) -> u64;
+    pub fn pb200_set_main_input(r: *mut pb200_renderer, bus_device: *const f32, frames: u64) -> c_int;
     pub fn pb200_render_device(r: *mut pb200_renderer, out_device: *mut f32, frames: u64, frames_written: *mut u64) -> c_int;
     pub fn pb200_position(r: *const pb200_renderer) -> u64;
     pub fn pb200_decode_wav(path: *const c_char, interleaved: *mut *mut f32, info: *mut pb200_wav_info) -> c_int;

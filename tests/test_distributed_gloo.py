@@ -51,6 +51,18 @@ def worker(rank, world, port, result_path):
         from phonic_b200.distributed import finish_on_main_bus
         from phonic_b200.player import DelayEffect
         np.save(result_path.replace(".npy", "_main.npy"), finish_on_main_bus(api, part.numpy(), 48000, lambda q: q.add_effect(DelayEffect())))
+    # the pipelined form: pieces rendered, reduced and run through rank 0's main-bus stage while the next piece renders
+    from phonic_b200.distributed import MainBusStage, render_sharded
+    from phonic_b200.player import DelayEffect as Delay2
+    p = Player(api, 48000)
+    build(p, mine)
+    bus, out = torch.zeros(FRAMES, 2), torch.zeros(FRAMES, 2)
+    stage = MainBusStage(api, 48000, lambda q: q.add_effect(Delay2())) if rank == 0 else None
+    stats = {}
+    render_sharded(p, bus, 5 * 1024, stage, out, stats=stats)
+    if rank == 0:
+        assert stats["pieces"] == 5 and stats["main_bus_ms"] > 0.0
+        np.save(result_path.replace(".npy", "_pipelined.npy"), out.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -88,6 +100,10 @@ def test_two_rank_reduce_matches_single_process_render(tmp_path, oracle_api):
     two_stage = np.load(result.replace(".npy", "_main.npy"))
     assert float(np.abs(full_main).max()) > 0.05
     assert float(np.abs(two_stage - full_main).max()) <= 2e-6
+    # ... and the pipelined render (per-piece reduce, main-bus stage fed through pb200_set_main_input) gives the same bytes
+    # as the two-stage one: same partial sums, same reduce, same chain on the same 1024-frame chunks
+    pipelined = np.load(result.replace(".npy", "_pipelined.npy"))
+    assert np.array_equal(pipelined, two_stage)
 
 
 def test_main_bus_stage_alone_is_bit_exact(oracle_api):
@@ -112,3 +128,43 @@ def test_main_bus_stage_alone_is_bit_exact(oracle_api):
     p.close()
     assert float(np.abs(full).max()) > 0.05
     assert np.array_equal(two_stage, full)
+
+
+def test_main_input_stage_is_bit_exact(oracle_api):
+    """pb200_set_main_input: the main mixer fed with the sub-mixers' summed bus (rendered by another renderer, in pieces)
+    gives the bytes of the single-graph render, and so does rendering the shard in pieces."""
+    import torch
+    from phonic_b200.distributed import MainBusStage, render_sharded
+    from phonic_b200.player import DelayEffect, FilterEffect, Player
+
+    def chain(q):
+        q.add_effect(FilterEffect(0, 3000.0, 0.707))
+        q.add_effect(DelayEffect())
+    p = Player(oracle_api, 48000)
+    build(p, [0, 1, 2])
+    bus, out = torch.zeros(FRAMES, 2), torch.zeros(FRAMES, 2)
+    stage = MainBusStage(oracle_api, 48000, chain)
+    stats = {}
+    render_sharded(p, bus, 7 * 1024, stage, out, stats=stats)
+    p.close()
+    stage.close()
+    assert stats["pieces"] == 4
+    p = Player(oracle_api, 48000)
+    build(p, [0, 1, 2])
+    chain(p)
+    full = p.render(FRAMES)
+    p.close()
+    assert float(np.abs(full).max()) > 0.05
+    assert np.array_equal(out.numpy(), full)
+
+
+def test_main_input_serves_one_render_call(oracle_api):
+    from phonic_b200.player import Player
+    p = Player(oracle_api, 48000)
+    bus = (np.random.default_rng(3).standard_normal((2048, 2)) * 0.1).astype(np.float32)
+    p.set_main_input(bus.ctypes.data, 2048)
+    assert np.array_equal(p.render(2048), bus)
+    assert not p.render(1024).any()          # detached again: the empty main mixer writes nothing
+    with pytest.raises(Exception):
+        p.set_main_input(bus.ctypes.data, 1000)  # not a multiple of the block
+    p.close()
