@@ -372,7 +372,9 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--piece-frames", type=int, default=131072,
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="cfg5 at N > 1: pieces travel as DMA pushes into rank 0's IPC staging buses (peer) or as NCCL reduces (nccl)")
+    ap.add_argument("--piece-frames", type=int, default=65536,
                     help="cfg5: frames per piece of the pipelined sharded render (shards render piece p+1 while rank 0's main-bus stage runs p)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -383,7 +385,7 @@ def main():
 
     import phonic_b200
     from phonic_b200 import workloads as W
-    from phonic_b200.distributed import MainBusStage, piece_bounds, reduce_partial_bus, render_sharded
+    from phonic_b200.distributed import MainBusStage, PeerBus, piece_bounds, reduce_partial_bus, render_sharded
     from phonic_b200.player import Player
 
     rank = int(os.environ.get("RANK", "0"))
@@ -415,6 +417,9 @@ def main():
         stages.append(MainBusStage(api, SR, W.add_main_bus_sends, device_ordinal=local_rank) if main_bus and rank == 0 else None)
     out_dev = torch.zeros(frames, 2, dtype=torch.float32, device=device)
     bus_dev = torch.zeros(frames, 2, dtype=torch.float32, device=device) if main_bus else out_dev
+    peer = None
+    if main_bus and world > 1 and args.transport == "peer":
+        peer = PeerBus(api, frames, len(piece_bounds(frames, args.piece_frames)), local_rank)
     clocks = ClockSampler(local_rank)
     dev_ms, wall_ms, voice_ms, skel_ms, fx_ms, launches, vframes = [], [], [], [], [], 0, 0
     sinc_ms, grain_ms, sinc_frames, grain_samples = [], [], 0, 0
@@ -441,10 +446,12 @@ def main():
                 dist.barrier()
             e0.record()
             pst = {}
-            render_sharded(p, bus_dev, args.piece_frames, stages[i], out_dev, stats=pst)
+            render_sharded(p, bus_dev, args.piece_frames, stages[i], out_dev, stats=pst, peer=peer)
             e1.record()
             torch.cuda.synchronize()
             step_ms = e0.elapsed_time(e1)
+            if "reduce_latency_ms" in pst:
+                print(f"[rank {rank}] step {i} reduce latencies {pst['reduce_latency_ms']} shard {pst['shard_ms']:.1f}", file=sys.stderr)
             extra_launches = pst["shard_launches"] + pst.get("main_bus_launches", 0)
             if i >= args.warmup:
                 shard_ms_all.append(pst["shard_ms"]); main_ms_all.append(pst.get("main_bus_ms", 0.0)); wait_ms_all.append(pst.get("reduce_wait_ms", 0.0))
@@ -516,7 +523,7 @@ def main():
         build_scene(p, args.workload, rank=rank, as_subtree=world > 1 or main_bus, world=world)   # uploads the sample buffer (H2D) + schedules events
         if main_bus:
             stage = MainBusStage(api, SR, W.add_main_bus_sends, device_ordinal=local_rank) if rank == 0 else None
-            render_sharded(p, bus_dev, args.piece_frames, stage, out_dev)
+            render_sharded(p, bus_dev, args.piece_frames, stage, out_dev, peer=peer)
             if rank == 0:
                 out_host.copy_(out_dev, non_blocking=False)   # the WAV data, D2H
                 stage.close()
@@ -551,6 +558,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    shard_ms_max = allmax(sum(shard_ms_all)) if main_bus else 0.0   # the slowest rank's shard render (device span)
     total_dev_ms = allmax(sum(dev_ms))
     total_e2e_ms = allmax(sum(e2e_ms))
     total_voice_ms = allmax(sum(voice_ms))
@@ -634,9 +642,12 @@ def main():
             line["multi_gpu"] = {"reduce_ms": reduce_alone_ms, "reduce_note": "every piece's NCCL reduce back to back behind a barrier, "
                                  "measured after the timed steps (inside them the reduces overlap the next piece's render)",
                                  "reduce_in_step_ms": sum(red_ms_all) / K if not main_bus else None,
-                                 "pieces": len(piece_bounds(frames, args.piece_frames)) if main_bus else 1}
+                                 "pieces": len(piece_bounds(frames, args.piece_frames)) if main_bus else 1,
+                                 "transport": ("peer: DMA pushes into rank 0's IPC staging buses, summed in rank order by its main mixer"
+                                               if peer is not None else "nccl reduce")}
             if main_bus:
-                line["multi_gpu"].update({"shard_ms": sum(shard_ms_all) / K, "main_bus_ms": sum(main_ms_all) / K,
+                line["multi_gpu"].update({"shard_ms": sum(shard_ms_all) / K, "shard_ms_slowest_rank": shard_ms_max / K,
+                                          "submixers_per_rank": cfg5_submixers(world), "main_bus_ms": sum(main_ms_all) / K,
                                           "reduce_wait_ms": sum(wait_ms_all) / K,
                                           "note": "ms_per_step is the span of the whole pipeline (events around it): shard pieces, "
                                                   "per-piece reduce, rank 0's main-bus chain on piece p while p+1 renders"})
@@ -646,6 +657,8 @@ def main():
         elif world > 1:
             line["cpu_baseline"] = None
         print(json.dumps(line))
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

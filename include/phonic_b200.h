@@ -331,6 +331,28 @@ PB200_API int pb200_render(pb200_renderer *r, float *out_interleaved, uint64_t f
  * the bus is the first frame of the NEXT pb200_render* call, which consumes the attachment (the pointer is borrowed for
  * that one call); `frames` is a multiple of block_frames; nullptr detaches. */
 PB200_API int pb200_set_main_input(pb200_renderer *r, const float *bus_device, uint64_t frames);
+/* Same with up to PB200_MAX_MAIN_INPUTS buses, added in the order given (one per rank of a sharded render: the sum order is
+ * fixed, unlike a tree reduce's). */
+#define PB200_MAX_MAIN_INPUTS 8
+PB200_API int pb200_set_main_inputs(pb200_renderer *r, const float *const *buses_device, uint32_t count, uint64_t frames);
+
+/* ---- peer memory for sharded renders (CUDA build only; no reference counterpart: the reference's sub-mixer workers share
+ * one address space, src/source/mixed/submixer/thread_pool.rs) --------------------------------------------------------------
+ * A rank's finished piece travels to rank 0 as a stream-ordered DMA copy into memory rank 0 allocated and exported through
+ * CUDA IPC, followed by a 4-byte flag: no kernel is involved, so the transfer does not queue behind the kernels of a device
+ * that is busy rendering. pb200_device_alloc: zero-filled cudaMalloc memory (IPC-exportable, unlike a caching allocator's
+ * sub-blocks); pb200_ipc_export / _open / _close: cudaIpcMemHandle_t as 64 opaque bytes; pb200_push_async: copy
+ * `bytes` from this renderer's device to `dst_peer`, then store `flag_value` to `flag_peer` (may be NULL), in order, on the
+ * renderer's copy stream; pb200_push_sync waits for all pushes; pb200_peek_u32 reads `count` words of device memory. */
+PB200_API int pb200_device_alloc(int device_ordinal, size_t bytes, void **ptr);
+PB200_API int pb200_device_free(void *ptr);
+PB200_API int pb200_ipc_export(const void *ptr, void *handle64);
+PB200_API int pb200_ipc_open(const void *handle64, int device_ordinal, void **ptr);
+PB200_API int pb200_ipc_close(void *ptr);
+PB200_API int pb200_push_async(pb200_renderer *r, void *dst_peer, const void *src_device, size_t bytes, uint32_t *flag_peer,
+                               uint32_t flag_value);
+PB200_API int pb200_push_sync(pb200_renderer *r);
+PB200_API int pb200_peek_u32(pb200_renderer *r, const uint32_t *src_device, uint32_t count, uint32_t *out_host);
 /* Output frames finalized so far, counted over ALL render calls of the renderer: after a call that rendered `frames` has
  * returned it has grown by `frames`; while a pb200_render_device call is still rendering it advances time block by time
  * block, and the frames it has passed are final in `out_device`. The one entry point that may be called from another host

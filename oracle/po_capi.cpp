@@ -36,6 +36,15 @@
 #define pb200_get_audio_level po_get_audio_level
 #define pb200_set_main_input po_set_main_input
 #define pb200_render_progress po_render_progress
+#define pb200_set_main_inputs po_set_main_inputs
+#define pb200_device_alloc po_device_alloc
+#define pb200_device_free po_device_free
+#define pb200_ipc_export po_ipc_export
+#define pb200_ipc_open po_ipc_open
+#define pb200_ipc_close po_ipc_close
+#define pb200_push_async po_push_async
+#define pb200_push_sync po_push_sync
+#define pb200_peek_u32 po_peek_u32
 #include "../include/phonic_b200.h"
 
 #include <atomic>
@@ -563,7 +572,7 @@ int pb200_render(pb200_renderer* r, float* out, uint64_t frames, uint64_t* frame
     done += bf;
     r->progress.store(progress_base + done, std::memory_order_release);
   }
-  r->main->ext_bus = nullptr; r->main->ext_frames = 0;   // (an external main-mixer input serves one render call)
+  r->main->ext_bus.clear(); r->main->ext_frames = 0;   // (external main-mixer inputs serve one render call)
   if (done < frames) std::memset(out + done * ch, 0, (frames - done) * ch * sizeof(float));
   if (frames_written) *frames_written = done;
   {  // PlaybackStatusEvent stream in a canonical order (frame, playback id, kind)
@@ -737,14 +746,25 @@ int pb200_render_to_wav(pb200_renderer* r, const char* path, uint64_t duration_n
 
 uint64_t pb200_render_progress(const pb200_renderer* r) { return r ? r->progress.load(std::memory_order_acquire) : 0; }
 
-int pb200_set_main_input(pb200_renderer* r, const float* bus, uint64_t frames) {
-  if (!r) return PB200_ERR_PARAMETER;
-  if (bus && frames % r->cfg.block_frames != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
-  r->main->ext_bus = bus;
+int pb200_set_main_inputs(pb200_renderer* r, const float* const* buses, uint32_t count, uint64_t frames) {
+  if (!r || (count && !buses)) return PB200_ERR_PARAMETER;
+  if (count > PB200_MAX_MAIN_INPUTS) return fail(r, PB200_ERR_PARAMETER, "too many main-mixer inputs");
+  if (count && frames % r->cfg.block_frames != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
+  r->main->ext_bus.assign(buses, buses + count);
   r->main->ext_start = r->playback_pos / r->cfg.channel_count;
-  r->main->ext_frames = bus ? frames : 0;
+  r->main->ext_frames = count ? frames : 0;
   return PB200_OK;
 }
+int pb200_set_main_input(pb200_renderer* r, const float* bus, uint64_t frames) { return pb200_set_main_inputs(r, &bus, bus ? 1u : 0u, frames); }
+// peer memory: device-only
+int pb200_device_alloc(int, size_t, void**) { return PB200_ERR_UNSUPPORTED; }
+int pb200_device_free(void*) { return PB200_ERR_UNSUPPORTED; }
+int pb200_ipc_export(const void*, void*) { return PB200_ERR_UNSUPPORTED; }
+int pb200_ipc_open(const void*, int, void**) { return PB200_ERR_UNSUPPORTED; }
+int pb200_ipc_close(void*) { return PB200_ERR_UNSUPPORTED; }
+int pb200_push_async(pb200_renderer* r, void*, const void*, size_t, uint32_t*, uint32_t) { return fail(r, PB200_ERR_UNSUPPORTED, "oracle has no device memory"); }
+int pb200_push_sync(pb200_renderer* r) { return fail(r, PB200_ERR_UNSUPPORTED, "oracle has no device memory"); }
+int pb200_peek_u32(pb200_renderer* r, const uint32_t*, uint32_t, uint32_t*) { return fail(r, PB200_ERR_UNSUPPORTED, "oracle has no device memory"); }
 
 int pb200_render_device(pb200_renderer* r, float*, uint64_t, uint64_t*) { return fail(r, PB200_ERR_UNSUPPORTED, "oracle has no device memory"); }
 

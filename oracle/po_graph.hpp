@@ -938,7 +938,7 @@ struct MixedSource : Source {
     }
     return produced;
   }
-  const float* ext_bus = nullptr;   // pb200_set_main_input (the oracle's "device" memory is host memory)
+  std::vector<const float*> ext_bus;   // pb200_set_main_inputs (the oracle's "device" memory is host memory)
   uint64_t ext_start = 0, ext_frames = 0;
   void process_effects(float* out, size_t len, const SourceTime& time, bool input_bypassed) {  // mixed.rs:627-655
     if (effects_bypassed && input_bypassed) return;
@@ -951,7 +951,7 @@ struct MixedSource : Source {
   }
   size_t write(float* out, size_t len, const SourceTime& time) override {  // mixed.rs:659-719
     process_messages(time);
-    if (playing_sources.empty() && effects.empty() && mixers.empty() && events.empty() && !ext_bus) return 0;
+    if (playing_sources.empty() && effects.empty() && mixers.empty() && events.empty() && ext_bus.empty()) return 0;
     clear_buffer(out, len);
     size_t out_frames = len / channels;
     size_t done = 0;
@@ -970,11 +970,13 @@ struct MixedSource : Source {
         SourceTime ct{time.pos_in_frames + done};
         float* chunk = out + done * channels;
         bool audible = false;
-        if (ext_bus && ct.pos_in_frames >= ext_start && ct.pos_in_frames < ext_start + ext_frames) {
-          // pb200_set_main_input: the summed output of sub-mixers rendered elsewhere, added like a SubMixerProcessor's
+        if (!ext_bus.empty() && ct.pos_in_frames >= ext_start && ct.pos_in_frames < ext_start + ext_frames) {
+          // pb200_set_main_inputs: the outputs of sub-mixers rendered elsewhere, added like SubMixerProcessors', in order
           const size_t m = (size_t)std::min<uint64_t>(n, ext_start + ext_frames - ct.pos_in_frames);
-          const float* e = ext_bus + (ct.pos_in_frames - ext_start) * channels;
-          for (size_t i = 0; i < m * channels; ++i) chunk[i] += e[i];
+          for (const float* bus : ext_bus) {
+            const float* e = bus + (ct.pos_in_frames - ext_start) * channels;
+            for (size_t i = 0; i < m * channels; ++i) chunk[i] += e[i];
+          }
           audible = true;
         }
         audible |= process_sub_mixers(chunk, n * channels, ct);

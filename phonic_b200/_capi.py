@@ -194,6 +194,15 @@ SYMBOLS = {
     "get_audio_level": (C.c_int, [_R, _P(AudioLevel)]),
     "set_main_input": (C.c_int, [_R, C.c_void_p, U64]),
     "render_progress": (U64, [_R]),
+    "set_main_inputs": (C.c_int, [_R, _P(C.c_void_p), U32, U64]),
+    "device_alloc": (C.c_int, [C.c_int, C.c_size_t, _P(C.c_void_p)]),
+    "device_free": (C.c_int, [C.c_void_p]),
+    "ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ipc_open": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_void_p)]),
+    "ipc_close": (C.c_int, [C.c_void_p]),
+    "push_async": (C.c_int, [_R, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, U32]),
+    "push_sync": (C.c_int, [_R]),
+    "peek_u32": (C.c_int, [_R, C.c_void_p, U32, _P(U32)]),
 }
 
 

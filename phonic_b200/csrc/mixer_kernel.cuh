@@ -15,6 +15,8 @@
 
 namespace pb {
 
+constexpr uint32_t PB_MAX_EXT = 8;   // external buses of a main mixer (PB200_MAX_MAIN_INPUTS)
+
 struct MixerKernelArgs {
   const MixerParams* mixers;
   MixerState* mstate;
@@ -46,8 +48,9 @@ struct MixerKernelArgs {
   uint32_t* fx_progress;          // [n_mixers][n_stages] chunks of this block finished by the stage (zeroed per block)
   uint8_t* fx_pflags;             // [n_mixers][n_stages][max_chunks] bit0 input still bypassed, bit1 some effect ran
   uint32_t* fx_ticket;            // CTA start counter of the launch (zeroed per launch)
-  const float* ext_in;            // main mixer: external stereo bus of this block added to its input (pb200_set_main_input) or nullptr
-  uint32_t ext_len;               // frames of it inside this block
+  const float* ext_in[PB_MAX_EXT]; // main mixer: external stereo buses of this block added to its input, in order (pb200_set_main_inputs)
+  uint32_t n_ext;
+  uint32_t ext_len;               // frames of them inside this block
   double* meter;                  // main mixer: [wav block of the render][peak L, peak R, sum of squares L, R] or nullptr (MeteredSource)
   uint64_t render_start;          // first frame of the render call (meter rows count from it)
   unsigned long long* progress;   // mapped host word: the main mixer's CTA stores progress_value when the block's output is final
@@ -75,7 +78,8 @@ __global__ void __launch_bounds__(256) mix_sum_kernel(MixerKernelArgs a) {
   }
   const uint32_t k = lo - cb;
   float2 s = make_float2(0.0f, 0.0f);
-  if (a.ext_in && mp.parent == 0xFFFFFFFFu && f < a.ext_len) s = __ldg(reinterpret_cast<const float2*>(a.ext_in) + f);   // the sub-mixers rendered elsewhere
+  if (a.n_ext && mp.parent == 0xFFFFFFFFu && f < a.ext_len)   // the sub-mixers rendered elsewhere, summed in the order given
+    for (uint32_t e = 0; e < a.n_ext; ++e) { const float2 v = __ldcg(reinterpret_cast<const float2*>(a.ext_in[e]) + f); s.x += v.x; s.y += v.y; }
   for (uint32_t ci = mp.child_begin; ci < mp.child_end; ++ci) {
     const uint32_t c = a.child_index[ci];
     if (a.mixer_flags[(size_t)c * a.max_chunks + k]) {
@@ -100,7 +104,9 @@ constexpr uint32_t FX_WORK_SMALL = 48 * 1024;   // every effect but the whole-ch
 constexpr uint32_t FX_WORK_BYTES = 120 * 1024;  // shared-memory work area of the chunk-parallel effects (the reverb's ten f64 planes of a whole chunk)
 
 // MINB = 2: the 128-register build, two CTAs per SM, for levels whose pipeline needs more co-resident CTAs than SMs
-template <int MINB>
+// PLAIN: the build for mixers WITHOUT effects (gate / master volume / output only): a few dozen registers, so its CTAs find
+// room next to the resident skeleton and replay CTAs instead of waiting for a whole free SM like the effect build does.
+template <int MINB, bool PLAIN = false>
 __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArgs a) {
   __shared__ float s_ch[2][PLANE];
   __shared__ double s_scratch[2][PLANE];
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const MixerParams mp = a.mixers[m];
   const bool is_main = mp.parent == 0xFFFFFFFFu;
-  const bool has_fx = mp.fx_end > mp.fx_begin;
+  const bool has_fx = !PLAIN && mp.fx_end > mp.fx_begin;
   // the effects this CTA runs, and its place in the mixer's pipeline
   uint32_t e_lo = mp.fx_begin, e_hi = mp.fx_end;
   if (n_stages > 1) {
@@ -153,6 +159,8 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   cbuf.scratch = &s_scratch[0][0];
   cbuf.lane_state = &s_lane_state[0][0];
 
+  float gate_mx = 0.0f;          // this thread's share of max|x| over the written-back chunks of the open parent chunk
+  uint32_t gate_covered = 0;     // frames of the open parent chunk those chunks cover (uniform)
   long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto tick = [&](int i, long long& t0) { if (a.prof) { const long long t1 = clock64(); pt[i] += t1 - t0; t0 = t1; } };
   // pb200_render_progress: the main mixer's (last-stage) CTA writes the block's output last; once every thread's stores are
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   constexpr uint32_t AUD_MAX = 1024;
   __shared__ uint8_t s_aud[AUD_MAX];
   auto audible_of = [&](const uint32_t kk) -> bool {
-    bool aud = is_main && a.ext_in != nullptr;   // (an external bus counts as an audible sub-mixer)
+    bool aud = is_main && a.n_ext != 0;   // (an external bus counts as an audible sub-mixer)
     for (uint32_t ci = mp.child_begin; ci < mp.child_end && !aud; ++ci) aud = a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (kk - cb)] != 0;
     for (uint32_t si = mp.src_begin; si < mp.src_end && !aud; ++si) aud = a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (kk - cb)] != 0;
     return aud;
@@ -349,8 +357,10 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
           }
           chunk_done = true;
         } else {
-          // write the processed chunk back
-          for (uint32_t i = tid; i < len * 2; i += nt) gchunk[i] = s_ch[i & 1][pidx(i >> 1)];
+          // write the processed chunk back; a sub-mixer's silence gate wants max|x| of the parent chunk: collected here,
+          // from shared memory, instead of re-reading the bus
+          for (uint32_t i = tid; i < len * 2; i += nt) { const float x = s_ch[i & 1][pidx(i >> 1)]; gchunk[i] = x; gate_mx = fmaxf(gate_mx, fabsf(x)); }
+          gate_covered += len;
         }
       } else if (n_stages > 1 && tid == 0) {
         for (uint32_t e = e_lo; e < e_hi; ++e) a.fx[e].bypassed = 1u;   // (the transition the skipped loop would have made)
@@ -422,8 +432,10 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
         const uint64_t p0 = a.chunk_bounds[pk];
         const uint32_t o0 = (uint32_t)(p0 - a.block_start);
         const uint32_t pl = (uint32_t)(c1 - p0);
-        float mx = 0.0f;
-        for (uint32_t i = tid; i < pl * 2; i += nt) mx = fmaxf(mx, fabsf(bus[(size_t)o0 * 2 + i]));
+        // frames of the span whose maximum the write-back above has not seen (chunks the effects skipped, mixers without effects)
+        float mx = gate_mx;
+        if (gate_covered != pl) { mx = 0.0f; for (uint32_t i = tid; i < pl * 2; i += nt) mx = fmaxf(mx, fabsf(bus[(size_t)o0 * 2 + i])); }
+        gate_mx = 0.0f; gate_covered = 0;
         for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         if (lane == 0) s_red[warp] = mx;
         __syncthreads();

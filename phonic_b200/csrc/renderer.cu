@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -305,8 +306,12 @@ struct pb200_renderer {
   // pb200_render_progress: output frames that are final (read from other host threads while a render runs)
   unsigned long long* progress = nullptr;   // pinned, mapped host word: the main mixer's last CTA of a time block stores into it
   uint64_t progress_base = 0;               // frames of all earlier render calls
-  const float* ext_input = nullptr;   // pb200_set_main_input: device stereo bus the next render adds to the main mixer
+  const float* ext_input[PB_MAX_EXT] = {};   // pb200_set_main_inputs: device stereo buses the next render adds to the main mixer
+  uint32_t n_ext = 0;
   uint64_t ext_frames = 0;
+  cudaStream_t sc = nullptr;                 // pb200_push_async: copies to a peer (DMA, no SMs)
+  uint32_t* push_flags = nullptr;            // pinned ring of flag values in flight
+  uint32_t push_seq = 0;
   uint32_t time_block = 32768;
   uint64_t voice_frames_total = 0;
   pb200_render_stats stats{};
@@ -617,13 +622,18 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
   }
   // The mixer pass is the end of every time block's dependency chain and its CTAs are few and long-running: they go first
   // when SMs free up (also against the kernels of another renderer on the same device, e.g. the shard of a sharded render
-  // next to rank 0's main-bus stage). The serial skeleton pass comes next, the wide replay launches last.
+  // next to rank 0's main-bus stage).
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // (numerically lower = higher priority)
   static const bool flat_prio = getenv("PB200_FLAT_PRIORITIES") != nullptr;
-  const int p_mix = flat_prio ? prio_lo : prio_hi, p_skel = flat_prio ? prio_lo : std::min(prio_lo, prio_hi + 1);
+  // The serial skeleton pass comes next, the wide replay launches last (best whole-render time). PB200_PRIO_ORDER=replay
+  // swaps the two: a time block that has been walked is finished before the walk of later blocks takes the SMs -- the first
+  // pieces of a sharded render leave earlier (cfg5 rank with 106 sub-mixers: 30 -> 22 ms) but the render ends later (62 -> 72).
+  static const bool skel_first = !(getenv("PB200_PRIO_ORDER") && !strcmp(getenv("PB200_PRIO_ORDER"), "replay"));
+  const int p_mid = std::min(prio_lo, prio_hi + 1);
+  const int p_mix = flat_prio ? prio_lo : prio_hi, p_skel = flat_prio || !skel_first ? prio_lo : p_mid, p_rep = flat_prio || skel_first ? prio_lo : p_mid;
   if (cudaStreamCreateWithPriority(&r->sv, cudaStreamNonBlocking, p_skel) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&r->sr_, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&r->sr_, cudaStreamNonBlocking, p_rep) != cudaSuccess ||
       cudaStreamCreateWithPriority(&r->sm, cudaStreamNonBlocking, p_mix) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
   r->progress = ProgressWords::get().take();
   if (!r->progress) { delete r; return PB200_ERR_CUDA; }
@@ -669,6 +679,8 @@ void pb200_destroy(pb200_renderer* r) {
   if (r->sr_) cudaStreamDestroy(r->sr_);
   if (r->sv) cudaStreamDestroy(r->sv);
   if (r->sm) cudaStreamDestroy(r->sm);
+  if (r->sc) { cudaStreamSynchronize(r->sc); cudaStreamDestroy(r->sc); }
+  if (r->push_flags) cudaFreeHost(r->push_flags);
   ProgressWords::get().give(r->progress);
   delete r;
 }
@@ -1269,7 +1281,7 @@ struct Compiled {
   std::vector<std::vector<uint32_t>> levels;  // mixers per depth
   std::vector<SizeClass> classes;
   uint32_t max_chunks = 1;
-  std::vector<uint32_t> level_offsets, class_offsets;
+  std::vector<uint32_t> level_offsets, class_offsets, level_fx_count;
 };
 
 // Jump tables for every steady ratio the graph can reach: the speeds of playing voices and of every pending note-on /
@@ -1416,7 +1428,13 @@ int upload_graph(pb200_renderer* r, Compiled& c) {
   for (size_t mi = 0; mi < r->mixers.size(); ++mi) if (!r->mixers[mi].removed) c.levels[r->mixers[mi].depth].push_back((uint32_t)mi);
   std::vector<uint32_t> level_mixers;
   c.level_offsets.clear();
-  for (auto& l : c.levels) { c.level_offsets.push_back((uint32_t)level_mixers.size()); for (uint32_t m : l) level_mixers.push_back(m); }
+  c.level_fx_count.clear();
+  for (auto& l : c.levels) {  // mixers with effects first: the two groups go to different builds of the mixer kernel
+    std::stable_partition(l.begin(), l.end(), [&](uint32_t m) { return !r->mixers[m].effects.empty(); });
+    c.level_fx_count.push_back((uint32_t)std::count_if(l.begin(), l.end(), [&](uint32_t m) { return !r->mixers[m].effects.empty(); }));
+    c.level_offsets.push_back((uint32_t)level_mixers.size());
+    for (uint32_t m : l) level_mixers.push_back(m);
+  }
   // size classes: groups bucketed by voices-per-group rounded up to a power of two
   c.classes.clear();
   for (uint32_t vpad = 1; vpad <= 1024; vpad <<= 1) {
@@ -1549,7 +1567,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   // WavStream finishes when the main mixer has nothing at all to do (wav.rs:231-234, mixed.rs:664-670)
   size_t live_mixers = 0, live_fx = 0;
   for (auto& m : r->mixers) if (!m.removed) { ++live_mixers; live_fx += m.effects.size(); }
-  if (r->groups.empty() && live_fx == 0 && live_mixers == 1 && !r->ext_input) r->finished = true;
+  if (r->groups.empty() && live_fx == 0 && live_mixers == 1 && !r->n_ext) r->finished = true;
   if (r->finished) {
     if (out_host) std::memset(out_host, 0, frames * 2 * sizeof(float));
     if (out_dev) CUDA_TRY(cudaMemsetAsync(out_dev, 0, frames * 2 * sizeof(float), r->sm));
@@ -1557,10 +1575,17 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     if (frames_written) *frames_written = 0;
     return PB200_OK;
   }
+  // PB200_HOST_PROF: wall time of the host-side phases of a render call (debug aid)
+  static const bool host_prof = getenv("PB200_HOST_PROF") != nullptr;
+  auto hp_now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double hp_t = host_prof ? hp_now() : 0.0;
+  auto hp_mark = [&](const char* what) { if (host_prof) { const double t = hp_now(); fprintf(stderr, "[host] %-28s %8.3f ms\n", what, t - hp_t); hp_t = t; } };
   Compiled c;
   if (int e = sync_state_to_host(r)) return e;
+  hp_mark("sync_state_to_host");
   // (events and cursors live on the host between render calls: always rebuild the flattened lists)
   if (int e = upload_graph(r, c)) return e;
+  hp_mark("upload_graph");
 
   const uint64_t p0 = r->position, p1 = p0 + frames;
   // Large graphs (every launch already fills the GPU) take longer time blocks: fewer launches and per-block joins
@@ -1728,7 +1753,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       if (max_fx < 2) continue;
       int per_sm = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mix_fx_kernel<1>, FX_THREADS, reverb ? FX_WORK_BYTES : FX_WORK_SMALL);
-      const size_t want = std::min<size_t>(max_fx, MAX_FX_STAGES), nlm = std::max<size_t>(1, c.levels[lvl].size());
+      const size_t want = std::min<size_t>(max_fx, MAX_FX_STAGES), nlm = std::max<size_t>(1, c.level_fx_count[lvl]);
       uint32_t S = (uint32_t)std::min<size_t>(want, (size_t)std::max(per_sm, 0) * dev_sms / nlm);
       if (S < want && !reverb && !no_small) {   // the 128-register build fits twice as many CTAs
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mix_fx_kernel<2>, FX_THREADS, FX_WORK_SMALL);
@@ -1775,6 +1800,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       CUDA_TRY(cudaStreamSynchronize(r->sm));
     }
   }
+  hp_mark("schedule + work areas");
   std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r0(n_blocks), ev_r1(n_blocks), ev_m0(n_blocks), ev_m1(n_blocks);
   std::vector<cudaEvent_t> ev_x((n_hq || n_rows) ? 3 * (size_t)n_blocks : 0);  // grain begin / grain end = sinc begin / sinc end
   for (auto& e : ev_x) CUDA_TRY(DevicePool::get().event(&e));
@@ -1994,8 +2020,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ma.prof = fx_prof;
     ma.progress = out_dev ? r->progress : nullptr;
     ma.progress_value = progress_base + (b0 - p0) + blen;
-    ma.ext_in = (r->ext_input && b0 - p0 < r->ext_frames) ? r->ext_input + (b0 - p0) * 2 : nullptr;
-    ma.ext_len = ma.ext_in ? (uint32_t)std::min<uint64_t>(blen, r->ext_frames - (b0 - p0)) : 0u;
+    ma.n_ext = (b0 - p0 < r->ext_frames) ? r->n_ext : 0u;
+    for (uint32_t e = 0; e < PB_MAX_EXT; ++e) ma.ext_in[e] = e < ma.n_ext ? r->ext_input[e] + (b0 - p0) * 2 : nullptr;
+    ma.ext_len = ma.n_ext ? (uint32_t)std::min<uint64_t>(blen, r->ext_frames - (b0 - p0)) : 0u;
     ma.prof_all = fx_prof_all ? 1u : 0u;
     for (int lvl = (int)c.levels.size() - 1; lvl >= 0 && !skel_only; --lvl) {
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
@@ -2010,25 +2037,34 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       ma.fx_progress = S > 1 ? r->d_fx_progress.p : nullptr;
       ma.fx_pflags = S > 1 ? r->d_fx_pflags.p : nullptr;
       ma.fx_ticket = S > 1 ? r->d_fx_progress.p + nm * (size_t)MAX_FX_STAGES : nullptr;
-      if (S > 1) {
+      const uint32_t n_fx = c.level_fx_count[lvl], n_plain = nlm - n_fx;
+      if (n_fx && S > 1) {
         // (an ordinary launch: the ticket order makes the hand-over deadlock-free; a cooperative launch would serialise the
         // kernel against everything else on the device, the replay of the next block included)
         CUDA_TRY(cudaMemsetAsync(r->d_fx_progress.p, 0, (nm * (size_t)MAX_FX_STAGES + 1) * sizeof(uint32_t), r->sm));
-        if (level_small[lvl]) mix_fx_kernel<2><<<dim3(nlm, S), FX_THREADS, ma.work_bytes, r->sm>>>(ma);
-        else mix_fx_kernel<1><<<dim3(nlm, S), FX_THREADS, ma.work_bytes, r->sm>>>(ma);
-      } else {
-        mix_fx_kernel<1><<<nlm, FX_THREADS, ma.work_bytes, r->sm>>>(ma);
+        if (level_small[lvl]) mix_fx_kernel<2><<<dim3(n_fx, S), FX_THREADS, ma.work_bytes, r->sm>>>(ma);
+        else mix_fx_kernel<1><<<dim3(n_fx, S), FX_THREADS, ma.work_bytes, r->sm>>>(ma);
+      } else if (n_fx) {
+        mix_fx_kernel<1><<<n_fx, FX_THREADS, ma.work_bytes, r->sm>>>(ma);
       }
-      launches += 2;
+      if (n_plain) {  // the mixers without effects: the light build
+        ma.level_mixers += n_fx;
+        ma.n_stages = 1; ma.stage_begin = nullptr; ma.fx_progress = nullptr; ma.fx_pflags = nullptr; ma.fx_ticket = nullptr;
+        ma.work_bytes = 0;
+        mix_fx_kernel<4, true><<<n_plain, FX_THREADS, 0, r->sm>>>(ma);
+      }
+      launches += 1 + (n_fx ? 1 : 0) + (n_plain ? 1 : 0);
     }
     CUDA_TRY(cudaEventRecord(ev_m1[b], r->sm));
   }
   CUDA_TRY(cudaEventRecord(ev_end, r->sm));
+  hp_mark("launches enqueued");
   if (out_host) CUDA_TRY(cudaMemcpyAsync(out_host, dout, frames * 2 * sizeof(float), cudaMemcpyDeviceToHost, r->sm));
   CUDA_TRY(cudaStreamSynchronize(r->sm));
   CUDA_TRY(cudaStreamSynchronize(r->sr_));
   CUDA_TRY(cudaStreamSynchronize(r->sv));
   CUDA_TRY(cudaGetLastError());
+  hp_mark("device done");
 
   if (fx_prof) {
     std::vector<unsigned long long> hp(fx_prof_n);
@@ -2151,7 +2187,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     // playing source, effect, sub-mixer or pending event left (mixed.rs:664-670). Sources are dropped at the end of
     // the block they finished in; an event is popped by the chunk that starts at its time.
     uint64_t written = frames;
-    if (live_fx == 0 && live_mixers == 1 && !r->ext_input) {
+    if (live_fx == 0 && live_mixers == 1 && !r->n_ext) {
       bool all_dead = true;
       uint64_t fin = p0;
       for (size_t gi = 0; gi < gs.size(); ++gi) {
@@ -2195,7 +2231,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     if (r->finished) r->position = p0 + written;  // WavStream::playback_pos stops with the stream
     if (frames_written) *frames_written = written;
   }
-  r->ext_input = nullptr; r->ext_frames = 0;   // (an external main-mixer input serves one render call)
+  hp_mark("state download + bookkeeping");
+  r->n_ext = 0; r->ext_frames = 0;   // (external main-mixer inputs serve one render call)
   return PB200_OK;
 }
 
@@ -2213,11 +2250,73 @@ int pb200_render_device(pb200_renderer* r, float* out_device, uint64_t frames, u
   return render_impl(r, out_device, nullptr, frames, frames_written);
 }
 
+int pb200_set_main_inputs(pb200_renderer* r, const float* const* buses_device, uint32_t count, uint64_t frames) {
+  if (!r || (count && !buses_device)) return PB200_ERR_PARAMETER;
+  if (count > PB_MAX_EXT) return fail(r, PB200_ERR_PARAMETER, "too many main-mixer inputs");
+  if (count && frames % r->cfg.block_frames != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
+  for (uint32_t i = 0; i < count; ++i) if (!buses_device[i]) return fail(r, PB200_ERR_PARAMETER, "null main-mixer input");
+  for (uint32_t i = 0; i < count; ++i) r->ext_input[i] = buses_device[i];
+  r->n_ext = count;
+  r->ext_frames = count ? frames : 0;
+  return PB200_OK;
+}
+
 int pb200_set_main_input(pb200_renderer* r, const float* bus_device, uint64_t frames) {
+  return pb200_set_main_inputs(r, &bus_device, bus_device ? 1u : 0u, frames);
+}
+
+// ---- peer memory (sharded renders): plain cudaMalloc allocations shared between the ranks' processes through CUDA IPC; pushes
+// are stream-ordered DMA copies plus a stream memory write as the "piece has landed" flag -- no kernel, so nothing waits for
+// SMs on a device that is busy rendering (an NCCL reduce kernel does: 5-10 ms per piece behind a shard's launches) ----------
+int pb200_device_alloc(int device_ordinal, size_t bytes, void** ptr) {
+  if (!ptr || !bytes) return PB200_ERR_PARAMETER;
+  if (device_ordinal >= 0 && cudaSetDevice(device_ordinal) != cudaSuccess) return PB200_ERR_CUDA;
+  if (cudaMalloc(ptr, bytes) != cudaSuccess) return PB200_ERR_CUDA;
+  if (cudaMemset(*ptr, 0, bytes) != cudaSuccess) return PB200_ERR_CUDA;
+  return PB200_OK;
+}
+int pb200_device_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? PB200_OK : PB200_ERR_CUDA; }
+int pb200_ipc_export(const void* ptr, void* handle64) {
+  if (!ptr || !handle64) return PB200_ERR_PARAMETER;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)) != cudaSuccess) return PB200_ERR_CUDA;
+  std::memcpy(handle64, &h, 64);
+  return PB200_OK;
+}
+int pb200_ipc_open(const void* handle64, int device_ordinal, void** ptr) {
+  if (!handle64 || !ptr) return PB200_ERR_PARAMETER;
+  if (device_ordinal >= 0 && cudaSetDevice(device_ordinal) != cudaSuccess) return PB200_ERR_CUDA;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  return cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? PB200_OK : PB200_ERR_CUDA;
+}
+int pb200_ipc_close(void* ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? PB200_OK : PB200_ERR_CUDA; }
+
+int pb200_push_async(pb200_renderer* r, void* dst_peer, const void* src_device, size_t bytes, uint32_t* flag_peer, uint32_t flag_value) {
+  if (!r || !dst_peer || !src_device) return PB200_ERR_PARAMETER;
+  cudaSetDevice(r->device);
+  if (!r->sc) CUDA_TRY(cudaStreamCreateWithFlags(&r->sc, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMemcpyAsync(dst_peer, src_device, bytes, cudaMemcpyDefault, r->sc));
+  if (flag_peer) {  // the flag follows the data on the same stream: a 4-byte copy out of a pinned ring (64 pushes may be in flight)
+    if (!r->push_flags) CUDA_TRY(cudaHostAlloc((void**)&r->push_flags, 64 * sizeof(uint32_t), cudaHostAllocPortable));
+    uint32_t* slot = r->push_flags + (r->push_seq++ & 63u);
+    *slot = flag_value;
+    CUDA_TRY(cudaMemcpyAsync(flag_peer, slot, sizeof(uint32_t), cudaMemcpyDefault, r->sc));
+  }
+  return PB200_OK;
+}
+int pb200_push_sync(pb200_renderer* r) {
   if (!r) return PB200_ERR_PARAMETER;
-  if (bus_device && frames % r->cfg.block_frames != 0) return fail(r, PB200_ERR_PARAMETER, "frames must be a multiple of block_frames");
-  r->ext_input = bus_device;
-  r->ext_frames = bus_device ? frames : 0;
+  if (r->sc) CUDA_TRY(cudaStreamSynchronize(r->sc));
+  return PB200_OK;
+}
+int pb200_peek_u32(pb200_renderer* r, const uint32_t* src_device, uint32_t count, uint32_t* out_host) {
+  if (!r || !src_device || !out_host) return PB200_ERR_PARAMETER;
+  cudaSetDevice(r->device);
+  if (!r->sc) CUDA_TRY(cudaStreamCreateWithFlags(&r->sc, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMemcpyAsync(out_host, src_device, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, r->sc));
+  CUDA_TRY(cudaStreamSynchronize(r->sc));
   return PB200_OK;
 }
 

@@ -590,6 +590,23 @@ class Player:
         oracle) to the main mixer's input -- the reduced output of the sub-mixers rendered on other ranks. None detaches."""
         self._check(self.api.set_main_input(self._r, C.c_void_p(device_ptr) if device_ptr else None, frames))
 
+    def set_main_inputs(self, device_ptrs, frames: int) -> None:
+        """Up to 8 external buses, added to the main mixer's input in the order given (one per rank of a sharded render)."""
+        arr = (C.c_void_p * len(device_ptrs))(*[C.c_void_p(p) for p in device_ptrs])
+        self._check(self.api.set_main_inputs(self._r, arr, len(device_ptrs), frames))
+
+    def push_async(self, dst_peer: int, src_device: int, nbytes: int, flag_peer: int | None, flag_value: int) -> None:
+        self._check(self.api.push_async(self._r, C.c_void_p(dst_peer), C.c_void_p(src_device), nbytes,
+                                        C.c_void_p(flag_peer) if flag_peer else None, flag_value))
+
+    def push_sync(self) -> None:
+        self._check(self.api.push_sync(self._r))
+
+    def peek_u32(self, src_device: int, count: int):
+        out = (A.U32 * count)()
+        self._check(self.api.peek_u32(self._r, C.c_void_p(src_device), count, out))
+        return list(out)
+
     def output_sample_frame_position(self) -> int:
         return int(self.api.position(self._r))
 

@@ -284,6 +284,15 @@ extern "C" {
     pub fn pb200_stop_all_sources(r: *mut pb200_renderer) -> c_int;
     pub fn pb200_render(r: *mut pb200_renderer, out_interleaved: *mut f32, frames: u64, frames_written: *mut u64) -> c_int;
     pub fn pb200_render_progress(r: *const pb200_renderer) -> u64;
+    pub fn pb200_set_main_inputs(r: *mut pb200_renderer, buses_device: *const *const f32, count: u32, frames: u64) -> c_int;
+    pub fn pb200_device_alloc(device_ordinal: c_int, bytes: usize, ptr: *mut *mut c_void) -> c_int;
+    pub fn pb200_device_free(ptr: *mut c_void) -> c_int;
+    pub fn pb200_ipc_export(ptr: *const c_void, handle64: *mut c_void) -> c_int;
+    pub fn pb200_ipc_open(handle64: *const c_void, device_ordinal: c_int, ptr: *mut *mut c_void) -> c_int;
+    pub fn pb200_ipc_close(ptr: *mut c_void) -> c_int;
+    pub fn pb200_push_async(r: *mut pb200_renderer, dst_peer: *mut c_void, src_device: *const c_void, bytes: usize, flag_peer: *mut u32, flag_value: u32) -> c_int;
+    pub fn pb200_push_sync(r: *mut pb200_renderer) -> c_int;
+    pub fn pb200_peek_u32(r: *mut pb200_renderer, src_device: *const u32, count: u32, out_host: *mut u32) -> c_int;
     pub fn pb200_set_main_input(r: *mut pb200_renderer, bus_device: *const f32, frames: u64) -> c_int;
     pub fn pb200_render_device(r: *mut pb200_renderer, out_device: *mut f32, frames: u64, frames_written: *mut u64) -> c_int;
     pub fn pb200_position(r: *const pb200_renderer) -> u64;

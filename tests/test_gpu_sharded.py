@@ -102,6 +102,21 @@ def nccl_worker(rank, world, port, result_path):
     render_sharded(p, bus, 6 * 1024, stage, out)
     if rank == 0:
         np.save(result_path, out.cpu().numpy())
+    p.close()
+    # the same render with the pieces pushed into rank 0's IPC staging buses instead of reduced (twice: the flags' generation)
+    from phonic_b200.distributed import PeerBus
+    peer = PeerBus(api, FRAMES, 4, rank)
+    for it in range(2):
+        p = Player(api, 48000, device_ordinal=rank)
+        build(p, mine)
+        stage = MainBusStage(api, 48000, chain, device_ordinal=rank) if rank == 0 else None
+        out.zero_()
+        render_sharded(p, bus, 6 * 1024, stage, out, peer=peer)
+        if rank == 0:
+            np.save(result_path.replace(".npy", f"_peer{it}.npy"), out.cpu().numpy())
+            stage.close()
+        p.close()
+    peer.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -116,3 +131,6 @@ def test_two_nccl_ranks_match_oracle(tmp_path, oracle_api):
     got = np.load(result)
     assert float(np.abs(full).max()) > 0.05
     assert float(np.abs(got - full).max()) <= 1e-5
+    for it in range(2):
+        got = np.load(result.replace(".npy", f"_peer{it}.npy"))
+        assert float(np.abs(got - full).max()) <= 1e-5
