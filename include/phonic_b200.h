@@ -344,6 +344,10 @@ PB200_API int pb200_set_main_inputs(pb200_renderer *r, const float *const *buses
  * sub-blocks); pb200_ipc_export / _open / _close: cudaIpcMemHandle_t as 64 opaque bytes; pb200_push_async: copy
  * `bytes` from this renderer's device to `dst_peer`, then store `flag_value` to `flag_peer` (may be NULL), in order, on the
  * renderer's copy stream; pb200_push_sync waits for all pushes; pb200_peek_u32 reads `count` words of device memory. */
+/* The library keeps device memory of destroyed renderers in a process-wide pool (cudaMalloc / cudaFree synchronise the
+ * device). pb200_trim_pool returns the idle blocks of one device (-1: all) to the driver and reports the bytes freed; the
+ * pool also trims itself when an allocation fails. No reference counterpart. */
+PB200_API uint64_t pb200_trim_pool(int device_ordinal);
 PB200_API int pb200_device_alloc(int device_ordinal, size_t bytes, void **ptr);
 PB200_API int pb200_device_free(void *ptr);
 PB200_API int pb200_ipc_export(const void *ptr, void *handle64);

@@ -45,6 +45,7 @@
 #define pb200_push_async po_push_async
 #define pb200_push_sync po_push_sync
 #define pb200_peek_u32 po_peek_u32
+#define pb200_trim_pool po_trim_pool
 #include "../include/phonic_b200.h"
 
 #include <atomic>
@@ -756,6 +757,7 @@ int pb200_set_main_inputs(pb200_renderer* r, const float* const* buses, uint32_t
   return PB200_OK;
 }
 int pb200_set_main_input(pb200_renderer* r, const float* bus, uint64_t frames) { return pb200_set_main_inputs(r, &bus, bus ? 1u : 0u, frames); }
+uint64_t pb200_trim_pool(int) { return 0; }
 // peer memory: device-only
 int pb200_device_alloc(int, size_t, void**) { return PB200_ERR_UNSUPPORTED; }
 int pb200_device_free(void*) { return PB200_ERR_UNSUPPORTED; }

@@ -195,6 +195,7 @@ SYMBOLS = {
     "set_main_input": (C.c_int, [_R, C.c_void_p, U64]),
     "render_progress": (U64, [_R]),
     "set_main_inputs": (C.c_int, [_R, _P(C.c_void_p), U32, U64]),
+    "trim_pool": (U64, [C.c_int]),
     "device_alloc": (C.c_int, [C.c_int, C.c_size_t, _P(C.c_void_p)]),
     "device_free": (C.c_int, [C.c_void_p]),
     "ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -56,8 +56,31 @@ struct DevicePool {
       if (!v.empty()) { *out = v.back(); v.pop_back(); *granted = c; return cudaSuccess; }
     }
     cudaError_t e = cudaMalloc(out, c);
+    if (e == cudaErrorMemoryAllocation) {  // the pool itself may hold the memory: give this device's idle blocks back and retry
+      cudaGetLastError();
+      trim(dev);
+      e = cudaMalloc(out, c);
+    }
     *granted = c;
     return e;
+  }
+  // cudaFree every pooled (idle) block of `dev` (-1: all devices); returns the bytes released (pb200_trim_pool)
+  size_t trim(int dev) {
+    std::vector<std::pair<int, void*>> victims;
+    size_t bytes = 0;
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (auto& kv : free_blocks) {
+        if (dev >= 0 && kv.first.first != dev) continue;
+        for (void* p : kv.second) { victims.push_back({kv.first.first, p}); bytes += kv.first.second; }
+        kv.second.clear();
+      }
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& v : victims) { cudaSetDevice(v.first); cudaFree(v.second); }
+    cudaSetDevice(cur);
+    return bytes;
   }
   void release(void* p, size_t cls) {
     if (!p) return;
@@ -546,8 +569,10 @@ int make_granular_buffer(pb200_renderer* r, uint32_t buffer_id, uint32_t* out_in
   const DevBuffer src = r->buffers[buffer_id].dev;
   const uint32_t sr = r->cfg.sample_rate;
   if (src.channels == 1 && src.sample_rate == sr) { *out_index = buffer_id; return PB200_OK; }  // "just copy": shared read-only
+  if (cudaSetDevice(r->device) != cudaSuccess) return fail(r, PB200_ERR_CUDA, "granular sample buffer: cudaSetDevice failed");
   pb200_config cfg = r->cfg;
   cfg.master_volume = 1.0f;
+  cfg.device_ordinal = r->device;   // (the borrowed sample pointer and the pool blocks below belong to THIS renderer's device)
   pb200_renderer* t = nullptr;
   if (int e = pb200_create(&cfg, &t)) return fail(r, e, "granular sample buffer: could not create the resampling renderer");
   HostBuffer borrowed;
@@ -579,10 +604,15 @@ int make_granular_buffer(pb200_renderer* r, uint32_t buffer_id, uint32_t* out_in
     DevicePool::get().release(tmp, tmp_cls);
     return fail(r, PB200_ERR_CUDA, "granular sample buffer: out of device memory");
   }
-  if (produced == 0) cudaMemsetAsync(mono, 0, sizeof(float), r->sm);  // "ensure sample buffer is not empty"
-  else downmix_kernel<<<(uint32_t)((produced + 255) / 256), 256, 0, r->sm>>>(tmp, mono, (uint32_t)produced, src.channels);
-  cudaStreamSynchronize(r->sm);
+  cudaError_t ce;
+  if (produced == 0) ce = cudaMemsetAsync(mono, 0, sizeof(float), r->sm);  // "ensure sample buffer is not empty"
+  else { downmix_kernel<<<(uint32_t)((produced + 255) / 256), 256, 0, r->sm>>>(tmp, mono, (uint32_t)produced, src.channels); ce = cudaGetLastError(); }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(r->sm);
   DevicePool::get().release(tmp, tmp_cls);
+  if (ce != cudaSuccess) {
+    DevicePool::get().release(mono, hb.cls);
+    return fail(r, PB200_ERR_CUDA, std::string("granular sample buffer: ") + cudaGetErrorString(ce));
+  }
   hb.dev.data = mono; hb.dev.n_samples = (uint32_t)n; hb.dev.channels = 1; hb.dev.sample_rate = sr;
   hb.dev.loop_start = -1; hb.dev.loop_end = -1;
   r->buffers.push_back(hb);
@@ -930,6 +960,7 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
   if (int e = validate_vol_pan(r, o->volume, o->panning)) return e;
   if (o->voices == 0) return fail(r, PB200_ERR_PARAMETER, "playback options voice count is '0'");
   if (o->voices > (uint32_t)VK_MAX_VOICES) return fail(r, PB200_ERR_UNSUPPORTED, "more than 1024 voices per sampler");
+  cudaSetDevice(r->device);
   auto mit = r->mixer_by_id.find(o->target_mixer);
   if (mit == r->mixer_by_id.end()) return fail(r, PB200_ERR_MIXER_NOT_FOUND, "Mixer not found");
   if (int e = sync_state_to_host(r)) return e;
@@ -1830,11 +1861,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   for (auto& g : r->groups) if (g.gp.kind == GROUP_FILE && !g.removed) ++n_file_groups;
   const uint32_t pos_rate = r->cfg.sample_rate;  // FilePlaybackOptions::default().playback_pos_emit_rate = 1 s (file.rs:110)
   const uint32_t status_cap = n_file_groups ? n_file_groups * (uint32_t)(frames / pos_rate + 4) : 0u;
-  if (status_cap) {
-    CUDA_TRY(r->d_status.reserve(status_cap));
-    CUDA_TRY(r->d_status_count.reserve(1));
-    CUDA_TRY(cudaMemsetAsync(r->d_status_count.p, 0, sizeof(uint32_t), r->sv));
-  }
+  if (status_cap) CUDA_TRY(r->d_status.reserve(status_cap));
+  CUDA_TRY(r->d_status_count.reserve(2));   // [0] status records appended, [1] snapshot-list overflow flag
+  CUDA_TRY(cudaMemsetAsync(r->d_status_count.p, 0, 2 * sizeof(uint32_t), r->sv));
   const bool metering = r->meter_interval != UINT64_MAX;
   const size_t meter_rows = (size_t)(frames / bf);
   if (metering) {
@@ -1891,7 +1920,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       CUDA_TRY(cudaMemsetAsync(va.gran.tile_range, 0xFF, (size_t)n_rows * n_tiles * 2 * sizeof(uint32_t), r->sv));
     }
     va.phase_tabs = r->d_phase_tabs.p; va.phase_dir = r->d_phase_dir.p; va.n_phase = (uint32_t)r->phase_off.size();
-    va.status = status_cap ? r->d_status.p : nullptr; va.status_count = r->d_status_count.p; va.status_cap = status_cap; va.pos_emit_rate = pos_rate;
+    va.status = status_cap ? r->d_status.p : nullptr; va.status_count = r->d_status_count.p; va.overflow = r->d_status_count.p + 1; va.status_cap = status_cap; va.pos_emit_rate = pos_rate;
     va.prof = prof_buf;
     va.debug_flags = getenv("PB200_SKEL_DEBUG") ? (uint32_t)atoi(getenv("PB200_SKEL_DEBUG")) : 0u;
     SkeletonLoop sl;
@@ -2146,9 +2175,11 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
         return fail(r, PB200_ERR_CUDA, "granular record list / grain storage overflowed");
     for (uint32_t b = 0; b < n_blocks; ++b) r->stats.grain_samples += counts[2 * b + 1];
   }
+  uint32_t counts2[2] = {0, 0};
+  CUDA_TRY(cudaMemcpy(counts2, r->d_status_count.p, sizeof(counts2), cudaMemcpyDeviceToHost));
+  if (counts2[1]) return fail(r, PB200_ERR_CUDA, "a voice's snapshot list filled up (more write calls per time block than seg_cap allows): output invalid");
   if (status_cap) {  // PlaybackStatusEvent stream, in emission order (frame, then the mixer's source order ~ id)
-    uint32_t n = 0;
-    CUDA_TRY(cudaMemcpy(&n, r->d_status_count.p, sizeof(n), cudaMemcpyDeviceToHost));
+    uint32_t n = counts2[0];
     if (n > status_cap) return fail(r, PB200_ERR_CUDA, "status event list overflowed");
     std::vector<StatusRec> recs(n);
     if (n) CUDA_TRY(cudaMemcpy(recs.data(), r->d_status.p, n * sizeof(StatusRec), cudaMemcpyDeviceToHost));
@@ -2319,6 +2350,8 @@ int pb200_peek_u32(pb200_renderer* r, const uint32_t* src_device, uint32_t count
   CUDA_TRY(cudaStreamSynchronize(r->sc));
   return PB200_OK;
 }
+
+uint64_t pb200_trim_pool(int device_ordinal) { return (uint64_t)DevicePool::get().trim(device_ordinal); }
 
 uint64_t pb200_render_progress(const pb200_renderer* r) { return r && r->progress ? __atomic_load_n(r->progress, __ATOMIC_ACQUIRE) : 0; }
 

@@ -54,6 +54,7 @@ struct SkeletonArgs {
   // PlaybackStatusEvent stream of file playbacks (nullptr: nobody listens)
   StatusRec* status;
   uint32_t* status_count;
+  uint32_t* overflow;        // set when a voice's / group's snapshot list filled up (records may have been dropped)
   uint32_t status_cap;
   uint32_t pos_emit_rate;            // frames between Position events (1 s)
   // exact 64-frame phase jumps (phase_table.cuh): one table per steady ratio of the graph, directory sorted by ratio bits
@@ -850,6 +851,7 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
         }
         sc_finish();
         if (cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
+        if (n_segs >= a.seg_cap) atomicOr(a.overflow, 1u);
         if (my_frames) atomicAdd((unsigned long long*)&s_gs.voice_frames, (unsigned long long)my_frames);
         __threadfence();
         const uint32_t arrived = atomicAdd(L.auton_done + (size_t)cta * L.n_blocks + bb, 1u) + 1u;
@@ -1196,6 +1198,7 @@ PB_DEV void skeleton_block(SkeletonArgs a, const TabSlot& tslot, const SkeletonL
 
   if (mine && cur_tile != 0xFFFFFFFFu) { my_first[cur_tile] = (uint16_t)cur_first; my_count[cur_tile] = (uint16_t)cur_cnt; }
   if (tid == 0 && gcur_tile != 0xFFFFFFFFu) { g_first[gcur_tile] = (uint16_t)gcur_first; g_count[gcur_tile] = (uint16_t)gcur_cnt; }
+  if ((mine && n_segs >= a.seg_cap) || (tid == 0 && n_gsegs >= a.seg_cap)) atomicOr(a.overflow, 1u);   // a full list may have dropped records
   if (mine) a.voices[gp.first_voice + tid] = v;
 #ifdef PB200_CYC
   if (CYC_ON(gp.first_voice + tid) && mine) g_cyc[7] += CYC_T() - cyc_block0;

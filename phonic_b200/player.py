@@ -392,7 +392,10 @@ class Player:
             self._batch, self._batch_notes = [], []
             try:
                 yield self
-            finally:
+            except BaseException:
+                self._batch, self._batch_notes = None, []   # the body failed: nothing of the partial batch is queued
+                raise
+            else:
                 evs, notes = self._batch, self._batch_notes
                 self._batch, self._batch_notes = None, []
                 if evs:

@@ -285,6 +285,7 @@ extern "C" {
     pub fn pb200_render(r: *mut pb200_renderer, out_interleaved: *mut f32, frames: u64, frames_written: *mut u64) -> c_int;
     pub fn pb200_render_progress(r: *const pb200_renderer) -> u64;
     pub fn pb200_set_main_inputs(r: *mut pb200_renderer, buses_device: *const *const f32, count: u32, frames: u64) -> c_int;
+    pub fn pb200_trim_pool(device_ordinal: c_int) -> u64;
     pub fn pb200_device_alloc(device_ordinal: c_int, bytes: usize, ptr: *mut *mut c_void) -> c_int;
     pub fn pb200_device_free(ptr: *mut c_void) -> c_int;
     pub fn pb200_ipc_export(ptr: *const c_void, handle64: *mut c_void) -> c_int;

@@ -56,7 +56,8 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.csv"), "w") as
     f.write("report,kernel,metric,value,unit\n")
     for spec in reps:
         rep, label = spec.split(":")
-        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # a report, or the raw page already exported on the GPU box (tools/final_gpu_pass.sh)
+        out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rr = list(csv.reader(out.splitlines()))
         h, r = rr[0], rr[2]
         kn = r[h.index("Kernel Name")]
