@@ -620,13 +620,17 @@ def main():
                         "fp32_peak_nominal_tflops": 74.45, "fp32_peak_used_tflops": fma_peak,
                         "hbm_achieved_gbs": (total_vframes / world) * 8.0 / (spans[dominant] / 1e3) / 1e9,
                         "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_kind": peak_kind, **passes}
-        # measured DRAM traffic of the dominant kernel (one ncu --set full capture, committed under profiles/)
+        # measured DRAM traffic of the kernel the roofline names (one ncu --set full capture, committed under profiles/)
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload) or {}
-            if tr.get("kernel") == roofline["kernel"] and tr.get("bytes_per_launch"):
-                roofline["traffic"] = tr["bytes_per_launch"]
-                roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one time block)"
-                roofline["traffic_source"] = tr["source"]
+            tr = (json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload) or {}).get("kernels", {})
+            ent = tr.get(roofline["kernel"].split(" ")[0])
+            if ent and ent.get("bytes_per_launch"):
+                roofline["traffic"] = ent["bytes_per_launch"]
+                roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)" + (
+                    f", one time block of {ent['block_frames']} frames" if ent.get("block_frames") else "")
+                roofline["traffic_source"] = ent["source"]
+                if ent.get("note"):
+                    roofline["traffic_note"] = ent["note"]
         except (OSError, ValueError):
             pass
         line = {"metric": METRIC, "value": value, "unit": "voice-samples/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
