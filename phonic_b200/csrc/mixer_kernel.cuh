@@ -159,6 +159,46 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   cbuf.scratch = &s_scratch[0][0];
   cbuf.lane_state = &s_lane_state[0][0];
 
+  // chunk <-> shared memory: interleaved global (L2: another SM may have written it) <-> planar padded shared; two frames per
+  // 16-byte access when the chunk starts on a 16-byte boundary, all of a thread's loads issued before its first store
+  auto stage_in = [&](const float* __restrict__ g, const uint32_t len) {
+    if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+      const float4* g4 = reinterpret_cast<const float4*>(g);
+      const uint32_t n4 = len >> 1;
+      for (uint32_t i0 = tid; i0 < n4; i0 += 4 * nt) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const uint32_t i = i0 + j * nt; if (i < n4) v[j] = __ldcg(g4 + i); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = i0 + j * nt;
+          if (i < n4) { const uint32_t f = 2 * i; s_ch[0][pidx(f)] = v[j].x; s_ch[1][pidx(f)] = v[j].y; s_ch[0][pidx(f + 1)] = v[j].z; s_ch[1][pidx(f + 1)] = v[j].w; }
+        }
+      }
+      if ((len & 1u) && tid < 2) s_ch[tid][pidx(len - 1)] = __ldcg(g + 2 * (len - 1) + tid);
+    } else {
+      for (uint32_t i = tid; i < len * 2; i += nt) s_ch[i & 1][pidx(i >> 1)] = __ldcg(g + i);
+    }
+  };
+  // returns this thread's max|x| of what it wrote when MX
+  auto stage_out = [&](float* __restrict__ g, const uint32_t len, const float gain, const bool scale) -> float {
+    float mx = 0.0f;
+    if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+      float4* g4 = reinterpret_cast<float4*>(g);
+      const uint32_t n4 = len >> 1;
+      for (uint32_t i = tid; i < n4; i += nt) {
+        const uint32_t f = 2 * i;
+        float4 v = make_float4(s_ch[0][pidx(f)], s_ch[1][pidx(f)], s_ch[0][pidx(f + 1)], s_ch[1][pidx(f + 1)]);
+        if (scale) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        g4[i] = v;
+      }
+      if ((len & 1u) && tid < 2) { float x = s_ch[tid][pidx(len - 1)]; if (scale) x *= gain; mx = fmaxf(mx, fabsf(x)); g[2 * (len - 1) + tid] = x; }
+    } else {
+      for (uint32_t i = tid; i < len * 2; i += nt) { float x = s_ch[i & 1][pidx(i >> 1)]; if (scale) x *= gain; mx = fmaxf(mx, fabsf(x)); g[i] = x; }
+    }
+    return mx;
+  };
   float gate_mx = 0.0f;          // this thread's share of max|x| over the written-back chunks of the open parent chunk
   uint32_t gate_covered = 0;     // frames of the open parent chunk those chunks cover (uniform)
   long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -181,7 +221,20 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
     for (uint32_t si = mp.src_begin; si < mp.src_end && !aud; ++si) aud = a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (kk - cb)] != 0;
     return aud;
   };
+  // this mixer's chunk boundaries of the block in shared memory (a dependent L2 load per use otherwise: ~700 cycles each,
+  // several per chunk)
+  __shared__ uint64_t s_bounds[AUD_MAX + 1];
+  const bool bounds_cached = ce - cb <= AUD_MAX + 1;
+  if (bounds_cached) {
+    for (uint32_t kk = cb + tid; kk < ce; kk += nt) s_bounds[kk - cb] = a.chunk_bounds[kk];
+    __syncthreads();
+  }
+  auto bound_at = [&](const uint32_t kk) -> uint64_t { return bounds_cached ? s_bounds[kk - cb] : a.chunk_bounds[kk]; };
+  uint64_t parent_next = is_main ? 0ull : a.chunk_bounds[pk + 1];   // end of the open parent chunk (kept in a register)
+  uint32_t eff_byp = a.mstate[m].effects_bypassed;                  // MixedSource::effects_bypassed: this CTA is its only writer
+  bool any_fx_events = false;   // (static: event lists do not change during a launch)
   if (has_fx) {
+    for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) any_fx_events |= a.fx[e].ev_end > a.fx[e].ev_begin;
     for (uint32_t kk = cb + tid; kk + 1 < ce && kk - cb < AUD_MAX; kk += nt) s_aud[kk - cb] = audible_of(kk) ? 1 : 0;
     __syncthreads();
   } else if (is_main && a.out && !a.meter) {
@@ -205,8 +258,8 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   }
   for (uint32_t k = cb; k + 1 < ce; ++k) {
     long long t0 = a.prof ? clock64() : 0;
-    const uint64_t c0 = a.chunk_bounds[k];
-    uint64_t c1 = a.chunk_bounds[k + 1];
+    const uint64_t c0 = bound_at(k);
+    uint64_t c1 = bound_at(k + 1);
     uint32_t len = (uint32_t)(c1 - c0);
     const uint32_t boff = (uint32_t)(c0 - a.block_start);
     float* gchunk = bus + (size_t)boff * 2;
@@ -221,7 +274,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
 
     if (has_fx) {
       // effect parameter events due at this chunk start (MixedSource::process_events, mixed.rs:683)
-      for (uint32_t e = e_lo; e < e_hi; ++e) {
+      for (uint32_t e = e_lo; e < e_hi && any_fx_events; ++e) {
         FxHeader& h = a.fx[e];
         // most chunks have no event due. The vote is also a barrier: every thread has read the cursor before thread 0 moves it
         if (!__syncthreads_or(h.ev_cursor < h.ev_end && a.fx_events[h.ev_cursor].time <= c0)) continue;
@@ -250,14 +303,14 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       // mixer come from its SOURCES' events (mixed.rs:686-693) and mean nothing to the effects.
       if (audible) {
         while (k + 2 < ce) {
-          const uint64_t nb = a.chunk_bounds[k + 1];   // start of the next chunk
+          const uint64_t nb = bound_at(k + 1);   // start of the next chunk
           if (nb % a.wav_block_frames == 0) break;
-          if (!is_main && nb == a.chunk_bounds[pk + 1]) break;
+          if (!is_main && nb == parent_next) break;
           if (!((k + 1 - cb < AUD_MAX) ? s_aud[k + 1 - cb] != 0 : audible_of(k + 1))) break;
           // an event of ANY effect of the mixer in (c0, nb] ends the merge. Judged on the event times alone (the
           // cursors belong to the effects' own stages), so that every stage of a pipeline cuts the same chunks.
           bool ev_due = false;
-          for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) {
+          for (uint32_t e = mp.fx_begin; e < mp.fx_end && any_fx_events; ++e) {
             const FxHeader& h = a.fx[e];
             uint32_t lo2 = h.ev_begin, hi2 = h.ev_end;   // first event with time > c0
             while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (a.fx_events[mid].time <= c0) lo2 = mid + 1; else hi2 = mid; }
@@ -265,7 +318,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
           }
           if (ev_due) break;
           ++k;
-          c1 = a.chunk_bounds[k + 1];
+          c1 = bound_at(k + 1);
         }
         len = (uint32_t)(c1 - c0);
       }
@@ -282,7 +335,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       }
       // (a pipeline stage cannot see the chain's verdict of the previous chunk; skipping is only a shortcut: with every
       // effect bypassed and the input silent each EffectProcessor stays bypassed by itself, mixed/effect.rs:88-91)
-      bool skip_all = n_stages == 1 && a.mstate[m].effects_bypassed && input_bypassed;  // mixed.rs:629
+      bool skip_all = n_stages == 1 && eff_byp && input_bypassed;  // mixed.rs:629
       if (n_stages > 1 && input_bypassed) {  // nothing to stage when every effect of this stage stays bypassed
         bool any = false;
         for (uint32_t e = e_lo; e < e_hi; ++e) any |= !(a.fx[e].tail_counter == 0 && a.fx[e].silence_counter == UINT64_MAX);
@@ -291,7 +344,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       tick(0, t0);
       if (!skip_all) {
         // stage the chunk: interleaved global -> planar padded shared (L2 loads: another SM may have written it)
-        for (uint32_t i = tid; i < len * 2; i += nt) s_ch[i & 1][pidx(i >> 1)] = __ldcg(gchunk + i);
+        stage_in(gchunk, len);
         __syncthreads();
         tick(1, t0);
         for (uint32_t e = e_lo; e < e_hi; ++e) {
@@ -347,19 +400,16 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
           __syncthreads();
         }
         tick(4, t0);
-        if (tid == 0 && last_stage) a.mstate[m].effects_bypassed = all_bypassed ? 1u : 0u;
+        if (last_stage) { eff_byp = all_bypassed ? 1u : 0u; if (tid == 0) a.mstate[m].effects_bypassed = eff_byp; }
         if (master_direct && last_stage) {
           // main mixer, master volume not ramping, no meter: the chunk goes from shared memory straight to the output
           // (nobody reads the main bus again), scaled as WavStream::process does per block (wav.rs:237)
-          for (uint32_t i = tid; i < len * 2; i += nt) {
-            const float x = s_ch[i & 1][pidx(i >> 1)];
-            a.out[(size_t)boff * 2 + i] = master_scale ? x * master_gain : x;
-          }
+          stage_out(a.out + (size_t)boff * 2, len, master_scale ? master_gain : 1.0f, master_scale);
           chunk_done = true;
         } else {
           // write the processed chunk back; a sub-mixer's silence gate wants max|x| of the parent chunk: collected here,
           // from shared memory, instead of re-reading the bus
-          for (uint32_t i = tid; i < len * 2; i += nt) { const float x = s_ch[i & 1][pidx(i >> 1)]; gchunk[i] = x; gate_mx = fmaxf(gate_mx, fabsf(x)); }
+          gate_mx = fmaxf(gate_mx, stage_out(gchunk, len, 1.0f, false));
           gate_covered += len;
         }
       } else if (n_stages > 1 && tid == 0) {
@@ -367,7 +417,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
         if (last_stage) a.mstate[m].effects_bypassed = all_bypassed ? 1u : 0u;
       }
       if (!last_stage) {  // hand chunk q to the next stage: samples first, then the flags, then the count
-        if (!is_main && c1 == a.chunk_bounds[pk + 1]) pk++;   // (the gate itself is the last stage's business)
+        if (!is_main && c1 == parent_next) { pk++; parent_next = a.chunk_bounds[pk + 1]; }   // (the gate itself is the last stage's business)
         __threadfence();
         __syncthreads();
         if (tid == 0) {
@@ -428,7 +478,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       }
     } else {
       // parent chunk ends here? -> SubMixerProcessor::process gate over the parent chunk span
-      if (c1 == a.chunk_bounds[pk + 1]) {
+      if (c1 == parent_next) {
         const uint64_t p0 = a.chunk_bounds[pk];
         const uint32_t o0 = (uint32_t)(p0 - a.block_start);
         const uint32_t pl = (uint32_t)(c1 - p0);
@@ -454,6 +504,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
         }
         __syncthreads();
         pk++;
+        parent_next = a.chunk_bounds[pk + 1];
       }
     }
     tick(6, t0);

@@ -2141,6 +2141,14 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   r->stats = pb200_render_stats{};
   cudaEventElapsedTime(&ms, ev_start, ev_end);
   r->stats.device_ms = ms;
+  if (host_prof) {  // device timeline of the call, ms since its first event
+    auto at = [&](cudaEvent_t e) { float t = 0; cudaEventElapsedTime(&t, ev_start, e); return t; };
+    fprintf(stderr, "[dev] end %.3f", at(ev_end));
+    if (persistent) fprintf(stderr, " | skeleton %.3f..%.3f", at(ev_v0[0]), at(ev_skel_end));
+    fprintf(stderr, "\n[dev] per block (replay start..end, mixer start..end):");
+    for (uint32_t b = 0; b < n_blocks; ++b) fprintf(stderr, " [%u] %.2f..%.2f %.2f..%.2f", b, at(ev_r0[b]), at(ev_r1[b]), at(ev_m0[b]), at(ev_m1[b]));
+    fprintf(stderr, "\n");
+  }
   for (uint32_t b = 0; b < n_blocks; ++b) {
     if (!persistent) { cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.skeleton_kernel_ms += ms; }
     else if (b == 0) { cudaEventElapsedTime(&ms, ev_v0[0], ev_skel_end); r->stats.skeleton_kernel_ms += ms; }
