@@ -232,6 +232,11 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   auto bound_at = [&](const uint32_t kk) -> uint64_t { return bounds_cached ? s_bounds[kk - cb] : a.chunk_bounds[kk]; };
   uint64_t parent_next = is_main ? 0ull : a.chunk_bounds[pk + 1];   // end of the open parent chunk (kept in a register)
   uint32_t eff_byp = a.mstate[m].effects_bypassed;                  // MixedSource::effects_bypassed: this CTA is its only writer
+  // WavStream's master-volume smoother: a shared copy (one L2 round trip per chunk otherwise); thread 0 is its only writer
+  __shared__ ExpSm s_master;
+  if (is_main && tid == 0) s_master = *a.master;
+  __syncthreads();
+  const uint32_t wbf = a.wav_block_frames;   // block_start is a multiple of it: boundaries are tested on 32-bit offsets
   bool any_fx_events = false;   // (static: event lists do not change during a launch)
   if (has_fx) {
     for (uint32_t e = mp.fx_begin; e < mp.fx_end; ++e) any_fx_events |= a.fx[e].ev_end > a.fx[e].ev_begin;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   } else if (is_main && a.out && !a.meter) {
     // a main mixer without effects (the top of a tree whose work sits in the sub-mixers): while the master volume is not
     // ramping the whole time block is one scaled copy, whatever the chunk boundaries are
-    const ExpSm ms0 = *a.master;
+    const ExpSm ms0 = s_master;
     if (!exp_need_ramp(ms0, a.fxc.comp)) {
       const float g = ms0.target;
       const bool scale = fabsf(1.0f - g) > 0.000001f;
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
     bool master_direct = false, master_scale = false, chunk_done = false;
     float master_gain = 1.0f;
     if (is_main && a.out && !a.meter) {
-      const ExpSm ms0 = *a.master;
+      const ExpSm ms0 = s_master;
       if (!exp_need_ramp(ms0, a.fxc.comp)) { master_direct = true; master_gain = ms0.target; master_scale = fabsf(1.0f - master_gain) > 0.000001f; }
     }
 
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       if (audible) {
         while (k + 2 < ce) {
           const uint64_t nb = bound_at(k + 1);   // start of the next chunk
-          if (nb % a.wav_block_frames == 0) break;
+          if ((uint32_t)(nb - a.block_start) % wbf == 0) break;
           if (!is_main && nb == parent_next) break;
           if (!((k + 1 - cb < AUD_MAX) ? s_aud[k + 1 - cb] != 0 : audible_of(k + 1))) break;
           // an event of ANY effect of the mixer in (c0, nb] ends the merge. Judged on the event times alone (the
@@ -437,8 +442,8 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       if (!chunk_done) for (uint32_t i = tid; i < len * 2; i += nt) a.out[(size_t)boff * 2 + i] = master_scale ? gchunk[i] * master_gain : gchunk[i];
     } else if (is_main) {
       // WavStream::process: apply_smoothed_gain once per 1024-frame block (wav.rs:228-237)
-      if ((c1 % a.wav_block_frames) == 0 || k + 2 == ce) {
-        const uint64_t wb0 = ((c1 - 1) / a.wav_block_frames) * a.wav_block_frames;
+      if (((uint32_t)(c1 - a.block_start) % wbf) == 0 || k + 2 == ce) {
+        const uint64_t wb0 = a.block_start + ((uint32_t)(c1 - 1 - a.block_start) / wbf) * wbf;
         const uint32_t o0 = (uint32_t)(wb0 - a.block_start);
         const uint32_t wl = (uint32_t)(c1 - wb0);
         float* wbuf = bus + (size_t)o0 * 2;
@@ -459,13 +464,14 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
           }
           __syncthreads();
         }
-        ExpSm ms = *a.master;
+        ExpSm ms = s_master;
         const bool ramp = exp_need_ramp(ms, a.fxc.comp);
         __syncthreads();
         if (ramp) {
           if (tid == 0) {
             for (uint32_t i = 0; i < wl * 2; ++i) wbuf[i] *= exp_next(ms, a.fxc.comp);
             *a.master = ms;
+            s_master = ms;
           }
           __syncthreads();
           if (a.out) for (uint32_t i = tid; i < wl * 2; i += nt) a.out[(size_t)o0 * 2 + i] = wbuf[i];

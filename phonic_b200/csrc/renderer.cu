@@ -308,7 +308,7 @@ struct pb200_renderer {
   DevVec<uint32_t> d_phase_tabs;
   DevVec<uint2> d_phase_dir, d_phase_new;
   size_t phase_words = 0;
-  cudaStream_t sr_ = nullptr;  // replay stream
+  cudaStream_t sr_ = nullptr, sr2 = nullptr;  // replay streams (sr2: every other block of a thin graph)
   DevVec<uint8_t> d_group_flags, d_mixer_flags;
   DevVec<ExpSm> d_master;
   ExpSm h_master;
@@ -664,6 +664,7 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
   const int p_mix = flat_prio ? prio_lo : prio_hi, p_skel = flat_prio || !skel_first ? prio_lo : p_mid, p_rep = flat_prio || skel_first ? prio_lo : p_mid;
   if (cudaStreamCreateWithPriority(&r->sv, cudaStreamNonBlocking, p_skel) != cudaSuccess ||
       cudaStreamCreateWithPriority(&r->sr_, cudaStreamNonBlocking, p_rep) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&r->sr2, cudaStreamNonBlocking, p_rep) != cudaSuccess ||
       cudaStreamCreateWithPriority(&r->sm, cudaStreamNonBlocking, p_mix) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
   r->progress = ProgressWords::get().take();
   if (!r->progress) { delete r; return PB200_ERR_CUDA; }
@@ -695,6 +696,7 @@ void pb200_destroy(pb200_renderer* r) {
   cudaSetDevice(r->device);
   if (r->sv) cudaStreamSynchronize(r->sv);
   if (r->sr_) cudaStreamSynchronize(r->sr_);
+  if (r->sr2) cudaStreamSynchronize(r->sr2);
   if (r->sm) cudaStreamSynchronize(r->sm);
   for (auto& b : r->buffers) if (b.cls) DevicePool::get().release((void*)b.dev.data, b.cls);  // cls 0: borrowed
   r->d_quiet_block.free(); r->d_auton.free(); r->d_stage_begin.free(); r->d_fx_progress.free(); r->d_fx_pflags.free(); r->d_status.free(); r->d_status_count.free(); r->d_meter.free(); r->d_block_done.free(); r->d_phase_tabs.free(); r->d_phase_dir.free(); r->d_phase_new.free(); r->d_hq_frames.free(); r->d_hq.free(); r->d_sinc_tables.free(); r->d_hq_scratch.free(); r->d_hq_recs.free(); r->d_hq_nrecs.free();
@@ -707,6 +709,7 @@ void pb200_destroy(pb200_renderer* r) {
   r->d_group_flags.free(); r->d_mixer_flags.free(); r->d_master.free();
   r->d_segs.free(); r->d_gsegs.free(); r->d_seg_first.free(); r->d_seg_count.free(); r->d_gseg_first.free(); r->d_gseg_count.free(); r->d_recs.free();
   if (r->sr_) cudaStreamDestroy(r->sr_);
+  if (r->sr2) cudaStreamDestroy(r->sr2);
   if (r->sv) cudaStreamDestroy(r->sv);
   if (r->sm) cudaStreamDestroy(r->sm);
   if (r->sc) { cudaStreamSynchronize(r->sc); cudaStreamDestroy(r->sc); }
@@ -1845,6 +1848,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaEventRecord(ev_start, r->sv));
   CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(r->sr2, ev_start, 0));
+  static const bool no_alt = getenv("PB200_NO_REPLAY_ALT") != nullptr;
+  const bool replay_alt = persistent && !no_alt && r->n_hq == 0 && r->n_gran_rows == 0;
   uint64_t launches = 0;
   uint32_t gen0 = 0;
   cudaEvent_t ev_skel_end;
@@ -1878,6 +1884,9 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     const uint64_t b0 = p0 + (uint64_t)b * tb;
     const uint32_t blen = (uint32_t)std::min<uint64_t>(tb, p1 - b0);
     const uint32_t slot = b % RING;
+    // thin graphs: the replay launches of consecutive blocks are independent (ring slots apart) and far from filling the GPU --
+    // alternate two streams so that a block's replay does not queue behind the previous one's (grain / sinc passes carry state: one stream)
+    cudaStream_t srb = (replay_alt && (b & 1u)) ? r->sr2 : r->sr_;
     const uint32_t sslot = persistent ? b : slot;  // slot of the tables the skeleton pass owns
     // pass 1 (skeleton) may not overwrite the segment slot the replay of block b-RING still reads
     // ... nor the group-flag slot the mixer of block b-RING still reads
@@ -1972,16 +1981,16 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     // pass 2 (replay): needs the segments of this block; may not overwrite a group-bus slot the mixer still reads
     if (!persistent) {
       CUDA_TRY(cudaEventRecord(ev_v1[b], r->sv));
-      CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_v1[b], 0));
+      CUDA_TRY(cudaStreamWaitEvent(srb, ev_v1[b], 0));
     } else {
       if (b == 0) CUDA_TRY(cudaEventRecord(ev_skel_end, r->sv));
-      if (stream_wait_value32()((CUstream)r->sr_, (CUdeviceptr)(r->d_block_done.p + b), (cuuint32_t)c.classes[0].groups.size(),
+      if (stream_wait_value32()((CUstream)srb, (CUdeviceptr)(r->d_block_done.p + b), (cuuint32_t)c.classes[0].groups.size(),
                                 CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
         return fail(r, PB200_ERR_CUDA, "cuStreamWaitValue32 failed");
-      if (b > 0) CUDA_TRY(cudaEventRecord(ev_v0[b], r->sr_));
-      CUDA_TRY(cudaEventRecord(ev_v1[b], r->sr_));
+      if (b > 0) CUDA_TRY(cudaEventRecord(ev_v0[b], srb));
+      CUDA_TRY(cudaEventRecord(ev_v1[b], srb));
     }
-    if (b >= RING) CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_m1[b - RING], 0));
+    if (b >= RING) CUDA_TRY(cudaStreamWaitEvent(srb, ev_m1[b - RING], 0));
     ReplayArgs ra;
     ra.groups = r->d_groups.p; ra.buffers = r->d_buffers.p;
     ra.segs = va.segs; ra.seg_first = va.seg_first; ra.seg_count = va.seg_count;
@@ -1993,7 +2002,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ra.hq_scratch = n_hq ? r->d_hq_scratch.p + (size_t)slot * n_hq * tb * 2 : nullptr;
     ra.gran_groups = va.gran_groups;
     std::memset(&ra.gran, 0, sizeof(ra.gran));
-    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b], r->sr_));
+    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b], srb));
     if (n_rows) {  // every grain's contribution to this block
       GrainArgs ga;
       ga.recs = va.gran.recs; ga.counters = va.gran.counters; ga.rec_cap = gran_rec_cap; ga.buffers = r->d_buffers.p;
@@ -2003,12 +2012,12 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       ga.carry_in = r->d_grain_carry[r->gran_parity ^ 1u].p;
       ga.carry_out = r->d_grain_carry[r->gran_parity].p;
       r->gran_parity ^= 1u;
-      grain_kernel<<<(gran_rec_cap + 127) / 128, 128, 0, r->sr_>>>(ga);
+      grain_kernel<<<(gran_rec_cap + 127) / 128, 128, 0, srb>>>(ga);
       ++launches;
       ra.gran.recs = ga.recs; ra.gran.vrec = va.gran.vrec; ra.gran.tile_range = va.gran.tile_range; ra.gran.storage = ga.storage;
       ra.gran.rec_cap = gran_rec_cap; ra.gran.vrec_cap = gran_vrec_cap; ra.gran.n_tiles = n_tiles; ra.gran.storage_cap = ga.storage_cap;
     }
-    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b + 1], r->sr_));
+    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b + 1], srb));
     if (n_hq) {  // materialise the resampler output this block consumes: one launch per filter table
       SincArgs sa;
       sa.recs = va.hq_recs; sa.n_recs = va.hq_n_recs; sa.cap = hq_cap; sa.buffers = r->d_buffers.p;
@@ -2017,21 +2026,21 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       const uint32_t n_tables = std::max<uint32_t>(1, (uint32_t)r->sinc_table_keys.size());
       for (uint32_t t = 0; t < n_tables; ++t) {
         sa.table = t; sa.do_copies = t == 0;
-        sinc_kernel<<<sm_count, SINC_THREADS, SINC_SMEM, r->sr_>>>(sa);
+        sinc_kernel<<<sm_count, SINC_THREADS, SINC_SMEM, srb>>>(sa);
         ++launches;
       }
     }
-    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b + 2], r->sr_));
+    if (!ev_x.empty()) CUDA_TRY(cudaEventRecord(ev_x[3 * (size_t)b + 2], srb));
     const uint32_t live_tiles = (blen + TILE - 1) / TILE;
-    CUDA_TRY(cudaEventRecord(ev_r0[b], r->sr_));  // stream order: every wait of this block's replay is behind it
+    CUDA_TRY(cudaEventRecord(ev_r0[b], srb));  // stream order: every wait of this block's replay is behind it
     static const bool skel_only = getenv("PB200_SKEL_ONLY") != nullptr;  // timing experiments: the skeleton pass alone (output invalid)
     if (!skel_only && ng > 0) {  // one launch over every group (the class lists are contiguous in d_class_groups)
       ra.group_list = r->d_class_groups.p;
       dim3 grid((live_tiles + REPLAY_THREADS - 1) / REPLAY_THREADS, ng);
-      replay_kernel<<<grid, REPLAY_THREADS, REPLAY_SMEM, r->sr_>>>(ra);
+      replay_kernel<<<grid, REPLAY_THREADS, REPLAY_SMEM, srb>>>(ra);
       ++launches;
     }
-    CUDA_TRY(cudaEventRecord(ev_r1[b], r->sr_));
+    CUDA_TRY(cudaEventRecord(ev_r1[b], srb));
     CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_r1[b], 0));
     CUDA_TRY(cudaEventRecord(ev_m0[b], r->sm));
     MixerKernelArgs ma;
@@ -2091,6 +2100,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   if (out_host) CUDA_TRY(cudaMemcpyAsync(out_host, dout, frames * 2 * sizeof(float), cudaMemcpyDeviceToHost, r->sm));
   CUDA_TRY(cudaStreamSynchronize(r->sm));
   CUDA_TRY(cudaStreamSynchronize(r->sr_));
+  CUDA_TRY(cudaStreamSynchronize(r->sr2));
   CUDA_TRY(cudaStreamSynchronize(r->sv));
   CUDA_TRY(cudaGetLastError());
   hp_mark("device done");
