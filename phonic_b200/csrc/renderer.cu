@@ -1849,6 +1849,18 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(r->sr2, ev_start, 0));
+  // host output in page-locked memory: copy block by block on the copy stream (an async copy to pageable memory would
+  // block this thread in the middle of the launch loop, so that case keeps the single copy at the end)
+  bool host_copy_per_block = false;
+  if (out_host) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, out_host) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+      if (!r->sc) CUDA_TRY(cudaStreamCreateWithFlags(&r->sc, cudaStreamNonBlocking));
+      host_copy_per_block = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
   static const bool no_alt = getenv("PB200_NO_REPLAY_ALT") != nullptr;
   const bool replay_alt = persistent && !no_alt && r->n_hq == 0 && r->n_gran_rows == 0;
   uint64_t launches = 0;
@@ -2094,10 +2106,15 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       launches += 1 + (n_fx ? 1 : 0) + (n_plain ? 1 : 0);
     }
     CUDA_TRY(cudaEventRecord(ev_m1[b], r->sm));
+    if (host_copy_per_block) {  // the block's WAV data leaves for the (pinned) host buffer while later blocks still render
+      CUDA_TRY(cudaStreamWaitEvent(r->sc, ev_m1[b], 0));
+      CUDA_TRY(cudaMemcpyAsync(out_host + (b0 - p0) * 2, dout + (b0 - p0) * 2, (size_t)blen * 2 * sizeof(float), cudaMemcpyDeviceToHost, r->sc));
+    }
   }
   CUDA_TRY(cudaEventRecord(ev_end, r->sm));
   hp_mark("launches enqueued");
-  if (out_host) CUDA_TRY(cudaMemcpyAsync(out_host, dout, frames * 2 * sizeof(float), cudaMemcpyDeviceToHost, r->sm));
+  if (out_host && !host_copy_per_block) CUDA_TRY(cudaMemcpyAsync(out_host, dout, frames * 2 * sizeof(float), cudaMemcpyDeviceToHost, r->sm));
+  if (host_copy_per_block) CUDA_TRY(cudaStreamSynchronize(r->sc));
   CUDA_TRY(cudaStreamSynchronize(r->sm));
   CUDA_TRY(cudaStreamSynchronize(r->sr_));
   CUDA_TRY(cudaStreamSynchronize(r->sr2));

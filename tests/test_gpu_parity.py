@@ -284,3 +284,23 @@ def test_phase_jumps_and_super_calls_equal_the_literal_loop(cuda_api, name):
         finally:
             del os.environ["PB200_SKEL_DEBUG"]
         assert np.array_equal(fast, slow), (name, flag)
+
+
+def test_pinned_host_output_is_copied_block_by_block(cuda_api):
+    """A page-locked output buffer takes the per-time-block copy path (renderer.cu host_copy_per_block): same bytes."""
+    import torch
+    from scenes import SCENES, SR
+    outs = []
+    for pinned in (False, True):
+        p = Player(cuda_api, SR)
+        info = SCENES["cfg2_small"](p)
+        frames = info["frames"]
+        if pinned:
+            t = torch.zeros(frames, 2, dtype=torch.float32).pin_memory()
+            p.render_into(t.numpy())
+            outs.append(t.numpy().copy())
+        else:
+            outs.append(p.render(frames))
+        p.close()
+    assert float(np.abs(outs[0]).max()) > 0.01
+    assert np.array_equal(outs[0], outs[1])
