@@ -53,6 +53,7 @@ struct MixerKernelArgs {
   uint32_t ext_len;               // frames of them inside this block
   double* meter;                  // main mixer: [wav block of the render][peak L, peak R, sum of squares L, R] or nullptr (MeteredSource)
   uint64_t render_start;          // first frame of the render call (meter rows count from it)
+  uint32_t direct_out;            // this level's (single) mixer writes the render output itself: its parent, the main mixer, has nothing else to do
   unsigned long long* progress;   // mapped host word: the main mixer's CTA stores progress_value when the block's output is final
   unsigned long long progress_value;
   unsigned long long* prof;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       for (uint32_t i = tid; i < len * 2; i += nt) s_ch[i & 1][pidx(i >> 1)] = __ldcg(g + i);
     }
   };
-  // returns this thread's max|x| of what it wrote when MX
+  // returns this thread's max|x| of the chunk's samples (before `gain`)
   auto stage_out = [&](float* __restrict__ g, const uint32_t len, const float gain, const bool scale) -> float {
     float mx = 0.0f;
     if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
@@ -189,13 +190,13 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       for (uint32_t i = tid; i < n4; i += nt) {
         const uint32_t f = 2 * i;
         float4 v = make_float4(s_ch[0][pidx(f)], s_ch[1][pidx(f)], s_ch[0][pidx(f + 1)], s_ch[1][pidx(f + 1)]);
-        if (scale) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
         mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        if (scale) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
         g4[i] = v;
       }
-      if ((len & 1u) && tid < 2) { float x = s_ch[tid][pidx(len - 1)]; if (scale) x *= gain; mx = fmaxf(mx, fabsf(x)); g[2 * (len - 1) + tid] = x; }
+      if ((len & 1u) && tid < 2) { float x = s_ch[tid][pidx(len - 1)]; mx = fmaxf(mx, fabsf(x)); if (scale) x *= gain; g[2 * (len - 1) + tid] = x; }
     } else {
-      for (uint32_t i = tid; i < len * 2; i += nt) { float x = s_ch[i & 1][pidx(i >> 1)]; if (scale) x *= gain; mx = fmaxf(mx, fabsf(x)); g[i] = x; }
+      for (uint32_t i = tid; i < len * 2; i += nt) { float x = s_ch[i & 1][pidx(i >> 1)]; mx = fmaxf(mx, fabsf(x)); if (scale) x *= gain; g[i] = x; }
     }
     return mx;
   };
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   uint32_t eff_byp = a.mstate[m].effects_bypassed;                  // MixedSource::effects_bypassed: this CTA is its only writer
   // WavStream's master-volume smoother: a shared copy (one L2 round trip per chunk otherwise); thread 0 is its only writer
   __shared__ ExpSm s_master;
-  if (is_main && tid == 0) s_master = *a.master;
+  const bool direct = !is_main && a.direct_out != 0;   // (host: the main mixer has this one child, no effects, no sources, static master volume)
+  if ((is_main || direct) && tid == 0) s_master = *a.master;
   __syncthreads();
   const uint32_t wbf = a.wav_block_frames;   // block_start is a multiple of it: boundaries are tested on 32-bit offsets
   bool any_fx_events = false;   // (static: event lists do not change during a launch)
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
     // move, so the decision holds for every chunk of the block
     bool master_direct = false, master_scale = false, chunk_done = false;
     float master_gain = 1.0f;
-    if (is_main && a.out && !a.meter) {
+    if ((is_main || direct) && a.out && !a.meter) {
       const ExpSm ms0 = s_master;
       if (!exp_need_ramp(ms0, a.fxc.comp)) { master_direct = true; master_gain = ms0.target; master_scale = fabsf(1.0f - master_gain) > 0.000001f; }
     }
@@ -409,7 +411,8 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
         if (master_direct && last_stage) {
           // main mixer, master volume not ramping, no meter: the chunk goes from shared memory straight to the output
           // (nobody reads the main bus again), scaled as WavStream::process does per block (wav.rs:237)
-          stage_out(a.out + (size_t)boff * 2, len, master_scale ? master_gain : 1.0f, master_scale);
+          const float mxo = stage_out(a.out + (size_t)boff * 2, len, master_scale ? master_gain : 1.0f, master_scale);
+          if (direct) { gate_mx = fmaxf(gate_mx, mxo); gate_covered += len; }   // (still a sub-mixer: its gate decides below)
           chunk_done = true;
         } else {
           // write the processed chunk back; a sub-mixer's silence gate wants max|x| of the parent chunk: collected here,
@@ -483,6 +486,8 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
         __syncthreads();
       }
     } else {
+      if (direct && master_direct && !chunk_done)   // (a chunk the effects did not touch, or a mixer without effects)
+        for (uint32_t i = tid; i < len * 2; i += nt) a.out[(size_t)boff * 2 + i] = master_scale ? gchunk[i] * master_gain : gchunk[i];
       // parent chunk ends here? -> SubMixerProcessor::process gate over the parent chunk span
       if (c1 == parent_next) {
         const uint64_t p0 = a.chunk_bounds[pk];
@@ -507,7 +512,11 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
             flag = 1u;
           }
           a.mixer_flags[(size_t)m * a.max_chunks + (pk - pcb)] = (uint8_t)flag;
+          s_run = flag;
         }
+        __syncthreads();
+        if (direct && master_direct && s_run == 0u)   // gated off: the main mixer does not add this span (submixer.rs:47-77)
+          for (uint32_t i = tid; i < pl * 2; i += nt) a.out[(size_t)o0 * 2 + i] = 0.0f;
         __syncthreads();
         pk++;
         parent_next = a.chunk_bounds[pk + 1];
@@ -515,7 +524,7 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
     }
     tick(6, t0);
   }
-  if (is_main && last_stage) publish_progress();
+  if ((is_main || direct) && last_stage) publish_progress();
   if (a.prof && tid == 0 && (is_main || a.prof_all))
     for (int i = 0; i < 8; ++i) atomicAdd(a.prof + (a.prof_all ? ((size_t)m * MAX_FX_STAGES + stage) * 8 : 0) + i, (unsigned long long)pt[i]);
 }

@@ -1861,6 +1861,18 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       cudaGetLastError();
     }
   }
+  // A main mixer that only passes its single sub-mixer through (no effects, no sources of its own, no external input, no
+  // meter, master volume at rest -- one rank's share of a sharded graph looks like this): the sub-mixer's kernel applies its
+  // own silence gate and the master gain and writes the output; the main level's two launches per block are skipped.
+  bool direct_child = false;
+  {
+    static const bool off = getenv("PB200_NO_DIRECT_CHILD") != nullptr;
+    const bool master_rest = r->h_master.current == r->h_master.target;
+    bool main_sources = false;
+    for (auto& g : r->groups) if (!g.removed && g.gp.mixer == 0) main_sources = true;
+    direct_child = !off && c.levels.size() >= 2 && c.levels[0].size() == 1 && c.levels[0][0] == 0 && c.levels[1].size() == 1 &&
+                   r->mixers[0].effects.empty() && !main_sources && r->n_ext == 0 && r->meter_interval == UINT64_MAX && master_rest;
+  }
   static const bool no_alt = getenv("PB200_NO_REPLAY_ALT") != nullptr;
   const bool replay_alt = persistent && !no_alt && r->n_hq == 0 && r->n_gran_rows == 0;
   uint64_t launches = 0;
@@ -2075,6 +2087,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     ma.ext_len = ma.n_ext ? (uint32_t)std::min<uint64_t>(blen, r->ext_frames - (b0 - p0)) : 0u;
     ma.prof_all = fx_prof_all ? 1u : 0u;
     for (int lvl = (int)c.levels.size() - 1; lvl >= 0 && !skel_only; --lvl) {
+      if (lvl == 0 && direct_child) break;          // the main mixer's only child has written the output itself
+      ma.direct_out = (lvl == 1 && direct_child) ? 1u : 0u;
       ma.level_mixers = r->d_level_mixers.p + c.level_offsets[lvl];
       const uint32_t nlm = (uint32_t)c.levels[lvl].size();
       mix_sum_kernel<<<dim3((blen + 255) / 256, nlm), 256, 0, r->sm>>>(ma);

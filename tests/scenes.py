@@ -251,7 +251,34 @@ def nested_and_gated(p: Player):
     return {"frames": W.frames_for(5, SR)}
 
 
+def single_submixer_gated(p: Player):
+    """the main mixer only passes ONE sub-mixer through (a rank's share of a sharded graph): the sub-mixer's kernel writes the
+    output itself (renderer.cu direct_child). No effects anywhere (bit-exact); the sub-mixer -- and a nested one -- go silent
+    for > 2 s, so the silence gate closes and re-opens."""
+    b = p.upload_buffer(tone(12000, 44100, seed=21), 44100)
+    m1 = p.add_mixer(None)
+    m2 = p.add_mixer(m1.id)
+    p.play_file_source(b, FilePlaybackOptions(volume=0.5, target_mixer=m1.id))
+    p.play_file_source(b, FilePlaybackOptions(volume=0.4, panning=-0.3, target_mixer=m2.id), start_time=3000)
+    p.play_file_source(b, FilePlaybackOptions(volume=0.5, target_mixer=m1.id), start_time=int(3.4 * SR) + 77)
+    p.play_file_source(b, FilePlaybackOptions(volume=0.3, panning=0.5, target_mixer=m2.id), start_time=int(4.1 * SR))
+    return {"frames": W.frames_for(5, SR)}
+
+
+def single_submixer_filter(p: Player):
+    """same shape with an effect chain on the single sub-mixer (staged chunks, bypass transitions) and a master volume != 1"""
+    b = p.upload_buffer(tone(12000, 44100, seed=22), 44100)
+    m1 = p.add_mixer(None)
+    fx = p.add_effect(FilterEffect(0, 2500.0, 0.707), m1.id)
+    fx.set_parameter("cuto", 1200.0, int(3.6 * SR))
+    p.play_file_source(b, FilePlaybackOptions(volume=0.5, target_mixer=m1.id))
+    p.play_file_source(b, FilePlaybackOptions(volume=0.5, target_mixer=m1.id), start_time=int(3.3 * SR) + 5)
+    return {"frames": W.frames_for(5, SR)}
+
+
 SCENES = {
+    "single_submixer_gated": single_submixer_gated,
+    "single_submixer_filter": single_submixer_filter,
     "file_mono_default": file_mono_default,
     "file_stereo_fast_loop": file_stereo_fast_loop,
     "file_events": file_events,
@@ -294,7 +321,7 @@ SCENES = {
 }
 
 # scenes whose whole path is +,-,*,/,sqrt in the reference's order: must be bit-exact on device
-BIT_EXACT = {"many_groups", "fx_gain_dc", "fx_panning", "fx_dist_softclip", "fx_dist_hardclip", "fx_dist_fold", "file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
+BIT_EXACT = {"single_submixer_gated", "many_groups", "fx_gain_dc", "fx_panning", "fx_dist_softclip", "fx_dist_hardclip", "fx_dist_fold", "file_mono_default", "file_stereo_fast_loop", "file_events", "file_bypass", "sampler_notes",
              "sampler_no_envelope", "hq_equal_rates", "gran_cloud", "gran_resampled_fixed", "gran_sequential_loop", "gran_dense"}
 # bit-exact voice path + time-invariant biquads evaluated by the f64 block scan (exact up to O(1e-16)
 # relative reassociation error before the f32 cast): at most a rare last-bit flip
