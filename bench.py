@@ -98,6 +98,18 @@ def cfg5_submixers(world):
     return [len(b) for b in bins]
 
 
+_CFG4_BUFFER = None
+
+
+def cfg4_buffer():
+    """cfg4's synthetic pad-shaped sample (host memory), synthesised once like `sample_buffer`: input data, not the path."""
+    global _CFG4_BUFFER
+    if _CFG4_BUFFER is None:
+        from phonic_b200 import workloads as W
+        _CFG4_BUFFER = W.synth_buffer(362835, 48000, seed=4)
+    return _CFG4_BUFFER
+
+
 def build_scene(player, name, rank=0, as_subtree=False, world=1):
     """Builds the workload on `player` from the host sample buffer (upload + graph + events)."""
     from phonic_b200 import workloads as W
@@ -118,7 +130,7 @@ def build_scene(player, name, rank=0, as_subtree=False, world=1):
             W.add_voice_bank_fast(player, W.VoiceBankSpec(voices=spec["voices"]), bid, mh.id, seed_offset=7919 * rank)
             player.add_effect(FilterEffect(0, 2000.0, 0.707), mh.id)
     elif name == "cfg4":
-        W.build_cfg4(player, spec["voices"])
+        W.build_cfg4(player, spec["voices"], buffer=cfg4_buffer())
     elif name == "sinc":
         W.build_sinc_bank(player, spec["voices"], buffer=buf)
     else:
@@ -248,7 +260,7 @@ def build_cpu_sample(p, name, rank=0, as_subtree=False):
         build_scene(p, name, rank=rank, as_subtree=as_subtree)
         return spec["voices"], f"full {name} render"
     if name == "cfg4":
-        W.build_cfg4(p, 32)
+        W.build_cfg4(p, 32, buffer=cfg4_buffer())
         return 32, "cfg4 with 32 of 160 voices (same per-voice events)"
     if name == "sinc":
         W.build_sinc_bank(p, 16, buffer=sample_buffer())
@@ -323,6 +335,8 @@ def run_reference(args):
     voices = spec["voices"]
     world = max(1, args.gpus)
     sample_buffer()
+    if args.workload == "cfg4":
+        cfg4_buffer()
     times = []
     v_per, sample = voices, ""
     for i in range(args.warmup + args.steps):
@@ -405,6 +419,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
 
     sample_buffer()  # synthesise the input data before anything is timed
+    if args.workload == "cfg4":
+        cfg4_buffer()
 
     # ---- device-resident arm: scenes built and uploaded before the timed region -------------------------------
     main_bus = bool(spec.get("main_bus"))

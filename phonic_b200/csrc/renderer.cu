@@ -235,6 +235,7 @@ struct pb200_renderer {
   RenderConsts rc;
 
   std::vector<HostBuffer> buffers;
+  std::map<uint32_t, uint32_t> gran_buffer_of;   // file buffer -> its mono, output-rate copy for granular playback
   std::vector<HostMixer> mixers;            // dense; [0] = main
   std::map<uint32_t, uint32_t> mixer_by_id; // public -> dense
   std::vector<HostGroup> groups;
@@ -996,8 +997,15 @@ int pb200_add_sampler(pb200_renderer* r, uint32_t buffer_id, const pb200_sampler
       return fail(r, PB200_ERR_PARAMETER, "Invalid granular parameters");
     if (p.variation != 0.0f || p.spray != 0.0f || p.pan_spread != 0.0f || p.playback_direction == 2)
       return fail(r, PB200_ERR_UNSUPPORTED, "OS-seeded grain randomisation is not reproducible");
+    // create_granular_sample_buffer (sampler.rs:908-952) depends on the file buffer and the output rate only: samplers
+    // that play the same buffer share one device copy of it instead of resampling it once each
     uint32_t gbuf = 0;
-    if (int e = make_granular_buffer(r, buffer_id, &gbuf)) return e;
+    auto cached = r->gran_buffer_of.find(buffer_id);
+    if (cached != r->gran_buffer_of.end()) gbuf = cached->second;
+    else {
+      if (int e = make_granular_buffer(r, buffer_id, &gbuf)) return e;
+      r->gran_buffer_of[buffer_id] = gbuf;
+    }
     const DevBuffer& fb = r->buffers[buffer_id].dev;  // (re-read: the buffer vector may have grown)
     gg.enabled = 1;
     gg.overlap_mode = p.overlap_mode; gg.window = p.window; gg.backward = p.playback_direction == 1;
@@ -1835,16 +1843,27 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     }
   }
   hp_mark("schedule + work areas");
+  // Every event of the call comes out of this set: however the call ends (each CUDA_TRY below may return early), the
+  // renderer's streams are drained first -- no kernel of a failed call is left in flight -- and the events go back to the pool.
+  struct EventSet {
+    pb200_renderer* r;
+    std::vector<cudaEvent_t> all;
+    cudaError_t get(cudaEvent_t* e) { const cudaError_t c = DevicePool::get().event(e); if (c == cudaSuccess) all.push_back(*e); return c; }
+    ~EventSet() {
+      for (cudaStream_t st : {r->sv, r->sr_, r->sr2, r->sm, r->sc}) if (st) cudaStreamSynchronize(st);
+      for (cudaEvent_t e : all) DevicePool::get().release_event(e);
+    }
+  } events{r, {}};
   std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r0(n_blocks), ev_r1(n_blocks), ev_m0(n_blocks), ev_m1(n_blocks);
   std::vector<cudaEvent_t> ev_x((n_hq || n_rows) ? 3 * (size_t)n_blocks : 0);  // grain begin / grain end = sinc begin / sinc end
-  for (auto& e : ev_x) CUDA_TRY(DevicePool::get().event(&e));
+  for (auto& e : ev_x) CUDA_TRY(events.get(&e));
   for (uint32_t b = 0; b < n_blocks; ++b) {
-    CUDA_TRY(DevicePool::get().event(&ev_v0[b])); CUDA_TRY(DevicePool::get().event(&ev_v1[b]));
-    CUDA_TRY(DevicePool::get().event(&ev_r1[b])); CUDA_TRY(DevicePool::get().event(&ev_m1[b]));
-    CUDA_TRY(DevicePool::get().event(&ev_r0[b])); CUDA_TRY(DevicePool::get().event(&ev_m0[b]));
+    CUDA_TRY(events.get(&ev_v0[b])); CUDA_TRY(events.get(&ev_v1[b]));
+    CUDA_TRY(events.get(&ev_r1[b])); CUDA_TRY(events.get(&ev_m1[b]));
+    CUDA_TRY(events.get(&ev_r0[b])); CUDA_TRY(events.get(&ev_m0[b]));
   }
   cudaEvent_t ev_start, ev_end;
-  CUDA_TRY(DevicePool::get().event(&ev_start)); CUDA_TRY(DevicePool::get().event(&ev_end));
+  CUDA_TRY(events.get(&ev_start)); CUDA_TRY(events.get(&ev_end));
   CUDA_TRY(cudaEventRecord(ev_start, r->sv));
   CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
   CUDA_TRY(cudaStreamWaitEvent(r->sr_, ev_start, 0));
@@ -1878,7 +1897,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   uint64_t launches = 0;
   uint32_t gen0 = 0;
   cudaEvent_t ev_skel_end;
-  CUDA_TRY(DevicePool::get().event(&ev_skel_end));
+  CUDA_TRY(events.get(&ev_skel_end));
   // PB200_SKEL_PROF=<file>: per-voice cycle counters of the skeleton pass (debug aid)
   unsigned long long* prof_buf = nullptr;
   if (getenv("PB200_SKEL_PROF")) {
@@ -2195,17 +2214,11 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     else if (b == 0) { cudaEventElapsedTime(&ms, ev_v0[0], ev_skel_end); r->stats.skeleton_kernel_ms += ms; }
     cudaEventElapsedTime(&ms, ev_r0[b], ev_r1[b]); r->stats.voice_kernel_ms += ms;   // the replay launches alone
     cudaEventElapsedTime(&ms, ev_m0[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
-    DevicePool::get().release_event(ev_v0[b]); DevicePool::get().release_event(ev_v1[b]);
-    DevicePool::get().release_event(ev_r1[b]); DevicePool::get().release_event(ev_m1[b]);
-    DevicePool::get().release_event(ev_r0[b]); DevicePool::get().release_event(ev_m0[b]);
   }
   for (uint32_t b = 0; b < n_blocks && !ev_x.empty(); ++b) {
     cudaEventElapsedTime(&ms, ev_x[3 * (size_t)b], ev_x[3 * (size_t)b + 1]); r->stats.grain_kernel_ms += ms;
     cudaEventElapsedTime(&ms, ev_x[3 * (size_t)b + 1], ev_x[3 * (size_t)b + 2]); r->stats.sinc_kernel_ms += ms;
   }
-  for (auto& e : ev_x) DevicePool::get().release_event(e);
-  DevicePool::get().release_event(ev_start); DevicePool::get().release_event(ev_end);
-  DevicePool::get().release_event(ev_skel_end);
   r->stats.kernel_launches = launches;
   if (n_hq) {
     std::vector<uint32_t> counts(n_blocks);

@@ -226,7 +226,7 @@ def add_main_bus_sends(player: Player):
 
 
 def build_cfg4(player: Player, voices: int = 160, voices_per_sampler: int = 8, time_scale: float = 1.0, seed: int = 4,
-               wav_path: str | None = None):
+               wav_path: str | None = None, buffer=None):
     """cfg4: granular synthesis, 16k grains/s: a pad-ambient.wav-shaped mono buffer (362 835 frames
     @ 48 kHz, loop 286 619..362 834), `voices` voices x density 100 Hz x size 100 ms, Hann, Forward, step 1.0, no
     randomisation. Notes as in cfg2 (on in [0, 2 s), off in [6, 8 s)), AHDSR (10 ms, 0, 500 ms, 0.75, 1 s)."""
@@ -234,7 +234,7 @@ def build_cfg4(player: Player, voices: int = 160, voices_per_sampler: int = 8, t
         bid, _ = player.upload_wav(wav_path)
     else:
         frames = 362835
-        buf = synth_buffer(frames, 48000, seed=seed)
+        buf = buffer if buffer is not None else synth_buffer(frames, 48000, seed=seed)   # (`buffer`: the same data, synthesised once)
         bid = player.upload_buffer(buf, 48000, loop_range=(286619, 362834))
     rng = np.random.default_rng(seed + 1)
     ahdsr = AhdsrParameters(attack=0.01, hold=0.0, decay=0.5, sustain=0.75, release=1.0)
