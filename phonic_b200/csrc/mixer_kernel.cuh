@@ -218,8 +218,19 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   __shared__ uint8_t s_aud[AUD_MAX];
   auto audible_of = [&](const uint32_t kk) -> bool {
     bool aud = is_main && a.n_ext != 0;   // (an external bus counts as an audible sub-mixer)
-    for (uint32_t ci = mp.child_begin; ci < mp.child_end && !aud; ++ci) aud = a.mixer_flags[(size_t)a.child_index[ci] * a.max_chunks + (kk - cb)] != 0;
-    for (uint32_t si = mp.src_begin; si < mp.src_end && !aud; ++si) aud = a.group_flags[(size_t)a.source_index[si] * a.max_chunks + (kk - cb)] != 0;
+    // (eight flags per round trip: the loads of a batch are independent, the early exit is taken between batches)
+    for (uint32_t ci = mp.child_begin; ci < mp.child_end && !aud; ci += 8) {
+      uint32_t any = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j) if (ci + j < mp.child_end) any |= a.mixer_flags[(size_t)a.child_index[ci + j] * a.max_chunks + (kk - cb)];
+      aud = any != 0;
+    }
+    for (uint32_t si = mp.src_begin; si < mp.src_end && !aud; si += 8) {
+      uint32_t any = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j) if (si + j < mp.src_end) any |= a.group_flags[(size_t)a.source_index[si + j] * a.max_chunks + (kk - cb)];
+      aud = any != 0;
+    }
     return aud;
   };
   // this mixer's chunk boundaries of the block in shared memory (a dependent L2 load per use otherwise: ~700 cycles each,

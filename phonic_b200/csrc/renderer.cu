@@ -97,6 +97,17 @@ struct DevicePool {
     return cudaEventCreate(ev);
   }
   void release_event(cudaEvent_t ev) { std::lock_guard<std::mutex> g(mu); free_events.push_back(ev); }
+  // idle non-blocking streams per (device, priority): creating four streams costs a short-lived renderer ~0.2 ms
+  std::map<std::pair<int, int>, std::vector<cudaStream_t>> free_streams;
+  cudaError_t stream(cudaStream_t* s, int dev, int prio) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto& v = free_streams[{dev, prio}];
+      if (!v.empty()) { *s = v.back(); v.pop_back(); return cudaSuccess; }
+    }
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio);
+  }
+  void release_stream(cudaStream_t s, int dev, int prio) { std::lock_guard<std::mutex> g(mu); free_streams[{dev, prio}].push_back(s); }   // (caller has drained it)
 };
 
 template <class T>
@@ -232,6 +243,7 @@ struct pb200_renderer {
   std::string last_error;
   int device = 0;
   cudaStream_t sv = nullptr, sm = nullptr;
+  int prio[3] = {0, 0, 0};   // priorities of sv, sr_/sr2, sm (the pool hands streams out per device and priority)
   RenderConsts rc;
 
   std::vector<HostBuffer> buffers;
@@ -663,17 +675,24 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
   static const bool skel_first = !(getenv("PB200_PRIO_ORDER") && !strcmp(getenv("PB200_PRIO_ORDER"), "replay"));
   const int p_mid = std::min(prio_lo, prio_hi + 1);
   const int p_mix = flat_prio ? prio_lo : prio_hi, p_skel = flat_prio || !skel_first ? prio_lo : p_mid, p_rep = flat_prio || skel_first ? prio_lo : p_mid;
-  if (cudaStreamCreateWithPriority(&r->sv, cudaStreamNonBlocking, p_skel) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&r->sr_, cudaStreamNonBlocking, p_rep) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&r->sr2, cudaStreamNonBlocking, p_rep) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&r->sm, cudaStreamNonBlocking, p_mix) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+  if (DevicePool::get().stream(&r->sv, r->device, p_skel) != cudaSuccess ||
+      DevicePool::get().stream(&r->sr_, r->device, p_rep) != cudaSuccess ||
+      DevicePool::get().stream(&r->sr2, r->device, p_rep) != cudaSuccess ||
+      DevicePool::get().stream(&r->sm, r->device, p_mix) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+  r->prio[0] = p_skel; r->prio[1] = p_rep; r->prio[2] = p_mix;
   r->progress = ProgressWords::get().take();
   if (!r->progress) { delete r; return PB200_ERR_CUDA; }
   *r->progress = 0;
-  {
-    double note_speed[128];
-    for (uint32_t n = 0; n < 128; ++n) note_speed[n] = speed_from_note_h(n);
-    if (cudaMemcpyToSymbol(c_note_speed, note_speed, sizeof(note_speed)) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+  {  // the note -> speed table is the same for every renderer: uploaded once per device
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> g(mu);
+    if (std::find(done.begin(), done.end(), r->device) == done.end()) {
+      double note_speed[128];
+      for (uint32_t n = 0; n < 128; ++n) note_speed[n] = speed_from_note_h(n);
+      if (cudaMemcpyToSymbol(c_note_speed, note_speed, sizeof(note_speed)) != cudaSuccess) { delete r; return PB200_ERR_CUDA; }
+      done.push_back(r->device);
+    }
   }
   r->rc.sample_rate = config->sample_rate;
   r->rc.rate_comp = 44100.0f / (float)config->sample_rate;
@@ -709,10 +728,10 @@ void pb200_destroy(pb200_renderer* r) {
   r->d_bounds.free(); r->d_chunk_begin.free(); r->d_group_bus.free(); r->d_mixer_bus.free(); r->d_out.free();
   r->d_group_flags.free(); r->d_mixer_flags.free(); r->d_master.free();
   r->d_segs.free(); r->d_gsegs.free(); r->d_seg_first.free(); r->d_seg_count.free(); r->d_gseg_first.free(); r->d_gseg_count.free(); r->d_recs.free();
-  if (r->sr_) cudaStreamDestroy(r->sr_);
-  if (r->sr2) cudaStreamDestroy(r->sr2);
-  if (r->sv) cudaStreamDestroy(r->sv);
-  if (r->sm) cudaStreamDestroy(r->sm);
+  if (r->sr_) DevicePool::get().release_stream(r->sr_, r->device, r->prio[1]);
+  if (r->sr2) DevicePool::get().release_stream(r->sr2, r->device, r->prio[1]);
+  if (r->sv) DevicePool::get().release_stream(r->sv, r->device, r->prio[0]);
+  if (r->sm) DevicePool::get().release_stream(r->sm, r->device, r->prio[2]);
   if (r->sc) { cudaStreamSynchronize(r->sc); cudaStreamDestroy(r->sc); }
   if (r->push_flags) cudaFreeHost(r->push_flags);
   ProgressWords::get().give(r->progress);
