@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <atomic>
@@ -215,6 +216,23 @@ constexpr uint32_t RING = 3;
 
 }  // namespace
 
+// The events of a render call. While the call runs they guard its exits: however it ends (each CUDA_TRY may return early)
+// the renderer's streams are drained first -- no kernel of a failed call is left in flight -- and the events go back to the
+// pool. After a successful call the set is kept by the renderer until somebody asks for the per-pass spans
+// (pb200_last_render_stats): ~50 cudaEventElapsedTime calls that a caller who only wants the audio does not pay for.
+struct SpanEvents {
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> all;
+  std::vector<cudaEvent_t> v0, v1, r0, r1, m0, m1, x;
+  cudaEvent_t start = nullptr, end = nullptr, skel_end = nullptr;
+  bool persistent = false, complete = false;
+  cudaError_t get(cudaEvent_t* e) { const cudaError_t c = DevicePool::get().event(e); if (c == cudaSuccess) all.push_back(*e); return c; }
+  ~SpanEvents() {
+    if (!complete) for (cudaStream_t st : streams) if (st) cudaStreamSynchronize(st);
+    for (cudaEvent_t e : all) DevicePool::get().release_event(e);
+  }
+};
+
 // Pinned, device-mapped progress words (one per renderer) out of one process-wide slab: cudaHostAlloc / cudaFreeHost per
 // renderer would synchronise the device every time a short-lived renderer comes or goes.
 class ProgressWords {
@@ -340,6 +358,7 @@ struct pb200_renderer {
   uint64_t position = 0;  // frames
   bool finished = false;
   // pb200_render_progress: output frames that are final (read from other host threads while a render runs)
+  std::unique_ptr<SpanEvents> spans;        // events of the last render call whose spans have not been read yet
   unsigned long long* progress = nullptr;   // pinned, mapped host word: the main mixer's last CTA of a time block stores into it
   uint64_t progress_base = 0;               // frames of all earlier render calls
   const float* ext_input[PB_MAX_EXT] = {};   // pb200_set_main_inputs: device stereo buses the next render adds to the main mixer
@@ -714,6 +733,7 @@ int pb200_create(const pb200_config* config, pb200_renderer** out) {
 void pb200_destroy(pb200_renderer* r) {
   if (!r) return;
   cudaSetDevice(r->device);
+  r->spans.reset();
   if (r->sv) cudaStreamSynchronize(r->sv);
   if (r->sr_) cudaStreamSynchronize(r->sr_);
   if (r->sr2) cudaStreamSynchronize(r->sr2);
@@ -1862,26 +1882,21 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     }
   }
   hp_mark("schedule + work areas");
-  // Every event of the call comes out of this set: however the call ends (each CUDA_TRY below may return early), the
-  // renderer's streams are drained first -- no kernel of a failed call is left in flight -- and the events go back to the pool.
-  struct EventSet {
-    pb200_renderer* r;
-    std::vector<cudaEvent_t> all;
-    cudaError_t get(cudaEvent_t* e) { const cudaError_t c = DevicePool::get().event(e); if (c == cudaSuccess) all.push_back(*e); return c; }
-    ~EventSet() {
-      for (cudaStream_t st : {r->sv, r->sr_, r->sr2, r->sm, r->sc}) if (st) cudaStreamSynchronize(st);
-      for (cudaEvent_t e : all) DevicePool::get().release_event(e);
-    }
-  } events{r, {}};
-  std::vector<cudaEvent_t> ev_v0(n_blocks), ev_v1(n_blocks), ev_r0(n_blocks), ev_r1(n_blocks), ev_m0(n_blocks), ev_m1(n_blocks);
-  std::vector<cudaEvent_t> ev_x((n_hq || n_rows) ? 3 * (size_t)n_blocks : 0);  // grain begin / grain end = sinc begin / sinc end
+  r->spans.reset();
+  std::unique_ptr<SpanEvents> sp(new SpanEvents);
+  SpanEvents& events = *sp;
+  events.streams = {r->sv, r->sr_, r->sr2, r->sm, r->sc};
+  auto &ev_v0 = sp->v0, &ev_v1 = sp->v1, &ev_r0 = sp->r0, &ev_r1 = sp->r1, &ev_m0 = sp->m0, &ev_m1 = sp->m1, &ev_x = sp->x;
+  for (auto* v : {&ev_v0, &ev_v1, &ev_r0, &ev_r1, &ev_m0, &ev_m1}) v->resize(n_blocks);
+  ev_x.resize((n_hq || n_rows) ? 3 * (size_t)n_blocks : 0);  // grain begin / grain end = sinc begin / sinc end
   for (auto& e : ev_x) CUDA_TRY(events.get(&e));
   for (uint32_t b = 0; b < n_blocks; ++b) {
     CUDA_TRY(events.get(&ev_v0[b])); CUDA_TRY(events.get(&ev_v1[b]));
     CUDA_TRY(events.get(&ev_r1[b])); CUDA_TRY(events.get(&ev_m1[b]));
     CUDA_TRY(events.get(&ev_r0[b])); CUDA_TRY(events.get(&ev_m0[b]));
   }
-  cudaEvent_t ev_start, ev_end;
+  sp->persistent = persistent;
+  cudaEvent_t &ev_start = sp->start, &ev_end = sp->end;
   CUDA_TRY(events.get(&ev_start)); CUDA_TRY(events.get(&ev_end));
   CUDA_TRY(cudaEventRecord(ev_start, r->sv));
   CUDA_TRY(cudaStreamWaitEvent(r->sm, ev_start, 0));
@@ -1915,7 +1930,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   const bool replay_alt = persistent && !no_alt && r->n_hq == 0 && r->n_gran_rows == 0;
   uint64_t launches = 0;
   uint32_t gen0 = 0;
-  cudaEvent_t ev_skel_end;
+  cudaEvent_t& ev_skel_end = sp->skel_end;
   CUDA_TRY(events.get(&ev_skel_end));
   // PB200_SKEL_PROF=<file>: per-voice cycle counters of the skeleton pass (debug aid)
   unsigned long long* prof_buf = nullptr;
@@ -2216,10 +2231,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     cudaMemcpyToSymbol(g_cyc, z, sizeof(z));
   }
 #endif
-  float ms = 0;
   r->stats = pb200_render_stats{};
-  cudaEventElapsedTime(&ms, ev_start, ev_end);
-  r->stats.device_ms = ms;
   if (host_prof) {  // device timeline of the call, ms since its first event
     auto at = [&](cudaEvent_t e) { float t = 0; cudaEventElapsedTime(&t, ev_start, e); return t; };
     fprintf(stderr, "[dev] end %.3f", at(ev_end));
@@ -2228,17 +2240,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
     for (uint32_t b = 0; b < n_blocks; ++b) fprintf(stderr, " [%u] %.2f..%.2f %.2f..%.2f", b, at(ev_r0[b]), at(ev_r1[b]), at(ev_m0[b]), at(ev_m1[b]));
     fprintf(stderr, "\n");
   }
-  for (uint32_t b = 0; b < n_blocks; ++b) {
-    if (!persistent) { cudaEventElapsedTime(&ms, ev_v0[b], ev_v1[b]); r->stats.skeleton_kernel_ms += ms; }
-    else if (b == 0) { cudaEventElapsedTime(&ms, ev_v0[0], ev_skel_end); r->stats.skeleton_kernel_ms += ms; }
-    cudaEventElapsedTime(&ms, ev_r0[b], ev_r1[b]); r->stats.voice_kernel_ms += ms;   // the replay launches alone
-    cudaEventElapsedTime(&ms, ev_m0[b], ev_m1[b]); r->stats.effect_kernel_ms += ms;
-  }
-  for (uint32_t b = 0; b < n_blocks && !ev_x.empty(); ++b) {
-    cudaEventElapsedTime(&ms, ev_x[3 * (size_t)b], ev_x[3 * (size_t)b + 1]); r->stats.grain_kernel_ms += ms;
-    cudaEventElapsedTime(&ms, ev_x[3 * (size_t)b + 1], ev_x[3 * (size_t)b + 2]); r->stats.sinc_kernel_ms += ms;
-  }
   r->stats.kernel_launches = launches;
+  hp_mark("  event spans");
   if (n_hq) {
     std::vector<uint32_t> counts(n_blocks);
     CUDA_TRY(cudaMemcpy(counts.data(), r->d_hq_nrecs.p, n_blocks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -2284,6 +2287,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
       r->status_events.push_back(e);
     }
   }
+  hp_mark("  list checks + status");
   r->host_state_valid = false;
   r->position = p1;
   // statistics + event cursors come back with the (small) group state
@@ -2345,6 +2349,8 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   }
   hp_mark("state download + bookkeeping");
   r->n_ext = 0; r->ext_frames = 0;   // (external main-mixer inputs serve one render call)
+  sp->complete = true;               // every stream has been drained above: the spans can be read whenever they are wanted
+  r->spans = std::move(sp);
   return PB200_OK;
 }
 
@@ -2550,6 +2556,23 @@ int pb200_get_audio_level(pb200_renderer* r, pb200_audio_level* out) {
 
 int pb200_last_render_stats(pb200_renderer* r, pb200_render_stats* st) {
   if (!r || !st) return PB200_ERR_PARAMETER;
+  if (r->spans) {  // the per-pass spans of the last call, computed on first request
+    const SpanEvents& e = *r->spans;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e.start, e.end);
+    r->stats.device_ms = ms;
+    for (size_t b = 0; b < e.r0.size(); ++b) {
+      if (!e.persistent) { cudaEventElapsedTime(&ms, e.v0[b], e.v1[b]); r->stats.skeleton_kernel_ms += ms; }
+      else if (b == 0) { cudaEventElapsedTime(&ms, e.v0[0], e.skel_end); r->stats.skeleton_kernel_ms += ms; }
+      cudaEventElapsedTime(&ms, e.r0[b], e.r1[b]); r->stats.voice_kernel_ms += ms;   // the replay launches alone
+      cudaEventElapsedTime(&ms, e.m0[b], e.m1[b]); r->stats.effect_kernel_ms += ms;
+    }
+    for (size_t b = 0; 3 * b + 2 < e.x.size(); ++b) {
+      cudaEventElapsedTime(&ms, e.x[3 * b], e.x[3 * b + 1]); r->stats.grain_kernel_ms += ms;
+      cudaEventElapsedTime(&ms, e.x[3 * b + 1], e.x[3 * b + 2]); r->stats.sinc_kernel_ms += ms;
+    }
+    r->spans.reset();
+  }
   *st = r->stats;
   return PB200_OK;
 }
