@@ -304,3 +304,18 @@ def test_pinned_host_output_is_copied_block_by_block(cuda_api):
         p.close()
     assert float(np.abs(outs[0]).max()) > 0.01
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_pool_trim_gives_memory_back_and_rendering_goes_on(cuda_api):
+    """pb200_trim_pool: idle pooled blocks go back to the driver; the next renderer simply allocates again (same bytes)."""
+    from scenes import SCENES, SR
+    outs = []
+    for it in range(2):
+        p = Player(cuda_api, SR)
+        info = SCENES["sampler_notes"](p)
+        outs.append(p.render(info["frames"]))
+        p.close()
+        freed = int(cuda_api.trim_pool(-1))
+        assert freed > 0, "a closed renderer leaves its blocks in the pool"
+        assert int(cuda_api.trim_pool(-1)) == 0
+    assert np.array_equal(outs[0], outs[1])
