@@ -325,6 +325,55 @@ PB_DEV void biquad_scan_stereo(const BiquadCoef& c, double* ic1, double* ic2, ui
   __syncthreads();
 }
 
+// The same scan over two f64 planes, in place (the reverb's three filters work on its f64 signal path): threads [0,128) /
+// [128,256) = plane 0 / 1. `ic`: the filter's state as [plane][2]. Ends with a CTA barrier.
+PB_DEV void biquad_scan_planes64(const BiquadCoef& c, double (*ic)[2], double* const* planes, double* lane_state, uint32_t len, uint32_t tid) {
+  const uint32_t ch = tid >> 7, j = tid & 127u, lane = tid & 31u, w = j >> 5;
+  const double in1 = ic[ch][0], in2 = ic[ch][1];
+  __syncthreads();  // every thread has read the incoming state before the owner of the last sample replaces it
+  if (len == 0) return;
+  const uint32_t B = (len + 127u) / 128u;
+  const uint32_t lo = min(j * B, len), hi = min(lo + B, len);
+  double* x = planes[ch];
+  double* ls = lane_state + (size_t)ch * 64;
+  const Mat2 A{2.0 * c.a1 - 1.0, -2.0 * c.a2, 2.0 * c.a2, 1.0 - 2.0 * c.a3};
+  double e1 = 0.0, e2 = 0.0;
+  for (uint32_t n = lo; n < hi; ++n) x[pidx(n)] = biquad_tick(c, e1, e2, x[pidx(n)]);   // zero-state response, in place
+  const Mat2 P = mat_pow(A, B);
+  Mat2 Pd = P;
+  double E1 = e1, E2 = e2;
+#pragma unroll
+  for (uint32_t d = 1; d < 32; d <<= 1) {
+    const double u1 = __shfl_up_sync(0xFFFFFFFFu, E1, d), u2 = __shfl_up_sync(0xFFFFFFFFu, E2, d);
+    if (lane >= d) { E1 += Pd.a * u1 + Pd.b * u2; E2 += Pd.c * u1 + Pd.d * u2; }
+    Pd = mat_mul(Pd, Pd);
+  }
+  if (lane == 31) { ls[w * 2] = E1; ls[w * 2 + 1] = E2; }
+  __syncthreads();
+  double W1 = in1, W2 = in2;
+  for (uint32_t q = 0; q < w; ++q) {
+    const double t1 = Pd.a * W1 + Pd.b * W2 + ls[q * 2], t2 = Pd.c * W1 + Pd.d * W2 + ls[q * 2 + 1];
+    W1 = t1; W2 = t2;
+  }
+  double p1 = __shfl_up_sync(0xFFFFFFFFu, E1, 1), p2 = __shfl_up_sync(0xFFFFFFFFu, E2, 1);
+  if (lane == 0) { p1 = 0.0; p2 = 0.0; }
+  Mat2 Q = P;
+#pragma unroll
+  for (uint32_t k = 0; k < 5; ++k) {
+    if ((lane >> k) & 1u) { const double t1 = Q.a * W1 + Q.b * W2, t2 = Q.c * W1 + Q.d * W2; W1 = t1; W2 = t2; }
+    Q = mat_mul(Q, Q);
+  }
+  const double C1 = c.m1 * c.a1 + c.m2 * c.a2, C2 = -c.m1 * c.a2 + c.m2 * (1.0 - c.a3);
+  double h1 = W1 + p1, h2 = W2 + p2;
+  for (uint32_t n = lo; n < hi; ++n) {
+    x[pidx(n)] += C1 * h1 + C2 * h2;
+    const double t1 = A.a * h1 + A.b * h2, t2 = A.c * h1 + A.d * h2;
+    h1 = t1; h2 = t2;
+  }
+  if (hi == len && lo < hi) { ic[ch][0] = h1 + e1; ic[ch][1] = h2 + e2; }
+  __syncthreads();
+}
+
 // ---- FilterEffect::process (filter.rs:166-201): warps 0/1 = channels ---------------------------------------
 PB_DEV void filter_process(FilterState& s, const FxCtx& cx, const ChunkBuf& cb, uint32_t frames, uint32_t lane, uint32_t warp) {
   const bool ramp = exp_need_ramp(s.cutoff, cx.comp) || lin_need_ramp(s.q);

@@ -495,13 +495,10 @@ PB_DEV void reverb_parallel_impl(ReverbState& s, const FxCtx& cx, const ChunkBuf
       }
     }
     // (b) biquad A (block scan, in place), * wet, sin
-    if (warp < 2) {
-      double ic1 = s.a_ic[warp][0], ic2 = s.a_ic[warp][1];
+    {
       const BiquadCoef cf = s.ca;
-      biquad_scan_channel(cf, ic1, ic2, nullptr, A[warp], cb.lane_state + (size_t)warp * 64, len, lane, A[warp], A[warp]);
-      if (lane == 0) { s.a_ic[warp][0] = ic1; s.a_ic[warp][1] = ic2; }
+      biquad_scan_planes64(cf, s.a_ic, A, cb.lane_state, len, tid);   // (all 256 threads; ends with a barrier)
     }
-    __syncthreads();
     // (c) sin(x * wet), then the four Schroeder allpasses in series (delay.rs:314-350). An allpass reads the slot the NEXT
     // frame overwrites, but never a slot written inside this sub-block (delay >= RVL): the chain is pointwise per
     // (frame, channel) -- all reads of the four stages first, then, behind one barrier, all writes.
@@ -602,25 +599,19 @@ PB_DEV void reverb_parallel_impl(ReverbState& s, const FxCtx& cx, const ChunkBuf
       if (tid < 16) carry[tid] = FB[tid * RV_BATCH + bl - 1];  // read again only behind the next batch's two barriers
     }
     // (e) biquad B, clamp, asin, biquad C, dry mix
-    if (warp < 2) {
-      double ic1 = s.b_ic[warp][0], ic2 = s.b_ic[warp][1];
+    {
       const BiquadCoef cf = s.cb;
-      biquad_scan_channel(cf, ic1, ic2, nullptr, A[warp], cb.lane_state + (size_t)warp * 64, len, lane, A[warp], A[warp]);
-      if (lane == 0) { s.b_ic[warp][0] = ic1; s.b_ic[warp][1] = ic2; }
+      biquad_scan_planes64(cf, s.b_ic, A, cb.lane_state, len, tid);   // (all 256 threads; ends with a barrier)
     }
-    __syncthreads();
     for (uint32_t i = tid; i < len * 2; i += nt) {
       const uint32_t f = i >> 1, ch = i & 1;
       A[ch][pidx(f)] = asin(fmin(fmax(A[ch][pidx(f)], -1.0), 1.0));
     }
     __syncthreads();
-    if (warp < 2) {
-      double ic1 = s.c_ic[warp][0], ic2 = s.c_ic[warp][1];
+    {
       const BiquadCoef cf = s.cc;
-      biquad_scan_channel(cf, ic1, ic2, nullptr, A[warp], cb.lane_state + (size_t)warp * 64, len, lane, A[warp], A[warp]);
-      if (lane == 0) { s.c_ic[warp][0] = ic1; s.c_ic[warp][1] = ic2; }
+      biquad_scan_planes64(cf, s.c_ic, A, cb.lane_state, len, tid);   // (all 256 threads; ends with a barrier)
     }
-    __syncthreads();
     for (uint32_t i = tid; i < len * 2; i += nt) {
       const uint32_t f = i >> 1, ch = i & 1;
       double x = (double)(ch ? CB_R(f0 + f) : CB_L(f0 + f));
