@@ -259,12 +259,13 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
     // a main mixer without effects (the top of a tree whose work sits in the sub-mixers): while the master volume is not
     // ramping the whole time block is one scaled copy, whatever the chunk boundaries are
     const ExpSm ms0 = s_master;
-    if (!exp_need_ramp(ms0, a.fxc.comp)) {
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(bus) | reinterpret_cast<uintptr_t>(a.out)) & 15u) == 0 && (a.block_len & 1u) == 0;
+    if (vec_ok && !exp_need_ramp(ms0, a.fxc.comp)) {   // (odd block_frames: the chunk loop below copies frame by frame)
       const float g = ms0.target;
       const bool scale = fabsf(1.0f - g) > 0.000001f;
       const float4* src = reinterpret_cast<const float4*>(bus);
       float4* dst = reinterpret_cast<float4*>(a.out);
-      const uint32_t n4 = a.block_len / 2;   // block lengths are multiples of the 1024-frame WavStream block
+      const uint32_t n4 = a.block_len / 2;
       for (uint32_t i = tid; i < n4; i += nt) {
         float4 v = src[i];
         if (scale) { v.x *= g; v.y *= g; v.z *= g; v.w *= g; }

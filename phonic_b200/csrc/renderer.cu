@@ -1692,7 +1692,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
   CUDA_TRY(cudaFuncSetAttribute(mix_fx_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_WORK_SMALL));
   CUDA_TRY(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REPLAY_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(skeleton_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (TAB_SLOT_WORDS * 4 + 12) + 16));
-  const uint32_t n_tiles = tb / TILE;
+  const uint32_t n_tiles = ((tb + TILE - 1) / TILE + 15u) / 16u * 16u;   // (a block size that is no multiple of 64 ends in a partial tile; rows stay 16-byte aligned)
   const uint32_t seg_cap = n_tiles + max_chunks + 8;
   if (seg_cap >= 65535) return fail(r, PB200_ERR_UNSUPPORTED, "too many chunk boundaries in one time block");
   const size_t nvoices = std::max<size_t>(1, r->h_voices.size());

@@ -151,11 +151,12 @@ __global__ void __launch_bounds__(REPLAY_THREADS, 6) replay_kernel(ReplayArgs a)
   float* gbus = a.group_bus + (size_t)g * a.block_frames * 2;
   for (uint32_t r = 0; r < 32; ++r) {
     const uint32_t rtile = blockIdx.x * REPLAY_THREADS + w0 + r;
-    if (rtile >= a.n_tiles) break;
+    if (rtile >= a.n_tiles || rtile * TILE >= a.block_frames) break;
     const float* src = smem + (size_t)(w0 + r) * ROWP;
     float* dst = gbus + (size_t)rtile * TILE * 2;
+    const uint32_t live = min(2u * TILE, (a.block_frames - rtile * TILE) * 2u);   // (a block size that is no multiple of 64 ends in a partial tile)
 #pragma unroll
-    for (uint32_t k = 0; k < 2 * TILE / 32; ++k) dst[k * 32 + lane] = src[k * 32 + lane];
+    for (uint32_t k = 0; k < 2 * TILE / 32; ++k) if (k * 32 + lane < live) dst[k * 32 + lane] = src[k * 32 + lane];
   }
 }
 

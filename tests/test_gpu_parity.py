@@ -319,3 +319,24 @@ def test_pool_trim_gives_memory_back_and_rendering_goes_on(cuda_api):
         assert freed > 0, "a closed renderer leaves its blocks in the pool"
         assert int(cuda_api.trim_pool(-1)) == 0
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("block_frames", [999, 500, 64])
+@pytest.mark.parametrize("name", ["single_submixer_gated", "sampler_notes", "many_groups", "gran_cloud", "gran_sequential_loop", "hq_events", "fx_reverb"])
+def test_other_block_sizes_are_bit_exact(cuda_api, oracle_api, name, block_frames):
+    """WavStream block sizes other than 1024 (odd ones too: the 16-byte staging paths must fall back): bit-exact scenes stay
+    bit-exact. The block size changes the reference's chunking, so both sides render with the same one."""
+    from scenes import SCENES, SR
+    outs = []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, SR, block_frames=block_frames)
+        info = SCENES[name](p)
+        frames = (min(info["frames"], 2 * SR) // block_frames) * block_frames
+        outs.append(p.render(frames))
+        p.close()
+    assert float(np.abs(outs[1]).max()) > 1e-3
+    if name.startswith("hq_") or name.startswith("fx_"):   # tolerance classes (sinc FIR order; feedback effect floor)
+        assert float(np.abs(outs[0] - outs[1]).max()) <= 1e-5
+        return
+    bad = np.flatnonzero((outs[0] != outs[1]).any(axis=1))
+    assert bad.size == 0, f"first differing frame {bad[0]} (+{bad.size - 1} more) of {len(outs[1])}, max err {np.abs(outs[0] - outs[1]).max():.3e}"
