@@ -340,3 +340,18 @@ def test_other_block_sizes_are_bit_exact(cuda_api, oracle_api, name, block_frame
         return
     bad = np.flatnonzero((outs[0] != outs[1]).any(axis=1))
     assert bad.size == 0, f"first differing frame {bad[0]} (+{bad.size - 1} more) of {len(outs[1])}, max err {np.abs(outs[0] - outs[1]).max():.3e}"
+
+
+def test_dense_event_schedule_beyond_the_cached_chunk_tables(cuda_api, oracle_api):
+    """2048 voices on ONE mixer with all their events inside 1.5 s: more than 1024 chunks per time block, so the mixer
+    kernel's shared-memory chunk tables do not apply (mixer_kernel.cuh AUD_MAX) and it reads the schedule from global memory."""
+    from phonic_b200 import workloads as W
+    frames = W.frames_for(2, 48000)
+    outs = []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, 48000)
+        W.build_cfg2(p, W.VoiceBankSpec(voices=2048), time_scale=0.15, fast=True)
+        outs.append(p.render(frames))
+        p.close()
+    assert float(np.abs(outs[1]).max()) > 1e-2
+    assert float(np.abs(outs[0] - outs[1]).max()) <= 2.5e-7
