@@ -168,3 +168,27 @@ def test_main_input_serves_one_render_call(oracle_api):
     with pytest.raises(Exception):
         p.set_main_input(bus.ctypes.data, 1000)  # not a multiple of the block
     p.close()
+
+
+def test_load_aware_partition_of_cfg5():
+    """Rank 0 carries the main-bus chain as a preload: with enough ranks it ends up holding the main bus only."""
+    import bench
+    from phonic_b200.distributed import assign_subtrees
+    assert bench.cfg5_submixers(1) == [64]
+    for world in (2, 4, 8):
+        per = bench.cfg5_submixers(world)
+        assert sum(per) == 64 * world and len(per) == world
+        assert per[0] <= min(per[1:]), per                  # rank 0 never holds more sub-mixers than anybody else
+        assert max(per[1:]) - min(per[1:]) <= 1, per        # the others are balanced
+    assert bench.cfg5_submixers(8)[0] == 0
+    # the preload is only a starting load: the packing itself stays the reference's heuristic
+    assert assign_subtrees([4, 4, 4, 4], 2, preload=[8, 0]) == [[2], [0, 1, 3]]   # (a tie goes to the first bin, like min_by_key)
+    assert assign_subtrees([4, 4, 4, 4], 2, preload=[0, 0]) == assign_subtrees([4, 4, 4, 4], 2)
+
+
+def test_piece_bounds():
+    from phonic_b200.distributed import piece_bounds
+    assert piece_bounds(5 * 1024, 2 * 1024) == [(0, 2048), (2048, 2048), (4096, 1024)]
+    assert piece_bounds(1024, 65536) == [(0, 1024)]
+    with pytest.raises(AssertionError):
+        piece_bounds(1000, 1024)
