@@ -355,3 +355,42 @@ def test_dense_event_schedule_beyond_the_cached_chunk_tables(cuda_api, oracle_ap
         p.close()
     assert float(np.abs(outs[1]).max()) > 1e-2
     assert float(np.abs(outs[0] - outs[1]).max()) <= 2.5e-7
+
+
+@pytest.mark.parametrize("voices_per_sampler", [24, 48, 300])
+def test_big_samplers_take_the_other_skeleton_mappings(cuda_api, oracle_api, voices_per_sampler):
+    """Samplers with more than 8 voices: warp-per-voice CTAs of up to 32 warps (24), the lane-per-voice mapping with more than
+    one warp per group (48 with many samplers resident, 300 = a 320-thread group CTA). Voice allocation / stealing across
+    warps, bit-exact voice path + the bus filter's bar."""
+    from phonic_b200 import workloads as W
+    n_samplers = 3 if voices_per_sampler >= 300 else 40
+    spec = W.VoiceBankSpec(voices=voices_per_sampler * n_samplers, voices_per_sampler=voices_per_sampler)
+    frames = W.frames_for(2, 48000)
+    outs, states = [], []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, 48000)
+        hs, _fx = W.build_cfg2(p, spec, time_scale=0.15)
+        outs.append(p.render(frames))
+        states.append([h.voice_states() for h in hs])
+        p.close()
+    assert float(np.abs(outs[1]).max()) > 1e-2
+    assert float(np.abs(outs[0] - outs[1]).max()) <= 2.5e-7
+    assert states[0] == states[1]
+
+
+@pytest.mark.parametrize("rate", [22050, 96000])
+@pytest.mark.parametrize("name", ["sampler_notes", "file_events", "fx_filter", "gran_cloud"])
+def test_other_output_rates(cuda_api, oracle_api, name, rate):
+    """Output rates other than 44.1 / 48 kHz (rate_comp of the smoothers, resampling ratios below 1/2 and above 2)."""
+    from scenes import SCENES, BIT_EXACT
+    outs = []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, rate)
+        info = SCENES[name](p)
+        outs.append(p.render((min(info["frames"], 96 * 1024) // 1024) * 1024))
+        p.close()
+    assert float(np.abs(outs[1]).max()) > 1e-3
+    if name in BIT_EXACT:
+        assert np.array_equal(outs[0], outs[1])
+    else:
+        assert float(np.abs(outs[0] - outs[1]).max()) <= 1e-5
