@@ -192,3 +192,30 @@ def test_piece_bounds():
     assert piece_bounds(1024, 65536) == [(0, 1024)]
     with pytest.raises(AssertionError):
         piece_bounds(1000, 1024)
+
+
+def test_consecutive_sharded_renders_continue_the_stream(oracle_api):
+    """Two render_sharded calls on the same shard renderer and main stage == one render of twice the length."""
+    import torch
+    from phonic_b200.distributed import MainBusStage, render_sharded
+    from phonic_b200.player import DelayEffect, Player
+
+    def chain(q):
+        q.add_effect(DelayEffect())
+    half = FRAMES // 2
+    p = Player(oracle_api, 48000)
+    build(p, [0, 1])
+    stage = MainBusStage(oracle_api, 48000, chain)
+    got = []
+    for _ in range(2):
+        bus, out = torch.zeros(half, 2), torch.zeros(half, 2)
+        render_sharded(p, bus, 4 * 1024, stage, out)
+        got.append(out.numpy().copy())
+    p.close()
+    stage.close()
+    p = Player(oracle_api, 48000)
+    build(p, [0, 1])
+    chain(p)
+    full = p.render(FRAMES)
+    p.close()
+    assert np.array_equal(np.concatenate(got), full)

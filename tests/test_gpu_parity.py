@@ -394,3 +394,27 @@ def test_other_output_rates(cuda_api, oracle_api, name, rate):
         assert np.array_equal(outs[0], outs[1])
     else:
         assert float(np.abs(outs[0] - outs[1]).max()) <= 1e-5
+
+
+def test_direct_child_toggles_between_render_calls(cuda_api, oracle_api):
+    """One sub-mixer under an effect-less main mixer (its kernel writes the output itself), then a second sub-mixer is added
+    (the main level is rendered again), then removed: the mixers' states carry over every switch."""
+    from scenes import tone
+    from phonic_b200.player import FilePlaybackOptions, FilterEffect
+    outs = []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, 48000)
+        b = p.upload_buffer(tone(30000, 44100, seed=31), 44100)
+        m1 = p.add_mixer(None)
+        p.add_effect(FilterEffect(0, 1800.0, 0.707), m1.id)
+        p.play_file_source(b, FilePlaybackOptions(volume=0.5, target_mixer=m1.id, repeat=3))
+        parts = [p.render(10 * 1024)]
+        m2 = p.add_mixer(None)
+        p.play_file_source(b, FilePlaybackOptions(volume=0.3, panning=0.4, target_mixer=m2.id, repeat=1))
+        parts.append(p.render(10 * 1024))
+        p.remove_mixer(m2.id)
+        parts.append(p.render(10 * 1024))
+        outs.append(np.concatenate(parts))
+        p.close()
+    assert float(np.abs(outs[1][25 * 1024:]).max()) > 1e-3
+    assert float(np.abs(outs[0] - outs[1]).max()) <= 1e-5
