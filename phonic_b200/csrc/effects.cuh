@@ -148,6 +148,11 @@ PB_DEV float lfo_run(LfoSt& l) {
   return v;
 }
 
+// exp of an f32 as the host libm gives it (glibc's expf is correctly rounded to within 0.502 ulp): the f64 exp rounded to f32.
+// Used where a coefficient is re-derived on the device after a parameter event -- a one-pole release coefficient
+// exp(-1 / (2 s x 48 kHz)) = 1 - 1.04e-5 has only ~7 significant bits in its distance from 1, so a last-bit difference
+// of the device's expf shows up as 5e-4 in a compressor's output (the same coefficients come from the host at construction).
+PB_DEV float expf_host_rounding(const float x) { return (float)exp((double)x); }
 PB_DEV float db_to_linear_dev(float value) {  // src/utils.rs:41-51
   const float DB_TO_LIN_FACTOR = 2.302585092994046f / 20.0f;
   if (isnan(value)) return value;
@@ -1062,10 +1067,10 @@ PB_DEV void fx_apply_param(FxHeader& h, const FxCtx& cx, const FxParamEvent& e) 
       else if (id == CC4('r', 'e', 'l', 's')) s.release_time = v;
       else if (id == CC4('r', 'n', 'g', 'e')) s.range = v;
       const float srf = (float)cx.sample_rate;  // update_coefficients (gate.rs:83-95)
-      s.env_atk = s.attack_time > 0.0f ? expf(-1.0f / (s.attack_time * srf)) : 0.0f;
-      s.env_rel = s.release_time > 0.0f ? expf(-1.0f / (s.release_time * srf)) : 0.0f;
-      s.attack_coeff = expf(-1.0f / (s.attack_time * srf));
-      s.release_coeff = expf(-1.0f / (s.release_time * srf));
+      s.env_atk = s.attack_time > 0.0f ? expf_host_rounding(-1.0f / (s.attack_time * srf)) : 0.0f;
+      s.env_rel = s.release_time > 0.0f ? expf_host_rounding(-1.0f / (s.release_time * srf)) : 0.0f;
+      s.attack_coeff = expf_host_rounding(-1.0f / (s.attack_time * srf));
+      s.release_coeff = expf_host_rounding(-1.0f / (s.release_time * srf));
       break;
     }
     case FX_DISTORTION: {
@@ -1115,8 +1120,8 @@ PB_DEV void fx_apply_param(FxHeader& h, const FxCtx& cx, const FxParamEvent& e) 
       else if (id == CC4('r', 'e', 'l', 's')) s.release_time = v;
       else if (id == CC4('g', 'a', 'i', 'n')) exp_set_target(s.makeup, v, cx.comp);
       else if (id == CC4('l', 'o', 'o', 'k')) s.lookahead_time = v;
-      s.atk_coeff = s.attack_time > 0.0f ? expf(-1.0f / (s.attack_time * (float)cx.sample_rate)) : 0.0f;
-      s.rel_coeff = s.release_time > 0.0f ? expf(-1.0f / (s.release_time * (float)cx.sample_rate)) : 0.0f;
+      s.atk_coeff = s.attack_time > 0.0f ? expf_host_rounding(-1.0f / (s.attack_time * (float)cx.sample_rate)) : 0.0f;
+      s.rel_coeff = s.release_time > 0.0f ? expf_host_rounding(-1.0f / (s.release_time * (float)cx.sample_rate)) : 0.0f;
       if (s.lookahead_time != old_look) {  // LookupDelayLine::new (delay.rs:182-203)
         uint32_t df = (uint32_t)f32_ceil_u64(s.lookahead_time * (float)cx.sample_rate);
         uint32_t n = 1; while (n < df) n <<= 1;

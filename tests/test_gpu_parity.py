@@ -418,3 +418,50 @@ def test_direct_child_toggles_between_render_calls(cuda_api, oracle_api):
         p.close()
     assert float(np.abs(outs[1][25 * 1024:]).max()) > 1e-3
     assert float(np.abs(outs[0] - outs[1]).max()) <= 1e-5
+
+
+@pytest.mark.parametrize("last", ["chorus", "reverb"])
+def test_pipelined_chain_with_events_and_silence(cuda_api, oracle_api, last):
+    """Four effects on one mixer = four pipeline stages (mixer_kernel.cuh): parameter events for effects of every stage at
+    odd times (the Compressor's threshold event re-derives its one-pole coefficients on the device: effects.cuh
+    expf_host_rounding), a > 2 s gap in the input (the bypass verdicts travel with the chunks), and on the Reverb variant a
+    reset message on the last stage."""
+    from scenes import tone
+    from phonic_b200.player import ChorusEffect, CompressorEffect, Eq5Effect, FilePlaybackOptions, FilterEffect, ReverbEffect
+    SRX = 48000
+    outs = []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, SRX)
+        b = p.upload_buffer(tone(20000, 44100, seed=41), 44100)
+        f = p.add_effect(FilterEffect(0, 3000.0, 0.707))
+        e = p.add_effect(Eq5Effect())
+        c = p.add_effect(CompressorEffect())
+        r = p.add_effect(ChorusEffect() if last == "chorus" else ReverbEffect(0.5, 0.3))
+        e.set_parameter("gan2", 5.0, 0)
+        f.set_parameter("cuto", 900.0, 7001)
+        e.set_parameter("gan4", -4.0, 15555)
+        c.set_parameter("thrs", -24.0, 23456)
+        f.set_parameter("cuto", 4000.0, int(3.1 * SRX) + 13)
+        if last == "chorus":
+            r.set_parameter("rate", 1.5, int(3.4 * SRX) + 5)
+        else:
+            r.send_message(A_MSG_REVERB_RESET, int(3.4 * SRX) + 5)
+        p.play_file_source(b, FilePlaybackOptions(volume=0.6))
+        p.play_file_source(b, FilePlaybackOptions(volume=0.6), start_time=int(3.0 * SRX) + 321)
+        outs.append(p.render(W_frames(4, SRX)))
+        p.close()
+    d = outs[0] - outs[1]
+    assert float(np.abs(outs[1]).max()) > 1e-2
+    rms = float(np.sqrt(np.mean(d ** 2)))
+    if last == "chorus":
+        assert float(np.abs(d).max()) <= 1e-5, f"max {np.abs(d).max():.2e}"
+    else:
+        assert dbfs(rms) < -90.0 and dbfs(np.abs(d).max()) < -80.0, f"rms {dbfs(rms):.1f} dBFS, max {np.abs(d).max():.2e}"
+
+
+from phonic_b200._capi import MSG_REVERB_RESET as A_MSG_REVERB_RESET  # noqa: E402
+
+
+def W_frames(seconds, sr):
+    from phonic_b200 import workloads as W
+    return W.frames_for(seconds, sr)
