@@ -465,3 +465,41 @@ from phonic_b200._capi import MSG_REVERB_RESET as A_MSG_REVERB_RESET  # noqa: E4
 def W_frames(seconds, sr):
     from phonic_b200 import workloads as W
     return W.frames_for(seconds, sr)
+
+
+def _param_cases():
+    from phonic_b200 import player as P
+    cases = {
+        "filter": (lambda: P.FilterEffect(0, 3000.0, 0.707), [("cuto", 800.0), ("fltq", 2.0)]),
+        "eq5": (lambda: P.Eq5Effect(), [("gan1", 4.0), ("frq3", 2000.0), ("bw_2", 2.5)]),
+        "compressor": (lambda: P.CompressorEffect(), [("thrs", -24.0), ("rato", 4.0), ("knee", 6.0), ("attk", 0.05), ("rels", 0.5), ("gain", 3.0), ("look", 0.02)]),
+        "limiter": (lambda: P.CompressorEffect.new_limiter(), [("thrs", -6.0), ("rels", 0.3), ("look", 0.01)]),
+        "chorus": (lambda: P.ChorusEffect(), [("rate", 2.0), ("phas", 1.0), ("dpth", 0.5), ("fdbk", -0.4), ("dlay", 20.0), ("wet_", 0.7), ("fltf", 4000.0), ("fltq", 0.5)]),
+        "delay": (lambda: P.DelayEffect(), [("dlay", 200.0), ("fdbk", 0.3), ("cuto", 3000.0), ("driv", 0.5), ("wet_", 0.8), ("wdth", 0.9), ("lfor", 2.0), ("lfdt", 0.3), ("ldfb", 0.2), ("lfdf", -0.3)]),
+        "reverb": (lambda: P.ReverbEffect(0.6, 0.35), [("room", 0.8), ("wet ", 0.6)]),
+        "gate": (lambda: P.GateEffect(), [("thrs", -20.0), ("attk", 0.01), ("hold", 0.05), ("rels", 0.5), ("rnge", -30.0)]),
+        "gain": (lambda: P.GainEffect(), [("gain", 0.5)]),
+        "pan": (lambda: P.PanningEffect(), [("pan ", -0.4), ("wdth", 1.5)]),
+        "distortion": (lambda: P.DistortionEffect(), [("driv", 2.0), ("mix ", 0.5)]),
+    }
+    return [(name, make, pid, val) for name, (make, params) in cases.items() for (pid, val) in params]
+
+
+@pytest.mark.parametrize("name,make,pid,val", _param_cases(), ids=lambda x: x.strip() if isinstance(x, str) else None)
+def test_every_effect_parameter_event(cuda_api, oracle_api, name, make, pid, val):
+    """One event per automatable parameter of every built-in effect, mid-render (Effect::process_parameter_update of
+    src/effect/*.rs: smoothed parameters ramp, plain ones re-derive coefficients on the device)."""
+    from scenes import tone
+    from phonic_b200 import player as P
+    outs = []
+    for api in (cuda_api, oracle_api):
+        p = Player(api, 48000)
+        b = p.upload_buffer(tone(30000, 44100, seed=51), 44100)
+        fx = p.add_effect(make())
+        fx.set_parameter(pid, val, 20011)
+        p.play_file_source(b, P.FilePlaybackOptions(volume=0.6, repeat=3))
+        outs.append(p.render(96 * 1024))
+        p.close()
+    d = outs[0] - outs[1]
+    assert float(np.abs(outs[1]).max()) > 1e-2
+    assert float(np.abs(d).max()) <= 1e-5, f"{name} {pid}: max {np.abs(d).max():.2e}"
