@@ -100,6 +100,9 @@ __global__ void __launch_bounds__(256) mix_sum_kernel(MixerKernelArgs a) {
 
 // ---- M2 -------------------------------------------------------------------------------------------------
 constexpr uint32_t FX_THREADS = FX_THREADS_C;
+// frames after a parameter event during which a smoothed effect parameter may still be ramping (the default exponential
+// smoother needs 278 x ln(delta / 3.3e-3) frames at 48 kHz: 4400 for a 20 kHz cutoff jump; 65536 covers every built-in smoother)
+constexpr uint64_t FX_RAMP_WINDOW = 65536;
 constexpr uint32_t MAX_FX_STAGES = 4;    // pipeline stages of a mixer's effect chain (one CTA each)
 constexpr uint32_t FX_WORK_SMALL = 48 * 1024;   // every effect but the whole-chunk reverb fits: keeps the L1 carve-out and 3 CTAs per SM
 constexpr uint32_t FX_WORK_BYTES = 120 * 1024;  // shared-memory work area of the chunk-parallel effects (the reverb's ten f64 planes of a whole chunk)
@@ -321,21 +324,26 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
       // to the next 1024-frame block boundary / parent chunk boundary / effect event -- most chunk boundaries of a busy
       // mixer come from its SOURCES' events (mixed.rs:686-693) and mean nothing to the effects.
       if (audible) {
-        while (k + 2 < ce) {
+        // An event of ANY effect of the mixer in (c0, nb] ends the merge, and so does a parameter event in the recent past:
+        // a smoothed parameter decides per process() call -- per chunk -- whether it still ramps (chorus.rs / filter.rs /
+        // eq5.rs ...: `if need_ramp { per-sample } else { constant }`), so while a ramp set off by an event may still be
+        // running the chunks are the reference's. Both are judged on the event times alone (the cursors and the smoothers
+        // belong to the effects' own stages), so that every stage of a pipeline cuts the same chunks.
+        uint64_t next_ev = UINT64_MAX;
+        bool can_merge = true;
+        for (uint32_t e = mp.fx_begin; e < mp.fx_end && any_fx_events; ++e) {
+          const FxHeader& h = a.fx[e];
+          uint32_t lo2 = h.ev_begin, hi2 = h.ev_end;   // first event with time > c0
+          while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (a.fx_events[mid].time <= c0) lo2 = mid + 1; else hi2 = mid; }
+          if (lo2 < h.ev_end) next_ev = min(next_ev, (uint64_t)a.fx_events[lo2].time);
+          if (lo2 > h.ev_begin && c0 - a.fx_events[lo2 - 1].time < FX_RAMP_WINDOW) can_merge = false;
+        }
+        while (can_merge && k + 2 < ce) {
           const uint64_t nb = bound_at(k + 1);   // start of the next chunk
           if ((uint32_t)(nb - a.block_start) % wbf == 0) break;
           if (!is_main && nb == parent_next) break;
           if (!((k + 1 - cb < AUD_MAX) ? s_aud[k + 1 - cb] != 0 : audible_of(k + 1))) break;
-          // an event of ANY effect of the mixer in (c0, nb] ends the merge. Judged on the event times alone (the
-          // cursors belong to the effects' own stages), so that every stage of a pipeline cuts the same chunks.
-          bool ev_due = false;
-          for (uint32_t e = mp.fx_begin; e < mp.fx_end && any_fx_events; ++e) {
-            const FxHeader& h = a.fx[e];
-            uint32_t lo2 = h.ev_begin, hi2 = h.ev_end;   // first event with time > c0
-            while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (a.fx_events[mid].time <= c0) lo2 = mid + 1; else hi2 = mid; }
-            ev_due |= lo2 < h.ev_end && a.fx_events[lo2].time <= nb;
-          }
-          if (ev_due) break;
+          if (next_ev <= nb) break;
           ++k;
           c1 = bound_at(k + 1);
         }

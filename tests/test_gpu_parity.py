@@ -505,12 +505,13 @@ def test_every_effect_parameter_event(cuda_api, oracle_api, name, make, pid, val
     assert float(np.abs(d).max()) <= 1e-5, f"{name} {pid}: max {np.abs(d).max():.2e}"
 
 
-@pytest.mark.parametrize("seed", list(range(0, 28)) + list(range(29, 40)))
+@pytest.mark.parametrize("seed", [s for s in range(0, 100) if s != 28] + [163])
 def test_random_graphs(cuda_api, oracle_api, seed):
     """tools/fuzz_scenes.py: random mixer trees, effect chains, file sources and samplers, events of every kind, structural
     changes between two render calls. (Seed 28 is left out: the oracle's second Compressor envelope equals threshold + knee / 2
     EXACTLY for one sample there, where compressor.rs:262-275's strict inequalities give no gain reduction -- a 1.3 dB blip
-    of one sample that the device, one ulp of log10f away, does not hit: tools/vol_repro.py.)"""
+    of one sample that the device, one ulp of log10f away, does not hit: tools/vol_repro.py; seed 186 is of the same kind.
+    Seed 163 is the one that caught the merged-chunk fault: a Chorus rate ramp still running across a merged chunk boundary.)"""
     import importlib.util
     spec = importlib.util.spec_from_file_location("fuzz_scenes", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_scenes.py"))
     F = importlib.util.module_from_spec(spec)
