@@ -44,7 +44,7 @@ struct MixerKernelArgs {
   // Effect-chain pipelining (n_stages > 1): CTA (mixer, stage) runs the effects [stage_begin[stage], stage_begin[stage+1]) of
   // its mixer; chunk q moves from stage to stage through the mixer bus in global memory, announced by fx_progress.
   uint32_t n_stages;              // gridDim.y of the launch; 1 = one CTA per mixer runs the whole chain
-  const uint32_t* stage_begin;    // [n_mixers][n_stages + 1] effect indices relative to fx_begin (by dense mixer index)
+  const uint32_t* stage_begin;    // [n_mixers][MAX_FX_STAGES + 1] effect indices relative to fx_begin (by dense mixer index)
   uint32_t* fx_progress;          // [n_mixers][n_stages] chunks of this block finished by the stage (zeroed per block)
   uint8_t* fx_pflags;             // [n_mixers][n_stages][max_chunks] bit0 input still bypassed, bit1 some effect ran
   uint32_t* fx_ticket;            // CTA start counter of the launch (zeroed per launch)
@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(FX_THREADS, MINB) mix_fx_kernel(MixerKernelArg
   // the effects this CTA runs, and its place in the mixer's pipeline
   uint32_t e_lo = mp.fx_begin, e_hi = mp.fx_end;
   if (n_stages > 1) {
-    const uint32_t* sb = a.stage_begin + (size_t)m * (n_stages + 1);
+    const uint32_t* sb = a.stage_begin + (size_t)m * (MAX_FX_STAGES + 1);
     e_lo = mp.fx_begin + sb[stage]; e_hi = mp.fx_begin + sb[stage + 1];
     if (stage > 0 && e_lo >= e_hi) return;   // (a mixer with fewer effects than stages; stage 0 always runs: gate / master)
   }
   const bool first_stage = e_lo == mp.fx_begin, last_stage = e_hi == mp.fx_end;
   uint32_t prev_stage = stage;               // the stage whose output this one consumes
-  if (!first_stage) { const uint32_t* sb = a.stage_begin + (size_t)m * (n_stages + 1); do { --prev_stage; } while (sb[prev_stage] == sb[prev_stage + 1]); }
+  if (!first_stage) { const uint32_t* sb = a.stage_begin + (size_t)m * (MAX_FX_STAGES + 1); do { --prev_stage; } while (sb[prev_stage] == sb[prev_stage + 1]); }
   volatile uint32_t* prog_in = a.fx_progress ? a.fx_progress + (size_t)m * n_stages + prev_stage : nullptr;
   uint32_t* prog_out = a.fx_progress ? a.fx_progress + (size_t)m * n_stages + stage : nullptr;
   const uint8_t* pf_in = a.fx_pflags ? a.fx_pflags + ((size_t)m * n_stages + prev_stage) * a.max_chunks : nullptr;

@@ -604,6 +604,7 @@ int make_granular_buffer(pb200_renderer* r, uint32_t buffer_id, uint32_t* out_in
   if (cudaSetDevice(r->device) != cudaSuccess) return fail(r, PB200_ERR_CUDA, "granular sample buffer: cudaSetDevice failed");
   pb200_config cfg = r->cfg;
   cfg.master_volume = 1.0f;
+  cfg.block_frames = 1024;          // (the resampling render below is sized in 1024-frame blocks whatever the caller's block size is)
   cfg.device_ordinal = r->device;   // (the borrowed sample pointer and the pool blocks below belong to THIS renderer's device)
   pb200_renderer* t = nullptr;
   if (int e = pb200_create(&cfg, &t)) return fail(r, e, "granular sample buffer: could not create the resampling renderer");
@@ -1868,7 +1869,7 @@ int render_impl(pb200_renderer* r, float* out_dev, float* out_host, uint64_t fra
                 const double v = std::max(best[k - 1][i], pre[j] - pre[i]);
                 if (v < best[k][j]) { best[k][j] = v; cut[k][j] = i; }
               }
-          uint32_t* sb = stage_begin.data() + (size_t)mi * (S + 1);
+          uint32_t* sb = stage_begin.data() + (size_t)mi * (MAX_FX_STAGES + 1);   // (one fixed-stride row per mixer: levels differ in S)
           for (uint32_t k = P; k <= S; ++k) sb[k] = (uint32_t)E;
           size_t j = E;
           for (uint32_t k = P; k >= 1; --k) { sb[k] = (uint32_t)j; j = cut[k][j]; }

@@ -3,6 +3,7 @@ Voice path + plain biquad: bit-exact. Effects that call device libm (tan/pow/sin
 <= 1e-5 max abs error; feedback effects (delay, reverb): error floor below -90 dBFS."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -519,3 +520,22 @@ def test_random_graphs(cuda_api, oracle_api, seed):
     x, y = F.build_and_render(cuda_api, seed), F.build_and_render(oracle_api, seed)
     assert float(np.abs(y).max()) > 1e-3
     assert float(np.abs(x - y).max()) <= 1e-5
+
+
+@pytest.mark.parametrize("seed", list(range(0, 80)) + [115, 124, 125])
+def test_random_graphs_wide(cuda_api, oracle_api, seed):
+    """tools/fuzz_scenes2.py: other block sizes, three render calls, HighQuality sources, granular samplers, sampler parameter
+    automation, loop ranges, up to three effects per mixer incl. Delay / Reverb (error floor), move_effect. Seeds 115 / 124 /
+    125 are the ones that caught the pipeline's stage table being indexed with a per-level stride (mixers of two tree levels
+    with different stage counts overwrote each other's rows: wrong effects per stage, NaNs, an illegal access)."""
+    import importlib.util
+    tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    sys.path.insert(0, tools)
+    spec = importlib.util.spec_from_file_location("fuzz_scenes2", os.path.join(tools, "fuzz_scenes2.py"))
+    F = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(F)
+    x, fb = F.build_and_render(cuda_api, seed)
+    y, _ = F.build_and_render(oracle_api, seed)
+    ok, mx = F.verdict(x, y, fb)
+    assert np.isfinite(x).all()
+    assert ok, f"max {mx:.2e} ({'feedback effects: floor' if fb else 'bar 1e-5'})"
